@@ -437,17 +437,24 @@ def argmax_first(scores: torch.Tensor, dim: int = 0) -> torch.Tensor:
 # --------------------------------------------------------------------------------------
 
 
-def candidate_scale(i: int, k: int, n: int, lambda_scaled: float) -> float:
-    """edm/main.py:776-779: hash(f"{i}_{k}_{n}") % 1000 / 1000 * lambda (salted str hash:
-    reproducible only under a fixed PYTHONHASHSEED)."""
-    return hash(f"{i}_{k}_{n}") % 1000 / 1000.0 * lambda_scaled
+def candidate_scale_seed(i: int, k: int, n: int) -> float:
+    """edm/main.py:776: hash(f"{i}_{k}_{n}") % 1000 / 1000 (salted str hash: reproducible
+    only under a fixed PYTHONHASHSEED)."""
+    return hash(f"{i}_{k}_{n}") % 1000 / 1000.0
+
+
+def candidate_scale_fp32(scale_seed: float, lambda_scaled: float) -> torch.Tensor:
+    """edm/main.py:779: `torch.ones(shape) * scale_seed * lambda_param` -- an fp32 tensor
+    rounded after EACH of the two multiplications (lambda_param is a numpy float64 scalar)."""
+    return torch.ones([]) * scale_seed * lambda_scaled
 
 
 def make_candidates(pivot: torch.Tensor, directions: Sequence[Optional[torch.Tensor]],
-                    scales: Sequence[float], fresh: Sequence[Optional[torch.Tensor]]) -> torch.Tensor:
+                    scales: Sequence[torch.Tensor], fresh: Sequence[Optional[torch.Tensor]]) -> torch.Tensor:
     """N candidates around `pivot` [b,C,H,W] (edm/main.py:749-800).
-    directions[n] (un-normalised) is used when fresh[n] is None; the scale is an fp32
-    tensor ([b,1,1,1] ones * scale, :779) multiplying the unit direction."""
+    directions[n] (un-normalised) is used when fresh[n] is None; scales[n] is the 0-d fp32
+    tensor of candidate_scale_fp32 (broadcast like the reference's [b,1,1,1] tensor, :779)
+    multiplying the fp64 unit direction."""
     out = []
     for n in range(len(scales)):
         if fresh[n] is not None:
@@ -455,8 +462,7 @@ def make_candidates(pivot: torch.Tensor, directions: Sequence[Optional[torch.Ten
             continue
         d = directions[n]
         d = d / torch.norm(d, p=2, dim=tuple(range(1, d.dim())), keepdim=True)
-        s = torch.ones([d.shape[0]] + [1] * (d.dim() - 1)) * scales[n]
-        out.append(pivot + s * d)
+        out.append(pivot + scales[n] * d)
     return torch.cat(out, dim=0)
 
 
@@ -508,11 +514,12 @@ def eps_greedy_search(net, latents, class_labels, scorer: Callable, *, N, K, lam
                 if bernoulli(i, k, n):
                     dirs.append(noise[i][:, k, n].reshape(pivot.shape))
                     fresh.append(None)
-                    scales.append(scale_fn(i, k, n) * lam if scale_fn else candidate_scale(i, k, n, lam))
+                    seed_ikn = scale_fn(i, k, n) if scale_fn else candidate_scale_seed(i, k, n)
+                    scales.append(candidate_scale_fp32(seed_ikn, lam))
                 else:
                     dirs.append(None)
                     fresh.append(noise[f'fresh_{i}_{k}_{n}'])
-                    scales.append(0.0)
+                    scales.append(None)
             cands = make_candidates(pivot, dirs, scales, fresh)                   # [N*b,...]
             labels_exp = class_labels.repeat(N, 1) if class_labels is not None else None
             _, x0 = heun_step(net, x_cur.repeat(N, 1, 1, 1), t_cur, t_next, i, cands, labels_exp, **kw)

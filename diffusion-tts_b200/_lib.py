@@ -1,0 +1,119 @@
+"""ctypes binding of libb200ns.so (C ABI declared in include/b200_noise_search.h).
+
+The library is built in-tree by `build.py` (nvcc, sm_100a).  There is NO fallback: if the
+shared object is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libb200ns.so')
+
+c_i32, c_i64, c_f32, c_f64, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_void_p
+
+
+class KSeg(C.Structure):
+    _fields_ = [('src', c_i32), ('taps', c_i32), ('cstart', c_i32), ('cblocks', c_i32)]
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [('a_ptr', c_vp * 2), ('a_channels', c_i32 * 2), ('n_seg', c_i32), ('seg', KSeg * 4),
+                ('batch', c_i32), ('H', c_i32), ('W', c_i32), ('w_ptr', c_vp), ('N', c_i32), ('Npad', c_i32),
+                ('Ktot', c_i32), ('bias', c_vp), ('residual', c_vp), ('ld_res', c_i32), ('out_scale', c_f32),
+                ('out', c_vp), ('ld_out', c_i32), ('out_fp32', c_i32), ('vt_out', c_vp), ('vt_col_start', c_i32),
+                ('heads', c_i32)]
+
+
+class GnStatsDesc(C.Structure):
+    _fields_ = [('x_ptr', c_vp * 2), ('x_channels', c_i32 * 2), ('batch', c_i32), ('HW', c_i32), ('groups', c_i32),
+                ('pre_add', c_vp), ('ld_pre_add', c_i32), ('b_emb', c_i32), ('partial', c_vp), ('splits', c_i32)]
+
+
+class GnApplyDesc(C.Structure):
+    _fields_ = [('x_ptr', c_vp * 2), ('x_channels', c_i32 * 2), ('batch', c_i32), ('H', c_i32), ('W', c_i32),
+                ('groups', c_i32), ('partial', c_vp), ('splits', c_i32), ('eps', c_f32), ('gamma', c_vp),
+                ('beta', c_vp), ('pre_add', c_vp), ('ld_pre_add', c_i32), ('film_scale', c_vp), ('film_shift', c_vp),
+                ('ld_film', c_i32), ('b_emb', c_i32), ('silu', c_i32), ('resample', c_i32), ('out', c_vp),
+                ('raw_out', c_vp)]
+
+
+class AttnDesc(C.Structure):
+    _fields_ = [('qk', c_vp), ('ld_qk', c_i32), ('k_col0', c_i32), ('vt', c_vp), ('out', c_vp), ('ld_out', c_i32),
+                ('batch', c_i32), ('heads', c_i32), ('L', c_i32)]
+
+
+class LinearDesc(C.Structure):
+    _fields_ = [('x', c_vp), ('rows', c_i32), ('K', c_i32), ('ld_x', c_i32), ('w', c_vp), ('bias', c_vp),
+                ('add', c_vp), ('ld_add', c_i32), ('N', c_i32), ('act', c_i32), ('out', c_vp), ('ld_out', c_i32)]
+
+
+class Im2colDesc(C.Structure):
+    _fields_ = [('x', c_vp), ('out', c_vp), ('batch', c_i32), ('C', c_i32), ('H', c_i32), ('W', c_i32)]
+
+
+# name -> (restype, argtypes); mirrors include/b200_noise_search.h one to one
+SIGNATURES = {
+    'b200ns_last_error': (C.c_char_p, []),
+    'b200ns_device_ok': (C.c_int, [C.c_int]),
+    'b200ns_heun_pre': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f64, c_f32, c_vp]),
+    'b200ns_heun_mid': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_f32, c_f32, c_f64, c_f64, c_f32, c_vp]),
+    'b200ns_heun_post': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_f32, c_f32, c_f64, c_f64,
+                                   c_f32, c_f32, c_f64, c_vp]),
+    'b200ns_quantize_u8': (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
+    'b200ns_channel_sums_u8': (C.c_int, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp]),
+    'b200ns_brightness_from_sums': (C.c_int, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp]),
+    'b200ns_argmax_first': (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    'b200ns_gather_rows': (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),
+    'b200ns_direction_norms': (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp]),
+    'b200ns_make_candidates': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),
+    'b200ns_plan_create': (c_vp, []),
+    'b200ns_plan_destroy': (None, [c_vp]),
+    'b200ns_plan_size': (C.c_int, [c_vp]),
+    'b200ns_plan_run': (C.c_int, [c_vp, c_vp]),
+    'b200ns_plan_run_range': (C.c_int, [c_vp, C.c_int, C.c_int, c_vp]),
+    'b200ns_plan_add_gemm': (C.c_int, [c_vp, C.POINTER(GemmDesc)]),
+    'b200ns_plan_add_gn_stats': (C.c_int, [c_vp, C.POINTER(GnStatsDesc)]),
+    'b200ns_plan_add_gn_apply': (C.c_int, [c_vp, C.POINTER(GnApplyDesc)]),
+    'b200ns_plan_add_attention': (C.c_int, [c_vp, C.POINTER(AttnDesc)]),
+    'b200ns_plan_add_linear': (C.c_int, [c_vp, C.POINTER(LinearDesc)]),
+    'b200ns_plan_add_im2col': (C.c_int, [c_vp, C.POINTER(Im2colDesc)]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libb200ns.so (once).  Raises if it has not been built -- there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f'{LIB_PATH} not found: run `python -c "import __graft_entry__ as g; g.build()"` '
+                               '(the CUDA extension is mandatory; there is no CPU fallback)')
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = ''):
+    if rc != 0:
+        msg = lib().b200ns_last_error().decode('utf-8', 'replace')
+        raise RuntimeError(f'libb200ns {what} failed (rc={rc}): {msg}')
+
+
+def ptr(t):
+    """Device pointer of a CUDA tensor (or None)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError('libb200ns takes CUDA tensors only (no CPU fallback)')
+    return t.data_ptr()
+
+
+def cur_stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,35 @@
+"""Build csrc/ into libb200ns.so with nvcc for sm_100a (in-tree, so the .so travels with gpurun)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+OUT = os.path.join(HERE, 'libb200ns.so')
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-shared',
+              '-Xcompiler', '-fPIC']
+
+
+def _newest_src():
+    return max(os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC)
+               if f.endswith(('.cu', '.cuh', '.h'))) if os.path.isdir(CSRC) else 0
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    hdr = os.path.join(os.path.dirname(HERE), 'include', 'b200_noise_search.h')
+    newest = max(_newest_src(), os.path.getmtime(hdr) if os.path.exists(hdr) else 0)
+    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= newest:
+        return OUT
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', OUT, os.path.join(CSRC, 'capi.cu')]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError('nvcc failed building libb200ns.so')
+    if verbose:
+        sys.stderr.write(res.stderr)
+    return OUT
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -1,0 +1,214 @@
+// Self-attention for head_dim 64 on tcgen05 tensor cores (flash-style, fp32 online softmax).
+//
+// One CTA = one (batch*head, 128-query tile).  Per key tile of KT keys:
+//   S = Q K^T      tcgen05.mma, A = Q [128 x 64] smem, B = K [KT x 64] smem, D in TMEM
+//   softmax        each of 128 threads owns one query row: tcgen05.ld -> running max / sum in
+//                  fp32 registers, P written as bf16 into a SWIZZLE_128B smem tile
+//   O_t = P V      tcgen05.mma, A = P [128 x KT], B = V^T [64 x KT] (keys contiguous), D in TMEM
+//   O   = O*alpha + O_t   in registers (64 fp32 per thread)
+// K/V tiles are double buffered through TMA; S(kt+1) is issued before O(kt) is consumed so the
+// tensor pipe overlaps the register epilogue.
+// Replaces AttentionOp.forward + the two einsums of UNetBlock.forward
+// (edm/training/networks.py:113-118, 182-184); softmax is fp32 like the reference.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+struct AttnArgs {
+  __nv_bfloat16* out;
+  int ld_out;
+  int heads, L;
+  int k_col0;
+};
+
+template <int KT>
+struct AttnCfg {
+  static constexpr int Q_BYTES = 128 * 128;
+  static constexpr int K_BYTES = KT * 128;
+  static constexpr int V_BYTES = (KT / 64) * 64 * 128;
+  static constexpr int P_BYTES = (KT / 64) * 128 * 128;
+  static constexpr int SMEM_BYTES = Q_BYTES + 2 * K_BYTES + 2 * V_BYTES + P_BYTES + 1024 + 128;
+};
+
+template <int KT>
+__global__ void __launch_bounds__(128)
+attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const AttnArgs a) {
+  using Cfg = AttnCfg<KT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::Q_BYTES;
+  uint8_t* sV = sK + 2 * Cfg::K_BYTES;
+  uint8_t* sP = sV + 2 * Cfg::V_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+  uint64_t* bar_q = bars;
+  uint64_t* bar_kv = bars + 1;   // [2]
+  uint64_t* bar_s = bars + 3;
+  uint64_t* bar_o = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int bh = blockIdx.y, bi = bh / a.heads, head = bh % a.heads;
+  const int q0 = blockIdx.x * 128;
+  const int row_base = bi * a.L;
+  const int nkt = a.L / KT;
+
+  if (tid == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+    mbar_init(bar_q, 1);
+    mbar_init(&bar_kv[0], 1);
+    mbar_init(&bar_kv[1], 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, KT);
+  constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64);
+
+  auto load_kv = [&](int kt, int st) {
+    mbar_arrive_expect_tx(&bar_kv[st], Cfg::K_BYTES + Cfg::V_BYTES);
+    tma_load_2d(sK + st * Cfg::K_BYTES, &tmK, &bar_kv[st], a.k_col0 + head * 64, row_base + kt * KT);
+#pragma unroll
+    for (int h = 0; h < KT / 64; ++h)
+      tma_load_2d(sV + st * Cfg::V_BYTES + h * 8192, &tmV, &bar_kv[st], kt * KT + h * 64, bh * 64);
+  };
+  auto issue_s = [&](int st) {
+    const uint64_t dq = umma_desc_sw128(smem_u32(sQ));
+    const uint64_t dk = umma_desc_sw128(smem_u32(sK + st * Cfg::K_BYTES));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16(tS, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+    umma_commit(bar_s);
+  };
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_q, Cfg::Q_BYTES);
+    tma_load_2d(sQ, &tmQ, bar_q, head * 64, row_base + q0);
+    load_kv(0, 0);
+    mbar_wait(bar_q, 0);
+    mbar_wait(&bar_kv[0], 0);
+    tc_fence_after();
+    issue_s(0);
+  }
+
+  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+  const float c = 0.125f * 1.4426950408889634f;     // 1/sqrt(64) * log2(e)
+  float m_run = -INFINITY, l_run = 0.f;
+  float o[64];
+#pragma unroll
+  for (int j = 0; j < 64; ++j) o[j] = 0.f;
+  const int r7 = tid & 7;
+
+  for (int kt = 0; kt < nkt; ++kt) {
+    const int st = kt & 1;
+    if (tid == 0 && kt + 1 < nkt) load_kv(kt + 1, st ^ 1);
+    mbar_wait(bar_s, kt & 1);
+    tc_fence_after();
+    // pass 1: row max
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c0 = 0; c0 < KT; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tS + lane_addr + c0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+    }
+    const float m_new = fmaxf(m_run, mx);
+    const float alpha = exp2f((m_run - m_new) * c);
+    const float mc = m_new * c;
+    float lsum = 0.f;
+    // pass 2: p = exp2(s*c - m*c), write bf16 P (K-major, SWIZZLE_128B)
+#pragma unroll 1
+    for (int c0 = 0; c0 < KT; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tS + lane_addr + c0, r);
+      tmem_ld_wait();
+      uint8_t* prow = sP + (c0 >> 6) * 16384 + tid * 128;
+      const int ch0 = (c0 & 63) >> 3;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float p[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          p[j] = exp2f(__uint_as_float(r[8 * g + j]) * c - mc);
+          lsum += p[j];
+        }
+        uint4 u;
+        u.x = pack_bf16(p[0], p[1]);
+        u.y = pack_bf16(p[2], p[3]);
+        u.z = pack_bf16(p[4], p[5]);
+        u.w = pack_bf16(p[6], p[7]);
+        *reinterpret_cast<uint4*>(prow + (((ch0 + g) ^ r7) << 4)) = u;
+      }
+    }
+    l_run = l_run * alpha + lsum;
+    m_run = m_new;
+    tc_fence_before();
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t dp = umma_desc_sw128(smem_u32(sP));
+      const uint64_t dv = umma_desc_sw128(smem_u32(sV + st * Cfg::V_BYTES));
+#pragma unroll
+      for (int k = 0; k < KT / 16; ++k) {
+        // P atoms are 16 KB apart (128 rows x 128 B), V^T atoms 8 KB apart (64 rows x 128 B)
+        const uint64_t pa = dp + static_cast<uint64_t>((k >> 2) * (16384 >> 4) + (k & 3) * 2);
+        const uint64_t va = dv + static_cast<uint64_t>((k >> 2) * (8192 >> 4) + (k & 3) * 2);
+        umma_bf16(tO, pa, va, idesc_o, k != 0);
+      }
+      umma_commit(bar_o);
+      if (kt + 1 < nkt) {
+        mbar_wait(&bar_kv[st ^ 1], ((kt + 1) >> 1) & 1);
+        tc_fence_after();
+        issue_s(st ^ 1);
+      }
+    }
+    mbar_wait(bar_o, kt & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t r[32];
+      tmem_ld32(tO + lane_addr + h * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) o[h * 32 + j] = o[h * 32 + j] * alpha + __uint_as_float(r[j]);
+    }
+  }
+
+  const int q = q0 + tid;
+  if (q < a.L) {
+    const float inv = 1.0f / l_run;
+    uint4* op = reinterpret_cast<uint4*>(a.out + static_cast<size_t>(row_base + q) * a.ld_out + head * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint4 u;
+      u.x = pack_bf16(o[8 * j + 0] * inv, o[8 * j + 1] * inv);
+      u.y = pack_bf16(o[8 * j + 2] * inv, o[8 * j + 3] * inv);
+      u.z = pack_bf16(o[8 * j + 4] * inv, o[8 * j + 5] * inv);
+      u.w = pack_bf16(o[8 * j + 6] * inv, o[8 * j + 7] * inv);
+      op[j] = u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,574 @@
+// C ABI of libb200ns.so (see include/b200_noise_search.h): launch wrappers, TMA descriptor
+// construction and the plan runner.  No torch types, no CPU fallback.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200_noise_search.h"
+#include "attention.cuh"
+#include "gemm_conv.cuh"
+#include "groupnorm.cuh"
+#include "sampler.cuh"
+
+using namespace b200;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string& msg) {
+  g_err = msg;
+  return 1;
+}
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return static_cast<int>(e);
+}
+#define CK(call)                                   \
+  do {                                             \
+    int _rc = check_cuda((call), #call);           \
+    if (_rc) return _rc;                           \
+  } while (0)
+#define CK_LAUNCH(name)                            \
+  do {                                             \
+    int _rc = check_cuda(cudaGetLastError(), name); \
+    if (_rc) return _rc;                           \
+  } while (0)
+
+cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int grid_for(int64_t work_items, int threads, int max_blocks = 148 * 16) {
+  int64_t b = (work_items + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return static_cast<int>(b);
+}
+
+// ------------------------------------------------------------------ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 tensor, `rank` dims (innermost first), 128B swizzle, zero OOB fill.
+int make_tmap(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) return fail("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5], es[5];
+  uint64_t stride = 2;
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    stride *= dims[i];
+    if (i < rank - 1) gstr[i] = stride;
+  }
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) rank=%d dims=[%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u]",
+             static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+             (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+             rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return fail(buf);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ plan ops
+enum OpKind { OP_GEMM, OP_GN_STATS, OP_GN_APPLY, OP_ATTN, OP_LINEAR, OP_IM2COL };
+
+struct GemmOp {
+  CUtensorMap tmA0, tmA1, tmB;
+  GemmArgs args;
+  int BN;
+  int grid;
+};
+struct GnStatsOp {
+  GnStatsArgs args;
+  dim3 grid;
+  int threads;
+};
+struct GnApplyOp {
+  GnApplyArgs args;
+  dim3 grid;
+  int threads;
+};
+struct AttnOp {
+  CUtensorMap tmQ, tmK, tmV;
+  AttnArgs args;
+  int KT;
+  dim3 grid;
+};
+struct LinearOp {
+  LinearArgs args;
+  int grid;
+};
+struct Im2colOp {
+  b200ns_im2col_desc d;
+  int grid;
+};
+
+struct Op {
+  OpKind kind;
+  union {
+    GemmOp gemm;
+    GnStatsOp gns;
+    GnApplyOp gna;
+    AttnOp attn;
+    LinearOp lin;
+    Im2colOp i2c;
+  };
+  Op() { memset(this, 0, sizeof(*this)); }
+};
+
+int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN>
+int launch_gemm_t(const GemmOp& g, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(gemm_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  gemm_conv_kernel<BN><<<g.grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(g.tmA0, g.tmA1, g.tmB, g.args);
+  CK_LAUNCH("gemm_conv_kernel");
+  return 0;
+}
+int launch_gemm(const GemmOp& g, cudaStream_t st) {
+  switch (g.BN) {
+    case 256: return launch_gemm_t<256>(g, st);
+    case 192: return launch_gemm_t<192>(g, st);
+    case 128: return launch_gemm_t<128>(g, st);
+    case 64: return launch_gemm_t<64>(g, st);
+    case 16: return launch_gemm_t<16>(g, st);
+  }
+  return fail("bad BN");
+}
+
+template <int KT>
+int launch_attn_t(const AttnOp& o, cudaStream_t st) {
+  using Cfg = AttnCfg<KT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(attention_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  attention_kernel<KT><<<o.grid, 128, Cfg::SMEM_BYTES, st>>>(o.tmQ, o.tmK, o.tmV, o.args);
+  CK_LAUNCH("attention_kernel");
+  return 0;
+}
+
+int run_op(const Op& op, cudaStream_t st) {
+  switch (op.kind) {
+    case OP_GEMM: return launch_gemm(op.gemm, st);
+    case OP_GN_STATS:
+      gn_stats_kernel<<<op.gns.grid, op.gns.threads, 0, st>>>(op.gns.args);
+      CK_LAUNCH("gn_stats_kernel");
+      return 0;
+    case OP_GN_APPLY:
+      gn_apply_kernel<<<op.gna.grid, op.gna.threads, 0, st>>>(op.gna.args);
+      CK_LAUNCH("gn_apply_kernel");
+      return 0;
+    case OP_ATTN: return op.attn.KT == 128 ? launch_attn_t<128>(op.attn, st) : launch_attn_t<64>(op.attn, st);
+    case OP_LINEAR:
+      linear_kernel<<<op.lin.grid, 256, 0, st>>>(op.lin.args);
+      CK_LAUNCH("linear_kernel");
+      return 0;
+    case OP_IM2COL:
+      im2col_c3_kernel<<<op.i2c.grid, 256, 0, st>>>(op.i2c.d.x, reinterpret_cast<__nv_bfloat16*>(op.i2c.d.out),
+                                                   op.i2c.d.batch, op.i2c.d.C, op.i2c.d.H, op.i2c.d.W);
+      CK_LAUNCH("im2col_c3_kernel");
+      return 0;
+  }
+  return fail("bad op kind");
+}
+
+}  // namespace
+
+struct b200ns_plan {
+  std::vector<Op> ops;
+};
+
+extern "C" {
+
+const char* b200ns_last_error(void) { return g_err.c_str(); }
+
+int b200ns_device_ok(int dev) {
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+// ------------------------------------------------------------------ sampler / scorer
+int b200ns_heun_pre(const double* x_cur, const double* eps, double* x_hat, float* net_in, int64_t R, int64_t b,
+                    int64_t E, double s, float c_in, void* stream) {
+  if (E % 2) return fail("heun_pre: E must be even");
+  const int64_t total = R * E;
+  heun_pre_kernel<<<grid_for(total / 2, 256), 256, 0, S(stream)>>>(x_cur, eps, x_hat, net_in, total, b * E, s, c_in);
+  CK_LAUNCH("heun_pre_kernel");
+  return 0;
+}
+
+int b200ns_heun_mid(const double* x_hat, const float* F1, float* net_in2, double* x_eul, int64_t R, int32_t C,
+                    int32_t HW, float c_skip, float c_out, double t_hat, double dt, float c_in_next, void* stream) {
+  HeunCoef k{};
+  k.c_skip1 = c_skip;
+  k.c_out1 = c_out;
+  k.t_hat = t_hat;
+  k.dt = dt;
+  k.c_in_next = c_in_next;
+  const int64_t total = R * C * HW;
+  heun_mid_kernel<<<grid_for(total, 256), 256, 0, S(stream)>>>(x_hat, F1, net_in2, x_eul, total, C, HW, k);
+  CK_LAUNCH("heun_mid_kernel");
+  return 0;
+}
+
+int b200ns_heun_post(const double* x_hat, const float* F1, const float* F2, double* x_next, uint8_t* x0_u8,
+                     uint32_t* chan_sums, int64_t R, int32_t C, int32_t HW, float c_skip1, float c_out1, double t_hat,
+                     double dt, float c_skip2, float c_out2, double t_next, void* stream) {
+  HeunCoef k{};
+  k.c_skip1 = c_skip1;
+  k.c_out1 = c_out1;
+  k.t_hat = t_hat;
+  k.dt = dt;
+  k.c_skip2 = c_skip2;
+  k.c_out2 = c_out2;
+  k.t_next = t_next;
+  if (R > 65535) return fail("heun_post: R > 65535");
+  if (chan_sums != nullptr) CK(cudaMemsetAsync(chan_sums, 0, sizeof(uint32_t) * 4 * R, S(stream)));
+  int chunks = static_cast<int>((2 * 148 + R - 1) / R);
+  const int max_chunks = (HW + 255) / 256;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  heun_post_kernel<<<dim3(chunks, static_cast<unsigned>(R)), 256, 0, S(stream)>>>(x_hat, F1, F2, x_next, x0_u8, chan_sums,
+                                                                                 C, HW, k);
+  CK_LAUNCH("heun_post_kernel");
+  return 0;
+}
+
+int b200ns_quantize_u8(const double* x, uint8_t* out, int64_t n, void* stream) {
+  quantize_u8_kernel<<<grid_for(n, 256), 256, 0, S(stream)>>>(x, out, n);
+  CK_LAUNCH("quantize_u8_kernel");
+  return 0;
+}
+
+int b200ns_channel_sums_u8(const uint8_t* img, uint32_t* chan_sums, int64_t M, int32_t C, int32_t HW, void* stream) {
+  if (M > 65535) return fail("channel_sums: M > 65535");
+  if (C > 4) return fail("channel_sums: C > 4");
+  CK(cudaMemsetAsync(chan_sums, 0, sizeof(uint32_t) * 4 * M, S(stream)));
+  int chunks = static_cast<int>((2 * 148 + M - 1) / M);
+  const int max_chunks = (HW + 255) / 256;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  channel_sums_u8_kernel<<<dim3(chunks, static_cast<unsigned>(M)), 256, 0, S(stream)>>>(img, chan_sums, C, HW);
+  CK_LAUNCH("channel_sums_u8_kernel");
+  return 0;
+}
+
+int b200ns_brightness_from_sums(const uint32_t* chan_sums, float* scores, int64_t M, int32_t C, int32_t HW,
+                                void* stream) {
+  brightness_kernel<<<grid_for(M, 128), 128, 0, S(stream)>>>(chan_sums, scores, M, C, HW);
+  CK_LAUNCH("brightness_kernel");
+  return 0;
+}
+
+int b200ns_argmax_first(const float* scores, int64_t N, int64_t b, int64_t idx_base, int64_t* idx,
+                        int64_t* packed_key, void* stream) {
+  if (idx_base + N > 0xFFFFFFFFll) return fail("argmax_first: index overflow");
+  argmax_first_kernel<<<static_cast<unsigned>(b), 32, 0, S(stream)>>>(scores, N, b, idx_base, idx, packed_key);
+  CK_LAUNCH("argmax_first_kernel");
+  return 0;
+}
+
+int b200ns_gather_rows(const double* src, const int64_t* idx, double* dst, int64_t N, int64_t b, int64_t E,
+                       void* stream) {
+  (void)N;
+  gather_rows_kernel<<<dim3(grid_for(E, 256, 64), static_cast<unsigned>(b)), 256, 0, S(stream)>>>(src, idx, dst, b, E);
+  CK_LAUNCH("gather_rows_kernel");
+  return 0;
+}
+
+int b200ns_direction_norms(const double* dirs, double* norms, int64_t R, int64_t E, void* stream) {
+  direction_norms_kernel<<<static_cast<unsigned>(R), 256, 0, S(stream)>>>(dirs, norms, E);
+  CK_LAUNCH("direction_norms_kernel");
+  return 0;
+}
+
+int b200ns_make_candidates(const double* pivot, const double* dirs, const double* norms, const float* scale,
+                           const uint8_t* fresh_mask, const double* fresh, double* cand, int64_t R, int64_t b,
+                           int64_t E, void* stream) {
+  if (R > 65535) return fail("make_candidates: R > 65535");
+  make_candidates_kernel<<<dim3(grid_for(E, 256, 16), static_cast<unsigned>(R)), 256, 0, S(stream)>>>(
+      pivot, dirs, norms, scale, fresh_mask, fresh, cand, b, E);
+  CK_LAUNCH("make_candidates_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------ plans
+b200ns_plan* b200ns_plan_create(void) { return new b200ns_plan(); }
+void b200ns_plan_destroy(b200ns_plan* p) { delete p; }
+int b200ns_plan_size(const b200ns_plan* p) { return static_cast<int>(p->ops.size()); }
+
+int b200ns_plan_run_range(b200ns_plan* p, int first, int last, void* stream) {
+  if (first < 0 || last > static_cast<int>(p->ops.size()) || first > last) return fail("plan_run_range: bad range");
+  for (int i = first; i < last; ++i) {
+    int rc = run_op(p->ops[i], S(stream));
+    if (rc) {
+      g_err = "plan op " + std::to_string(i) + ": " + g_err;
+      return rc;
+    }
+  }
+  return 0;
+}
+int b200ns_plan_run(b200ns_plan* p, void* stream) {
+  return b200ns_plan_run_range(p, 0, static_cast<int>(p->ops.size()), stream);
+}
+
+int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d) {
+  Op op;
+  op.kind = OP_GEMM;
+  GemmOp& g = op.gemm;
+  GemmArgs& a = g.args;
+  const int H = d->H, W = d->W;
+  if (W <= 0 || W > 128 || 128 % W) return fail("gemm: W must divide 128");
+  int tileH = 128 / W;
+  if (tileH > H) tileH = H;
+  if (H % tileH) return fail("gemm: H not a multiple of the tile height");
+  const int tileN = 128 / (W * tileH);
+  a.H = H;
+  a.W = W;
+  a.tileH = tileH;
+  a.tileN = tileN;
+  a.tiles_per_img = (H * W >= 128) ? (H * W) / 128 : 0;
+  a.M = d->batch * H * W;
+  a.N = d->N;
+  a.m_tiles = (a.M + 127) / 128;
+  if (d->Npad % 16) return fail("gemm: Npad must be a multiple of 16");
+  int BN = 0;
+  const int cands[5] = {256, 192, 128, 64, 16};
+  for (int c : cands)
+    if (d->Npad % c == 0) {
+      BN = c;
+      break;
+    }
+  if (!BN) return fail("gemm: no tile width divides Npad");
+  g.BN = BN;
+  a.n_tiles = d->Npad / BN;
+  a.n_seg = d->n_seg;
+  if (d->n_seg < 1 || d->n_seg > 4) return fail("gemm: n_seg out of range");
+  int nkb = 0;
+  for (int s = 0; s < d->n_seg; ++s) {
+    const b200ns_kseg& sg = d->seg[s];
+    if (sg.taps != 1 && sg.taps != 9) return fail("gemm: taps must be 1 or 9");
+    if (sg.src < 0 || sg.src > 1 || d->a_ptr[sg.src] == nullptr) return fail("gemm: bad segment source");
+    if (sg.cstart % 64 || sg.cstart + sg.cblocks * 64 > d->a_channels[sg.src]) return fail("gemm: bad channel range");
+    a.seg[s] = KSeg{sg.src, sg.taps, sg.cstart, sg.cblocks};
+    nkb += sg.taps * sg.cblocks;
+  }
+  if (nkb * 64 != d->Ktot) return fail("gemm: Ktot does not match the K segments");
+  a.nkb = nkb;
+  a.bias = d->bias;
+  a.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
+  a.ld_res = d->ld_res;
+  a.out_scale = d->out_scale;
+  a.out = d->out;
+  a.ld_out = d->ld_out;
+  a.out_fp32 = d->out_fp32;
+  a.vt_out = reinterpret_cast<__nv_bfloat16*>(d->vt_out);
+  a.vt_col_start = d->vt_col_start;
+  a.heads = d->heads;
+  a.L = H * W;
+  if (!d->out_fp32 && (d->ld_out % 8)) return fail("gemm: ld_out must be a multiple of 8 for bf16 output");
+  if (d->residual != nullptr && (d->ld_res % 8)) return fail("gemm: ld_res must be a multiple of 8");
+  if (d->vt_out != nullptr && (d->vt_col_start % 64)) return fail("gemm: vt_col_start must be a multiple of 64");
+
+  for (int i = 0; i < 2; ++i) {
+    const void* ptr = d->a_ptr[i] ? d->a_ptr[i] : d->a_ptr[0];
+    const int ch = d->a_ptr[i] ? d->a_channels[i] : d->a_channels[0];
+    if (ch % 64) return fail("gemm: activation channels must be a multiple of 64");
+    const uint64_t dims[4] = {static_cast<uint64_t>(ch), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                              static_cast<uint64_t>(d->batch)};
+    const uint32_t box[4] = {64, static_cast<uint32_t>(W), static_cast<uint32_t>(tileH), static_cast<uint32_t>(tileN)};
+    int rc = make_tmap(i == 0 ? &g.tmA0 : &g.tmA1, ptr, 4, dims, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(d->Ktot), static_cast<uint64_t>(d->Npad)};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(BN)};
+    int rc = make_tmap(&g.tmB, d->w_ptr, 2, dims, box);
+    if (rc) return rc;
+  }
+  const int tiles = a.m_tiles * a.n_tiles;
+  g.grid = tiles < num_sms() ? tiles : num_sms();
+  p->ops.push_back(op);
+  return 0;
+}
+
+int b200ns_plan_add_gn_stats(b200ns_plan* p, const b200ns_gn_stats_desc* d) {
+  Op op;
+  op.kind = OP_GN_STATS;
+  GnStatsArgs& a = op.gns.args;
+  a.x0 = reinterpret_cast<const __nv_bfloat16*>(d->x_ptr[0]);
+  a.x1 = reinterpret_cast<const __nv_bfloat16*>(d->x_ptr[1]);
+  a.C0 = d->x_channels[0];
+  a.C1 = d->x_ptr[1] ? d->x_channels[1] : 0;
+  a.C = a.C0 + a.C1;
+  if (a.C % 8 || a.C0 % 8 || a.C > 2048) return fail("gn_stats: channels must be multiples of 8 and <= 2048");
+  if (d->groups > 64 || a.C % d->groups) return fail("gn_stats: bad group count");
+  a.HW = d->HW;
+  a.groups = d->groups;
+  a.cpg = a.C / d->groups;
+  a.pre_add = d->pre_add;
+  a.ld_pre_add = d->ld_pre_add;
+  a.b_emb = d->b_emb > 0 ? d->b_emb : 1;
+  a.partial = reinterpret_cast<double*>(d->partial);
+  a.splits = d->splits;
+  if (d->splits < 1 || d->HW % d->splits) return fail("gn_stats: splits must divide HW");
+  const int VC = a.C / 8;
+  a.PY = 256 / VC;
+  if (a.PY < 1) a.PY = 1;
+  op.gns.threads = VC * a.PY;
+  op.gns.grid = dim3(d->splits, d->batch);
+  p->ops.push_back(op);
+  return 0;
+}
+
+int b200ns_plan_add_gn_apply(b200ns_plan* p, const b200ns_gn_apply_desc* d) {
+  Op op;
+  op.kind = OP_GN_APPLY;
+  GnApplyArgs& a = op.gna.args;
+  a.x0 = reinterpret_cast<const __nv_bfloat16*>(d->x_ptr[0]);
+  a.x1 = reinterpret_cast<const __nv_bfloat16*>(d->x_ptr[1]);
+  a.C0 = d->x_channels[0];
+  a.C1 = d->x_ptr[1] ? d->x_channels[1] : 0;
+  a.C = a.C0 + a.C1;
+  if (a.C % 8 || a.C0 % 8 || a.C > 2048) return fail("gn_apply: channels must be multiples of 8 and <= 2048");
+  if (d->groups > 64 || a.C % d->groups) return fail("gn_apply: bad group count");
+  if (d->resample == 2 && (d->H % 2 || d->W % 2)) return fail("gn_apply: odd size cannot be downsampled");
+  a.H = d->H;
+  a.W = d->W;
+  a.groups = d->groups;
+  a.cpg = a.C / d->groups;
+  a.partial = reinterpret_cast<const double*>(d->partial);
+  a.splits = d->splits;
+  a.eps = d->eps;
+  a.gamma = d->gamma;
+  a.beta = d->beta;
+  a.pre_add = d->pre_add;
+  a.ld_pre_add = d->ld_pre_add;
+  a.film_scale = d->film_scale;
+  a.film_shift = d->film_shift;
+  a.ld_film = d->ld_film;
+  a.b_emb = d->b_emb > 0 ? d->b_emb : 1;
+  a.silu = d->silu;
+  a.resample = d->resample;
+  a.out = reinterpret_cast<__nv_bfloat16*>(d->out);
+  a.raw_out = reinterpret_cast<__nv_bfloat16*>(d->raw_out);
+  const int VC = a.C / 8;
+  a.PY = 256 / VC;
+  if (a.PY < 1) a.PY = 1;
+  a.ITER = 4;
+  op.gna.threads = VC * a.PY;
+  const int dom = d->resample == 2 ? (d->H / 2) * (d->W / 2) : d->H * d->W;
+  const int per_cta = a.PY * a.ITER;
+  op.gna.grid = dim3((dom + per_cta - 1) / per_cta, d->batch);
+  p->ops.push_back(op);
+  return 0;
+}
+
+int b200ns_plan_add_attention(b200ns_plan* p, const b200ns_attn_desc* d) {
+  Op op;
+  op.kind = OP_ATTN;
+  AttnOp& o = op.attn;
+  if (d->L % 64) return fail("attention: L must be a multiple of 64");
+  o.KT = (d->L % 128 == 0) ? 128 : 64;
+  o.args.out = reinterpret_cast<__nv_bfloat16*>(d->out);
+  o.args.ld_out = d->ld_out;
+  o.args.heads = d->heads;
+  o.args.L = d->L;
+  o.args.k_col0 = d->k_col0;
+  const uint64_t M = static_cast<uint64_t>(d->batch) * d->L;
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(d->ld_qk), M};
+    const uint32_t boxq[2] = {64, 128};
+    const uint32_t boxk[2] = {64, static_cast<uint32_t>(o.KT)};
+    int rc = make_tmap(&o.tmQ, d->qk, 2, dims, boxq);
+    if (rc) return rc;
+    rc = make_tmap(&o.tmK, d->qk, 2, dims, boxk);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(d->L), static_cast<uint64_t>(d->batch) * d->heads * 64};
+    const uint32_t box[2] = {64, 64};
+    int rc = make_tmap(&o.tmV, d->vt, 2, dims, box);
+    if (rc) return rc;
+  }
+  o.grid = dim3((d->L + 127) / 128, d->batch * d->heads);
+  p->ops.push_back(op);
+  return 0;
+}
+
+int b200ns_plan_add_linear(b200ns_plan* p, const b200ns_linear_desc* d) {
+  Op op;
+  op.kind = OP_LINEAR;
+  LinearArgs& a = op.lin.args;
+  a.x = d->x;
+  a.rows = d->rows;
+  a.K = d->K;
+  a.ld_x = d->ld_x;
+  a.w = d->w;
+  a.bias = d->bias;
+  a.add = d->add;
+  a.ld_add = d->ld_add;
+  a.N = d->N;
+  a.act = d->act;
+  a.out = d->out;
+  a.ld_out = d->ld_out;
+  const int64_t warps = static_cast<int64_t>(d->rows) * d->N;
+  op.lin.grid = static_cast<int>((warps * 32 + 255) / 256);
+  p->ops.push_back(op);
+  return 0;
+}
+
+int b200ns_plan_add_im2col(b200ns_plan* p, const b200ns_im2col_desc* d) {
+  if (d->C * 9 > 64) return fail("im2col: C*9 must be <= 64");
+  Op op;
+  op.kind = OP_IM2COL;
+  op.i2c.d = *d;
+  op.i2c.grid = grid_for(static_cast<int64_t>(d->batch) * d->H * d->W * 8, 256);
+  p->ops.push_back(op);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,235 @@
+// GroupNorm for bf16 NHWC activations, split in two HBM-bound passes:
+//   gn_stats_kernel : per-(sample, split, group) partial sum / sum-of-squares (fp64 partials,
+//                     fixed reduction order -> bit-identical for identical inputs regardless
+//                     of batch position or shard, which exact-tie argmax relies on)
+//   gn_apply_kernel : finalise mean/rstd, then y = act(FiLM(norm(x))) with optional 2x resample
+// Both read up to two concatenated sources (decoder skip concat, networks.py:458) so the
+// concat is never materialised.  Replaces GroupNorm.forward (edm/training/networks.py:104-106)
+// and the silu/addcmul glue of UNetBlock.forward (:168, :173-175, :182).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+struct GnStatsArgs {
+  const __nv_bfloat16* x0;
+  const __nv_bfloat16* x1;
+  int C0, C1, C;           // C = C0 + C1
+  int HW, groups, cpg;
+  const float* pre_add;    // [b_emb, ld_pre_add] or null
+  int ld_pre_add, b_emb;
+  double* partial;         // [batch, splits, groups, 2]
+  int splits, PY;
+};
+
+DEVINL void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  float2 t;
+  t = unpack_bf16(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16(u.w); f[6] = t.x; f[7] = t.y;
+}
+DEVINL void store8(__nv_bfloat16* p, const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16(f[0], f[1]);
+  u.y = pack_bf16(f[2], f[3]);
+  u.z = pack_bf16(f[4], f[5]);
+  u.w = pack_bf16(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// grid (splits, batch); block = (C/8) * PY threads (<= 256)
+__global__ void gn_stats_kernel(const GnStatsArgs a) {
+  __shared__ float s_sum[2048];
+  __shared__ float s_sq[2048];
+  const int VC = a.C >> 3;
+  const int vx = threadIdx.x % VC, py = threadIdx.x / VC;
+  const int split = blockIdx.x, bi = blockIdx.y;
+  const int ppb = a.HW / a.splits;
+  const int c = vx * 8;
+  const __nv_bfloat16* src;
+  int ld;
+  if (c < a.C0) {
+    src = a.x0 + c;
+    ld = a.C0;
+  } else {
+    src = a.x1 + (c - a.C0);
+    ld = a.C1;
+  }
+  src += (static_cast<size_t>(bi) * a.HW + static_cast<size_t>(split) * ppb) * ld;
+  float pa[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (a.pre_add != nullptr) {
+    const float* pp = a.pre_add + static_cast<size_t>(bi % a.b_emb) * a.ld_pre_add + c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pa[j] = pp[j];
+  }
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ss[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int p = py; p < ppb; p += a.PY) {
+    float f[8];
+    load8(src + static_cast<size_t>(p) * ld, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = f[j] + pa[j];
+      s[j] += v;
+      ss[j] += v * v;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s_sum[py * a.C + c + j] = s[j];
+    s_sq[py * a.C + c + j] = ss[j];
+  }
+  __syncthreads();
+  // one thread per group: fixed-order fp64 reduction over (py, channel-in-group)
+  for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
+    double ds = 0.0, dq = 0.0;
+    for (int cc = g * a.cpg; cc < (g + 1) * a.cpg; ++cc)
+      for (int y = 0; y < a.PY; ++y) {
+        ds += static_cast<double>(s_sum[y * a.C + cc]);
+        dq += static_cast<double>(s_sq[y * a.C + cc]);
+      }
+    double* o = a.partial + ((static_cast<size_t>(bi) * a.splits + split) * a.groups + g) * 2;
+    o[0] = ds;
+    o[1] = dq;
+  }
+}
+
+struct GnApplyArgs {
+  const __nv_bfloat16* x0;
+  const __nv_bfloat16* x1;
+  int C0, C1, C;
+  int H, W, groups, cpg;   // INPUT spatial dims
+  const double* partial;
+  int splits;
+  float eps;
+  const float* gamma;
+  const float* beta;
+  const float* pre_add;
+  int ld_pre_add;
+  const float* film_scale;
+  const float* film_shift;
+  int ld_film, b_emb;
+  int silu, resample;      // 0 none, 1 up x2, 2 down x2
+  __nv_bfloat16* out;
+  __nv_bfloat16* raw_out;
+  int PY, ITER;
+};
+
+// grid (pixel chunks, batch); block = (C/8) * PY threads
+__global__ void gn_apply_kernel(const GnApplyArgs a) {
+  __shared__ float s_mean[64];
+  __shared__ float s_rstd[64];
+  const int VC = a.C >> 3;
+  const int vx = threadIdx.x % VC, py = threadIdx.x / VC;
+  const int bi = blockIdx.y;
+  const int HW = a.H * a.W;
+  if (threadIdx.x < a.groups) {
+    const int g = threadIdx.x;
+    double ds = 0.0, dq = 0.0;
+    for (int sp = 0; sp < a.splits; ++sp) {
+      const double* o = a.partial + ((static_cast<size_t>(bi) * a.splits + sp) * a.groups + g) * 2;
+      ds += o[0];
+      dq += o[1];
+    }
+    const double n = static_cast<double>(HW) * a.cpg;
+    const double mean = ds / n;
+    double var = dq / n - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    s_mean[g] = static_cast<float>(mean);
+    s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
+  }
+  __syncthreads();
+
+  const int c = vx * 8;
+  const __nv_bfloat16* src;
+  int ld;
+  if (c < a.C0) {
+    src = a.x0 + c;
+    ld = a.C0;
+  } else {
+    src = a.x1 + (c - a.C0);
+    ld = a.C1;
+  }
+  src += static_cast<size_t>(bi) * HW * ld;
+
+  // y = act(x * ka + kb) per channel
+  float ka[8], kb[8];
+  {
+    const int e = bi % a.b_emb;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int cc = c + j;
+      const int g = cc / a.cpg;
+      const float rs = s_rstd[g] * a.gamma[cc];
+      float k1 = rs;
+      float k0 = a.beta[cc] - s_mean[g] * rs;
+      if (a.pre_add != nullptr) k0 += a.pre_add[static_cast<size_t>(e) * a.ld_pre_add + cc] * rs;
+      if (a.film_scale != nullptr) {
+        const float sc = a.film_scale[static_cast<size_t>(e) * a.ld_film + cc] + 1.0f;
+        const float sh = a.film_shift[static_cast<size_t>(e) * a.ld_film + cc];
+        k1 *= sc;
+        k0 = k0 * sc + sh;
+      }
+      ka[j] = k1;
+      kb[j] = k0;
+    }
+  }
+
+  const int outW = a.resample == 1 ? a.W * 2 : (a.resample == 2 ? a.W / 2 : a.W);
+  const int outH = a.resample == 1 ? a.H * 2 : (a.resample == 2 ? a.H / 2 : a.H);
+  const size_t out_base = static_cast<size_t>(bi) * outH * outW * a.C + c;
+  const int dom = a.resample == 2 ? outH * outW : HW;      // loop domain
+  const int p_begin = blockIdx.x * a.PY * a.ITER + py;
+
+  for (int it = 0; it < a.ITER; ++it) {
+    const int p = p_begin + it * a.PY;
+    if (p >= dom) break;
+    if (a.resample == 2) {
+      const int oy = p / outW, ox = p - oy * outW;
+      float accv[8] = {0, 0, 0, 0, 0, 0, 0, 0}, accr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int iy = 2 * oy + (t >> 1), ix = 2 * ox + (t & 1);
+        float f[8];
+        load8(src + static_cast<size_t>(iy * a.W + ix) * ld, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v = f[j] * ka[j] + kb[j];
+          if (a.silu) v = silu_f(v);
+          accv[j] += v;
+          accr[j] += f[j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        accv[j] *= 0.25f;
+        accr[j] *= 0.25f;
+      }
+      store8(a.out + out_base + static_cast<size_t>(p) * a.C, accv);
+      if (a.raw_out != nullptr) store8(a.raw_out + out_base + static_cast<size_t>(p) * a.C, accr);
+    } else {
+      float f[8], v[8];
+      load8(src + static_cast<size_t>(p) * ld, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[j] = f[j] * ka[j] + kb[j];
+        if (a.silu) v[j] = silu_f(v[j]);
+      }
+      if (a.resample == 0) {
+        store8(a.out + out_base + static_cast<size_t>(p) * a.C, v);
+        if (a.raw_out != nullptr) store8(a.raw_out + out_base + static_cast<size_t>(p) * a.C, f);
+      } else {
+        const int iy = p / a.W, ix = p - iy * a.W;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const size_t op = static_cast<size_t>((2 * iy + (t >> 1)) * outW + 2 * ix + (t & 1)) * a.C;
+          store8(a.out + out_base + op, v);
+          if (a.raw_out != nullptr) store8(a.raw_out + out_base + op, f);
+        }
+      }
+    }
+  }
+}
+
+}  // namespace b200

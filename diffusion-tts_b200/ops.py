@@ -1,0 +1,270 @@
+"""Thin Python wrappers over the C ABI: sampler/scorer ops on torch CUDA tensors and the
+`Plan` builder for the U-Net engine.  Everything here launches hand-written sm_100a kernels
+from libb200ns.so on torch's current stream; nothing falls back to PyTorch math."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+def _chk_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('b200 ops need CUDA tensors (no CPU fallback)')
+
+
+def _c(t: torch.Tensor, dtype) -> torch.Tensor:
+    if t.dtype != dtype or not t.is_contiguous():
+        raise RuntimeError(f'expected contiguous {dtype} tensor, got {t.dtype} contiguous={t.is_contiguous()}')
+    return t
+
+
+# ------------------------------------------------------------------ sampler / scorer
+def heun_pre(x_cur: torch.Tensor, eps: torch.Tensor, s: float, c_in: float):
+    """x_hat = x_cur + s*eps; net_in = c_in*fp32(x_hat).  x_cur [b,C,H,W] fp64, eps [R,C,H,W] fp64."""
+    _chk_cuda(x_cur, eps)
+    _c(x_cur, torch.float64), _c(eps, torch.float64)
+    R, b = eps.shape[0], x_cur.shape[0]
+    E = eps[0].numel()
+    x_hat = torch.empty_like(eps)
+    net_in = torch.empty(eps.shape, dtype=torch.float32, device=eps.device)
+    L.check(L.lib().b200ns_heun_pre(L.ptr(x_cur), L.ptr(eps), L.ptr(x_hat), L.ptr(net_in), R, b, E, float(s),
+                                    float(c_in), L.cur_stream()), 'heun_pre')
+    return x_hat, net_in
+
+
+def heun_mid(x_hat: torch.Tensor, F1: torch.Tensor, c_skip, c_out, t_hat, dt, c_in_next, want_x_eul=False):
+    """Euler half step.  F1 fp32 NHWC [R,H,W,C] (U-Net output)."""
+    _chk_cuda(x_hat, F1)
+    _c(x_hat, torch.float64), _c(F1, torch.float32)
+    R, Cc, H, W = x_hat.shape
+    net_in2 = torch.empty(x_hat.shape, dtype=torch.float32, device=x_hat.device)
+    x_eul = torch.empty_like(x_hat) if want_x_eul else None
+    L.check(L.lib().b200ns_heun_mid(L.ptr(x_hat), L.ptr(F1), L.ptr(net_in2), L.ptr(x_eul), R, Cc, H * W, float(c_skip),
+                                    float(c_out), float(t_hat), float(dt), float(c_in_next), L.cur_stream()), 'heun_mid')
+    return (net_in2, x_eul) if want_x_eul else net_in2
+
+
+def heun_post(x_hat, F1, F2, c_skip1, c_out1, t_hat, dt, c_skip2=0.0, c_out2=0.0, t_next=1.0,
+              want_x_next=True, want_u8=False, want_sums=True):
+    """Heun correction (F2 None = last step) + x0 -> uint8 + integer channel sums."""
+    _chk_cuda(x_hat, F1, F2)
+    _c(x_hat, torch.float64), _c(F1, torch.float32)
+    if F2 is not None:
+        _c(F2, torch.float32)
+    R, Cc, H, W = x_hat.shape
+    dev = x_hat.device
+    x_next = torch.empty_like(x_hat) if want_x_next else None
+    u8 = torch.empty(x_hat.shape, dtype=torch.uint8, device=dev) if want_u8 else None
+    sums = torch.empty((R, 4), dtype=torch.int32, device=dev) if want_sums else None
+    L.check(L.lib().b200ns_heun_post(L.ptr(x_hat), L.ptr(F1), L.ptr(F2), L.ptr(x_next), L.ptr(u8), L.ptr(sums), R, Cc,
+                                     H * W, float(c_skip1), float(c_out1), float(t_hat), float(dt), float(c_skip2),
+                                     float(c_out2), float(t_next), L.cur_stream()), 'heun_post')
+    return x_next, u8, sums
+
+
+def quantize_u8(x: torch.Tensor) -> torch.Tensor:
+    _chk_cuda(x)
+    _c(x, torch.float64)
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    L.check(L.lib().b200ns_quantize_u8(L.ptr(x), L.ptr(out), x.numel(), L.cur_stream()), 'quantize_u8')
+    return out
+
+
+def channel_sums_u8(img: torch.Tensor) -> torch.Tensor:
+    _chk_cuda(img)
+    _c(img, torch.uint8)
+    M, Cc = img.shape[0], img.shape[1]
+    HW = img[0, 0].numel()
+    sums = torch.empty((M, 4), dtype=torch.int32, device=img.device)
+    L.check(L.lib().b200ns_channel_sums_u8(L.ptr(img), L.ptr(sums), M, Cc, HW, L.cur_stream()), 'channel_sums_u8')
+    return sums
+
+
+def brightness_from_sums(sums: torch.Tensor, Cc: int, HW: int) -> torch.Tensor:
+    _chk_cuda(sums)
+    M = sums.shape[0]
+    scores = torch.empty((M,), dtype=torch.float32, device=sums.device)
+    L.check(L.lib().b200ns_brightness_from_sums(L.ptr(sums), L.ptr(scores), M, Cc, HW, L.cur_stream()), 'brightness')
+    return scores
+
+
+def argmax_first(scores: torch.Tensor, idx_base: int = 0, want_key: bool = False):
+    """scores [N,b] fp32 -> idx [b] int64 (first maximal n) and optionally the packed u64 key."""
+    _chk_cuda(scores)
+    _c(scores, torch.float32)
+    N, b = scores.shape
+    idx = torch.empty((b,), dtype=torch.int64, device=scores.device)
+    key = torch.empty((b,), dtype=torch.int64, device=scores.device) if want_key else None
+    L.check(L.lib().b200ns_argmax_first(L.ptr(scores), N, b, idx_base, L.ptr(idx), L.ptr(key), L.cur_stream()), 'argmax')
+    return (idx, key) if want_key else idx
+
+
+def gather_rows(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """src [N,b,...] fp64, idx [b] -> [b,...]."""
+    _chk_cuda(src, idx)
+    _c(src, torch.float64), _c(idx, torch.int64)
+    N, b = src.shape[0], src.shape[1]
+    E = src[0, 0].numel()
+    dst = torch.empty(src.shape[1:], dtype=torch.float64, device=src.device)
+    L.check(L.lib().b200ns_gather_rows(L.ptr(src), L.ptr(idx), L.ptr(dst), N, b, E, L.cur_stream()), 'gather_rows')
+    return dst
+
+
+def direction_norms(dirs: torch.Tensor) -> torch.Tensor:
+    _chk_cuda(dirs)
+    _c(dirs, torch.float64)
+    R = dirs.shape[0]
+    norms = torch.empty((R,), dtype=torch.float64, device=dirs.device)
+    L.check(L.lib().b200ns_direction_norms(L.ptr(dirs), L.ptr(norms), R, dirs[0].numel(), L.cur_stream()), 'norms')
+    return norms
+
+
+def make_candidates(pivot, dirs, norms, scale, fresh_mask=None, fresh=None) -> torch.Tensor:
+    """pivot [b,...] fp64; dirs [R,...] fp64; norms [R] fp64; scale [R] fp32; fresh_mask [R] u8; fresh [R,...]."""
+    _chk_cuda(pivot, dirs, norms, scale, fresh_mask, fresh)
+    _c(pivot, torch.float64), _c(dirs, torch.float64), _c(norms, torch.float64), _c(scale, torch.float32)
+    R, b = dirs.shape[0], pivot.shape[0]
+    E = dirs[0].numel()
+    cand = torch.empty_like(dirs)
+    L.check(L.lib().b200ns_make_candidates(L.ptr(pivot), L.ptr(dirs), L.ptr(norms), L.ptr(scale), L.ptr(fresh_mask),
+                                           L.ptr(fresh), L.ptr(cand), R, b, E, L.cur_stream()), 'make_candidates')
+    return cand
+
+
+# ------------------------------------------------------------------ plans
+class Plan:
+    """Ordered list of kernel launches (b200ns_plan).  Keeps every tensor it references alive."""
+
+    def __init__(self):
+        self._h = L.lib().b200ns_plan_create()
+        self._keep: List[torch.Tensor] = []
+        self.labels: List[str] = []
+
+    def __del__(self):
+        try:
+            if self._h:
+                L.lib().b200ns_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def _k(self, *ts):
+        for t in ts:
+            if t is not None:
+                _chk_cuda(t)
+                self._keep.append(t)
+
+    def __len__(self):
+        return L.lib().b200ns_plan_size(self._h)
+
+    def run(self, first: Optional[int] = None, last: Optional[int] = None):
+        if first is None:
+            L.check(L.lib().b200ns_plan_run(self._h, L.cur_stream()), 'plan_run')
+        else:
+            L.check(L.lib().b200ns_plan_run_range(self._h, first, last, L.cur_stream()), 'plan_run_range')
+
+    def add_gemm(self, a: Sequence[torch.Tensor], segs: Sequence[Tuple[int, int, int, int]], w: torch.Tensor, N: int,
+                 out: torch.Tensor, *, bias=None, residual=None, out_scale=1.0, vt_out=None, vt_col_start=0, heads=0,
+                 label='gemm'):
+        """a: 1-2 NHWC bf16 tensors [B,H,W,C]; segs: (src, taps, cstart, cblocks); w: bf16 [Npad,Ktot]."""
+        d = L.GemmDesc()
+        B, H, W_, _ = a[0].shape
+        for i, t in enumerate(a):
+            _c(t, torch.bfloat16)
+            d.a_ptr[i] = L.ptr(t)
+            d.a_channels[i] = t.shape[3]
+        d.n_seg = len(segs)
+        for i, (src, taps, cstart, cblocks) in enumerate(segs):
+            d.seg[i] = L.KSeg(src, taps, cstart, cblocks)
+        d.batch, d.H, d.W = B, H, W_
+        _c(w, torch.bfloat16)
+        d.w_ptr, d.N, d.Npad, d.Ktot = L.ptr(w), N, w.shape[0], w.shape[1]
+        d.bias = L.ptr(bias)
+        d.residual = L.ptr(residual)
+        d.ld_res = residual.shape[-1] if residual is not None else 0
+        d.out_scale = float(out_scale)
+        d.out, d.ld_out = L.ptr(out), out.shape[-1]
+        d.out_fp32 = 1 if out.dtype == torch.float32 else 0
+        d.vt_out, d.vt_col_start, d.heads = L.ptr(vt_out), vt_col_start, heads
+        self._k(*a, w, bias, residual, out, vt_out)
+        L.check(L.lib().b200ns_plan_add_gemm(self._h, C.byref(d)), 'plan_add_gemm')
+        self.labels.append(label)
+
+    def add_gn_stats(self, x: Sequence[torch.Tensor], groups: int, partial: torch.Tensor, splits: int, *, pre_add=None,
+                     b_emb=1, label='gn_stats'):
+        d = L.GnStatsDesc()
+        B, H, W_, _ = x[0].shape
+        for i, t in enumerate(x):
+            _c(t, torch.bfloat16)
+            d.x_ptr[i] = L.ptr(t)
+            d.x_channels[i] = t.shape[3]
+        d.batch, d.HW, d.groups = B, H * W_, groups
+        d.pre_add = L.ptr(pre_add)
+        d.ld_pre_add = pre_add.stride(0) if pre_add is not None else 0
+        d.b_emb = b_emb
+        _c(partial, torch.float64)
+        d.partial, d.splits = L.ptr(partial), splits
+        self._k(*x, pre_add, partial)
+        L.check(L.lib().b200ns_plan_add_gn_stats(self._h, C.byref(d)), 'plan_add_gn_stats')
+        self.labels.append(label)
+
+    def add_gn_apply(self, x: Sequence[torch.Tensor], groups: int, partial: torch.Tensor, splits: int, eps: float,
+                     gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor, *, pre_add=None, film_scale=None,
+                     film_shift=None, b_emb=1, silu=True, resample=0, raw_out=None, label='gn_apply'):
+        d = L.GnApplyDesc()
+        B, H, W_, _ = x[0].shape
+        for i, t in enumerate(x):
+            _c(t, torch.bfloat16)
+            d.x_ptr[i] = L.ptr(t)
+            d.x_channels[i] = t.shape[3]
+        d.batch, d.H, d.W, d.groups = B, H, W_, groups
+        d.partial, d.splits, d.eps = L.ptr(partial), splits, float(eps)
+        d.gamma, d.beta = L.ptr(_c(gamma, torch.float32)), L.ptr(_c(beta, torch.float32))
+        d.pre_add = L.ptr(pre_add)
+        d.ld_pre_add = pre_add.stride(0) if pre_add is not None else 0
+        d.film_scale, d.film_shift = L.ptr(film_scale), L.ptr(film_shift)
+        d.ld_film = film_scale.stride(0) if film_scale is not None else 0
+        d.b_emb = b_emb
+        d.silu, d.resample = int(silu), resample
+        d.out, d.raw_out = L.ptr(_c(out, torch.bfloat16)), L.ptr(raw_out)
+        self._k(*x, partial, gamma, beta, pre_add, film_scale, film_shift, out, raw_out)
+        L.check(L.lib().b200ns_plan_add_gn_apply(self._h, C.byref(d)), 'plan_add_gn_apply')
+        self.labels.append(label)
+
+    def add_attention(self, qk: torch.Tensor, k_col0: int, vt: torch.Tensor, out: torch.Tensor, batch: int, heads: int,
+                      Lseq: int, label='attention'):
+        d = L.AttnDesc()
+        d.qk, d.ld_qk, d.k_col0 = L.ptr(_c(qk, torch.bfloat16)), qk.shape[-1], k_col0
+        d.vt = L.ptr(_c(vt, torch.bfloat16))
+        d.out, d.ld_out = L.ptr(_c(out, torch.bfloat16)), out.shape[-1]
+        d.batch, d.heads, d.L = batch, heads, Lseq
+        self._k(qk, vt, out)
+        L.check(L.lib().b200ns_plan_add_attention(self._h, C.byref(d)), 'plan_add_attention')
+        self.labels.append(label)
+
+    def add_linear(self, x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, add=None, act=0,
+                   label='linear'):
+        d = L.LinearDesc()
+        _c(w, torch.float32)
+        d.x, d.rows, d.K, d.ld_x = L.ptr(x), x.shape[0], w.shape[1], x.stride(0)
+        d.w, d.bias, d.add = L.ptr(w), L.ptr(bias), L.ptr(add)
+        d.ld_add = add.stride(0) if add is not None else 0
+        d.N, d.act = w.shape[0], act
+        d.out, d.ld_out = L.ptr(out), out.stride(0)
+        self._k(x, w, bias, add, out)
+        L.check(L.lib().b200ns_plan_add_linear(self._h, C.byref(d)), 'plan_add_linear')
+        self.labels.append(label)
+
+    def add_im2col(self, x: torch.Tensor, out: torch.Tensor, label='im2col'):
+        d = L.Im2colDesc()
+        B, Cc, H, W_ = x.shape
+        d.x, d.out = L.ptr(_c(x, torch.float32)), L.ptr(_c(out, torch.bfloat16))
+        d.batch, d.C, d.H, d.W = B, Cc, H, W_
+        self._k(x, out)
+        L.check(L.lib().b200ns_plan_add_im2col(self._h, C.byref(d)), 'plan_add_im2col')
+        self.labels.append(label)

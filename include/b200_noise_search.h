@@ -1,0 +1,217 @@
+/* b200_noise_search.h -- C ABI of libb200ns.so: the sm_100a kernels behind the
+ * candidate-batched noise-search step of rvignav/diffusion-tts.
+ *
+ * The reference has no FFI of its own (pure Python/PyTorch): the seam is the
+ * Python call sites listed per entry point below (paths relative to the reference checkout).
+ * Every pointer is a DEVICE pointer unless stated; every function enqueues on `stream`
+ * (a cudaStream_t passed as void*) and returns 0 on success or a non-zero code, with the
+ * message available from b200ns_last_error().  There is no CPU fallback anywhere.
+ *
+ * Layout conventions
+ *   sampler state      fp64, NCHW flattened to [R, E], R = N*b candidate rows (row = n*b + j),
+ *                      E = C*H*W                               (edm/main.py:803-806 layout)
+ *   U-Net activations  bf16 NHWC [B, H, W, C], C a multiple of 64
+ *   U-Net weights      bf16 [Cout_pad, Ktot], K-major; K order = (segment, tap kh*3+kw, channel)
+ */
+#ifndef B200_NOISE_SEARCH_H
+#define B200_NOISE_SEARCH_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* b200ns_last_error(void);
+/* 1 if device `dev` is compute capability 10.x (B200), else 0. */
+int b200ns_device_ok(int dev);
+
+/* ------------------------------------------------------------------ sampler / scorer
+ * x_hat = x_cur + s*eps ; net_in = c_in * fp32(x_hat)                 edm/main.py:85,
+ * edm/training/networks.py:655,665.  x_cur is [b,E] (broadcast over candidates: row % b),
+ * eps/x_hat are [R,E] fp64, net_in is fp32 [R,E] (NCHW).  s = sqrt(t_hat^2-t_cur^2)*S_noise. */
+int b200ns_heun_pre(const double* x_cur, const double* eps, double* x_hat, float* net_in,
+                    int64_t R, int64_t b, int64_t E, double s, float c_in, void* stream);
+
+/* Euler half step: D1 = c_skip*fp32(x_hat) + c_out*F1 ; d = (x_hat - D1)/t_hat ;
+ * x_eul = x_hat + dt*d ; net_in2 = c_in_next*fp32(x_eul).            edm/main.py:87-91,
+ * networks.py:667.  F1 is the U-Net output, fp32 NHWC [R, HW, C].  x_eul may be NULL. */
+int b200ns_heun_mid(const double* x_hat, const float* F1, float* net_in2, double* x_eul,
+                    int64_t R, int32_t C, int32_t HW, float c_skip, float c_out, double t_hat,
+                    double dt, float c_in_next, void* stream);
+
+/* Second-order correction + Tweedie x0 + uint8 quantise + per-channel integer pixel sums.
+ * F2 == NULL selects the last step (no correction; x_next = x_eul, denoised = D1).
+ * Outputs (each may be NULL): x_next fp64 [R,E]; x0_u8 uint8 [R,C,HW];
+ * chan_sums uint32 [R,4] (zeroed by this call, then accumulated with integer atomics).
+ * edm/main.py:88-96, 825-827; edm/scorers.py:37-46. */
+int b200ns_heun_post(const double* x_hat, const float* F1, const float* F2, double* x_next,
+                     uint8_t* x0_u8, uint32_t* chan_sums, int64_t R, int32_t C, int32_t HW,
+                     float c_skip1, float c_out1, double t_hat, double dt, float c_skip2,
+                     float c_out2, double t_next, void* stream);
+
+/* (x*127.5+128).clip(0,255) truncated to uint8.                      edm/main.py:827,869 */
+int b200ns_quantize_u8(const double* x, uint8_t* out, int64_t n, void* stream);
+
+/* Per-channel integer pixel sums of uint8 images [M,C,HW] -> uint32 [M,4] (C <= 4). */
+int b200ns_channel_sums_u8(const uint8_t* img, uint32_t* chan_sums, int64_t M, int32_t C,
+                           int32_t HW, void* stream);
+
+/* BrightnessScorer from integer sums: C==3 -> clamp(sum_c w_c*S_c/(255*HW),0,1) with
+ * w=(0.2126,0.7152,0.0722); otherwise the plain mean over C*HW.      edm/scorers.py:37-52,
+ * sd/scorers.py:66-67. */
+int b200ns_brightness_from_sums(const uint32_t* chan_sums, float* scores, int64_t M, int32_t C,
+                                int32_t HW, void* stream);
+
+/* First-maximal argmax over candidates: scores [N,b] -> idx [b] (int64, local index n) and the
+ * key (orderable_i32(score) << 32) | (0xFFFFFFFF - (idx_base + n)) [b] (may be NULL), a SIGNED
+ * int64 whose max picks the best score and, among equal scores, the lowest global index -- the
+ * same rule as torch.argmax -- so shards combine with ncclAllReduce(max, int64).
+ * edm/main.py:842. */
+int b200ns_argmax_first(const float* scores, int64_t N, int64_t b, int64_t idx_base, int64_t* idx,
+                        int64_t* packed_key, void* stream);
+
+/* dst[j,:] = src[idx[j], j, :] for src [N,b,E] fp64.                  edm/main.py:848-851 */
+int b200ns_gather_rows(const double* src, const int64_t* idx, double* dst, int64_t N, int64_t b,
+                       int64_t E, void* stream);
+
+/* ||dirs[r,:]||_2 in fp64 (deterministic block reduction).           edm/main.py:764,770 */
+int b200ns_direction_norms(const double* dirs, double* norms, int64_t R, int64_t E, void* stream);
+
+/* cand[r] = fresh_mask[r] ? fresh[r] : pivot[r % b] + (double)scale[r] * (dirs[r]/norms[r]).
+ * edm/main.py:749-800.  fresh may be NULL when no row is masked. */
+int b200ns_make_candidates(const double* pivot, const double* dirs, const double* norms,
+                           const float* scale, const uint8_t* fresh_mask, const double* fresh,
+                           double* cand, int64_t R, int64_t b, int64_t E, void* stream);
+
+/* ------------------------------------------------------------------ U-Net engine (plans)
+ * A plan is an ordered list of kernel launches with all shapes, pointers and TMA descriptors
+ * resolved at build time; b200ns_plan_run enqueues them on one stream.  It is the
+ * B200 replacement for DhariwalUNet.forward / SongUNet.forward
+ * (edm/training/networks.py:435-461, 320-363) and their leaves (:39-43, 68-90, 104-106,
+ * 115-118, 166-187). */
+typedef struct b200ns_plan b200ns_plan;
+b200ns_plan* b200ns_plan_create(void);
+void b200ns_plan_destroy(b200ns_plan* p);
+int b200ns_plan_size(const b200ns_plan* p);
+int b200ns_plan_run(b200ns_plan* p, void* stream);
+/* Run ops [first, last) only (per-layer parity tests and profiling). */
+int b200ns_plan_run_range(b200ns_plan* p, int first, int last, void* stream);
+
+typedef struct {
+  int32_t src;      /* 0 or 1: which activation tensor */
+  int32_t taps;     /* 1 (1x1 / plain GEMM) or 9 (3x3, pad 1) */
+  int32_t cstart;   /* first channel inside the source (multiple of 64) */
+  int32_t cblocks;  /* number of 64-channel blocks */
+} b200ns_kseg;
+
+/* Implicit-GEMM convolution / GEMM on tcgen05 tensor cores:
+ *   out[m, n] = out_scale * ( sum_k A[m,k]*W[n,k] + bias[n] + residual[m,n] )
+ * Replaces Conv2d.forward (networks.py:68-90) for kernel 3 and 1, the channel concat of
+ * the decoder (networks.py:458) via two activation sources, and the fused
+ * `conv1(x) + skip(orig)` of UNetBlock.forward (networks.py:177-179) via several K segments. */
+typedef struct {
+  const void* a_ptr[2];      /* bf16 NHWC [batch,H,W,a_channels[i]] */
+  int32_t a_channels[2];
+  int32_t n_seg;
+  b200ns_kseg seg[4];
+  int32_t batch, H, W;
+  const void* w_ptr;         /* bf16 [Npad, Ktot] */
+  int32_t N, Npad, Ktot;
+  const float* bias;         /* [N] or NULL */
+  const void* residual;      /* bf16 [M, ld_res] or NULL */
+  int32_t ld_res;
+  float out_scale;
+  void* out;                 /* bf16 or fp32 [M, ld_out] */
+  int32_t ld_out;
+  int32_t out_fp32;
+  /* qkv mode: columns >= vt_col_start are written transposed as V^T
+   * [batch*heads, 64, H*W] bf16 for the attention kernel (networks.py:182-184). */
+  void* vt_out;
+  int32_t vt_col_start;
+  int32_t heads;
+} b200ns_gemm_desc;
+int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d);
+
+/* GroupNorm statistics (networks.py:104-106): per-(sample, group) partial sums of x and x^2
+ * over up to two concatenated sources, written as fp64 [batch, splits, groups, 2].
+ * pre_add (fp32 [b_emb, C] or NULL) is added per channel first (networks.py:175). */
+typedef struct {
+  const void* x_ptr[2];
+  int32_t x_channels[2];
+  int32_t batch, HW, groups;
+  const float* pre_add;
+  int32_t ld_pre_add, b_emb;
+  double* partial;           /* fp64 [batch, splits, groups, 2] */
+  int32_t splits;
+} b200ns_gn_stats_desc;
+int b200ns_plan_add_gn_stats(b200ns_plan* p, const b200ns_gn_stats_desc* d);
+
+/* GroupNorm apply + optional FiLM + optional SiLU + optional 2x resample, bf16 -> bf16:
+ *   y = act( (x+pre_add - mean)*rstd*gamma + beta ) ; FiLM: y = act( shift + norm*(scale+1) )
+ * (networks.py:168, 173, 175, 182, 460).  resample: 0 none, 1 = 2x nearest up, 2 = 2x2 mean down
+ * (networks.py:64-65, 82-85).  raw_out (optional) receives the resampled UN-normalised input
+ * (the block's skip path, networks.py:159,178). */
+typedef struct {
+  const void* x_ptr[2];
+  int32_t x_channels[2];
+  int32_t batch, H, W, groups;
+  const double* partial;     /* from b200ns_plan_add_gn_stats */
+  int32_t splits;
+  float eps;
+  const float* gamma;
+  const float* beta;
+  const float* pre_add;
+  int32_t ld_pre_add;
+  const float* film_scale;   /* fp32 [b_emb, ld_film] or NULL */
+  const float* film_shift;
+  int32_t ld_film, b_emb;
+  int32_t silu;
+  int32_t resample;
+  void* out;                 /* bf16 [batch, H', W', C] */
+  void* raw_out;             /* bf16 [batch, H', W', C] or NULL */
+} b200ns_gn_apply_desc;
+int b200ns_plan_add_gn_apply(b200ns_plan* p, const b200ns_gn_apply_desc* d);
+
+/* Self-attention, head_dim 64 (networks.py:113-118, 182-185): for each (batch, head)
+ * O = softmax(Q K^T / sqrt(64)) V with fp32 softmax; Q,K come from qk [batch*L, ld_qk]
+ * (Q at column head*64, K at column k_col0 + head*64), V^T from vt [batch*heads, 64, L];
+ * output bf16 [batch*L, ld_out] at column head*64. */
+typedef struct {
+  const void* qk;
+  int32_t ld_qk, k_col0;
+  const void* vt;
+  void* out;
+  int32_t ld_out;
+  int32_t batch, heads, L;
+} b200ns_attn_desc;
+int b200ns_plan_add_attention(b200ns_plan* p, const b200ns_attn_desc* d);
+
+/* fp32 linear layers of the embedding network (networks.py:39-43, 437-447, 170):
+ *   out[r, n] = act( sum_k x[r,k]*W[n,k] + bias[n] + add[r,n] ), act: 0 none, 1 SiLU. */
+typedef struct {
+  const float* x;
+  int32_t rows, K, ld_x;
+  const float* w;            /* [N, K] */
+  const float* bias;         /* [N] or NULL */
+  const float* add;          /* [rows, ld_add] or NULL */
+  int32_t ld_add;
+  int32_t N;
+  int32_t act;
+  float* out;
+  int32_t ld_out;
+} b200ns_linear_desc;
+int b200ns_plan_add_linear(b200ns_plan* p, const b200ns_linear_desc* d);
+
+/* 3x3 im2col of the fp32 NCHW network input (Cin <= 7) into bf16 [batch*H*W, 64]
+ * (K index = (kh*3+kw)*Cin + c, zero padded) feeding the first conv (networks.py:410). */
+typedef struct {
+  const float* x;
+  void* out;
+  int32_t batch, C, H, W;
+} b200ns_im2col_desc;
+int b200ns_plan_add_im2col(b200ns_plan* p, const b200ns_im2col_desc* d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_NOISE_SEARCH_H */

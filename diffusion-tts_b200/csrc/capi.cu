@@ -99,7 +99,7 @@ int make_tmap(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims, 
 enum OpKind { OP_GEMM, OP_GN_STATS, OP_GN_APPLY, OP_ATTN, OP_LINEAR, OP_IM2COL };
 
 struct GemmOp {
-  CUtensorMap tmA0, tmA1, tmB;
+  CUtensorMap tmA[3], tmB;
   GemmArgs args;
   int BN;
   int grid;
@@ -161,7 +161,7 @@ int launch_gemm_t(const GemmOp& g, cudaStream_t st) {
     CK(cudaFuncSetAttribute(gemm_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  gemm_conv_kernel<BN><<<g.grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(g.tmA0, g.tmA1, g.tmB, g.args);
+  gemm_conv_kernel<BN><<<g.grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(g.tmA[0], g.tmA[1], g.tmA[2], g.tmB, g.args);
   CK_LAUNCH("gemm_conv_kernel");
   return 0;
 }
@@ -391,7 +391,7 @@ int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d) {
   for (int s = 0; s < d->n_seg; ++s) {
     const b200ns_kseg& sg = d->seg[s];
     if (sg.taps != 1 && sg.taps != 9) return fail("gemm: taps must be 1 or 9");
-    if (sg.src < 0 || sg.src > 1 || d->a_ptr[sg.src] == nullptr) return fail("gemm: bad segment source");
+    if (sg.src < 0 || sg.src > 2 || d->a_ptr[sg.src] == nullptr) return fail("gemm: bad segment source");
     if (sg.cstart % 64 || sg.cstart + sg.cblocks * 64 > d->a_channels[sg.src]) return fail("gemm: bad channel range");
     a.seg[s] = KSeg{sg.src, sg.taps, sg.cstart, sg.cblocks};
     nkb += sg.taps * sg.cblocks;
@@ -413,14 +413,14 @@ int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d) {
   if (d->residual != nullptr && (d->ld_res % 8)) return fail("gemm: ld_res must be a multiple of 8");
   if (d->vt_out != nullptr && (d->vt_col_start % 64)) return fail("gemm: vt_col_start must be a multiple of 64");
 
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 3; ++i) {
     const void* ptr = d->a_ptr[i] ? d->a_ptr[i] : d->a_ptr[0];
     const int ch = d->a_ptr[i] ? d->a_channels[i] : d->a_channels[0];
     if (ch % 64) return fail("gemm: activation channels must be a multiple of 64");
     const uint64_t dims[4] = {static_cast<uint64_t>(ch), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
                               static_cast<uint64_t>(d->batch)};
     const uint32_t box[4] = {64, static_cast<uint32_t>(W), static_cast<uint32_t>(tileH), static_cast<uint32_t>(tileN)};
-    int rc = make_tmap(i == 0 ? &g.tmA0 : &g.tmA1, ptr, 4, dims, box);
+    int rc = make_tmap(&g.tmA[i], ptr, 4, dims, box);
     if (rc) return rc;
   }
   {

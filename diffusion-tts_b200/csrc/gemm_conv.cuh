@@ -58,7 +58,7 @@ struct GemmCfg {
 template <int BN>
 __global__ void __launch_bounds__(192, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                 const __grid_constant__ CUtensorMap tmB, const GemmArgs a) {
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const GemmArgs a) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -79,6 +79,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA0);
     prefetch_tmap(&tmA1);
+    prefetch_tmap(&tmA2);
     prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -117,7 +118,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         int kb = 0;
         for (int s = 0; s < a.n_seg; ++s) {
           const KSeg sg = a.seg[s];
-          const CUtensorMap* tm = sg.src ? &tmA1 : &tmA0;
+          const CUtensorMap* tm = sg.src == 0 ? &tmA0 : (sg.src == 1 ? &tmA1 : &tmA2);
           for (int tap = 0; tap < sg.taps; ++tap) {
             const int dy = sg.taps == 9 ? tap / 3 - 1 : 0;
             const int dx = sg.taps == 9 ? tap % 3 - 1 : 0;

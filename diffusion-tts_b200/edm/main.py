@@ -1,0 +1,332 @@
+"""Drop-in for the reference's `edm/main.py` search driver on B200.
+
+Same names and signatures as the reference module (edm/main.py:27-55): `SamplingMethod`,
+`SamplingParams`, `generate_image_grid(...)`; same `precomputed_noise` protocol
+(edm/main.py:114-117, 734-737, 753-755, 791-792) and the same torch RNG call sequence, so a
+run without precomputed noise draws exactly the numbers the reference would draw on the same
+device and seed.  What changes is everything underneath: the candidate fan-out, the two
+batched denoiser calls, Tweedie x0, scoring and the argmax all run as hand-written sm_100a
+kernels (libb200ns.so), the loop never synchronises with the host, and the candidate
+dimension can be sharded over the ranks of a torch.distributed (NCCL) process group.
+
+Deviations from the reference, each deliberate (SURVEY.md hard part 11):
+  * no `os.environ["CUDA_VISIBLE_DEVICES"] = "0"` at import (edm/main.py:12) -- it would put
+    every torchrun rank on GPU 0;
+  * BEAM_SEARCH implements the evident intent (k = B beams, b = N noises per beam, stable
+    top-k with lowest-index tie rule); the reference branch raises AttributeError at :140;
+  * MCTS is not on the B200 path (out of scope) and raises NotImplementedError.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from enum import Enum, auto
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..denoiser import B200Denoiser, HeunStepper, StepTable, load_network
+from ..scorers import BrightnessScorer, Scorer
+
+
+class SamplingMethod(Enum):
+    MCTS = auto()
+    BEAM_SEARCH = auto()
+    ZERO_ORDER = auto()
+    NAIVE = auto()
+    REJECTION_SAMPLING = auto()
+    EPS_GREEDY = auto()
+
+
+@dataclass
+class SamplingParams:
+    B: int = 2
+    N: int = 4
+    K: int = 20
+    lambda_param: float = 0.15
+    eps: float = 0.4
+    S: int = 8
+    scorer: Scorer = field(default_factory=lambda: BrightnessScorer(dtype=torch.float32))
+
+
+@dataclass
+class SearchRecord:
+    """Optional trace of a run (device tensors; nothing here forces a sync)."""
+    scores: List[torch.Tensor] = field(default_factory=list)      # per round: [N, b] (global N)
+    indices: List[torch.Tensor] = field(default_factory=list)     # per round: [b] global candidate index
+    pivots: List[torch.Tensor] = field(default_factory=list)      # per step: committed noise
+    x_steps: List[torch.Tensor] = field(default_factory=list)     # per step: committed x_next (fp64)
+    final_image: Optional[torch.Tensor] = None
+    final_scores: Optional[torch.Tensor] = None
+    scored_candidates: int = 0
+
+
+@dataclass
+class Shard:
+    """Candidate sharding over a process group: rank r owns n in [r*N/G, (r+1)*N/G)."""
+    rank: int = 0
+    world: int = 1
+    group: Any = None
+
+    def bounds(self, N: int):
+        if N % self.world:
+            raise ValueError(f'N={N} must be divisible by the number of ranks ({self.world})')
+        per = N // self.world
+        return self.rank * per, (self.rank + 1) * per
+
+
+def _score_rows(scorer, stepper: HeunStepper, x_cur, eps, i, labels_rows, C, HW):
+    """Evaluate `eps` rows and score their Tweedie x0.  Fused path for scorers that take channel sums."""
+    if getattr(scorer, 'fused_sums', False):
+        _, _, sums = stepper.step(x_cur, eps, i, want_x_next=False, want_sums=True)
+        return scorer.score_from_sums(sums, C, HW)
+    _, u8, _ = stepper.step(x_cur, eps, i, want_x_next=False, want_u8=True, want_sums=False)
+    timesteps = torch.zeros(u8.shape[0], device=u8.device)               # edm/main.py:829
+    s = scorer(u8, labels_rows, timesteps)
+    return torch.as_tensor(s).to(device=u8.device, dtype=torch.float32).reshape(-1).contiguous()
+
+
+def _scale_table(num_steps: int, K: int, N: int, lam: float) -> torch.Tensor:
+    """fp32 scales of edm/main.py:776-779 for every (i,k,n): `ones * scale_seed * lambda_param`
+    (fp32, rounded after each product); hash() is this process's salted str hash, as in the reference."""
+    seeds = torch.tensor([[[hash(f"{i}_{k}_{n}") % 1000 / 1000.0 for n in range(N)] for k in range(K)]
+                          for i in range(num_steps)], dtype=torch.float64)
+    return (torch.ones_like(seeds, dtype=torch.float32) * seeds.to(torch.float32)) * torch.tensor(lam).to(torch.float32)
+
+
+@torch.no_grad()
+def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: SamplingParams, table: StepTable, *,
+                      precomputed_noise: Optional[Dict] = None, shard: Optional[Shard] = None, record: bool = False,
+                      norm_mode: str = 'kernel', scale_table: Optional[torch.Tensor] = None,
+                      teacher_x: Optional[List[torch.Tensor]] = None) -> (torch.Tensor, SearchRecord):
+    """ZERO_ORDER == EPS_GREEDY branch (edm/main.py:714-860)."""
+    device = net.device
+    shard = shard or Shard()
+    N, K, eps_p = params.N, params.K, params.eps
+    lo, hi = shard.bounds(N)
+    lam = params.lambda_param * np.sqrt(3 * 64 * 64)                      # :716
+    num_steps = table.num_steps
+    rec = SearchRecord()
+    x_next = latents.to(torch.float64) * table.t_steps[0]                 # :99
+    b = x_next.shape[0]
+    C, HW = x_next.shape[1], x_next.shape[2] * x_next.shape[3]
+    stepper = HeunStepper(net, table, class_labels)
+    scales = (scale_table if scale_table is not None else _scale_table(num_steps, K, N, lam)).to(device)
+    labels_rows = class_labels.repeat(hi - lo, 1) if class_labels is not None else None
+    pre = precomputed_noise
+    if pre is not None and 'pivot' in pre:                                # :724-727 (value unused, RNG untouched)
+        pass
+    else:
+        torch.randn_like(x_next)                                          # keeps the RNG stream aligned with :727
+    for i in range(num_steps):
+        x_cur = x_next
+        if pre is not None and f'pivot_{i}' in pre:                       # :734-737
+            pivot = pre[f'pivot_{i}'].to(device=device, dtype=torch.float64).contiguous()
+        else:
+            pivot = torch.randn_like(x_cur)
+        for k in range(K):
+            # ---- candidate construction (:749-800).  RNG calls mirror the reference one for one; the
+            # Bernoulli stays on the device (no host sync) unless precomputed noise covers only one of
+            # the two branches AND 0 < eps < 1, where the reference's RNG consumption is data dependent.
+            dirs, fresh, perturb = [], [], []
+            for n in range(N):
+                p_t = torch.rand(1, device=device) < (1 - eps_p)                  # :751
+                has_dir = pre is not None and i in pre and k < pre[i].shape[1] and n < pre[i].shape[2]
+                fkey = f'fresh_{i}_{k}_{n}'
+                has_fresh = pre is not None and fkey in pre
+                z_dir = pre[i][:, k, n].reshape(pivot.shape) if has_dir else None          # :755-759
+                z_fresh = pre[fkey] if has_fresh else None                                 # :791-792
+                if not has_dir and not has_fresh:
+                    z_dir = z_fresh = torch.randn_like(pivot)             # :767 / :795: one draw either way
+                elif not (has_dir and has_fresh):
+                    branch = True if eps_p <= 0 else (False if eps_p >= 1 else bool(p_t))
+                    if branch and not has_dir:
+                        z_dir = torch.randn_like(pivot)
+                    if not branch and not has_fresh:
+                        z_fresh = torch.randn_like(x_cur)
+                    z_dir = z_dir if z_dir is not None else z_fresh
+                    z_fresh = z_fresh if z_fresh is not None else z_dir
+                dirs.append(z_dir)
+                fresh.append(z_fresh)
+                perturb.append(p_t)
+            as64 = lambda ts: torch.stack([t.to(device=device, dtype=torch.float64) for t in ts]).reshape(
+                N * b, *pivot.shape[1:]).contiguous()
+            Z = as64(dirs)
+            ZF = Z if all(f is d for f, d in zip(fresh, dirs)) else as64(fresh)
+            fresh_mask = (~torch.cat(perturb)).to(torch.uint8).repeat_interleave(b).contiguous()
+            if norm_mode == 'torch':                                      # strict: the reference's own call (:764)
+                norms = torch.cat([torch.norm(z.to(device), p=2, dim=tuple(range(1, z.dim()))) for z in dirs]).to(torch.float64)
+            else:
+                norms = ops.direction_norms(Z)
+            sc = scales[i, k].repeat_interleave(b).contiguous()
+            cands = ops.make_candidates(pivot, Z, norms, sc, fresh_mask, ZF)      # [N*b, C, H, W]
+            # ---- evaluate this rank's slice: 2 NFE + Tweedie x0 + score (:809-838)
+            local = cands[lo * b:hi * b]
+            scores = _score_rows(params.scorer, stepper, x_cur, local, i, labels_rows, C, HW).reshape(hi - lo, b)
+            rec.scored_candidates += (hi - lo) * b
+            # ---- first-max argmax (+ cross-rank reduction of the packed key) (:842)
+            idx, key = ops.argmax_first(scores, idx_base=lo, want_key=True)
+            if shard.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(key, op=dist.ReduceOp.MAX, group=shard.group)
+                idx = 0xFFFFFFFF - (key & 0xFFFFFFFF)
+            else:
+                idx = idx + lo
+            pivot = ops.gather_rows(cands.reshape(N, b, *cands.shape[1:]), idx.contiguous())      # :848-857
+            if record:
+                rec.scores.append(scores)
+                rec.indices.append(idx)
+        # ---- commit (:860)
+        x_next, _, _ = stepper.step(x_cur, pivot, i, want_x_next=True)
+        if record:
+            rec.pivots.append(pivot)
+            rec.x_steps.append(x_next)
+        if teacher_x is not None:
+            x_next = teacher_x[i].to(device=device, dtype=torch.float64).contiguous()
+    return x_next, rec
+
+
+@torch.no_grad()
+def naive_search(net, latents, class_labels, table: StepTable, *, noise: Optional[List[torch.Tensor]] = None,
+                 record=False):
+    """NAIVE branch (edm/main.py:862-866)."""
+    rec = SearchRecord()
+    stepper = HeunStepper(net, table, class_labels)
+    x_next = latents.to(torch.float64) * table.t_steps[0]
+    for i in range(table.num_steps):
+        eps_i = noise[i].to(device=net.device, dtype=torch.float64).contiguous() if noise is not None else torch.randn_like(x_next)
+        x_next, _, _ = stepper.step(x_next, eps_i, i, want_x_next=True)
+        if record:
+            rec.x_steps.append(x_next)
+    return x_next, rec
+
+
+@torch.no_grad()
+def rejection_search(net, latents, class_labels, params: SamplingParams, table: StepTable, *,
+                     precomputed_noise: Optional[Dict] = None, record=False):
+    """REJECTION_SAMPLING branch (edm/main.py:101-137): rows are image-major (row = j*N + n)."""
+    N = params.N
+    rec = SearchRecord()
+    x_next = latents.to(torch.float64) * table.t_steps[0]
+    b = x_next.shape[0]
+    x = x_next.repeat_interleave(N, dim=0).contiguous()
+    labels = class_labels.repeat_interleave(N, dim=0) if class_labels is not None else None
+    stepper = HeunStepper(net, table, labels)
+    for i in range(table.num_steps):
+        if precomputed_noise is not None and i in precomputed_noise:
+            eps_i = precomputed_noise[i][:, :N].reshape(b * N, *x.shape[1:]).to(device=net.device, dtype=torch.float64).contiguous()
+        else:
+            eps_i = torch.randn_like(x)
+        x, _, _ = stepper.step(x, eps_i, i, want_x_next=True)
+    u8 = ops.quantize_u8(x)
+    scores = params.scorer(u8, labels, torch.zeros(u8.shape[0], device=u8.device))
+    scores = torch.as_tensor(scores).to(device=net.device, dtype=torch.float32).view(b, N)
+    rec.scored_candidates = b * N
+    best = ops.argmax_first(scores.t().contiguous())                      # [N,b] -> [b]
+    xr = x.view(b, N, *x.shape[1:]).transpose(0, 1).contiguous()          # [N,b,...]
+    x_next = ops.gather_rows(xr, best)
+    if record:
+        rec.scores.append(scores)
+        rec.indices.append(best)
+    return x_next, rec
+
+
+@torch.no_grad()
+def beam_search(net, latents, class_labels, params: SamplingParams, table: StepTable, *,
+                precomputed_noise: Optional[Dict] = None, record=False):
+    """BEAM_SEARCH, intended semantics of edm/main.py:138-404 (k = B beams, N noises per beam,
+    score the step's denoised x0, keep the top-k of k*N by score; ties -> lowest flat index
+    beam*N + n, as the SD twin's stable sort, pipeline_stable_diffusion.py:1132)."""
+    kb, N = params.B, params.N
+    rec = SearchRecord()
+    x0 = latents.to(torch.float64) * table.t_steps[0]
+    b = x0.shape[0]
+    C, HW = x0.shape[1], x0.shape[2] * x0.shape[3]
+    beams = x0.unsqueeze(0).repeat(kb, 1, 1, 1, 1).reshape(kb * b, *x0.shape[1:]).contiguous()     # [k*b]
+    stepper = HeunStepper(net, table, class_labels.repeat(kb, 1) if class_labels is not None else None)
+    labels_rows = class_labels.repeat(N * kb, 1) if class_labels is not None else None
+    for i in range(table.num_steps):
+        if precomputed_noise is not None and i in precomputed_noise:      # [b, k, N, C, H, W]
+            eps_i = precomputed_noise[i][:, :kb, :N].permute(2, 1, 0, 3, 4, 5).reshape(N * kb * b, *x0.shape[1:])
+            eps_i = eps_i.to(device=net.device, dtype=torch.float64).contiguous()
+        else:
+            eps_i = torch.randn(N * kb * b, *x0.shape[1:], dtype=torch.float64, device=net.device)
+        getu8 = not getattr(params.scorer, 'fused_sums', False)
+        x_cand, u8, sums = stepper.step(beams, eps_i, i, want_x_next=True, want_u8=getu8, want_sums=not getu8)
+        if getu8:
+            s = params.scorer(u8, labels_rows, torch.zeros(u8.shape[0], device=u8.device))
+            s = torch.as_tensor(s).to(device=net.device, dtype=torch.float32)
+        else:
+            s = params.scorer.score_from_sums(sums, C, HW)
+        rec.scored_candidates += N * kb * b
+        flat = s.reshape(N, kb, b).permute(2, 1, 0).reshape(b, kb * N)     # [b, beam*N + n]
+        order = torch.sort(flat, dim=1, descending=True, stable=True).indices[:, :kb]         # [b, k]
+        beam_i, n_i = order // N, order % N
+        xc = x_cand.reshape(N, kb, b, *x0.shape[1:])
+        j = torch.arange(b, device=net.device).unsqueeze(1).expand(b, kb)
+        beams = xc[n_i, beam_i, j].permute(1, 0, 2, 3, 4).reshape(kb * b, *x0.shape[1:]).contiguous()
+        if record:
+            rec.scores.append(flat)
+            rec.indices.append(order)
+    x_next = beams.reshape(kb, b, *x0.shape[1:])[0].contiguous()          # best beam (:404)
+    return x_next, rec
+
+
+def generate_image_grid(
+    network_pkl, dest_path, latents, class_labels,
+    seed=0, gridw=8, gridh=8, device=torch.device('cuda'),
+    num_steps=18, sigma_min=0.002, sigma_max=80, rho=7,
+    S_churn=0, S_min=0, S_max=float('inf'), S_noise=1,
+    sampling_method: SamplingMethod = SamplingMethod.NAIVE,
+    sampling_params: Optional[Dict[str, Any]] = None,
+    precomputed_noise: Optional[Dict[int, torch.Tensor]] = None,
+    shard: Optional[Shard] = None, record: bool = False,
+):
+    """Same contract as the reference's generate_image_grid (edm/main.py:47-886).  Returns None
+    like the reference unless `record=True`, in which case the SearchRecord is returned."""
+    device = torch.device(device)
+    if device.type != 'cuda':
+        raise RuntimeError('the B200 path needs a CUDA device; there is no CPU fallback')
+    batch_size = gridw * gridh
+    torch.manual_seed(seed)
+    if sampling_params is None:
+        sampling_params = {}
+    method_params = SamplingParams(**sampling_params)                     # TypeError on unknown keys, like :64
+    print(f'Using sampling method: {sampling_method.name}')
+    print(f'Loading network from "{network_pkl}"...')
+    net = load_network(network_pkl, device)
+    latents = latents.to(device)
+    if class_labels is not None:
+        class_labels = class_labels.to(device)
+    table = StepTable(net, device, num_steps, sigma_min, sigma_max, rho, S_churn, S_min, S_max, S_noise)
+    if sampling_method == SamplingMethod.REJECTION_SAMPLING:
+        x_next, rec = rejection_search(net, latents, class_labels, method_params, table,
+                                       precomputed_noise=precomputed_noise, record=record)
+    elif sampling_method == SamplingMethod.BEAM_SEARCH:
+        x_next, rec = beam_search(net, latents, class_labels, method_params, table,
+                                  precomputed_noise=precomputed_noise, record=record)
+    elif sampling_method == SamplingMethod.MCTS:
+        raise NotImplementedError('MCTS is not part of the B200 hot path (SURVEY.md 8 f4)')
+    elif sampling_method in (SamplingMethod.ZERO_ORDER, SamplingMethod.EPS_GREEDY):
+        print(f"Zero-Order parameters: lambda={method_params.lambda_param}, N={method_params.N}, "
+              f"K={method_params.K}, eps={method_params.eps}")
+        x_next, rec = eps_greedy_search(net, latents, class_labels, method_params, table,
+                                        precomputed_noise=precomputed_noise, shard=shard, record=record)
+    else:
+        x_next, rec = naive_search(net, latents, class_labels, table, record=record)
+
+    image = ops.quantize_u8(x_next.contiguous())                          # :869
+    timesteps = torch.zeros(image.shape[0], device=device)
+    scores = method_params.scorer(image.clone(), class_labels, timesteps)
+    avg_score = torch.as_tensor(scores).float().mean().item()
+    print(f'Average score: {avg_score}')
+    rec.final_image, rec.final_scores = image, scores
+    if dest_path is not None and (shard is None or shard.rank == 0):
+        import PIL.Image
+        print(f'Saving image grid to "{dest_path}"...')
+        grid = image.reshape(gridh, gridw, *image.shape[1:]).permute(0, 3, 1, 4, 2)
+        grid = grid.reshape(gridh * net.img_resolution, gridw * net.img_resolution, net.img_channels)
+        PIL.Image.fromarray(grid.cpu().numpy(), 'RGB').save(dest_path)
+    print('Done.')
+    return rec if record else None

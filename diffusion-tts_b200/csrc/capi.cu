@@ -118,6 +118,7 @@ struct AttnOp {
   CUtensorMap tmQ, tmK, tmV;
   AttnArgs args;
   int KT;
+  int vrow;
   dim3 grid;
 };
 struct LinearOp {
@@ -176,15 +177,15 @@ int launch_gemm(const GemmOp& g, cudaStream_t st) {
   return fail("bad BN");
 }
 
-template <int KT>
+template <int KT, bool VROW>
 int launch_attn_t(const AttnOp& o, cudaStream_t st) {
   using Cfg = AttnCfg<KT>;
   static bool attr_set = false;
   if (!attr_set) {
-    CK(cudaFuncSetAttribute(attention_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(attention_kernel<KT, VROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  attention_kernel<KT><<<o.grid, 128, Cfg::SMEM_BYTES, st>>>(o.tmQ, o.tmK, o.tmV, o.args);
+  attention_kernel<KT, VROW><<<o.grid, 128, Cfg::SMEM_BYTES, st>>>(o.tmQ, o.tmK, o.tmV, o.args);
   CK_LAUNCH("attention_kernel");
   return 0;
 }
@@ -200,7 +201,9 @@ int run_op(const Op& op, cudaStream_t st) {
       gn_apply_kernel<<<op.gna.grid, op.gna.threads, 0, st>>>(op.gna.args);
       CK_LAUNCH("gn_apply_kernel");
       return 0;
-    case OP_ATTN: return op.attn.KT == 128 ? launch_attn_t<128>(op.attn, st) : launch_attn_t<64>(op.attn, st);
+    case OP_ATTN:
+      if (op.attn.vrow) return op.attn.KT == 128 ? launch_attn_t<128, true>(op.attn, st) : launch_attn_t<64, true>(op.attn, st);
+      return op.attn.KT == 128 ? launch_attn_t<128, false>(op.attn, st) : launch_attn_t<64, false>(op.attn, st);
     case OP_LINEAR:
       linear_kernel<<<op.lin.grid, 256, 0, st>>>(op.lin.args);
       CK_LAUNCH("linear_kernel");
@@ -498,9 +501,12 @@ int b200ns_plan_add_gn_apply(b200ns_plan* p, const b200ns_gn_apply_desc* d) {
   const int VC = a.C / 8;
   a.PY = 256 / VC;
   if (a.PY < 1) a.PY = 1;
-  a.ITER = 4;
   op.gna.threads = VC * a.PY;
   const int dom = d->resample == 2 ? (d->H / 2) * (d->W / 2) : d->H * d->W;
+  // pixels per thread: as many as keep >= ~4 CTAs per SM in flight (fewer prologues per byte), 4..32
+  a.ITER = 32;
+  while (a.ITER > 4 && static_cast<long long>((dom + a.PY * a.ITER - 1) / (a.PY * a.ITER)) * d->batch < 4LL * num_sms())
+    a.ITER /= 2;
   const int per_cta = a.PY * a.ITER;
   op.gna.grid = dim3((dom + per_cta - 1) / per_cta, d->batch);
   p->ops.push_back(op);
@@ -528,7 +534,14 @@ int b200ns_plan_add_attention(b200ns_plan* p, const b200ns_attn_desc* d) {
     rc = make_tmap(&o.tmK, d->qk, 2, dims, boxk);
     if (rc) return rc;
   }
-  {
+  o.vrow = d->vt == nullptr ? 1 : 0;
+  o.args.v_col0 = d->v_col0;
+  if (o.vrow) {       // V row-major inside the qkv matrix: box [KT keys][64 d]
+    const uint64_t dims[2] = {static_cast<uint64_t>(d->ld_qk), M};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(o.KT)};
+    int rc = make_tmap(&o.tmV, d->qk, 2, dims, box);
+    if (rc) return rc;
+  } else {
     const uint64_t dims[2] = {static_cast<uint64_t>(d->L), static_cast<uint64_t>(d->batch) * d->heads * 64};
     const uint32_t box[2] = {64, 64};
     int rc = make_tmap(&o.tmV, d->vt, 2, dims, box);

@@ -137,13 +137,18 @@ DEVINL uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 // Instruction descriptor for kind::f16: D fp32, A/B bf16, both K-major, M x N tile.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
-         (static_cast<uint32_t>(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool b_mn_major = false) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn_major ? (1u << 16) : 0u) |
+         (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 // ---------------------------------------------------------------- misc
-DEVINL float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+DEVINL float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+DEVINL float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 DEVINL uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);

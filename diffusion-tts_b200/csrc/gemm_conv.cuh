@@ -10,8 +10,9 @@
 // one accumulator).  Accumulators live in TMEM (double buffered), so the epilogue of tile i
 // overlaps the main loop of tile i+1.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner),
-// warps 2..5 = epilogue (TMEM -> registers -> global).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner),
+// warps 2..9 = epilogue (TMEM -> registers -> global): two warps per TMEM lane quarter, each taking
+// half of the tile's columns, residual rows prefetched one chunk ahead.
 // Replaces Conv2d.forward, edm/training/networks.py:68-90 (kernel 3 / 1, no resample).
 #pragma once
 #include "common.cuh"
@@ -51,12 +52,13 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 192 ? 5 : 6);
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int THREADS = 192;
+  static constexpr int STAGING_BYTES = 8 * 2048;   // per-epilogue-warp 32 rows x 64 B transpose buffer
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int THREADS = 320;
 };
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const GemmArgs a) {
   using Cfg = GemmCfg<BN>;
@@ -65,7 +67,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* smem_stg = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + Cfg::STAGING_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
@@ -87,7 +90,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], 8);
     }
     fence_barrier_init();
   }
@@ -172,21 +175,42 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;       // which half of the tile's columns
     const int row = q * 32 + lane;          // row inside the 128-row tile
+    constexpr int CH = (BN % 32 == 0) ? 32 : 16;
+    constexpr int NCH = BN / CH;
+    constexpr int CH_PER_HALF = (NCH + 1) / 2;
+    const int ch_begin = half * CH_PER_HALF;
+    const int ch_end = (ch_begin + CH_PER_HALF < NCH) ? ch_begin + CH_PER_HALF : NCH;
+    const bool has_res = a.residual != nullptr;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile / a.n_tiles, nt = tile % a.n_tiles;
       const int m = mt * 128 + row;
       const bool m_ok = m < a.M;
+      uint4 rnext[CH / 8];
+      auto load_res = [&](int ch, uint4 (&dst)[CH / 8]) {
+        const int nb = nt * BN + ch * CH;
+        if (has_res && m_ok && nb + CH <= a.N) {
+          const uint4* rp = reinterpret_cast<const uint4*>(a.residual + static_cast<size_t>(m) * a.ld_res + nb);
+#pragma unroll
+          for (int j = 0; j < CH / 8; ++j) dst[j] = __ldg(rp + j);
+        }
+      };
+      if (ch_begin < ch_end) load_res(ch_begin, rnext);     // in flight while the main loop still runs
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-      constexpr int CH = (BN % 32 == 0) ? 32 : 16;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += CH) {
+      for (int ch = ch_begin; ch < ch_end; ++ch) {
+        const int c0 = ch * CH;
+        uint4 rcur[CH / 8];
+#pragma unroll
+        for (int j = 0; j < CH / 8; ++j) rcur[j] = rnext[j];
+        if (ch + 1 < ch_end) load_res(ch + 1, rnext);
         float v[CH];
         if constexpr (CH == 32) {
           uint32_t r[32];
@@ -202,18 +226,25 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
         }
         const int n_base = nt * BN + c0;
-        if (!m_ok || n_base >= a.N) continue;
+        if (n_base >= a.N) continue;                       // warp-uniform
         const bool full = (n_base + CH <= a.N);
         if (a.bias != nullptr) {
+          if (full) {      // warp-uniform address: 16-byte broadcast loads
 #pragma unroll
-          for (int j = 0; j < CH; ++j)
-            if (full || n_base + j < a.N) v[j] += __ldg(a.bias + n_base + j);
+            for (int j = 0; j < CH / 4; ++j) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + n_base) + j);
+              v[4 * j + 0] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (n_base + j < a.N) v[j] += __ldg(a.bias + n_base + j);
+          }
         }
-        if (a.residual != nullptr && full) {
-          const uint4* rp = reinterpret_cast<const uint4*>(a.residual + static_cast<size_t>(m) * a.ld_res + n_base);
+        if (has_res && full) {
 #pragma unroll
           for (int j = 0; j < CH / 8; ++j) {
-            const uint4 u = __ldg(rp + j);
+            const uint4 u = rcur[j];
             float2 f;
             f = unpack_bf16(u.x); v[8 * j + 0] += f.x; v[8 * j + 1] += f.y;
             f = unpack_bf16(u.y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
@@ -225,11 +256,14 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         for (int j = 0; j < CH; ++j) v[j] *= a.out_scale;
 
         if (a.out_fp32) {
-          float* op = reinterpret_cast<float*>(a.out) + static_cast<size_t>(m) * a.ld_out + n_base;
+          if (m_ok) {
+            float* op = reinterpret_cast<float*>(a.out) + static_cast<size_t>(m) * a.ld_out + n_base;
 #pragma unroll
-          for (int j = 0; j < CH; ++j)
-            if (full || n_base + j < a.N) op[j] = v[j];
+            for (int j = 0; j < CH; ++j)
+              if (full || n_base + j < a.N) op[j] = v[j];
+          }
         } else if (a.vt_out != nullptr && n_base >= a.vt_col_start) {
+          if (!m_ok) continue;
           // V^T[(batch*heads + head), d, p] : consecutive lanes -> consecutive pixels p
           const int vc = n_base - a.vt_col_start;
           const int head = vc >> 6, d0 = vc & 63;
@@ -237,19 +271,31 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           __nv_bfloat16* vp = a.vt_out + (static_cast<size_t>(bi * a.heads + head) * 64 + d0) * a.L + p;
 #pragma unroll
           for (int j = 0; j < CH; ++j) vp[static_cast<size_t>(j) * a.L] = __float2bfloat16(v[j]);
-        } else if (full) {
-          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) +
-                                               static_cast<size_t>(m) * a.ld_out + n_base);
+        } else if (full && CH == 32) {
+          // transpose through a per-warp smem buffer so that 4 consecutive lanes write one row's 64 B:
+          // every global store instruction covers 8 rows x 64 contiguous bytes (full 32 B sectors)
+          uint8_t* stg = smem_stg + (warp - 2) * 2048;
+          const int sw = (lane >> 1) & 3;
 #pragma unroll
-          for (int j = 0; j < CH / 8; ++j) {
+          for (int j = 0; j < 4; ++j) {
             uint4 u;
             u.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
             u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
             u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
             u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-            op[j] = u;
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ sw) << 4)) = u;
           }
-        } else {
+          __syncwarp();
+          __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(a.out) + n_base + (lane & 3) * 8;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = i * 8 + (lane >> 2);
+            const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4));
+            const int mrow = mt * 128 + q * 32 + rr;
+            if (mrow < a.M) *reinterpret_cast<uint4*>(obase + static_cast<size_t>(mrow) * a.ld_out) = val;
+          }
+          __syncwarp();
+        } else if (m_ok) {
           __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + static_cast<size_t>(m) * a.ld_out + n_base;
           for (int j = 0; j < CH; ++j)
             if (n_base + j < a.N) op[j] = __float2bfloat16(v[j]);

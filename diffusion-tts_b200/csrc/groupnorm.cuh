@@ -30,6 +30,14 @@ DEVINL void load8(const __nv_bfloat16* p, float (&f)[8]) {
   t = unpack_bf16(u.z); f[4] = t.x; f[5] = t.y;
   t = unpack_bf16(u.w); f[6] = t.x; f[7] = t.y;
 }
+DEVINL uint4 load_raw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+DEVINL void unpack8(const uint4& u, float (&f)[8]) {
+  float2 t;
+  t = unpack_bf16(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16(u.w); f[6] = t.x; f[7] = t.y;
+}
 DEVINL void store8(__nv_bfloat16* p, const float (&f)[8]) {
   uint4 u;
   u.x = pack_bf16(f[0], f[1]);
@@ -40,7 +48,7 @@ DEVINL void store8(__nv_bfloat16* p, const float (&f)[8]) {
 }
 
 // grid (splits, batch); block = (C/8) * PY threads (<= 256)
-__global__ void gn_stats_kernel(const GnStatsArgs a) {
+__global__ void __launch_bounds__(256, 4) gn_stats_kernel(const GnStatsArgs a) {
   __shared__ float s_sum[2048];
   __shared__ float s_sq[2048];
   const int VC = a.C >> 3;
@@ -65,7 +73,26 @@ __global__ void gn_stats_kernel(const GnStatsArgs a) {
     for (int j = 0; j < 8; ++j) pa[j] = pp[j];
   }
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ss[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int p = py; p < ppb; p += a.PY) {
+  // 4 independent 16-byte loads in flight per thread; the pixel order per thread is fixed
+  // (p = py, py+PY, ...), so the sums do not depend on batch size or position.
+  int p = py;
+  for (; p + 7 * a.PY < ppb; p += 8 * a.PY) {
+    uint4 raw[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) raw[u] = load_raw(src + static_cast<size_t>(p + u * a.PY) * ld);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      float f[8];
+      unpack8(raw[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v = f[j] + pa[j];
+        s[j] += v;
+        ss[j] += v * v;
+      }
+    }
+  }
+  for (; p < ppb; p += a.PY) {
     float f[8];
     load8(src + static_cast<size_t>(p) * ld, f);
 #pragma unroll
@@ -81,7 +108,7 @@ __global__ void gn_stats_kernel(const GnStatsArgs a) {
     s_sq[py * a.C + c + j] = ss[j];
   }
   __syncthreads();
-  // one thread per group: fixed-order fp64 reduction over (py, channel-in-group)
+  // one thread per group: fixed-order fp64 reduction over (channel-in-group, py)
   for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
     double ds = 0.0, dq = 0.0;
     for (int cc = g * a.cpg; cc < (g + 1) * a.cpg; ++cc)
@@ -117,7 +144,7 @@ struct GnApplyArgs {
 };
 
 // grid (pixel chunks, batch); block = (C/8) * PY threads
-__global__ void gn_apply_kernel(const GnApplyArgs a) {
+__global__ void __launch_bounds__(256, 3) gn_apply_kernel(const GnApplyArgs a) {
   __shared__ float s_mean[64];
   __shared__ float s_rstd[64];
   const int VC = a.C >> 3;
@@ -182,25 +209,25 @@ __global__ void gn_apply_kernel(const GnApplyArgs a) {
   const int dom = a.resample == 2 ? outH * outW : HW;      // loop domain
   const int p_begin = blockIdx.x * a.PY * a.ITER + py;
 
-  for (int it = 0; it < a.ITER; ++it) {
-    const int p = p_begin + it * a.PY;
-    if (p >= dom) break;
-    if (a.resample == 2) {
+  if (a.resample == 2) {
+    for (int it = 0; it < a.ITER; ++it) {
+      const int p = p_begin + it * a.PY;
+      if (p >= dom) break;
       const int oy = p / outW, ox = p - oy * outW;
+      float f[4][8];
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        load8(src + static_cast<size_t>((2 * oy + (t >> 1)) * a.W + 2 * ox + (t & 1)) * ld, f[t]);
       float accv[8] = {0, 0, 0, 0, 0, 0, 0, 0}, accr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int iy = 2 * oy + (t >> 1), ix = 2 * ox + (t & 1);
-        float f[8];
-        load8(src + static_cast<size_t>(iy * a.W + ix) * ld, f);
+      for (int t = 0; t < 4; ++t)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float v = f[j] * ka[j] + kb[j];
+          float v = f[t][j] * ka[j] + kb[j];
           if (a.silu) v = silu_f(v);
           accv[j] += v;
-          accr[j] += f[j];
+          accr[j] += f[t][j];
         }
-      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         accv[j] *= 0.25f;
@@ -208,24 +235,38 @@ __global__ void gn_apply_kernel(const GnApplyArgs a) {
       }
       store8(a.out + out_base + static_cast<size_t>(p) * a.C, accv);
       if (a.raw_out != nullptr) store8(a.raw_out + out_base + static_cast<size_t>(p) * a.C, accr);
-    } else {
-      float f[8], v[8];
-      load8(src + static_cast<size_t>(p) * ld, f);
+    }
+  } else {
+    for (int it0 = 0; it0 < a.ITER; it0 += 4) {
+      uint4 raw[4];
+      int pp[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        v[j] = f[j] * ka[j] + kb[j];
-        if (a.silu) v[j] = silu_f(v[j]);
+      for (int u = 0; u < 4; ++u) {
+        pp[u] = p_begin + (it0 + u) * a.PY;
+        if (pp[u] < dom) raw[u] = load_raw(src + static_cast<size_t>(pp[u]) * ld);
       }
-      if (a.resample == 0) {
-        store8(a.out + out_base + static_cast<size_t>(p) * a.C, v);
-        if (a.raw_out != nullptr) store8(a.raw_out + out_base + static_cast<size_t>(p) * a.C, f);
-      } else {
-        const int iy = p / a.W, ix = p - iy * a.W;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const size_t op = static_cast<size_t>((2 * iy + (t >> 1)) * outW + 2 * ix + (t & 1)) * a.C;
-          store8(a.out + out_base + op, v);
-          if (a.raw_out != nullptr) store8(a.raw_out + out_base + op, f);
+      for (int u = 0; u < 4; ++u) {
+        if (pp[u] >= dom) continue;
+        float f[8], v[8];
+        unpack8(raw[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j] = f[j] * ka[j] + kb[j];
+          if (a.silu) v[j] = silu_f(v[j]);
+        }
+        if (a.resample == 0) {
+          store8(a.out + out_base + static_cast<size_t>(pp[u]) * a.C, v);
+          if (a.raw_out != nullptr)
+            *reinterpret_cast<uint4*>(a.raw_out + out_base + static_cast<size_t>(pp[u]) * a.C) = raw[u];
+        } else {
+          const int iy = pp[u] / a.W, ix = pp[u] - iy * a.W;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const size_t op = static_cast<size_t>((2 * iy + (t >> 1)) * outW + 2 * ix + (t & 1)) * a.C;
+            store8(a.out + out_base + op, v);
+            if (a.raw_out != nullptr) *reinterpret_cast<uint4*>(a.raw_out + out_base + op) = raw[u];
+          }
         }
       }
     }

@@ -76,15 +76,16 @@ class Shard:
         return self.rank * per, (self.rank + 1) * per
 
 
-def _score_rows(scorer, stepper: HeunStepper, x_cur, eps, i, labels_rows, C, HW):
-    """Evaluate `eps` rows and score their Tweedie x0.  Fused path for scorers that take channel sums."""
+def _score_rows(scorer, stepper: HeunStepper, x_cur, eps, i, labels_rows, C, HW, want_x_next=False):
+    """Evaluate `eps` rows and score their Tweedie x0 -> (scores [R], x_next or None).
+    Fused path for scorers that take channel sums (no uint8 image is materialised)."""
     if getattr(scorer, 'fused_sums', False):
-        _, _, sums = stepper.step(x_cur, eps, i, want_x_next=False, want_sums=True)
-        return scorer.score_from_sums(sums, C, HW)
-    _, u8, _ = stepper.step(x_cur, eps, i, want_x_next=False, want_u8=True, want_sums=False)
+        x_next, _, sums = stepper.step(x_cur, eps, i, want_x_next=want_x_next, want_sums=True)
+        return scorer.score_from_sums(sums, C, HW), x_next
+    x_next, u8, _ = stepper.step(x_cur, eps, i, want_x_next=want_x_next, want_u8=True, want_sums=False)
     timesteps = torch.zeros(u8.shape[0], device=u8.device)               # edm/main.py:829
     s = scorer(u8, labels_rows, timesteps)
-    return torch.as_tensor(s).to(device=u8.device, dtype=torch.float32).reshape(-1).contiguous()
+    return torch.as_tensor(s).to(device=u8.device, dtype=torch.float32).reshape(-1).contiguous(), x_next
 
 
 def _scale_table(num_steps: int, K: int, N: int, lam: float) -> torch.Tensor:
@@ -100,14 +101,23 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
                       precomputed_noise: Optional[Dict] = None, shard: Optional[Shard] = None, record: bool = False,
                       norm_mode: str = 'kernel', scale_table: Optional[torch.Tensor] = None,
                       teacher_x: Optional[List[torch.Tensor]] = None, step_indices: Optional[List[int]] = None,
-                      x_init: Optional[torch.Tensor] = None, on_step=None) -> (torch.Tensor, SearchRecord):
+                      x_init: Optional[torch.Tensor] = None, on_step=None,
+                      commit: str = 'reuse') -> (torch.Tensor, SearchRecord):
     """ZERO_ORDER == EPS_GREEDY branch (edm/main.py:714-860).
 
     Extras over the reference (all optional): `shard` (candidate sharding over ranks), `record`,
     `norm_mode` ('kernel' = in-kernel fp64 block reduction, 'torch' = the reference's own torch.norm
     calls), `teacher_x` (force the committed state per step; parity tests), `step_indices` / `x_init`
     (run a sub-sequence of steps from a given state; benchmarks), `on_step(i, x_next, idx, scores)`
-    (called after every committed step, e.g. to read results back to the host)."""
+    (called after every committed step, e.g. to read results back to the host).
+
+    `commit`: the reference re-runs `step` on the winning noise at batch b (edm/main.py:860).  All kernels
+    here are batch-size and batch-position invariant (fixed reduction orders), so the winner's x_next from
+    the last candidate round is bit-identical to that recomputation ('reuse', default; asserted by
+    tests/test_search_gpu.py::test_commit_reuse_is_bit_identical); 'recompute' runs the two extra network
+    evaluations like the reference."""
+    if commit not in ('reuse', 'recompute'):
+        raise ValueError("commit must be 'reuse' or 'recompute'")
     device = net.device
     shard = shard or Shard()
     N, K, eps_p = params.N, params.K, params.eps
@@ -183,7 +193,9 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
             cands = ops.make_candidates(pivot, Z, norms, sc, fresh_mask, ZF)      # [N*b, C, H, W]
             # ---- evaluate this rank's slice: 2 NFE + Tweedie x0 + score (:809-838)
             local = cands[lo * b:hi * b]
-            scores = _score_rows(params.scorer, stepper, x_cur, local, i, labels_rows, C, HW).reshape(hi - lo, b)
+            want_x = commit == 'reuse' and k == K - 1
+            scores, x_cands = _score_rows(params.scorer, stepper, x_cur, local, i, labels_rows, C, HW, want_x)
+            scores = scores.reshape(hi - lo, b)
             rec.scored_candidates += (hi - lo) * b
             # ---- first-max argmax (+ cross-rank reduction of the packed key) (:842)
             idx, key = ops.argmax_first(scores, idx_base=lo, want_key=True)
@@ -198,7 +210,18 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
                 rec.scores.append(scores)
                 rec.indices.append(idx)
         # ---- commit (:860)
-        x_next, _, _ = stepper.step(x_cur, pivot, i, want_x_next=True)
+        if commit == 'reuse' and K > 0:
+            xc = x_cands.reshape(hi - lo, b, *x_cands.shape[1:])
+            if shard.world > 1:       # only the owner of the winner contributes; x + 0 is exact
+                import torch.distributed as dist
+                owned = ((idx >= lo) & (idx < hi))
+                x_next = ops.gather_rows(xc, (idx - lo).clamp(0, hi - lo - 1).contiguous())
+                x_next = x_next * owned.to(torch.float64).view(b, *([1] * (x_next.dim() - 1)))
+                dist.all_reduce(x_next, op=dist.ReduceOp.SUM, group=shard.group)
+            else:
+                x_next = ops.gather_rows(xc, idx.contiguous())
+        else:
+            x_next, _, _ = stepper.step(x_cur, pivot, i, want_x_next=True)
         if record:
             rec.pivots.append(pivot)
             rec.x_steps.append(x_next)

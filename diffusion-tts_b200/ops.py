@@ -278,11 +278,14 @@ class Plan:
         self.kinds.append('gn_apply')
         self.flops.append(0.0)
 
-    def add_attention(self, qk: torch.Tensor, k_col0: int, vt: torch.Tensor, out: torch.Tensor, batch: int, heads: int,
-                      Lseq: int, label='attention'):
+    def add_attention(self, qk: torch.Tensor, k_col0: int, vt: Optional[torch.Tensor], out: torch.Tensor, batch: int,
+                      heads: int, Lseq: int, label='attention', v_col0: int = 0):
+        """qk: [batch*L, ld] with Q at col head*64, K at k_col0 + head*64; V either transposed in `vt`
+        ([batch*heads*64, L]) or (vt=None) row-major in `qk` at v_col0 + head*64."""
         d = L.AttnDesc()
         d.qk, d.ld_qk, d.k_col0 = L.ptr(_c(qk, torch.bfloat16)), qk.shape[-1], k_col0
-        d.vt = L.ptr(_c(vt, torch.bfloat16))
+        d.vt = L.ptr(vt)
+        d.v_col0 = v_col0
         d.out, d.ld_out = L.ptr(_c(out, torch.bfloat16)), out.shape[-1]
         d.batch, d.heads, d.L = batch, heads, Lseq
         self._k(qk, vt, out)

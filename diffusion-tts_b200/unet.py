@@ -10,7 +10,7 @@ Data flow per UNetBlock (networks.py:166-187), all activations bf16 NHWC:
   tcgen05 conv3x3(a0) + bias                                    -> h
   gn_stats(h) -> gn_apply(norm1, FiLM scale/shift, SiLU)        -> a1
   tcgen05 [conv3x3(a1) | conv1x1(orig)] + bias (+orig) * skip_scale -> out   (one accumulator)
-  [attention] gn_stats/apply(norm2) -> tcgen05 qkv (Q|K row-major, V^T) -> flash attention
+  [attention] gn_stats/apply(norm2) -> tcgen05 qkv ([Q|K|V] row-major) -> flash attention (V as MN-major operand)
               -> tcgen05 proj + bias + out, * skip_scale
 The embedding MLP and all per-block `affine` layers depend only on (sigma, label), i.e. are
 identical for all N candidates of an image: they run once per distinct image (b_emb rows).
@@ -163,12 +163,11 @@ class ForwardPlan:
     def _act(self, key: str, B, H, W, C) -> torch.Tensor:
         return self._buf(key, B * H * W * C)[:B * H * W * C].view(B, H, W, C)
 
-    def _splits(self, HW: int) -> int:
-        want = max(1, (2 * 148 + self.B - 1) // self.B)
-        s = 1
-        while s * 2 <= want and HW % (s * 2) == 0 and HW // (s * 2) >= 16:
-            s *= 2
-        return s
+    @staticmethod
+    def _splits(HW: int) -> int:
+        """GroupNorm partial-sum splits: a function of the image size ONLY, so the reduction order -- and
+        with it every bit of the network output -- is independent of batch size and batch position."""
+        return max(1, min(16, HW // 64))
 
     def _gn(self, xs, C, H, W, gamma, beta, out, *, silu=True, resample=0, raw_out=None, film=None, pre_add=None,
             label=''):
@@ -297,12 +296,13 @@ class ForwardPlan:
             raise NotImplementedError(f'{n}: attention head_dim {cout // heads} (only 64 is implemented)')
         a2 = self._act('a1', B, Ho, Ho, cout)
         self._gn([out], cout, Ho, Ho, W_[f'{n}.norm2.weight'], W_[f'{n}.norm2.bias'], a2, silu=False, label=f'{n}.norm2')
-        qk = self._act('qk', B, Ho, Ho, 2 * cout)
-        vt = self._buf('vt', B * cout * L)[:B * cout * L].view(B * heads * 64, L)
-        P.add_gemm([a2], [(0, 1, 0, cout // 64)], W_[f'{n}.qkv.w'], 3 * cout, qk, bias=W_[f'{n}.qkv.b'], vt_out=vt,
-                   vt_col_start=2 * cout, heads=heads, label=f'{n}.qkv')
+        qkv = self._act('qkv', B, Ho, Ho, 3 * cout)          # [Q | K | V], each head-major, row-major per pixel
+        P.add_gemm([a2], [(0, 1, 0, cout // 64)], W_[f'{n}.qkv.w'], 3 * cout, qkv, bias=W_[f'{n}.qkv.b'],
+                   label=f'{n}.qkv')
         att = self._act('a0', B, Ho, Ho, cout)
-        P.add_attention(qk.view(B * L, 2 * cout), cout, vt, att.view(B * L, cout), B, heads, L, label=f'{n}.attn')
+        # V is consumed in place as an MN-major UMMA operand: no transposed copy
+        P.add_attention(qkv.view(B * L, 3 * cout), cout, None, att.view(B * L, cout), B, heads, L,
+                        v_col0=2 * cout, label=f'{n}.attn')
         out2 = torch.empty(B, Ho, Ho, cout, device=dev, dtype=torch.bfloat16)
         P.add_gemm([att], [(0, 1, 0, cout // 64)], W_[f'{n}.proj.w'], cout, out2, bias=W_[f'{n}.proj.b'], residual=out,
                    out_scale=cfg.skip_scale, label=f'{n}.proj')

@@ -179,10 +179,11 @@ int b200ns_plan_add_gn_apply(b200ns_plan* p, const b200ns_gn_apply_desc* d);
 typedef struct {
   const void* qk;
   int32_t ld_qk, k_col0;
-  const void* vt;
+  const void* vt;            /* V^T [batch*heads, 64, L], or NULL: V row-major in `qk` at column v_col0 */
   void* out;
   int32_t ld_out;
   int32_t batch, heads, L;
+  int32_t v_col0;
 } b200ns_attn_desc;
 int b200ns_plan_add_attention(b200ns_plan* p, const b200ns_attn_desc* d);
 

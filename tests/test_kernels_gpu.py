@@ -193,6 +193,23 @@ def test_attention(ops, B, heads, L):
     assert _rel_err(out, ref) < 1e-2
 
 
+@pytest.mark.parametrize('B,heads,L', [(2, 2, 64), (1, 6, 1024), (3, 9, 256), (2, 1, 128)])
+def test_attention_row_major_v(ops, B, heads, L):
+    """V consumed in place from the row-major qkv matrix (MN-major UMMA B operand): no V^T copy."""
+    torch.manual_seed(15)
+    dev = 'cuda'
+    C = heads * 64
+    qkv = torch.randn(B, L, 3 * C, device=dev).to(torch.bfloat16).contiguous()
+    out = torch.zeros(B, L, C, device=dev, dtype=torch.bfloat16)
+    plan = ops.Plan()
+    plan.add_attention(qkv.reshape(B * L, 3 * C), C, None, out.reshape(B * L, C), B, heads, L, v_col0=2 * C)
+    plan.run()
+    qf, kf, vf = [qkv[..., i * C:(i + 1) * C].float().reshape(B, L, heads, 64).permute(0, 2, 1, 3) for i in range(3)]
+    w = torch.softmax(qf @ kf.transpose(-1, -2) / 8.0, dim=-1)
+    ref = (w @ vf).permute(0, 2, 1, 3).reshape(B, L, C)
+    assert _rel_err(out, ref) < 1e-2
+
+
 def test_qkv_gemm_writes_v_transposed(ops):
     torch.manual_seed(6)
     dev = 'cuda'

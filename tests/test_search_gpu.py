@@ -120,6 +120,27 @@ def test_noise_free_steps_are_exact_ties(pkg):
         assert rec.indices[i].tolist() == [0] * s.shape[1]
 
 
+def test_commit_reuse_is_bit_identical(pkg):
+    """edm/main.py:860 recomputes the winner at batch b; the engine is batch-size invariant, so reusing the
+    winner's candidate-batch result must give the same bits (SURVEY.md 8 a14 'proven-equivalent reuse')."""
+    den, em, sc = pkg
+    g = load_golden('search_eps_greedy_tiny.pt')
+    onet, spec, sd = oracle_net(g['cfg'], g['seed'])
+    latents, labels, pre = search_inputs(g)
+    net = den.B200Denoiser(sd, device='cuda')
+    table = den.StepTable(net, 'cuda', g['num_steps'], **g['sampler_kw'])
+    params = em.SamplingParams(N=g['N'], K=g['K'], eps=0.0, lambda_param=g['lambda_param'], scorer=sc.BrightnessScorer())
+    noise = {k: v.cuda() for k, v in pre.items()}
+    out = {}
+    for mode in ('reuse', 'recompute'):
+        x, rec = em.eps_greedy_search(net, latents.cuda(), labels.cuda(), params, table, precomputed_noise=noise,
+                                      record=True, commit=mode)
+        out[mode] = (x.cpu(), [t.cpu() for t in rec.x_steps], [t.cpu() for t in rec.indices])
+    assert all(torch.equal(a, b) for a, b in zip(out['reuse'][2], out['recompute'][2]))
+    assert all(torch.equal(a, b) for a, b in zip(out['reuse'][1], out['recompute'][1]))
+    assert torch.equal(out['reuse'][0], out['recompute'][0])
+
+
 def test_generate_image_grid_naive_and_rejection(pkg):
     """Public API smoke + parity of the remaining EDM methods against the oracle (loose: free-running
     18-step trajectories accumulate the bf16 network error)."""

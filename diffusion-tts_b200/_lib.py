@@ -72,6 +72,7 @@ SIGNATURES = {
     'b200ns_plan_destroy': (None, [c_vp]),
     'b200ns_plan_size': (C.c_int, [c_vp]),
     'b200ns_plan_run': (C.c_int, [c_vp, c_vp]),
+    'b200ns_plan_instantiate_graph': (C.c_int, [c_vp]),
     'b200ns_plan_run_range': (C.c_int, [c_vp, C.c_int, C.c_int, c_vp]),
     'b200ns_plan_add_gemm': (C.c_int, [c_vp, C.POINTER(GemmDesc)]),
     'b200ns_plan_add_gn_stats': (C.c_int, [c_vp, C.POINTER(GnStatsDesc)]),

@@ -220,4 +220,194 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// v2 (row-major V only): single-buffered K/V/P (80 KB smem -> two CTAs per SM), one-pass softmax
+// with the 128 scores of a row held in registers, K(kt+1)/V(kt+1) TMA loads issued as soon as the
+// MMA that last read the buffer has committed.
+template <int KT>
+struct AttnCfg2 {
+  static constexpr int Q_BYTES = 128 * 128;
+  static constexpr int K_BYTES = KT * 128;
+  static constexpr int V_BYTES = KT * 128;
+  static constexpr int P_BYTES = (KT / 64) * 128 * 128;
+  static constexpr int SMEM_BYTES = Q_BYTES + K_BYTES + V_BYTES + P_BYTES + 1024 + 128;
+};
+
+template <int KT>
+__global__ void __launch_bounds__(128, 2)
+attention_kernel_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const AttnArgs a) {
+  using Cfg = AttnCfg2<KT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::Q_BYTES;
+  uint8_t* sV = sK + Cfg::K_BYTES;
+  uint8_t* sP = sV + Cfg::V_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+  uint64_t* bar_q = bars;
+  uint64_t* bar_k = bars + 1;
+  uint64_t* bar_v = bars + 2;
+  uint64_t* bar_s = bars + 3;
+  uint64_t* bar_o = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int bh = blockIdx.y, bi = bh / a.heads, head = bh % a.heads;
+  const int q0 = blockIdx.x * 128;
+  const int row_base = bi * a.L;
+  const int nkt = a.L / KT;
+
+  if (tid == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, KT);
+  constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, true);      // B = V, MN-major
+
+  auto load_k = [&](int kt) {
+    mbar_arrive_expect_tx(bar_k, Cfg::K_BYTES);
+    tma_load_2d(sK, &tmK, bar_k, a.k_col0 + head * 64, row_base + kt * KT);
+  };
+  auto load_v = [&](int kt) {
+    mbar_arrive_expect_tx(bar_v, Cfg::V_BYTES);
+    tma_load_2d(sV, &tmV, bar_v, a.v_col0 + head * 64, row_base + kt * KT);
+  };
+  auto issue_s = [&]() {
+    const uint64_t dq = umma_desc_sw128(smem_u32(sQ));
+    const uint64_t dk = umma_desc_sw128(smem_u32(sK));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16(tS, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+    umma_commit(bar_s);
+  };
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_q, Cfg::Q_BYTES);
+    tma_load_2d(sQ, &tmQ, bar_q, head * 64, row_base + q0);
+    load_k(0);
+    load_v(0);
+    mbar_wait(bar_q, 0);
+    mbar_wait(bar_k, 0);
+    tc_fence_after();
+    issue_s();
+  }
+
+  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+  const float c = 0.125f * 1.4426950408889634f;     // 1/sqrt(64) * log2(e)
+  float m_run = -INFINITY, l_run = 0.f;
+  float o[64];
+#pragma unroll
+  for (int j = 0; j < 64; ++j) o[j] = 0.f;
+  const int r7 = tid & 7;
+  uint8_t* prow = sP + tid * 128;
+
+  for (int kt = 0; kt < nkt; ++kt) {
+    const uint32_t ph = kt & 1;
+    mbar_wait(bar_s, ph);                         // S(kt) complete: K buffer is free again
+    tc_fence_after();
+    if (tid == 0 && kt + 1 < nkt) load_k(kt + 1);
+    // ---- one-pass softmax over the KT scores of this row
+    uint32_t sr[KT];
+#pragma unroll
+    for (int c0 = 0; c0 < KT; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tS + lane_addr + c0, r);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sr[c0 + j] = r[j];
+    }
+    tmem_ld_wait();
+    float mx = __uint_as_float(sr[0]);
+#pragma unroll
+    for (int j = 1; j < KT; ++j) mx = fmaxf(mx, __uint_as_float(sr[j]));
+    const float m_new = fmaxf(m_run, mx);
+    const float alpha = ex2_approx((m_run - m_new) * c);
+    const float mc = m_new * c;
+    float lsum = 0.f;
+#pragma unroll
+    for (int g = 0; g < KT / 8; ++g) {
+      float p[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        p[j] = ex2_approx(fmaf(__uint_as_float(sr[8 * g + j]), c, -mc));
+        lsum += p[j];
+      }
+      uint4 u;
+      u.x = pack_bf16(p[0], p[1]);
+      u.y = pack_bf16(p[2], p[3]);
+      u.z = pack_bf16(p[4], p[5]);
+      u.w = pack_bf16(p[6], p[7]);
+      // key block g (8 keys = 16 B) of atom g/8, swizzled by the row
+      *reinterpret_cast<uint4*>(prow + (g >> 3) * 16384 + (((g & 7) ^ r7) << 4)) = u;
+    }
+    l_run = l_run * alpha + lsum;
+    m_run = m_new;
+    tc_fence_before();
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      mbar_wait(bar_v, ph);
+      tc_fence_after();
+      const uint64_t dp = umma_desc_sw128(smem_u32(sP));
+      const uint64_t dv = umma_desc_sw128(smem_u32(sV));
+#pragma unroll
+      for (int k = 0; k < KT / 16; ++k) {
+        const uint64_t pa = dp + static_cast<uint64_t>((k >> 2) * (16384 >> 4) + (k & 3) * 2);
+        const uint64_t va = dv + static_cast<uint64_t>(k * (2048 >> 4));
+        umma_bf16(tO, pa, va, idesc_o, k != 0);
+      }
+      umma_commit(bar_o);
+      if (kt + 1 < nkt) {
+        mbar_wait(bar_k, ph ^ 1);
+        tc_fence_after();
+        issue_s();
+      }
+    }
+    mbar_wait(bar_o, ph);                         // PV(kt) complete: V and P buffers are free again
+    tc_fence_after();
+    if (tid == 0 && kt + 1 < nkt) load_v(kt + 1);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t r[32];
+      tmem_ld32(tO + lane_addr + h * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) o[h * 32 + j] = fmaf(o[h * 32 + j], alpha, __uint_as_float(r[j]));
+    }
+  }
+
+  const int q = q0 + tid;
+  if (q < a.L) {
+    const float inv = 1.0f / l_run;
+    uint4* op = reinterpret_cast<uint4*>(a.out + static_cast<size_t>(row_base + q) * a.ld_out + head * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint4 u;
+      u.x = pack_bf16(o[8 * j + 0] * inv, o[8 * j + 1] * inv);
+      u.y = pack_bf16(o[8 * j + 2] * inv, o[8 * j + 3] * inv);
+      u.z = pack_bf16(o[8 * j + 4] * inv, o[8 * j + 5] * inv);
+      u.w = pack_bf16(o[8 * j + 6] * inv, o[8 * j + 7] * inv);
+      op[j] = u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 }  // namespace b200

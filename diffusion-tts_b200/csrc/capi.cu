@@ -190,6 +190,19 @@ int launch_attn_t(const AttnOp& o, cudaStream_t st) {
   return 0;
 }
 
+template <int KT>
+int launch_attn_v2(const AttnOp& o, cudaStream_t st) {
+  using Cfg = AttnCfg2<KT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(attention_kernel_v2<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  attention_kernel_v2<KT><<<o.grid, 128, Cfg::SMEM_BYTES, st>>>(o.tmQ, o.tmK, o.tmV, o.args);
+  CK_LAUNCH("attention_kernel_v2");
+  return 0;
+}
+
 int run_op(const Op& op, cudaStream_t st) {
   switch (op.kind) {
     case OP_GEMM: return launch_gemm(op.gemm, st);
@@ -202,7 +215,7 @@ int run_op(const Op& op, cudaStream_t st) {
       CK_LAUNCH("gn_apply_kernel");
       return 0;
     case OP_ATTN:
-      if (op.attn.vrow) return op.attn.KT == 128 ? launch_attn_t<128, true>(op.attn, st) : launch_attn_t<64, true>(op.attn, st);
+      if (op.attn.vrow) return op.attn.KT == 128 ? launch_attn_v2<128>(op.attn, st) : launch_attn_v2<64>(op.attn, st);
       return op.attn.KT == 128 ? launch_attn_t<128, false>(op.attn, st) : launch_attn_t<64, false>(op.attn, st);
     case OP_LINEAR:
       linear_kernel<<<op.lin.grid, 256, 0, st>>>(op.lin.args);
@@ -221,6 +234,8 @@ int run_op(const Op& op, cudaStream_t st) {
 
 struct b200ns_plan {
   std::vector<Op> ops;
+  cudaGraphExec_t graph_exec = nullptr;     // optional: the whole plan captured once as a CUDA graph
+  size_t graph_ops = 0;
 };
 
 extern "C" {
@@ -340,7 +355,41 @@ int b200ns_make_candidates(const double* pivot, const double* dirs, const double
 
 // ------------------------------------------------------------------ plans
 b200ns_plan* b200ns_plan_create(void) { return new b200ns_plan(); }
-void b200ns_plan_destroy(b200ns_plan* p) { delete p; }
+void b200ns_plan_destroy(b200ns_plan* p) {
+  if (p != nullptr && p->graph_exec != nullptr) cudaGraphExecDestroy(p->graph_exec);
+  delete p;
+}
+
+// Capture all ops of the plan into a CUDA graph (on a private stream; pointers and TMA descriptors are
+// static), so that b200ns_plan_run costs one graph launch instead of one launch per kernel.
+int b200ns_plan_instantiate_graph(b200ns_plan* p) {
+  if (p->graph_exec != nullptr) {
+    cudaGraphExecDestroy(p->graph_exec);
+    p->graph_exec = nullptr;
+  }
+  // one eager pass first: sets the per-kernel attributes (max dynamic smem) outside the capture
+  cudaStream_t cs;
+  CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    int rc = run_op(p->ops[i], cs);
+    if (rc) {
+      cudaStreamDestroy(cs);
+      return rc;
+    }
+  }
+  CK(cudaStreamSynchronize(cs));
+  cudaGraph_t graph = nullptr;
+  CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+  int rc = 0;
+  for (size_t i = 0; i < p->ops.size() && rc == 0; ++i) rc = run_op(p->ops[i], cs);
+  cudaError_t e = cudaStreamEndCapture(cs, &graph);
+  if (rc == 0 && e != cudaSuccess) rc = check_cuda(e, "cudaStreamEndCapture");
+  if (rc == 0) rc = check_cuda(cudaGraphInstantiate(&p->graph_exec, graph, 0), "cudaGraphInstantiate");
+  if (graph != nullptr) cudaGraphDestroy(graph);
+  cudaStreamDestroy(cs);
+  if (rc == 0) p->graph_ops = p->ops.size();
+  return rc;
+}
 int b200ns_plan_size(const b200ns_plan* p) { return static_cast<int>(p->ops.size()); }
 
 int b200ns_plan_run_range(b200ns_plan* p, int first, int last, void* stream) {
@@ -355,6 +404,10 @@ int b200ns_plan_run_range(b200ns_plan* p, int first, int last, void* stream) {
   return 0;
 }
 int b200ns_plan_run(b200ns_plan* p, void* stream) {
+  if (p->graph_exec != nullptr && p->graph_ops == p->ops.size()) {
+    CK(cudaGraphLaunch(p->graph_exec, S(stream)));
+    return 0;
+  }
   return b200ns_plan_run_range(p, 0, static_cast<int>(p->ops.size()), stream);
 }
 

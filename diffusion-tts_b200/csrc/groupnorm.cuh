@@ -108,14 +108,36 @@ __global__ void __launch_bounds__(256, 4) gn_stats_kernel(const GnStatsArgs a) {
     s_sq[py * a.C + c + j] = ss[j];
   }
   __syncthreads();
-  // one thread per group: fixed-order fp64 reduction over (channel-in-group, py)
+  // level 1 (all threads): per-channel sum over py in fixed order; level 2: per-group fp64 sum
+  float cs[11], cq[11];          // ceil(2048 / 192) channels per thread at most
+#pragma unroll
+  for (int k = 0; k < 11; ++k) {
+    const int cc = threadIdx.x + k * blockDim.x;
+    float ts = 0.f, tq = 0.f;
+    if (cc < a.C)
+      for (int y = 0; y < a.PY; ++y) {
+        ts += s_sum[y * a.C + cc];
+        tq += s_sq[y * a.C + cc];
+      }
+    cs[k] = ts;
+    cq[k] = tq;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 11; ++k) {
+    const int cc = threadIdx.x + k * blockDim.x;
+    if (cc < a.C) {
+      s_sum[cc] = cs[k];
+      s_sq[cc] = cq[k];
+    }
+  }
+  __syncthreads();
   for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
     double ds = 0.0, dq = 0.0;
-    for (int cc = g * a.cpg; cc < (g + 1) * a.cpg; ++cc)
-      for (int y = 0; y < a.PY; ++y) {
-        ds += static_cast<double>(s_sum[y * a.C + cc]);
-        dq += static_cast<double>(s_sq[y * a.C + cc]);
-      }
+    for (int cc = g * a.cpg; cc < (g + 1) * a.cpg; ++cc) {
+      ds += static_cast<double>(s_sum[cc]);
+      dq += static_cast<double>(s_sq[cc]);
+    }
     double* o = a.partial + ((static_cast<size_t>(bi) * a.splits + split) * a.groups + g) * 2;
     o[0] = ds;
     o[1] = dq;

@@ -192,6 +192,10 @@ class Plan:
             L.check(L.lib().b200ns_plan_run_range(self._h, first, last, L.cur_stream()), 'plan_run_range')
             _count(last - first)
 
+    def instantiate_graph(self):
+        """Capture the whole plan as one CUDA graph (static buffers): run() then costs one launch."""
+        L.check(L.lib().b200ns_plan_instantiate_graph(self._h), 'plan_instantiate_graph')
+
     def run_timed(self):
         """Run op by op with CUDA events around each launch; returns per-op milliseconds."""
         n = len(self.labels)

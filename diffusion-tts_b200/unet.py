@@ -151,6 +151,9 @@ class ForwardPlan:
         self._scratch: Dict[str, torch.Tensor] = {}
         self.block_out: Dict[str, torch.Tensor] = {}      # per-block outputs (persistent; per-layer parity tests)
         self._build(eng)
+        if eng.use_graphs:
+            torch.cuda.synchronize(dev)
+            self.plan.instantiate_graph()
 
     # -- helpers
     def _buf(self, key: str, numel: int, dtype=torch.bfloat16) -> torch.Tensor:
@@ -312,8 +315,9 @@ class ForwardPlan:
 class UNetEngine:
     """Packed weights + cached ForwardPlans.  `forward(x_in, c_noise, labels)` returns F_x."""
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device='cuda'):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device='cuda', use_graphs: bool = True):
         from . import _lib
+        self.use_graphs = use_graphs
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise RuntimeError('UNetEngine requires a CUDA device (B200); there is no CPU fallback')

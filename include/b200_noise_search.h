@@ -94,6 +94,8 @@ b200ns_plan* b200ns_plan_create(void);
 void b200ns_plan_destroy(b200ns_plan* p);
 int b200ns_plan_size(const b200ns_plan* p);
 int b200ns_plan_run(b200ns_plan* p, void* stream);
+/* Capture the plan once as a CUDA graph; later b200ns_plan_run calls launch the graph. */
+int b200ns_plan_instantiate_graph(b200ns_plan* p);
 /* Run ops [first, last) only (per-layer parity tests and profiling). */
 int b200ns_plan_run_range(b200ns_plan* p, int first, int last, void* stream);
 

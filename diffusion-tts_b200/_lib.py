@@ -41,7 +41,7 @@ class GnApplyDesc(C.Structure):
 
 class AttnDesc(C.Structure):
     _fields_ = [('qk', c_vp), ('ld_qk', c_i32), ('k_col0', c_i32), ('vt', c_vp), ('out', c_vp), ('ld_out', c_i32),
-                ('batch', c_i32), ('heads', c_i32), ('L', c_i32), ('v_col0', c_i32)]
+                ('batch', c_i32), ('heads', c_i32), ('L', c_i32), ('v_col0', c_i32), ('head_dim', c_i32)]
 
 
 class LinearDesc(C.Structure):

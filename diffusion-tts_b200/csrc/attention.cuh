@@ -410,4 +410,182 @@ attention_kernel_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// head_dim 256, one head, L <= 256 (DDPM++ / SongUNet: `num_heads=1`, networks.py:263; attention at
+// 16x16 and 8x8).  The whole score row fits in TMEM (L <= 256 columns), so the softmax is exact
+// two-pass (no online rescaling): S = Q K^T accumulated over four 64-wide d chunks, P overwrites the
+// Q buffer, O = P V with V as an MN-major operand of N = 256 (four 64-wide d blocks, LBO = 8 KB).
+struct AttnCfg256 {
+  static constexpr int QP_BYTES = 4 * 128 * 128;      // Q: 4 d-atoms [128 x 64]; later P: L/64 key-atoms
+  static constexpr int KV_BYTES = 4 * 64 * 128;       // one chunk of 64 keys x 256 d
+  static constexpr int SMEM_BYTES = QP_BYTES + 2 * KV_BYTES + 1024 + 128;
+};
+
+__global__ void __launch_bounds__(128, 1)
+attention_d256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnArgs a) {
+  using Cfg = AttnCfg256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQP = smem;
+  uint8_t* sKV = smem + Cfg::QP_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + 2 * Cfg::KV_BYTES);
+  uint64_t* bar_q = bars;
+  uint64_t* bar_full = bars + 1;    // [2]
+  uint64_t* bar_free = bars + 3;    // [2]
+  uint64_t* bar_s = bars + 5;
+  uint64_t* bar_o = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int bi = blockIdx.y;
+  const int q0 = blockIdx.x * 128;
+  const int row_base = bi * a.L;
+  const int n = a.L / 64;            // key chunks (1..4)
+
+  if (tid == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmKV);
+    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tO = tmem_base + 256;
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64);
+  constexpr uint32_t idesc_o = umma_idesc_bf16(128, 256, true);
+
+  // chunk g in [0, n): K chunk g ; g in [n, 2n): V chunk g-n
+  auto load_chunk = [&](int g) {
+    const int st = g & 1;
+    const int col0 = g < n ? a.k_col0 : a.v_col0;
+    const int kc = g < n ? g : g - n;
+    mbar_arrive_expect_tx(&bar_full[st], Cfg::KV_BYTES);
+#pragma unroll
+    for (int dc = 0; dc < 4; ++dc)
+      tma_load_2d(sKV + st * Cfg::KV_BYTES + dc * 8192, &tmKV, &bar_full[st], col0 + dc * 64, row_base + kc * 64);
+  };
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_q, Cfg::QP_BYTES);
+#pragma unroll
+    for (int dc = 0; dc < 4; ++dc) tma_load_2d(sQP + dc * 16384, &tmQ, bar_q, dc * 64, row_base + q0);
+    load_chunk(0);
+    if (2 * n > 1) load_chunk(1);
+    mbar_wait(bar_q, 0);
+    for (int g = 0; g < n; ++g) {                      // ---- S = Q K^T
+      const int st = g & 1;
+      mbar_wait(&bar_full[st], (g >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int dc = 0; dc < 4; ++dc) {
+        const uint64_t dq = umma_desc_sw128(smem_u32(sQP + dc * 16384));
+        const uint64_t dk = umma_desc_sw128(smem_u32(sKV + st * Cfg::KV_BYTES + dc * 8192));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tS + g * 64, dq + 2 * k, dk + 2 * k, idesc_s, (dc | k) != 0);
+      }
+      umma_commit(&bar_free[st]);
+      if (g + 2 < 2 * n) {
+        mbar_wait(&bar_free[st], (g >> 1) & 1);
+        load_chunk(g + 2);
+      }
+    }
+    umma_commit(bar_s);
+  }
+
+  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+  const float c = 0.0625f * 1.4426950408889634f;     // 1/sqrt(256) * log2(e)
+  mbar_wait(bar_s, 0);
+  tc_fence_after();
+  float mx = -INFINITY;
+  for (int c0 = 0; c0 < a.L; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(tS + lane_addr + c0, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+  }
+  const float mc = mx * c;
+  float lsum = 0.f;
+  const int r7 = tid & 7;
+  for (int c0 = 0; c0 < a.L; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(tS + lane_addr + c0, r);
+    tmem_ld_wait();
+    uint8_t* prow = sQP + (c0 >> 6) * 16384 + tid * 128;
+    const int ch0 = (c0 & 63) >> 3;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float p[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        p[j] = ex2_approx(fmaf(__uint_as_float(r[8 * g + j]), c, -mc));
+        lsum += p[j];
+      }
+      uint4 u;
+      u.x = pack_bf16(p[0], p[1]);
+      u.y = pack_bf16(p[2], p[3]);
+      u.z = pack_bf16(p[4], p[5]);
+      u.w = pack_bf16(p[6], p[7]);
+      *reinterpret_cast<uint4*>(prow + (((ch0 + g) ^ r7) << 4)) = u;
+    }
+  }
+  tc_fence_before();
+  fence_proxy_async_smem();
+  __syncthreads();
+
+  if (tid == 0) {                                        // ---- O = P V
+    tc_fence_after();
+    for (int g = n; g < 2 * n; ++g) {
+      const int st = g & 1, kc = g - n;
+      mbar_wait(&bar_full[st], (g >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t dp = umma_desc_sw128(smem_u32(sQP + kc * 16384)) + 2 * k;
+        const uint64_t dv = umma_desc_sw128_lbo(smem_u32(sKV + st * Cfg::KV_BYTES + k * 2048), 8192);
+        umma_bf16(tO, dp, dv, idesc_o, (kc | k) != 0);
+      }
+      umma_commit(&bar_free[st]);
+      if (g + 2 < 2 * n) {
+        mbar_wait(&bar_free[st], (g >> 1) & 1);
+        load_chunk(g + 2);
+      }
+    }
+    umma_commit(bar_o);
+  }
+  mbar_wait(bar_o, 0);
+  tc_fence_after();
+  const int q = q0 + tid;
+  const float inv = 1.0f / lsum;
+  for (int c0 = 0; c0 < 256; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(tO + lane_addr + c0, r);
+    tmem_ld_wait();
+    if (q < a.L) {
+      uint4* op = reinterpret_cast<uint4*>(a.out + static_cast<size_t>(row_base + q) * a.ld_out + c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 u;
+        u.x = pack_bf16(__uint_as_float(r[8 * j + 0]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
+        u.y = pack_bf16(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
+        u.z = pack_bf16(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
+        u.w = pack_bf16(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
+        op[j] = u;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace b200

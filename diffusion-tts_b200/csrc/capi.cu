@@ -119,6 +119,7 @@ struct AttnOp {
   AttnArgs args;
   int KT;
   int vrow;
+  int head_dim;
   dim3 grid;
 };
 struct LinearOp {
@@ -215,6 +216,16 @@ int run_op(const Op& op, cudaStream_t st) {
       CK_LAUNCH("gn_apply_kernel");
       return 0;
     case OP_ATTN:
+      if (op.attn.head_dim == 256) {
+        static bool attr_set = false;
+        if (!attr_set) {
+          CK(cudaFuncSetAttribute(attention_d256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg256::SMEM_BYTES));
+          attr_set = true;
+        }
+        attention_d256_kernel<<<op.attn.grid, 128, AttnCfg256::SMEM_BYTES, st>>>(op.attn.tmQ, op.attn.tmK, op.attn.args);
+        CK_LAUNCH("attention_d256_kernel");
+        return 0;
+      }
       if (op.attn.vrow) return op.attn.KT == 128 ? launch_attn_v2<128>(op.attn, st) : launch_attn_v2<64>(op.attn, st);
       return op.attn.KT == 128 ? launch_attn_t<128, false>(op.attn, st) : launch_attn_t<64, false>(op.attn, st);
     case OP_LINEAR:
@@ -571,13 +582,30 @@ int b200ns_plan_add_attention(b200ns_plan* p, const b200ns_attn_desc* d) {
   op.kind = OP_ATTN;
   AttnOp& o = op.attn;
   if (d->L % 64) return fail("attention: L must be a multiple of 64");
+  o.head_dim = d->head_dim > 0 ? d->head_dim : 64;
   o.KT = (d->L % 128 == 0) ? 128 : 64;
   o.args.out = reinterpret_cast<__nv_bfloat16*>(d->out);
   o.args.ld_out = d->ld_out;
   o.args.heads = d->heads;
   o.args.L = d->L;
   o.args.k_col0 = d->k_col0;
+  o.args.v_col0 = d->v_col0;
   const uint64_t M = static_cast<uint64_t>(d->batch) * d->L;
+  if (o.head_dim == 256) {
+    if (d->heads != 1 || d->L > 256 || d->vt != nullptr) return fail("attention: head_dim 256 needs 1 head, L <= 256, row-major V");
+    const uint64_t dims[2] = {static_cast<uint64_t>(d->ld_qk), M};
+    const uint32_t boxq[2] = {64, 128};
+    const uint32_t boxk[2] = {64, 64};
+    int rc = make_tmap(&o.tmQ, d->qk, 2, dims, boxq);
+    if (rc) return rc;
+    rc = make_tmap(&o.tmK, d->qk, 2, dims, boxk);
+    if (rc) return rc;
+    o.vrow = 1;
+    o.grid = dim3((d->L + 127) / 128, d->batch);
+    p->ops.push_back(op);
+    return 0;
+  }
+  if (o.head_dim != 64) return fail("attention: head_dim must be 64 or 256");
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(d->ld_qk), M};
     const uint32_t boxq[2] = {64, 128};
@@ -588,7 +616,6 @@ int b200ns_plan_add_attention(b200ns_plan* p, const b200ns_attn_desc* d) {
     if (rc) return rc;
   }
   o.vrow = d->vt == nullptr ? 1 : 0;
-  o.args.v_col0 = d->v_col0;
   if (o.vrow) {       // V row-major inside the qkv matrix: box [KT keys][64 d]
     const uint64_t dims[2] = {static_cast<uint64_t>(d->ld_qk), M};
     const uint32_t box[2] = {64, static_cast<uint32_t>(o.KT)};

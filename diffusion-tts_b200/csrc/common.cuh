@@ -136,6 +136,17 @@ DEVINL uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
   return d;
 }
+// Same, with an explicit leading-dimension byte offset: for an MN-major operand wider than one
+// 64-element swizzle atom, LBO is the distance between consecutive 64-element MN blocks.
+DEVINL uint64_t umma_desc_sw128_lbo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // Instruction descriptor for kind::f16: D fp32, A/B bf16, both K-major, M x N tile.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool b_mn_major = false) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn_major ? (1u << 16) : 0u) |

@@ -283,20 +283,21 @@ class Plan:
         self.flops.append(0.0)
 
     def add_attention(self, qk: torch.Tensor, k_col0: int, vt: Optional[torch.Tensor], out: torch.Tensor, batch: int,
-                      heads: int, Lseq: int, label='attention', v_col0: int = 0):
+                      heads: int, Lseq: int, label='attention', v_col0: int = 0, head_dim: int = 64):
         """qk: [batch*L, ld] with Q at col head*64, K at k_col0 + head*64; V either transposed in `vt`
         ([batch*heads*64, L]) or (vt=None) row-major in `qk` at v_col0 + head*64."""
         d = L.AttnDesc()
         d.qk, d.ld_qk, d.k_col0 = L.ptr(_c(qk, torch.bfloat16)), qk.shape[-1], k_col0
         d.vt = L.ptr(vt)
         d.v_col0 = v_col0
+        d.head_dim = head_dim
         d.out, d.ld_out = L.ptr(_c(out, torch.bfloat16)), out.shape[-1]
         d.batch, d.heads, d.L = batch, heads, Lseq
         self._k(qk, vt, out)
         L.check(L.lib().b200ns_plan_add_attention(self._h, C.byref(d)), 'plan_add_attention')
         self.labels.append(label)
         self.kinds.append('attention')
-        self.flops.append(4.0 * batch * heads * Lseq * Lseq * 64)
+        self.flops.append(4.0 * batch * heads * Lseq * Lseq * head_dim)
 
     def add_linear(self, x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, add=None, act=0,
                    label='linear'):

@@ -295,8 +295,9 @@ class ForwardPlan:
         if not blk.attention:
             return out
         heads, L = blk.heads, Ho * Ho
-        if cout // heads != 64:
-            raise NotImplementedError(f'{n}: attention head_dim {cout // heads} (only 64 is implemented)')
+        hd = cout // heads
+        if hd not in (64, 256) or (hd == 256 and (heads != 1 or L > 256)):
+            raise NotImplementedError(f'{n}: attention head_dim {hd} x {heads} heads at L={L} is not implemented')
         a2 = self._act('a1', B, Ho, Ho, cout)
         self._gn([out], cout, Ho, Ho, W_[f'{n}.norm2.weight'], W_[f'{n}.norm2.bias'], a2, silu=False, label=f'{n}.norm2')
         qkv = self._act('qkv', B, Ho, Ho, 3 * cout)          # [Q | K | V], each head-major, row-major per pixel
@@ -305,7 +306,7 @@ class ForwardPlan:
         att = self._act('a0', B, Ho, Ho, cout)
         # V is consumed in place as an MN-major UMMA operand: no transposed copy
         P.add_attention(qkv.view(B * L, 3 * cout), cout, None, att.view(B * L, cout), B, heads, L,
-                        v_col0=2 * cout, label=f'{n}.attn')
+                        v_col0=2 * cout, head_dim=hd, label=f'{n}.attn')
         out2 = torch.empty(B, Ho, Ho, cout, device=dev, dtype=torch.bfloat16)
         P.add_gemm([att], [(0, 1, 0, cout // 64)], W_[f'{n}.proj.w'], cout, out2, bias=W_[f'{n}.proj.b'], residual=out,
                    out_scale=cfg.skip_scale, label=f'{n}.proj')

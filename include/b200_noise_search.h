@@ -174,7 +174,7 @@ typedef struct {
 } b200ns_gn_apply_desc;
 int b200ns_plan_add_gn_apply(b200ns_plan* p, const b200ns_gn_apply_desc* d);
 
-/* Self-attention, head_dim 64 (networks.py:113-118, 182-185): for each (batch, head)
+/* Self-attention, head_dim 64 or 256 (networks.py:113-118, 182-185): for each (batch, head)
  * O = softmax(Q K^T / sqrt(64)) V with fp32 softmax; Q,K come from qk [batch*L, ld_qk]
  * (Q at column head*64, K at column k_col0 + head*64), V^T from vt [batch*heads, 64, L];
  * output bf16 [batch*L, ld_out] at column head*64. */
@@ -186,6 +186,7 @@ typedef struct {
   int32_t ld_out;
   int32_t batch, heads, L;
   int32_t v_col0;
+  int32_t head_dim;          /* 64 (default when 0) or 256 (one head, L <= 256: DDPM++, networks.py:263) */
 } b200ns_attn_desc;
 int b200ns_plan_add_attention(b200ns_plan* p, const b200ns_attn_desc* d);
 

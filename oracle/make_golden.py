@@ -32,8 +32,9 @@ GOLD = os.path.join(ROOT, 'tests', 'golden')
 
 TINY_ADM = dict(model_type='DhariwalUNet', img_resolution=16, in_channels=3, out_channels=3, label_dim=10,
                 model_channels=64, channel_mult=[1, 2], num_blocks=1, attn_resolutions=[8])
+# attention sits at 8x8 with 256 channels = one head of 256, like the CIFAR-10 DDPM++ preset
 TINY_SONG = dict(model_type='SongUNet', img_resolution=16, in_channels=3, out_channels=3, label_dim=0,
-                 model_channels=64, channel_mult=[1, 2], num_blocks=1, attn_resolutions=[8])
+                 model_channels=64, channel_mult=[2, 4], num_blocks=1, attn_resolutions=[8])
 FULL_ADM = dict(model_type='DhariwalUNet', img_resolution=64, in_channels=3, out_channels=3, label_dim=1000,
                 model_channels=192, channel_mult=[1, 2, 3, 4], num_blocks=3, attn_resolutions=[32, 16, 8])
 FULL_SONG = dict(model_type='SongUNet', img_resolution=32, in_channels=3, out_channels=3, label_dim=0,

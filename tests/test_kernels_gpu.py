@@ -210,6 +210,22 @@ def test_attention_row_major_v(ops, B, heads, L):
     assert _rel_err(out, ref) < 1e-2
 
 
+@pytest.mark.parametrize('B,L', [(2, 256), (3, 64), (1, 128)])
+def test_attention_head_dim_256(ops, B, L):
+    """DDPM++ attention: one head of 256 channels (networks.py:263), exact two-pass softmax in TMEM."""
+    torch.manual_seed(16)
+    dev = 'cuda'
+    C = 256
+    qkv = torch.randn(B, L, 3 * C, device=dev).to(torch.bfloat16).contiguous()
+    out = torch.zeros(B, L, C, device=dev, dtype=torch.bfloat16)
+    plan = ops.Plan()
+    plan.add_attention(qkv.reshape(B * L, 3 * C), C, None, out.reshape(B * L, C), B, 1, L, v_col0=2 * C, head_dim=256)
+    plan.run()
+    q, k, v = [qkv[..., i * C:(i + 1) * C].float() for i in range(3)]
+    w = torch.softmax(q @ k.transpose(-1, -2) / 16.0, dim=-1)
+    assert _rel_err(out, w @ v) < 1e-2
+
+
 def test_qkv_gemm_writes_v_transposed(ops):
     torch.manual_seed(6)
     dev = 'cuda'

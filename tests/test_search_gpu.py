@@ -141,6 +141,31 @@ def test_commit_reuse_is_bit_identical(pkg):
     assert torch.equal(out['reuse'][0], out['recompute'][0])
 
 
+def test_naive_ddpmpp_config1(pkg):
+    """BASELINE.json configs[0] in miniature: DDPM++ (SongUNet), --method naive, 18-step Heun, brightness,
+    batch 1 -- B200 engine vs the oracle on the same per-step noise (edm/main.py:862-866)."""
+    den, em, sc = pkg
+    g = load_golden('search_naive_tiny_song.pt')
+    onet, spec, sd = oracle_net(g['cfg'], g['seed'])
+    latents, labels, _ = search_inputs(g)
+    torch.manual_seed(g['seed'])
+    noise = [torch.randn(latents.shape, dtype=torch.float64) for _ in range(g['num_steps'])]
+    oracle = O.naive_search(onet, latents, labels, lambda im, lab, t: O.brightness_score(im), noise=noise,
+                            num_steps=g['num_steps'], **g['sampler_kw'])
+    net = den.B200Denoiser(sd, device='cuda')
+    table = den.StepTable(net, 'cuda', g['num_steps'], **g['sampler_kw'])
+    x, rec = em.naive_search(net, latents.cuda(), None, table, noise=[z.cuda() for z in noise], record=True)
+    # per-step drift of the free-running trajectory stays at the bf16 level
+    for i, (xs, xo) in enumerate(zip(rec.x_steps, oracle.x_steps)):
+        assert (xs.cpu() - xo).abs().max() < 6e-2 * xo.abs().max(), i
+    from diffusion_tts_b200 import ops
+    img = ops.quantize_u8(x.contiguous()).cpu()
+    diff = (img.int() - oracle.final_image.int()).abs().float()
+    assert diff.mean() < 3.0, diff.mean()
+    score = sc.BrightnessScorer()(img.cuda(), None, None).cpu()
+    assert (score - oracle.final_scores).abs().max() < 1e-2
+
+
 def test_generate_image_grid_naive_and_rejection(pkg):
     """Public API smoke + parity of the remaining EDM methods against the oracle (loose: free-running
     18-step trajectories accumulate the bf16 network error)."""

@@ -80,6 +80,10 @@ SIGNATURES = {
     'b200ns_plan_add_attention': (C.c_int, [c_vp, C.POINTER(AttnDesc)]),
     'b200ns_plan_add_linear': (C.c_int, [c_vp, C.POINTER(LinearDesc)]),
     'b200ns_plan_add_im2col': (C.c_int, [c_vp, C.POINTER(Im2colDesc)]),
+    'b200ns_plan_add_u8_to_f32': (C.c_int, [c_vp, c_vp, c_vp, c_i64]),
+    'b200ns_plan_add_pool_tokens': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32]),
+    'b200ns_plan_add_pool_attention': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32]),
+    'b200ns_plan_add_softmax_gather': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32]),
 }
 
 _lib = None

@@ -62,6 +62,54 @@ def adm_param_shapes(img_resolution=64, in_channels=3, out_channels=3, label_dim
     return shp
 
 
+def classifier_param_shapes(image_size=64, in_channels=3, model_channels=128, out_channels=1000, num_res_blocks=4,
+                            attention_ds: Sequence[int] = (2, 4, 8), channel_mult: Sequence[int] = (1, 2, 3, 4)):
+    """Parameter inventory of the ADM classifier the reference's ImageNetScorer builds
+    (EncoderUNetModel kwargs at edm/scorers.py:127-140; module registration edm/unet.py:747-866)."""
+    E = model_channels * 4
+    shp: Dict[str, Tuple[int, ...]] = {'time_embed.0.weight': (E, model_channels), 'time_embed.0.bias': (E,),
+                                       'time_embed.2.weight': (E, E), 'time_embed.2.bias': (E,)}
+    ch = int(channel_mult[0] * model_channels)
+    shp['input_blocks.0.0.weight'], shp['input_blocks.0.0.bias'] = (ch, in_channels, 3, 3), (ch,)
+
+    def res_block(p, cin, cout):
+        shp[f'{p}.in_layers.0.weight'] = shp[f'{p}.in_layers.0.bias'] = (cin,)
+        shp[f'{p}.in_layers.2.weight'], shp[f'{p}.in_layers.2.bias'] = (cout, cin, 3, 3), (cout,)
+        shp[f'{p}.emb_layers.1.weight'], shp[f'{p}.emb_layers.1.bias'] = (2 * cout, E), (2 * cout,)
+        shp[f'{p}.out_layers.0.weight'] = shp[f'{p}.out_layers.0.bias'] = (cout,)
+        shp[f'{p}.out_layers.3.weight'], shp[f'{p}.out_layers.3.bias'] = (cout, cout, 3, 3), (cout,)
+        if cin != cout:
+            shp[f'{p}.skip_connection.weight'], shp[f'{p}.skip_connection.bias'] = (cout, cin, 1, 1), (cout,)
+
+    def attn_block(p, c):
+        shp[f'{p}.norm.weight'] = shp[f'{p}.norm.bias'] = (c,)
+        shp[f'{p}.qkv.weight'], shp[f'{p}.qkv.bias'] = (3 * c, c, 1), (3 * c,)
+        shp[f'{p}.proj_out.weight'], shp[f'{p}.proj_out.bias'] = (c, c, 1), (c,)
+
+    ds, idx = 1, 1
+    for level, mult in enumerate(channel_mult):
+        for _ in range(num_res_blocks):
+            cout = int(mult * model_channels)
+            res_block(f'input_blocks.{idx}.0', ch, cout)
+            if ds in attention_ds:
+                attn_block(f'input_blocks.{idx}.1', cout)
+            ch = cout
+            idx += 1
+        if level != len(channel_mult) - 1:
+            res_block(f'input_blocks.{idx}.0', ch, ch)
+            idx += 1
+            ds *= 2
+    res_block('middle_block.0', ch, ch)
+    attn_block('middle_block.1', ch)
+    res_block('middle_block.2', ch, ch)
+    side = image_size // ds
+    shp['out.0.weight'] = shp['out.0.bias'] = (ch,)
+    shp['out.2.positional_embedding'] = (ch, side * side + 1)
+    shp['out.2.qkv_proj.weight'], shp['out.2.qkv_proj.bias'] = (3 * ch, ch, 1), (3 * ch,)
+    shp['out.2.c_proj.weight'], shp['out.2.c_proj.bias'] = (out_channels, ch, 1), (out_channels,)
+    return shp
+
+
 def random_state_dict(shapes: Dict[str, Tuple[int, ...]], seed: int = 1234) -> Dict[str, torch.Tensor]:
     """Every tensor ~ N(0, 1/fan_in) (biases N(0, 0.01), norm gains 1 + N(0, 0.01)) from one seeded
     CPU generator in sorted-name order: the same convention as the parity fixtures."""

@@ -10,6 +10,7 @@
 
 #include "../../include/b200_noise_search.h"
 #include "attention.cuh"
+#include "classifier.cuh"
 #include "gemm_conv.cuh"
 #include "groupnorm.cuh"
 #include "sampler.cuh"
@@ -96,7 +97,8 @@ int make_tmap(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims, 
 }
 
 // ------------------------------------------------------------------ plan ops
-enum OpKind { OP_GEMM, OP_GN_STATS, OP_GN_APPLY, OP_ATTN, OP_LINEAR, OP_IM2COL };
+enum OpKind { OP_GEMM, OP_GN_STATS, OP_GN_APPLY, OP_ATTN, OP_LINEAR, OP_IM2COL, OP_U8F32, OP_POOL_TOKENS, OP_POOL_ATTN,
+              OP_SOFTMAX_GATHER };
 
 struct GemmOp {
   CUtensorMap tmA[3], tmB;
@@ -131,9 +133,19 @@ struct Im2colOp {
   int grid;
 };
 
+struct MiscOp {          // the small classifier kernels: plain pointers + a few ints
+  const void* p0;
+  const void* p1;
+  void* p2;
+  void* p3;
+  int64_t n;
+  int i0, i1, i2;
+};
+
 struct Op {
   OpKind kind;
   union {
+    MiscOp misc;
     GemmOp gemm;
     GnStatsOp gns;
     GnApplyOp gna;
@@ -236,6 +248,30 @@ int run_op(const Op& op, cudaStream_t st) {
       im2col_c3_kernel<<<op.i2c.grid, 256, 0, st>>>(op.i2c.d.x, reinterpret_cast<__nv_bfloat16*>(op.i2c.d.out),
                                                    op.i2c.d.batch, op.i2c.d.C, op.i2c.d.H, op.i2c.d.W);
       CK_LAUNCH("im2col_c3_kernel");
+      return 0;
+    case OP_U8F32:
+      u8_to_unit_f32_kernel<<<grid_for(op.misc.n, 256), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(op.misc.p0),
+                                                                    reinterpret_cast<float*>(op.misc.p2), op.misc.n);
+      CK_LAUNCH("u8_to_unit_f32_kernel");
+      return 0;
+    case OP_POOL_TOKENS:
+      pool_tokens_kernel<<<op.misc.i0, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(op.misc.p0),
+                                                     reinterpret_cast<const float*>(op.misc.p1),
+                                                     reinterpret_cast<__nv_bfloat16*>(op.misc.p2),
+                                                     reinterpret_cast<float*>(op.misc.p3), op.misc.i1, op.misc.i2);
+      CK_LAUNCH("pool_tokens_kernel");
+      return 0;
+    case OP_POOL_ATTN:
+      pool_attention_kernel<<<dim3(op.misc.i2 / 64, op.misc.i0), 128, 0, st>>>(
+          reinterpret_cast<const float*>(op.misc.p0), reinterpret_cast<const __nv_bfloat16*>(op.misc.p1),
+          reinterpret_cast<float*>(op.misc.p2), op.misc.i1, op.misc.i2);
+      CK_LAUNCH("pool_attention_kernel");
+      return 0;
+    case OP_SOFTMAX_GATHER:
+      softmax_gather_kernel<<<op.misc.i0, 256, 0, st>>>(reinterpret_cast<const float*>(op.misc.p0),
+                                                        reinterpret_cast<const int64_t*>(op.misc.p1),
+                                                        reinterpret_cast<float*>(op.misc.p2), op.misc.i1);
+      CK_LAUNCH("softmax_gather_kernel");
       return 0;
   }
   return fail("bad op kind");
@@ -650,6 +686,59 @@ int b200ns_plan_add_linear(b200ns_plan* p, const b200ns_linear_desc* d) {
   a.ld_out = d->ld_out;
   const int64_t warps = static_cast<int64_t>(d->rows) * d->N;
   op.lin.grid = static_cast<int>((warps * 32 + 255) / 256);
+  p->ops.push_back(op);
+  return 0;
+}
+
+int b200ns_plan_add_u8_to_f32(b200ns_plan* p, const uint8_t* in, float* out, int64_t n) {
+  Op op;
+  op.kind = OP_U8F32;
+  op.misc.p0 = in;
+  op.misc.p2 = out;
+  op.misc.n = n;
+  p->ops.push_back(op);
+  return 0;
+}
+
+int b200ns_plan_add_pool_tokens(b200ns_plan* p, const void* act, const float* pos, void* tok, float* tok0,
+                                int32_t batch, int32_t T, int32_t C) {
+  Op op;
+  op.kind = OP_POOL_TOKENS;
+  op.misc.p0 = act;
+  op.misc.p1 = pos;
+  op.misc.p2 = tok;
+  op.misc.p3 = tok0;
+  op.misc.i0 = batch;
+  op.misc.i1 = T;
+  op.misc.i2 = C;
+  p->ops.push_back(op);
+  return 0;
+}
+
+int b200ns_plan_add_pool_attention(b200ns_plan* p, const float* qkv0, const void* kv, float* out, int32_t batch,
+                                   int32_t T, int32_t C) {
+  if (T > 127 || C % 64) return fail("pool_attention: T <= 127 and C % 64 == 0 required");
+  Op op;
+  op.kind = OP_POOL_ATTN;
+  op.misc.p0 = qkv0;
+  op.misc.p1 = kv;
+  op.misc.p2 = out;
+  op.misc.i0 = batch;
+  op.misc.i1 = T;
+  op.misc.i2 = C;
+  p->ops.push_back(op);
+  return 0;
+}
+
+int b200ns_plan_add_softmax_gather(b200ns_plan* p, const float* logits, const int64_t* target, float* scores,
+                                   int32_t rows, int32_t K) {
+  Op op;
+  op.kind = OP_SOFTMAX_GATHER;
+  op.misc.p0 = logits;
+  op.misc.p1 = target;
+  op.misc.p2 = scores;
+  op.misc.i0 = rows;
+  op.misc.i1 = K;
   p->ops.push_back(op);
   return 0;
 }

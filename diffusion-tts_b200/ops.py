@@ -324,3 +324,34 @@ class Plan:
         self.labels.append(label)
         self.kinds.append('im2col')
         self.flops.append(0.0)
+
+    def _misc(self, kind, label):
+        self.labels.append(label)
+        self.kinds.append(kind)
+        self.flops.append(0.0)
+
+    def add_u8_to_f32(self, src: torch.Tensor, dst: torch.Tensor, label='u8_to_f32'):
+        self._k(src, dst)
+        L.check(L.lib().b200ns_plan_add_u8_to_f32(self._h, L.ptr(_c(src, torch.uint8)), L.ptr(_c(dst, torch.float32)),
+                                                  src.numel()), 'plan_add_u8_to_f32')
+        self._misc('misc', label)
+
+    def add_pool_tokens(self, act, pos, tok, tok0, batch, T, Cc, label='pool_tokens'):
+        self._k(act, pos, tok, tok0)
+        L.check(L.lib().b200ns_plan_add_pool_tokens(self._h, L.ptr(_c(act, torch.bfloat16)), L.ptr(_c(pos, torch.float32)),
+                                                    L.ptr(_c(tok, torch.bfloat16)), L.ptr(_c(tok0, torch.float32)), batch, T,
+                                                    Cc), 'plan_add_pool_tokens')
+        self._misc('misc', label)
+
+    def add_pool_attention(self, qkv0, kv, out, batch, T, Cc, label='pool_attention'):
+        self._k(qkv0, kv, out)
+        L.check(L.lib().b200ns_plan_add_pool_attention(self._h, L.ptr(_c(qkv0, torch.float32)), L.ptr(_c(kv, torch.bfloat16)),
+                                                       L.ptr(_c(out, torch.float32)), batch, T, Cc), 'plan_add_pool_attention')
+        self._misc('misc', label)
+
+    def add_softmax_gather(self, logits, target, scores, label='softmax_gather'):
+        self._k(logits, target, scores)
+        L.check(L.lib().b200ns_plan_add_softmax_gather(self._h, L.ptr(_c(logits, torch.float32)),
+                                                       L.ptr(_c(target, torch.int64)), L.ptr(_c(scores, torch.float32)),
+                                                       logits.shape[0], logits.shape[1]), 'plan_add_softmax_gather')
+        self._misc('misc', label)

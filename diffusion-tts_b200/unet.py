@@ -167,6 +167,10 @@ class ForwardPlan:
         return self._buf(key, B * H * W * C)[:B * H * W * C].view(B, H, W, C)
 
     @staticmethod
+    def _num_groups(C: int) -> int:
+        return _groups(C)                 # EDM: min(32, C // 4) (networks.py:99)
+
+    @staticmethod
     def _splits(HW: int) -> int:
         """GroupNorm partial-sum splits: a function of the image size ONLY, so the reduction order -- and
         with it every bit of the network output -- is independent of batch size and batch position."""
@@ -174,7 +178,7 @@ class ForwardPlan:
 
     def _gn(self, xs, C, H, W, gamma, beta, out, *, silu=True, resample=0, raw_out=None, film=None, pre_add=None,
             label=''):
-        g = _groups(C)
+        g = self._num_groups(C)
         splits = self._splits(H * W)
         partial = self._buf('partial', self.B * 512 * 32 * 2, torch.float64)[:self.B * splits * g * 2].view(
             self.B, splits, g, 2)

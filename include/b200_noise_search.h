@@ -215,6 +215,23 @@ typedef struct {
 } b200ns_im2col_desc;
 int b200ns_plan_add_im2col(b200ns_plan* p, const b200ns_im2col_desc* d);
 
+/* ------------------------------------------------------------------ classifier scorer glue
+ * ImageNetScorer (edm/scorers.py:143-174) around EncoderUNetModel (edm/unet.py:701-912): the torso runs
+ * on the plan ops above; these are the remaining pieces. */
+/* out = float(in) / 255                                               edm/scorers.py:153 */
+int b200ns_plan_add_u8_to_f32(b200ns_plan* p, const uint8_t* in, float* out, int64_t n);
+/* AttentionPool2d token construction (edm/unet.py:63-65): act bf16 [batch,T,C], pos fp32 [C,T+1] ->
+ * tok bf16 [batch,T,C] (spatial tokens + pos) and tok0 fp32 [batch,C] (mean token + pos). */
+int b200ns_plan_add_pool_tokens(b200ns_plan* p, const void* act, const float* pos, void* tok, float* tok0,
+                                int32_t batch, int32_t T, int32_t C);
+/* QKVAttention (edm/unet.py:388-407) for query token 0: qkv0 fp32 [batch,3C], kv bf16 [batch,T,2C] ->
+ * out fp32 [batch,C]; heads of 64 channels. */
+int b200ns_plan_add_pool_attention(b200ns_plan* p, const float* qkv0, const void* kv, float* out, int32_t batch,
+                                   int32_t T, int32_t C);
+/* scores[r] = softmax(logits[r,:K])[target[r]]                        edm/scorers.py:163-172 */
+int b200ns_plan_add_softmax_gather(b200ns_plan* p, const float* logits, const int64_t* target, float* scores,
+                                   int32_t rows, int32_t K);
+
 #ifdef __cplusplus
 }
 #endif

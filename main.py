@@ -7,7 +7,8 @@ Differences from the reference CLI, all forced by the offline B200 setting:
   * `--network` (new, optional): a local network pickle / `.pt` bundle.  The reference downloads
     the ImageNet-64 ADM pickle (main.py:157-158); without `--network` this front end builds a
     random-init ADM of the same architecture so that the path can run without network access.
-  * `--backend sd`, `--scorer clip|imagenet|compressibility` and `--method mcts` are not part of
+  * `--classifier` (new, optional): a local `64x64_classifier.pt` for `--scorer imagenet` (random-init otherwise).
+  * `--backend sd`, `--scorer clip|compressibility` and `--method mcts` are not part of
     the B200 hot path yet and raise the same ValueError / NotImplementedError a wrong choice would.
 """
 import argparse
@@ -15,13 +16,22 @@ import argparse
 import torch
 
 
-def get_scorer(backend, scorer_name, device='cuda'):
+def get_scorer(backend, scorer_name, device='cuda', classifier=None):
     """Scorer factory (reference main.py:60-71)."""
     from diffusion_tts_b200 import scorers
     if scorer_name == 'brightness':
         return scorers.BrightnessScorer(dtype=torch.float32, device=device)
-    if scorer_name in ('compressibility', 'imagenet') and backend == 'edm':
-        raise NotImplementedError(f"scorer '{scorer_name}' is not on the B200 path yet (SURVEY.md 8: a11/a12)")
+    if scorer_name == 'imagenet' and backend == 'edm':
+        from diffusion_tts_b200.arch import classifier_param_shapes, random_state_dict
+        from diffusion_tts_b200.classifier import ImageNetScorer
+        if classifier is not None:
+            sd = torch.load(classifier, map_location='cpu')
+        else:       # the reference downloads 64x64_classifier.pt (edm/scorers.py:61-74): unreachable offline
+            print('[imagenet scorer] no --classifier checkpoint given: using a random-init ADM classifier')
+            sd = random_state_dict(classifier_param_shapes(), 22)
+        return ImageNetScorer(sd, dtype=torch.float32, device=device)
+    if scorer_name == 'compressibility' and backend == 'edm':
+        raise NotImplementedError("scorer 'compressibility' is not on the B200 path yet (SURVEY.md 8: a12)")
     raise ValueError(f"Unknown or invalid scorer '{scorer_name}' for backend '{backend}'")
 
 
@@ -51,6 +61,7 @@ def main():
     parser.add_argument('--seed', type=int, default=0, help='Random seed')
     parser.add_argument('--device', type=str, default='cuda', help='Device')
     parser.add_argument('--network', type=str, default=None, help='Local network pickle / .pt bundle')
+    parser.add_argument('--classifier', type=str, default=None, help='Local 64x64_classifier.pt for --scorer imagenet')
     args = parser.parse_args()
 
     if args.backend == 'sd' and args.scorer == 'imagenet':
@@ -60,7 +71,7 @@ def main():
     if args.backend == 'sd':
         raise NotImplementedError('the SD backend is not on the B200 hot path yet (SURVEY.md 8: a16, f1-f2)')
 
-    scorer = get_scorer('edm', args.scorer, args.device)
+    scorer = get_scorer('edm', args.scorer, args.device, args.classifier)
     num_images = 1
     gridw = gridh = 1
     latents = torch.randn([num_images, 3, 64, 64])

@@ -144,6 +144,40 @@ def gen_search(cfg, seed, name, method, N, K, num_steps, b=1, eps=0.0):
                     final_image=rec.calls[-1][0], final_scores=rec.calls[-1][1]))
 
 
+TINY_CLS = dict(image_size=16, in_channels=3, model_channels=64, out_channels=10, num_res_blocks=1,
+                attention_resolutions=(2,), channel_mult=(1, 2))
+FULL_CLS = dict(image_size=64, in_channels=3, model_channels=128, out_channels=1000, num_res_blocks=4,
+                attention_resolutions=(2, 4, 8), channel_mult=(1, 2, 3, 4))
+
+
+def gen_classifier(cfg, seed, name, batch):
+    """Reference EncoderUNetModel (edm/unet.py:701) + the reference ImageNetScorer.__call__
+    (edm/scorers.py:143-174; __init__ bypassed: it downloads the pretrained checkpoint)."""
+    import scorers as ref_scorers
+    from unet import EncoderUNetModel
+    from oracle import classifier_oracle as CO
+    model = EncoderUNetModel(num_head_channels=64, use_scale_shift_norm=True, resblock_updown=True,
+                             pool='attention', **cfg)
+    sd = CO.seeded_classifier_state_dict(CO.classifier_param_shapes(**cfg), seed)
+    assert set(sd) == set(model.state_dict()), sorted(set(sd) ^ set(model.state_dict()))
+    model.load_state_dict(sd)
+    model.eval().requires_grad_(False)
+    sc = ref_scorers.ImageNetScorer.__new__(ref_scorers.ImageNetScorer)
+    torch.nn.Module.__init__(sc)
+    sc.dtype = torch.float32
+    sc.model = model
+    g = torch.Generator().manual_seed(seed + 1)
+    res = cfg['image_size']
+    images = torch.randint(0, 256, (batch, 3, res, res), generator=g, dtype=torch.uint8)
+    images[1] = images[0]
+    labels = torch.eye(cfg['out_channels'])[torch.randint(cfg['out_channels'], (batch,), generator=g)].clone()
+    timesteps = torch.zeros(batch)
+    with torch.no_grad():
+        scores = sc(images, labels, timesteps)
+        logits = model(images.float() / 255.0, timesteps)
+    save(name, dict(cfg=cfg, seed=seed, images=images, labels=labels, scores=scores.clone(), logits=logits.clone()))
+
+
 def gen_scalar():
     import scorers as ref_scorers
     g = torch.Generator().manual_seed(7)
@@ -177,7 +211,9 @@ def main():
     gen_search(TINY_ADM, 11, 'search_eps1_tiny.pt', 'EPS_GREEDY', N=3, K=1, num_steps=4, b=1, eps=1.0)
     gen_search(TINY_ADM, 11, 'search_rejection_tiny.pt', 'REJECTION_SAMPLING', N=4, K=1, num_steps=5, b=2)
     gen_search(TINY_SONG, 12, 'search_naive_tiny_song.pt', 'NAIVE', N=1, K=1, num_steps=18, b=1)
+    gen_classifier(TINY_CLS, 21, 'classifier_tiny.pt', batch=4)
     if args.full:
+        gen_classifier(FULL_CLS, 22, 'classifier_full.pt', batch=2)
         gen_unet(FULL_ADM, 1234, 'unet_full_adm.pt', batch=1, sigmas=[2.0])
         gen_unet(FULL_SONG, 4321, 'unet_full_song.pt', batch=1, sigmas=[2.0])
 

@@ -68,6 +68,8 @@ SIGNATURES = {
     'b200ns_gather_rows': (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),
     'b200ns_direction_norms': (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp]),
     'b200ns_make_candidates': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),
+    'b200ns_jpeg_size': (C.c_int, [c_vp, c_vp, c_i64, c_i32, c_i32, c_f32, c_f32, c_vp, c_vp, c_vp]),
+    'b200ns_jpeg_tables_bytes': (C.c_int, []),
     'b200ns_plan_create': (c_vp, []),
     'b200ns_plan_destroy': (None, [c_vp]),
     'b200ns_plan_size': (C.c_int, [c_vp]),

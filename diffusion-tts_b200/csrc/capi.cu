@@ -13,6 +13,7 @@
 #include "classifier.cuh"
 #include "gemm_conv.cuh"
 #include "groupnorm.cuh"
+#include "jpeg.cuh"
 #include "sampler.cuh"
 
 using namespace b200;
@@ -399,6 +400,23 @@ int b200ns_make_candidates(const double* pivot, const double* dirs, const double
   CK_LAUNCH("make_candidates_kernel");
   return 0;
 }
+
+int b200ns_jpeg_size(const uint8_t* img, const void* tables, int64_t M, int32_t H, int32_t W, float min_size,
+                     float max_size, int32_t* sizes, float* scores, void* stream) {
+  if (H % 16 || W % 16 || H > 64 || W > 64 || H <= 0 || W <= 0) return fail("jpeg_size: H, W must be multiples of 16, <= 64");
+  const size_t smem = jpeg_smem_bytes(H, W);
+  static size_t attr = 0;
+  if (smem > attr) {
+    CK(cudaFuncSetAttribute(jpeg_size_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr = smem;
+  }
+  jpeg_size_kernel<<<static_cast<unsigned>(M), 128, smem, S(stream)>>>(img, reinterpret_cast<const JpegTables*>(tables), H, W,
+                                                                       min_size, max_size, sizes, scores);
+  CK_LAUNCH("jpeg_size_kernel");
+  return 0;
+}
+
+int b200ns_jpeg_tables_bytes(void) { return static_cast<int>(sizeof(JpegTables)); }
 
 // ------------------------------------------------------------------ plans
 b200ns_plan* b200ns_plan_create(void) { return new b200ns_plan(); }

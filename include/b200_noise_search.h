@@ -83,6 +83,15 @@ int b200ns_make_candidates(const double* pivot, const double* dirs, const double
                            const float* scale, const uint8_t* fresh_mask, const double* fresh,
                            double* cand, int64_t R, int64_t b, int64_t E, void* stream);
 
+/* Exact baseline-JPEG byte count (PIL/libjpeg: 4:2:0, standard Huffman tables) and the compressibility
+ * score 1 - clip((size-min)/(max-min),0,1) of uint8 RGB images [M,3,H,W], H and W multiples of 16, <= 64.
+ * `tables` is a device copy of the table block (b200ns_jpeg_tables_bytes() bytes, int32 fields: q[2][64],
+ * dc_len[2][16], dc_code[2][16], ac_len[2][256], ac_code[2][256], header_bytes) built from a header that
+ * libjpeg itself wrote for this size/quality.                         edm/scorers.py:207-244 */
+int b200ns_jpeg_size(const uint8_t* img, const void* tables, int64_t M, int32_t H, int32_t W, float min_size,
+                     float max_size, int32_t* sizes, float* scores, void* stream);
+int b200ns_jpeg_tables_bytes(void);
+
 /* ------------------------------------------------------------------ U-Net engine (plans)
  * A plan is an ordered list of kernel launches with all shapes, pointers and TMA descriptors
  * resolved at build time; b200ns_plan_run enqueues them on one stream.  It is the

@@ -8,7 +8,7 @@ Differences from the reference CLI, all forced by the offline B200 setting:
     the ImageNet-64 ADM pickle (main.py:157-158); without `--network` this front end builds a
     random-init ADM of the same architecture so that the path can run without network access.
   * `--classifier` (new, optional): a local `64x64_classifier.pt` for `--scorer imagenet` (random-init otherwise).
-  * `--backend sd`, `--scorer clip|compressibility` and `--method mcts` are not part of
+  * `--backend sd`, `--scorer clip` and `--method mcts` are not part of
     the B200 hot path yet and raise the same ValueError / NotImplementedError a wrong choice would.
 """
 import argparse
@@ -30,8 +30,8 @@ def get_scorer(backend, scorer_name, device='cuda', classifier=None):
             print('[imagenet scorer] no --classifier checkpoint given: using a random-init ADM classifier')
             sd = random_state_dict(classifier_param_shapes(), 22)
         return ImageNetScorer(sd, dtype=torch.float32, device=device)
-    if scorer_name == 'compressibility' and backend == 'edm':
-        raise NotImplementedError("scorer 'compressibility' is not on the B200 path yet (SURVEY.md 8: a12)")
+    if scorer_name == 'compressibility':
+        return scorers.CompressibilityScorer(dtype=torch.float32, device=device)
     raise ValueError(f"Unknown or invalid scorer '{scorer_name}' for backend '{backend}'")
 
 

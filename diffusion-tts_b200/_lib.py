@@ -22,8 +22,7 @@ class GemmDesc(C.Structure):
     _fields_ = [('a_ptr', c_vp * 3), ('a_channels', c_i32 * 3), ('n_seg', c_i32), ('seg', KSeg * 4),
                 ('batch', c_i32), ('H', c_i32), ('W', c_i32), ('w_ptr', c_vp), ('N', c_i32), ('Npad', c_i32),
                 ('Ktot', c_i32), ('bias', c_vp), ('residual', c_vp), ('ld_res', c_i32), ('out_scale', c_f32),
-                ('out', c_vp), ('ld_out', c_i32), ('out_fp32', c_i32), ('vt_out', c_vp), ('vt_col_start', c_i32),
-                ('heads', c_i32)]
+                ('out', c_vp), ('ld_out', c_i32), ('out_fp32', c_i32), ('gn_stats', c_vp)]
 
 
 class GnStatsDesc(C.Structure):
@@ -36,7 +35,12 @@ class GnApplyDesc(C.Structure):
                 ('groups', c_i32), ('partial', c_vp), ('splits', c_i32), ('eps', c_f32), ('gamma', c_vp),
                 ('beta', c_vp), ('pre_add', c_vp), ('ld_pre_add', c_i32), ('film_scale', c_vp), ('film_shift', c_vp),
                 ('ld_film', c_i32), ('b_emb', c_i32), ('silu', c_i32), ('resample', c_i32), ('out', c_vp),
-                ('raw_out', c_vp)]
+                ('raw_out', c_vp), ('mean_rstd', c_vp)]
+
+
+class GnFinalizeDesc(C.Structure):
+    _fields_ = [('stats_ptr', c_vp * 2), ('x_channels', c_i32 * 2), ('batch', c_i32), ('HW', c_i32), ('groups', c_i32),
+                ('pre_add', c_vp), ('ld_pre_add', c_i32), ('b_emb', c_i32), ('eps', c_f32), ('mean_rstd', c_vp)]
 
 
 class AttnDesc(C.Structure):
@@ -79,6 +83,7 @@ SIGNATURES = {
     'b200ns_plan_add_gemm': (C.c_int, [c_vp, C.POINTER(GemmDesc)]),
     'b200ns_plan_add_gn_stats': (C.c_int, [c_vp, C.POINTER(GnStatsDesc)]),
     'b200ns_plan_add_gn_apply': (C.c_int, [c_vp, C.POINTER(GnApplyDesc)]),
+    'b200ns_plan_add_gn_finalize': (C.c_int, [c_vp, C.POINTER(GnFinalizeDesc)]),
     'b200ns_plan_add_attention': (C.c_int, [c_vp, C.POINTER(AttnDesc)]),
     'b200ns_plan_add_linear': (C.c_int, [c_vp, C.POINTER(LinearDesc)]),
     'b200ns_plan_add_im2col': (C.c_int, [c_vp, C.POINTER(Im2colDesc)]),

@@ -47,6 +47,8 @@ class ClassifierPlan(ForwardPlan):
         self.plan = Plan()
         self._scratch: Dict[str, torch.Tensor] = {}
         self.block_out: Dict[str, torch.Tensor] = {}
+        self._stats: Dict[int, torch.Tensor] = {}
+        self.fused_gn_stats = True
         self._eps = 1e-5
         self._build_classifier(eng)
         if eng.use_graphs:
@@ -76,7 +78,8 @@ class ClassifierPlan(ForwardPlan):
         P.add_im2col(self.x_in, col, label='input_conv.im2col')
         c0 = eng.blocks[0].cin
         x = torch.empty(B, H, H, c0, device=dev, dtype=torch.bfloat16)
-        P.add_gemm([col], [(0, 1, 0, 1)], W_['input_conv.w'], c0, x, bias=W_['input_conv.b'], alg_k=27, label='input_conv')
+        P.add_gemm([col], [(0, 1, 0, 1)], W_['input_conv.w'], c0, x, bias=W_['input_conv.b'], alg_k=27,
+                   gn_stats=self._new_stats(x), label='input_conv')
         for blk in eng.blocks:
             x = self._block(eng, blk, [x])
             self.block_out[blk.name] = x

@@ -97,12 +97,33 @@ int make_tmap(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims, 
   return 0;
 }
 
+// bf16 [rows, cols] matrix with row pitch `ld` elements; box = [box_rows][box_cols], 128B swizzle.
+int make_tmap_2d_ld(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_cols,
+                    uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) return fail("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstr[1] = {ld * 2};
+  const cuuint32_t bx[2] = {box_cols, box_rows};
+  const cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[200];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled (2d, ld) failed (%d) cols=%llu rows=%llu ld=%llu", static_cast<int>(r),
+             (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)ld);
+    return fail(buf);
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------ plan ops
-enum OpKind { OP_GEMM, OP_GN_STATS, OP_GN_APPLY, OP_ATTN, OP_LINEAR, OP_IM2COL, OP_U8F32, OP_POOL_TOKENS, OP_POOL_ATTN,
+enum OpKind { OP_GEMM, OP_GN_STATS, OP_GN_APPLY, OP_GN_FINALIZE, OP_ATTN, OP_LINEAR, OP_IM2COL, OP_U8F32, OP_POOL_TOKENS, OP_POOL_ATTN,
               OP_SOFTMAX_GATHER };
 
 struct GemmOp {
-  CUtensorMap tmA[3], tmB;
+  CUtensorMap tmA[3], tmB, tmO, tmR;
   GemmArgs args;
   int BN;
   int grid;
@@ -116,6 +137,10 @@ struct GnApplyOp {
   GnApplyArgs args;
   dim3 grid;
   int threads;
+};
+struct GnFinalizeOp {
+  GnFinalizeArgs args;
+  dim3 grid;
 };
 struct AttnOp {
   CUtensorMap tmQ, tmK, tmV;
@@ -150,6 +175,7 @@ struct Op {
     GemmOp gemm;
     GnStatsOp gns;
     GnApplyOp gna;
+    GnFinalizeOp gnf;
     AttnOp attn;
     LinearOp lin;
     Im2colOp i2c;
@@ -176,8 +202,20 @@ int launch_gemm_t(const GemmOp& g, cudaStream_t st) {
     CK(cudaFuncSetAttribute(gemm_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  gemm_conv_kernel<BN><<<g.grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(g.tmA[0], g.tmA[1], g.tmA[2], g.tmB, g.args);
+  gemm_conv_kernel<BN><<<g.grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(g.tmA[0], g.tmA[1], g.tmA[2], g.tmB, g.tmO, g.tmR,
+                                                                      g.args);
   CK_LAUNCH("gemm_conv_kernel");
+  return 0;
+}
+int launch_gemm_small_n(const GemmOp& g, cudaStream_t st) {
+  using Cfg = GemmCfg<16>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(gemm_small_n_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  gemm_small_n_kernel<<<g.grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(g.tmA[0], g.tmA[1], g.tmA[2], g.tmB, g.args);
+  CK_LAUNCH("gemm_small_n_kernel");
   return 0;
 }
 int launch_gemm(const GemmOp& g, cudaStream_t st) {
@@ -186,7 +224,7 @@ int launch_gemm(const GemmOp& g, cudaStream_t st) {
     case 192: return launch_gemm_t<192>(g, st);
     case 128: return launch_gemm_t<128>(g, st);
     case 64: return launch_gemm_t<64>(g, st);
-    case 16: return launch_gemm_t<16>(g, st);
+    case 16: return launch_gemm_small_n(g, st);
   }
   return fail("bad BN");
 }
@@ -227,6 +265,10 @@ int run_op(const Op& op, cudaStream_t st) {
     case OP_GN_APPLY:
       gn_apply_kernel<<<op.gna.grid, op.gna.threads, 0, st>>>(op.gna.args);
       CK_LAUNCH("gn_apply_kernel");
+      return 0;
+    case OP_GN_FINALIZE:
+      gn_finalize_kernel<<<op.gnf.grid, 128, 0, st>>>(op.gnf.args);
+      CK_LAUNCH("gn_finalize_kernel");
       return 0;
     case OP_ATTN:
       if (op.attn.head_dim == 256) {
@@ -496,14 +538,28 @@ int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d) {
   a.N = d->N;
   a.m_tiles = (a.M + 127) / 128;
   if (d->Npad % 16) return fail("gemm: Npad must be a multiple of 16");
+  // tile width: among the widths dividing Npad, minimise (waves over the SMs) x (cycles per K block of one tile);
+  // per K block the tensor pipe needs ~2*BN cycles and the shared-memory operand feed ~(128 + BN).
   int BN = 0;
-  const int cands[5] = {256, 192, 128, 64, 16};
-  for (int c : cands)
-    if (d->Npad % c == 0) {
-      BN = c;
-      break;
+  if (d->out_fp32) {
+    BN = 16;
+  } else {
+    const int cands[4] = {256, 192, 128, 64};
+    long best = -1;
+    for (int c : cands) {
+      if (d->Npad % c) continue;
+      const long tiles = static_cast<long>(a.m_tiles) * (d->Npad / c);
+      const long waves = (tiles + num_sms() - 1) / num_sms();
+      const long per_kb = 2 * c > 128 + c ? 2 * c : 128 + c;
+      const long cost = waves * per_kb;
+      if (best < 0 || cost < best) {
+        best = cost;
+        BN = c;
+      }
     }
-  if (!BN) return fail("gemm: no tile width divides Npad");
+    if (!BN) BN = 16;
+  }
+  if (d->Npad % BN) return fail("gemm: no tile width divides Npad");
   g.BN = BN;
   a.n_tiles = d->Npad / BN;
   a.n_seg = d->n_seg;
@@ -526,13 +582,18 @@ int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d) {
   a.out = d->out;
   a.ld_out = d->ld_out;
   a.out_fp32 = d->out_fp32;
-  a.vt_out = reinterpret_cast<__nv_bfloat16*>(d->vt_out);
-  a.vt_col_start = d->vt_col_start;
-  a.heads = d->heads;
-  a.L = H * W;
+  a.gn_stats = reinterpret_cast<float2*>(d->gn_stats);
+  if (d->gn_stats != nullptr && (BN == 16 || a.M % 64)) return fail("gemm: gn_stats needs bf16 output, N tiles >= 64 and M % 64 == 0");
   if (!d->out_fp32 && (d->ld_out % 8)) return fail("gemm: ld_out must be a multiple of 8 for bf16 output");
   if (d->residual != nullptr && (d->ld_res % 8)) return fail("gemm: ld_res must be a multiple of 8");
-  if (d->vt_out != nullptr && (d->vt_col_start % 64)) return fail("gemm: vt_col_start must be a multiple of 64");
+  if (BN != 16) {
+    int rc = make_tmap_2d_ld(&g.tmO, d->out, static_cast<uint64_t>(d->N), static_cast<uint64_t>(a.M),
+                             static_cast<uint64_t>(d->ld_out), 64, 128);
+    if (rc) return rc;
+    rc = make_tmap_2d_ld(&g.tmR, d->residual ? d->residual : d->out, static_cast<uint64_t>(d->N),
+                         static_cast<uint64_t>(a.M), static_cast<uint64_t>(d->residual ? d->ld_res : d->ld_out), 64, 128);
+    if (rc) return rc;
+  }
 
   for (int i = 0; i < 3; ++i) {
     const void* ptr = d->a_ptr[i] ? d->a_ptr[i] : d->a_ptr[0];
@@ -616,6 +677,8 @@ int b200ns_plan_add_gn_apply(b200ns_plan* p, const b200ns_gn_apply_desc* d) {
   a.resample = d->resample;
   a.out = reinterpret_cast<__nv_bfloat16*>(d->out);
   a.raw_out = reinterpret_cast<__nv_bfloat16*>(d->raw_out);
+  a.mean_rstd = reinterpret_cast<const float2*>(d->mean_rstd);
+  if (d->mean_rstd == nullptr && d->partial == nullptr) return fail("gn_apply: need partial or mean_rstd");
   const int VC = a.C / 8;
   a.PY = 256 / VC;
   if (a.PY < 1) a.PY = 1;
@@ -627,6 +690,31 @@ int b200ns_plan_add_gn_apply(b200ns_plan* p, const b200ns_gn_apply_desc* d) {
     a.ITER /= 2;
   const int per_cta = a.PY * a.ITER;
   op.gna.grid = dim3((dom + per_cta - 1) / per_cta, d->batch);
+  p->ops.push_back(op);
+  return 0;
+}
+
+int b200ns_plan_add_gn_finalize(b200ns_plan* p, const b200ns_gn_finalize_desc* d) {
+  Op op;
+  op.kind = OP_GN_FINALIZE;
+  GnFinalizeArgs& a = op.gnf.args;
+  a.st0 = reinterpret_cast<const float2*>(d->stats_ptr[0]);
+  a.st1 = reinterpret_cast<const float2*>(d->stats_ptr[1]);
+  a.C0 = d->x_channels[0];
+  a.C1 = d->stats_ptr[1] ? d->x_channels[1] : 0;
+  a.C = a.C0 + a.C1;
+  if (d->stats_ptr[0] == nullptr || d->mean_rstd == nullptr) return fail("gn_finalize: null pointer");
+  if (d->groups < 1 || d->groups > 64 || a.C % d->groups) return fail("gn_finalize: bad group count");
+  if (d->HW % 64) return fail("gn_finalize: HW must be a multiple of 64");
+  a.HW = d->HW;
+  a.groups = d->groups;
+  a.cpg = a.C / d->groups;
+  a.pre_add = d->pre_add;
+  a.ld_pre_add = d->ld_pre_add;
+  a.b_emb = d->b_emb > 0 ? d->b_emb : 1;
+  a.eps = d->eps;
+  a.mean_rstd = reinterpret_cast<float2*>(d->mean_rstd);
+  op.gnf.grid = dim3(d->groups, d->batch);
   p->ops.push_back(op);
   return 0;
 }

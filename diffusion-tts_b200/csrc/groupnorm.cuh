@@ -144,6 +144,78 @@ __global__ void __launch_bounds__(256, 4) gn_stats_kernel(const GnStatsArgs a) {
   }
 }
 
+// GroupNorm statistics from the per-channel (sum, sum of squares) the producing GEMMs wrote per 64-row half
+// tile (gemm_conv.cuh): fp64 accumulation, fixed order -> independent of batch size / position / shard.
+struct GnFinalizeArgs {
+  const float2* st0;
+  const float2* st1;
+  int C0, C1, C;
+  int HW, groups, cpg;
+  const float* pre_add;
+  int ld_pre_add, b_emb;
+  float eps;
+  float2* mean_rstd;       // [batch, groups]
+};
+
+// grid (groups, batch); 128 threads
+__global__ void __launch_bounds__(128) gn_finalize_kernel(const GnFinalizeArgs a) {
+  __shared__ double sh_s[128];
+  __shared__ double sh_q[128];
+  const int g = blockIdx.x, bi = blockIdx.y;
+  const int R = a.HW >> 6;
+  const int total = R * a.cpg;
+  double ds = 0.0, dq = 0.0;
+  auto fetch = [&](int i, float2& v, double& pa) {
+    const int r = i / a.cpg;
+    const int cc = g * a.cpg + (i - r * a.cpg);
+    const size_t prow = static_cast<size_t>(bi) * R + r;
+    v = cc < a.C0 ? __ldg(a.st0 + prow * a.C0 + cc) : __ldg(a.st1 + prow * a.C1 + (cc - a.C0));
+    pa = a.pre_add != nullptr ? static_cast<double>(a.pre_add[static_cast<size_t>(bi % a.b_emb) * a.ld_pre_add + cc]) : 0.0;
+  };
+  auto accum = [&](const float2& v, double pa) {
+    const double s = static_cast<double>(v.x), q = static_cast<double>(v.y);
+    dq += q + 2.0 * pa * s + 64.0 * pa * pa;
+    ds += s + 64.0 * pa;
+  };
+  int i = threadIdx.x;
+  for (; i + 3 * 128 < total; i += 4 * 128) {      // 4 loads in flight; accumulation order stays fixed
+    float2 v0, v1, v2, v3;
+    double p0, p1, p2, p3;
+    fetch(i, v0, p0);
+    fetch(i + 128, v1, p1);
+    fetch(i + 256, v2, p2);
+    fetch(i + 384, v3, p3);
+    accum(v0, p0);
+    accum(v1, p1);
+    accum(v2, p2);
+    accum(v3, p3);
+  }
+  for (; i < total; i += 128) {
+    float2 v;
+    double pa;
+    fetch(i, v, pa);
+    accum(v, pa);
+  }
+  sh_s[threadIdx.x] = ds;
+  sh_q[threadIdx.x] = dq;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sh_s[threadIdx.x] += sh_s[threadIdx.x + o];
+      sh_q[threadIdx.x] += sh_q[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double n = static_cast<double>(a.HW) * a.cpg;
+    const double mean = sh_s[0] / n;
+    double var = sh_q[0] / n - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    a.mean_rstd[static_cast<size_t>(bi) * a.groups + g] =
+        make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps))));
+  }
+}
+
 struct GnApplyArgs {
   const __nv_bfloat16* x0;
   const __nv_bfloat16* x1;
@@ -163,6 +235,7 @@ struct GnApplyArgs {
   __nv_bfloat16* out;
   __nv_bfloat16* raw_out;
   int PY, ITER;
+  const float2* mean_rstd; // [batch, groups] from gn_finalize_kernel (then `partial` is unused)
 };
 
 // grid (pixel chunks, batch); block = (C/8) * PY threads
@@ -173,7 +246,13 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const GnApplyArgs a) {
   const int vx = threadIdx.x % VC, py = threadIdx.x / VC;
   const int bi = blockIdx.y;
   const int HW = a.H * a.W;
-  if (threadIdx.x < a.groups) {
+  if (a.mean_rstd != nullptr) {
+    if (threadIdx.x < a.groups) {
+      const float2 mr = a.mean_rstd[static_cast<size_t>(bi) * a.groups + threadIdx.x];
+      s_mean[threadIdx.x] = mr.x;
+      s_rstd[threadIdx.x] = mr.y;
+    }
+  } else if (threadIdx.x < a.groups) {
     const int g = threadIdx.x;
     double ds = 0.0, dq = 0.0;
     for (int sp = 0; sp < a.splits; ++sp) {

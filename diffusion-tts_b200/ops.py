@@ -209,9 +209,9 @@ class Plan:
         return [evs[i].elapsed_time(evs[i + 1]) for i in range(n)]
 
     def add_gemm(self, a: Sequence[torch.Tensor], segs: Sequence[Tuple[int, int, int, int]], w: torch.Tensor, N: int,
-                 out: torch.Tensor, *, bias=None, residual=None, out_scale=1.0, vt_out=None, vt_col_start=0, heads=0,
-                 label='gemm', alg_k=None):
-        """a: 1-2 NHWC bf16 tensors [B,H,W,C]; segs: (src, taps, cstart, cblocks); w: bf16 [Npad,Ktot]."""
+                 out: torch.Tensor, *, bias=None, residual=None, out_scale=1.0, gn_stats=None, label='gemm', alg_k=None):
+        """a: 1-3 NHWC bf16 tensors [B,H,W,C]; segs: (src, taps, cstart, cblocks); w: bf16 [Npad,Ktot].
+        gn_stats: optional fp32 [M/64, N, 2] receiving per-channel (sum, sumsq) of the stored output."""
         d = L.GemmDesc()
         B, H, W_, _ = a[0].shape
         for i, t in enumerate(a):
@@ -230,8 +230,12 @@ class Plan:
         d.out_scale = float(out_scale)
         d.out, d.ld_out = L.ptr(out), out.shape[-1]
         d.out_fp32 = 1 if out.dtype == torch.float32 else 0
-        d.vt_out, d.vt_col_start, d.heads = L.ptr(vt_out), vt_col_start, heads
-        self._k(*a, w, bias, residual, out, vt_out)
+        if gn_stats is not None:
+            _c(gn_stats, torch.float32)
+            if gn_stats.numel() != (B * H * W_ // 64) * N * 2:
+                raise RuntimeError('gn_stats must be fp32 [M/64, N, 2]')
+        d.gn_stats = L.ptr(gn_stats)
+        self._k(*a, w, bias, residual, out, gn_stats)
         L.check(L.lib().b200ns_plan_add_gemm(self._h, C.byref(d)), 'plan_add_gemm')
         self.labels.append(label)
         self.kinds.append('gemm')
@@ -257,9 +261,28 @@ class Plan:
         self.kinds.append('gn_stats')
         self.flops.append(0.0)
 
-    def add_gn_apply(self, x: Sequence[torch.Tensor], groups: int, partial: torch.Tensor, splits: int, eps: float,
+    def add_gn_finalize(self, stats: Sequence[torch.Tensor], channels: Sequence[int], batch: int, HW: int, groups: int,
+                        eps: float, mean_rstd: torch.Tensor, *, pre_add=None, b_emb=1, label='gn_finalize'):
+        """stats: per-source fp32 [batch*HW/64, C_i, 2] written by the producing GEMMs -> mean_rstd fp32 [batch, groups, 2]."""
+        d = L.GnFinalizeDesc()
+        for i, (t, c) in enumerate(zip(stats, channels)):
+            _c(t, torch.float32)
+            d.stats_ptr[i] = L.ptr(t)
+            d.x_channels[i] = c
+        d.batch, d.HW, d.groups = batch, HW, groups
+        d.pre_add = L.ptr(pre_add)
+        d.ld_pre_add = pre_add.stride(0) if pre_add is not None else 0
+        d.b_emb, d.eps = b_emb, float(eps)
+        d.mean_rstd = L.ptr(_c(mean_rstd, torch.float32))
+        self._k(*stats, pre_add, mean_rstd)
+        L.check(L.lib().b200ns_plan_add_gn_finalize(self._h, C.byref(d)), 'plan_add_gn_finalize')
+        self.labels.append(label)
+        self.kinds.append('gn_finalize')
+        self.flops.append(0.0)
+
+    def add_gn_apply(self, x: Sequence[torch.Tensor], groups: int, partial: Optional[torch.Tensor], splits: int, eps: float,
                      gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor, *, pre_add=None, film_scale=None,
-                     film_shift=None, b_emb=1, silu=True, resample=0, raw_out=None, label='gn_apply'):
+                     film_shift=None, b_emb=1, silu=True, resample=0, raw_out=None, mean_rstd=None, label='gn_apply'):
         d = L.GnApplyDesc()
         B, H, W_, _ = x[0].shape
         for i, t in enumerate(x):
@@ -276,7 +299,8 @@ class Plan:
         d.b_emb = b_emb
         d.silu, d.resample = int(silu), resample
         d.out, d.raw_out = L.ptr(_c(out, torch.bfloat16)), L.ptr(raw_out)
-        self._k(*x, partial, gamma, beta, pre_add, film_scale, film_shift, out, raw_out)
+        d.mean_rstd = L.ptr(mean_rstd)
+        self._k(*x, partial, gamma, beta, pre_add, film_scale, film_shift, out, raw_out, mean_rstd)
         L.check(L.lib().b200ns_plan_add_gn_apply(self._h, C.byref(d)), 'plan_add_gn_apply')
         self.labels.append(label)
         self.kinds.append('gn_apply')

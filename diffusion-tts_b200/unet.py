@@ -141,6 +141,7 @@ class ForwardPlan:
     def __init__(self, eng: 'UNetEngine', B: int, b_emb: int):
         cfg, dev = eng.cfg, eng.device
         self.B, self.b_emb = B, b_emb
+        self.fused_gn_stats = eng.fused_gn_stats
         H = cfg.img_resolution
         f32 = dict(device=dev, dtype=torch.float32)
         self.x_in = torch.zeros(B, cfg.in_channels, H, H, **f32)                  # c_in * x  (NCHW fp32)
@@ -150,6 +151,8 @@ class ForwardPlan:
         self.plan = Plan()
         self._scratch: Dict[str, torch.Tensor] = {}
         self.block_out: Dict[str, torch.Tensor] = {}      # per-block outputs (persistent; per-layer parity tests)
+        # data_ptr -> fp32 [M/64, C, 2] per-channel (sum, sumsq) left behind by the GEMM that produced the tensor
+        self._stats: Dict[int, torch.Tensor] = {}
         self._build(eng)
         if eng.use_graphs:
             torch.cuda.synchronize(dev)
@@ -166,6 +169,16 @@ class ForwardPlan:
     def _act(self, key: str, B, H, W, C) -> torch.Tensor:
         return self._buf(key, B * H * W * C)[:B * H * W * C].view(B, H, W, C)
 
+    def _new_stats(self, t: torch.Tensor, key: Optional[str] = None) -> Optional[torch.Tensor]:
+        """Statistics buffer for a GEMM output that a GroupNorm will consume (None when the fused path is off)."""
+        if not self.fused_gn_stats:
+            return None
+        B, H, W, C = t.shape
+        n = (B * H * W // 64) * C * 2
+        st = (self._buf(key, n, torch.float32)[:n] if key else torch.empty(n, device=t.device, dtype=torch.float32))
+        self._stats[t.data_ptr()] = st
+        return st
+
     @staticmethod
     def _num_groups(C: int) -> int:
         return _groups(C)                 # EDM: min(32, C // 4) (networks.py:99)
@@ -179,6 +192,17 @@ class ForwardPlan:
     def _gn(self, xs, C, H, W, gamma, beta, out, *, silu=True, resample=0, raw_out=None, film=None, pre_add=None,
             label=''):
         g = self._num_groups(C)
+        stats = [self._stats.get(t.data_ptr()) for t in xs]
+        if all(st is not None for st in stats):
+            # statistics come from the producing GEMMs' epilogues: no pass over the activations
+            mr = self._buf('mean_rstd', self.B * 64 * 2, torch.float32)[:self.B * g * 2]
+            self.plan.add_gn_finalize(stats, [t.shape[3] for t in xs], self.B, H * W, g, self._eps, mr, pre_add=pre_add,
+                                      b_emb=self.b_emb, label=f'{label}.finalize')
+            self.plan.add_gn_apply(xs, g, None, 1, self._eps, gamma, beta, out, pre_add=pre_add,
+                                   film_scale=film[0] if film else None, film_shift=film[1] if film else None,
+                                   b_emb=self.b_emb, silu=silu, resample=resample, raw_out=raw_out, mean_rstd=mr,
+                                   label=f'{label}.apply')
+            return
         splits = self._splits(H * W)
         partial = self._buf('partial', self.B * 512 * 32 * 2, torch.float64)[:self.B * splits * g * 2].view(
             self.B, splits, g, 2)
@@ -229,7 +253,7 @@ class ForwardPlan:
                 P.add_im2col(self.x_in, col, label=f'{blk.name}.im2col')
                 x = torch.empty(B, H, H, blk.cout, device=dev, dtype=torch.bfloat16)
                 P.add_gemm([col], [(0, 1, 0, 1)], W_[f'{blk.name}.w'], blk.cout, x, bias=W_[f'{blk.name}.b'], alg_k=9 * blk.cin,
-                           label=f'{blk.name}')
+                           gn_stats=self._new_stats(x), label=f'{blk.name}')
             else:
                 x = self._block(eng, blk, [x])
             self.block_out[blk.name] = x
@@ -275,7 +299,8 @@ class ForwardPlan:
         self._gn(xs, cin, Hin, Hin, W_[f'{n}.norm0.weight'], W_[f'{n}.norm0.bias'], a0, silu=True, resample=resample,
                  raw_out=xr, label=f'{n}.norm0')
         h = self._act('h', B, Ho, Ho, cout)
-        P.add_gemm([a0], [(0, 9, 0, cin // 64)], W_[f'{n}.conv0.w'], cout, h, bias=W_[f'{n}.conv0.b'], label=f'{n}.conv0')
+        P.add_gemm([a0], [(0, 9, 0, cin // 64)], W_[f'{n}.conv0.w'], cout, h, bias=W_[f'{n}.conv0.b'],
+                   gn_stats=self._new_stats(h, 'h_stats'), label=f'{n}.conv0')
         a1 = self._act('a1', B, Ho, Ho, cout)
         off = eng.affine_off[n]
         if cfg.adaptive_scale:
@@ -290,12 +315,12 @@ class ForwardPlan:
             srcs = [a1] + skip_src
             segs = [(0, 9, 0, cout // 64)] + [(i + 1, 1, 0, t.shape[3] // 64) for i, t in enumerate(skip_src)]
             P.add_gemm(srcs, segs, W_[f'{n}.conv1skip.w'], cout, out, bias=W_[f'{n}.conv1skip.b'],
-                       out_scale=cfg.skip_scale, label=f'{n}.conv1+skip')
+                       out_scale=cfg.skip_scale, gn_stats=self._new_stats(out), label=f'{n}.conv1+skip')
         else:
             res = xr if need_raw else xs[0]
             assert len(xs) == 1
             P.add_gemm([a1], [(0, 9, 0, cout // 64)], W_[f'{n}.conv1.w'], cout, out, bias=W_[f'{n}.conv1.b'],
-                       residual=res, out_scale=cfg.skip_scale, label=f'{n}.conv1')
+                       residual=res, out_scale=cfg.skip_scale, gn_stats=self._new_stats(out), label=f'{n}.conv1')
         if not blk.attention:
             return out
         heads, L = blk.heads, Ho * Ho
@@ -313,16 +338,18 @@ class ForwardPlan:
                         v_col0=2 * cout, head_dim=hd, label=f'{n}.attn')
         out2 = torch.empty(B, Ho, Ho, cout, device=dev, dtype=torch.bfloat16)
         P.add_gemm([att], [(0, 1, 0, cout // 64)], W_[f'{n}.proj.w'], cout, out2, bias=W_[f'{n}.proj.b'], residual=out,
-                   out_scale=cfg.skip_scale, label=f'{n}.proj')
+                   out_scale=cfg.skip_scale, gn_stats=self._new_stats(out2), label=f'{n}.proj')
         return out2
 
 
 class UNetEngine:
     """Packed weights + cached ForwardPlans.  `forward(x_in, c_noise, labels)` returns F_x."""
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device='cuda', use_graphs: bool = True):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device='cuda', use_graphs: bool = True,
+                 fused_gn_stats: bool = True):
         from . import _lib
         self.use_graphs = use_graphs
+        self.fused_gn_stats = fused_gn_stats      # GroupNorm statistics from the producing GEMM's epilogue
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise RuntimeError('UNetEngine requires a CUDA device (B200); there is no CPU fallback')

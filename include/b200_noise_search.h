@@ -135,11 +135,10 @@ typedef struct {
   void* out;                 /* bf16 or fp32 [M, ld_out] */
   int32_t ld_out;
   int32_t out_fp32;
-  /* qkv mode: columns >= vt_col_start are written transposed as V^T
-   * [batch*heads, 64, H*W] bf16 for the attention kernel (networks.py:182-184). */
-  void* vt_out;
-  int32_t vt_col_start;
-  int32_t heads;
+  /* optional (bf16 output, M % 64 == 0): fp32 [M/64, N, 2] = per-channel (sum, sum of squares) of the
+   * STORED values over each 64-row half tile, reduced in the epilogue in a fixed order; feeds
+   * b200ns_plan_add_gn_finalize so the consumer's GroupNorm needs no statistics pass over HBM. */
+  float* gn_stats;
 } b200ns_gemm_desc;
 int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d);
 
@@ -157,6 +156,21 @@ typedef struct {
 } b200ns_gn_stats_desc;
 int b200ns_plan_add_gn_stats(b200ns_plan* p, const b200ns_gn_stats_desc* d);
 
+/* GroupNorm statistics from the per-channel sums a producing GEMM left behind (b200ns_gemm_desc.gn_stats):
+ * up to two concatenated sources; fp64 accumulation in a fixed order (bit-identical for identical inputs at
+ * any batch position); pre_add as in gn_stats.  Writes fp32 [batch, groups, 2] = (mean, rstd)
+ * (networks.py:104-106: var = E[x^2] - mean^2, biased, rstd = 1/sqrt(var + eps)). */
+typedef struct {
+  const float* stats_ptr[2]; /* fp32 [batch*HW/64, x_channels[i], 2] */
+  int32_t x_channels[2];
+  int32_t batch, HW, groups;
+  const float* pre_add;
+  int32_t ld_pre_add, b_emb;
+  float eps;
+  float* mean_rstd;          /* fp32 [batch, groups, 2] */
+} b200ns_gn_finalize_desc;
+int b200ns_plan_add_gn_finalize(b200ns_plan* p, const b200ns_gn_finalize_desc* d);
+
 /* GroupNorm apply + optional FiLM + optional SiLU + optional 2x resample, bf16 -> bf16:
  *   y = act( (x+pre_add - mean)*rstd*gamma + beta ) ; FiLM: y = act( shift + norm*(scale+1) )
  * (networks.py:168, 173, 175, 182, 460).  resample: 0 none, 1 = 2x nearest up, 2 = 2x2 mean down
@@ -166,7 +180,7 @@ typedef struct {
   const void* x_ptr[2];
   int32_t x_channels[2];
   int32_t batch, H, W, groups;
-  const double* partial;     /* from b200ns_plan_add_gn_stats */
+  const double* partial;     /* from b200ns_plan_add_gn_stats (or NULL with mean_rstd) */
   int32_t splits;
   float eps;
   const float* gamma;
@@ -180,6 +194,7 @@ typedef struct {
   int32_t resample;
   void* out;                 /* bf16 [batch, H', W', C] */
   void* raw_out;             /* bf16 [batch, H', W', C] or NULL */
+  const float* mean_rstd;    /* fp32 [batch, groups, 2] from gn_finalize; when set, `partial` is ignored */
 } b200ns_gn_apply_desc;
 int b200ns_plan_add_gn_apply(b200ns_plan* p, const b200ns_gn_apply_desc* d);
 

@@ -226,22 +226,54 @@ def test_attention_head_dim_256(ops, B, L):
     assert _rel_err(out, w @ v) < 1e-2
 
 
-def test_qkv_gemm_writes_v_transposed(ops):
+@pytest.mark.parametrize('B,H,C0,C1,Cout,k,pre', [
+    (2, 16, 128, 0, 192, 3, False), (3, 8, 64, 64, 128, 1, False), (2, 32, 64, 0, 384, 3, True), (5, 8, 192, 128, 768, 3, False),
+])
+def test_gemm_epilogue_gn_stats_and_finalize(ops, B, H, C0, C1, Cout, k, pre):
+    """The GEMM epilogue leaves per-channel (sum, sumsq) of the STORED bf16 output per 64-row half tile; gn_finalize
+    turns the statistics of up to two concatenated tensors into (mean, rstd); gn_apply consumes them.  Checked against
+    sums recomputed from the stored tensor (tight) and against torch group_norm of the concat (GN tolerance)."""
     torch.manual_seed(6)
     dev = 'cuda'
-    B, H, C, heads = 2, 8, 128, 2
-    x = _nhwc(torch.randn(B, C, H, H, device=dev))
-    w = (torch.randn(3 * C, C, device=dev) / math.sqrt(C)).to(torch.bfloat16)
-    bias = torch.randn(3 * C, device=dev)
-    qk = torch.empty(B, H, H, 2 * C, device=dev, dtype=torch.bfloat16)
-    vt = torch.empty(B * heads * 64, H * H, device=dev, dtype=torch.bfloat16)
+    outs, stats = [], []
+    for Cin in [c for c in (C0, C1) if c]:
+        x = _nhwc(torch.randn(B, Cin, H, H, device=dev))
+        w = torch.randn(Cout, Cin, k, k, device=dev) / math.sqrt(Cin * k * k)
+        bias = torch.randn(Cout, device=dev)
+        res = _nhwc(torch.randn(B, Cout, H, H, device=dev))
+        out = torch.empty(B, H, H, Cout, device=dev, dtype=torch.bfloat16)
+        st = torch.full((B * H * H // 64, Cout, 2), float('nan'), device=dev)
+        plan = ops.Plan()
+        plan.add_gemm([x], [(0, k * k, 0, Cin // 64)], _pack_w(w), Cout, out, bias=bias, residual=res, out_scale=0.7,
+                      gn_stats=st)
+        plan.run()
+        torch.cuda.synchronize()
+        ref = (F.conv2d(x.float().permute(0, 3, 1, 2), _pack_w(w).float().reshape(Cout, k, k, Cin).permute(0, 3, 1, 2), bias,
+                        padding=k // 2).permute(0, 2, 3, 1) + res.float()) * 0.7
+        assert _rel_err(out, ref) < 6e-3
+        o64 = out.double().reshape(-1, 64, Cout)
+        assert torch.allclose(st[..., 0].double(), o64.sum(1), rtol=1e-5, atol=1e-4)
+        assert torch.allclose(st[..., 1].double(), (o64 * o64).sum(1), rtol=1e-5, atol=1e-4)
+        outs.append(out)
+        stats.append(st)
+    C = Cout * len(outs)
+    groups = min(32, C // 4)
+    pa = torch.randn(1, C, device=dev) if pre else None
+    gamma, beta = torch.randn(C, device=dev), torch.randn(C, device=dev)
+    mr = torch.empty(B, groups, 2, device=dev)
+    y = torch.empty(B, H, H, C, device=dev, dtype=torch.bfloat16)
     plan = ops.Plan()
-    plan.add_gemm([x], [(0, 1, 0, C // 64)], w, 3 * C, qk, bias=bias, vt_out=vt, vt_col_start=2 * C, heads=heads)
+    plan.add_gn_finalize(stats, [Cout] * len(outs), B, H * H, groups, 1e-5, mr, pre_add=pa)
+    plan.add_gn_apply(outs, groups, None, 1, 1e-5, gamma, beta, y, pre_add=pa, silu=True, mean_rstd=mr)
     plan.run()
-    ref = x.float().reshape(B, H * H, C) @ w.float().t() + bias
-    assert _rel_err(qk.reshape(B, H * H, 2 * C), ref[..., :2 * C]) < 6e-3
-    v_ref = ref[..., 2 * C:].reshape(B, H * H, heads, 64).permute(0, 2, 3, 1).reshape(B * heads * 64, H * H)
-    assert _rel_err(vt, v_ref) < 6e-3
+    xc = torch.cat(outs, dim=3).float().permute(0, 3, 1, 2)
+    if pre:
+        xc = xc + pa.view(1, C, 1, 1)
+    xg = xc.double().reshape(B, groups, -1)
+    assert torch.allclose(mr[..., 0].double(), xg.mean(2), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(mr[..., 1].double(), 1.0 / torch.sqrt(xg.var(2, unbiased=False) + 1e-5), rtol=1e-4)
+    ref = F.silu(F.group_norm(xc, groups, gamma, beta, 1e-5)).permute(0, 2, 3, 1)
+    assert _rel_err(y, ref) < 5e-3
 
 
 def test_linear(ops):

@@ -22,7 +22,7 @@ class GemmDesc(C.Structure):
     _fields_ = [('a_ptr', c_vp * 3), ('a_channels', c_i32 * 3), ('n_seg', c_i32), ('seg', KSeg * 4),
                 ('batch', c_i32), ('H', c_i32), ('W', c_i32), ('w_ptr', c_vp), ('N', c_i32), ('Npad', c_i32),
                 ('Ktot', c_i32), ('bias', c_vp), ('residual', c_vp), ('ld_res', c_i32), ('out_scale', c_f32),
-                ('out', c_vp), ('ld_out', c_i32), ('out_fp32', c_i32), ('gn_stats', c_vp)]
+                ('out', c_vp), ('ld_out', c_i32), ('out_fp32', c_i32), ('gn_stats', c_vp), ('reverse', c_i32)]
 
 
 class GnStatsDesc(C.Structure):
@@ -35,7 +35,7 @@ class GnApplyDesc(C.Structure):
                 ('groups', c_i32), ('partial', c_vp), ('splits', c_i32), ('eps', c_f32), ('gamma', c_vp),
                 ('beta', c_vp), ('pre_add', c_vp), ('ld_pre_add', c_i32), ('film_scale', c_vp), ('film_shift', c_vp),
                 ('ld_film', c_i32), ('b_emb', c_i32), ('silu', c_i32), ('resample', c_i32), ('out', c_vp),
-                ('raw_out', c_vp), ('mean_rstd', c_vp)]
+                ('raw_out', c_vp), ('mean_rstd', c_vp), ('reverse', c_i32)]
 
 
 class GnFinalizeDesc(C.Structure):
@@ -45,7 +45,7 @@ class GnFinalizeDesc(C.Structure):
 
 class AttnDesc(C.Structure):
     _fields_ = [('qk', c_vp), ('ld_qk', c_i32), ('k_col0', c_i32), ('vt', c_vp), ('out', c_vp), ('ld_out', c_i32),
-                ('batch', c_i32), ('heads', c_i32), ('L', c_i32), ('v_col0', c_i32), ('head_dim', c_i32)]
+                ('batch', c_i32), ('heads', c_i32), ('L', c_i32), ('v_col0', c_i32), ('head_dim', c_i32), ('reverse', c_i32)]
 
 
 class LinearDesc(C.Structure):

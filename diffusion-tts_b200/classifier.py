@@ -49,6 +49,8 @@ class ClassifierPlan(ForwardPlan):
         self.block_out: Dict[str, torch.Tensor] = {}
         self._stats: Dict[int, torch.Tensor] = {}
         self.fused_gn_stats = True
+        self._dir: Dict[int, bool] = {}
+        self.alternate_walk = True
         self._eps = 1e-5
         self._build_classifier(eng)
         if eng.use_graphs:

@@ -21,6 +21,7 @@ struct AttnArgs {
   int heads, L;
   int k_col0;
   int v_col0;      // VROW mode: V lives row-major in the same [batch*L, ld] matrix at this column
+  int reverse;     // walk (batch, head, query tile) last-to-first: start on what the qkv GEMM wrote last
 };
 
 template <int KT>
@@ -51,8 +52,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int bh = blockIdx.y, bi = bh / a.heads, head = bh % a.heads;
-  const int q0 = blockIdx.x * 128;
+  const int bh = a.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y, bi = bh / a.heads, head = bh % a.heads;
+  const int q0 = (a.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * 128;
   const int row_base = bi * a.L;
   const int nkt = a.L / KT;
 
@@ -253,8 +254,8 @@ attention_kernel_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int bh = blockIdx.y, bi = bh / a.heads, head = bh % a.heads;
-  const int q0 = blockIdx.x * 128;
+  const int bh = a.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y, bi = bh / a.heads, head = bh % a.heads;
+  const int q0 = (a.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * 128;
   const int row_base = bi * a.L;
   const int nkt = a.L / KT;
 
@@ -437,8 +438,8 @@ attention_d256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int bi = blockIdx.y;
-  const int q0 = blockIdx.x * 128;
+  const int bi = a.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
+  const int q0 = (a.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * 128;
   const int row_base = bi * a.L;
   const int n = a.L / 64;            // key chunks (1..4)
 

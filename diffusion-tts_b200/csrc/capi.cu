@@ -583,6 +583,7 @@ int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d) {
   a.ld_out = d->ld_out;
   a.out_fp32 = d->out_fp32;
   a.gn_stats = reinterpret_cast<float2*>(d->gn_stats);
+  a.reverse = d->reverse;
   if (d->gn_stats != nullptr && (BN == 16 || a.M % 64)) return fail("gemm: gn_stats needs bf16 output, N tiles >= 64 and M % 64 == 0");
   if (!d->out_fp32 && (d->ld_out % 8)) return fail("gemm: ld_out must be a multiple of 8 for bf16 output");
   if (d->residual != nullptr && (d->ld_res % 8)) return fail("gemm: ld_res must be a multiple of 8");
@@ -678,6 +679,7 @@ int b200ns_plan_add_gn_apply(b200ns_plan* p, const b200ns_gn_apply_desc* d) {
   a.out = reinterpret_cast<__nv_bfloat16*>(d->out);
   a.raw_out = reinterpret_cast<__nv_bfloat16*>(d->raw_out);
   a.mean_rstd = reinterpret_cast<const float2*>(d->mean_rstd);
+  a.reverse = d->reverse;
   if (d->mean_rstd == nullptr && d->partial == nullptr) return fail("gn_apply: need partial or mean_rstd");
   const int VC = a.C / 8;
   a.PY = 256 / VC;
@@ -732,6 +734,7 @@ int b200ns_plan_add_attention(b200ns_plan* p, const b200ns_attn_desc* d) {
   o.args.L = d->L;
   o.args.k_col0 = d->k_col0;
   o.args.v_col0 = d->v_col0;
+  o.args.reverse = d->reverse;
   const uint64_t M = static_cast<uint64_t>(d->batch) * d->L;
   if (o.head_dim == 256) {
     if (d->heads != 1 || d->L > 256 || d->vt != nullptr) return fail("attention: head_dim 256 needs 1 head, L <= 256, row-major V");

@@ -49,6 +49,7 @@ struct GemmArgs {
   int ld_out;
   int out_fp32;
   float2* gn_stats;              // [M/64, N] (sum, sum of squares) per 64-row half tile, or null
+  int reverse;                   // walk the tiles last-to-first (start on what the producer of A wrote last: L2 hits)
 };
 
 template <int BN>
@@ -79,7 +80,8 @@ DEVINL void gemm_producer(const CUtensorMap& tmA0, const CUtensorMap& tmA1, cons
   int stage = 0;
   uint32_t phase = 0;
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int mt = tile / a.n_tiles, nt = tile % a.n_tiles;
+    const int tl = a.reverse ? num_tiles - 1 - tile : tile;
+    const int mt = tl / a.n_tiles, nt = tl % a.n_tiles;
     int n0, y0;
     if (a.tiles_per_img > 0) {
       n0 = mt / a.tiles_per_img;
@@ -229,7 +231,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int tile = blockIdx.x + static_cast<int>(kk / NSUB) * gridDim.x;
       if (tile >= num_tiles) return;
       const int j = kk % NSUB;
-      const int mt = tile / a.n_tiles, nt = tile % a.n_tiles;
+      const int tl = a.reverse ? num_tiles - 1 - tile : tile;
+    const int mt = tl / a.n_tiles, nt = tl % a.n_tiles;
       const uint32_t s = kk % SLOTS;
       mbar_arrive_expect_tx(&rfull_bar[s], Cfg::SLOT_BYTES);
       tma_load_2d(smem_slot + s * Cfg::SLOT_BYTES, &tmR, &rfull_bar[s], nt * BN + j * 64, mt * 128);
@@ -243,7 +246,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int mt = tile / a.n_tiles, nt = tile % a.n_tiles;
+      const int tl = a.reverse ? num_tiles - 1 - tile : tile;
+    const int mt = tl / a.n_tiles, nt = tl % a.n_tiles;
       // bias of this tile's columns -> smem (double buffered by accumulator index)
       if (et < BN) {
         const int n = nt * BN + et;
@@ -253,18 +257,13 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      uint32_t r[32];
+      tmem_ld32(t_row + half * 32, r);
 #pragma unroll 1
       for (int j = 0; j < NSUB; ++j, ++k) {
         const uint32_t slot = slot0 + (k % SLOTS) * Cfg::SLOT_BYTES;
-        uint32_t r[32];
-        tmem_ld32(t_row + j * 64 + half * 32, r);
         if (has_res) mbar_wait(&rfull_bar[k % SLOTS], (k / SLOTS) & 1);
         tmem_ld_wait();
-        if (j == NSUB - 1) {                // accumulator fully read: hand it back to the MMA warp early
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        }
         float v[32];
         const uint32_t bsrc = bias0 + static_cast<uint32_t>(acc * BN + j * 64 + half * 32) * 4u;
 #pragma unroll
@@ -274,6 +273,13 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + __uint_as_float(bb.y);
           v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + __uint_as_float(bb.z);
           v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + __uint_as_float(bb.w);
+        }
+        if (j == NSUB - 1) {                // accumulator fully read: hand it back to the MMA warp early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        } else {                            // next sub-box's accumulator columns stream in behind this one's maths
+          tmem_ld32(t_row + (j + 1) * 64 + half * 32, r);
         }
         if (has_res) {
 #pragma unroll
@@ -308,25 +314,43 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           bulk_commit_group();
         }
         if (a.gn_stats != nullptr) {
-          // column sums of the stored bf16 values: lane -> (column, row quarter); fixed order, no atomics
-          const int col = (et >> 5) * 8 + (lane >> 2);
-          const int rq = lane & 3;
-          const uint32_t cbase = slot + ((col & 7) << 1);
-          const uint32_t unit = static_cast<uint32_t>(col >> 3);
-          float s = 0.f, ss = 0.f;
-#pragma unroll 8
-          for (int i = 0; i < 32; ++i) {
-            const uint32_t rr = static_cast<uint32_t>(rq * 32 + ((i + rq) & 31));
-            const float x = lds_bf16(cbase + rr * 128u + ((unit ^ (rr & 7u)) << 4));
-            s += x;
-            ss = fmaf(x, x, ss);
+          // column sums of the stored bf16 values, fixed order, no atomics.  lane -> (row residue rg = lane & 7,
+          // column pair cp = lane >> 3) of the warp's 16-byte unit; rows rg + 8*i: the 8 residues hit 8 different
+          // swizzle positions (conflict-free) and the per-row offset i*1024 is an immediate.
+          const uint32_t rg = lane & 7, cp = lane >> 3;
+          const uint32_t unit = static_cast<uint32_t>(et >> 5);
+          const uint32_t base = slot + rg * 128u + ((unit ^ rg) << 4) + cp * 4u;
+          float s0[2] = {0.f, 0.f}, q0[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f}, q1[2] = {0.f, 0.f};
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint32_t w = lds32(base + i * 1024u);
+            const float x0 = __uint_as_float(w << 16), x1 = __uint_as_float(w & 0xffff0000u);
+            const int hf = i >> 3;
+            s0[hf] += x0;
+            q0[hf] = fmaf(x0, x0, q0[hf]);
+            s1[hf] += x1;
+            q1[hf] = fmaf(x1, x1, q1[hf]);
           }
-          s += __shfl_xor_sync(0xffffffffu, s, 1);
-          ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-          const int hrow = mt * 2 + (rq >> 1);         // 64-row half tile
-          const int n = nt * BN + j * 64 + col;
-          if ((rq & 1) == 0 && hrow * 64 < a.M && n < a.N)
-            a.gn_stats[static_cast<size_t>(hrow) * a.N + n] = make_float2(s, ss);
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              s0[hf] += __shfl_xor_sync(0xffffffffu, s0[hf], o);
+              q0[hf] += __shfl_xor_sync(0xffffffffu, q0[hf], o);
+              s1[hf] += __shfl_xor_sync(0xffffffffu, s1[hf], o);
+              q1[hf] += __shfl_xor_sync(0xffffffffu, q1[hf], o);
+            }
+          }
+          if (rg < 2) {                               // lane rg = 0 writes the first 64-row half, rg = 1 the second
+            const int hrow = mt * 2 + static_cast<int>(rg);
+            const int n = nt * BN + j * 64 + static_cast<int>(unit * 8 + cp * 2);
+            if (hrow * 64 < a.M && n + 1 < a.N) {
+              const float4 o4 = rg == 0 ? make_float4(s0[0], q0[0], s1[0], q1[0]) : make_float4(s0[1], q0[1], s1[1], q1[1]);
+              *reinterpret_cast<float4*>(a.gn_stats + static_cast<size_t>(hrow) * a.N + n) = o4;
+            } else if (hrow * 64 < a.M && n < a.N) {
+              a.gn_stats[static_cast<size_t>(hrow) * a.N + n] = rg == 0 ? make_float2(s0[0], q0[0]) : make_float2(s0[1], q0[1]);
+            }
+          }
         }
       }
       if (++acc == 2) {
@@ -405,7 +429,8 @@ gemm_small_n_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int mt = tile / a.n_tiles, nt = tile % a.n_tiles;
+      const int tl = a.reverse ? num_tiles - 1 - tile : tile;
+    const int mt = tl / a.n_tiles, nt = tl % a.n_tiles;
       const int m = mt * 128 + row;
       const bool m_ok = m < a.M;
       mbar_wait(&tfull_bar[acc], acc_phase);

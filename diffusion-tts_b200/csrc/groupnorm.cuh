@@ -236,6 +236,7 @@ struct GnApplyArgs {
   __nv_bfloat16* raw_out;
   int PY, ITER;
   const float2* mean_rstd; // [batch, groups] from gn_finalize_kernel (then `partial` is unused)
+  int reverse;             // walk samples / pixel chunks last-to-first (L2 hits on what the producer wrote last)
 };
 
 // grid (pixel chunks, batch); block = (C/8) * PY threads
@@ -244,7 +245,8 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const GnApplyArgs a) {
   __shared__ float s_rstd[64];
   const int VC = a.C >> 3;
   const int vx = threadIdx.x % VC, py = threadIdx.x / VC;
-  const int bi = blockIdx.y;
+  const int bi = a.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
+  const int bx = a.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
   const int HW = a.H * a.W;
   if (a.mean_rstd != nullptr) {
     if (threadIdx.x < a.groups) {
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const GnApplyArgs a) {
   const int outH = a.resample == 1 ? a.H * 2 : (a.resample == 2 ? a.H / 2 : a.H);
   const size_t out_base = static_cast<size_t>(bi) * outH * outW * a.C + c;
   const int dom = a.resample == 2 ? outH * outW : HW;      // loop domain
-  const int p_begin = blockIdx.x * a.PY * a.ITER + py;
+  const int p_begin = bx * a.PY * a.ITER + py;
 
   if (a.resample == 2) {
     for (int it = 0; it < a.ITER; ++it) {
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const GnApplyArgs a) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float v = f[t][j] * ka[j] + kb[j];
-          if (a.silu) v = silu_f(v);
+          if (a.silu) v = silu_tanh(v);
           accv[j] += v;
           accr[j] += f[t][j];
         }
@@ -338,23 +340,23 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const GnApplyArgs a) {
       if (a.raw_out != nullptr) store8(a.raw_out + out_base + static_cast<size_t>(p) * a.C, accr);
     }
   } else {
-    for (int it0 = 0; it0 < a.ITER; it0 += 4) {
-      uint4 raw[4];
-      int pp[4];
+    for (int it0 = 0; it0 < a.ITER; it0 += 8) {
+      uint4 raw[8];                                   // 8 independent 16-byte loads in flight per thread
+      int pp[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        pp[u] = p_begin + (it0 + u) * a.PY;
+      for (int u = 0; u < 8; ++u) {
+        pp[u] = (it0 + u < a.ITER) ? p_begin + (it0 + u) * a.PY : dom;
         if (pp[u] < dom) raw[u] = load_raw(src + static_cast<size_t>(pp[u]) * ld);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         if (pp[u] >= dom) continue;
         float f[8], v[8];
         unpack8(raw[u], f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           v[j] = f[j] * ka[j] + kb[j];
-          if (a.silu) v[j] = silu_f(v[j]);
+          if (a.silu) v[j] = silu_tanh(v[j]);
         }
         if (a.resample == 0) {
           store8(a.out + out_base + static_cast<size_t>(pp[u]) * a.C, v);

@@ -209,7 +209,8 @@ class Plan:
         return [evs[i].elapsed_time(evs[i + 1]) for i in range(n)]
 
     def add_gemm(self, a: Sequence[torch.Tensor], segs: Sequence[Tuple[int, int, int, int]], w: torch.Tensor, N: int,
-                 out: torch.Tensor, *, bias=None, residual=None, out_scale=1.0, gn_stats=None, label='gemm', alg_k=None):
+                 out: torch.Tensor, *, bias=None, residual=None, out_scale=1.0, gn_stats=None, reverse=False, label='gemm',
+                 alg_k=None):
         """a: 1-3 NHWC bf16 tensors [B,H,W,C]; segs: (src, taps, cstart, cblocks); w: bf16 [Npad,Ktot].
         gn_stats: optional fp32 [M/64, N, 2] receiving per-channel (sum, sumsq) of the stored output."""
         d = L.GemmDesc()
@@ -235,6 +236,7 @@ class Plan:
             if gn_stats.numel() != (B * H * W_ // 64) * N * 2:
                 raise RuntimeError('gn_stats must be fp32 [M/64, N, 2]')
         d.gn_stats = L.ptr(gn_stats)
+        d.reverse = int(reverse)
         self._k(*a, w, bias, residual, out, gn_stats)
         L.check(L.lib().b200ns_plan_add_gemm(self._h, C.byref(d)), 'plan_add_gemm')
         self.labels.append(label)
@@ -282,7 +284,8 @@ class Plan:
 
     def add_gn_apply(self, x: Sequence[torch.Tensor], groups: int, partial: Optional[torch.Tensor], splits: int, eps: float,
                      gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor, *, pre_add=None, film_scale=None,
-                     film_shift=None, b_emb=1, silu=True, resample=0, raw_out=None, mean_rstd=None, label='gn_apply'):
+                     film_shift=None, b_emb=1, silu=True, resample=0, raw_out=None, mean_rstd=None, reverse=False,
+                     label='gn_apply'):
         d = L.GnApplyDesc()
         B, H, W_, _ = x[0].shape
         for i, t in enumerate(x):
@@ -300,6 +303,7 @@ class Plan:
         d.silu, d.resample = int(silu), resample
         d.out, d.raw_out = L.ptr(_c(out, torch.bfloat16)), L.ptr(raw_out)
         d.mean_rstd = L.ptr(mean_rstd)
+        d.reverse = int(reverse)
         self._k(*x, partial, gamma, beta, pre_add, film_scale, film_shift, out, raw_out, mean_rstd)
         L.check(L.lib().b200ns_plan_add_gn_apply(self._h, C.byref(d)), 'plan_add_gn_apply')
         self.labels.append(label)
@@ -307,7 +311,7 @@ class Plan:
         self.flops.append(0.0)
 
     def add_attention(self, qk: torch.Tensor, k_col0: int, vt: Optional[torch.Tensor], out: torch.Tensor, batch: int,
-                      heads: int, Lseq: int, label='attention', v_col0: int = 0, head_dim: int = 64):
+                      heads: int, Lseq: int, label='attention', v_col0: int = 0, head_dim: int = 64, reverse=False):
         """qk: [batch*L, ld] with Q at col head*64, K at k_col0 + head*64; V either transposed in `vt`
         ([batch*heads*64, L]) or (vt=None) row-major in `qk` at v_col0 + head*64."""
         d = L.AttnDesc()
@@ -315,6 +319,7 @@ class Plan:
         d.vt = L.ptr(vt)
         d.v_col0 = v_col0
         d.head_dim = head_dim
+        d.reverse = int(reverse)
         d.out, d.ld_out = L.ptr(_c(out, torch.bfloat16)), out.shape[-1]
         d.batch, d.heads, d.L = batch, heads, Lseq
         self._k(qk, vt, out)

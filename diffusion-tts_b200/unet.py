@@ -153,6 +153,8 @@ class ForwardPlan:
         self.block_out: Dict[str, torch.Tensor] = {}      # per-block outputs (persistent; per-layer parity tests)
         # data_ptr -> fp32 [M/64, C, 2] per-channel (sum, sumsq) left behind by the GEMM that produced the tensor
         self._stats: Dict[int, torch.Tensor] = {}
+        self._dir: Dict[int, bool] = {}                   # data_ptr -> tensor was written last-to-first
+        self.alternate_walk = getattr(eng, 'alternate_walk', True)
         self._build(eng)
         if eng.use_graphs:
             torch.cuda.synchronize(dev)
@@ -168,6 +170,15 @@ class ForwardPlan:
 
     def _act(self, key: str, B, H, W, C) -> torch.Tensor:
         return self._buf(key, B * H * W * C)[:B * H * W * C].view(B, H, W, C)
+
+    def _rev(self, src: torch.Tensor, dst: Optional[torch.Tensor] = None, *more) -> bool:
+        """Walk direction for an op reading `src`: opposite to the direction `src` was written in, so the op starts on
+        the rows its producer finished last (still in L2).  Records the direction on the op's outputs."""
+        rev = self.alternate_walk and not self._dir.get(src.data_ptr(), False)
+        for t in (dst,) + more:
+            if t is not None:
+                self._dir[t.data_ptr()] = rev
+        return rev
 
     def _new_stats(self, t: torch.Tensor, key: Optional[str] = None) -> Optional[torch.Tensor]:
         """Statistics buffer for a GEMM output that a GroupNorm will consume (None when the fused path is off)."""
@@ -201,7 +212,7 @@ class ForwardPlan:
             self.plan.add_gn_apply(xs, g, None, 1, self._eps, gamma, beta, out, pre_add=pre_add,
                                    film_scale=film[0] if film else None, film_shift=film[1] if film else None,
                                    b_emb=self.b_emb, silu=silu, resample=resample, raw_out=raw_out, mean_rstd=mr,
-                                   label=f'{label}.apply')
+                                   reverse=self._rev(xs[0], out, raw_out), label=f'{label}.apply')
             return
         splits = self._splits(H * W)
         partial = self._buf('partial', self.B * 512 * 32 * 2, torch.float64)[:self.B * splits * g * 2].view(
@@ -209,7 +220,8 @@ class ForwardPlan:
         self.plan.add_gn_stats(xs, g, partial, splits, pre_add=pre_add, b_emb=self.b_emb, label=f'{label}.stats')
         self.plan.add_gn_apply(xs, g, partial, splits, self._eps, gamma, beta, out, pre_add=pre_add,
                                film_scale=film[0] if film else None, film_shift=film[1] if film else None,
-                               b_emb=self.b_emb, silu=silu, resample=resample, raw_out=raw_out, label=f'{label}.apply')
+                               b_emb=self.b_emb, silu=silu, resample=resample, raw_out=raw_out,
+                               reverse=self._rev(xs[0], out, raw_out), label=f'{label}.apply')
 
     # -- build
     def _build(self, eng: 'UNetEngine'):
@@ -253,7 +265,7 @@ class ForwardPlan:
                 P.add_im2col(self.x_in, col, label=f'{blk.name}.im2col')
                 x = torch.empty(B, H, H, blk.cout, device=dev, dtype=torch.bfloat16)
                 P.add_gemm([col], [(0, 1, 0, 1)], W_[f'{blk.name}.w'], blk.cout, x, bias=W_[f'{blk.name}.b'], alg_k=9 * blk.cin,
-                           gn_stats=self._new_stats(x), label=f'{blk.name}')
+                           gn_stats=self._new_stats(x), reverse=self._rev(col, x), label=f'{blk.name}')
             else:
                 x = self._block(eng, blk, [x])
             self.block_out[blk.name] = x
@@ -269,7 +281,7 @@ class ForwardPlan:
                          label=blk.name)
             elif blk.kind == 'aux_conv':
                 P.add_gemm([aux_in], [(0, 9, 0, blk.cin // 64)], W_[f'{blk.name}.w'], blk.cout, self.out,
-                           bias=W_[f'{blk.name}.b'], label=blk.name)
+                           bias=W_[f'{blk.name}.b'], reverse=self._rev(aux_in), label=blk.name)
             else:
                 xs = [x]
                 if x.shape[3] != blk.cin:
@@ -283,7 +295,7 @@ class ForwardPlan:
             a = self._act('a0', B, H, H, C)
             self._gn([x], C, H, H, W_['out_norm.weight'], W_['out_norm.bias'], a, silu=True, label='out_norm')
             P.add_gemm([a], [(0, 9, 0, C // 64)], W_['out_conv.w'], cfg.out_channels, self.out, bias=W_['out_conv.b'],
-                       label='out_conv')
+                       reverse=self._rev(a), label='out_conv')
 
     def _block(self, eng: 'UNetEngine', blk: Block, xs: List[torch.Tensor]) -> torch.Tensor:
         cfg, P, W_ = eng.cfg, self.plan, eng.w
@@ -300,7 +312,7 @@ class ForwardPlan:
                  raw_out=xr, label=f'{n}.norm0')
         h = self._act('h', B, Ho, Ho, cout)
         P.add_gemm([a0], [(0, 9, 0, cin // 64)], W_[f'{n}.conv0.w'], cout, h, bias=W_[f'{n}.conv0.b'],
-                   gn_stats=self._new_stats(h, 'h_stats'), label=f'{n}.conv0')
+                   gn_stats=self._new_stats(h, 'h_stats'), reverse=self._rev(a0, h), label=f'{n}.conv0')
         a1 = self._act('a1', B, Ho, Ho, cout)
         off = eng.affine_off[n]
         if cfg.adaptive_scale:
@@ -315,12 +327,14 @@ class ForwardPlan:
             srcs = [a1] + skip_src
             segs = [(0, 9, 0, cout // 64)] + [(i + 1, 1, 0, t.shape[3] // 64) for i, t in enumerate(skip_src)]
             P.add_gemm(srcs, segs, W_[f'{n}.conv1skip.w'], cout, out, bias=W_[f'{n}.conv1skip.b'],
-                       out_scale=cfg.skip_scale, gn_stats=self._new_stats(out), label=f'{n}.conv1+skip')
+                       out_scale=cfg.skip_scale, gn_stats=self._new_stats(out), reverse=self._rev(a1, out),
+                       label=f'{n}.conv1+skip')
         else:
             res = xr if need_raw else xs[0]
             assert len(xs) == 1
             P.add_gemm([a1], [(0, 9, 0, cout // 64)], W_[f'{n}.conv1.w'], cout, out, bias=W_[f'{n}.conv1.b'],
-                       residual=res, out_scale=cfg.skip_scale, gn_stats=self._new_stats(out), label=f'{n}.conv1')
+                       residual=res, out_scale=cfg.skip_scale, gn_stats=self._new_stats(out), reverse=self._rev(a1, out),
+                       label=f'{n}.conv1')
         if not blk.attention:
             return out
         heads, L = blk.heads, Ho * Ho
@@ -331,14 +345,14 @@ class ForwardPlan:
         self._gn([out], cout, Ho, Ho, W_[f'{n}.norm2.weight'], W_[f'{n}.norm2.bias'], a2, silu=False, label=f'{n}.norm2')
         qkv = self._act('qkv', B, Ho, Ho, 3 * cout)          # [Q | K | V], each head-major, row-major per pixel
         P.add_gemm([a2], [(0, 1, 0, cout // 64)], W_[f'{n}.qkv.w'], 3 * cout, qkv, bias=W_[f'{n}.qkv.b'],
-                   label=f'{n}.qkv')
+                   reverse=self._rev(a2, qkv), label=f'{n}.qkv')
         att = self._act('a0', B, Ho, Ho, cout)
         # V is consumed in place as an MN-major UMMA operand: no transposed copy
         P.add_attention(qkv.view(B * L, 3 * cout), cout, None, att.view(B * L, cout), B, heads, L,
-                        v_col0=2 * cout, head_dim=hd, label=f'{n}.attn')
+                        v_col0=2 * cout, head_dim=hd, reverse=self._rev(qkv, att), label=f'{n}.attn')
         out2 = torch.empty(B, Ho, Ho, cout, device=dev, dtype=torch.bfloat16)
         P.add_gemm([att], [(0, 1, 0, cout // 64)], W_[f'{n}.proj.w'], cout, out2, bias=W_[f'{n}.proj.b'], residual=out,
-                   out_scale=cfg.skip_scale, gn_stats=self._new_stats(out2), label=f'{n}.proj')
+                   out_scale=cfg.skip_scale, gn_stats=self._new_stats(out2), reverse=self._rev(att, out2), label=f'{n}.proj')
         return out2
 
 
@@ -346,10 +360,11 @@ class UNetEngine:
     """Packed weights + cached ForwardPlans.  `forward(x_in, c_noise, labels)` returns F_x."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], device='cuda', use_graphs: bool = True,
-                 fused_gn_stats: bool = True):
+                 fused_gn_stats: bool = True, alternate_walk: bool = True):
         from . import _lib
         self.use_graphs = use_graphs
         self.fused_gn_stats = fused_gn_stats      # GroupNorm statistics from the producing GEMM's epilogue
+        self.alternate_walk = alternate_walk      # consecutive kernels walk the batch in opposite directions (L2 reuse)
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise RuntimeError('UNetEngine requires a CUDA device (B200); there is no CPU fallback')

@@ -139,6 +139,9 @@ typedef struct {
    * STORED values over each 64-row half tile, reduced in the epilogue in a fixed order; feeds
    * b200ns_plan_add_gn_finalize so the consumer's GroupNorm needs no statistics pass over HBM. */
   float* gn_stats;
+  /* 1: process the output tiles last-to-first.  Alternating the walk direction between producer and consumer
+   * makes the consumer start on the rows the producer wrote last, which are still in the 126 MB L2. */
+  int32_t reverse;
 } b200ns_gemm_desc;
 int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d);
 
@@ -195,6 +198,7 @@ typedef struct {
   void* out;                 /* bf16 [batch, H', W', C] */
   void* raw_out;             /* bf16 [batch, H', W', C] or NULL */
   const float* mean_rstd;    /* fp32 [batch, groups, 2] from gn_finalize; when set, `partial` is ignored */
+  int32_t reverse;           /* walk direction, see b200ns_gemm_desc.reverse */
 } b200ns_gn_apply_desc;
 int b200ns_plan_add_gn_apply(b200ns_plan* p, const b200ns_gn_apply_desc* d);
 
@@ -211,6 +215,7 @@ typedef struct {
   int32_t batch, heads, L;
   int32_t v_col0;
   int32_t head_dim;          /* 64 (default when 0) or 256 (one head, L <= 256: DDPM++, networks.py:263) */
+  int32_t reverse;           /* walk direction, see b200ns_gemm_desc.reverse */
 } b200ns_attn_desc;
 int b200ns_plan_add_attention(b200ns_plan* p, const b200ns_attn_desc* d);
 

@@ -6,11 +6,13 @@ import torch
 from diffusion_tts_b200 import build
 build.build()
 from diffusion_tts_b200.arch import adm_param_shapes, random_state_dict
-from diffusion_tts_b200.denoiser import B200Denoiser
+from diffusion_tts_b200.unet import UNetEngine
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 64
-net = B200Denoiser(random_state_dict(adm_param_shapes(), 1234), device='cuda')
-fp = net.engine.plan(B, 1)
+eng = UNetEngine(random_state_dict(adm_param_shapes(), 1234), device='cuda', use_graphs='--graph' in sys.argv,
+                 alternate_walk='--no-alt' not in sys.argv, fused_gn_stats='--no-fused-stats' not in sys.argv)
+fp = eng.plan(B, 1)
+fp.x_in.normal_()
 plan = fp.plan
 for _ in range(2):
     plan.run_timed()
@@ -21,6 +23,14 @@ for i, (lab, kind, fl, t) in enumerate(zip(plan.labels, plan.kinds, plan.flops, 
     rows.append((i, lab, kind, t, fl / (t * 1e-3) / 1e12 if fl else 0.0))
 tot = sum(ms)
 print(f'B={B} ops={len(ms)} total {tot:.3f} ms')
+if '--graph' in sys.argv:
+    for _ in range(3): plan.run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): plan.run()
+    e1.record(); torch.cuda.synchronize()
+    print(f'graph NFE: {e0.elapsed_time(e1) / 10:.3f} ms')
 agg = {}
 for i, lab, kind, t, tf in rows:
     a = agg.setdefault(kind, [0.0, 0.0, 0])

@@ -141,6 +141,7 @@ struct GnApplyOp {
 struct GnFinalizeOp {
   GnFinalizeArgs args;
   dim3 grid;
+  int n_pairs;
 };
 struct AttnOp {
   CUtensorMap tmQ, tmK, tmV;
@@ -267,7 +268,7 @@ int run_op(const Op& op, cudaStream_t st) {
       CK_LAUNCH("gn_apply_kernel");
       return 0;
     case OP_GN_FINALIZE:
-      gn_finalize_kernel<<<op.gnf.grid, 128, 0, st>>>(op.gnf.args);
+      gn_finalize_kernel<<<op.gnf.grid, 256, 0, st>>>(op.gnf.args, op.gnf.n_pairs);
       CK_LAUNCH("gn_finalize_kernel");
       return 0;
     case OP_ATTN:
@@ -716,7 +717,8 @@ int b200ns_plan_add_gn_finalize(b200ns_plan* p, const b200ns_gn_finalize_desc* d
   a.b_emb = d->b_emb > 0 ? d->b_emb : 1;
   a.eps = d->eps;
   a.mean_rstd = reinterpret_cast<float2*>(d->mean_rstd);
-  op.gnf.grid = dim3(d->groups, d->batch);
+  op.gnf.n_pairs = d->groups * d->batch;
+  op.gnf.grid = dim3((op.gnf.n_pairs + 7) / 8);
   p->ops.push_back(op);
   return 0;
 }

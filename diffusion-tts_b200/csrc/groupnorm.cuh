@@ -157,11 +157,12 @@ struct GnFinalizeArgs {
   float2* mean_rstd;       // [batch, groups]
 };
 
-// grid (groups, batch); 128 threads
-__global__ void __launch_bounds__(128) gn_finalize_kernel(const GnFinalizeArgs a) {
-  __shared__ double sh_s[128];
-  __shared__ double sh_q[128];
-  const int g = blockIdx.x, bi = blockIdx.y;
+// one warp per (sample, group); 8 warps per block; grid = ceil(batch*groups / 8)
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const GnFinalizeArgs a, int n_pairs) {
+  const int lane = threadIdx.x & 31;
+  const int pair = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (pair >= n_pairs) return;
+  const int bi = pair / a.groups, g = pair - bi * a.groups;
   const int R = a.HW >> 6;
   const int total = R * a.cpg;
   double ds = 0.0, dq = 0.0;
@@ -177,39 +178,34 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const GnFinalizeArgs a
     dq += q + 2.0 * pa * s + 64.0 * pa * pa;
     ds += s + 64.0 * pa;
   };
-  int i = threadIdx.x;
-  for (; i + 3 * 128 < total; i += 4 * 128) {      // 4 loads in flight; accumulation order stays fixed
+  int i = lane;
+  for (; i + 3 * 32 < total; i += 4 * 32) {       // 4 loads in flight; accumulation order stays fixed
     float2 v0, v1, v2, v3;
     double p0, p1, p2, p3;
     fetch(i, v0, p0);
-    fetch(i + 128, v1, p1);
-    fetch(i + 256, v2, p2);
-    fetch(i + 384, v3, p3);
+    fetch(i + 32, v1, p1);
+    fetch(i + 64, v2, p2);
+    fetch(i + 96, v3, p3);
     accum(v0, p0);
     accum(v1, p1);
     accum(v2, p2);
     accum(v3, p3);
   }
-  for (; i < total; i += 128) {
+  for (; i < total; i += 32) {
     float2 v;
     double pa;
     fetch(i, v, pa);
     accum(v, pa);
   }
-  sh_s[threadIdx.x] = ds;
-  sh_q[threadIdx.x] = dq;
-  __syncthreads();
-  for (int o = 64; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
-      sh_s[threadIdx.x] += sh_s[threadIdx.x + o];
-      sh_q[threadIdx.x] += sh_q[threadIdx.x + o];
-    }
-    __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {               // butterfly: every lane ends with the same, order-fixed sum
+    ds += __shfl_xor_sync(0xffffffffu, ds, o);
+    dq += __shfl_xor_sync(0xffffffffu, dq, o);
   }
-  if (threadIdx.x == 0) {
+  if (lane == 0) {
     const double n = static_cast<double>(a.HW) * a.cpg;
-    const double mean = sh_s[0] / n;
-    double var = sh_q[0] / n - mean * mean;
+    const double mean = ds / n;
+    double var = dq / n - mean * mean;
     var = var < 0.0 ? 0.0 : var;
     a.mean_rstd[static_cast<size_t>(bi) * a.groups + g] =
         make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps))));

@@ -77,6 +77,7 @@ SIGNATURES = {
     'b200ns_plan_create': (c_vp, []),
     'b200ns_plan_destroy': (None, [c_vp]),
     'b200ns_plan_size': (C.c_int, [c_vp]),
+    'b200ns_plan_set_lane': (C.c_int, [c_vp, C.c_int]),
     'b200ns_plan_run': (C.c_int, [c_vp, c_vp]),
     'b200ns_plan_instantiate_graph': (C.c_int, [c_vp]),
     'b200ns_plan_run_range': (C.c_int, [c_vp, C.c_int, C.c_int, c_vp]),

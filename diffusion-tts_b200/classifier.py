@@ -49,8 +49,10 @@ class ClassifierPlan(ForwardPlan):
         self.block_out: Dict[str, torch.Tensor] = {}
         self._stats: Dict[int, torch.Tensor] = {}
         self.fused_gn_stats = True
-        self._dir: Dict[int, bool] = {}
+        self._dir: Dict[tuple, bool] = {}
         self.alternate_walk = True
+        self._full: Dict[str, torch.Tensor] = {}
+        self.B_full, self.n_lanes, self._lane = B, 1, None
         self._eps = 1e-5
         self._build_classifier(eng)
         if eng.use_graphs:

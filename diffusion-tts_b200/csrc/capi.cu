@@ -181,6 +181,7 @@ struct Op {
     LinearOp lin;
     Im2colOp i2c;
   };
+  int lane;     // 0 = main stream; k > 0: parallel branch k of the captured graph (see b200ns_plan_set_lane)
   Op() { memset(this, 0, sizeof(*this)); }
 };
 
@@ -325,6 +326,11 @@ int run_op(const Op& op, cudaStream_t st) {
 
 struct b200ns_plan {
   std::vector<Op> ops;
+  int cur_lane = 0;
+  void push(Op& op) {
+    op.lane = cur_lane;
+    ops.push_back(op);
+  }
   cudaGraphExec_t graph_exec = nullptr;     // optional: the whole plan captured once as a CUDA graph
   size_t graph_ops = 0;
 };
@@ -486,17 +492,60 @@ int b200ns_plan_instantiate_graph(b200ns_plan* p) {
     }
   }
   CK(cudaStreamSynchronize(cs));
+  // lanes > 0 become parallel branches: forked from the main stream at their first op, joined back before the
+  // next main-lane op (and at the end).  Run eagerly (plan_run_range) the same ops simply execute in order.
+  constexpr int MAX_LANES = 4;
+  cudaStream_t ls[MAX_LANES] = {cs, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+  bool open[MAX_LANES] = {false, false, false, false};
+  CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+  for (int l = 1; l < MAX_LANES; ++l) {
+    CK(cudaStreamCreateWithFlags(&ls[l], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ev_join[l], cudaEventDisableTiming));
+  }
   cudaGraph_t graph = nullptr;
   CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
   int rc = 0;
-  for (size_t i = 0; i < p->ops.size() && rc == 0; ++i) rc = run_op(p->ops[i], cs);
+  auto join_all = [&]() {
+    for (int l = 1; l < MAX_LANES && rc == 0; ++l)
+      if (open[l]) {
+        rc = check_cuda(cudaEventRecord(ev_join[l], ls[l]), "cudaEventRecord(join)");
+        if (rc == 0) rc = check_cuda(cudaStreamWaitEvent(cs, ev_join[l], 0), "cudaStreamWaitEvent(join)");
+        open[l] = false;
+      }
+  };
+  for (size_t i = 0; i < p->ops.size() && rc == 0; ++i) {
+    const int lane = p->ops[i].lane;
+    if (lane <= 0 || lane >= MAX_LANES) {
+      join_all();
+      if (rc == 0) rc = run_op(p->ops[i], cs);
+      continue;
+    }
+    if (!open[lane]) {
+      rc = check_cuda(cudaEventRecord(ev_fork, cs), "cudaEventRecord(fork)");
+      if (rc == 0) rc = check_cuda(cudaStreamWaitEvent(ls[lane], ev_fork, 0), "cudaStreamWaitEvent(fork)");
+      open[lane] = true;
+    }
+    if (rc == 0) rc = run_op(p->ops[i], ls[lane]);
+  }
+  join_all();
   cudaError_t e = cudaStreamEndCapture(cs, &graph);
   if (rc == 0 && e != cudaSuccess) rc = check_cuda(e, "cudaStreamEndCapture");
   if (rc == 0) rc = check_cuda(cudaGraphInstantiate(&p->graph_exec, graph, 0), "cudaGraphInstantiate");
   if (graph != nullptr) cudaGraphDestroy(graph);
+  for (int l = 1; l < MAX_LANES; ++l) {
+    cudaStreamDestroy(ls[l]);
+    cudaEventDestroy(ev_join[l]);
+  }
+  cudaEventDestroy(ev_fork);
   cudaStreamDestroy(cs);
   if (rc == 0) p->graph_ops = p->ops.size();
   return rc;
+}
+int b200ns_plan_set_lane(b200ns_plan* p, int lane) {
+  if (lane < 0 || lane > 3) return fail("plan_set_lane: lane must be 0..3");
+  p->cur_lane = lane;
+  return 0;
 }
 int b200ns_plan_size(const b200ns_plan* p) { return static_cast<int>(p->ops.size()); }
 
@@ -615,7 +664,7 @@ int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d) {
   }
   const int tiles = a.m_tiles * a.n_tiles;
   g.grid = tiles < num_sms() ? tiles : num_sms();
-  p->ops.push_back(op);
+  p->push(op);
   return 0;
 }
 
@@ -644,7 +693,7 @@ int b200ns_plan_add_gn_stats(b200ns_plan* p, const b200ns_gn_stats_desc* d) {
   if (a.PY < 1) a.PY = 1;
   op.gns.threads = VC * a.PY;
   op.gns.grid = dim3(d->splits, d->batch);
-  p->ops.push_back(op);
+  p->push(op);
   return 0;
 }
 
@@ -693,7 +742,7 @@ int b200ns_plan_add_gn_apply(b200ns_plan* p, const b200ns_gn_apply_desc* d) {
     a.ITER /= 2;
   const int per_cta = a.PY * a.ITER;
   op.gna.grid = dim3((dom + per_cta - 1) / per_cta, d->batch);
-  p->ops.push_back(op);
+  p->push(op);
   return 0;
 }
 
@@ -719,7 +768,7 @@ int b200ns_plan_add_gn_finalize(b200ns_plan* p, const b200ns_gn_finalize_desc* d
   a.mean_rstd = reinterpret_cast<float2*>(d->mean_rstd);
   op.gnf.n_pairs = d->groups * d->batch;
   op.gnf.grid = dim3((op.gnf.n_pairs + 7) / 8);
-  p->ops.push_back(op);
+  p->push(op);
   return 0;
 }
 
@@ -749,7 +798,7 @@ int b200ns_plan_add_attention(b200ns_plan* p, const b200ns_attn_desc* d) {
     if (rc) return rc;
     o.vrow = 1;
     o.grid = dim3((d->L + 127) / 128, d->batch);
-    p->ops.push_back(op);
+    p->push(op);
     return 0;
   }
   if (o.head_dim != 64) return fail("attention: head_dim must be 64 or 256");
@@ -775,7 +824,7 @@ int b200ns_plan_add_attention(b200ns_plan* p, const b200ns_attn_desc* d) {
     if (rc) return rc;
   }
   o.grid = dim3((d->L + 127) / 128, d->batch * d->heads);
-  p->ops.push_back(op);
+  p->push(op);
   return 0;
 }
 
@@ -797,7 +846,7 @@ int b200ns_plan_add_linear(b200ns_plan* p, const b200ns_linear_desc* d) {
   a.ld_out = d->ld_out;
   const int64_t warps = static_cast<int64_t>(d->rows) * d->N;
   op.lin.grid = static_cast<int>((warps * 32 + 255) / 256);
-  p->ops.push_back(op);
+  p->push(op);
   return 0;
 }
 
@@ -807,7 +856,7 @@ int b200ns_plan_add_u8_to_f32(b200ns_plan* p, const uint8_t* in, float* out, int
   op.misc.p0 = in;
   op.misc.p2 = out;
   op.misc.n = n;
-  p->ops.push_back(op);
+  p->push(op);
   return 0;
 }
 
@@ -822,7 +871,7 @@ int b200ns_plan_add_pool_tokens(b200ns_plan* p, const void* act, const float* po
   op.misc.i0 = batch;
   op.misc.i1 = T;
   op.misc.i2 = C;
-  p->ops.push_back(op);
+  p->push(op);
   return 0;
 }
 
@@ -837,7 +886,7 @@ int b200ns_plan_add_pool_attention(b200ns_plan* p, const float* qkv0, const void
   op.misc.i0 = batch;
   op.misc.i1 = T;
   op.misc.i2 = C;
-  p->ops.push_back(op);
+  p->push(op);
   return 0;
 }
 
@@ -850,7 +899,7 @@ int b200ns_plan_add_softmax_gather(b200ns_plan* p, const float* logits, const in
   op.misc.p2 = scores;
   op.misc.i0 = rows;
   op.misc.i1 = K;
-  p->ops.push_back(op);
+  p->push(op);
   return 0;
 }
 
@@ -860,7 +909,7 @@ int b200ns_plan_add_im2col(b200ns_plan* p, const b200ns_im2col_desc* d) {
   op.kind = OP_IM2COL;
   op.i2c.d = *d;
   op.i2c.grid = grid_for(static_cast<int64_t>(d->batch) * d->H * d->W * 8, 256);
-  p->ops.push_back(op);
+  p->push(op);
   return 0;
 }
 

@@ -192,6 +192,10 @@ class Plan:
             L.check(L.lib().b200ns_plan_run_range(self._h, first, last, L.cur_stream()), 'plan_run_range')
             _count(last - first)
 
+    def set_lane(self, lane: int):
+        """Ops added from now on go to graph branch `lane` (0 = main stream; 1..3 run in parallel when captured)."""
+        L.check(L.lib().b200ns_plan_set_lane(self._h, lane), 'plan_set_lane')
+
     def instantiate_graph(self):
         """Capture the whole plan as one CUDA graph (static buffers): run() then costs one launch."""
         L.check(L.lib().b200ns_plan_instantiate_graph(self._h), 'plan_instantiate_graph')

@@ -18,6 +18,7 @@ identical for all N candidates of an image: they run once per distinct image (b_
 from __future__ import annotations
 
 import math
+import os
 import re
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
@@ -136,11 +137,17 @@ def _groups(c: int) -> int:
 
 
 class ForwardPlan:
-    """All buffers + the kernel plan for one (batch B, b_emb) shape."""
+    """All buffers + the kernel plan for one (batch B, b_emb) shape.
+
+    Lanes: at resolutions >= eng.lane_min_res the batch is processed as `eng.lanes` independent sub-batches whose ops
+    sit on parallel branches of the captured CUDA graph, so the HBM-bound GroupNorm passes of one sub-batch overlap
+    the tensor-core GEMMs of the other (and one sub-batch's GEMM fills the tail wave of the other's).  Every
+    per-sample result is batch-invariant, so the split changes no bits.  Builder state (x, skips) always holds the
+    FULL-batch tensors; ops see the current lane's slice (`_view`)."""
 
     def __init__(self, eng: 'UNetEngine', B: int, b_emb: int):
         cfg, dev = eng.cfg, eng.device
-        self.B, self.b_emb = B, b_emb
+        self.B, self.B_full, self.b_emb = B, B, b_emb
         self.fused_gn_stats = eng.fused_gn_stats
         H = cfg.img_resolution
         f32 = dict(device=dev, dtype=torch.float32)
@@ -150,11 +157,16 @@ class ForwardPlan:
         self.out = torch.empty(B, H, H, cfg.out_channels, **f32)                  # F_x, NHWC fp32
         self.plan = Plan()
         self._scratch: Dict[str, torch.Tensor] = {}
+        self._full: Dict[str, torch.Tensor] = {}          # persistent full-batch tensors by name
         self.block_out: Dict[str, torch.Tensor] = {}      # per-block outputs (persistent; per-layer parity tests)
-        # data_ptr -> fp32 [M/64, C, 2] per-channel (sum, sumsq) left behind by the GEMM that produced the tensor
-        self._stats: Dict[int, torch.Tensor] = {}
-        self._dir: Dict[int, bool] = {}                   # data_ptr -> tensor was written last-to-first
+        # (data_ptr, batch) -> fp32 [M/64, C, 2] per-channel (sum, sumsq) left behind by the GEMM that produced it
+        self._stats: Dict[tuple, torch.Tensor] = {}
+        self._dir: Dict[tuple, bool] = {}                 # (data_ptr, batch) -> tensor was written last-to-first
         self.alternate_walk = getattr(eng, 'alternate_walk', True)
+        lanes = getattr(eng, 'lanes', 1)
+        self.n_lanes = lanes if (lanes > 1 and B % lanes == 0 and (B // lanes) % b_emb == 0) else 1
+        self.lane_min_res = getattr(eng, 'lane_min_res', 32)
+        self._lane: Optional[int] = None                  # None: full batch on the main stream
         self._build(eng)
         if eng.use_graphs:
             torch.cuda.synchronize(dev)
@@ -162,6 +174,7 @@ class ForwardPlan:
 
     # -- helpers
     def _buf(self, key: str, numel: int, dtype=torch.bfloat16) -> torch.Tensor:
+        key = f'{key}@{self._lane}'                       # scratch is private to a lane (lanes run concurrently)
         t = self._scratch.get(key)
         if t is None or t.numel() < numel:
             t = torch.empty(numel, device=self.x_in.device, dtype=dtype)
@@ -171,23 +184,59 @@ class ForwardPlan:
     def _act(self, key: str, B, H, W, C) -> torch.Tensor:
         return self._buf(key, B * H * W * C)[:B * H * W * C].view(B, H, W, C)
 
+    def _persist(self, key: str, *shape, dtype=torch.bfloat16) -> torch.Tensor:
+        """Full-batch tensor that outlives the op (block outputs / skips), allocated once per name."""
+        t = self._full.get(key)
+        if t is None:
+            t = torch.empty(self.B_full, *shape, device=self.x_in.device, dtype=dtype)
+            self._full[key] = t
+        return t
+
+    def _view(self, t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        """The current lane's rows of a full-batch tensor."""
+        if t is None or self._lane is None:
+            return t
+        Bs = self.B_full // self.n_lanes
+        return t[self._lane * Bs:(self._lane + 1) * Bs]
+
+    def _set_lane(self, lane: Optional[int]):
+        self._lane = lane
+        self.B = self.B_full if lane is None else self.B_full // self.n_lanes
+        self.plan.set_lane(0 if lane is None else lane + 1)
+
+    @staticmethod
+    def _tk(t: torch.Tensor) -> tuple:
+        return (t.data_ptr(), t.shape[0])
+
     def _rev(self, src: torch.Tensor, dst: Optional[torch.Tensor] = None, *more) -> bool:
         """Walk direction for an op reading `src`: opposite to the direction `src` was written in, so the op starts on
         the rows its producer finished last (still in L2).  Records the direction on the op's outputs."""
-        rev = self.alternate_walk and not self._dir.get(src.data_ptr(), False)
+        rev = self.alternate_walk and not self._dir.get(self._tk(src), False)
         for t in (dst,) + more:
             if t is not None:
-                self._dir[t.data_ptr()] = rev
+                self._dir[self._tk(t)] = rev
         return rev
 
-    def _new_stats(self, t: torch.Tensor, key: Optional[str] = None) -> Optional[torch.Tensor]:
-        """Statistics buffer for a GEMM output that a GroupNorm will consume (None when the fused path is off)."""
+    def _new_stats(self, t: torch.Tensor, key: Optional[str] = None, full: Optional[torch.Tensor] = None):
+        """Statistics buffer for a GEMM output `t` that a GroupNorm will consume (None when the fused path is off).
+        `key`: lane-private scratch name; `full`: the full-batch tensor `t` is a lane view of (the statistics of a
+        persistent tensor are persistent and full-batch too, so a full-batch consumer can read all lanes' rows)."""
         if not self.fused_gn_stats:
             return None
         B, H, W, C = t.shape
-        n = (B * H * W // 64) * C * 2
-        st = (self._buf(key, n, torch.float32)[:n] if key else torch.empty(n, device=t.device, dtype=torch.float32))
-        self._stats[t.data_ptr()] = st
+        rows = B * H * W // 64
+        if key is not None:
+            st = self._buf(key, rows * C * 2, torch.float32)[:rows * C * 2]
+        else:
+            full = t if full is None else full
+            fk = ('stats',) + self._tk(full)
+            sf = self._full.get(fk)
+            if sf is None:
+                sf = torch.empty(full.shape[0] * H * W // 64, C, 2, device=t.device, dtype=torch.float32)
+                self._full[fk] = sf
+                self._stats[self._tk(full)] = sf
+            st = sf if self._lane is None else sf[self._lane * rows:(self._lane + 1) * rows]
+        self._stats[self._tk(t)] = st
         return st
 
     @staticmethod
@@ -203,7 +252,7 @@ class ForwardPlan:
     def _gn(self, xs, C, H, W, gamma, beta, out, *, silu=True, resample=0, raw_out=None, film=None, pre_add=None,
             label=''):
         g = self._num_groups(C)
-        stats = [self._stats.get(t.data_ptr()) for t in xs]
+        stats = [self._stats.get(self._tk(t)) for t in xs]
         if all(st is not None for st in stats):
             # statistics come from the producing GEMMs' epilogues: no pass over the activations
             mr = self._buf('mean_rstd', self.B * 64 * 2, torch.float32)[:self.B * g * 2]
@@ -226,14 +275,14 @@ class ForwardPlan:
     # -- build
     def _build(self, eng: 'UNetEngine'):
         cfg, P, W_ = eng.cfg, self.plan, eng.w
-        B, b_emb = self.B, self.b_emb
+        b_emb = self.b_emb
         adm = cfg.model_type == 'DhariwalUNet'
         self._eps = cfg.eps
         dev = self.x_in.device
         f32 = dict(device=dev, dtype=torch.float32)
         E = cfg.emb_channels
 
-        # ---- embedding network (candidate-invariant: b_emb rows)
+        # ---- embedding network (candidate-invariant: b_emb rows), main stream
         t0 = torch.empty(b_emb, E, **f32)
         self.emb = torch.empty(b_emb, E, **f32)
         if adm:
@@ -255,52 +304,72 @@ class ForwardPlan:
         self.film = torch.empty(b_emb, eng.affine_total, **f32)
         P.add_linear(self.emb, W_['affine_all.weight'], self.film, bias=W_['affine_all.bias'], label='affine_all')
 
-        # ---- encoder
-        skips: List[torch.Tensor] = []
-        x = None
-        for blk in cfg.enc:
-            if blk.kind == 'conv':
-                H = blk.res
-                col = self._act('col', B, H, H, 64)
-                P.add_im2col(self.x_in, col, label=f'{blk.name}.im2col')
-                x = torch.empty(B, H, H, blk.cout, device=dev, dtype=torch.bfloat16)
-                P.add_gemm([col], [(0, 1, 0, 1)], W_[f'{blk.name}.w'], blk.cout, x, bias=W_[f'{blk.name}.b'], alg_k=9 * blk.cin,
-                           gn_stats=self._new_stats(x), reverse=self._rev(col, x), label=f'{blk.name}')
+        # ---- U-Net body as regions of consecutive items that are either split over the lanes or run full-batch
+        items = [('enc', blk) for blk in cfg.enc] + [('dec', blk) for blk in cfg.dec] + ([('out', None)] if adm else [])
+        res_of = lambda it: cfg.img_resolution if it[1] is None else it[1].res
+        regions: List[tuple] = []
+        for it in items:
+            split = self.n_lanes > 1 and res_of(it) >= self.lane_min_res
+            if regions and regions[-1][0] == split:
+                regions[-1][1].append(it)
             else:
-                x = self._block(eng, blk, [x])
-            self.block_out[blk.name] = x
-            skips.append(x)
+                regions.append((split, [it]))
+        state = dict(x=None, skips=[], aux_in=None)
+        for split, its in regions:
+            start = dict(x=state['x'], skips=list(state['skips']), aux_in=None)
+            for lane in (range(self.n_lanes) if split else [None]):
+                self._set_lane(lane)
+                state = dict(x=start['x'], skips=list(start['skips']), aux_in=None)     # every lane replays the region
+                for kind, blk in its:
+                    self._item(eng, kind, blk, state)
+        self._set_lane(None)
 
-        # ---- decoder
-        aux_in = None
-        for blk in cfg.dec:
-            if blk.kind == 'aux_norm':
-                H = blk.res
-                aux_in = self._act('a0', B, H, H, blk.cin)
-                self._gn([x], blk.cin, H, H, W_[f'{blk.name}.weight'], W_[f'{blk.name}.bias'], aux_in, silu=True,
-                         label=blk.name)
-            elif blk.kind == 'aux_conv':
-                P.add_gemm([aux_in], [(0, 9, 0, blk.cin // 64)], W_[f'{blk.name}.w'], blk.cout, self.out,
-                           bias=W_[f'{blk.name}.b'], reverse=self._rev(aux_in), label=blk.name)
-            else:
-                xs = [x]
-                if x.shape[3] != blk.cin:
-                    xs.append(skips.pop())
-                    assert xs[0].shape[3] + xs[1].shape[3] == blk.cin
-                x = self._block(eng, blk, xs)
-                self.block_out[blk.name] = x
-        if adm:
+    def _item(self, eng: 'UNetEngine', kind: str, blk: Optional[Block], st: dict):
+        cfg, P, W_ = eng.cfg, self.plan, eng.w
+        B = self.B
+        if kind == 'out':                                    # ADM: out_norm + SiLU + out_conv (networks.py:460)
             H = cfg.img_resolution
+            x = self._view(st['x'])
             C = x.shape[3]
             a = self._act('a0', B, H, H, C)
             self._gn([x], C, H, H, W_['out_norm.weight'], W_['out_norm.bias'], a, silu=True, label='out_norm')
-            P.add_gemm([a], [(0, 9, 0, C // 64)], W_['out_conv.w'], cfg.out_channels, self.out, bias=W_['out_conv.b'],
-                       reverse=self._rev(a), label='out_conv')
+            P.add_gemm([a], [(0, 9, 0, C // 64)], W_['out_conv.w'], cfg.out_channels, self._view(self.out),
+                       bias=W_['out_conv.b'], reverse=self._rev(a), label='out_conv')
+        elif kind == 'enc':
+            if blk.kind == 'conv':
+                H = blk.res
+                col = self._act('col', B, H, H, 64)
+                P.add_im2col(self._view(self.x_in), col, label=f'{blk.name}.im2col')
+                xf = self._persist(blk.name, H, H, blk.cout)
+                x = self._view(xf)
+                P.add_gemm([col], [(0, 1, 0, 1)], W_[f'{blk.name}.w'], blk.cout, x, bias=W_[f'{blk.name}.b'],
+                           alg_k=9 * blk.cin, gn_stats=self._new_stats(x, full=xf), reverse=self._rev(col, x),
+                           label=f'{blk.name}')
+                st['x'] = xf
+            else:
+                st['x'] = self._block(eng, blk, [st['x']])
+            self.block_out[blk.name] = st['x']
+            st['skips'].append(st['x'])
+        elif blk.kind == 'aux_norm':
+            H = blk.res
+            st['aux_in'] = self._act('a0', B, H, H, blk.cin)
+            self._gn([self._view(st['x'])], blk.cin, H, H, W_[f'{blk.name}.weight'], W_[f'{blk.name}.bias'], st['aux_in'],
+                     silu=True, label=blk.name)
+        elif blk.kind == 'aux_conv':
+            P.add_gemm([st['aux_in']], [(0, 9, 0, blk.cin // 64)], W_[f'{blk.name}.w'], blk.cout, self._view(self.out),
+                       bias=W_[f'{blk.name}.b'], reverse=self._rev(st['aux_in']), label=blk.name)
+        else:
+            xs = [st['x']]
+            if st['x'].shape[3] != blk.cin:
+                xs.append(st['skips'].pop())
+                assert xs[0].shape[3] + xs[1].shape[3] == blk.cin
+            st['x'] = self._block(eng, blk, xs)
+            self.block_out[blk.name] = st['x']
 
     def _block(self, eng: 'UNetEngine', blk: Block, xs: List[torch.Tensor]) -> torch.Tensor:
         cfg, P, W_ = eng.cfg, self.plan, eng.w
         B, n = self.B, blk.name
-        dev = self.x_in.device
+        xs = [self._view(t) for t in xs]                  # builder state holds full-batch tensors
         Hin = xs[0].shape[1]
         Ho = blk.res
         cin, cout = blk.cin, blk.cout
@@ -321,22 +390,24 @@ class ForwardPlan:
         else:
             self._gn([h], cout, Ho, Ho, W_[f'{n}.norm1.weight'], W_[f'{n}.norm1.bias'], a1,
                      pre_add=self.film[:, off:off + cout], label=f'{n}.norm1')
-        out = torch.empty(B, Ho, Ho, cout, device=dev, dtype=torch.bfloat16)
+        out_full = self._persist(f'{n}.out', Ho, Ho, cout)
+        out = self._view(out_full)
         if blk.skip_conv:
             skip_src = [xr] if need_raw else xs
             srcs = [a1] + skip_src
             segs = [(0, 9, 0, cout // 64)] + [(i + 1, 1, 0, t.shape[3] // 64) for i, t in enumerate(skip_src)]
             P.add_gemm(srcs, segs, W_[f'{n}.conv1skip.w'], cout, out, bias=W_[f'{n}.conv1skip.b'],
-                       out_scale=cfg.skip_scale, gn_stats=self._new_stats(out), reverse=self._rev(a1, out),
+                       out_scale=cfg.skip_scale, gn_stats=self._new_stats(out, full=out_full), reverse=self._rev(a1, out),
                        label=f'{n}.conv1+skip')
         else:
             res = xr if need_raw else xs[0]
             assert len(xs) == 1
             P.add_gemm([a1], [(0, 9, 0, cout // 64)], W_[f'{n}.conv1.w'], cout, out, bias=W_[f'{n}.conv1.b'],
-                       residual=res, out_scale=cfg.skip_scale, gn_stats=self._new_stats(out), reverse=self._rev(a1, out),
+                       residual=res, out_scale=cfg.skip_scale, gn_stats=self._new_stats(out, full=out_full),
+                       reverse=self._rev(a1, out),
                        label=f'{n}.conv1')
         if not blk.attention:
-            return out
+            return out_full
         heads, L = blk.heads, Ho * Ho
         hd = cout // heads
         if hd not in (64, 256) or (hd == 256 and (heads != 1 or L > 256)):
@@ -350,21 +421,27 @@ class ForwardPlan:
         # V is consumed in place as an MN-major UMMA operand: no transposed copy
         P.add_attention(qkv.view(B * L, 3 * cout), cout, None, att.view(B * L, cout), B, heads, L,
                         v_col0=2 * cout, head_dim=hd, reverse=self._rev(qkv, att), label=f'{n}.attn')
-        out2 = torch.empty(B, Ho, Ho, cout, device=dev, dtype=torch.bfloat16)
+        out2_full = self._persist(f'{n}.out2', Ho, Ho, cout)
+        out2 = self._view(out2_full)
         P.add_gemm([att], [(0, 1, 0, cout // 64)], W_[f'{n}.proj.w'], cout, out2, bias=W_[f'{n}.proj.b'], residual=out,
-                   out_scale=cfg.skip_scale, gn_stats=self._new_stats(out2), reverse=self._rev(att, out2), label=f'{n}.proj')
-        return out2
+                   out_scale=cfg.skip_scale, gn_stats=self._new_stats(out2, full=out2_full), reverse=self._rev(att, out2),
+                   label=f'{n}.proj')
+        return out2_full
 
 
 class UNetEngine:
     """Packed weights + cached ForwardPlans.  `forward(x_in, c_noise, labels)` returns F_x."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], device='cuda', use_graphs: bool = True,
-                 fused_gn_stats: bool = True, alternate_walk: bool = True):
+                 fused_gn_stats: bool = True, alternate_walk: bool = True, lanes: Optional[int] = None,
+                 lane_min_res: int = 32):
         from . import _lib
         self.use_graphs = use_graphs
         self.fused_gn_stats = fused_gn_stats      # GroupNorm statistics from the producing GEMM's epilogue
         self.alternate_walk = alternate_walk      # consecutive kernels walk the batch in opposite directions (L2 reuse)
+        # sub-batches on parallel graph branches at resolutions >= lane_min_res (see ForwardPlan)
+        self.lanes = int(os.environ.get('B200NS_LANES', '1')) if lanes is None else lanes
+        self.lane_min_res = lane_min_res
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise RuntimeError('UNetEngine requires a CUDA device (B200); there is no CPU fallback')

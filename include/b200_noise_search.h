@@ -105,6 +105,10 @@ int b200ns_plan_size(const b200ns_plan* p);
 int b200ns_plan_run(b200ns_plan* p, void* stream);
 /* Capture the plan once as a CUDA graph; later b200ns_plan_run calls launch the graph. */
 int b200ns_plan_instantiate_graph(b200ns_plan* p);
+/* Ops added after this call belong to `lane` (0..3).  Lane 0 is the main stream; in the captured graph the ops
+ * of a lane k > 0 form a parallel branch (forked at the lane's first op, joined before the next lane-0 op), so
+ * HBM-bound kernels of one half batch overlap the tensor-core kernels of the other.  Eager runs ignore lanes. */
+int b200ns_plan_set_lane(b200ns_plan* p, int lane);
 /* Run ops [first, last) only (per-layer parity tests and profiling). */
 int b200ns_plan_run_range(b200ns_plan* p, int first, int last, void* stream);
 

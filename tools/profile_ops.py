@@ -10,7 +10,9 @@ from diffusion_tts_b200.unet import UNetEngine
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 64
 eng = UNetEngine(random_state_dict(adm_param_shapes(), 1234), device='cuda', use_graphs='--graph' in sys.argv,
-                 alternate_walk='--no-alt' not in sys.argv, fused_gn_stats='--no-fused-stats' not in sys.argv)
+                 alternate_walk='--no-alt' not in sys.argv, fused_gn_stats='--no-fused-stats' not in sys.argv,
+                 lanes=int(sys.argv[sys.argv.index('--lanes') + 1]) if '--lanes' in sys.argv else None,
+                 lane_min_res=int(sys.argv[sys.argv.index('--lane-min-res') + 1]) if '--lane-min-res' in sys.argv else 32)
 fp = eng.plan(B, 1)
 fp.x_in.normal_()
 plan = fp.plan

@@ -412,6 +412,218 @@ attention_kernel_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------
+// v3 (row-major V, head_dim 64): 160 threads = 4 softmax warps (one query row per thread) + 1 issuer warp
+// (TMA loads + tcgen05.mma).  K and V are double buffered; P never touches shared memory: each thread
+// stores its bf16 probabilities straight into TMEM (tcgen05.st) and the PV product reads A = P from TMEM.
+// The issuer launches S(kt+1) = Q K(kt+1)^T as soon as every thread has pulled S(kt) into registers, so the
+// tensor pipe works underneath the exponentials of tile kt; O accumulates in TMEM over all key tiles and is
+// only rescaled (lazily) when a row's maximum grows by more than 2^8, so no thread waits on an MMA it just
+// requested.  80 KB smem + 256 TMEM columns -> two CTAs per SM.
+template <int KT>
+struct AttnCfg3 {
+  static constexpr int Q_BYTES = 128 * 128;
+  static constexpr int K_BYTES = KT * 128;
+  static constexpr int V_BYTES = KT * 128;
+  static constexpr int SMEM_BYTES = Q_BYTES + 2 * K_BYTES + 2 * V_BYTES + 1024 + 128;
+  static constexpr int THREADS = 160;
+};
+
+template <int KT>
+__global__ void __launch_bounds__(160, 2)
+attention_kernel_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const AttnArgs a) {
+  using Cfg = AttnCfg3<KT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::Q_BYTES;                 // [2]
+  uint8_t* sV = sK + 2 * Cfg::K_BYTES;             // [2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * Cfg::V_BYTES);
+  uint64_t* bar_q = bars;
+  uint64_t* bar_k = bars + 1;                      // [2] K tile landed
+  uint64_t* bar_v = bars + 3;                      // [2] V tile landed
+  uint64_t* bar_s = bars + 5;                      // S(kt) complete (tcgen05.commit)
+  uint64_t* bar_o = bars + 6;                      // PV(kt) complete (tcgen05.commit)
+  uint64_t* bar_sfree = bars + 7;                  // 128 arrivals: every thread holds S(kt) in registers
+  uint64_t* bar_pready = bars + 8;                 // 128 arrivals: P(kt) is in TMEM and PV(kt-1) has been consumed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bh = a.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y, bi = bh / a.heads, head = bh % a.heads;
+  const int q0 = (a.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * 128;
+  const int row_base = bi * a.L;
+  const int nkt = a.L / KT;
+
+  if (tid == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    mbar_init(bar_sfree, 128);
+    mbar_init(bar_pready, 128);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tP = tmem_base + KT, tO = tmem_base + KT + KT / 2;
+
+  if (warp == 4) {
+    // ===================== issuer: TMA + MMA (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, KT);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, true);      // B = V, MN-major
+      auto load_k = [&](int kt) {
+        mbar_arrive_expect_tx(&bar_k[kt & 1], Cfg::K_BYTES);
+        tma_load_2d(sK + (kt & 1) * Cfg::K_BYTES, &tmK, &bar_k[kt & 1], a.k_col0 + head * 64, row_base + kt * KT);
+      };
+      auto load_v = [&](int kt) {
+        mbar_arrive_expect_tx(&bar_v[kt & 1], Cfg::V_BYTES);
+        tma_load_2d(sV + (kt & 1) * Cfg::V_BYTES, &tmV, &bar_v[kt & 1], a.v_col0 + head * 64, row_base + kt * KT);
+      };
+      auto issue_s = [&](int kt) {
+        const uint64_t dq = umma_desc_sw128(smem_u32(sQ));
+        const uint64_t dk = umma_desc_sw128(smem_u32(sK + (kt & 1) * Cfg::K_BYTES));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tS, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        umma_commit(bar_s);
+      };
+      mbar_arrive_expect_tx(bar_q, Cfg::Q_BYTES);
+      tma_load_2d(sQ, &tmQ, bar_q, head * 64, row_base + q0);
+      load_k(0);
+      load_v(0);
+      if (nkt > 1) {
+        load_k(1);
+        load_v(1);
+      }
+      mbar_wait(bar_q, 0);
+      mbar_wait(&bar_k[0], 0);
+      tc_fence_after();
+      issue_s(0);
+      for (int kt = 0; kt < nkt; ++kt) {
+        if (kt + 1 < nkt) {
+          mbar_wait(bar_sfree, kt & 1);               // S(kt) is in registers => S(kt) finished: S columns and K buffer kt&1 are free
+          if (kt + 2 < nkt) load_k(kt + 2);
+          mbar_wait(&bar_k[(kt + 1) & 1], ((kt + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_s(kt + 1);
+        }
+        mbar_wait(bar_pready, kt & 1);                // P(kt) stored; PV(kt-1) consumed => V buffer (kt+1)&1 is free
+        if (kt >= 1 && kt + 1 < nkt) load_v(kt + 1);
+        mbar_wait(&bar_v[kt & 1], (kt >> 1) & 1);
+        tc_fence_after();
+        const uint64_t dv = umma_desc_sw128(smem_u32(sV + (kt & 1) * Cfg::V_BYTES));
+#pragma unroll
+        for (int k = 0; k < KT / 16; ++k)             // 16 keys per MMA: 8 packed TMEM columns of P, 2 KB of V rows
+          umma_bf16_ts(tO, tP + k * 8, dv + static_cast<uint64_t>(k * (2048 >> 4)), idesc_o, (kt | k) != 0);
+        umma_commit(bar_o);
+      }
+    }
+  } else {
+    // ===================== softmax warps: one query row per thread =====================
+    // O accumulates in TMEM across key tiles.  The running maximum is only raised when the new tile exceeds it by
+    // more than 2^8 (in the base-2 exponent domain); otherwise the stale maximum is kept -- softmax is shift
+    // invariant, probabilities stay <= 256, and the O rescale (TMEM load, multiply, store) is skipped for the warp.
+    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+    const float c = 0.125f * 1.4426950408889634f;     // 1/sqrt(64) * log2(e)
+    float m_used = -INFINITY, l_run = 0.f;
+    for (int kt = 0; kt < nkt; ++kt) {
+      mbar_wait(bar_s, kt & 1);
+      tc_fence_after();
+      uint32_t sr[KT];
+#pragma unroll
+      for (int c0 = 0; c0 < KT; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tS + lane_addr + c0, r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sr[c0 + j] = r[j];
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bar_sfree);
+      float mx = __uint_as_float(sr[0]);
+#pragma unroll
+      for (int j = 1; j < KT; ++j) mx = fmaxf(mx, __uint_as_float(sr[j]));
+      const bool raise = (mx - m_used) * c > 8.0f;     // always true for the first tile (m_used = -inf)
+      float alpha = 1.0f;
+      if (raise) {
+        alpha = ex2_approx((m_used - mx) * c);         // 0 for the first tile
+        m_used = mx;
+      }
+      const float mc = m_used * c;
+      float lsum = 0.f;
+      uint32_t pk[KT / 2];
+#pragma unroll
+      for (int j = 0; j < KT / 2; ++j) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(sr[2 * j]), c, -mc));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(sr[2 * j + 1]), c, -mc));
+        lsum += p0 + p1;
+        pk[j] = pack_bf16(p0, p1);
+      }
+      l_run = l_run * alpha + lsum;
+      if (kt > 0) {
+        mbar_wait(bar_o, (kt - 1) & 1);               // PV(kt-1) complete: O is consistent, the P columns are free
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, raise)) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t r[32];
+            tmem_ld32(tO + lane_addr + h * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * alpha);
+            tmem_st32(tO + lane_addr + h * 32, r);
+          }
+        }
+      }
+#pragma unroll
+      for (int c0 = 0; c0 < KT / 2; c0 += 32) {
+        uint32_t r[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = pk[c0 + j];
+        tmem_st32(tP + lane_addr + c0, r);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_pready);
+    }
+    mbar_wait(bar_o, (nkt - 1) & 1);
+    tc_fence_after();
+    const int q = q0 + tid;
+    const float inv = 1.0f / l_run;
+    uint4* op = reinterpret_cast<uint4*>(a.out + static_cast<size_t>(row_base + q) * a.ld_out + head * 64);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t r[32];
+      tmem_ld32(tO + lane_addr + h * 32, r);
+      tmem_ld_wait();
+      if (q < a.L) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(r[8 * j + 0]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
+          u.y = pack_bf16(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
+          u.z = pack_bf16(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
+          u.w = pack_bf16(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
+          op[h * 4 + j] = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // head_dim 256, one head, L <= 256 (DDPM++ / SongUNet: `num_heads=1`, networks.py:263; attention at
 // 16x16 and 8x8).  The whole score row fits in TMEM (L <= 256 columns), so the softmax is exact
 // two-pass (no online rescaling): S = Q K^T accumulated over four 64-wide d chunks, P overwrites the

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -149,6 +150,7 @@ struct AttnOp {
   int KT;
   int vrow;
   int head_dim;
+  int variant;
   dim3 grid;
 };
 struct LinearOp {
@@ -245,6 +247,19 @@ int launch_attn_t(const AttnOp& o, cudaStream_t st) {
 }
 
 template <int KT>
+int launch_attn_v3(const AttnOp& o, cudaStream_t st) {
+  using Cfg = AttnCfg3<KT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(attention_kernel_v3<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  attention_kernel_v3<KT><<<o.grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(o.tmQ, o.tmK, o.tmV, o.args);
+  CK_LAUNCH("attention_kernel_v3");
+  return 0;
+}
+
+template <int KT>
 int launch_attn_v2(const AttnOp& o, cudaStream_t st) {
   using Cfg = AttnCfg2<KT>;
   static bool attr_set = false;
@@ -283,7 +298,8 @@ int run_op(const Op& op, cudaStream_t st) {
         CK_LAUNCH("attention_d256_kernel");
         return 0;
       }
-      if (op.attn.vrow) return op.attn.KT == 128 ? launch_attn_v2<128>(op.attn, st) : launch_attn_v2<64>(op.attn, st);
+      if (op.attn.vrow && op.attn.variant == 2) return op.attn.KT == 128 ? launch_attn_v2<128>(op.attn, st) : launch_attn_v2<64>(op.attn, st);
+      if (op.attn.vrow) return op.attn.KT == 128 ? launch_attn_v3<128>(op.attn, st) : launch_attn_v3<64>(op.attn, st);
       return op.attn.KT == 128 ? launch_attn_t<128, false>(op.attn, st) : launch_attn_t<64, false>(op.attn, st);
     case OP_LINEAR:
       linear_kernel<<<op.lin.grid, 256, 0, st>>>(op.lin.args);
@@ -812,6 +828,10 @@ int b200ns_plan_add_attention(b200ns_plan* p, const b200ns_attn_desc* d) {
     if (rc) return rc;
   }
   o.vrow = d->vt == nullptr ? 1 : 0;
+  {
+    const char* v = getenv("B200NS_ATTN");
+    o.variant = (v != nullptr && v[0] == '2') ? 2 : 3;
+  }
   if (o.vrow) {       // V row-major inside the qkv matrix: box [KT keys][64 d]
     const uint64_t dims[2] = {static_cast<uint64_t>(d->ld_qk), M};
     const uint32_t box[2] = {64, static_cast<uint32_t>(o.KT)};

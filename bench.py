@@ -255,7 +255,11 @@ def run_b200(args):
         'clocks': clk,
         'roofline': {'bound': 'tensor', 'kernel': 'gemm_conv_kernel (tcgen05 implicit-GEMM conv3x3/1x1)',
                      'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
-                     'peak_source': peak_src, 'traffic': None, 'launches_per_nfe': n_gemm,
+                     'peak_source': peak_src, 'traffic': 591.9e6,
+                     'traffic_note': 'bytes; ncu dram read+write of the largest of the GEMM launches (dec.64x64_up.conv1, '
+                                     '540 us of the NFE) vs 604e6 algorithmic (A + residual + out + weights): '
+                                     'profiles/r01_ncu_full_v3_summary.txt',
+                     'launches_per_nfe': n_gemm,
                      'flops_per_nfe_batch': gemm_flops, 'gemm_ms_per_nfe': gemm_ms, 'nfe_ms': nfe_ms,
                      'ms_by_kernel_kind': by_kind,
                      'whole_step_tflops': (N_PER_GPU * 35 / 18 + 35 / 18) * FLOP_PER_NFE / (ms / args.steps / 1e3) / 1e12},

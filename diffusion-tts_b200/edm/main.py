@@ -133,6 +133,11 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
     C, HW = x_next.shape[1], x_next.shape[2] * x_next.shape[3]
     stepper = HeunStepper(net, table, class_labels)
     scales = (scale_table if scale_table is not None else _scale_table(num_steps, K, N, lam)).to(device)
+    if shard.world > 1:
+        # hash() is salted per process (edm/main.py:776 inherits that): all ranks must perturb with rank 0's scales
+        import torch.distributed as dist
+        scales = scales.contiguous()
+        dist.broadcast(scales, src=dist.get_global_rank(shard.group, 0) if shard.group is not None else 0, group=shard.group)
     labels_rows = class_labels.repeat(hi - lo, 1) if class_labels is not None else None
     pre = precomputed_noise
     if pre is not None and 'pivot' in pre:                                # :724-727 (value unused, RNG untouched)

@@ -198,12 +198,11 @@ def run_b200(args):
     # ---- device-resident run
     _, x, _ = timed(on_dev, order[:args.warmup], x0)
     clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
+    clocks.start()                      # every rank samples its own GPU; rank 0's goes into `clocks`, all into `per_rank`
     ops.LAUNCHES[0] = 0
     ms, x, rec = timed(on_dev, order[args.warmup:], x)
     launches = ops.LAUNCHES[0]
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop()
     value = N * args.steps / (ms / 1e3)
 
     # ---- end-to-end run: host (pinned) noise in, per-step results out
@@ -232,6 +231,13 @@ def run_b200(args):
         by_kind[k] = by_kind.get(k, 0.0) + t
     nfe_ms = sum(per_op)
 
+    per_rank = None
+    if world > 1:                       # which GPU is the slow one?  (weak scaling waits for the slowest rank every step)
+        mine = {'rank': rank, 'sm_mhz': clk.get('sm_mhz'), 'reasons': clk.get('reasons'), 'nfe_ms': nfe_ms}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        per_rank = {'sm_mhz': [g['sm_mhz'] for g in gathered], 'nfe_ms': [round(g['nfe_ms'], 3) for g in gathered],
+                    'reasons': sorted({r for g in gathered for r in (g['reasons'] or [])})}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -253,6 +259,7 @@ def run_b200(args):
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': launches,
         'clocks': clk,
+        'per_rank': per_rank,
         'roofline': {'bound': 'tensor', 'kernel': 'gemm_conv_kernel (tcgen05 implicit-GEMM conv3x3/1x1)',
                      'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
                      'peak_source': peak_src, 'traffic': 591.9e6,

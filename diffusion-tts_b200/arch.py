@@ -123,3 +123,74 @@ def random_state_dict(shapes: Dict[str, Tuple[int, ...]], seed: int = 1234) -> D
         else:
             sd[name] = torch.randn(shp, generator=g) / math.sqrt(int(math.prod(shp[1:])))
     return sd
+
+
+def sd_unet_param_shapes(in_channels=4, out_channels=4, block_out_channels: Sequence[int] = (320, 640, 1280, 1280),
+                         layers_per_block=2, cross_attn_down: Sequence[bool] = (True, True, True, False),
+                         cross_attention_dim=768) -> Dict[str, Tuple[int, ...]]:
+    """Parameter inventory of the SD-1.5-shaped `UNet2DConditionModel` (BASELINE.json config 5): names and shapes as the
+    vendored diffusers registers them (sd/diffusers/src/diffusers/models/unets/unet_2d_condition.py:237-480,
+    unet_2d_blocks.py CrossAttnDownBlock2D/DownBlock2D/UNetMidBlock2DCrossAttn/UpBlock2D/CrossAttnUpBlock2D,
+    resnet.py ResnetBlock2D, transformers/transformer_2d.py, attention.py BasicTransformerBlock).  The up path mirrors
+    the down path (`cross_attn_down` reversed).  tests/golden/sd_unet_shapes.json pins this against the reference."""
+    boc = list(block_out_channels)
+    E = boc[0] * 4
+    shp: Dict[str, Tuple[int, ...]] = {
+        'conv_in.weight': (boc[0], in_channels, 3, 3), 'conv_in.bias': (boc[0],),
+        'time_embedding.linear_1.weight': (E, boc[0]), 'time_embedding.linear_1.bias': (E,),
+        'time_embedding.linear_2.weight': (E, E), 'time_embedding.linear_2.bias': (E,),
+    }
+
+    def resnet(p, cin, cout):
+        shp[f'{p}.norm1.weight'] = shp[f'{p}.norm1.bias'] = (cin,)
+        shp[f'{p}.conv1.weight'], shp[f'{p}.conv1.bias'] = (cout, cin, 3, 3), (cout,)
+        shp[f'{p}.time_emb_proj.weight'], shp[f'{p}.time_emb_proj.bias'] = (cout, E), (cout,)
+        shp[f'{p}.norm2.weight'] = shp[f'{p}.norm2.bias'] = (cout,)
+        shp[f'{p}.conv2.weight'], shp[f'{p}.conv2.bias'] = (cout, cout, 3, 3), (cout,)
+        if cin != cout:
+            shp[f'{p}.conv_shortcut.weight'], shp[f'{p}.conv_shortcut.bias'] = (cout, cin, 1, 1), (cout,)
+
+    def transformer(p, c):
+        shp[f'{p}.norm.weight'] = shp[f'{p}.norm.bias'] = (c,)
+        shp[f'{p}.proj_in.weight'], shp[f'{p}.proj_in.bias'] = (c, c, 1, 1), (c,)
+        t = f'{p}.transformer_blocks.0'
+        for nm in ('norm1', 'norm2', 'norm3'):
+            shp[f'{t}.{nm}.weight'] = shp[f'{t}.{nm}.bias'] = (c,)
+        for a, kdim in (('attn1', c), ('attn2', cross_attention_dim)):
+            shp[f'{t}.{a}.to_q.weight'] = (c, c)
+            shp[f'{t}.{a}.to_k.weight'] = shp[f'{t}.{a}.to_v.weight'] = (c, kdim)
+            shp[f'{t}.{a}.to_out.0.weight'], shp[f'{t}.{a}.to_out.0.bias'] = (c, c), (c,)
+        shp[f'{t}.ff.net.0.proj.weight'], shp[f'{t}.ff.net.0.proj.bias'] = (8 * c, c), (8 * c,)
+        shp[f'{t}.ff.net.2.weight'], shp[f'{t}.ff.net.2.bias'] = (c, 4 * c), (c,)
+        shp[f'{p}.proj_out.weight'], shp[f'{p}.proj_out.bias'] = (c, c, 1, 1), (c,)
+
+    out_c = boc[0]
+    for i, c in enumerate(boc):
+        in_c, out_c = out_c, c
+        for j in range(layers_per_block):
+            resnet(f'down_blocks.{i}.resnets.{j}', in_c if j == 0 else out_c, out_c)
+            if cross_attn_down[i]:
+                transformer(f'down_blocks.{i}.attentions.{j}', out_c)
+        if i != len(boc) - 1:
+            shp[f'down_blocks.{i}.downsamplers.0.conv.weight'] = (out_c, out_c, 3, 3)
+            shp[f'down_blocks.{i}.downsamplers.0.conv.bias'] = (out_c,)
+    resnet('mid_block.resnets.0', boc[-1], boc[-1])
+    transformer('mid_block.attentions.0', boc[-1])
+    resnet('mid_block.resnets.1', boc[-1], boc[-1])
+    rev = boc[::-1]
+    cross_up = list(cross_attn_down)[::-1]
+    out_c = rev[0]
+    for i in range(len(rev)):
+        prev_out, out_c = out_c, rev[i]
+        in_c = rev[min(i + 1, len(rev) - 1)]
+        for j in range(layers_per_block + 1):
+            skip_c = in_c if j == layers_per_block else out_c
+            resnet(f'up_blocks.{i}.resnets.{j}', (prev_out if j == 0 else out_c) + skip_c, out_c)
+            if cross_up[i]:
+                transformer(f'up_blocks.{i}.attentions.{j}', out_c)
+        if i != len(rev) - 1:
+            shp[f'up_blocks.{i}.upsamplers.0.conv.weight'] = (out_c, out_c, 3, 3)
+            shp[f'up_blocks.{i}.upsamplers.0.conv.bias'] = (out_c,)
+    shp['conv_norm_out.weight'] = shp['conv_norm_out.bias'] = (boc[0],)
+    shp['conv_out.weight'], shp['conv_out.bias'] = (out_channels, boc[0], 3, 3), (out_channels,)
+    return shp

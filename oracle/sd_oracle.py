@@ -1,0 +1,224 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle of the SD-backend beam-search step (BASELINE.json config 5).
+
+Plain-PyTorch functional restatement (no nn.Module, weights from a state dict) of
+  * `UNet2DConditionModel.forward` for the SD-1.5 family: sd/diffusers/src/diffusers/models/unets/
+    unet_2d_condition.py:1039-1310 (time embedding :1098-1116, down :1192-1224, mid :1241-1260, up :1276-1302,
+    post-process :1305-1308), blocks unet_2d_blocks.py (CrossAttnDownBlock2D, DownBlock2D, UNetMidBlock2DCrossAttn,
+    UpBlock2D, CrossAttnUpBlock2D), resnet.py ResnetBlock2D.forward, downsampling.py / upsampling.py,
+    transformers/transformer_2d.py Transformer2DModel.forward, attention.py BasicTransformerBlock.forward,
+    attention_processor.py AttnProcessor2_0, activations.py GEGLU, embeddings.py get_timestep_embedding;
+  * the reference's edited `DDIMScheduler.step` (eta defaults to 1, returns (prev_sample, pred_original_sample)):
+    sd/diffusers/src/diffusers/schedulers/scheduling_ddim.py:342-471, `_get_variance` :218-227,
+    `set_timesteps` :297-340 ('leading' spacing + steps_offset);
+  * the beam loop of `StableDiffusionPipeline.__call__`: pipelines/stable_diffusion/pipeline_stable_diffusion.py:1045-1170,
+    with an injectable decode stage (identity for config 5: the 4-channel latent takes the non-RGB branch of
+    sd/scorers.py:66-67 after the uint8 quantisation of :1115).
+
+Pinned by oracle/make_golden_sd.py against the vendored diffusers modules themselves (tests/golden/sd_*.pt).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module."""
+import math
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+
+# ---------------------------------------------------------------------------------------------- UNet
+def sd_config_from_state_dict(sd: Dict[str, torch.Tensor]) -> dict:
+    """Recover (block_out_channels, layers_per_block, which blocks carry attention, cross dim) from key names/shapes."""
+    n_down = 1 + max(int(k.split('.')[1]) for k in sd if k.startswith('down_blocks.'))
+    boc = [sd[f'down_blocks.{i}.resnets.0.conv1.weight'].shape[0] for i in range(n_down)]
+    lpb = 1 + max(int(k.split('.')[3]) for k in sd if k.startswith('down_blocks.0.resnets.'))
+    cross = [f'down_blocks.{i}.attentions.0.norm.weight' in sd for i in range(n_down)]
+    cdim = next(v.shape[1] for k, v in sd.items() if k.endswith('attn2.to_k.weight'))
+    return dict(block_out_channels=boc, layers_per_block=lpb, cross_attn_down=cross, cross_attention_dim=cdim, heads=8,
+                groups=32, in_channels=sd['conv_in.weight'].shape[1], out_channels=sd['conv_out.weight'].shape[0])
+
+
+def timestep_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
+    """embeddings.py get_timestep_embedding with flip_sin_to_cos=True, downscale_freq_shift=0 (SD-1.5 config)."""
+    half = dim // 2
+    exponent = -math.log(10000) * torch.arange(0, half, dtype=torch.float32, device=t.device)
+    exponent = exponent / (half - 0)
+    emb = t[:, None].float() * torch.exp(exponent)[None, :]
+    emb = torch.cat([torch.sin(emb), torch.cos(emb)], dim=-1)
+    return torch.cat([emb[:, half:], emb[:, :half]], dim=-1)
+
+
+def _resnet(sd, p, x, temb_act, groups=32, eps=1e-5):
+    """resnet.py ResnetBlock2D.forward (time_embedding_norm='default', output_scale_factor=1)."""
+    h = F.silu(F.group_norm(x, groups, sd[f'{p}.norm1.weight'], sd[f'{p}.norm1.bias'], eps))
+    h = F.conv2d(h, sd[f'{p}.conv1.weight'], sd[f'{p}.conv1.bias'], padding=1)
+    t = F.linear(temb_act, sd[f'{p}.time_emb_proj.weight'], sd[f'{p}.time_emb_proj.bias'])[:, :, None, None]
+    h = h + t
+    h = F.silu(F.group_norm(h, groups, sd[f'{p}.norm2.weight'], sd[f'{p}.norm2.bias'], eps))
+    h = F.conv2d(h, sd[f'{p}.conv2.weight'], sd[f'{p}.conv2.bias'], padding=1)
+    if f'{p}.conv_shortcut.weight' in sd:
+        x = F.conv2d(x, sd[f'{p}.conv_shortcut.weight'], sd[f'{p}.conv_shortcut.bias'])
+    return x + h
+
+
+def _attention(sd, p, x, ctx, heads):
+    """attention_processor.py AttnProcessor2_0: q/k/v linears without bias, SDPA with scale head_dim^-0.5, to_out.0."""
+    B, L, C = x.shape
+    kv = x if ctx is None else ctx
+    q = F.linear(x, sd[f'{p}.to_q.weight'])
+    k = F.linear(kv, sd[f'{p}.to_k.weight'])
+    v = F.linear(kv, sd[f'{p}.to_v.weight'])
+    hd = C // heads
+    q, k, v = [t.view(B, -1, heads, hd).transpose(1, 2) for t in (q, k, v)]
+    o = F.scaled_dot_product_attention(q, k, v, attn_mask=None, dropout_p=0.0, is_causal=False)
+    o = o.transpose(1, 2).reshape(B, L, C)
+    return F.linear(o, sd[f'{p}.to_out.0.weight'], sd[f'{p}.to_out.0.bias'])
+
+
+def _transformer(sd, p, x, ctx, heads, groups=32):
+    """transformer_2d.py Transformer2DModel.forward (continuous input, conv projections, one BasicTransformerBlock)."""
+    B, C, H, W = x.shape
+    res = x
+    h = F.group_norm(x, groups, sd[f'{p}.norm.weight'], sd[f'{p}.norm.bias'], 1e-6)
+    h = F.conv2d(h, sd[f'{p}.proj_in.weight'], sd[f'{p}.proj_in.bias'])
+    h = h.permute(0, 2, 3, 1).reshape(B, H * W, C)
+    t = f'{p}.transformer_blocks.0'
+    n = F.layer_norm(h, (C,), sd[f'{t}.norm1.weight'], sd[f'{t}.norm1.bias'], 1e-5)
+    h = _attention(sd, f'{t}.attn1', n, None, heads) + h
+    n = F.layer_norm(h, (C,), sd[f'{t}.norm2.weight'], sd[f'{t}.norm2.bias'], 1e-5)
+    h = _attention(sd, f'{t}.attn2', n, ctx, heads) + h
+    n = F.layer_norm(h, (C,), sd[f'{t}.norm3.weight'], sd[f'{t}.norm3.bias'], 1e-5)
+    g = F.linear(n, sd[f'{t}.ff.net.0.proj.weight'], sd[f'{t}.ff.net.0.proj.bias'])
+    a, gate = g.chunk(2, dim=-1)
+    h = F.linear(a * F.gelu(gate), sd[f'{t}.ff.net.2.weight'], sd[f'{t}.ff.net.2.bias']) + h
+    h = h.reshape(B, H, W, C).permute(0, 3, 1, 2).contiguous()
+    h = F.conv2d(h, sd[f'{p}.proj_out.weight'], sd[f'{p}.proj_out.bias'])
+    return h + res
+
+
+def sd_unet_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, t, ctx: torch.Tensor, cfg: Optional[dict] = None,
+                    taps: Optional[dict] = None) -> torch.Tensor:
+    """eps = UNet(x [B,4,H,W], timestep t (int or [B]), encoder_hidden_states ctx [B,77,D]).  `taps` (optional dict)
+    receives the output of every resnet / transformer / sampler by module name (per-layer parity tests)."""
+    cfg = cfg or sd_config_from_state_dict(sd)
+    boc, lpb, heads, groups = cfg['block_out_channels'], cfg['layers_per_block'], cfg['heads'], cfg['groups']
+    B = x.shape[0]
+    tt = torch.as_tensor(t, device=x.device)
+    tt = tt.reshape(-1).expand(B) if tt.numel() == 1 else tt
+    emb = timestep_embedding(tt, boc[0]).to(x.dtype)
+    emb = F.linear(emb, sd['time_embedding.linear_1.weight'], sd['time_embedding.linear_1.bias'])
+    emb = F.linear(F.silu(emb), sd['time_embedding.linear_2.weight'], sd['time_embedding.linear_2.bias'])
+    temb_act = F.silu(emb)                                               # ResnetBlock2D applies nonlinearity(temb) first
+
+    def tap(name, v):
+        if taps is not None:
+            taps[name] = v
+        return v
+
+    h = tap('conv_in', F.conv2d(x, sd['conv_in.weight'], sd['conv_in.bias'], padding=1))
+    skips = [h]
+    for i in range(len(boc)):
+        for j in range(lpb):
+            h = tap(f'down_blocks.{i}.resnets.{j}', _resnet(sd, f'down_blocks.{i}.resnets.{j}', h, temb_act, groups))
+            if cfg['cross_attn_down'][i]:
+                h = tap(f'down_blocks.{i}.attentions.{j}', _transformer(sd, f'down_blocks.{i}.attentions.{j}', h, ctx, heads, groups))
+            skips.append(h)
+        if i != len(boc) - 1:
+            p = f'down_blocks.{i}.downsamplers.0.conv'
+            h = tap(p, F.conv2d(h, sd[f'{p}.weight'], sd[f'{p}.bias'], stride=2, padding=1))
+            skips.append(h)
+    h = tap('mid_block.resnets.0', _resnet(sd, 'mid_block.resnets.0', h, temb_act, groups))
+    h = tap('mid_block.attentions.0', _transformer(sd, 'mid_block.attentions.0', h, ctx, heads, groups))
+    h = tap('mid_block.resnets.1', _resnet(sd, 'mid_block.resnets.1', h, temb_act, groups))
+    cross_up = list(cfg['cross_attn_down'])[::-1]
+    for i in range(len(boc)):
+        for j in range(lpb + 1):
+            h = torch.cat([h, skips.pop()], dim=1)
+            h = tap(f'up_blocks.{i}.resnets.{j}', _resnet(sd, f'up_blocks.{i}.resnets.{j}', h, temb_act, groups))
+            if cross_up[i]:
+                h = tap(f'up_blocks.{i}.attentions.{j}', _transformer(sd, f'up_blocks.{i}.attentions.{j}', h, ctx, heads, groups))
+        if i != len(boc) - 1:
+            p = f'up_blocks.{i}.upsamplers.0.conv'
+            h = F.interpolate(h, scale_factor=2.0, mode='nearest')
+            h = tap(p, F.conv2d(h, sd[f'{p}.weight'], sd[f'{p}.bias'], padding=1))
+    h = F.silu(F.group_norm(h, groups, sd['conv_norm_out.weight'], sd['conv_norm_out.bias'], 1e-5))
+    return F.conv2d(h, sd['conv_out.weight'], sd['conv_out.bias'], padding=1)
+
+
+# ---------------------------------------------------------------------------------------------- DDIM
+class DDIMTable:
+    """DDIMScheduler(beta_start=.00085, beta_end=.012, 'scaled_linear', clip_sample=False, set_alpha_to_one=False,
+    steps_offset=1) after set_timesteps(num_inference_steps): scheduling_ddim.py:190-216, 297-340."""
+
+    def __init__(self, num_inference_steps: int, num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012,
+                 steps_offset=1):
+        betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+        self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+        self.final_alpha_cumprod = self.alphas_cumprod[0]                     # set_alpha_to_one=False
+        self.num_train_timesteps, self.num_inference_steps = num_train_timesteps, num_inference_steps
+        ratio = num_train_timesteps // num_inference_steps                    # 'leading'
+        import numpy as np
+        ts = (np.arange(0, num_inference_steps) * ratio).round()[::-1].copy().astype(np.int64) + steps_offset
+        self.timesteps = [int(v) for v in ts]
+
+    def coeffs(self, t: int, eta: float = 1.0):
+        """(alpha_prod_t, alpha_prod_t_prev, std_dev_t) as fp32 tensors, scheduling_ddim.py:398-435."""
+        prev = t - self.num_train_timesteps // self.num_inference_steps
+        a_t = self.alphas_cumprod[t]
+        a_prev = self.alphas_cumprod[prev] if prev >= 0 else self.final_alpha_cumprod
+        variance = ((1 - a_prev) / (1 - a_t)) * (1 - a_t / a_prev)                # _get_variance :218-227
+        return a_t, a_prev, eta * variance ** 0.5
+
+
+def ddim_step(tab: DDIMTable, model_output, t: int, sample, variance_noise=None, eta: float = 1.0):
+    """scheduling_ddim.py:342-471 (epsilon prediction, no clipping): returns (prev_sample, pred_original_sample)."""
+    a_t, a_prev, std = tab.coeffs(t, eta)
+    beta_t = 1 - a_t
+    pred_x0 = (sample - beta_t ** 0.5 * model_output) / a_t ** 0.5
+    direction = (1 - a_prev - std ** 2) ** 0.5 * model_output
+    prev = a_prev ** 0.5 * pred_x0 + direction
+    if eta > 0 and variance_noise is not None:
+        prev = prev + std * variance_noise
+    return prev, pred_x0
+
+
+def latent_brightness(pred_x0: torch.Tensor) -> torch.Tensor:
+    """pipeline...:1115 quantisation, then the non-RGB branch of BrightnessScorer (sd/scorers.py:66-67)."""
+    u8 = (pred_x0 * 127.5 + 128).clip(0, 255).to(torch.uint8)
+    return (u8.float() / 255.0).mean(dim=(1, 2, 3))
+
+
+def beam_search(unet: Callable, tab: DDIMTable, latents: torch.Tensor, ctx_pair: torch.Tensor, B: int, N: int,
+                noises: Sequence[torch.Tensor], guidance: float = 7.5, score_fn: Callable = latent_brightness,
+                record: Optional[dict] = None) -> torch.Tensor:
+    """pipeline_stable_diffusion.py:1045-1170 with identity decode.  unet(x [M,4,H,W], t, ctx [M,77,D]) -> eps;
+    ctx_pair = [uncond, cond] embeddings [2,77,D]; noises[i] = [B, N, 4, H, W] variance noise of step i.
+    Returns the best final latent [1,4,H,W]."""
+    def guided(x, t):
+        xin = torch.cat([x, x])                                                    # :1058 (scale_model_input is identity)
+        ctx = torch.cat([ctx_pair[0:1].expand(x.shape[0], -1, -1), ctx_pair[1:2].expand(x.shape[0], -1, -1)])
+        e = unet(xin, t, ctx)
+        eu, et = e.chunk(2)
+        return eu + guidance * (et - eu)                                           # :1073-1075
+
+    beams = [latents.clone() for _ in range(B)]                                    # :1046
+    for i, t in enumerate(tab.timesteps):
+        cands, scores = [], []
+        for bi, beam in enumerate(beams):
+            eps = guided(beam, t)
+            for n in range(N):
+                cand, _ = ddim_step(tab, eps, t, beam, variance_noise=noises[i][bi, n:n + 1])      # :1083
+                eps2 = guided(cand, t)                                             # second UNet call at the SAME t (:1090)
+                _, pred_next = ddim_step(tab, eps2, t, cand)                       # :1109 (only pred_original_sample is used)
+                cands.append(cand)
+                scores.append(float(score_fn(pred_next)))
+        order = sorted(range(len(scores)), key=lambda k: scores[k], reverse=True)  # stable: lowest flat index wins ties (:1132)
+        if record is not None:
+            record.setdefault('scores', []).append(torch.tensor(scores))
+            record.setdefault('best', []).append(torch.tensor(order[:B]))
+        beams = [cands[k] for k in order[:B]]
+    best, best_score = beams[0], float('-inf')                                     # :1153-1166
+    for cand in beams:
+        s = float(score_fn(cand))
+        if s > best_score:
+            best, best_score = cand, s
+    if record is not None:
+        record['final_score'] = best_score
+    return best

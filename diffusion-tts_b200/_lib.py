@@ -22,7 +22,7 @@ class GemmDesc(C.Structure):
     _fields_ = [('a_ptr', c_vp * 3), ('a_channels', c_i32 * 3), ('n_seg', c_i32), ('seg', KSeg * 4),
                 ('batch', c_i32), ('H', c_i32), ('W', c_i32), ('w_ptr', c_vp), ('N', c_i32), ('Npad', c_i32),
                 ('Ktot', c_i32), ('bias', c_vp), ('residual', c_vp), ('ld_res', c_i32), ('out_scale', c_f32),
-                ('out', c_vp), ('ld_out', c_i32), ('out_fp32', c_i32), ('gn_stats', c_vp), ('reverse', c_i32)]
+                ('out', c_vp), ('ld_out', c_i32), ('out_fp32', c_i32), ('gn_stats', c_vp), ('reverse', c_i32), ('a_stride', c_i32 * 3)]
 
 
 class GnStatsDesc(C.Structure):
@@ -45,7 +45,8 @@ class GnFinalizeDesc(C.Structure):
 
 class AttnDesc(C.Structure):
     _fields_ = [('qk', c_vp), ('ld_qk', c_i32), ('k_col0', c_i32), ('vt', c_vp), ('out', c_vp), ('ld_out', c_i32),
-                ('batch', c_i32), ('heads', c_i32), ('L', c_i32), ('v_col0', c_i32), ('head_dim', c_i32), ('reverse', c_i32)]
+                ('batch', c_i32), ('heads', c_i32), ('L', c_i32), ('v_col0', c_i32), ('head_dim', c_i32), ('reverse', c_i32), ('scale', c_f32), ('kv', c_vp), ('ld_kv', c_i32),
+                ('kv_batch', c_i32), ('kv_rows', c_i32), ('kv_len', c_i32), ('kv_div', c_i32)]
 
 
 class LinearDesc(C.Structure):
@@ -92,6 +93,11 @@ SIGNATURES = {
     'b200ns_plan_add_pool_tokens': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32]),
     'b200ns_plan_add_pool_attention': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32]),
     'b200ns_plan_add_softmax_gather': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32]),
+    'b200ns_plan_add_layernorm': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_f32]),
+    'b200ns_plan_add_geglu': (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i32]),
+    'b200ns_plan_add_upsample2x': (C.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32]),
+    'b200ns_ddim_cfg_step': (C.c_int, [c_vp] * 6 + [c_i64, c_i32, c_i32, c_i32] + [c_f32] * 6 + [c_vp]),
+    'b200ns_ddim_x0_score': (C.c_int, [c_vp] * 6 + [c_i64, c_i32, c_i32] + [c_f32] * 3 + [c_vp]),
 }
 
 _lib = None

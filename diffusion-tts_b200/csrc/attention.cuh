@@ -22,6 +22,10 @@ struct AttnArgs {
   int k_col0;
   int v_col0;      // VROW mode: V lives row-major in the same [batch*L, ld] matrix at this column
   int reverse;     // walk (batch, head, query tile) last-to-first: start on what the qkv GEMM wrote last
+  float scale;     // softmax scale (head_dim^-0.5 of the TRUE head dimension)
+  int kv_rows;     // cross-attention: padded rows per context (multiple of the key tile); 0 = self-attention
+  int kv_len;      //   real tokens per context
+  int kv_div;      //   context index = batch index / kv_div
 };
 
 template <int KT>
@@ -419,20 +423,27 @@ attention_kernel_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 // tensor pipe works underneath the exponentials of tile kt; O accumulates in TMEM over all key tiles and is
 // only rescaled (lazily) when a row's maximum grows by more than 2^8, so no thread waits on an MMA it just
 // requested.  80 KB smem + 256 TMEM columns -> two CTAs per SM.
-template <int KT>
+// D = (padded) head dimension, a multiple of 64: D/64 SWIZZLE_128B atoms per Q/K/V tile.  Heads whose true
+// dimension is not a multiple of 64 (SD-1.5: 40, 80, 160) are zero-padded by the projection weights.
+template <int KT, int D = 64>
 struct AttnCfg3 {
-  static constexpr int Q_BYTES = 128 * 128;
-  static constexpr int K_BYTES = KT * 128;
-  static constexpr int V_BYTES = KT * 128;
+  static constexpr int ATOMS = D / 64;
+  static constexpr int Q_BYTES = ATOMS * 128 * 128;
+  static constexpr int K_BYTES = ATOMS * KT * 128;
+  static constexpr int V_BYTES = ATOMS * KT * 128;
   static constexpr int SMEM_BYTES = Q_BYTES + 2 * K_BYTES + 2 * V_BYTES + 1024 + 128;
   static constexpr int THREADS = 160;
+  static constexpr int TMEM_NEED = KT + KT / 2 + D;
+  static constexpr int TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
+  static constexpr int MIN_CTAS = (TMEM_COLS == 256 && SMEM_BYTES <= 110 * 1024) ? 2 : 1;
 };
 
-template <int KT>
-__global__ void __launch_bounds__(160, 2)
+template <int KT, int D = 64>
+__global__ void __launch_bounds__(160, AttnCfg3<KT, D>::MIN_CTAS)
 attention_kernel_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnArgs a) {
-  using Cfg = AttnCfg3<KT>;
+  using Cfg = AttnCfg3<KT, D>;
+  constexpr int ATOMS = Cfg::ATOMS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -452,7 +463,12 @@ attention_kernel_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int bh = a.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y, bi = bh / a.heads, head = bh % a.heads;
   const int q0 = (a.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * 128;
   const int row_base = bi * a.L;
-  const int nkt = a.L / KT;
+  // keys/values: self-attention reads this sample's own L rows; cross-attention (kv_rows > 0) reads the kv_rows
+  // (padded, multiple of KT) rows of context bi / kv_div, of which the first kv_len are real tokens
+  const int kv_rows = a.kv_rows > 0 ? a.kv_rows : a.L;
+  const int kv_base = a.kv_rows > 0 ? (bi / a.kv_div) * a.kv_rows : row_base;
+  const int kv_len = a.kv_rows > 0 ? a.kv_len : a.L;
+  const int nkt = kv_rows / KT;
 
   if (tid == 0) {
     prefetch_tmap(&tmQ);
@@ -464,7 +480,7 @@ attention_kernel_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 0) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -477,24 +493,34 @@ attention_kernel_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // ===================== issuer: TMA + MMA (one thread) =====================
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, KT);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, true);      // B = V, MN-major
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, D, true);       // B = V, MN-major, N = D
       auto load_k = [&](int kt) {
         mbar_arrive_expect_tx(&bar_k[kt & 1], Cfg::K_BYTES);
-        tma_load_2d(sK + (kt & 1) * Cfg::K_BYTES, &tmK, &bar_k[kt & 1], a.k_col0 + head * 64, row_base + kt * KT);
+#pragma unroll
+        for (int at = 0; at < ATOMS; ++at)
+          tma_load_2d(sK + (kt & 1) * Cfg::K_BYTES + at * KT * 128, &tmK, &bar_k[kt & 1], a.k_col0 + head * D + at * 64,
+                      kv_base + kt * KT);
       };
       auto load_v = [&](int kt) {
         mbar_arrive_expect_tx(&bar_v[kt & 1], Cfg::V_BYTES);
-        tma_load_2d(sV + (kt & 1) * Cfg::V_BYTES, &tmV, &bar_v[kt & 1], a.v_col0 + head * 64, row_base + kt * KT);
+#pragma unroll
+        for (int at = 0; at < ATOMS; ++at)
+          tma_load_2d(sV + (kt & 1) * Cfg::V_BYTES + at * KT * 128, &tmV, &bar_v[kt & 1], a.v_col0 + head * D + at * 64,
+                      kv_base + kt * KT);
       };
       auto issue_s = [&](int kt) {
-        const uint64_t dq = umma_desc_sw128(smem_u32(sQ));
-        const uint64_t dk = umma_desc_sw128(smem_u32(sK + (kt & 1) * Cfg::K_BYTES));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tS, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        for (int at = 0; at < ATOMS; ++at) {
+          const uint64_t dq = umma_desc_sw128(smem_u32(sQ + at * 128 * 128));
+          const uint64_t dk = umma_desc_sw128(smem_u32(sK + (kt & 1) * Cfg::K_BYTES + at * KT * 128));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tS, dq + 2 * k, dk + 2 * k, idesc_s, (at | k) != 0);
+        }
         umma_commit(bar_s);
       };
       mbar_arrive_expect_tx(bar_q, Cfg::Q_BYTES);
-      tma_load_2d(sQ, &tmQ, bar_q, head * 64, row_base + q0);
+#pragma unroll
+      for (int at = 0; at < ATOMS; ++at) tma_load_2d(sQ + at * 128 * 128, &tmQ, bar_q, head * D + at * 64, row_base + q0);
       load_k(0);
       load_v(0);
       if (nkt > 1) {
@@ -517,7 +543,9 @@ attention_kernel_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (kt >= 1 && kt + 1 < nkt) load_v(kt + 1);
         mbar_wait(&bar_v[kt & 1], (kt >> 1) & 1);
         tc_fence_after();
-        const uint64_t dv = umma_desc_sw128(smem_u32(sV + (kt & 1) * Cfg::V_BYTES));
+        // V tile = ATOMS blocks of [KT keys x 64 d]; as the MN-major B operand of N = D the leading-dimension byte
+        // offset is the distance between consecutive 64-wide d blocks
+        const uint64_t dv = umma_desc_sw128_lbo(smem_u32(sV + (kt & 1) * Cfg::V_BYTES), KT * 128);
 #pragma unroll
         for (int k = 0; k < KT / 16; ++k)             // 16 keys per MMA: 8 packed TMEM columns of P, 2 KB of V rows
           umma_bf16_ts(tO, tP + k * 8, dv + static_cast<uint64_t>(k * (2048 >> 4)), idesc_o, (kt | k) != 0);
@@ -530,7 +558,7 @@ attention_kernel_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // more than 2^8 (in the base-2 exponent domain); otherwise the stale maximum is kept -- softmax is shift
     // invariant, probabilities stay <= 256, and the O rescale (TMEM load, multiply, store) is skipped for the warp.
     const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-    const float c = 0.125f * 1.4426950408889634f;     // 1/sqrt(64) * log2(e)
+    const float c = a.scale * 1.4426950408889634f;    // head_dim^-0.5 * log2(e)
     float m_used = -INFINITY, l_run = 0.f;
     for (int kt = 0; kt < nkt; ++kt) {
       mbar_wait(bar_s, kt & 1);
@@ -546,6 +574,11 @@ attention_kernel_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(bar_sfree);
+      if ((kt + 1) * KT > kv_len) {                    // padded keys (cross-attention): score = -inf => p = 0
+#pragma unroll
+        for (int j = 0; j < KT; ++j)
+          if (kt * KT + j >= kv_len) sr[j] = 0xff800000u;
+      }
       float mx = __uint_as_float(sr[0]);
 #pragma unroll
       for (int j = 1; j < KT; ++j) mx = fmaxf(mx, __uint_as_float(sr[j]));
@@ -571,7 +604,7 @@ attention_kernel_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tc_fence_after();
         if (__any_sync(0xffffffffu, raise)) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          for (int h = 0; h < D / 32; ++h) {
             uint32_t r[32];
             tmem_ld32(tO + lane_addr + h * 32, r);
             tmem_ld_wait();
@@ -596,9 +629,9 @@ attention_kernel_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tc_fence_after();
     const int q = q0 + tid;
     const float inv = 1.0f / l_run;
-    uint4* op = reinterpret_cast<uint4*>(a.out + static_cast<size_t>(row_base + q) * a.ld_out + head * 64);
+    uint4* op = reinterpret_cast<uint4*>(a.out + static_cast<size_t>(row_base + q) * a.ld_out + head * D);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < D / 32; ++h) {
       uint32_t r[32];
       tmem_ld32(tO + lane_addr + h * 32, r);
       tmem_ld_wait();
@@ -619,7 +652,7 @@ attention_kernel_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 

@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -16,6 +17,7 @@
 #include "groupnorm.cuh"
 #include "jpeg.cuh"
 #include "sampler.cuh"
+#include "sdops.cuh"
 
 using namespace b200;
 
@@ -70,7 +72,8 @@ EncodeTiledFn get_encode() {
 }
 
 // bf16 tensor, `rank` dims (innermost first), 128B swizzle, zero OOB fill.
-int make_tmap(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box) {
+int make_tmap(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box,
+              const uint32_t* elem_strides = nullptr) {
   EncodeTiledFn enc = get_encode();
   if (enc == nullptr) return fail("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   cuuint64_t gdim[5];
@@ -80,7 +83,7 @@ int make_tmap(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims, 
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = elem_strides ? elem_strides[i] : 1;
     stride *= dims[i];
     if (i < rank - 1) gstr[i] = stride;
   }
@@ -121,7 +124,7 @@ int make_tmap_2d_ld(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t ro
 
 // ------------------------------------------------------------------ plan ops
 enum OpKind { OP_GEMM, OP_GN_STATS, OP_GN_APPLY, OP_GN_FINALIZE, OP_ATTN, OP_LINEAR, OP_IM2COL, OP_U8F32, OP_POOL_TOKENS, OP_POOL_ATTN,
-              OP_SOFTMAX_GATHER };
+              OP_SOFTMAX_GATHER, OP_LAYERNORM, OP_GEGLU, OP_UPSAMPLE2X };
 
 struct GemmOp {
   CUtensorMap tmA[3], tmB, tmO, tmR;
@@ -169,6 +172,7 @@ struct MiscOp {          // the small classifier kernels: plain pointers + a few
   void* p3;
   int64_t n;
   int i0, i1, i2;
+  float f0;
 };
 
 struct Op {
@@ -246,15 +250,15 @@ int launch_attn_t(const AttnOp& o, cudaStream_t st) {
   return 0;
 }
 
-template <int KT>
+template <int KT, int D = 64>
 int launch_attn_v3(const AttnOp& o, cudaStream_t st) {
-  using Cfg = AttnCfg3<KT>;
+  using Cfg = AttnCfg3<KT, D>;
   static bool attr_set = false;
   if (!attr_set) {
-    CK(cudaFuncSetAttribute(attention_kernel_v3<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(attention_kernel_v3<KT, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  attention_kernel_v3<KT><<<o.grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(o.tmQ, o.tmK, o.tmV, o.args);
+  attention_kernel_v3<KT, D><<<o.grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(o.tmQ, o.tmK, o.tmV, o.args);
   CK_LAUNCH("attention_kernel_v3");
   return 0;
 }
@@ -280,7 +284,10 @@ int run_op(const Op& op, cudaStream_t st) {
       CK_LAUNCH("gn_stats_kernel");
       return 0;
     case OP_GN_APPLY:
-      gn_apply_kernel<<<op.gna.grid, op.gna.threads, 0, st>>>(op.gna.args);
+      if (op.gna.threads > 256)
+        gn_apply_kernel<true><<<op.gna.grid, op.gna.threads, 0, st>>>(op.gna.args);
+      else
+        gn_apply_kernel<false><<<op.gna.grid, op.gna.threads, 0, st>>>(op.gna.args);
       CK_LAUNCH("gn_apply_kernel");
       return 0;
     case OP_GN_FINALIZE:
@@ -299,6 +306,8 @@ int run_op(const Op& op, cudaStream_t st) {
         return 0;
       }
       if (op.attn.vrow && op.attn.variant == 2) return op.attn.KT == 128 ? launch_attn_v2<128>(op.attn, st) : launch_attn_v2<64>(op.attn, st);
+      if (op.attn.vrow && op.attn.head_dim == 128) return launch_attn_v3<64, 128>(op.attn, st);
+      if (op.attn.vrow && op.attn.head_dim == 192) return launch_attn_v3<64, 192>(op.attn, st);
       if (op.attn.vrow) return op.attn.KT == 128 ? launch_attn_v3<128>(op.attn, st) : launch_attn_v3<64>(op.attn, st);
       return op.attn.KT == 128 ? launch_attn_t<128, false>(op.attn, st) : launch_attn_t<64, false>(op.attn, st);
     case OP_LINEAR:
@@ -333,6 +342,25 @@ int run_op(const Op& op, cudaStream_t st) {
                                                         reinterpret_cast<const int64_t*>(op.misc.p1),
                                                         reinterpret_cast<float*>(op.misc.p2), op.misc.i1);
       CK_LAUNCH("softmax_gather_kernel");
+      return 0;
+    case OP_LAYERNORM:
+      layernorm_kernel<<<static_cast<unsigned>((op.misc.n + 7) / 8), 256, 0, st>>>(
+          reinterpret_cast<const __nv_bfloat16*>(op.misc.p0), reinterpret_cast<const float*>(op.misc.p1),
+          reinterpret_cast<const float*>(op.misc.p3), reinterpret_cast<__nv_bfloat16*>(op.misc.p2), op.misc.n, op.misc.i0,
+          op.misc.f0);
+      CK_LAUNCH("layernorm_kernel");
+      return 0;
+    case OP_GEGLU:
+      geglu_kernel<<<grid_for(op.misc.n * (op.misc.i0 / 8), 256, 148 * 32), 256, 0, st>>>(
+          reinterpret_cast<const __nv_bfloat16*>(op.misc.p0), reinterpret_cast<__nv_bfloat16*>(op.misc.p2), op.misc.n, op.misc.i0);
+      CK_LAUNCH("geglu_kernel");
+      return 0;
+    case OP_UPSAMPLE2X:
+      upsample2x_kernel<<<grid_for(static_cast<int64_t>(op.misc.i0) * op.misc.i1 * op.misc.i2 * 4 * (op.misc.n / 8), 256, 148 * 32),
+                          256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(op.misc.p0),
+                                        reinterpret_cast<__nv_bfloat16*>(op.misc.p2), op.misc.i0, op.misc.i1, op.misc.i2,
+                                        static_cast<int>(op.misc.n));
+      CK_LAUNCH("upsample2x_kernel");
       return 0;
   }
   return fail("bad op kind");
@@ -663,14 +691,20 @@ int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d) {
   }
 
   for (int i = 0; i < 3; ++i) {
-    const void* ptr = d->a_ptr[i] ? d->a_ptr[i] : d->a_ptr[0];
-    const int ch = d->a_ptr[i] ? d->a_channels[i] : d->a_channels[0];
+    const bool used = d->a_ptr[i] != nullptr;
+    const void* ptr = used ? d->a_ptr[i] : d->a_ptr[0];
+    const int ch = used ? d->a_channels[i] : d->a_channels[0];
+    const int sdn = (used ? d->a_stride[i] : d->a_stride[0]) == 2 ? 2 : 1;      // 2: this source is read with stride 2
     if (ch % 64) return fail("gemm: activation channels must be a multiple of 64");
-    const uint64_t dims[4] = {static_cast<uint64_t>(ch), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+    if (W * sdn > 256 || tileH * sdn > 256) return fail("gemm: strided box exceeds 256 elements");
+    const uint64_t dims[4] = {static_cast<uint64_t>(ch), static_cast<uint64_t>(W) * sdn, static_cast<uint64_t>(H) * sdn,
                               static_cast<uint64_t>(d->batch)};
-    const uint32_t box[4] = {64, static_cast<uint32_t>(W), static_cast<uint32_t>(tileH), static_cast<uint32_t>(tileN)};
-    int rc = make_tmap(&g.tmA[i], ptr, 4, dims, box);
+    const uint32_t box[4] = {64, static_cast<uint32_t>(W * sdn), static_cast<uint32_t>(tileH * sdn),
+                             static_cast<uint32_t>(tileN)};
+    const uint32_t es[4] = {1, static_cast<uint32_t>(sdn), static_cast<uint32_t>(sdn), 1};
+    int rc = make_tmap(&g.tmA[i], ptr, 4, dims, box, es);
     if (rc) return rc;
+    a.src_stride[i] = sdn;
   }
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(d->Ktot), static_cast<uint64_t>(d->Npad)};
@@ -722,7 +756,7 @@ int b200ns_plan_add_gn_apply(b200ns_plan* p, const b200ns_gn_apply_desc* d) {
   a.C0 = d->x_channels[0];
   a.C1 = d->x_ptr[1] ? d->x_channels[1] : 0;
   a.C = a.C0 + a.C1;
-  if (a.C % 8 || a.C0 % 8 || a.C > 2048) return fail("gn_apply: channels must be multiples of 8 and <= 2048");
+  if (a.C % 8 || a.C0 % 8 || a.C > 4096) return fail("gn_apply: channels must be multiples of 8 and <= 4096");
   if (d->groups > 64 || a.C % d->groups) return fail("gn_apply: bad group count");
   if (d->resample == 2 && (d->H % 2 || d->W % 2)) return fail("gn_apply: odd size cannot be downsampled");
   a.H = d->H;
@@ -817,27 +851,46 @@ int b200ns_plan_add_attention(b200ns_plan* p, const b200ns_attn_desc* d) {
     p->push(op);
     return 0;
   }
-  if (o.head_dim != 64) return fail("attention: head_dim must be 64 or 256");
-  {
-    const uint64_t dims[2] = {static_cast<uint64_t>(d->ld_qk), M};
-    const uint32_t boxq[2] = {64, 128};
-    const uint32_t boxk[2] = {64, static_cast<uint32_t>(o.KT)};
-    int rc = make_tmap(&o.tmQ, d->qk, 2, dims, boxq);
-    if (rc) return rc;
-    rc = make_tmap(&o.tmK, d->qk, 2, dims, boxk);
-    if (rc) return rc;
-  }
+  if (o.head_dim != 64 && o.head_dim != 128 && o.head_dim != 192)
+    return fail("attention: (padded) head_dim must be 64, 128, 192 or 256");
   o.vrow = d->vt == nullptr ? 1 : 0;
   {
     const char* v = getenv("B200NS_ATTN");
     o.variant = (v != nullptr && v[0] == '2') ? 2 : 3;
   }
-  if (o.vrow) {       // V row-major inside the qkv matrix: box [KT keys][64 d]
+  const bool cross = d->kv != nullptr;
+  if ((o.head_dim != 64 || cross || d->scale > 0.f) && (!o.vrow || o.variant != 3))
+    return fail("attention: padded head dims / cross-attention / custom scale need the row-major-V v3 kernel");
+  if (o.head_dim != 64) o.KT = 64;
+  if (cross) {
+    if (d->kv_rows <= 0 || d->kv_rows % 128 || d->kv_len <= 0 || d->kv_len > d->kv_rows || d->kv_div <= 0 || d->kv_batch <= 0)
+      return fail("attention: cross-attention needs kv_rows % 128 == 0, 0 < kv_len <= kv_rows, kv_div > 0, kv_batch > 0");
+    o.KT = 64;
+  }
+  o.args.scale = d->scale > 0.f ? d->scale : 1.0f / sqrtf(static_cast<float>(o.head_dim));
+  o.args.kv_rows = cross ? d->kv_rows : 0;
+  o.args.kv_len = cross ? d->kv_len : 0;
+  o.args.kv_div = cross ? d->kv_div : 1;
+  {
     const uint64_t dims[2] = {static_cast<uint64_t>(d->ld_qk), M};
-    const uint32_t box[2] = {64, static_cast<uint32_t>(o.KT)};
-    int rc = make_tmap(&o.tmV, d->qk, 2, dims, box);
+    const uint32_t boxq[2] = {64, 128};
+    int rc = make_tmap(&o.tmQ, d->qk, 2, dims, boxq);
     if (rc) return rc;
-  } else {
+  }
+  {
+    // K (and row-major V) tiles: [KT keys][64 d] boxes of the qkv matrix, or of the context K/V matrix (cross)
+    const void* kvp = cross ? d->kv : d->qk;
+    const uint64_t dims[2] = {static_cast<uint64_t>(cross ? d->ld_kv : d->ld_qk),
+                              cross ? static_cast<uint64_t>(d->kv_batch) * d->kv_rows : M};
+    const uint32_t boxk[2] = {64, static_cast<uint32_t>(o.KT)};
+    int rc = make_tmap(&o.tmK, kvp, 2, dims, boxk);
+    if (rc) return rc;
+    if (o.vrow) {
+      rc = make_tmap(&o.tmV, kvp, 2, dims, boxk);
+      if (rc) return rc;
+    }
+  }
+  if (!o.vrow) {
     const uint64_t dims[2] = {static_cast<uint64_t>(d->L), static_cast<uint64_t>(d->batch) * d->heads * 64};
     const uint32_t box[2] = {64, 64};
     int rc = make_tmap(&o.tmV, d->vt, 2, dims, box);
@@ -920,6 +973,70 @@ int b200ns_plan_add_softmax_gather(b200ns_plan* p, const float* logits, const in
   op.misc.i0 = rows;
   op.misc.i1 = K;
   p->push(op);
+  return 0;
+}
+
+int b200ns_plan_add_layernorm(b200ns_plan* p, const void* x, const float* gamma, const float* beta, void* out, int64_t rows,
+                              int32_t C, float eps) {
+  if (C % 8 || C > 2048) return fail("layernorm: C must be a multiple of 8 and <= 2048");
+  Op op;
+  op.kind = OP_LAYERNORM;
+  op.misc.p0 = x;
+  op.misc.p1 = gamma;
+  op.misc.p3 = const_cast<float*>(beta);
+  op.misc.p2 = out;
+  op.misc.n = rows;
+  op.misc.i0 = C;
+  op.misc.f0 = eps;
+  p->push(op);
+  return 0;
+}
+
+int b200ns_plan_add_geglu(b200ns_plan* p, const void* in, void* out, int64_t rows, int32_t F) {
+  if (F % 8) return fail("geglu: F must be a multiple of 8");
+  Op op;
+  op.kind = OP_GEGLU;
+  op.misc.p0 = in;
+  op.misc.p2 = out;
+  op.misc.n = rows;
+  op.misc.i0 = F;
+  p->push(op);
+  return 0;
+}
+
+int b200ns_plan_add_upsample2x(b200ns_plan* p, const void* in, void* out, int32_t batch, int32_t H, int32_t W, int32_t C) {
+  if (C % 8) return fail("upsample2x: C must be a multiple of 8");
+  Op op;
+  op.kind = OP_UPSAMPLE2X;
+  op.misc.p0 = in;
+  op.misc.p2 = out;
+  op.misc.i0 = batch;
+  op.misc.i1 = H;
+  op.misc.i2 = W;
+  op.misc.n = C;
+  p->push(op);
+  return 0;
+}
+
+int b200ns_ddim_cfg_step(const float* eps_u, const float* eps_t, const float* sample, const float* noise, float* prev,
+                         float* net_in, int64_t R, int32_t per_parent, int32_t C, int32_t HW, float guidance,
+                         float sqrt_beta_t, float sqrt_alpha_t, float sqrt_alpha_prev, float dir_coef, float std_dev,
+                         void* stream) {
+  if (R <= 0 || per_parent <= 0 || R % per_parent) return fail("ddim_cfg_step: R must be a positive multiple of per_parent");
+  ddim_cfg_step_kernel<<<grid_for(R * C * HW, 256, 148 * 16), 256, 0, S(stream)>>>(
+      eps_u, eps_t, sample, noise, prev, net_in, R, per_parent, C, HW, guidance, sqrt_beta_t, sqrt_alpha_t, sqrt_alpha_prev,
+      dir_coef, std_dev);
+  CK_LAUNCH("ddim_cfg_step_kernel");
+  return 0;
+}
+
+int b200ns_ddim_x0_score(const float* eps_u, const float* eps_t, const float* cand, float* pred_x0, int32_t* sums,
+                         float* scores, int64_t R, int32_t C, int32_t HW, float guidance, float sqrt_beta_t,
+                         float sqrt_alpha_t, void* stream) {
+  if (R <= 0) return fail("ddim_x0_score: R must be positive");
+  ddim_x0_score_kernel<<<static_cast<unsigned>(R), 256, 0, S(stream)>>>(eps_u, eps_t, cand, pred_x0, sums, scores, C, HW,
+                                                                        guidance, sqrt_beta_t, sqrt_alpha_t);
+  CK_LAUNCH("ddim_x0_score_kernel");
   return 0;
 }
 

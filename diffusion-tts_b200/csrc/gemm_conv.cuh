@@ -49,6 +49,7 @@ struct GemmArgs {
   int ld_out;
   int out_fp32;
   float2* gn_stats;              // [M/64, N] (sum, sum of squares) per 64-row half tile, or null
+  int src_stride[3];             // 1, or 2: the source is sampled with stride 2 (3x3 stride-2 pad-1 conv: Downsample2D)
   int reverse;                   // walk the tiles last-to-first (start on what the producer of A wrote last: L2 hits)
 };
 
@@ -94,13 +95,14 @@ DEVINL void gemm_producer(const CUtensorMap& tmA0, const CUtensorMap& tmA1, cons
     for (int s = 0; s < a.n_seg; ++s) {
       const KSeg sg = a.seg[s];
       const CUtensorMap* tm = sg.src == 0 ? &tmA0 : (sg.src == 1 ? &tmA1 : &tmA2);
+      const int sdn = a.src_stride[sg.src];          // stride 2: input row = 2*out_row + dy (TMA elementStrides = 2)
       for (int tap = 0; tap < sg.taps; ++tap) {
         const int dy = sg.taps == 9 ? tap / 3 - 1 : 0;
         const int dx = sg.taps == 9 ? tap % 3 - 1 : 0;
         for (int cb = 0; cb < sg.cblocks; ++cb, ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_4d(smem_a + stage * Cfg::A_BYTES, tm, &full_bar[stage], sg.cstart + cb * 64, dx, y0 + dy, n0);
+          tma_load_4d(smem_a + stage * Cfg::A_BYTES, tm, &full_bar[stage], sg.cstart + cb * 64, dx, y0 * sdn + dy, n0);
           tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * 64, nt * BN);
           if (++stage == STAGES) {
             stage = 0;

@@ -236,7 +236,9 @@ struct GnApplyArgs {
 };
 
 // grid (pixel chunks, batch); block = (C/8) * PY threads
-__global__ void __launch_bounds__(256, 3) gn_apply_kernel(const GnApplyArgs a) {
+// WIDE: more than 2048 channels (SD-1.5 decoder concat 2560): up to 512 threads per block
+template <bool WIDE>
+__global__ void __launch_bounds__(WIDE ? 512 : 256, WIDE ? 1 : 3) gn_apply_kernel(const GnApplyArgs a) {
   __shared__ float s_mean[64];
   __shared__ float s_rstd[64];
   const int VC = a.C >> 3;

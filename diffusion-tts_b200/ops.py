@@ -156,6 +156,47 @@ def make_candidates(pivot, dirs, norms, scale, fresh_mask=None, fresh=None) -> t
     return cand
 
 
+def ddim_cfg_step(eps_pair: torch.Tensor, sample: torch.Tensor, noise: Optional[torch.Tensor], per_parent: int, guidance: float,
+                  sqrt_beta_t: float, sqrt_alpha_t: float, sqrt_alpha_prev: float, dir_coef: float, std_dev: float, *,
+                  net_in: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """CFG + DDIM step (variance noise supplied).  eps_pair fp32 NHWC [2P,H,W,C] = UNet output for [uncond; cond];
+    sample fp32 NCHW [P,C,H,W]; noise fp32 NCHW [P*per_parent,C,H,W] or None.  Returns prev [R,C,H,W]; fills net_in
+    ([2R,C,H,W], both CFG halves) when given."""
+    _chk_cuda(eps_pair, sample, noise, net_in)
+    _c(eps_pair, torch.float32), _c(sample, torch.float32)
+    P, Cc, H, W = sample.shape
+    R = P * per_parent
+    if eps_pair.shape[0] != 2 * P:
+        raise RuntimeError('ddim_cfg_step: eps_pair must hold the uncond and cond halves of the P parents')
+    if noise is not None:
+        _c(noise, torch.float32)
+    prev = torch.empty((R, Cc, H, W), dtype=torch.float32, device=sample.device)
+    eu, et = eps_pair[:P], eps_pair[P:]
+    L.check(L.lib().b200ns_ddim_cfg_step(L.ptr(eu), L.ptr(et), L.ptr(sample), L.ptr(noise), L.ptr(prev),
+                                         L.ptr(_c(net_in, torch.float32)) if net_in is not None else None, R, per_parent, Cc,
+                                         H * W, float(guidance), float(sqrt_beta_t), float(sqrt_alpha_t),
+                                         float(sqrt_alpha_prev), float(dir_coef), float(std_dev), L.cur_stream()), 'ddim_cfg_step')
+    _count()
+    return prev
+
+
+def ddim_x0_score(eps_pair: torch.Tensor, cand: torch.Tensor, guidance: float, sqrt_beta_t: float, sqrt_alpha_t: float, *,
+                  want_x0: bool = False):
+    """Guided eps of the 2nd UNet call -> pred_x0 -> uint8 -> mean(u8/255).  eps_pair fp32 NHWC [2R,H,W,C]; cand fp32
+    NCHW [R,C,H,W].  Returns (scores fp32 [R], integer sums int32 [R], pred_x0 or None)."""
+    _chk_cuda(eps_pair, cand)
+    _c(eps_pair, torch.float32), _c(cand, torch.float32)
+    R, Cc, H, W = cand.shape
+    scores = torch.empty((R,), dtype=torch.float32, device=cand.device)
+    sums = torch.empty((R,), dtype=torch.int32, device=cand.device)
+    x0 = torch.empty_like(cand) if want_x0 else None
+    L.check(L.lib().b200ns_ddim_x0_score(L.ptr(eps_pair[:R]), L.ptr(eps_pair[R:]), L.ptr(cand), L.ptr(x0), L.ptr(sums),
+                                         L.ptr(scores), R, Cc, H * W, float(guidance), float(sqrt_beta_t),
+                                         float(sqrt_alpha_t), L.cur_stream()), 'ddim_x0_score')
+    _count()
+    return scores, sums, x0
+
+
 # ------------------------------------------------------------------ plans
 class Plan:
     """Ordered list of kernel launches (b200ns_plan).  Keeps every tensor it references alive."""
@@ -213,16 +254,21 @@ class Plan:
         return [evs[i].elapsed_time(evs[i + 1]) for i in range(n)]
 
     def add_gemm(self, a: Sequence[torch.Tensor], segs: Sequence[Tuple[int, int, int, int]], w: torch.Tensor, N: int,
-                 out: torch.Tensor, *, bias=None, residual=None, out_scale=1.0, gn_stats=None, reverse=False, label='gemm',
-                 alg_k=None):
+                 out: torch.Tensor, *, bias=None, residual=None, out_scale=1.0, gn_stats=None, reverse=False, a_stride=None,
+                 label='gemm', alg_k=None):
         """a: 1-3 NHWC bf16 tensors [B,H,W,C]; segs: (src, taps, cstart, cblocks); w: bf16 [Npad,Ktot].
         gn_stats: optional fp32 [M/64, N, 2] receiving per-channel (sum, sumsq) of the stored output."""
         d = L.GemmDesc()
+        a_stride = list(a_stride) if a_stride is not None else [1] * len(a)
         B, H, W_, _ = a[0].shape
+        H, W_ = H // a_stride[0], W_ // a_stride[0]           # output spatial dims (stride-2 sources are 2H x 2W)
         for i, t in enumerate(a):
             _c(t, torch.bfloat16)
+            if t.shape[1] != H * a_stride[i] or t.shape[2] != W_ * a_stride[i]:
+                raise RuntimeError('gemm: source spatial dims do not match the output dims times the source stride')
             d.a_ptr[i] = L.ptr(t)
             d.a_channels[i] = t.shape[3]
+            d.a_stride[i] = a_stride[i]
         d.n_seg = len(segs)
         for i, (src, taps, cstart, cblocks) in enumerate(segs):
             d.seg[i] = L.KSeg(src, taps, cstart, cblocks)
@@ -315,7 +361,8 @@ class Plan:
         self.flops.append(0.0)
 
     def add_attention(self, qk: torch.Tensor, k_col0: int, vt: Optional[torch.Tensor], out: torch.Tensor, batch: int,
-                      heads: int, Lseq: int, label='attention', v_col0: int = 0, head_dim: int = 64, reverse=False):
+                      heads: int, Lseq: int, label='attention', v_col0: int = 0, head_dim: int = 64, reverse=False,
+                      scale: float = 0.0, kv: Optional[torch.Tensor] = None, kv_rows: int = 0, kv_len: int = 0, kv_div: int = 1):
         """qk: [batch*L, ld] with Q at col head*64, K at k_col0 + head*64; V either transposed in `vt`
         ([batch*heads*64, L]) or (vt=None) row-major in `qk` at v_col0 + head*64."""
         d = L.AttnDesc()
@@ -324,13 +371,18 @@ class Plan:
         d.v_col0 = v_col0
         d.head_dim = head_dim
         d.reverse = int(reverse)
+        d.scale = float(scale)
+        if kv is not None:         # cross-attention: K/V of the (few) contexts, [kv_batch * kv_rows, ld_kv]
+            d.kv, d.ld_kv = L.ptr(_c(kv, torch.bfloat16)), kv.shape[-1]
+            d.kv_batch, d.kv_rows, d.kv_len, d.kv_div = kv.numel() // (kv.shape[-1] * kv_rows), kv_rows, kv_len, kv_div
+            self._keep.append(kv)
         d.out, d.ld_out = L.ptr(_c(out, torch.bfloat16)), out.shape[-1]
         d.batch, d.heads, d.L = batch, heads, Lseq
         self._k(qk, vt, out)
         L.check(L.lib().b200ns_plan_add_attention(self._h, C.byref(d)), 'plan_add_attention')
         self.labels.append(label)
         self.kinds.append('attention')
-        self.flops.append(4.0 * batch * heads * Lseq * Lseq * head_dim)
+        self.flops.append(4.0 * batch * heads * Lseq * (kv_rows if kv is not None else Lseq) * head_dim)
 
     def add_linear(self, x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, add=None, act=0,
                    label='linear'):
@@ -346,6 +398,33 @@ class Plan:
         self.labels.append(label)
         self.kinds.append('linear')
         self.flops.append(0.0)
+
+    def add_layernorm(self, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor, eps: float = 1e-5,
+                      label='layernorm'):
+        """nn.LayerNorm over the last dim of a bf16 tensor [..., C]."""
+        Cc = x.shape[-1]
+        self._k(x, gamma, beta, out)
+        L.check(L.lib().b200ns_plan_add_layernorm(self._h, L.ptr(_c(x, torch.bfloat16)), L.ptr(_c(gamma, torch.float32)),
+                                                  L.ptr(_c(beta, torch.float32)), L.ptr(_c(out, torch.bfloat16)),
+                                                  x.numel() // Cc, Cc, float(eps)), 'plan_add_layernorm')
+        self._misc('layernorm', label)
+
+    def add_geglu(self, x: torch.Tensor, out: torch.Tensor, label='geglu'):
+        """x bf16 [..., 2F] = [hidden | gate] -> out bf16 [..., F] = hidden * gelu(gate)."""
+        F_ = out.shape[-1]
+        if x.shape[-1] != 2 * F_:
+            raise RuntimeError('geglu: input must be twice as wide as the output')
+        self._k(x, out)
+        L.check(L.lib().b200ns_plan_add_geglu(self._h, L.ptr(_c(x, torch.bfloat16)), L.ptr(_c(out, torch.bfloat16)),
+                                              out.numel() // F_, F_), 'plan_add_geglu')
+        self._misc('geglu', label)
+
+    def add_upsample2x(self, x: torch.Tensor, out: torch.Tensor, label='upsample2x'):
+        B, H, W_, Cc = x.shape
+        self._k(x, out)
+        L.check(L.lib().b200ns_plan_add_upsample2x(self._h, L.ptr(_c(x, torch.bfloat16)), L.ptr(_c(out, torch.bfloat16)),
+                                                   B, H, W_, Cc), 'plan_add_upsample2x')
+        self._misc('upsample2x', label)
 
     def add_im2col(self, x: torch.Tensor, out: torch.Tensor, label='im2col'):
         d = L.Im2colDesc()

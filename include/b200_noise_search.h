@@ -146,6 +146,9 @@ typedef struct {
   /* 1: process the output tiles last-to-first.  Alternating the walk direction between producer and consumer
    * makes the consumer start on the rows the producer wrote last, which are still in the 126 MB L2. */
   int32_t reverse;
+  /* per source: 1, or 2 = the source is [batch, 2H, 2W, C] and is sampled with stride 2, i.e. a 3x3 stride-2 pad-1
+   * convolution (Downsample2D, sd/diffusers/src/diffusers/models/downsampling.py) through TMA elementStrides. */
+  int32_t a_stride[3];
 } b200ns_gemm_desc;
 int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d);
 
@@ -220,6 +223,14 @@ typedef struct {
   int32_t v_col0;
   int32_t head_dim;          /* 64 (default when 0) or 256 (one head, L <= 256: DDPM++, networks.py:263) */
   int32_t reverse;           /* walk direction, see b200ns_gemm_desc.reverse */
+  /* --- SD-1.5 UNet (attention_processor.py AttnProcessor2_0): head_dim may be 128 / 192 = the true head dimension
+   * (80 / 160; 40 -> 64) zero-padded by the projection weights; `scale` = true_head_dim^-0.5 (0 = head_dim^-0.5).
+   * Cross-attention: K/V come from `kv` [kv_batch*kv_rows, ld_kv] (K at k_col0, V at v_col0, per head head*head_dim);
+   * sample b attends context b / kv_div; each context has kv_rows rows (multiple of 128) of which the first
+   * kv_len are tokens (the rest must be finite, e.g. zero: they are masked to -inf). */
+  float scale;
+  const void* kv;
+  int32_t ld_kv, kv_batch, kv_rows, kv_len, kv_div;
 } b200ns_attn_desc;
 int b200ns_plan_add_attention(b200ns_plan* p, const b200ns_attn_desc* d);
 
@@ -264,6 +275,32 @@ int b200ns_plan_add_pool_attention(b200ns_plan* p, const float* qkv0, const void
 /* scores[r] = softmax(logits[r,:K])[target[r]]                        edm/scorers.py:163-172 */
 int b200ns_plan_add_softmax_gather(b200ns_plan* p, const float* logits, const int64_t* target, float* scores,
                                    int32_t rows, int32_t K);
+
+/* ------------------------------------------------------------------ SD backend (BASELINE.json config 5)
+ * Leaves of the SD-1.5-shaped UNet2DConditionModel that are not GEMM / GroupNorm / attention, as plan ops. */
+/* nn.LayerNorm over the channels of a bf16 token tensor [rows, C] (attention.py BasicTransformerBlock norm1-3). */
+int b200ns_plan_add_layernorm(b200ns_plan* p, const void* x, const float* gamma, const float* beta, void* out, int64_t rows,
+                              int32_t C, float eps);
+/* GEGLU (activations.py:117-123): in bf16 [rows, 2F] = [hidden | gate] -> out bf16 [rows, F] = hidden * gelu_erf(gate). */
+int b200ns_plan_add_geglu(b200ns_plan* p, const void* in, void* out, int64_t rows, int32_t F);
+/* F.interpolate(scale_factor=2, mode="nearest") on bf16 NHWC (upsampling.py Upsample2D.forward). */
+int b200ns_plan_add_upsample2x(b200ns_plan* p, const void* in, void* out, int32_t batch, int32_t H, int32_t W, int32_t C);
+
+/* Classifier-free guidance (pipeline_stable_diffusion.py:1073-1075) + the reference's DDIM step with supplied variance
+ * noise (scheduling_ddim.py:398-460) for R candidate rows; row r descends from parent r / per_parent.
+ *   eps = eu + g*(et-eu); x0 = (sample - sqrt(1-a_t) eps)/sqrt(a_t); prev = sqrt(a_prev) x0 + dir_coef eps + std noise
+ * eps_u/eps_t: UNet output fp32 NHWC [P,H,W,C]; sample fp32 NCHW [P,C,H,W]; noise fp32 NCHW [R,...] or NULL.
+ * prev: fp32 NCHW [R,...]; net_in (optional): the next UNet input, both CFG halves ([2R,...]). fp32, bit-exact vs torch. */
+int b200ns_ddim_cfg_step(const float* eps_u, const float* eps_t, const float* sample, const float* noise, float* prev,
+                         float* net_in, int64_t R, int32_t per_parent, int32_t C, int32_t HW, float guidance,
+                         float sqrt_beta_t, float sqrt_alpha_t, float sqrt_alpha_prev, float dir_coef, float std_dev,
+                         void* stream);
+/* Guided eps of the second UNet call -> pred_original_sample of each candidate (scheduling_ddim.py:409) -> uint8
+ * quantisation (pipeline...:1115) -> score = mean(u8/255) over (C,H,W) (sd/scorers.py:66-67, non-RGB branch).
+ * pred_x0 (optional) fp32 NCHW [R,...]; sums (optional) int32 [R] = exact integer sum of the uint8 image. */
+int b200ns_ddim_x0_score(const float* eps_u, const float* eps_t, const float* cand, float* pred_x0, int32_t* sums,
+                         float* scores, int64_t R, int32_t C, int32_t HW, float guidance, float sqrt_beta_t,
+                         float sqrt_alpha_t, void* stream);
 
 #ifdef __cplusplus
 }

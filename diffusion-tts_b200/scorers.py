@@ -33,6 +33,7 @@ class BrightnessScorer(Scorer):
     fp32 pipeline by at most 1 ulp; identical images always score identically (exact ties)."""
 
     fused_sums = True      # tells the search loop it can pass heun_post's channel sums directly
+    latent_fused = True    # SD beam: the 4-channel plain-mean branch is fused into ddim_x0_score_kernel
 
     def __init__(self, dtype=torch.float32, device='cuda'):
         super().__init__(dtype)

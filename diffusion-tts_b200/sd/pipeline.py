@@ -1,0 +1,74 @@
+"""Host-side mirror of the reference SD entry point for the beam step (BASELINE.json config 5).
+
+The reference drives the SD backend as
+    result, score = pipe(prompt=..., num_inference_steps=50, score_function=scorer, method=method, params=MASTER_PARAMS)
+(main.py:135-141; StableDiffusionPipeline.__call__, pipeline_stable_diffusion.py:785-816, returns `(out, score)` :1485).
+`B200LatentBeamPipeline.__call__` keeps that call shape for `method="beam"` and runs the search on the B200 engine
+(`sd_beam_search`).  What is deliberately different, all forced by config 5 / the offline setting:
+  * scoring happens in latent space on the Tweedie x0 (config 5: "brightness scorer on Tweedie x0"): `decode` is the
+    identity unless a decoder is injected (VAE decode in the loop is SURVEY.md 8 f1, not built);
+  * the CLIP text encoder's weights are unreachable offline: `encode_prompt` is injectable, and the default produces a
+    deterministic pseudo-embedding pair [uncond, cond] of the right shape from the prompt string;
+  * `out.images` is a visualisation of the first three latent channels (no VAE); `out.latents` is the real result.
+Methods other than beam raise NotImplementedError (8 f2: batched SD eps_greedy / zero_order is a "next" row).
+"""
+from __future__ import annotations
+
+import hashlib
+from types import SimpleNamespace
+from typing import Callable, Dict, Optional
+
+import torch
+
+from ..sd_unet import SDUNetEngine
+from .beam import DDIMTable, sd_beam_search
+
+
+def pseudo_prompt_embeddings(prompt: str, negative_prompt: str = '', tokens: int = 77, dim: int = 768) -> torch.Tensor:
+    """[2, tokens, dim] = [negative/uncond, prompt] stand-ins for CLIP last_hidden_state (layer-normed scale ~ 1)."""
+    out = []
+    for text in (negative_prompt, prompt):
+        seed = int.from_bytes(hashlib.sha256(text.encode()).digest()[:8], 'little') % (2 ** 63)
+        out.append(torch.randn(tokens, dim, generator=torch.Generator().manual_seed(seed)))
+    return torch.stack(out)
+
+
+class B200LatentBeamPipeline:
+    def __init__(self, unet_state_dict: Dict[str, torch.Tensor], device='cuda', encode_prompt: Optional[Callable] = None,
+                 decode: Optional[Callable] = None, shard=None):
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise RuntimeError('B200LatentBeamPipeline runs on a B200 only (no CPU fallback)')
+        self.unet = SDUNetEngine(unet_state_dict, device=self.device)
+        self.encode_prompt = encode_prompt or (lambda p, n='': pseudo_prompt_embeddings(p, n, dim=self.unet.cfg['cross_attention_dim']))
+        self.decode = decode
+        self.shard = shard
+
+    @torch.no_grad()
+    def __call__(self, prompt: str, num_inference_steps: int = 50, score_function: Optional[Callable] = None,
+                 method: str = 'beam', params: Optional[dict] = None, guidance_scale: float = 7.5,
+                 negative_prompt: str = '', latents: Optional[torch.Tensor] = None, height: int = 512, width: int = 512,
+                 generator: Optional[torch.Generator] = None):
+        if method != 'beam':
+            raise NotImplementedError(f"SD method '{method}' is not on the B200 hot path (only 'beam'; SURVEY.md 8 f2)")
+        params = params or {}
+        B, N = int(params['B']), int(params['N'])                          # pipeline_stable_diffusion.py:1046,1080
+        if height != width or height % 64:
+            raise ValueError('height == width, a multiple of 64, is required')
+        H = height // 8                                                   # vae_scale_factor = 8
+        if latents is None:                                               # prepare_latents: randn * init_noise_sigma (= 1)
+            latents = torch.randn(1, self.unet.cfg['in_channels'], H, H, generator=generator)
+        ctx = self.encode_prompt(prompt, negative_prompt)
+        table = DDIMTable(num_inference_steps)
+        fused = self.decode is None and (score_function is None or getattr(score_function, 'latent_fused', False))
+        if fused:
+            best, rec = sd_beam_search(self.unet, table, latents, ctx, B, N, guidance_scale=guidance_scale, shard=self.shard)
+        else:
+            decode = self.decode or (lambda x0: (x0 * 127.5 + 128).clip(0, 255).to(torch.uint8))    # :1115
+            scorer = lambda im: score_function(im, [prompt] * im.shape[0], torch.zeros(im.shape[0], device=im.device))
+            best, rec = sd_beam_search(self.unet, table, latents, ctx, B, N, guidance_scale=guidance_scale, decode=decode,
+                                       scorer=scorer, shard=self.shard)
+        from PIL import Image
+        vis = (best[0, :3] * 127.5 + 128).clip(0, 255).to(torch.uint8).permute(1, 2, 0).cpu().numpy()
+        out = SimpleNamespace(images=[Image.fromarray(vis, 'RGB')], latents=best, record=rec)
+        return out, float(rec.final_score)

@@ -8,8 +8,10 @@ Differences from the reference CLI, all forced by the offline B200 setting:
     the ImageNet-64 ADM pickle (main.py:157-158); without `--network` this front end builds a
     random-init ADM of the same architecture so that the path can run without network access.
   * `--classifier` (new, optional): a local `64x64_classifier.pt` for `--scorer imagenet` (random-init otherwise).
-  * `--backend sd`, `--scorer clip` and `--method mcts` are not part of
-    the B200 hot path yet and raise the same ValueError / NotImplementedError a wrong choice would.
+  * `--backend sd` runs `--method beam` only (BASELINE.json config 5): an SD-1.5-shaped UNet (random-init unless
+    `--network` names a state-dict `.pt`), latent-space scoring of the Tweedie x0, pseudo prompt embeddings (the CLIP
+    text encoder and the VAE are unreachable offline).  `--steps` (new) overrides the 50 DDIM steps.
+  * `--scorer clip` and `--method mcts` are not part of the B200 hot path and raise NotImplementedError / ValueError.
 """
 import argparse
 
@@ -42,6 +44,32 @@ def random_init_adm(seed=1234):
     return dict(state_dict=random_state_dict(adm_param_shapes(), seed), sigma_data=0.5)
 
 
+def main_sd(args):
+    """SD backend (reference main.py:111-146): `pipe(prompt, num_inference_steps=50, score_function, method, params)`."""
+    from diffusion_tts_b200.arch import random_state_dict, sd_unet_param_shapes
+    from diffusion_tts_b200.sd.pipeline import B200LatentBeamPipeline
+    if args.scorer == 'clip':
+        raise NotImplementedError('the CLIP scorer is not on the B200 hot path (SURVEY.md 8 f4)')
+    scorer = get_scorer('sd', args.scorer, args.device)
+    if args.network is not None:
+        sd = torch.load(args.network, map_location='cpu')
+    else:
+        print('[sd] no --network given: using a random-init SD-1.5-shaped UNet2DConditionModel (859.5M parameters)')
+        sd = random_state_dict(sd_unet_param_shapes(), 1234)
+    torch.manual_seed(args.seed)
+    pipe = B200LatentBeamPipeline(sd, device=args.device)
+    params = {'N': args.N, 'lambda': args.lambda_, 'eps': args.eps, 'K': args.K, 'B': args.B, 'S': args.S}
+    best_result, best_score = None, float('-inf')
+    for _ in range(params['N'] if args.method == 'rejection' else 1):
+        result, score = pipe(prompt=args.prompt, num_inference_steps=args.steps or 50, score_function=scorer,
+                             method=args.method, params=params)
+        if score > best_score:
+            best_result, best_score = result, score
+    outname = args.output or f"sd_{args.method}_{args.scorer}.png"
+    best_result.images[0].save(outname)
+    print(f"\n[SD] Saved: {outname}\nBest score: {best_score}\n")
+
+
 def main():
     parser = argparse.ArgumentParser(description='Unified Diffusion Image Generator (EDM/SD) -- B200 path',
                                      formatter_class=argparse.ArgumentDefaultsHelpFormatter)
@@ -62,6 +90,7 @@ def main():
     parser.add_argument('--device', type=str, default='cuda', help='Device')
     parser.add_argument('--network', type=str, default=None, help='Local network pickle / .pt bundle')
     parser.add_argument('--classifier', type=str, default=None, help='Local 64x64_classifier.pt for --scorer imagenet')
+    parser.add_argument('--steps', type=int, default=None, help='Override the number of sampler steps (sd: 50)')
     args = parser.parse_args()
 
     if args.backend == 'sd' and args.scorer == 'imagenet':
@@ -69,7 +98,7 @@ def main():
     if args.backend == 'edm' and args.scorer == 'clip':
         raise ValueError('clip scorer is only available for sd backend')
     if args.backend == 'sd':
-        raise NotImplementedError('the SD backend is not on the B200 hot path yet (SURVEY.md 8: a16, f1-f2)')
+        return main_sd(args)
 
     scorer = get_scorer('edm', args.scorer, args.device, args.classifier)
     num_images = 1

@@ -214,6 +214,8 @@ def beam_search(unet: Callable, tab: DDIMTable, latents: torch.Tensor, ctx_pair:
             record.setdefault('scores', []).append(torch.tensor(scores))
             record.setdefault('best', []).append(torch.tensor(order[:B]))
         beams = [cands[k] for k in order[:B]]
+        if record is not None:
+            record.setdefault('beams', []).append(torch.cat(beams))
     best, best_score = beams[0], float('-inf')                                     # :1153-1166
     for cand in beams:
         s = float(score_fn(cand))

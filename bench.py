@@ -214,7 +214,9 @@ def run_b200(args):
     _, xe, _ = timed(host, order[:args.warmup], x0, read_back)
     ms_e2e, xe, _ = timed(host, order[args.warmup:], xe, read_back)
     e2e = N * args.steps / (ms_e2e / 1e3)
-    h2d = sum(host[k].numel() * 8 for k in (f'pivot_{order[-1]}', order[-1]))
+    # every rank uploads the step's pivot noise and ITS slice of the N candidate directions (fp64)
+    h2d_rank = host[f'pivot_{order[-1]}'].numel() * 8 + host[order[-1]].numel() * 8 // world
+    h2d = h2d_rank * world
     d2h = 8 + 4 + x0.numel() * 8
 
     # ---- dominant kernel (tcgen05 implicit-GEMM conv) roofline: per-op CUDA-event timing of one NFE at B = N/GPU
@@ -255,7 +257,8 @@ def run_b200(args):
         'config': {'workload': workload_name(N), 'N_per_gpu': N_PER_GPU, 'K': 1, 'num_steps': NUM_STEPS,
                    'l2': 'not flushed: per-step working set (0.6 GB bf16 weights + >2 GB activations) exceeds the 126 MB L2',
                    'sampler_state': 'fp64', 'unet': 'bf16 storage, fp32 accumulate/GroupNorm/softmax'},
-        'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+        'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h * world,
+                'h2d_bytes_per_step_per_rank': h2d_rank, 'd2h_bytes_per_step_per_rank': d2h,
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': launches,
         'clocks': clk,

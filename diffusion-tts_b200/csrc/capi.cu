@@ -343,13 +343,23 @@ int run_op(const Op& op, cudaStream_t st) {
                                                         reinterpret_cast<float*>(op.misc.p2), op.misc.i1);
       CK_LAUNCH("softmax_gather_kernel");
       return 0;
-    case OP_LAYERNORM:
-      layernorm_kernel<<<static_cast<unsigned>((op.misc.n + 7) / 8), 256, 0, st>>>(
-          reinterpret_cast<const __nv_bfloat16*>(op.misc.p0), reinterpret_cast<const float*>(op.misc.p1),
-          reinterpret_cast<const float*>(op.misc.p3), reinterpret_cast<__nv_bfloat16*>(op.misc.p2), op.misc.n, op.misc.i0,
-          op.misc.f0);
+    case OP_LAYERNORM: {
+      const __nv_bfloat16* lx = reinterpret_cast<const __nv_bfloat16*>(op.misc.p0);
+      const float* lg = reinterpret_cast<const float*>(op.misc.p1);
+      const float* lb = reinterpret_cast<const float*>(op.misc.p3);
+      __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(op.misc.p2);
+      const int nchunk = op.misc.i0 / 8;
+      const int64_t rows = op.misc.n;
+      if (nchunk <= 40) {               // 4 rows per warp, 32 per CTA
+        layernorm_kernel<8, 5><<<static_cast<unsigned>((rows + 31) / 32), 256, 0, st>>>(lx, lg, lb, lo, rows, op.misc.i0, op.misc.f0);
+      } else if (nchunk <= 80) {
+        layernorm_kernel<16, 5><<<static_cast<unsigned>((rows + 15) / 16), 256, 0, st>>>(lx, lg, lb, lo, rows, op.misc.i0, op.misc.f0);
+      } else {
+        layernorm_kernel<32, 8><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(lx, lg, lb, lo, rows, op.misc.i0, op.misc.f0);
+      }
       CK_LAUNCH("layernorm_kernel");
       return 0;
+    }
     case OP_GEGLU:
       geglu_kernel<<<grid_for(op.misc.n * (op.misc.i0 / 8), 256, 148 * 32), 256, 0, st>>>(
           reinterpret_cast<const __nv_bfloat16*>(op.misc.p0), reinterpret_cast<__nv_bfloat16*>(op.misc.p2), op.misc.n, op.misc.i0);
@@ -592,6 +602,10 @@ int b200ns_plan_set_lane(b200ns_plan* p, int lane) {
   return 0;
 }
 int b200ns_plan_size(const b200ns_plan* p) { return static_cast<int>(p->ops.size()); }
+int b200ns_plan_gemm_cols(const b200ns_plan* p, int op) {
+  if (op < 0 || op >= static_cast<int>(p->ops.size()) || p->ops[op].kind != OP_GEMM) return -1;
+  return p->ops[op].gemm.args.N;
+}
 
 int b200ns_plan_run_range(b200ns_plan* p, int first, int last, void* stream) {
   if (first < 0 || last > static_cast<int>(p->ops.size()) || first > last) return fail("plan_run_range: bad range");
@@ -612,7 +626,67 @@ int b200ns_plan_run(b200ns_plan* p, void* stream) {
   return b200ns_plan_run_range(p, 0, static_cast<int>(p->ops.size()), stream);
 }
 
+static int g_force_bn = 0;
+void b200ns_debug_force_tile_width(int bn) { g_force_bn = bn; }
+
+// Relative cost of one K block of a 128 x c tile, MEASURED on B200 (tools/profile_gemm_bn.py, gpurun_out/gemm_bn.log:
+// 3x3 convs at 64x64..8x8, batch 64): widths 192 and 256 run at the same rate per column (the tensor pipe needs ~2c
+// cycles), 128 at ~0.78 of it and 64 at ~0.43 (the shared-memory operand feed, ~128 + c, and the per-tile epilogue).
+static long gemm_per_kb(int c) { return c >= 192 ? 2 * c : (c == 128 ? 330 : 300); }
+
+static int add_gemm_part(b200ns_plan* p, const b200ns_gemm_desc* d, int BN_forced, int ld_stats);
+
 int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d) {
+  // Tile width.  One launch uses one width c (a template parameter) and needs c | columns, so a weight matrix whose
+  // padded width has no wide divisor (SD-1.5: 320 = 5 x 64) is covered by up to TWO launches over column slices
+  // [0, n1*c1) and [n1*c1, Npad) of widths c1 != c2 (320 = 192 + 128, 640 = 2*192 + 256): pointers are shifted, the A operand is shared.
+  // Cost model per part: (waves over the SMs) x (cycles per K block of one tile); an extra launch costs one more tail.
+  if (d->out_fp32 || d->Npad % 64) return add_gemm_part(p, d, 0, d->N);
+  if (g_force_bn > 0 && d->Npad % g_force_bn == 0) return add_gemm_part(p, d, g_force_bn, d->N);
+  const int m_tiles = (d->batch * d->H * d->W + 127) / 128;
+  const int cands[4] = {256, 192, 128, 64};
+  long best = -1;
+  int bc1 = 0, bn1 = 0, bc2 = 0;
+  auto waves = [&](long tiles) { return (tiles + num_sms() - 1) / num_sms(); };
+  for (int c1 : cands) {
+    for (int n1 = 1; n1 * c1 <= d->Npad; ++n1) {
+      const int rest = d->Npad - n1 * c1;
+      if (rest == 0) {
+        const long cost = waves(static_cast<long>(m_tiles) * n1) * gemm_per_kb(c1);
+        if (best < 0 || cost < best) best = cost, bc1 = c1, bn1 = n1, bc2 = 0;
+        continue;
+      }
+      for (int c2 : cands) {
+        if (c2 == c1 || rest % c2) continue;
+        const long cost = waves(static_cast<long>(m_tiles) * n1) * gemm_per_kb(c1) +
+                          waves(static_cast<long>(m_tiles) * (rest / c2)) * gemm_per_kb(c2) + gemm_per_kb(c2) / 2;
+        if (best < 0 || cost < best) best = cost, bc1 = c1, bn1 = n1, bc2 = c2;
+      }
+    }
+  }
+  if (bc2 == 0) return add_gemm_part(p, d, bc1, d->N);
+  const int split = bn1 * bc1;                      // first column of the second slice
+  if (split >= d->N) {                              // the second slice would be padding only
+    b200ns_gemm_desc d1 = *d;
+    d1.Npad = split;
+    return add_gemm_part(p, &d1, bc1, d->N);
+  }
+  b200ns_gemm_desc d1 = *d, d2 = *d;
+  d1.N = split;
+  d1.Npad = split;
+  d2.N = d->N - split;
+  d2.Npad = d->Npad - split;
+  d2.w_ptr = static_cast<const char*>(d->w_ptr) + static_cast<size_t>(split) * d->Ktot * 2;
+  if (d->bias) d2.bias = d->bias + split;
+  if (d->residual) d2.residual = static_cast<const char*>(d->residual) + static_cast<size_t>(split) * 2;
+  d2.out = static_cast<char*>(d->out) + static_cast<size_t>(split) * 2;
+  if (d->gn_stats) d2.gn_stats = d->gn_stats + static_cast<size_t>(split) * 2;
+  const int rc = add_gemm_part(p, &d1, bc1, d->N);
+  if (rc) return rc;
+  return add_gemm_part(p, &d2, bc2, d->N);
+}
+
+static int add_gemm_part(b200ns_plan* p, const b200ns_gemm_desc* d, int BN_forced, int ld_stats) {
   Op op;
   op.kind = OP_GEMM;
   GemmOp& g = op.gemm;
@@ -632,20 +706,16 @@ int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d) {
   a.N = d->N;
   a.m_tiles = (a.M + 127) / 128;
   if (d->Npad % 16) return fail("gemm: Npad must be a multiple of 16");
-  // tile width: among the widths dividing Npad, minimise (waves over the SMs) x (cycles per K block of one tile);
-  // per K block the tensor pipe needs ~2*BN cycles and the shared-memory operand feed ~(128 + BN).
-  int BN = 0;
+  int BN = BN_forced;
   if (d->out_fp32) {
     BN = 16;
-  } else {
+  } else if (!BN) {
     const int cands[4] = {256, 192, 128, 64};
     long best = -1;
     for (int c : cands) {
       if (d->Npad % c) continue;
       const long tiles = static_cast<long>(a.m_tiles) * (d->Npad / c);
-      const long waves = (tiles + num_sms() - 1) / num_sms();
-      const long per_kb = 2 * c > 128 + c ? 2 * c : 128 + c;
-      const long cost = waves * per_kb;
+      const long cost = ((tiles + num_sms() - 1) / num_sms()) * gemm_per_kb(c);
       if (best < 0 || cost < best) {
         best = cost;
         BN = c;
@@ -677,6 +747,7 @@ int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d) {
   a.ld_out = d->ld_out;
   a.out_fp32 = d->out_fp32;
   a.gn_stats = reinterpret_cast<float2*>(d->gn_stats);
+  a.ld_stats = ld_stats;
   a.reverse = d->reverse;
   if (d->gn_stats != nullptr && (BN == 16 || a.M % 64)) return fail("gemm: gn_stats needs bf16 output, N tiles >= 64 and M % 64 == 0");
   if (!d->out_fp32 && (d->ld_out % 8)) return fail("gemm: ld_out must be a multiple of 8 for bf16 output");

@@ -48,7 +48,8 @@ struct GemmArgs {
   void* out;
   int ld_out;
   int out_fp32;
-  float2* gn_stats;              // [M/64, N] (sum, sum of squares) per 64-row half tile, or null
+  float2* gn_stats;              // [M/64, ld_stats] (sum, sum of squares) per 64-row half tile, or null
+  int ld_stats;                  // row pitch of gn_stats in channels (= the full N when this launch covers a column slice)
   int src_stride[3];             // 1, or 2: the source is sampled with stride 2 (3x3 stride-2 pad-1 conv: Downsample2D)
   int reverse;                   // walk the tiles last-to-first (start on what the producer of A wrote last: L2 hits)
 };
@@ -348,9 +349,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const int n = nt * BN + j * 64 + static_cast<int>(unit * 8 + cp * 2);
             if (hrow * 64 < a.M && n + 1 < a.N) {
               const float4 o4 = rg == 0 ? make_float4(s0[0], q0[0], s1[0], q1[0]) : make_float4(s0[1], q0[1], s1[1], q1[1]);
-              *reinterpret_cast<float4*>(a.gn_stats + static_cast<size_t>(hrow) * a.N + n) = o4;
+              *reinterpret_cast<float4*>(a.gn_stats + static_cast<size_t>(hrow) * a.ld_stats + n) = o4;
             } else if (hrow * 64 < a.M && n < a.N) {
-              a.gn_stats[static_cast<size_t>(hrow) * a.N + n] = rg == 0 ? make_float2(s0[0], q0[0]) : make_float2(s0[1], q0[1]);
+              a.gn_stats[static_cast<size_t>(hrow) * a.ld_stats + n] = rg == 0 ? make_float2(s0[0], q0[0]) : make_float2(s0[1], q0[1]);
             }
           }
         }

@@ -12,33 +12,44 @@
 
 namespace b200 {
 
-// one warp per token row; C multiple of 8; bf16 in/out, fp32 statistics (two-pass over registers)
+// LPR lanes per token row (a warp normalises 32/LPR consecutive rows at once), each lane holding up to CPL 16-byte
+// chunks of its row in registers: all loads of a warp are issued before the first reduction, so a C=320 row (40 chunks,
+// LPR=8, 5 chunks per lane) keeps 4 rows x 640 B in flight per warp instead of one.  C multiple of 8, C/8 <= LPR*CPL;
+// bf16 in/out, fp32 statistics (two-pass over the registers, fixed shuffle order => batch-position invariant).
+template <int LPR, int CPL>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                                                         int64_t rows, int C, float eps) {
+  constexpr int RPW = 32 / LPR;                   // rows per warp
   const int lane = threadIdx.x & 31;
-  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const __nv_bfloat16* xr = x + row * C;
-  const int nchunk = C >> 3;                      // 16-byte chunks per row (<= 256 => <= 8 per lane)
-  float v[8][8];
+  const int sub = lane % LPR;
+  const int64_t warp = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t row = warp * RPW + lane / LPR;
+  const bool live = row < rows;
+  const __nv_bfloat16* xr = x + (live ? row : 0) * C;
+  const int nchunk = C >> 3;
+  float v[CPL][8];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int ch = lane + i * 32;
+  for (int i = 0; i < CPL; ++i) {
+    const int ch = sub + i * LPR;
+    if (ch < nchunk) load8(xr + ch * 8, v[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    const int ch = sub + i * LPR;
     if (ch < nchunk) {
-      load8(xr + ch * 8, v[i]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += v[i][j];
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mean = s / static_cast<float>(C);
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int ch = lane + i * 32;
+  for (int i = 0; i < CPL; ++i) {
+    const int ch = sub + i * LPR;
     if (ch < nchunk) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -48,15 +59,20 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = rsqrtf(q / static_cast<float>(C) + eps);
+  if (!live) return;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int ch = lane + i * 32;
+  for (int i = 0; i < CPL; ++i) {
+    const int ch = sub + i * LPR;
     if (ch < nchunk) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + ch * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + ch * 8) + 1);
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       float o8[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o8[j] = (v[i][j] - mean) * rstd * __ldg(gamma + ch * 8 + j) + __ldg(beta + ch * 8 + j);
+      for (int j = 0; j < 8; ++j) o8[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
       store8(out + row * C + ch * 8, o8);
     }
   }

@@ -25,7 +25,7 @@ from typing import Any, Dict, List, Optional
 import numpy as np
 import torch
 
-from .. import ops
+from .. import ops, philox
 from ..denoiser import B200Denoiser, HeunStepper, StepTable, load_network
 from ..scorers import BrightnessScorer, Scorer
 
@@ -88,6 +88,18 @@ def _score_rows(scorer, stepper: HeunStepper, x_cur, eps, i, labels_rows, C, HW,
     return torch.as_tensor(s).to(device=u8.device, dtype=torch.float32).reshape(-1).contiguous(), x_next
 
 
+def _gather_winner(rows: torch.Tensor, idx: torch.Tensor, lo: int, hi: int, shard: 'Shard') -> torch.Tensor:
+    """rows [hi-lo, b, ...] fp64 = this rank's slice; idx [b] global winner indices -> [b, ...] on every rank."""
+    if shard.world == 1:
+        return ops.gather_rows(rows, (idx - lo).contiguous())
+    import torch.distributed as dist
+    owned = (idx >= lo) & (idx < hi)
+    out = ops.gather_rows(rows, (idx - lo).clamp(0, hi - lo - 1).contiguous())
+    out = out * owned.to(torch.float64).view(-1, *([1] * (out.dim() - 1)))
+    dist.all_reduce(out, op=dist.ReduceOp.SUM, group=shard.group)
+    return out
+
+
 def _scale_table(num_steps: int, K: int, N: int, lam: float) -> torch.Tensor:
     """fp32 scales of edm/main.py:776-779 for every (i,k,n): `ones * scale_seed * lambda_param`
     (fp32, rounded after each product); hash() is this process's salted str hash, as in the reference."""
@@ -102,7 +114,7 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
                       norm_mode: str = 'kernel', scale_table: Optional[torch.Tensor] = None,
                       teacher_x: Optional[List[torch.Tensor]] = None, step_indices: Optional[List[int]] = None,
                       x_init: Optional[torch.Tensor] = None, on_step=None,
-                      commit: str = 'reuse') -> (torch.Tensor, SearchRecord):
+                      commit: str = 'reuse', mirror_rng: bool = True) -> (torch.Tensor, SearchRecord):
     """ZERO_ORDER == EPS_GREEDY branch (edm/main.py:714-860).
 
     Extras over the reference (all optional): `shard` (candidate sharding over ranks), `record`,
@@ -139,6 +151,7 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
         scales = scales.contiguous()
         dist.broadcast(scales, src=dist.get_global_rank(shard.group, 0) if shard.group is not None else 0, group=shard.group)
     labels_rows = class_labels.repeat(hi - lo, 1) if class_labels is not None else None
+    use_mirror = mirror_rng and philox.mirror_ok(device)
     pre = precomputed_noise
     if pre is not None and 'pivot' in pre:                                # :724-727 (value unused, RNG untouched)
         pass
@@ -157,47 +170,60 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
             bulk = (pre is not None and i in pre and k < pre[i].shape[1] and N <= pre[i].shape[2] and
                     (eps_p <= 0 or all(f'fresh_{i}_{k}_{n}' in pre for n in range(N))))
             dirs, fresh, perturb = [], [], []
-            for n in range(N):
-                p_t = torch.rand(1, device=device) < (1 - eps_p)                  # :751
-                perturb.append(p_t)
-                if bulk:
-                    continue
-                has_dir = pre is not None and i in pre and k < pre[i].shape[1] and n < pre[i].shape[2]
-                fkey = f'fresh_{i}_{k}_{n}'
-                has_fresh = pre is not None and fkey in pre
-                z_dir = pre[i][:, k, n].reshape(pivot.shape) if has_dir else None          # :755-759
-                z_fresh = pre[fkey] if has_fresh else None                                 # :791-792
-                if not has_dir and not has_fresh:
-                    z_dir = z_fresh = torch.randn_like(pivot)             # :767 / :795: one draw either way
-                elif not (has_dir and has_fresh):
-                    branch = True if eps_p <= 0 else (False if eps_p >= 1 else bool(p_t))
-                    if branch and not has_dir:
-                        z_dir = torch.randn_like(pivot)
-                    if not branch and not has_fresh:
-                        z_fresh = torch.randn_like(x_cur)
-                    z_dir = z_dir if z_dir is not None else z_fresh
-                    z_fresh = z_fresh if z_fresh is not None else z_dir
-                dirs.append(z_dir)
-                fresh.append(z_fresh)
-            if bulk:      # every direction comes from one precomputed tensor: a single (async) transfer
-                Z = pre[i][:, k, :N].to(device=device, dtype=torch.float64, non_blocking=True).transpose(0, 1).reshape(
-                    N * b, *pivot.shape[1:]).contiguous()
+            if bulk and use_mirror:
+                # the N `torch.rand(1)` draws of :751 evaluated on the host from the generator's (seed, offset) --
+                # same values, same final RNG state, no kernels in the stream (philox.py)
+                perturb_host = philox.rand1_sequence(device, N) < np.float32(1 - eps_p)
+            else:
+                perturb_host = None
+                for n in range(N):
+                    p_t = torch.rand(1, device=device) < (1 - eps_p)                  # :751
+                    perturb.append(p_t)
+                    if bulk:
+                        continue
+                    has_dir = pre is not None and i in pre and k < pre[i].shape[1] and n < pre[i].shape[2]
+                    fkey = f'fresh_{i}_{k}_{n}'
+                    has_fresh = pre is not None and fkey in pre
+                    z_dir = pre[i][:, k, n].reshape(pivot.shape) if has_dir else None          # :755-759
+                    z_fresh = pre[fkey] if has_fresh else None                                 # :791-792
+                    if not has_dir and not has_fresh:
+                        z_dir = z_fresh = torch.randn_like(pivot)             # :767 / :795: one draw either way
+                    elif not (has_dir and has_fresh):
+                        branch = True if eps_p <= 0 else (False if eps_p >= 1 else bool(p_t))
+                        if branch and not has_dir:
+                            z_dir = torch.randn_like(pivot)
+                        if not branch and not has_fresh:
+                            z_fresh = torch.randn_like(x_cur)
+                        z_dir = z_dir if z_dir is not None else z_fresh
+                        z_fresh = z_fresh if z_fresh is not None else z_dir
+                    dirs.append(z_dir)
+                    fresh.append(z_fresh)
+            # ---- only this rank's candidates [lo, hi) are materialised (1/G of the transfers and of the fp64 passes)
+            nl = hi - lo
+            if bulk:      # every direction comes from one precomputed tensor: a single (async) transfer of the slice
+                Z = pre[i][:, k, lo:hi].to(device=device, dtype=torch.float64, non_blocking=True).transpose(0, 1).reshape(
+                    nl * b, *pivot.shape[1:]).contiguous()
                 ZF = Z if eps_p <= 0 else torch.stack([pre[f'fresh_{i}_{k}_{n}'].to(device=device, dtype=torch.float64)
-                                                       for n in range(N)]).reshape(N * b, *pivot.shape[1:]).contiguous()
+                                                       for n in range(lo, hi)]).reshape(nl * b, *pivot.shape[1:]).contiguous()
             else:
                 as64 = lambda ts: torch.stack([t.to(device=device, dtype=torch.float64) for t in ts]).reshape(
-                    N * b, *pivot.shape[1:]).contiguous()
-                Z = as64(dirs)
-                ZF = Z if all(f is d for f, d in zip(fresh, dirs)) else as64(fresh)
-            fresh_mask = (~torch.cat(perturb)).to(torch.uint8).repeat_interleave(b).contiguous()
+                    nl * b, *pivot.shape[1:]).contiguous()
+                Z = as64(dirs[lo:hi])
+                ZF = Z if all(f is d for f, d in zip(fresh[lo:hi], dirs[lo:hi])) else as64(fresh[lo:hi])
+            if perturb_host is not None:
+                if perturb_host[lo:hi].all():
+                    fresh_mask = torch.zeros(nl * b, dtype=torch.uint8, device=device)
+                else:
+                    fresh_mask = torch.from_numpy((~perturb_host[lo:hi]).astype(np.uint8)).to(device).repeat_interleave(b).contiguous()
+            else:
+                fresh_mask = (~torch.cat(perturb[lo:hi])).to(torch.uint8).repeat_interleave(b).contiguous()
             if norm_mode == 'torch':                                      # strict: the reference's own call (:764)
-                norms = torch.cat([torch.norm(z, p=2, dim=tuple(range(1, z.dim()))) for z in Z.reshape(N, b, *pivot.shape[1:])]).to(torch.float64)
+                norms = torch.cat([torch.norm(z, p=2, dim=tuple(range(1, z.dim()))) for z in Z.reshape(nl, b, *pivot.shape[1:])]).to(torch.float64)
             else:
                 norms = ops.direction_norms(Z)
-            sc = scales[i, k].repeat_interleave(b).contiguous()
-            cands = ops.make_candidates(pivot, Z, norms, sc, fresh_mask, ZF)      # [N*b, C, H, W]
+            sc = scales[i, k, lo:hi].repeat_interleave(b).contiguous()
+            local = ops.make_candidates(pivot, Z, norms, sc, fresh_mask, ZF)      # [(hi-lo)*b, C, H, W]
             # ---- evaluate this rank's slice: 2 NFE + Tweedie x0 + score (:809-838)
-            local = cands[lo * b:hi * b]
             want_x = commit == 'reuse' and k == K - 1
             scores, x_cands = _score_rows(params.scorer, stepper, x_cur, local, i, labels_rows, C, HW, want_x)
             scores = scores.reshape(hi - lo, b)
@@ -210,21 +236,17 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
                 idx = 0xFFFFFFFF - (key & 0xFFFFFFFF)
             else:
                 idx = idx + lo
-            pivot = ops.gather_rows(cands.reshape(N, b, *cands.shape[1:]), idx.contiguous())      # :848-857
+            # ---- new pivot = the winning candidate (:848-857); it lives on its owner's GPU only: the other ranks
+            # contribute zeros to an all_reduce(SUM) (x + 0 is exact), 96 KiB per image over NVLink -- and only when
+            # somebody reads it (another local-search round, a recomputed commit, a trace)
+            if k < K - 1 or commit != 'reuse' or record:
+                pivot = _gather_winner(local.reshape(hi - lo, b, *local.shape[1:]), idx, lo, hi, shard)
             if record:
                 rec.scores.append(scores)
                 rec.indices.append(idx)
         # ---- commit (:860)
         if commit == 'reuse' and K > 0:
-            xc = x_cands.reshape(hi - lo, b, *x_cands.shape[1:])
-            if shard.world > 1:       # only the owner of the winner contributes; x + 0 is exact
-                import torch.distributed as dist
-                owned = ((idx >= lo) & (idx < hi))
-                x_next = ops.gather_rows(xc, (idx - lo).clamp(0, hi - lo - 1).contiguous())
-                x_next = x_next * owned.to(torch.float64).view(b, *([1] * (x_next.dim() - 1)))
-                dist.all_reduce(x_next, op=dist.ReduceOp.SUM, group=shard.group)
-            else:
-                x_next = ops.gather_rows(xc, idx.contiguous())
+            x_next = _gather_winner(x_cands.reshape(hi - lo, b, *x_cands.shape[1:]), idx, lo, hi, shard)
         else:
             x_next, _, _ = stepper.step(x_cur, pivot, i, want_x_next=True)
         if record:

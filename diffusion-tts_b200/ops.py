@@ -288,10 +288,14 @@ class Plan:
         d.gn_stats = L.ptr(gn_stats)
         d.reverse = int(reverse)
         self._k(*a, w, bias, residual, out, gn_stats)
+        n_before = L.lib().b200ns_plan_size(self._h)
         L.check(L.lib().b200ns_plan_add_gemm(self._h, C.byref(d)), 'plan_add_gemm')
-        self.labels.append(label)
-        self.kinds.append('gemm')
-        self.flops.append(2.0 * B * H * W_ * N * (alg_k if alg_k else w.shape[1]))
+        n_after = L.lib().b200ns_plan_size(self._h)
+        for j in range(n_before, n_after):             # one launch, or two over column slices (e.g. 320 = 192 + 128)
+            cols = L.lib().b200ns_plan_gemm_cols(self._h, j)
+            self.labels.append(label if n_after - n_before == 1 else f'{label}[{cols}]')
+            self.kinds.append('gemm')
+            self.flops.append(2.0 * B * H * W_ * cols * (alg_k if alg_k else w.shape[1]))
 
     def add_gn_stats(self, x: Sequence[torch.Tensor], groups: int, partial: torch.Tensor, splits: int, *, pre_add=None,
                      b_emb=1, label='gn_stats'):

@@ -102,6 +102,9 @@ typedef struct b200ns_plan b200ns_plan;
 b200ns_plan* b200ns_plan_create(void);
 void b200ns_plan_destroy(b200ns_plan* p);
 int b200ns_plan_size(const b200ns_plan* p);
+/* Valid output columns of GEMM launch `op` (-1 if `op` is not a GEMM).  One b200ns_plan_add_gemm call may append two
+ * launches over column slices (see there), so callers that keep per-launch metadata ask how the columns were split. */
+int b200ns_plan_gemm_cols(const b200ns_plan* p, int op);
 int b200ns_plan_run(b200ns_plan* p, void* stream);
 /* Capture the plan once as a CUDA graph; later b200ns_plan_run calls launch the graph. */
 int b200ns_plan_instantiate_graph(b200ns_plan* p);
@@ -151,6 +154,9 @@ typedef struct {
   int32_t a_stride[3];
 } b200ns_gemm_desc;
 int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d);
+/* Tuning aid: force the N tile width (64/128/192/256; 0 = cost model) of subsequently added bf16 GEMMs whose padded
+ * width it divides.  Used by tools/profile_gemm_bn.py to measure the widths against each other. */
+void b200ns_debug_force_tile_width(int bn);
 
 /* GroupNorm statistics (networks.py:104-106): per-(sample, group) partial sums of x and x^2
  * over up to two concatenated sources, written as fp64 [batch, splits, groups, 2].

@@ -142,3 +142,18 @@ def test_sharded_argmax_gloo_world2():
     for rank, idx, ref in res:
         assert idx == ref, (rank, idx, ref)
         assert idx[1] == 2 and idx[2] == 0
+
+
+def test_philox4x32_known_answers():
+    """Random123 known-answer vectors for Philox4x32-10 (the generator behind torch's CUDA RNG), and the host mirror of
+    `torch.rand(1, device='cuda')` after `torch.manual_seed(0)` (first draw 0.3990..)."""
+    import numpy as np
+    from diffusion_tts_b200.philox import philox4x32_10, rand1_values
+    kat = lambda c, k: philox4x32_10(np.array([c], dtype=np.uint32), np.array([k], dtype=np.uint32))[0].tolist()
+    assert kat([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert kat([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert kat([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    v = rand1_values(0, 0, 4)
+    assert v.dtype == np.float32 and abs(float(v[0]) - 0.39904648) < 1e-7 and ((v >= 0) & (v < 1)).all()
+    assert np.array_equal(rand1_values(0, 8, 2), v[2:])            # offset advances by 4 per call

@@ -200,3 +200,52 @@ def test_generate_image_grid_naive_and_rejection(pkg):
     last = rec_b.scores[-1].cpu()
     order = rec_b.indices[-1].cpu()
     assert (last.gather(1, order)[:, 0] == last.max(dim=1).values).all()
+
+
+def test_philox_mirror_matches_torch_rand():
+    """philox.rand1_sequence == N consecutive torch.rand(1, device='cuda') calls: same values, same generator offset
+    afterwards (edm/main.py:751 draws one per candidate)."""
+    import numpy as np
+    from diffusion_tts_b200 import philox
+    for seed in (0, 123456789, 2 ** 40 + 7):
+        torch.manual_seed(seed)
+        torch.randn(1000, device='cuda')                      # move the offset away from 0
+        gen = torch.cuda.default_generators[torch.cuda.current_device()]
+        st = gen.get_state()
+        want = torch.cat([torch.rand(1, device='cuda') for _ in range(64)]).cpu().numpy()
+        end = gen.get_offset()
+        after_want = torch.randn(4, device='cuda').cpu()
+        gen.set_state(st)
+        got = philox.rand1_sequence('cuda', 64)
+        assert np.array_equal(want, got)
+        assert gen.get_offset() == end
+        assert torch.equal(torch.randn(4, device='cuda').cpu(), after_want)      # the stream continues identically
+    assert philox.mirror_ok('cuda')
+
+
+def test_search_with_mirrored_rng_is_identical(pkg):
+    """eps = 0.4 with precomputed directions AND fresh noises: the host-mirrored Bernoulli draws pick the same
+    perturb/fresh branches, indices and states as the per-candidate torch.rand(1) calls, and leave the RNG aligned."""
+    den, em, sc = pkg
+    g = load_golden('search_eps_greedy_tiny.pt')
+    onet, spec, sd = oracle_net(g['cfg'], g['seed'])
+    latents, labels, pre = search_inputs(g)
+    net = den.B200Denoiser(sd, device='cuda')
+    table = den.StepTable(net, 'cuda', g['num_steps'], **g['sampler_kw'])
+    params = em.SamplingParams(N=g['N'], K=g['K'], eps=0.4, lambda_param=g['lambda_param'], scorer=sc.BrightnessScorer())
+    noise = {k: v.cuda() for k, v in pre.items()}
+    gen = torch.Generator().manual_seed(77)
+    for i in range(g['num_steps']):
+        for k in range(g['K']):
+            for n in range(g['N']):
+                noise[f'fresh_{i}_{k}_{n}'] = torch.randn(latents.shape, generator=gen, dtype=torch.float64).cuda()
+    out = {}
+    for mirror in (True, False):
+        torch.manual_seed(5)
+        x, rec = em.eps_greedy_search(net, latents.cuda(), labels.cuda(), params, table, precomputed_noise=noise,
+                                      record=True, mirror_rng=mirror)
+        out[mirror] = (x.cpu(), [t.cpu() for t in rec.indices], [t.cpu() for t in rec.scores], torch.rand(3, device='cuda').cpu())
+    assert all(torch.equal(a, b) for a, b in zip(out[True][1], out[False][1]))
+    assert all(torch.equal(a, b) for a, b in zip(out[True][2], out[False][2]))
+    assert torch.equal(out[True][0], out[False][0])
+    assert torch.equal(out[True][3], out[False][3])

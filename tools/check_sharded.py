@@ -12,6 +12,7 @@ import torch.distributed as dist
 ap = argparse.ArgumentParser()
 ap.add_argument('--N', type=int, default=256)
 ap.add_argument('--steps', type=int, default=4)
+ap.add_argument('--K', type=int, default=1)
 args = ap.parse_args()
 rank, world, lrank = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
 torch.cuda.set_device(lrank)
@@ -34,9 +35,9 @@ steps = [5, 9, 13, 16][:args.steps]
 x0 = (torch.randn(1, 3, 64, 64, generator=g, dtype=torch.float64) * 3).to(dev)
 pre = {}
 for i in steps:
-    pre[i] = torch.randn(1, 1, N, 3, 64, 64, generator=g, dtype=torch.float64).to(dev)
+    pre[i] = torch.randn(1, args.K, N, 3, 64, 64, generator=g, dtype=torch.float64).to(dev)
     pre[f'pivot_{i}'] = torch.randn(1, 3, 64, 64, generator=g, dtype=torch.float64).to(dev)
-params = SamplingParams(N=N, K=1, eps=0.0, lambda_param=0.15, scorer=BrightnessScorer(device=dev))
+params = SamplingParams(N=N, K=args.K, eps=0.0, lambda_param=0.15, scorer=BrightnessScorer(device=dev))
 shard = Shard(rank, world, None) if world > 1 else Shard()
 
 def run(sh):

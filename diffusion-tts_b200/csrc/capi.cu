@@ -1111,6 +1111,14 @@ int b200ns_ddim_x0_score(const float* eps_u, const float* eps_t, const float* ca
   return 0;
 }
 
+int b200ns_sd_candidates(const float* pivot, const float* dirs, const float* u, const uint8_t* fresh, float* cand,
+                         int64_t N, int64_t E, float lambda, float sqrt_e, void* stream) {
+  if (N <= 0 || E <= 0) return fail("sd_candidates: N and E must be positive");
+  sd_candidates_kernel<<<static_cast<unsigned>(N), 256, 0, S(stream)>>>(pivot, dirs, u, fresh, cand, E, lambda, sqrt_e);
+  CK_LAUNCH("sd_candidates_kernel");
+  return 0;
+}
+
 int b200ns_plan_add_im2col(b200ns_plan* p, const b200ns_im2col_desc* d) {
   if (d->C * 9 > 64) return fail("im2col: C*9 must be <= 64");
   Op op;

@@ -183,4 +183,39 @@ __global__ void __launch_bounds__(256) ddim_x0_score_kernel(const float* __restr
   }
 }
 
+// SD eps_greedy / zero_order candidate noises (pipeline_stable_diffusion.py:1368-1378), fp32, one CTA per candidate n:
+//   fresh[n] != 0 :  cand = dirs[n]                                            (a fresh N(0,I) draw, :1375)
+//   else          :  cand = pivot + (((dirs[n] / ||dirs[n]||_2) * u[n]) * lambda) * sqrt(C*H*W)   (:1377-1379, the reference's
+//                    left-to-right tensor-scalar products, each rounded to fp32)
+// The norm is a fixed-order fp32 block reduction (torch.norm's summation order is not reproducible outside ATen: the
+// candidates agree with the reference's to fp32 rounding, identical inputs always give identical bits).
+__global__ void __launch_bounds__(256) sd_candidates_kernel(const float* __restrict__ pivot, const float* __restrict__ dirs,
+                                                            const float* __restrict__ u, const uint8_t* __restrict__ fresh,
+                                                            float* __restrict__ cand, int64_t E, float lambda, float sqrt_e) {
+  __shared__ float s_part[8];
+  __shared__ float s_norm;
+  const int64_t n = blockIdx.x;
+  const float* d = dirs + n * E;
+  float* o = cand + n * E;
+  if (fresh != nullptr && fresh[n] != 0) {
+    for (int64_t e = threadIdx.x; e < E; e += blockDim.x) o[e] = d[e];
+    return;
+  }
+  float acc = 0.f;
+  for (int64_t e = threadIdx.x; e < E; e += blockDim.x) acc = fmaf(d[e], d[e], acc);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) t += s_part[w];
+    s_norm = sqrtf(t);
+  }
+  __syncthreads();
+  const float nrm = s_norm, un = u[n];
+  for (int64_t e = threadIdx.x; e < E; e += blockDim.x)
+    o[e] = __fadd_rn(pivot[e], __fmul_rn(__fmul_rn(__fmul_rn(__fdiv_rn(d[e], nrm), un), lambda), sqrt_e));
+}
+
 }  // namespace b200

@@ -197,6 +197,24 @@ def ddim_x0_score(eps_pair: torch.Tensor, cand: torch.Tensor, guidance: float, s
     return scores, sums, x0
 
 
+def sd_candidates(pivot: torch.Tensor, dirs: torch.Tensor, scale: torch.Tensor, lam: float, sqrt_e: float,
+                  fresh: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """SD eps_greedy / zero_order candidate noises: pivot fp32 [1,C,H,W]; dirs fp32 [N,C,H,W]; scale fp32 [N] (the rand(1)
+    draws); fresh u8 [N].  cand = fresh ? dirs : pivot + ((dirs/||dirs|| * scale) * lam) * sqrt_e."""
+    _chk_cuda(pivot, dirs, scale, fresh)
+    _c(pivot, torch.float32), _c(dirs, torch.float32), _c(scale, torch.float32)
+    if fresh is not None:
+        _c(fresh, torch.uint8)
+    N, E = dirs.shape[0], dirs[0].numel()
+    if pivot.numel() != E or scale.numel() != N:
+        raise RuntimeError('sd_candidates: shape mismatch')
+    cand = torch.empty_like(dirs)
+    L.check(L.lib().b200ns_sd_candidates(L.ptr(pivot), L.ptr(dirs), L.ptr(scale), L.ptr(fresh), L.ptr(cand), N, E,
+                                         float(lam), float(sqrt_e), L.cur_stream()), 'sd_candidates')
+    _count()
+    return cand
+
+
 # ------------------------------------------------------------------ plans
 class Plan:
     """Ordered list of kernel launches (b200ns_plan).  Keeps every tensor it references alive."""

@@ -72,17 +72,17 @@ _OK = {}
 
 
 def mirror_ok(device) -> bool:
-    """One-time self check against the real thing (3 draws; generator state restored afterwards)."""
+    """One-time self check against the real thing (32 draws; generator state restored afterwards)."""
     key = str(torch.device(device))
     if key not in _OK:
         try:
             g = _generator(device)
             state = g.get_state()
-            want = rand1_values(g.initial_seed(), g.get_offset(), 3)
-            got = torch.cat([torch.rand(1, device=device) for _ in range(3)]).cpu().numpy()
+            want = rand1_values(g.initial_seed(), g.get_offset(), 32)
+            got = torch.cat([torch.rand(1, device=device) for _ in range(32)]).cpu().numpy()
             end = g.get_offset()
             g.set_state(state)
-            _OK[key] = bool(np.array_equal(want, got)) and end == g.get_offset() + 12 and g.get_offset() % 4 == 0
+            _OK[key] = bool(np.array_equal(want, got)) and end == g.get_offset() + 128 and g.get_offset() % 4 == 0
         except Exception:
             _OK[key] = False
     return _OK[key]

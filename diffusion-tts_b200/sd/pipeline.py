@@ -10,7 +10,8 @@ The reference drives the SD backend as
   * the CLIP text encoder's weights are unreachable offline: `encode_prompt` is injectable, and the default produces a
     deterministic pseudo-embedding pair [uncond, cond] of the right shape from the prompt string;
   * `out.images` is a visualisation of the first three latent channels (no VAE); `out.latents` is the real result.
-Methods other than beam raise NotImplementedError (8 f2: batched SD eps_greedy / zero_order is a "next" row).
+`method` = beam (sd/beam.py), eps_greedy / zero_order / naive (sd/search.py; 'rejection' is the naive loop, repeated by
+main.py like the reference's main.py:131); mcts raises NotImplementedError (8 f4).
 """
 from __future__ import annotations
 
@@ -22,6 +23,7 @@ import torch
 
 from ..sd_unet import SDUNetEngine
 from .beam import DDIMTable, sd_beam_search
+from .search import sd_eps_greedy_search
 
 
 def pseudo_prompt_embeddings(prompt: str, negative_prompt: str = '', tokens: int = 77, dim: int = 768) -> torch.Tensor:
@@ -49,10 +51,11 @@ class B200LatentBeamPipeline:
                  method: str = 'beam', params: Optional[dict] = None, guidance_scale: float = 7.5,
                  negative_prompt: str = '', latents: Optional[torch.Tensor] = None, height: int = 512, width: int = 512,
                  generator: Optional[torch.Generator] = None):
-        if method != 'beam':
-            raise NotImplementedError(f"SD method '{method}' is not on the B200 hot path (only 'beam'; SURVEY.md 8 f2)")
+        if method == 'mcts':
+            raise NotImplementedError("SD method 'mcts' is not on the B200 hot path (SURVEY.md 8 f4)")
+        if method not in ('beam', 'eps_greedy', 'zero_order', 'naive', 'rejection'):
+            raise ValueError(f"Unknown method: {method}")
         params = params or {}
-        B, N = int(params['B']), int(params['N'])                          # pipeline_stable_diffusion.py:1046,1080
         if height != width or height % 64:
             raise ValueError('height == width, a multiple of 64, is required')
         H = height // 8                                                   # vae_scale_factor = 8
@@ -61,14 +64,20 @@ class B200LatentBeamPipeline:
         ctx = self.encode_prompt(prompt, negative_prompt)
         table = DDIMTable(num_inference_steps)
         fused = self.decode is None and (score_function is None or getattr(score_function, 'latent_fused', False))
-        if fused:
-            best, rec = sd_beam_search(self.unet, table, latents, ctx, B, N, guidance_scale=guidance_scale, shard=self.shard)
-        else:
-            decode = self.decode or (lambda x0: (x0 * 127.5 + 128).clip(0, 255).to(torch.uint8))    # :1115
-            scorer = lambda im: score_function(im, [prompt] * im.shape[0], torch.zeros(im.shape[0], device=im.device))
-            best, rec = sd_beam_search(self.unet, table, latents, ctx, B, N, guidance_scale=guidance_scale, decode=decode,
-                                       scorer=scorer, shard=self.shard)
+        kw = dict(guidance_scale=guidance_scale, shard=self.shard)
+        if not fused:
+            kw['decode'] = self.decode or (lambda x0: (x0 * 127.5 + 128).clip(0, 255).to(torch.uint8))    # :1115
+            kw['scorer'] = lambda im: score_function(im, [prompt] * im.shape[0], torch.zeros(im.shape[0], device=im.device))
+        if method == 'beam':
+            B, N = int(params['B']), int(params['N'])                      # pipeline_stable_diffusion.py:1046,1080
+            best, rec = sd_beam_search(self.unet, table, latents, ctx, B, N, **kw)
+            score = float(rec.final_score)
+        else:   # eps_greedy / zero_order, and the plain eta=1 DDIM loop every other method name falls through to (:1330-1437)
+            m = method if method in ('eps_greedy', 'zero_order') else 'naive'
+            best, rec = sd_eps_greedy_search(self.unet, table, latents, ctx, int(params.get('N', 1)), int(params.get('K', 1)),
+                                             float(params.get('lambda', 0.15)), float(params.get('eps', 0.4)), m, **kw)
+            score = float(rec.max_score)
         from PIL import Image
         vis = (best[0, :3] * 127.5 + 128).clip(0, 255).to(torch.uint8).permute(1, 2, 0).cpu().numpy()
         out = SimpleNamespace(images=[Image.fromarray(vis, 'RGB')], latents=best, record=rec)
-        return out, float(rec.final_score)
+        return out, score

@@ -308,6 +308,12 @@ int b200ns_ddim_x0_score(const float* eps_u, const float* eps_t, const float* ca
                          float* scores, int64_t R, int32_t C, int32_t HW, float guidance, float sqrt_beta_t,
                          float sqrt_alpha_t, void* stream);
 
+/* Candidate noises of the SD eps_greedy / zero_order search (pipeline_stable_diffusion.py:1368-1379), fp32:
+ * cand[n] = fresh[n] ? dirs[n] : pivot + ((dirs[n] / ||dirs[n]||_2 * u[n]) * lambda) * sqrt_e;  pivot [E],
+ * dirs/cand [N, E], u [N] (the per-candidate torch.rand(1) scale draws), fresh uint8 [N] or NULL. */
+int b200ns_sd_candidates(const float* pivot, const float* dirs, const float* u, const uint8_t* fresh, float* cand,
+                         int64_t N, int64_t E, float lambda, float sqrt_e, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,7 +8,7 @@ Differences from the reference CLI, all forced by the offline B200 setting:
     the ImageNet-64 ADM pickle (main.py:157-158); without `--network` this front end builds a
     random-init ADM of the same architecture so that the path can run without network access.
   * `--classifier` (new, optional): a local `64x64_classifier.pt` for `--scorer imagenet` (random-init otherwise).
-  * `--backend sd` runs `--method beam` only (BASELINE.json config 5): an SD-1.5-shaped UNet (random-init unless
+  * `--backend sd` runs `--method beam | eps_greedy | zero_order | naive | rejection` (BASELINE.json config 5 = beam): an SD-1.5-shaped UNet (random-init unless
     `--network` names a state-dict `.pt`), latent-space scoring of the Tweedie x0, pseudo prompt embeddings (the CLIP
     text encoder and the VAE are unreachable offline).  `--steps` (new) overrides the 50 DDIM steps.
   * `--scorer clip` and `--method mcts` are not part of the B200 hot path and raise NotImplementedError / ValueError.

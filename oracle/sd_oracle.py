@@ -17,6 +17,8 @@ Plain-PyTorch functional restatement (no nn.Module, weights from a state dict) o
 Pinned by oracle/make_golden_sd.py against the vendored diffusers modules themselves (tests/golden/sd_*.pt).
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module."""
 import math
+
+import numpy as np
 from typing import Callable, Dict, List, Optional, Sequence
 
 import torch
@@ -224,3 +226,54 @@ def beam_search(unet: Callable, tab: DDIMTable, latents: torch.Tensor, ctx_pair:
     if record is not None:
         record['final_score'] = best_score
     return best
+
+
+def eps_greedy_search(unet: Callable, tab: DDIMTable, latents: torch.Tensor, ctx_pair: torch.Tensor, N: int, K: int,
+                      lam: float, eps: float, method: str, noise: dict, guidance: float = 7.5,
+                      score_fn: Callable = latent_brightness, record: Optional[dict] = None):
+    """pipeline_stable_diffusion.py:1330-1436 (`eps_greedy` / `zero_order` / `naive`) with identity decode.
+    noise['pivot'][i] [1,4,H,W]; noise['dirs'][i][k] [N,4,H,W] (the randn_like draw of candidate n, :1375/:1377);
+    noise['r'][i][k][n], noise['u'][i][k][n] = the two torch.rand(1).item() draws (:1373, :1379; u unused on the fresh
+    branch).  Returns (final latents, max_score of the last selection or None)."""
+    def guided(x, t):
+        xin = torch.cat([x, x])                                                    # :1341
+        ctx = torch.cat([ctx_pair[0:1].expand(x.shape[0], -1, -1), ctx_pair[1:2].expand(x.shape[0], -1, -1)])
+        eu, et = unet(xin, t, ctx).chunk(2)
+        return eu + guidance * (et - eu)                                           # :1357-1359
+
+    x = latents.clone()
+    max_score = None
+    for i, t in enumerate(tab.timesteps):
+        eps_pred = guided(x, t)
+        pivot = noise['pivot'][i]                                                  # :1366
+        if method in ('eps_greedy', 'zero_order'):
+            for k in range(K):
+                cands = []
+                for n in range(N):
+                    r = float(noise['r'][i][k][n])
+                    if (r < eps) if method == 'eps_greedy' else 0.0:               # :1374 (zero_order never draws fresh)
+                        cands.append(noise['dirs'][i][k][n:n + 1])
+                    else:
+                        to_add = noise['dirs'][i][k][n:n + 1]
+                        to_add = to_add / torch.norm(to_add)
+                        cands.append(pivot + to_add * float(noise['u'][i][k][n]) * lam * np.sqrt(
+                            x.shape[-1] * x.shape[-2] * x.shape[-3]))              # :1379
+                scores = []
+                for c in cands:
+                    lat_c, _ = ddim_step(tab, eps_pred, t, x, variance_noise=c)    # :1384
+                    eps2 = guided(lat_c, t)                                        # :1392-1406, the SAME t
+                    _, pred_next = ddim_step(tab, eps2, t, lat_c)                  # :1412
+                    scores.append(float(score_fn(pred_next)))                      # :1414-1431
+                max_score = max(scores)
+                best = scores.index(max_score)                                     # first maximal key of the dict (:1435)
+                pivot = cands[best]
+                if record is not None:
+                    record.setdefault('scores', []).append(torch.tensor(scores))
+                    record.setdefault('best', []).append(best)
+                    record.setdefault('cands', []).append(torch.cat(cands))
+        x, _ = ddim_step(tab, eps_pred, t, x, variance_noise=pivot)                # :1437
+        if record is not None:
+            record.setdefault('x', []).append(x.clone())
+    if max_score is None:                                                          # :1469-1474
+        max_score = float(score_fn(x))
+    return x, max_score

@@ -459,6 +459,7 @@ attention_kernel_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* bar_pready = bars + 8;                 // 128 arrivals: P(kt) is in TMEM and PV(kt-1) has been consumed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
+  pdl_launch_dependents();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bh = a.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y, bi = bh / a.heads, head = bh % a.heads;
   const int q0 = (a.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * 128;
@@ -488,6 +489,7 @@ attention_kernel_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tP = tmem_base + KT, tO = tmem_base + KT + KT / 2;
+  pdl_wait();
 
   if (warp == 4) {
     // ===================== issuer: TMA + MMA (one thread) =====================

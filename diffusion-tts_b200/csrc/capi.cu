@@ -47,6 +47,34 @@ int check_cuda(cudaError_t e, const char* what) {
 
 cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Launch with the programmatic-stream-serialization attribute (PDL): only for kernels that call pdl_wait() before
+// their first global-memory access (common.cuh).  OFF by default, B200NS_PDL=1 turns it on: measured on B200
+// (profiles/r01_pdl_ab.txt) the eps_greedy step is 32.5 ms with PDL against 32.2 ms without -- the GPU runs
+// power-capped (sw_power_cap, ~1.7 GHz), so the idle gaps between kernels are paid back as clocks and hiding them gains
+// nothing.
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200NS_PDL");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 int grid_for(int64_t work_items, int threads, int max_blocks = 148 * 16) {
   int64_t b = (work_items + threads - 1) / threads;
   if (b < 1) b = 1;
@@ -210,8 +238,8 @@ int launch_gemm_t(const GemmOp& g, cudaStream_t st) {
     CK(cudaFuncSetAttribute(gemm_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  gemm_conv_kernel<BN><<<g.grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(g.tmA[0], g.tmA[1], g.tmA[2], g.tmB, g.tmO, g.tmR,
-                                                                      g.args);
+  launch_pdl(gemm_conv_kernel<BN>, dim3(g.grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, g.tmA[0], g.tmA[1], g.tmA[2], g.tmB,
+             g.tmO, g.tmR, g.args);
   CK_LAUNCH("gemm_conv_kernel");
   return 0;
 }
@@ -222,7 +250,7 @@ int launch_gemm_small_n(const GemmOp& g, cudaStream_t st) {
     CK(cudaFuncSetAttribute(gemm_small_n_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  gemm_small_n_kernel<<<g.grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(g.tmA[0], g.tmA[1], g.tmA[2], g.tmB, g.args);
+  launch_pdl(gemm_small_n_kernel, dim3(g.grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, g.tmA[0], g.tmA[1], g.tmA[2], g.tmB, g.args);
   CK_LAUNCH("gemm_small_n_kernel");
   return 0;
 }
@@ -258,7 +286,7 @@ int launch_attn_v3(const AttnOp& o, cudaStream_t st) {
     CK(cudaFuncSetAttribute(attention_kernel_v3<KT, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  attention_kernel_v3<KT, D><<<o.grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(o.tmQ, o.tmK, o.tmV, o.args);
+  launch_pdl(attention_kernel_v3<KT, D>, o.grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, o.tmQ, o.tmK, o.tmV, o.args);
   CK_LAUNCH("attention_kernel_v3");
   return 0;
 }
@@ -285,13 +313,13 @@ int run_op(const Op& op, cudaStream_t st) {
       return 0;
     case OP_GN_APPLY:
       if (op.gna.threads > 256)
-        gn_apply_kernel<true><<<op.gna.grid, op.gna.threads, 0, st>>>(op.gna.args);
+        launch_pdl(gn_apply_kernel<true>, op.gna.grid, dim3(op.gna.threads), 0, st, op.gna.args);
       else
-        gn_apply_kernel<false><<<op.gna.grid, op.gna.threads, 0, st>>>(op.gna.args);
+        launch_pdl(gn_apply_kernel<false>, op.gna.grid, dim3(op.gna.threads), 0, st, op.gna.args);
       CK_LAUNCH("gn_apply_kernel");
       return 0;
     case OP_GN_FINALIZE:
-      gn_finalize_kernel<<<op.gnf.grid, 256, 0, st>>>(op.gnf.args, op.gnf.n_pairs);
+      launch_pdl(gn_finalize_kernel, dim3(op.gnf.grid), dim3(256), 0, st, op.gnf.args, op.gnf.n_pairs);
       CK_LAUNCH("gn_finalize_kernel");
       return 0;
     case OP_ATTN:
@@ -311,12 +339,12 @@ int run_op(const Op& op, cudaStream_t st) {
       if (op.attn.vrow) return op.attn.KT == 128 ? launch_attn_v3<128>(op.attn, st) : launch_attn_v3<64>(op.attn, st);
       return op.attn.KT == 128 ? launch_attn_t<128, false>(op.attn, st) : launch_attn_t<64, false>(op.attn, st);
     case OP_LINEAR:
-      linear_kernel<<<op.lin.grid, 256, 0, st>>>(op.lin.args);
+      launch_pdl(linear_kernel, dim3(op.lin.grid), dim3(256), 0, st, op.lin.args);
       CK_LAUNCH("linear_kernel");
       return 0;
     case OP_IM2COL:
-      im2col_c3_kernel<<<op.i2c.grid, 256, 0, st>>>(op.i2c.d.x, reinterpret_cast<__nv_bfloat16*>(op.i2c.d.out),
-                                                   op.i2c.d.batch, op.i2c.d.C, op.i2c.d.H, op.i2c.d.W);
+      launch_pdl(im2col_c3_kernel, dim3(op.i2c.grid), dim3(256), 0, st, op.i2c.d.x, reinterpret_cast<__nv_bfloat16*>(op.i2c.d.out),
+                 op.i2c.d.batch, op.i2c.d.C, op.i2c.d.H, op.i2c.d.W);
       CK_LAUNCH("im2col_c3_kernel");
       return 0;
     case OP_U8F32:
@@ -351,25 +379,24 @@ int run_op(const Op& op, cudaStream_t st) {
       const int nchunk = op.misc.i0 / 8;
       const int64_t rows = op.misc.n;
       if (nchunk <= 40) {               // 4 rows per warp, 32 per CTA
-        layernorm_kernel<8, 5><<<static_cast<unsigned>((rows + 31) / 32), 256, 0, st>>>(lx, lg, lb, lo, rows, op.misc.i0, op.misc.f0);
+        launch_pdl(layernorm_kernel<8, 5>, dim3(static_cast<unsigned>((rows + 31) / 32)), dim3(256), 0, st, lx, lg, lb, lo, rows, op.misc.i0, op.misc.f0);
       } else if (nchunk <= 80) {
-        layernorm_kernel<16, 5><<<static_cast<unsigned>((rows + 15) / 16), 256, 0, st>>>(lx, lg, lb, lo, rows, op.misc.i0, op.misc.f0);
+        launch_pdl(layernorm_kernel<16, 5>, dim3(static_cast<unsigned>((rows + 15) / 16)), dim3(256), 0, st, lx, lg, lb, lo, rows, op.misc.i0, op.misc.f0);
       } else {
-        layernorm_kernel<32, 8><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(lx, lg, lb, lo, rows, op.misc.i0, op.misc.f0);
+        launch_pdl(layernorm_kernel<32, 8>, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, st, lx, lg, lb, lo, rows, op.misc.i0, op.misc.f0);
       }
       CK_LAUNCH("layernorm_kernel");
       return 0;
     }
     case OP_GEGLU:
-      geglu_kernel<<<grid_for(op.misc.n * (op.misc.i0 / 8), 256, 148 * 32), 256, 0, st>>>(
-          reinterpret_cast<const __nv_bfloat16*>(op.misc.p0), reinterpret_cast<__nv_bfloat16*>(op.misc.p2), op.misc.n, op.misc.i0);
+      launch_pdl(geglu_kernel, dim3(grid_for(op.misc.n * (op.misc.i0 / 8), 256, 148 * 32)), dim3(256), 0, st,
+                 reinterpret_cast<const __nv_bfloat16*>(op.misc.p0), reinterpret_cast<__nv_bfloat16*>(op.misc.p2), op.misc.n, op.misc.i0);
       CK_LAUNCH("geglu_kernel");
       return 0;
     case OP_UPSAMPLE2X:
-      upsample2x_kernel<<<grid_for(static_cast<int64_t>(op.misc.i0) * op.misc.i1 * op.misc.i2 * 4 * (op.misc.n / 8), 256, 148 * 32),
-                          256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(op.misc.p0),
-                                        reinterpret_cast<__nv_bfloat16*>(op.misc.p2), op.misc.i0, op.misc.i1, op.misc.i2,
-                                        static_cast<int>(op.misc.n));
+      launch_pdl(upsample2x_kernel, dim3(grid_for(static_cast<int64_t>(op.misc.i0) * op.misc.i1 * op.misc.i2 * 4 * (op.misc.n / 8), 256, 148 * 32)),
+                 dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(op.misc.p0),
+                 reinterpret_cast<__nv_bfloat16*>(op.misc.p2), op.misc.i0, op.misc.i1, op.misc.i2, static_cast<int>(op.misc.n));
       CK_LAUNCH("upsample2x_kernel");
       return 0;
   }

@@ -120,6 +120,14 @@ DEVINL void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.ct
 DEVINL void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// (prologue: barrier init, TMEM allocation, descriptor prefetch) while its predecessor in the stream is still draining;
+// pdl_wait() blocks until the predecessor grid has completed and its memory is visible -- it must precede the first
+// access to global memory; pdl_launch_dependents() lets the successor be scheduled as soon as resources free up.
+// Both are no-ops for a kernel launched without the attribute.
+DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 

@@ -181,6 +181,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* rfull_bar = bars + 2 * STAGES + 4;                            // [SLOTS] residual sub-box landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + SLOTS);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = a.m_tiles * a.n_tiles;
@@ -212,6 +213,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                   // everything above overlapped the previous kernel's tail (PDL)
 
   if (warp == 0) {
     if (lane == 0) gemm_producer<BN>(tmA0, tmA1, tmA2, tmB, a, smem_a, smem_b, full_bar, empty_bar);
@@ -392,6 +394,7 @@ gemm_small_n_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = a.m_tiles * a.n_tiles;
@@ -419,6 +422,7 @@ gemm_small_n_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                   // everything above overlapped the previous kernel's tail (PDL)
 
   if (warp == 0) {
     if (lane == 0) gemm_producer<BN>(tmA0, tmA1, tmA2, tmB, a, smem_a, smem_b, full_bar, empty_bar);

@@ -159,6 +159,8 @@ struct GnFinalizeArgs {
 
 // one warp per (sample, group); 8 warps per block; grid = ceil(batch*groups / 8)
 __global__ void __launch_bounds__(256) gn_finalize_kernel(const GnFinalizeArgs a, int n_pairs) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int pair = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (pair >= n_pairs) return;
@@ -241,6 +243,8 @@ template <bool WIDE>
 __global__ void __launch_bounds__(WIDE ? 512 : 256, WIDE ? 1 : 3) gn_apply_kernel(const GnApplyArgs a) {
   __shared__ float s_mean[64];
   __shared__ float s_rstd[64];
+  pdl_launch_dependents();
+  pdl_wait();
   const int VC = a.C >> 3;
   const int vx = threadIdx.x % VC, py = threadIdx.x / VC;
   const int bi = a.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;

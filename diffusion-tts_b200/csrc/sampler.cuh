@@ -254,6 +254,8 @@ struct LinearArgs {
   int ld_out;
 };
 __global__ void linear_kernel(const LinearArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp_global >= a.rows * a.N) return;
@@ -275,6 +277,8 @@ __global__ void linear_kernel(const LinearArgs a) {
 // 3x3 im2col of fp32 NCHW [B,C,H,W] (C<=7) -> bf16 [B*H*W, 64]; k = (kh*3+kw)*C + c.
 __global__ void im2col_c3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int C, int H,
                                  int W) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t total = static_cast<int64_t>(B) * H * W * 8;    // 8 chunks of 8 bf16 per row
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {

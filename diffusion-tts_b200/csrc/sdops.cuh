@@ -20,6 +20,8 @@ template <int LPR, int CPL>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                                                         int64_t rows, int C, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int RPW = 32 / LPR;                   // rows per warp
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPR;
@@ -81,6 +83,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
 // in [rows, 2F] = [hidden | gate] -> out [rows, F] = hidden * gelu(gate)   (F multiple of 8)
 __global__ void __launch_bounds__(256) geglu_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                                     int64_t rows, int F) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t total = rows * (F >> 3);
   const int fc = F >> 3;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -99,6 +103,8 @@ __global__ void __launch_bounds__(256) geglu_kernel(const __nv_bfloat16* __restr
 // bf16 NHWC [B,H,W,C] -> [B,2H,2W,C], nearest
 __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                                          int B, int H, int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cc = C >> 3;
   const int64_t total = static_cast<int64_t>(B) * 2 * H * 2 * W * cc;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;

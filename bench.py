@@ -40,9 +40,12 @@ METRIC = 'scored_candidates_per_sec'
 UNIT = 'candidates/s'
 
 
-def workload_name(n_total):
+def workload_name(n_total, scorer='brightness'):
+    sc = 'brightness scorer' if scorer == 'brightness' else ('ImageNet classifier-probability scorer (EncoderUNetModel 64x64, '
+                                                             'random-init, in the loop)' if scorer == 'imagenet' else
+                                                             'compressibility scorer (exact JPEG q80 byte count)')
     return (f'EDM ImageNet-64 ADM (DhariwalUNet 295.9M, class-cond, random-init), eps_greedy N={n_total} '
-            f'(={N_PER_GPU}/GPU) K=1 lambda=0.15 eps=0, brightness scorer, 18-step Heun cycle, b=1 image')
+            f'(={N_PER_GPU}/GPU) K=1 lambda=0.15 eps=0, {sc}, 18-step Heun cycle, b=1 image')
 
 
 class ClockSampler:
@@ -163,7 +166,16 @@ def run_b200(args):
     net = B200Denoiser(random_state_dict(adm_param_shapes(), 1234), device=dev)
     table = StepTable(net, dev, NUM_STEPS, **SAMPLER)
     shard = Shard(rank, world, None)
-    params = SamplingParams(N=N, K=1, eps=0.0, lambda_param=0.15, scorer=BrightnessScorer(device=dev))
+    if args.scorer == 'imagenet':          # BASELINE.json configs[3]: the classifier network runs inside the search loop
+        from diffusion_tts_b200.arch import classifier_param_shapes
+        from diffusion_tts_b200.classifier import ImageNetScorer
+        scorer = ImageNetScorer(random_state_dict(classifier_param_shapes(), 22), device=dev)
+    elif args.scorer == 'compressibility':
+        from diffusion_tts_b200.scorers import CompressibilityScorer
+        scorer = CompressibilityScorer(device=dev)
+    else:
+        scorer = BrightnessScorer(device=dev)
+    params = SamplingParams(N=N, K=1, eps=0.0, lambda_param=0.15, scorer=scorer)
     g = torch.Generator().manual_seed(1)
     latents = torch.randn(1, 3, 64, 64, generator=g)
     labels = torch.eye(1000)[torch.randint(1000, (1,), generator=g)].to(dev)
@@ -254,7 +266,7 @@ def run_b200(args):
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'bf16', 'data': 'synthetic',
-        'config': {'workload': workload_name(N), 'N_per_gpu': N_PER_GPU, 'K': 1, 'num_steps': NUM_STEPS,
+        'config': {'workload': workload_name(N, args.scorer), 'N_per_gpu': N_PER_GPU, 'K': 1, 'num_steps': NUM_STEPS,
                    'l2': 'not flushed: per-step working set (0.6 GB bf16 weights + >2 GB activations) exceeds the 126 MB L2',
                    'sampler_state': 'fp64', 'unet': 'bf16 storage, fp32 accumulate/GroupNorm/softmax'},
         'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h * world,
@@ -287,6 +299,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', type=str, default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--scorer', type=str, default='brightness', choices=['brightness', 'imagenet', 'compressibility'],
+                    help='brightness = BASELINE.json configs[1] (the headline); imagenet = configs[3]')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

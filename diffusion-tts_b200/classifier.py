@@ -271,7 +271,9 @@ class ImageNetScorer(Scorer):
         class_labels = class_labels.to(self.device)
         target = torch.argmax(class_labels, dim=1) if class_labels.dim() > 1 else class_labels
         t = 0.0
-        if timesteps is not None and torch.is_tensor(timesteps) and timesteps.numel():
+        if getattr(timesteps, '_b200_uniform_value', None) is not None:      # the search loop's own zeros: no host sync
+            t = float(timesteps._b200_uniform_value)
+        elif timesteps is not None and torch.is_tensor(timesteps) and timesteps.numel():
             if not bool((timesteps == timesteps.flatten()[0]).all()):
                 raise NotImplementedError('per-sample timesteps are not used by the search path (always zeros)')
             t = float(timesteps.flatten()[0])

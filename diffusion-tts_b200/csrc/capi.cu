@@ -669,6 +669,11 @@ int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d) {
   // [0, n1*c1) and [n1*c1, Npad) of widths c1 != c2 (320 = 192 + 128, 640 = 2*192 + 256): pointers are shifted, the A operand is shared.
   // Cost model per part: (waves over the SMs) x (cycles per K block of one tile); an extra launch costs one more tail.
   if (d->out_fp32 || d->Npad % 64) return add_gemm_part(p, d, 0, d->N);
+  if (d->geglu) {
+    if (d->Npad % 128 || d->N % 128 || d->residual != nullptr || d->gn_stats != nullptr)
+      return fail("gemm: geglu needs N and Npad multiples of 128, no residual and no gn_stats");
+    return add_gemm_part(p, d, d->Npad % 256 == 0 ? 256 : 128, d->N);
+  }
   if (g_force_bn > 0 && d->Npad % g_force_bn == 0) return add_gemm_part(p, d, g_force_bn, d->N);
   const int m_tiles = (d->batch * d->H * d->W + 127) / 128;
   const int cands[4] = {256, 192, 128, 64};
@@ -776,11 +781,12 @@ static int add_gemm_part(b200ns_plan* p, const b200ns_gemm_desc* d, int BN_force
   a.gn_stats = reinterpret_cast<float2*>(d->gn_stats);
   a.ld_stats = ld_stats;
   a.reverse = d->reverse;
+  a.geglu = d->geglu;
   if (d->gn_stats != nullptr && (BN == 16 || a.M % 64)) return fail("gemm: gn_stats needs bf16 output, N tiles >= 64 and M % 64 == 0");
   if (!d->out_fp32 && (d->ld_out % 8)) return fail("gemm: ld_out must be a multiple of 8 for bf16 output");
   if (d->residual != nullptr && (d->ld_res % 8)) return fail("gemm: ld_res must be a multiple of 8");
   if (BN != 16) {
-    int rc = make_tmap_2d_ld(&g.tmO, d->out, static_cast<uint64_t>(d->N), static_cast<uint64_t>(a.M),
+    int rc = make_tmap_2d_ld(&g.tmO, d->out, static_cast<uint64_t>(d->geglu ? d->N / 2 : d->N), static_cast<uint64_t>(a.M),
                              static_cast<uint64_t>(d->ld_out), 64, 128);
     if (rc) return rc;
     rc = make_tmap_2d_ld(&g.tmR, d->residual ? d->residual : d->out, static_cast<uint64_t>(d->N),

@@ -52,6 +52,9 @@ struct GemmArgs {
   int ld_stats;                  // row pitch of gn_stats in channels (= the full N when this launch covers a column slice)
   int src_stride[3];             // 1, or 2: the source is sampled with stride 2 (3x3 stride-2 pad-1 conv: Downsample2D)
   int reverse;                   // walk the tiles last-to-first (start on what the producer of A wrote last: L2 hits)
+  int geglu;                     // 1: the weight rows come in groups of 128 = [64 hidden | 64 gate] and the epilogue stores
+                                 //    hidden * gelu(gate) (exact erf GELU) as bf16 [M, N/2]: GEGLU (activations.py:117-123)
+                                 //    fused into the projection, whose [M, N] output never touches HBM
 };
 
 template <int BN>
@@ -247,10 +250,79 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       issue_res(1);
     }
 
+    bool num_tiles_done = false;
     uint32_t k = 0;                         // sub-box counter of this CTA
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    if constexpr (NSUB % 2 == 0) {
+      if (a.geglu) {
+        // ---- GEGLU epilogue: input sub-boxes (2jj, 2jj+1) = (hidden, gate) columns of the same 64 output features
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          const int tl = a.reverse ? num_tiles - 1 - tile : tile;
+          const int mt = tl / a.n_tiles, nt = tl % a.n_tiles;
+          if (et < BN) {
+            const int n = nt * BN + et;
+            smem_bias[acc * BN + et] = (a.bias != nullptr && n < a.N) ? __ldg(a.bias + n) : 0.f;
+          }
+          named_barrier_sync(1, 256);
+          mbar_wait(&tfull_bar[acc], acc_phase);
+          tc_fence_after();
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+          for (int jj = 0; jj < NSUB / 2; ++jj, ++k) {
+            const uint32_t slot = slot0 + (k % SLOTS) * Cfg::SLOT_BYTES;
+            uint32_t rh[32], rg[32];
+            tmem_ld32(t_row + (2 * jj) * 64 + half * 32, rh);
+            tmem_ld32(t_row + (2 * jj + 1) * 64 + half * 32, rg);
+            tmem_ld_wait();
+            if (jj == NSUB / 2 - 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            }
+            const uint32_t bh = bias0 + static_cast<uint32_t>(acc * BN + (2 * jj) * 64 + half * 32) * 4u;
+            const uint32_t bg = bh + 64u * 4u;
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint4 b1 = lds128(bh + i * 16), b2 = lds128(bg + i * 16);
+              const float hb[4] = {__uint_as_float(b1.x), __uint_as_float(b1.y), __uint_as_float(b1.z), __uint_as_float(b1.w)};
+              const float gb[4] = {__uint_as_float(b2.x), __uint_as_float(b2.y), __uint_as_float(b2.z), __uint_as_float(b2.w)};
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                // the unfused path rounds the projection to bf16 before GEGLU: keep that rounding so that both paths agree
+                const float hv = __bfloat162float(__float2bfloat16(__uint_as_float(rh[4 * i + c]) + hb[c]));
+                const float gv = __bfloat162float(__float2bfloat16(__uint_as_float(rg[4 * i + c]) + gb[c]));
+                v[4 * i + c] = hv * gelu_erf(gv);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 u;
+              u.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
+              u.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+              u.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+              u.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+              sts128(slot + row_off + (((half * 4 + i) ^ rsw) << 4), u);
+            }
+            fence_proxy_async_smem();
+            if (is_e) bulk_wait_group_read<1>();      // stores <= k-3 have released their slots (4-slot ring)
+            named_barrier_sync(1, 256);
+            if (is_e) {
+              tma_store_2d(&tmO, smem_slot + (k % SLOTS) * Cfg::SLOT_BYTES, nt * (BN / 2) + jj * 64, mt * 128);
+              bulk_commit_group();
+            }
+          }
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+        }
+        if (is_e) bulk_wait_group<0>();
+        num_tiles_done = true;
+      }
+    }
+    for (int tile = blockIdx.x; !num_tiles_done && tile < num_tiles; tile += gridDim.x) {
       const int tl = a.reverse ? num_tiles - 1 - tile : tile;
     const int mt = tl / a.n_tiles, nt = tl % a.n_tiles;
       // bias of this tile's columns -> smem (double buffered by accumulator index)

@@ -1,6 +1,6 @@
 // HBM-bound leaves of the SD-1.5-shaped UNet2DConditionModel (BASELINE.json config 5) and the DDIM beam step:
 //   layernorm_kernel   nn.LayerNorm over channels of a token tensor      (attention.py BasicTransformerBlock norm1-3)
-//   geglu_kernel       hidden * gelu(gate), exact erf GELU               (activations.py GEGLU.forward :117-123)
+//   geglu_kernel       hidden * gelu(gate), erf GELU (1.5e-7)              (activations.py GEGLU.forward :117-123)
 //   upsample2x_kernel  F.interpolate(scale_factor=2, mode='nearest')     (upsampling.py Upsample2D.forward)
 //   ddim_cfg_step_kernel / ddim_x0_score_kernel                          (pipeline_stable_diffusion.py:1073-1123,
 //                                                                         scheduling_ddim.py:398-460, sd/scorers.py:66-67)
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) geglu_kernel(const __nv_bfloat16* __restr
     load8(in + r * 2 * F + c, a);
     load8(in + r * 2 * F + F + c, g);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = a[j] * (0.5f * g[j] * (1.0f + erff(g[j] * 0.70710678118654752f)));
+    for (int j = 0; j < 8; ++j) o[j] = a[j] * gelu_erf(g[j]);
     store8(out + r * F + c, o);
   }
 }

@@ -215,6 +215,14 @@ def sd_candidates(pivot: torch.Tensor, dirs: torch.Tensor, scale: torch.Tensor, 
     return cand
 
 
+def interleave_geglu(t: torch.Tensor) -> torch.Tensor:
+    """Rows [hidden (F) ; gate (F)] of a GEGLU projection (weight [2F, K] or bias [2F]) -> groups of
+    [64 hidden | 64 gate] rows, the order the fused GEGLU epilogue of the GEMM expects.  F % 64 == 0."""
+    F = t.shape[0] // 2
+    h, g = t[:F].reshape(F // 64, 64, *t.shape[1:]), t[F:].reshape(F // 64, 64, *t.shape[1:])
+    return torch.stack([h, g], dim=1).reshape(t.shape).contiguous()
+
+
 # ------------------------------------------------------------------ plans
 class Plan:
     """Ordered list of kernel launches (b200ns_plan).  Keeps every tensor it references alive."""
@@ -273,9 +281,10 @@ class Plan:
 
     def add_gemm(self, a: Sequence[torch.Tensor], segs: Sequence[Tuple[int, int, int, int]], w: torch.Tensor, N: int,
                  out: torch.Tensor, *, bias=None, residual=None, out_scale=1.0, gn_stats=None, reverse=False, a_stride=None,
-                 label='gemm', alg_k=None):
+                 label='gemm', alg_k=None, geglu=False):
         """a: 1-3 NHWC bf16 tensors [B,H,W,C]; segs: (src, taps, cstart, cblocks); w: bf16 [Npad,Ktot].
-        gn_stats: optional fp32 [M/64, N, 2] receiving per-channel (sum, sumsq) of the stored output."""
+        gn_stats: optional fp32 [M/64, N, 2] receiving per-channel (sum, sumsq) of the stored output.
+        geglu: w / bias rows in groups of [64 hidden | 64 gate] (`interleave_geglu`); out is [.., N/2] = hidden * gelu(gate)."""
         d = L.GemmDesc()
         a_stride = list(a_stride) if a_stride is not None else [1] * len(a)
         B, H, W_, _ = a[0].shape
@@ -305,6 +314,9 @@ class Plan:
                 raise RuntimeError('gn_stats must be fp32 [M/64, N, 2]')
         d.gn_stats = L.ptr(gn_stats)
         d.reverse = int(reverse)
+        d.geglu = int(bool(geglu))
+        if geglu and out.shape[-1] * 2 != N:
+            raise RuntimeError('gemm(geglu): out must have N/2 columns')
         self._k(*a, w, bias, residual, out, gn_stats)
         n_before = L.lib().b200ns_plan_size(self._h)
         L.check(L.lib().b200ns_plan_add_gemm(self._h, C.byref(d)), 'plan_add_gemm')

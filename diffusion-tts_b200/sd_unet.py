@@ -24,7 +24,7 @@ from typing import Dict, List, Optional
 
 import torch
 
-from .ops import Plan
+from .ops import Plan, interleave_geglu
 from .unet import ForwardPlan, _pack_conv
 
 CTX_ROWS = 128          # 77 context tokens padded to a multiple of the key tile
@@ -148,11 +148,15 @@ class SDPlan(ForwardPlan):
         t2 = self._act('t0', B, H, H, C)
         self._attn(eng, f'{t}.attn2', n, t1, t2, cross=True)
         P.add_layernorm(t2, W_[f'{t}.norm3.weight'], W_[f'{t}.norm3.bias'], n, label=f'{t}.norm3')
-        g = self._act('ffg', B, H, H, 8 * C)
-        P.add_gemm([n], [(0, 1, 0, C // 64)], W_[f'{t}.ff1.w'], 8 * C, g, bias=W_[f'{t}.ff1.b'], reverse=self._rev(n, g),
-                   label=f'{t}.ff.proj')
         f = self._act('fff', B, H, H, 4 * C)
-        P.add_geglu(g, f, label=f'{t}.ff.geglu')
+        if eng.fused_geglu:       # hidden * gelu(gate) in the projection's epilogue: the [B*HW, 8C] tensor never exists
+            P.add_gemm([n], [(0, 1, 0, C // 64)], W_[f'{t}.ff1.wi'], 8 * C, f, bias=W_[f'{t}.ff1.bi'], reverse=self._rev(n, f),
+                       label=f'{t}.ff.proj+geglu', geglu=True)
+        else:
+            g = self._act('ffg', B, H, H, 8 * C)
+            P.add_gemm([n], [(0, 1, 0, C // 64)], W_[f'{t}.ff1.w'], 8 * C, g, bias=W_[f'{t}.ff1.b'], reverse=self._rev(n, g),
+                       label=f'{t}.ff.proj')
+            P.add_geglu(g, f, label=f'{t}.ff.geglu')
         t3 = self._act('t1', B, H, H, C)
         P.add_gemm([f], [(0, 1, 0, 4 * C // 64)], W_[f'{t}.ff2.w'], C, t3, bias=W_[f'{t}.ff2.b'], residual=t2,
                    reverse=self._rev(f, t3), label=f'{t}.ff.out')
@@ -234,10 +238,11 @@ class SDPlan(ForwardPlan):
 class SDUNetEngine:
     """Packed weights + cached plans.  `set_context(ctx_pair)` once per prompt, then `forward(x, t)`."""
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device='cuda', use_graphs: bool = True):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device='cuda', use_graphs: bool = True, fused_geglu: bool = True):
         from . import _lib
         _lib.lib()
         self.device = torch.device(device)
+        self.fused_geglu = fused_geglu
         if self.device.type != 'cuda':
             raise RuntimeError('SDUNetEngine requires a CUDA device (B200); there is no CPU fallback')
         self.use_graphs = use_graphs
@@ -329,7 +334,11 @@ class SDUNetEngine:
             for a in (a1, a2):
                 w[f'{a}.out.w'] = bf(pad_cols(cpu(sd[f'{a}.to_out.0.weight']), hd, dp))
                 w[f'{a}.out.b'] = f(sd[f'{a}.to_out.0.bias'])
-            w[f'{t}.ff1.w'], w[f'{t}.ff1.b'] = bf(cpu(sd[f'{t}.ff.net.0.proj.weight'])), f(sd[f'{t}.ff.net.0.proj.bias'])
+            if self.fused_geglu:      # rows regrouped as [64 hidden | 64 gate] for the fused GEGLU epilogue
+                w[f'{t}.ff1.wi'] = bf(interleave_geglu(cpu(sd[f'{t}.ff.net.0.proj.weight'])))
+                w[f'{t}.ff1.bi'] = f(interleave_geglu(sd[f'{t}.ff.net.0.proj.bias']))
+            else:
+                w[f'{t}.ff1.w'], w[f'{t}.ff1.b'] = bf(cpu(sd[f'{t}.ff.net.0.proj.weight'])), f(sd[f'{t}.ff.net.0.proj.bias'])
             w[f'{t}.ff2.w'], w[f'{t}.ff2.b'] = bf(cpu(sd[f'{t}.ff.net.2.weight'])), f(sd[f'{t}.ff.net.2.bias'])
 
     # ------------------------------------------------------------------ context

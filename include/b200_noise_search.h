@@ -152,6 +152,10 @@ typedef struct {
   /* per source: 1, or 2 = the source is [batch, 2H, 2W, C] and is sampled with stride 2, i.e. a 3x3 stride-2 pad-1
    * convolution (Downsample2D, sd/diffusers/src/diffusers/models/downsampling.py) through TMA elementStrides. */
   int32_t a_stride[3];
+  /* 1: GEGLU fused into the epilogue (diffusers GEGLU.forward, activations.py:117-123).  The weight rows / bias entries
+   * come in groups of 128 = [64 hidden rows | 64 gate rows] of the same 64 output features; `out` is bf16 [M, N/2]
+   * (ld_out >= N/2) = hidden * gelu(gate), exact erf GELU.  No residual / gn_stats; Npad % 128 == 0. */
+  int32_t geglu;
 } b200ns_gemm_desc;
 int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d);
 /* Tuning aid: force the N tile width (64/128/192/256; 0 = cost model) of subsequently added bf16 GEMMs whose padded

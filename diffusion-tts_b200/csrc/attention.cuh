@@ -438,7 +438,7 @@ struct AttnCfg3 {
   static constexpr int MIN_CTAS = (TMEM_COLS == 256 && SMEM_BYTES <= 110 * 1024) ? 2 : 1;
 };
 
-template <int KT, int D = 64>
+template <int KT, int D = 64, bool POLY = false>
 __global__ void __launch_bounds__(160, AttnCfg3<KT, D>::MIN_CTAS)
 attention_kernel_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnArgs a) {
@@ -595,8 +595,12 @@ attention_kernel_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       uint32_t pk[KT / 2];
 #pragma unroll
       for (int j = 0; j < KT / 2; ++j) {
-        const float p0 = ex2_approx(fmaf(__uint_as_float(sr[2 * j]), c, -mc));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(sr[2 * j + 1]), c, -mc));
+        // the exponentials bound this kernel (MUFU: 16 per clock and SM): with POLY every 4th pair is evaluated on
+        // the FMA pipe instead (ex2_poly), which moves ~1/4 of the work off the saturated unit
+        const float x0 = fmaf(__uint_as_float(sr[2 * j]), c, -mc), x1 = fmaf(__uint_as_float(sr[2 * j + 1]), c, -mc);
+        const bool poly = POLY && (j & 3) == 3;
+        const float p0 = poly ? ex2_poly(x0) : ex2_approx(x0);
+        const float p1 = poly ? ex2_poly(x1) : ex2_approx(x1);
         lsum += p0 + p1;
         pk[j] = pack_bf16(p0, p1);
       }

@@ -278,17 +278,32 @@ int launch_attn_t(const AttnOp& o, cudaStream_t st) {
   return 0;
 }
 
-template <int KT, int D = 64>
-int launch_attn_v3(const AttnOp& o, cudaStream_t st) {
+// B200NS_ATTN_POLY=1 evaluates 1/4 of the softmax exponentials on the FMA pipe (ex2_poly) instead of the MUFU unit.
+// Measured on B200 (profiles/r01_attention_poly_ab.txt): no gain (L=4096 D=64: 3.29 vs 3.29 ms; L=1024 D=128: 0.35 vs
+// 0.32 ms) although ncu shows the XU pipe 70 % busy -- the softmax warps are issue/latency-bound, not MUFU-bound.  Off.
+bool attn_poly() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200NS_ATTN_POLY");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+template <int KT, int D, bool POLY>
+int launch_attn_v3_p(const AttnOp& o, cudaStream_t st) {
   using Cfg = AttnCfg3<KT, D>;
   static bool attr_set = false;
   if (!attr_set) {
-    CK(cudaFuncSetAttribute(attention_kernel_v3<KT, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(attention_kernel_v3<KT, D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  launch_pdl(attention_kernel_v3<KT, D>, o.grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, o.tmQ, o.tmK, o.tmV, o.args);
+  launch_pdl(attention_kernel_v3<KT, D, POLY>, o.grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, o.tmQ, o.tmK, o.tmV, o.args);
   CK_LAUNCH("attention_kernel_v3");
   return 0;
+}
+template <int KT, int D = 64>
+int launch_attn_v3(const AttnOp& o, cudaStream_t st) {
+  return attn_poly() ? launch_attn_v3_p<KT, D, true>(o, st) : launch_attn_v3_p<KT, D, false>(o, st);
 }
 
 template <int KT>

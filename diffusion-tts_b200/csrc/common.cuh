@@ -237,6 +237,19 @@ DEVINL float ex2_approx(float x) {
   return y;
 }
 
+// 2^x on the FMA / integer pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 minimax polynomial
+// for 2^f (relative error 7.5e-5, 50x below the bf16 resolution of the softmax probabilities it feeds), n added into
+// the exponent field.  x <= -126 gives a value <= 2^-126 (flushed to ~0); valid for x < 126.
+DEVINL float ex2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float xf = __fadd_rn(x, 12582912.0f);                  // 1.5 * 2^23: n lands in the low mantissa bits
+  const float fr = __fsub_rn(x, __fsub_rn(xf, 12582912.0f));
+  float p = fmaf(0.0551716648f, fr, 0.2426111251f);
+  p = fmaf(p, fr, 0.6932609677f);
+  p = fmaf(p, fr, 0.9999280572f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xf) << 23));
+}
+
 // erf-GELU x * 0.5 * (1 + erf(x / sqrt 2)) (torch.nn.functional.gelu default, diffusers GEGLU) with
 // erf(z) = 1 - (a1 t + .. + a5 t^5) exp(-z^2), t = 1/(1 + p z)  (Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7 -- four
 // orders of magnitude below the bf16 resolution of the stored result): ~17 instructions incl. 2 MUFU instead of ~45 for

@@ -425,7 +425,11 @@ attention_kernel_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 // requested.  80 KB smem + 256 TMEM columns -> two CTAs per SM.
 // D = (padded) head dimension, a multiple of 64: D/64 SWIZZLE_128B atoms per Q/K/V tile.  Heads whose true
 // dimension is not a multiple of 64 (SD-1.5: 40, 80, 160) are zero-padded by the projection weights.
-template <int KT, int D = 64>
+// ALIAS: P(kt) is stored over the (already consumed) S(kt) columns, so a CTA needs only KT + D TMEM columns (128 for
+// KT = D = 64) and THREE CTAs fit an SM instead of two -- a third independent softmax stream to fill the MUFU / issue
+// slots the other two leave idle while they wait on TMEM loads, stores and MMA completions.  The price: S(kt+1) can only
+// be issued after PV(kt) (it overwrites P(kt)); the tensor pipe executes one thread's MMAs in issue order.
+template <int KT, int D = 64, bool ALIAS = false>
 struct AttnCfg3 {
   static constexpr int ATOMS = D / 64;
   static constexpr int Q_BYTES = ATOMS * 128 * 128;
@@ -433,16 +437,16 @@ struct AttnCfg3 {
   static constexpr int V_BYTES = ATOMS * KT * 128;
   static constexpr int SMEM_BYTES = Q_BYTES + 2 * K_BYTES + 2 * V_BYTES + 1024 + 128;
   static constexpr int THREADS = 160;
-  static constexpr int TMEM_NEED = KT + KT / 2 + D;
-  static constexpr int TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
-  static constexpr int MIN_CTAS = (TMEM_COLS == 256 && SMEM_BYTES <= 110 * 1024) ? 2 : 1;
+  static constexpr int TMEM_NEED = ALIAS ? KT + D : KT + KT / 2 + D;
+  static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
+  static constexpr int MIN_CTAS = (TMEM_COLS == 128 && SMEM_BYTES <= 72 * 1024) ? 3 : ((TMEM_COLS <= 256 && SMEM_BYTES <= 110 * 1024) ? 2 : 1);
 };
 
-template <int KT, int D = 64, bool POLY = false>
-__global__ void __launch_bounds__(160, AttnCfg3<KT, D>::MIN_CTAS)
+template <int KT, int D = 64, bool POLY = false, bool ALIAS = false>
+__global__ void __launch_bounds__(160, AttnCfg3<KT, D, ALIAS>::MIN_CTAS)
 attention_kernel_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnArgs a) {
-  using Cfg = AttnCfg3<KT, D>;
+  using Cfg = AttnCfg3<KT, D, ALIAS>;
   constexpr int ATOMS = Cfg::ATOMS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -488,7 +492,7 @@ attention_kernel_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tP = tmem_base + KT, tO = tmem_base + KT + KT / 2;
+  const uint32_t tS = tmem_base, tP = ALIAS ? tmem_base : tmem_base + KT, tO = tmem_base + (ALIAS ? KT : KT + KT / 2);
   pdl_wait();
 
   if (warp == 4) {
@@ -534,7 +538,7 @@ attention_kernel_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tc_fence_after();
       issue_s(0);
       for (int kt = 0; kt < nkt; ++kt) {
-        if (kt + 1 < nkt) {
+        if (!ALIAS && kt + 1 < nkt) {
           mbar_wait(bar_sfree, kt & 1);               // S(kt) is in registers => S(kt) finished: S columns and K buffer kt&1 are free
           if (kt + 2 < nkt) load_k(kt + 2);
           mbar_wait(&bar_k[(kt + 1) & 1], ((kt + 1) >> 1) & 1);
@@ -552,6 +556,12 @@ attention_kernel_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int k = 0; k < KT / 16; ++k)             // 16 keys per MMA: 8 packed TMEM columns of P, 2 KB of V rows
           umma_bf16_ts(tO, tP + k * 8, dv + static_cast<uint64_t>(k * (2048 >> 4)), idesc_o, (kt | k) != 0);
         umma_commit(bar_o);
+        if (ALIAS && kt + 1 < nkt) {                  // S(kt+1) overwrites P(kt): issued behind PV(kt), executed in order
+          if (kt + 2 < nkt) load_k(kt + 2);           // pready(kt) implies S(kt) was consumed: K buffer kt&1 is free
+          mbar_wait(&bar_k[(kt + 1) & 1], ((kt + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_s(kt + 1);
+        }
       }
     }
   } else {

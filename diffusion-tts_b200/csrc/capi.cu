@@ -182,6 +182,7 @@ struct AttnOp {
   int vrow;
   int head_dim;
   int variant;
+  int alias;
   dim3 grid;
 };
 struct LinearOp {
@@ -289,20 +290,32 @@ bool attn_poly() {
   }
   return v == 1;
 }
-template <int KT, int D, bool POLY>
+// B200NS_ATTN_ALIAS: 1 = head_dim-64 self-attention runs the aliased-P variant (KT = 64, 128 TMEM columns, 3 CTAs per SM)
+bool attn_alias() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200NS_ATTN_ALIAS");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+template <int KT, int D, bool POLY, bool ALIAS = false>
 int launch_attn_v3_p(const AttnOp& o, cudaStream_t st) {
-  using Cfg = AttnCfg3<KT, D>;
+  using Cfg = AttnCfg3<KT, D, ALIAS>;
   static bool attr_set = false;
   if (!attr_set) {
-    CK(cudaFuncSetAttribute(attention_kernel_v3<KT, D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(attention_kernel_v3<KT, D, POLY, ALIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  launch_pdl(attention_kernel_v3<KT, D, POLY>, o.grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, o.tmQ, o.tmK, o.tmV, o.args);
+  launch_pdl(attention_kernel_v3<KT, D, POLY, ALIAS>, o.grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, o.tmQ, o.tmK, o.tmV, o.args);
   CK_LAUNCH("attention_kernel_v3");
   return 0;
 }
 template <int KT, int D = 64>
 int launch_attn_v3(const AttnOp& o, cudaStream_t st) {
+  if constexpr (KT == 64 && D == 64) {
+    if (o.alias) return launch_attn_v3_p<64, 64, false, true>(o, st);
+  }
   return attn_poly() ? launch_attn_v3_p<KT, D, true>(o, st) : launch_attn_v3_p<KT, D, false>(o, st);
 }
 
@@ -981,6 +994,8 @@ int b200ns_plan_add_attention(b200ns_plan* p, const b200ns_attn_desc* d) {
   if ((o.head_dim != 64 || cross || d->scale > 0.f) && (!o.vrow || o.variant != 3))
     return fail("attention: padded head dims / cross-attention / custom scale need the row-major-V v3 kernel");
   if (o.head_dim != 64) o.KT = 64;
+  o.alias = (attn_alias() && o.head_dim == 64 && !cross && o.vrow && o.variant == 3 && d->L >= 256) ? 1 : 0;
+  if (o.alias) o.KT = 64;
   if (cross) {
     if (d->kv_rows <= 0 || d->kv_rows % 128 || d->kv_len <= 0 || d->kv_len > d->kv_rows || d->kv_div <= 0 || d->kv_batch <= 0)
       return fail("attention: cross-attention needs kv_rows % 128 == 0, 0 < kv_len <= kv_rows, kv_div > 0, kv_batch > 0");

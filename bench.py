@@ -199,7 +199,7 @@ def run_b200(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         x, rec = eps_greedy_search(net, None, labels, params, table, precomputed_noise=noise, shard=shard,
-                                   step_indices=steps_idx, x_init=x_init, on_step=on_step)
+                                   step_indices=steps_idx, x_init=x_init, on_step=on_step, prefetch=bool(args.prefetch))
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -220,8 +220,20 @@ def run_b200(args):
     # ---- end-to-end run: host (pinned) noise in, per-step results out
     results = []
 
+    # per-step results land in pinned host buffers (asynchronous device->host copies in stream order, like the
+    # host->device noise copies); the timed region ends with a synchronize, so every byte has arrived inside it
+    pinned = [(torch.empty(1, dtype=torch.int64).pin_memory(), torch.empty(1, dtype=torch.float32).pin_memory(),
+               torch.empty(x0.shape, dtype=torch.float64).pin_memory()) for _ in range(total)]
+
     def read_back(i, x_next, idx, scores):
-        results.append((idx.cpu(), scores.max().cpu(), x_next.cpu()))
+        if not args.async_readback:
+            results.append((idx.cpu(), scores.max().cpu(), x_next.cpu()))
+            return
+        bi, bs, bx = pinned[len(results) % total]
+        bi.copy_(idx, non_blocking=True)
+        bs.copy_(scores.max().reshape(1), non_blocking=True)
+        bx.copy_(x_next, non_blocking=True)
+        results.append((bi, bs, bx))
 
     _, xe, _ = timed(host, order[:args.warmup], x0, read_back)
     ms_e2e, xe, _ = timed(host, order[args.warmup:], xe, read_back)
@@ -299,6 +311,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', type=str, default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--prefetch', type=int, default=1, help='e2e: stage the next step\'s host noise on a side stream')
+    ap.add_argument('--async-readback', type=int, default=1, help='e2e: per-step results into pinned buffers, asynchronously')
     ap.add_argument('--scorer', type=str, default='brightness', choices=['brightness', 'imagenet', 'compressibility'],
                     help='brightness = BASELINE.json configs[1] (the headline); imagenet = configs[3]')
     args = ap.parse_args()

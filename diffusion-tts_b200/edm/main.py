@@ -109,13 +109,70 @@ def _scale_table(num_steps: int, K: int, N: int, lam: float) -> torch.Tensor:
     return (torch.ones_like(seeds, dtype=torch.float32) * seeds.to(torch.float32)) * torch.tensor(lam).to(torch.float32)
 
 
+class _NoiseStager:
+    """Host -> device staging of precomputed noise ONE round ahead on a side stream, so that the (pinned) host buffers of
+    round r+1 cross PCIe underneath the network evaluations of round r.  Two persistent device buffers per tensor kind are
+    reused alternately (no allocator traffic, nothing to defer-free across streams): round r+1 is staged into the buffer
+    round r-1 used, after an event on the compute stream that follows all of round r-1's work.  Only host-resident fp64
+    tensors are staged; everything else falls through to the caller's own path."""
+
+    def __init__(self, pre: Optional[Dict], device, lo: int, hi: int, enabled: bool = True):
+        self.pre, self.device, self.lo, self.hi = pre, device, lo, hi
+        self.enabled = bool(enabled) and pre is not None and torch.device(device).type == 'cuda'
+        self.stream = torch.cuda.Stream(device=device) if self.enabled else None
+        self.bufs: Dict[Any, torch.Tensor] = {}
+        self.staged: Dict[Any, Any] = {}
+        self.round = 0
+
+    def _host(self, key):
+        t = self.pre.get(key) if self.pre is not None else None
+        return t if (torch.is_tensor(t) and not t.is_cuda and t.dtype == torch.float64) else None
+
+    def prefetch(self, i, k: int):
+        if not self.enabled or i is None:
+            return
+        self.round += 1
+        main = torch.cuda.current_stream(self.device)
+        fence = torch.cuda.Event()
+        fence.record(main)                       # everything enqueued so far (incl. the round that last used the buffer)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(fence)
+            for key in ((f'pivot_{i}',) if k == 0 else ()) + ((i, k),):
+                if key in self.staged:
+                    continue
+                src = self._host(key[0] if isinstance(key, tuple) else key)
+                if src is None:
+                    continue
+                if isinstance(key, tuple):
+                    if k >= src.shape[1] or self.hi > src.shape[2]:
+                        continue
+                    src = src[:, k, self.lo:self.hi]
+                slot = ('dir' if isinstance(key, tuple) else 'pivot', self.round & 1, tuple(src.shape))
+                if slot not in self.bufs:
+                    self.bufs[slot] = torch.empty(src.shape, dtype=torch.float64, device=self.device)
+                dst = self.bufs[slot]
+                dst.copy_(src, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+                self.staged[key] = (dst, ev)
+
+    def take(self, key):
+        """The staged device copy of `key` (made visible to the current stream), or None."""
+        item = self.staged.pop(key, None)
+        if item is None:
+            return None
+        dst, ev = item
+        torch.cuda.current_stream(self.device).wait_event(ev)
+        return dst
+
+
 @torch.no_grad()
 def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: SamplingParams, table: StepTable, *,
                       precomputed_noise: Optional[Dict] = None, shard: Optional[Shard] = None, record: bool = False,
                       norm_mode: str = 'kernel', scale_table: Optional[torch.Tensor] = None,
                       teacher_x: Optional[List[torch.Tensor]] = None, step_indices: Optional[List[int]] = None,
                       x_init: Optional[torch.Tensor] = None, on_step=None,
-                      commit: str = 'reuse', mirror_rng: bool = True) -> (torch.Tensor, SearchRecord):
+                      commit: str = 'reuse', mirror_rng: bool = True, prefetch: bool = False) -> (torch.Tensor, SearchRecord):
     """ZERO_ORDER == EPS_GREEDY branch (edm/main.py:714-860).
 
     Extras over the reference (all optional): `shard` (candidate sharding over ranks), `record`,
@@ -123,6 +180,12 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
     calls), `teacher_x` (force the committed state per step; parity tests), `step_indices` / `x_init`
     (run a sub-sequence of steps from a given state; benchmarks), `on_step(i, x_next, idx, scores)`
     (called after every committed step, e.g. to read results back to the host).
+
+    `prefetch`: precomputed noise that lives in (pinned) host memory is staged one round ahead on a side stream, so the
+    host->device copies run underneath the previous round's network evaluations.  Meant for callers whose `on_step` does
+    not synchronise (asynchronous copies into pinned buffers, as bench.py's end-to-end leg does): measured on B200,
+    33.27 -> 32.96 ms per step end to end; with a blocking `on_step` (`.cpu()`) it is counter-productive (42 ms), hence off
+    by default.
 
     `commit`: the reference re-runs `step` on the winning noise at batch b (edm/main.py:860).  All kernels
     here are batch-size and batch-position invariant (fixed reduction orders), so the winner's x_next from
@@ -158,13 +221,22 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
         pass
     else:
         torch.randn_like(x_next)                                          # keeps the RNG stream aligned with :727
-    for i in (step_indices if step_indices is not None else range(num_steps)):
+    seq = list(step_indices) if step_indices is not None else list(range(num_steps))
+    stager = _NoiseStager(pre, device, lo, hi, enabled=prefetch)
+    for pos, i in enumerate(seq):
         x_cur = x_next
         if pre is not None and f'pivot_{i}' in pre:                       # :734-737
-            pivot = pre[f'pivot_{i}'].to(device=device, dtype=torch.float64).contiguous()
+            pivot = stager.take(f'pivot_{i}')
+            if pivot is not None:
+                pivot = pivot.clone()             # the staging buffer is recycled two rounds later; pivots may be recorded
+            else:
+                pivot = pre[f'pivot_{i}'].to(device=device, dtype=torch.float64, non_blocking=True)
+            pivot = pivot.contiguous()
         else:
             pivot = torch.randn_like(x_cur)
         for k in range(K):
+            # next round's host noise starts crossing PCIe now, on the side stream
+            stager.prefetch(*((i, k + 1) if k + 1 < K else (seq[pos + 1] if pos + 1 < len(seq) else None, 0)))
             # ---- candidate construction (:749-800).  RNG calls mirror the reference one for one; the
             # Bernoulli stays on the device (no host sync) unless precomputed noise covers only one of
             # the two branches AND 0 < eps < 1, where the reference's RNG consumption is data dependent.
@@ -202,8 +274,10 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
             # ---- only this rank's candidates [lo, hi) are materialised (1/G of the transfers and of the fp64 passes)
             nl = hi - lo
             if bulk:      # every direction comes from one precomputed tensor: a single (async) transfer of the slice
-                Z = pre[i][:, k, lo:hi].to(device=device, dtype=torch.float64, non_blocking=True).transpose(0, 1).reshape(
-                    nl * b, *pivot.shape[1:]).contiguous()
+                Z = stager.take((i, k))
+                if Z is None:
+                    Z = pre[i][:, k, lo:hi].to(device=device, dtype=torch.float64, non_blocking=True)
+                Z = Z.transpose(0, 1).reshape(nl * b, *pivot.shape[1:]).contiguous()
                 ZF = Z if eps_p <= 0 else torch.stack([pre[f'fresh_{i}_{k}_{n}'].to(device=device, dtype=torch.float64)
                                                        for n in range(lo, hi)]).reshape(nl * b, *pivot.shape[1:]).contiguous()
             else:

@@ -249,3 +249,26 @@ def test_search_with_mirrored_rng_is_identical(pkg):
     assert all(torch.equal(a, b) for a, b in zip(out[True][2], out[False][2]))
     assert torch.equal(out[True][0], out[False][0])
     assert torch.equal(out[True][3], out[False][3])
+
+
+def test_host_noise_prefetch_is_identical(pkg):
+    """Precomputed noise living in (pinned) HOST memory: staging round r+1 on a side stream while round r computes gives
+    the same bits as the in-order copies, and the same as device-resident noise."""
+    den, em, sc = pkg
+    g = load_golden('search_eps_greedy_tiny.pt')
+    onet, spec, sd = oracle_net(g['cfg'], g['seed'])
+    latents, labels, pre = search_inputs(g)
+    net = den.B200Denoiser(sd, device='cuda')
+    table = den.StepTable(net, 'cuda', g['num_steps'], **g['sampler_kw'])
+    params = em.SamplingParams(N=g['N'], K=g['K'], eps=0.0, lambda_param=g['lambda_param'], scorer=sc.BrightnessScorer())
+    host = {k: v.clone().pin_memory() for k, v in pre.items()}
+    out = []
+    for noise, pf in ((host, True), (host, False), ({k: v.cuda() for k, v in pre.items()}, True)):
+        x, rec = em.eps_greedy_search(net, latents.cuda(), labels.cuda(), params, table, precomputed_noise=noise,
+                                      record=True, prefetch=pf)
+        torch.cuda.synchronize()
+        out.append((x.cpu(), [t.cpu() for t in rec.indices], [t.cpu() for t in rec.scores]))
+    for o in out[1:]:
+        assert torch.equal(o[0], out[0][0])
+        assert all(torch.equal(a, b) for a, b in zip(o[1], out[0][1]))
+        assert all(torch.equal(a, b) for a, b in zip(o[2], out[0][2]))

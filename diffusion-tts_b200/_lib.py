@@ -99,6 +99,9 @@ SIGNATURES = {
     'b200ns_plan_add_geglu': (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i32]),
     'b200ns_plan_add_upsample2x': (C.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32]),
     'b200ns_ddim_cfg_step': (C.c_int, [c_vp] * 6 + [c_i64, c_i32, c_i32, c_i32] + [c_f32] * 6 + [c_vp]),
+    'b200ns_plan_add_softmax_rows': (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i32, c_f32]),
+    'b200ns_post_quant': (C.c_int, [c_vp] * 4 + [c_i32, c_i32, c_i32, c_vp]),
+    'b200ns_image_sums': (C.c_int, [c_vp] * 3 + [c_i64, c_i32, c_i32, c_vp]),
     'b200ns_sd_candidates': (C.c_int, [c_vp] * 5 + [c_i64, c_i64, c_f32, c_f32, c_vp]),
     'b200ns_ddim_x0_score': (C.c_int, [c_vp] * 6 + [c_i64, c_i32, c_i32] + [c_f32] * 3 + [c_vp]),
 }

@@ -194,3 +194,43 @@ def sd_unet_param_shapes(in_channels=4, out_channels=4, block_out_channels: Sequ
     shp['conv_norm_out.weight'] = shp['conv_norm_out.bias'] = (boc[0],)
     shp['conv_out.weight'], shp['conv_out.bias'] = (out_channels, boc[0], 3, 3), (out_channels,)
     return shp
+
+
+def vae_decoder_param_shapes(latent_channels=4, out_channels=3, block_out_channels: Sequence[int] = (128, 256, 512, 512),
+                             layers_per_block=2) -> Dict[str, Tuple[int, ...]]:
+    """Parameter inventory of the decode half of the SD `AutoencoderKL` (`post_quant_conv` + `decoder.*`): names and shapes
+    as the vendored diffusers registers them (sd/diffusers/src/diffusers/models/autoencoders/autoencoder_kl.py:100-130,
+    vae.py Decoder :204-290, unet_2d_blocks.py UNetMidBlock2D / UpDecoderBlock2D, resnet.py ResnetBlock2D with temb=None,
+    attention_processor.py Attention with one head).  tests/golden/sd_vae_shapes.json pins this against the reference."""
+    boc = list(block_out_channels)
+    shp: Dict[str, Tuple[int, ...]] = {'post_quant_conv.weight': (latent_channels, latent_channels, 1, 1),
+                                       'post_quant_conv.bias': (latent_channels,)}
+    top = boc[-1]
+    shp['decoder.conv_in.weight'], shp['decoder.conv_in.bias'] = (top, latent_channels, 3, 3), (top,)
+
+    def resnet(p, cin, cout):
+        shp[f'{p}.norm1.weight'], shp[f'{p}.norm1.bias'] = (cin,), (cin,)
+        shp[f'{p}.conv1.weight'], shp[f'{p}.conv1.bias'] = (cout, cin, 3, 3), (cout,)
+        shp[f'{p}.norm2.weight'], shp[f'{p}.norm2.bias'] = (cout,), (cout,)
+        shp[f'{p}.conv2.weight'], shp[f'{p}.conv2.bias'] = (cout, cout, 3, 3), (cout,)
+        if cin != cout:
+            shp[f'{p}.conv_shortcut.weight'], shp[f'{p}.conv_shortcut.bias'] = (cout, cin, 1, 1), (cout,)
+
+    a = 'decoder.mid_block.attentions.0'
+    shp[f'{a}.group_norm.weight'], shp[f'{a}.group_norm.bias'] = (top,), (top,)
+    for nm in ('to_q', 'to_k', 'to_v', 'to_out.0'):
+        shp[f'{a}.{nm}.weight'], shp[f'{a}.{nm}.bias'] = (top, top), (top,)
+    resnet('decoder.mid_block.resnets.0', top, top)
+    resnet('decoder.mid_block.resnets.1', top, top)
+    rev = boc[::-1]
+    cin = rev[0]
+    for i, cout in enumerate(rev):
+        for j in range(layers_per_block + 1):
+            resnet(f'decoder.up_blocks.{i}.resnets.{j}', cin if j == 0 else cout, cout)
+        if i != len(rev) - 1:
+            shp[f'decoder.up_blocks.{i}.upsamplers.0.conv.weight'] = (cout, cout, 3, 3)
+            shp[f'decoder.up_blocks.{i}.upsamplers.0.conv.bias'] = (cout,)
+        cin = cout
+    shp['decoder.conv_norm_out.weight'], shp['decoder.conv_norm_out.bias'] = (boc[0],), (boc[0],)
+    shp['decoder.conv_out.weight'], shp['decoder.conv_out.bias'] = (out_channels, boc[0], 3, 3), (out_channels,)
+    return shp

@@ -18,6 +18,7 @@
 #include "jpeg.cuh"
 #include "sampler.cuh"
 #include "sdops.cuh"
+#include "vae.cuh"
 
 using namespace b200;
 
@@ -152,7 +153,7 @@ int make_tmap_2d_ld(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t ro
 
 // ------------------------------------------------------------------ plan ops
 enum OpKind { OP_GEMM, OP_GN_STATS, OP_GN_APPLY, OP_GN_FINALIZE, OP_ATTN, OP_LINEAR, OP_IM2COL, OP_U8F32, OP_POOL_TOKENS, OP_POOL_ATTN,
-              OP_SOFTMAX_GATHER, OP_LAYERNORM, OP_GEGLU, OP_UPSAMPLE2X };
+              OP_SOFTMAX_GATHER, OP_LAYERNORM, OP_GEGLU, OP_UPSAMPLE2X, OP_SOFTMAX_ROWS };
 
 struct GemmOp {
   CUtensorMap tmA[3], tmB, tmO, tmR;
@@ -420,6 +421,12 @@ int run_op(const Op& op, cudaStream_t st) {
       launch_pdl(geglu_kernel, dim3(grid_for(op.misc.n * (op.misc.i0 / 8), 256, 148 * 32)), dim3(256), 0, st,
                  reinterpret_cast<const __nv_bfloat16*>(op.misc.p0), reinterpret_cast<__nv_bfloat16*>(op.misc.p2), op.misc.n, op.misc.i0);
       CK_LAUNCH("geglu_kernel");
+      return 0;
+    case OP_SOFTMAX_ROWS:
+      softmax_rows_kernel<<<static_cast<unsigned>(op.misc.n), 256, 0, st>>>(reinterpret_cast<const float*>(op.misc.p0),
+                                                                             reinterpret_cast<__nv_bfloat16*>(op.misc.p2),
+                                                                             op.misc.i0, op.misc.f0);
+      CK_LAUNCH("softmax_rows_kernel");
       return 0;
     case OP_UPSAMPLE2X:
       launch_pdl(upsample2x_kernel, dim3(grid_for(static_cast<int64_t>(op.misc.i0) * op.misc.i1 * op.misc.i2 * 4 * (op.misc.n / 8), 256, 148 * 32)),
@@ -752,11 +759,14 @@ static int add_gemm_part(b200ns_plan* p, const b200ns_gemm_desc* d, int BN_force
   GemmOp& g = op.gemm;
   GemmArgs& a = g.args;
   const int H = d->H, W = d->W;
-  if (W <= 0 || W > 128 || 128 % W) return fail("gemm: W must divide 128");
-  int tileH = 128 / W;
+  if (W <= 0 || (W <= 128 ? 128 % W : W % 128)) return fail("gemm: W must divide 128 or be a multiple of 128");
+  const int x_chunks = W > 128 ? W / 128 : 1;      // rows wider than a tile: 128 consecutive pixels of one row per tile
+  const int boxW = W > 128 ? 128 : W;
+  int tileH = 128 / boxW;
   if (tileH > H) tileH = H;
   if (H % tileH) return fail("gemm: H not a multiple of the tile height");
-  const int tileN = 128 / (W * tileH);
+  const int tileN = 128 / (boxW * tileH);
+  a.x_chunks = x_chunks;
   a.H = H;
   a.W = W;
   a.tileH = tileH;
@@ -828,10 +838,10 @@ static int add_gemm_part(b200ns_plan* p, const b200ns_gemm_desc* d, int BN_force
     const int ch = used ? d->a_channels[i] : d->a_channels[0];
     const int sdn = (used ? d->a_stride[i] : d->a_stride[0]) == 2 ? 2 : 1;      // 2: this source is read with stride 2
     if (ch % 64) return fail("gemm: activation channels must be a multiple of 64");
-    if (W * sdn > 256 || tileH * sdn > 256) return fail("gemm: strided box exceeds 256 elements");
+    if (boxW * sdn > 256 || tileH * sdn > 256) return fail("gemm: strided box exceeds 256 elements");
     const uint64_t dims[4] = {static_cast<uint64_t>(ch), static_cast<uint64_t>(W) * sdn, static_cast<uint64_t>(H) * sdn,
                               static_cast<uint64_t>(d->batch)};
-    const uint32_t box[4] = {64, static_cast<uint32_t>(W * sdn), static_cast<uint32_t>(tileH * sdn),
+    const uint32_t box[4] = {64, static_cast<uint32_t>(boxW * sdn), static_cast<uint32_t>(tileH * sdn),
                              static_cast<uint32_t>(tileN)};
     const uint32_t es[4] = {1, static_cast<uint32_t>(sdn), static_cast<uint32_t>(sdn), 1};
     int rc = make_tmap(&g.tmA[i], ptr, 4, dims, box, es);
@@ -1123,6 +1133,39 @@ int b200ns_plan_add_layernorm(b200ns_plan* p, const void* x, const float* gamma,
   op.misc.i0 = C;
   op.misc.f0 = eps;
   p->push(op);
+  return 0;
+}
+
+int b200ns_plan_add_softmax_rows(b200ns_plan* p, const float* S, void* P, int64_t rows, int32_t L, float scale) {
+  if (L % 8 || L > 8192 || rows <= 0) return fail("softmax_rows: L must be a multiple of 8 and <= 8192");
+  Op op;
+  op.kind = OP_SOFTMAX_ROWS;
+  op.misc.p0 = S;
+  op.misc.p2 = P;
+  op.misc.n = rows;
+  op.misc.i0 = L;
+  op.misc.f0 = scale * 1.4426950408889634f;
+  p->push(op);
+  return 0;
+}
+
+int b200ns_post_quant(const float* x, const float* w, const float* bias, float* out, int32_t B, int32_t C, int32_t HW,
+                      void* stream) {
+  if (C < 1 || C > 8) return fail("post_quant: 1 <= C <= 8");
+  post_quant_kernel<<<grid_for(static_cast<int64_t>(B) * HW, 256), 256, 0, S(stream)>>>(x, w, bias, out, B, C, HW);
+  CK_LAUNCH("post_quant_kernel");
+  return 0;
+}
+
+int b200ns_image_sums(const float* img, uint32_t* chan_sums, uint8_t* u8, int64_t B, int32_t C, int32_t HW, void* stream) {
+  if (C < 1 || C > 4 || B > 65535) return fail("image_sums: 1 <= C <= 4, B <= 65535");
+  CK(cudaMemsetAsync(chan_sums, 0, sizeof(uint32_t) * 4 * B, S(stream)));
+  int chunks = static_cast<int>((4 * 148 + B - 1) / B);
+  const int max_chunks = (HW + 255) / 256;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  image_sums_kernel<<<dim3(chunks, static_cast<unsigned>(B)), 256, 0, S(stream)>>>(img, chan_sums, u8, C, HW);
+  CK_LAUNCH("image_sums_kernel");
   return 0;
 }
 

@@ -40,6 +40,7 @@ struct GemmArgs {
   int H, W;                      // spatial dims
   int tileH, tileN;              // box = [tileN][tileH][W] pixels = 128 rows
   int tiles_per_img;             // H*W/128 (0 if an image is smaller than a tile)
+  int x_chunks;                  // W/128 when a row is wider than a tile (VAE decoder, W = 256 / 512): tile = 128 pixels of ONE row
   int m_tiles, n_tiles;
   const float* bias;
   const __nv_bfloat16* residual;
@@ -87,10 +88,12 @@ DEVINL void gemm_producer(const CUtensorMap& tmA0, const CUtensorMap& tmA1, cons
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int tl = a.reverse ? num_tiles - 1 - tile : tile;
     const int mt = tl / a.n_tiles, nt = tl % a.n_tiles;
-    int n0, y0;
+    int n0, y0, x0 = 0;
     if (a.tiles_per_img > 0) {
       n0 = mt / a.tiles_per_img;
-      y0 = (mt % a.tiles_per_img) * a.tileH;
+      const int r = mt % a.tiles_per_img;
+      y0 = (r / a.x_chunks) * a.tileH;
+      x0 = (r % a.x_chunks) * 128;
     } else {
       n0 = mt * a.tileN;
       y0 = 0;
@@ -106,7 +109,7 @@ DEVINL void gemm_producer(const CUtensorMap& tmA0, const CUtensorMap& tmA1, cons
         for (int cb = 0; cb < sg.cblocks; ++cb, ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_4d(smem_a + stage * Cfg::A_BYTES, tm, &full_bar[stage], sg.cstart + cb * 64, dx, y0 * sdn + dy, n0);
+          tma_load_4d(smem_a + stage * Cfg::A_BYTES, tm, &full_bar[stage], sg.cstart + cb * 64, x0 * sdn + dx, y0 * sdn + dy, n0);
           tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * 64, nt * BN);
           if (++stage == STAGES) {
             stage = 0;

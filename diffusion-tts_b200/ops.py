@@ -215,6 +215,30 @@ def sd_candidates(pivot: torch.Tensor, dirs: torch.Tensor, scale: torch.Tensor, 
     return cand
 
 
+def post_quant(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """1x1 conv C -> C on fp32 NCHW latents (AutoencoderKL.post_quant_conv)."""
+    _chk_cuda(x, w, bias, out)
+    _c(x, torch.float32), _c(w, torch.float32), _c(bias, torch.float32)
+    B, Cc = x.shape[0], x.shape[1]
+    out = torch.empty_like(x) if out is None else _c(out, torch.float32)
+    L.check(L.lib().b200ns_post_quant(L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(out), B, Cc, x[0, 0].numel(), L.cur_stream()),
+            'post_quant')
+    _count()
+    return out
+
+
+def image_sums(img: torch.Tensor, want_u8: bool = False):
+    """img fp32 NHWC [B,H,W,C<=4] -> (integer channel sums int32 [B,4] of the uint8 quantisation, uint8 NCHW image or None)."""
+    _chk_cuda(img)
+    _c(img, torch.float32)
+    B, H, W_, Cc = img.shape
+    sums = torch.empty((B, 4), dtype=torch.int32, device=img.device)
+    u8 = torch.empty((B, Cc, H, W_), dtype=torch.uint8, device=img.device) if want_u8 else None
+    L.check(L.lib().b200ns_image_sums(L.ptr(img), L.ptr(sums), L.ptr(u8), B, Cc, H * W_, L.cur_stream()), 'image_sums')
+    _count()
+    return sums, u8
+
+
 def interleave_geglu(t: torch.Tensor) -> torch.Tensor:
     """Rows [hidden (F) ; gate (F)] of a GEGLU projection (weight [2F, K] or bias [2F]) -> groups of
     [64 hidden | 64 gate] rows, the order the fused GEGLU epilogue of the GEMM expects.  F % 64 == 0."""
@@ -452,6 +476,14 @@ class Plan:
         L.check(L.lib().b200ns_plan_add_geglu(self._h, L.ptr(_c(x, torch.bfloat16)), L.ptr(_c(out, torch.bfloat16)),
                                               out.numel() // F_, F_), 'plan_add_geglu')
         self._misc('geglu', label)
+
+    def add_softmax_rows(self, S: torch.Tensor, P: torch.Tensor, scale: float, label='softmax'):
+        """S fp32 [rows, L] -> P bf16 [rows, L] = softmax(scale * S) over the last axis."""
+        self._k(S, P)
+        rows, L_ = S.shape[-2] * (S.numel() // (S.shape[-1] * S.shape[-2])), S.shape[-1]
+        L.check(L.lib().b200ns_plan_add_softmax_rows(self._h, L.ptr(_c(S, torch.float32)), L.ptr(_c(P, torch.bfloat16)), rows, L_,
+                                                     float(scale)), 'plan_add_softmax_rows')
+        self._misc('softmax_rows', label)
 
     def add_upsample2x(self, x: torch.Tensor, out: torch.Tensor, label='upsample2x'):
         B, H, W_, Cc = x.shape

@@ -293,6 +293,17 @@ int b200ns_plan_add_layernorm(b200ns_plan* p, const void* x, const float* gamma,
                               int32_t C, float eps);
 /* GEGLU (activations.py:117-123): in bf16 [rows, 2F] = [hidden | gate] -> out bf16 [rows, F] = hidden * gelu_erf(gate). */
 int b200ns_plan_add_geglu(b200ns_plan* p, const void* in, void* out, int64_t rows, int32_t F);
+
+/* --- SD VAE decoder (AutoencoderKL.decode, autoencoder_kl.py:287-320; vae.py Decoder) ---------------
+ * Row softmax of the unfused mid-block attention (one head of dimension 512, attention_processor.py AttnProcessor2_0):
+ * P[r, :] = softmax(scale * S[r, :]), fp32 [rows, L] -> bf16 [rows, L]. */
+int b200ns_plan_add_softmax_rows(b200ns_plan* p, const float* S, void* P, int64_t rows, int32_t L, float scale);
+/* post_quant_conv (1x1, C -> C, C <= 8) on fp32 NCHW latents [B, C, HW]; w [C, C], bias [C]. */
+int b200ns_post_quant(const float* x, const float* w, const float* bias, float* out, int32_t B, int32_t C, int32_t HW,
+                      void* stream);
+/* Decoded image fp32 NHWC [B, HW, C] -> uint8 = trunc(clip(x*127.5+128, 0, 255)) (pipeline_stable_diffusion.py:1115):
+ * integer channel sums chan_sums [B, 4] (feed b200ns_brightness_from_sums) and, if u8 != NULL, the uint8 NCHW image. */
+int b200ns_image_sums(const float* img, uint32_t* chan_sums, uint8_t* u8, int64_t B, int32_t C, int32_t HW, void* stream);
 /* F.interpolate(scale_factor=2, mode="nearest") on bf16 NHWC (upsampling.py Upsample2D.forward). */
 int b200ns_plan_add_upsample2x(b200ns_plan* p, const void* in, void* out, int32_t batch, int32_t H, int32_t W, int32_t C);
 

@@ -277,3 +277,60 @@ def eps_greedy_search(unet: Callable, tab: DDIMTable, latents: torch.Tensor, ctx
     if max_score is None:                                                          # :1469-1474
         max_score = float(score_fn(x))
     return x, max_score
+
+
+# ---------------------------------------------------------------------------------------------- VAE decode
+def vae_decode(sd: Dict[str, torch.Tensor], z: torch.Tensor, taps: Optional[dict] = None, groups: int = 32) -> torch.Tensor:
+    """AutoencoderKL._decode (autoencoder_kl.py:287-298) = post_quant_conv + Decoder.forward (vae.py:291-340):
+    conv_in -> UNetMidBlock2D (resnet, one-head attention, resnet) -> UpDecoderBlock2D x n (resnets, nearest x2 + conv)
+    -> GroupNorm(eps 1e-6) -> SiLU -> conv_out.  z [B,4,h,w] (already divided by scaling_factor) -> image [B,3,8h,8w]."""
+    def tap(name, t):
+        if taps is not None:
+            taps[name] = t
+        return t
+
+    def resnet(p, x):                                          # resnet.py ResnetBlock2D.forward, temb = None
+        h = F.silu(F.group_norm(x, groups, sd[f'{p}.norm1.weight'], sd[f'{p}.norm1.bias'], 1e-6))
+        h = F.conv2d(h, sd[f'{p}.conv1.weight'], sd[f'{p}.conv1.bias'], padding=1)
+        h = F.silu(F.group_norm(h, groups, sd[f'{p}.norm2.weight'], sd[f'{p}.norm2.bias'], 1e-6))
+        h = F.conv2d(h, sd[f'{p}.conv2.weight'], sd[f'{p}.conv2.bias'], padding=1)
+        if f'{p}.conv_shortcut.weight' in sd:
+            x = F.conv2d(x, sd[f'{p}.conv_shortcut.weight'], sd[f'{p}.conv_shortcut.bias'])
+        return tap(p, x + h)                                   # output_scale_factor = 1
+
+    def attention(p, x):                                       # attention_processor.py AttnProcessor2_0, heads = 1
+        B, C, H, W = x.shape
+        t = x.view(B, C, H * W)
+        t = F.group_norm(t, groups, sd[f'{p}.group_norm.weight'], sd[f'{p}.group_norm.bias'], 1e-6).transpose(1, 2)
+        q = F.linear(t, sd[f'{p}.to_q.weight'], sd[f'{p}.to_q.bias'])
+        k = F.linear(t, sd[f'{p}.to_k.weight'], sd[f'{p}.to_k.bias'])
+        v = F.linear(t, sd[f'{p}.to_v.weight'], sd[f'{p}.to_v.bias'])
+        o = F.scaled_dot_product_attention(q[:, None], k[:, None], v[:, None])[:, 0]
+        o = F.linear(o, sd[f'{p}.to_out.0.weight'], sd[f'{p}.to_out.0.bias'])
+        return tap(p, o.transpose(1, 2).reshape(B, C, H, W) + x)      # residual_connection, rescale_output_factor = 1
+
+    z = F.conv2d(z, sd['post_quant_conv.weight'], sd['post_quant_conv.bias'])
+    h = tap('decoder.conv_in', F.conv2d(z, sd['decoder.conv_in.weight'], sd['decoder.conv_in.bias'], padding=1))
+    h = resnet('decoder.mid_block.resnets.0', h)
+    h = attention('decoder.mid_block.attentions.0', h)
+    h = resnet('decoder.mid_block.resnets.1', h)
+    i = 0
+    while f'decoder.up_blocks.{i}.resnets.0.norm1.weight' in sd:
+        j = 0
+        while f'decoder.up_blocks.{i}.resnets.{j}.norm1.weight' in sd:
+            h = resnet(f'decoder.up_blocks.{i}.resnets.{j}', h)
+            j += 1
+        p = f'decoder.up_blocks.{i}.upsamplers.0.conv'
+        if f'{p}.weight' in sd:                                # upsampling.py Upsample2D: nearest x2, then conv
+            h = F.interpolate(h, scale_factor=2.0, mode='nearest')
+            h = tap(p, F.conv2d(h, sd[f'{p}.weight'], sd[f'{p}.bias'], padding=1))
+        i += 1
+    h = F.silu(F.group_norm(h, groups, sd['decoder.conv_norm_out.weight'], sd['decoder.conv_norm_out.bias'], 1e-6))
+    return F.conv2d(h, sd['decoder.conv_out.weight'], sd['decoder.conv_out.bias'], padding=1)
+
+
+def image_brightness(image: torch.Tensor) -> torch.Tensor:
+    """pipeline...:1115 quantisation of the decoded image, then BrightnessScorer's RGB branch (sd/scorers.py:43-64)."""
+    u8 = (image * 127.5 + 128).clip(0, 255).to(torch.uint8)
+    w = torch.tensor([0.2126, 0.7152, 0.0722]).view(1, 3, 1, 1)
+    return ((u8.float() / 255.0) * w).sum(dim=1).mean(dim=(1, 2)).clamp(0, 1)

@@ -5,11 +5,13 @@ The reference drives the SD backend as
 (main.py:135-141; StableDiffusionPipeline.__call__, pipeline_stable_diffusion.py:785-816, returns `(out, score)` :1485).
 `B200LatentBeamPipeline.__call__` keeps that call shape for `method="beam"` and runs the search on the B200 engine
 (`sd_beam_search`).  What is deliberately different, all forced by config 5 / the offline setting:
-  * scoring happens in latent space on the Tweedie x0 (config 5: "brightness scorer on Tweedie x0"): `decode` is the
-    identity unless a decoder is injected (VAE decode in the loop is SURVEY.md 8 f1, not built);
+  * without a VAE, scoring happens in latent space on the Tweedie x0 (config 5: "brightness scorer on Tweedie x0");
+    with `vae_state_dict` every candidate's x0 is decoded to an image on the B200 VAE engine (vae.py) and
+    the image is scored, as the reference does (pipeline_stable_diffusion.py:1111-1123);
   * the CLIP text encoder's weights are unreachable offline: `encode_prompt` is injectable, and the default produces a
     deterministic pseudo-embedding pair [uncond, cond] of the right shape from the prompt string;
-  * `out.images` is a visualisation of the first three latent channels (no VAE); `out.latents` is the real result.
+  * `out.images` is the decoded image when a VAE is given, else a visualisation of the first three latent channels;
+    `out.latents` is the search result itself.
 `method` = beam (sd/beam.py), eps_greedy / zero_order / naive (sd/search.py; 'rejection' is the naive loop, repeated by
 main.py like the reference's main.py:131); mcts raises NotImplementedError (8 f4).
 """
@@ -37,7 +39,8 @@ def pseudo_prompt_embeddings(prompt: str, negative_prompt: str = '', tokens: int
 
 class B200LatentBeamPipeline:
     def __init__(self, unet_state_dict: Dict[str, torch.Tensor], device='cuda', encode_prompt: Optional[Callable] = None,
-                 decode: Optional[Callable] = None, shard=None):
+                 decode: Optional[Callable] = None, shard=None, vae_state_dict: Optional[Dict[str, torch.Tensor]] = None,
+                 vae_chunk: int = 16):
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise RuntimeError('B200LatentBeamPipeline runs on a B200 only (no CPU fallback)')
@@ -45,6 +48,11 @@ class B200LatentBeamPipeline:
         self.encode_prompt = encode_prompt or (lambda p, n='': pseudo_prompt_embeddings(p, n, dim=self.unet.cfg['cross_attention_dim']))
         self.decode = decode
         self.shard = shard
+        self.vae = None
+        if vae_state_dict is not None:
+            from ..vae import VAEDecoderEngine
+            self.vae = VAEDecoderEngine(vae_state_dict, device=self.device)
+        self.vae_chunk = vae_chunk
 
     @torch.no_grad()
     def __call__(self, prompt: str, num_inference_steps: int = 50, score_function: Optional[Callable] = None,
@@ -65,7 +73,11 @@ class B200LatentBeamPipeline:
         table = DDIMTable(num_inference_steps)
         fused = self.decode is None and (score_function is None or getattr(score_function, 'latent_fused', False))
         kw = dict(guidance_scale=guidance_scale, shard=self.shard)
-        if not fused:
+        if self.vae is not None and self.decode is None:      # decode + quantise + score every candidate's x0 (:1111-1123)
+            from ..vae import DecodedImageScorer
+            kw['decode'] = lambda x0: x0
+            kw['scorer'] = DecodedImageScorer(self.vae, score_function, prompt, self.vae_chunk)
+        elif not fused:
             kw['decode'] = self.decode or (lambda x0: (x0 * 127.5 + 128).clip(0, 255).to(torch.uint8))    # :1115
             kw['scorer'] = lambda im: score_function(im, [prompt] * im.shape[0], torch.zeros(im.shape[0], device=im.device))
         if method == 'beam':
@@ -78,6 +90,10 @@ class B200LatentBeamPipeline:
                                              float(params.get('lambda', 0.15)), float(params.get('eps', 0.4)), m, **kw)
             score = float(rec.max_score)
         from PIL import Image
-        vis = (best[0, :3] * 127.5 + 128).clip(0, 255).to(torch.uint8).permute(1, 2, 0).cpu().numpy()
+        if self.vae is not None:
+            img = self.vae.decode_latents(best)[0]                                                  # fp32 [H, W, 3]
+            vis = (img * 127.5 + 128).clip(0, 255).to(torch.uint8).cpu().numpy()
+        else:
+            vis = (best[0, :3] * 127.5 + 128).clip(0, 255).to(torch.uint8).permute(1, 2, 0).cpu().numpy()
         out = SimpleNamespace(images=[Image.fromarray(vis, 'RGB')], latents=best, record=rec)
         return out, score

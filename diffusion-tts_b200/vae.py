@@ -245,3 +245,33 @@ class VAEDecoderEngine:
 
     def decode_latents(self, latents: torch.Tensor) -> torch.Tensor:
         return self.decode(latents.to(torch.float32) / self.scaling_factor)
+
+
+class DecodedImageScorer:
+    """`scores = scorer(x0)` for the SD search drivers (`decode` = identity): decodes each candidate's Tweedie x0 to an image
+    (pipeline_stable_diffusion.py:1111-1118: `vae.decode(pred_x0 / scaling_factor)`, `(image*127.5+128).clip(0,255).to(uint8)`)
+    and scores it -- in chunks of `chunk` candidates, so a beam step with hundreds of candidates needs the activations of
+    only `chunk` 512x512 decodes at a time.  `score_function` None or a scorer with `latent_fused` (BrightnessScorer):
+    the RGB luminance comes from exact integer channel sums of the quantised image and no uint8 image is materialised;
+    any other scorer receives `score_function(images_uint8 [M,3,H,W], prompts, timesteps)` like the reference."""
+
+    def __init__(self, vae: VAEDecoderEngine, score_function=None, prompt: str = '', chunk: int = 16):
+        self.vae, self.fn, self.prompt, self.chunk = vae, score_function, prompt, chunk
+        self.fused = score_function is None or getattr(score_function, 'latent_fused', False)
+        self.decoded = 0
+
+    @torch.no_grad()
+    def __call__(self, x0: torch.Tensor) -> torch.Tensor:
+        R = x0.shape[0]
+        out = torch.empty(R, device=x0.device, dtype=torch.float32)
+        for lo in range(0, R, self.chunk):
+            hi = min(R, lo + self.chunk)
+            img = self.vae.decode_latents(x0[lo:hi])
+            sums, u8 = ops.image_sums(img, want_u8=not self.fused)
+            if self.fused:
+                out[lo:hi] = ops.brightness_from_sums(sums, img.shape[3], img.shape[1] * img.shape[2])
+            else:
+                s = self.fn(u8, [self.prompt] * (hi - lo), torch.zeros(hi - lo, device=x0.device))
+                out[lo:hi] = torch.as_tensor(s).to(device=x0.device, dtype=torch.float32).reshape(-1)
+            self.decoded += hi - lo
+        return out

@@ -10,7 +10,8 @@ Differences from the reference CLI, all forced by the offline B200 setting:
   * `--classifier` (new, optional): a local `64x64_classifier.pt` for `--scorer imagenet` (random-init otherwise).
   * `--backend sd` runs `--method beam | eps_greedy | zero_order | naive | rejection` (BASELINE.json config 5 = beam): an SD-1.5-shaped UNet (random-init unless
     `--network` names a state-dict `.pt`), latent-space scoring of the Tweedie x0, pseudo prompt embeddings (the CLIP
-    text encoder and the VAE are unreachable offline).  `--steps` (new) overrides the 50 DDIM steps.
+    text encoder and the VAE are unreachable offline; SURVEY.md 8 f1).  `--steps` (new) overrides the 50 DDIM steps;
+    `--vae PATH|random` (new) decodes every candidate's x0 to a 512x512 image on the B200 VAE engine before scoring.
   * `--scorer clip` and `--method mcts` are not part of the B200 hot path and raise NotImplementedError / ValueError.
 """
 import argparse
@@ -57,7 +58,15 @@ def main_sd(args):
         print('[sd] no --network given: using a random-init SD-1.5-shaped UNet2DConditionModel (859.5M parameters)')
         sd = random_state_dict(sd_unet_param_shapes(), 1234)
     torch.manual_seed(args.seed)
-    pipe = B200LatentBeamPipeline(sd, device=args.device)
+    vae_sd = None
+    if args.vae is not None:        # decode every candidate's Tweedie x0 to an image before scoring, like the reference
+        if args.vae == 'random':
+            from diffusion_tts_b200.arch import vae_decoder_param_shapes
+            print('[sd] --vae random: random-init SD-1.5 AutoencoderKL decoder (49.5M parameters)')
+            vae_sd = random_state_dict(vae_decoder_param_shapes(), 4321)
+        else:
+            vae_sd = torch.load(args.vae, map_location='cpu')
+    pipe = B200LatentBeamPipeline(sd, device=args.device, vae_state_dict=vae_sd)
     params = {'N': args.N, 'lambda': args.lambda_, 'eps': args.eps, 'K': args.K, 'B': args.B, 'S': args.S}
     best_result, best_score = None, float('-inf')
     for _ in range(params['N'] if args.method == 'rejection' else 1):
@@ -91,6 +100,8 @@ def main():
     parser.add_argument('--network', type=str, default=None, help='Local network pickle / .pt bundle')
     parser.add_argument('--classifier', type=str, default=None, help='Local 64x64_classifier.pt for --scorer imagenet')
     parser.add_argument('--steps', type=int, default=None, help='Override the number of sampler steps (sd: 50)')
+    parser.add_argument('--vae', type=str, default=None,
+                        help="sd: AutoencoderKL state-dict .pt (or 'random'): decode each candidate before scoring")
     args = parser.parse_args()
 
     if args.backend == 'sd' and args.scorer == 'imagenet':

@@ -175,6 +175,7 @@ struct GnFinalizeOp {
   GnFinalizeArgs args;
   dim3 grid;
   int n_pairs;
+  int wide;
 };
 struct AttnOp {
   CUtensorMap tmQ, tmK, tmV;
@@ -348,7 +349,10 @@ int run_op(const Op& op, cudaStream_t st) {
       CK_LAUNCH("gn_apply_kernel");
       return 0;
     case OP_GN_FINALIZE:
-      launch_pdl(gn_finalize_kernel, dim3(op.gnf.grid), dim3(256), 0, st, op.gnf.args, op.gnf.n_pairs);
+      if (op.gnf.wide)
+        launch_pdl(gn_finalize_kernel<true>, dim3(op.gnf.n_pairs), dim3(256), 0, st, op.gnf.args, op.gnf.n_pairs);
+      else
+        launch_pdl(gn_finalize_kernel<false>, dim3(op.gnf.grid), dim3(256), 0, st, op.gnf.args, op.gnf.n_pairs);
       CK_LAUNCH("gn_finalize_kernel");
       return 0;
     case OP_ATTN:
@@ -960,6 +964,7 @@ int b200ns_plan_add_gn_finalize(b200ns_plan* p, const b200ns_gn_finalize_desc* d
   a.mean_rstd = reinterpret_cast<float2*>(d->mean_rstd);
   op.gnf.n_pairs = d->groups * d->batch;
   op.gnf.grid = dim3((op.gnf.n_pairs + 7) / 8);
+  op.gnf.wide = static_cast<long long>(a.HW / 64) * a.cpg > 4096 ? 1 : 0;      // a function of the shape only
   p->push(op);
   return 0;
 }

@@ -157,16 +157,26 @@ struct GnFinalizeArgs {
   float2* mean_rstd;       // [batch, groups]
 };
 
-// one warp per (sample, group); 8 warps per block; grid = ceil(batch*groups / 8)
+// WIDE = false: one warp per (sample, group); 8 warps per block; grid = ceil(batch*groups / 8).
+// WIDE = true : one 8-warp CTA per (sample, group) -- each warp reduces a contiguous eighth of the (row, channel) list
+//               and the eight partial sums are combined in warp order: for the VAE decoder's 512x512 activations
+//               (4096 statistics rows per sample) a single warp per pair left the GPU idle (271 us per launch).
+// Which variant runs depends only on the tensor shape, so results stay batch-size and batch-position invariant.
+template <bool WIDE>
 __global__ void __launch_bounds__(256) gn_finalize_kernel(const GnFinalizeArgs a, int n_pairs) {
+  __shared__ double s_part[16];
   pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31;
-  const int pair = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int wid = threadIdx.x >> 5;
+  const int pair = WIDE ? blockIdx.x : blockIdx.x * 8 + wid;
   if (pair >= n_pairs) return;
   const int bi = pair / a.groups, g = pair - bi * a.groups;
   const int R = a.HW >> 6;
-  const int total = R * a.cpg;
+  const int total_all = R * a.cpg;
+  const int chunk = WIDE ? (total_all + 7) / 8 : total_all;
+  const int begin = WIDE ? wid * chunk : 0;
+  const int total = WIDE ? min(total_all, begin + chunk) : total_all;
   double ds = 0.0, dq = 0.0;
   auto fetch = [&](int i, float2& v, double& pa) {
     const int r = i / a.cpg;
@@ -180,7 +190,7 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const GnFinalizeArgs a
     dq += q + 2.0 * pa * s + 64.0 * pa * pa;
     ds += s + 64.0 * pa;
   };
-  int i = lane;
+  int i = begin + lane;
   for (; i + 3 * 32 < total; i += 4 * 32) {       // 4 loads in flight; accumulation order stays fixed
     float2 v0, v1, v2, v3;
     double p0, p1, p2, p3;
@@ -203,6 +213,20 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const GnFinalizeArgs a
   for (int o = 16; o > 0; o >>= 1) {               // butterfly: every lane ends with the same, order-fixed sum
     ds += __shfl_xor_sync(0xffffffffu, ds, o);
     dq += __shfl_xor_sync(0xffffffffu, dq, o);
+  }
+  if (WIDE) {
+    if (lane == 0) {
+      s_part[2 * wid] = ds;
+      s_part[2 * wid + 1] = dq;
+    }
+    __syncthreads();
+    if (wid != 0) return;
+    ds = 0.0;
+    dq = 0.0;
+    for (int w = 0; w < 8; ++w) {                    // fixed order
+      ds += s_part[2 * w];
+      dq += s_part[2 * w + 1];
+    }
   }
   if (lane == 0) {
     const double n = static_cast<double>(a.HW) * a.cpg;

@@ -17,6 +17,7 @@ ap.add_argument('--gpus', type=int, default=1)
 ap.add_argument('--steps', type=int, default=10)
 ap.add_argument('--warmup', type=int, default=3)
 ap.add_argument('--per-gpu', type=int, default=32)
+ap.add_argument('--vae', action='store_true', help='decode every candidate x0 to a 512x512 image before scoring (SURVEY 8 f1)')
 args = ap.parse_args()
 rank, world, lrank = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
 torch.cuda.set_device(lrank)
@@ -31,6 +32,8 @@ from diffusion_tts_b200.arch import random_state_dict, sd_unet_param_shapes
 from diffusion_tts_b200.edm.main import Shard
 from diffusion_tts_b200.sd.beam import DDIMTable, sd_beam_search
 from diffusion_tts_b200.sd_unet import SDUNetEngine
+from diffusion_tts_b200.arch import vae_decoder_param_shapes
+from diffusion_tts_b200.vae import DecodedImageScorer, VAEDecoderEngine
 
 B = 8
 N = args.per_gpu * world // B
@@ -40,6 +43,10 @@ eng.set_context(torch.randn(2, 77, 768, generator=g).to(dev))
 lat = torch.randn(1, 4, 64, 64, generator=g).to(dev)
 tab = DDIMTable(50)
 shard = Shard(rank, world, None) if world > 1 else None
+vae_kw = {}
+if args.vae:
+    veng = VAEDecoderEngine(random_state_dict(vae_decoder_param_shapes(), 4321), device=dev)
+    vae_kw = dict(decode=lambda x0: x0, scorer=DecodedImageScorer(veng, None, chunk=8))
 total = args.warmup + args.steps
 noises = {i: torch.randn(B, N, 4, 64, 64, generator=g).to(dev) for i in range(total)}      # same on every rank
 
@@ -54,7 +61,7 @@ def timed(step_ids):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    best, rec = sd_beam_search(eng, tab, lat, None, B, N, noises=noises, shard=shard, steps=step_ids)
+    best, rec = sd_beam_search(eng, tab, lat, None, B, N, noises=noises, shard=shard, steps=step_ids, **vae_kw)
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -89,7 +96,7 @@ if rank == 0:
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'bf16', 'data': 'synthetic',
         'config': {'workload': f'SD-1.5-shaped UNet2DConditionModel (859.5M, random-init) 4x64x64 latents, beam B={B} N={N} '
-                               f'(={args.per_gpu} candidates/GPU), DDIM eta=1 CFG 7.5, latent brightness on Tweedie x0',
+                               f'(={args.per_gpu} candidates/GPU), DDIM eta=1 CFG 7.5, ' + ('SD-1.5 VAE decode (49.5M, random-init) of every Tweedie x0 to 512x512 + RGB brightness' if args.vae else 'latent brightness on Tweedie x0'),
                    'B': B, 'N': N, 'candidates_per_gpu': args.per_gpu, 'unet_forwards_per_rank_step': fwd_per_step,
                    'l2': 'not flushed: 1.7 GB bf16 weights + ~9 GB activations per call exceed the 126 MB L2'},
         'gpu_launches': launches, 'clocks': clk,

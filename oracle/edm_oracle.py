@@ -582,3 +582,127 @@ def rejection_search(net, latents, class_labels, scorer, *, N, noise: Dict[int, 
     rec.final_image = quantize_u8(x_next)
     rec.final_scores = scorer(rec.final_image, class_labels, torch.zeros(b))
     return rec
+
+
+# --------------------------------------------------------------------------------------
+# MCTS (edm/main.py:405-713) -- SURVEY.md 8 f4
+# --------------------------------------------------------------------------------------
+
+
+class MCTSNode:
+    """One tree node: the state x at depth `depth` (= number of steps taken), its children, visit / reward sums."""
+    __slots__ = ('x', 'depth', 'children', 'reward', 'visit')
+
+    def __init__(self, x, depth, visit=0):
+        self.x, self.depth, self.children, self.reward, self.visit = x, depth, [], 0.0, visit
+
+
+def mcts_select(root: MCTSNode) -> List[MCTSNode]:
+    """Selection (edm/main.py:548-572): descend by UCB1 while the node has children; an unvisited child scores +inf and
+    np.argmax takes the FIRST maximum.  Returns the path root..leaf."""
+    import numpy as np
+    path = [root]
+    node = root
+    while node.children:
+        ucb = []
+        for ch in node.children:
+            if ch.visit == 0:
+                ucb.append(float('inf'))
+            else:
+                ucb.append(ch.reward / ch.visit + np.sqrt(2 * np.log(node.visit) / ch.visit))
+        node = node.children[int(np.argmax(ucb))]
+        path.append(node)
+    return path
+
+
+def mcts_search(net, latents, class_labels, scorer: Callable, *, N: int, S: int, noise: Optional[Dict[int, torch.Tensor]] = None,
+                num_steps=18, sigma_min=0.002, sigma_max=80.0, rho=7.0, record: Optional[dict] = None, **sampler_kw):
+    """SamplingMethod.MCTS (edm/main.py:405-713) for the images of `latents`, in the reference's mini-batches of
+    min(2, batch) samples.  b = N children per expansion, S simulations per timestep, run in groups of 16 whose statistics
+    are only backed up after the whole group (:521, :664-679).  Per timestep: expand the root if needed (:467-512); every
+    simulation selects a leaf (mcts_select), expands it unless it is at the last step (:575-591; all nodes of one depth
+    share the b noises of that depth), descends into a np.random child (:594), rolls out DETERMINISTICALLY (zero noise) to
+    t = 0 (:617-640) and is scored on the final image (:657-661); the root moves to its visited child with the best mean
+    reward, first maximum (:682-700), keeping its subtree.
+    RNG: like the reference, the per-depth noises come from torch.randn (fp32) unless `noise[i]` ([1, b, C, H, W]) is
+    given, every expansion evaluates one throw-away torch.randn (the eager default of the dict .get at :578), and the
+    rollout child comes from np.random.randint -- seed both generators to reproduce a run."""
+    import numpy as np
+    t_steps = karras_schedule(num_steps, sigma_min, sigma_max, rho)
+    x_all = latents.to(torch.float64) * t_steps[0]
+    batch = x_all.shape[0]
+    b = N
+    results = []
+    mbs = min(2, batch)
+    for mb0 in range(0, batch, mbs):
+        mb = min(mb0 + mbs, batch) - mb0
+        xb = x_all[mb0:mb0 + mb]
+        lb = None if class_labels is None else class_labels[mb0:mb0 + mb]
+        lab = lambda s: None if lb is None else lb[s:s + 1]
+        depth_noise = {}
+        for i in range(num_steps):                                             # :439-447
+            if noise is not None and i in noise:
+                depth_noise[i] = noise[i].repeat(mb, 1, 1, 1, 1)
+            else:
+                depth_noise[i] = torch.randn(mb, b, *xb.shape[1:])
+        roots = [MCTSNode(xb[s:s + 1].clone(), 0, visit=1) for s in range(mb)]
+
+        def expand(node: MCTSNode, s: int, throwaway: bool):
+            i = node.depth
+            for n in range(b):
+                if throwaway:
+                    torch.randn(1, *xb.shape[1:])                              # eager default argument of .get (:578)
+                x_child, _ = heun_step(net, node.x, t_steps[i], t_steps[i + 1], i, depth_noise[i][s, n:n + 1], lab(s),
+                                       num_steps=num_steps, **sampler_kw)
+                node.children.append(MCTSNode(x_child, i + 1))
+
+        for i in range(num_steps):
+            need = [s for s in range(mb) if not roots[s].children]             # root expansion, ONE batched step (:467-512)
+            if need:
+                xs = torch.cat([roots[s].x for s in need for _ in range(b)])
+                es = torch.cat([depth_noise[i][s:s + 1, n] for s in need for n in range(b)])
+                ls = None if lb is None else torch.cat([lb[s:s + 1] for s in need for _ in range(b)])
+                xc, _ = heun_step(net, xs, t_steps[i], t_steps[i + 1], i, es, ls, num_steps=num_steps, **sampler_kw)
+                for r, s in enumerate(s for s in need for _ in range(b)):
+                    roots[s].children.append(MCTSNode(xc[r:r + 1], i + 1))
+            group = min(16, S * mb)
+            for g0 in range(0, S * mb, group):
+                paths, starts = [], []
+                for sim in range(g0, min(g0 + group, S * mb)):
+                    s = sim % mb
+                    path = mcts_select(roots[s])
+                    leaf = path[-1]
+                    if leaf.depth < num_steps - 1:                             # :575 (i_traverse < len(t_steps) - 2)
+                        expand(leaf, s, throwaway=True)
+                        leaf = leaf.children[np.random.randint(0, len(leaf.children))]
+                        path.append(leaf)
+                    paths.append(path)
+                    starts.append((leaf.x.clone(), leaf.depth, s))
+                finals = []
+                for x, d, s in starts:                                         # deterministic rollout (:617-640)
+                    for j in range(d, num_steps):
+                        x, _ = heun_step(net, x, t_steps[j], t_steps[j + 1], j, torch.zeros_like(x), lab(s),
+                                         num_steps=num_steps, **sampler_kw)
+                    finals.append(x)
+                img = quantize_u8(torch.cat(finals))
+                labs = None if lb is None else torch.cat([lb[s:s + 1] for _, _, s in starts])
+                rewards = scorer(img, labs, torch.zeros(img.shape[0]))
+                if record is not None:
+                    record.setdefault('rewards', []).append(rewards.clone())
+                    record.setdefault('depths', []).append([d for _, d, _ in starts])
+                for path, r in zip(paths, rewards):                            # backup after the whole group (:664-679)
+                    for node in path:
+                        node.reward += r.item()
+                        node.visit += 1
+            for s in range(mb):                                                # :682-700
+                best, best_r = None, -float('inf')
+                for k, ch in enumerate(roots[s].children):
+                    if ch.visit > 0 and ch.reward / ch.visit > best_r:
+                        best, best_r = ch, ch.reward / ch.visit
+                assert best is not None
+                if record is not None:
+                    record.setdefault('chosen', []).append(roots[s].children.index(best))
+                    record.setdefault('x', []).append(best.x.clone())
+                roots[s] = best
+        results.extend(r.x for r in roots)
+    return torch.cat(results)

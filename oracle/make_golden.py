@@ -144,6 +144,35 @@ def gen_search(cfg, seed, name, method, N, K, num_steps, b=1, eps=0.0):
                     final_image=rec.calls[-1][0], final_scores=rec.calls[-1][1]))
 
 
+def gen_mcts(cfg, seed, name, N, S, num_steps, b=1, with_noise=True):
+    """SamplingMethod.MCTS on the real reference (edm/main.py:405-713): b = N children, S simulations per step."""
+    import numpy as np
+    import main as ref_main
+    import scorers as ref_scorers
+    net, spec, sd = ref_net(cfg, seed)
+    tmp = tempfile.mkdtemp()
+    pkl = os.path.join(tmp, 'net.pkl')
+    with open(pkl, 'wb') as f:
+        pickle.dump(dict(ema=net), f)
+    g = torch.Generator().manual_seed(seed + 3)
+    res, c = cfg['img_resolution'], cfg['in_channels']
+    latents = torch.randn(b, c, res, res, generator=g)
+    labels = torch.eye(cfg['label_dim'])[torch.randint(cfg['label_dim'], (b,), generator=g)] if cfg['label_dim'] else None
+    pre = {i: torch.randn(1, N, c, res, res, generator=g) for i in range(num_steps)} if with_noise else None
+    rec = Rec(ref_scorers.BrightnessScorer())
+    params = dict(scorer=rec, N=N, S=S)
+    kw = dict(S_churn=40, S_min=0.05, S_max=50, S_noise=1.003)
+    np.random.seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        ref_main.generate_image_grid(pkl, os.path.join(tmp, 'o.png'), latents, labels, seed=seed, gridw=b, gridh=1,
+                                     device=torch.device('cpu'), num_steps=num_steps,
+                                     sampling_method=ref_main.SamplingMethod.MCTS, sampling_params=params,
+                                     precomputed_noise=None if pre is None else dict(pre), **kw)
+    save(name, dict(cfg=cfg, seed=seed, method='MCTS', N=N, S=S, num_steps=num_steps, b=b, with_noise=with_noise,
+                    sampler_kw=kw, rewards=[r for _, r in rec.calls[:-1]], final_image=rec.calls[-1][0],
+                    final_scores=rec.calls[-1][1]))
+
+
 TINY_CLS = dict(image_size=16, in_channels=3, model_channels=64, out_channels=10, num_res_blocks=1,
                 attention_resolutions=(2,), channel_mult=(1, 2))
 FULL_CLS = dict(image_size=64, in_channels=3, model_channels=128, out_channels=1000, num_res_blocks=4,
@@ -211,6 +240,8 @@ def main():
     gen_search(TINY_ADM, 11, 'search_eps1_tiny.pt', 'EPS_GREEDY', N=3, K=1, num_steps=4, b=1, eps=1.0)
     gen_search(TINY_ADM, 11, 'search_rejection_tiny.pt', 'REJECTION_SAMPLING', N=4, K=1, num_steps=5, b=2)
     gen_search(TINY_SONG, 12, 'search_naive_tiny_song.pt', 'NAIVE', N=1, K=1, num_steps=18, b=1)
+    gen_mcts(TINY_ADM, 11, 'search_mcts_tiny.pt', N=2, S=20, num_steps=4, b=1)
+    gen_mcts(TINY_ADM, 11, 'search_mcts_tiny_b2.pt', N=3, S=5, num_steps=3, b=2, with_noise=False)
     gen_classifier(TINY_CLS, 21, 'classifier_tiny.pt', batch=4)
     if args.full:
         gen_classifier(FULL_CLS, 22, 'classifier_full.pt', batch=2)

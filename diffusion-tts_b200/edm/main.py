@@ -14,7 +14,8 @@ Deviations from the reference, each deliberate (SURVEY.md hard part 11):
     every torchrun rank on GPU 0;
   * BEAM_SEARCH implements the evident intent (k = B beams, b = N noises per beam, stable
     top-k with lowest-index tie rule); the reference branch raises AttributeError at :140;
-  * MCTS is not on the B200 path (out of scope) and raises NotImplementedError.
+  * MCTS (`mcts_search`) keeps the reference's tree logic and RNG streams but batches every expansion and the rollouts
+    of a simulation group.
 """
 from __future__ import annotations
 
@@ -379,6 +380,135 @@ def rejection_search(net, latents, class_labels, params: SamplingParams, table: 
     return x_next, rec
 
 
+class _MCTSNode:
+    __slots__ = ('x', 'depth', 'children', 'reward', 'visit')
+
+    def __init__(self, x, depth, visit=0):
+        self.x, self.depth, self.children, self.reward, self.visit = x, depth, [], 0.0, visit
+
+
+def _mcts_select(root: _MCTSNode) -> List[_MCTSNode]:
+    """UCB1 descent (edm/main.py:548-572): unvisited children score +inf, np.argmax takes the first maximum."""
+    path, node = [root], root
+    while node.children:
+        ucb = [float('inf') if ch.visit == 0 else ch.reward / ch.visit + np.sqrt(2 * np.log(node.visit) / ch.visit)
+               for ch in node.children]
+        node = node.children[int(np.argmax(ucb))]
+        path.append(node)
+    return path
+
+
+@torch.no_grad()
+def mcts_search(net: B200Denoiser, latents, class_labels, params: SamplingParams, table: StepTable, *,
+                precomputed_noise: Optional[Dict] = None, record: bool = False):
+    """MCTS branch (edm/main.py:405-713): b = params.N children per expansion, params.S simulations per
+    timestep in groups of 16 whose rewards are backed up after the whole group, deterministic (zero-noise) rollouts to
+    t = 0 scored on the final image, root <- visited child with the best mean reward (first maximum), subtree kept.
+    The tree logic and both RNG streams (torch.randn for the per-depth noises and the throw-away draw of every expansion,
+    np.random.randint for the rollout child) follow the reference call for call; what changes is the execution:
+      * an expansion is ONE Heun step at batch b (the reference steps the b children of a deeper node one by one),
+      * the rollouts of a simulation group advance together -- at step j one batched Heun step over every simulation that
+        has reached depth j (the reference finishes them one by one at batch 1); rows are padded to 1/2/4/8/16 so that five
+        cached plans serve every group.  The engine is batch-size and batch-position invariant, so neither changes a bit.
+    Samples are processed in the reference's mini-batches of min(2, batch) (a group's 16 simulations are dealt round-robin
+    to the samples of a mini-batch)."""
+    device = net.device
+    num_steps = table.num_steps
+    scorer = params.scorer
+    b, S = params.N, params.S
+    x_all = latents.to(torch.float64) * table.t_steps[0]
+    batch = x_all.shape[0]
+    shape = tuple(x_all.shape[1:])
+    rec = SearchRecord()
+    rec.mcts_rewards, rec.mcts_depths, rec.mcts_chosen = [], [], []
+    results = []
+    mbs = min(2, batch)
+    for mb0 in range(0, batch, mbs):
+        mb = min(mb0 + mbs, batch) - mb0
+        steppers = [HeunStepper(net, table, None if class_labels is None else class_labels[mb0 + s:mb0 + s + 1])
+                    for s in range(mb)]
+        depth_noise = {}
+        for i in range(num_steps):                                            # :439-447
+            if precomputed_noise is not None and i in precomputed_noise:
+                depth_noise[i] = precomputed_noise[i].to(device).repeat(mb, 1, 1, 1, 1)
+            else:
+                depth_noise[i] = torch.randn(mb, b, *shape, device=device)
+        roots = [_MCTSNode(x_all[mb0 + s:mb0 + s + 1].clone(), 0, visit=1) for s in range(mb)]
+
+        def expand(node: _MCTSNode, s: int, throwaway: bool):
+            i = node.depth
+            if throwaway:
+                for _ in range(b):
+                    torch.randn(1, *shape, device=device)                     # eager default of the dict .get at :578
+            eps = depth_noise[i][s].to(torch.float64).contiguous()            # [b, C, H, W]
+            xc, _, _ = steppers[s].step(node.x.contiguous(), eps, i, want_x_next=True)
+            node.children = [_MCTSNode(xc[n:n + 1], i + 1) for n in range(b)]
+
+        for i in range(num_steps):
+            for s in range(mb):                                               # :467-512
+                if not roots[s].children:
+                    expand(roots[s], s, throwaway=False)
+            group = min(16, S * mb)
+            for g0 in range(0, S * mb, group):
+                paths, starts = [], []
+                for sim in range(g0, min(g0 + group, S * mb)):
+                    s = sim % mb
+                    path = _mcts_select(roots[s])
+                    leaf = path[-1]
+                    if leaf.depth < num_steps - 1:                            # :575
+                        expand(leaf, s, throwaway=True)
+                        leaf = leaf.children[np.random.randint(0, len(leaf.children))]
+                        path.append(leaf)
+                    paths.append(path)
+                    starts.append((leaf.x, leaf.depth, s))
+                # ---- deterministic rollouts (:617-640), batched per sample and per step
+                finals: List[Optional[torch.Tensor]] = [None] * len(starts)
+                for s in range(mb):
+                    mine = [k for k, st in enumerate(starts) if st[2] == s]
+                    if not mine:
+                        continue
+                    cur = {k: starts[k][0] for k in mine}
+                    for j in range(min(starts[k][1] for k in mine), num_steps):
+                        act = [k for k in mine if starts[k][1] <= j]
+                        R = len(act)
+                        Rp = 1 << (R - 1).bit_length()                        # 1, 2, 4, 8, 16 rows
+                        X = torch.cat([cur[k] for k in act] + [cur[act[-1]]] * (Rp - R)).contiguous()
+                        xn, _, _ = steppers[s].step(X, torch.zeros_like(X), j, want_x_next=True)
+                        for r, k in enumerate(act):
+                            cur[k] = xn[r:r + 1]
+                    for k in mine:
+                        finals[k] = cur[k]
+                img = ops.quantize_u8(torch.cat(finals).contiguous())         # :657
+                if getattr(scorer, 'fused_sums', False):
+                    rewards = scorer.score_from_sums(ops.channel_sums_u8(img), img.shape[1], img.shape[2] * img.shape[3])
+                else:
+                    labs = None if class_labels is None else torch.cat([class_labels[mb0 + st[2]:mb0 + st[2] + 1] for st in starts])
+                    timesteps = torch.zeros(img.shape[0], device=device)
+                    timesteps._b200_uniform_value = 0.0
+                    rewards = torch.as_tensor(scorer(img, labs, timesteps)).to(device)
+                rewards_host = rewards.float().cpu()                          # the tree statistics live on the host (:676)
+                rec.scored_candidates += len(starts)
+                if record:
+                    rec.mcts_rewards.append(rewards_host)
+                    rec.mcts_depths.append([st[1] for st in starts])
+                for path, r in zip(paths, rewards_host):                      # backup after the whole group (:664-679)
+                    for node in path:
+                        node.reward += r.item()
+                        node.visit += 1
+            for s in range(mb):                                               # :682-700
+                best, best_r = None, -float('inf')
+                for ch in roots[s].children:
+                    if ch.visit > 0 and ch.reward / ch.visit > best_r:
+                        best, best_r = ch, ch.reward / ch.visit
+                assert best is not None
+                if record:
+                    rec.mcts_chosen.append(roots[s].children.index(best))
+                    rec.x_steps.append(best.x)
+                roots[s] = best
+        results.extend(r.x for r in roots)
+    return torch.cat(results), rec
+
+
 @torch.no_grad()
 def beam_search(net, latents, class_labels, params: SamplingParams, table: StepTable, *,
                 precomputed_noise: Optional[Dict] = None, record=False):
@@ -454,7 +584,8 @@ def generate_image_grid(
         x_next, rec = beam_search(net, latents, class_labels, method_params, table,
                                   precomputed_noise=precomputed_noise, record=record)
     elif sampling_method == SamplingMethod.MCTS:
-        raise NotImplementedError('MCTS is not part of the B200 hot path (SURVEY.md 8 f4)')
+        x_next, rec = mcts_search(net, latents, class_labels, method_params, table, precomputed_noise=precomputed_noise,
+                                  record=record)
     elif sampling_method in (SamplingMethod.ZERO_ORDER, SamplingMethod.EPS_GREEDY):
         print(f"Zero-Order parameters: lambda={method_params.lambda_param}, N={method_params.N}, "
               f"K={method_params.K}, eps={method_params.eps}")

@@ -12,7 +12,8 @@ Differences from the reference CLI, all forced by the offline B200 setting:
     `--network` names a state-dict `.pt`), latent-space scoring of the Tweedie x0, pseudo prompt embeddings (the CLIP
     text encoder and the VAE are unreachable offline; SURVEY.md 8 f1).  `--steps` (new) overrides the 50 DDIM steps;
     `--vae PATH|random` (new) decodes every candidate's x0 to a 512x512 image on the B200 VAE engine before scoring.
-  * `--scorer clip` and `--method mcts` are not part of the B200 hot path and raise NotImplementedError / ValueError.
+  * `--scorer clip` (a second network family) and `--backend sd --method mcts` are not part of the B200 hot path and raise
+    NotImplementedError; `--backend edm --method mcts` runs (batched expansions / rollouts).
 """
 import argparse
 

@@ -1,6 +1,6 @@
 """GPU debug: per-block comparison of the engine against the CPU oracle (tiny ADM)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root
 import torch
 from oracle import edm_oracle as O
 from tests.helpers import load_golden, oracle_net

@@ -311,7 +311,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', type=str, default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--prefetch', type=int, default=1, help='e2e: stage the next step\'s host noise on a side stream')
+    ap.add_argument('--prefetch', type=int, default=0, help='e2e: stage the next step\'s host noise on a side stream (no measurable gain)')
     ap.add_argument('--async-readback', type=int, default=1, help='e2e: per-step results into pinned buffers, asynchronously')
     ap.add_argument('--scorer', type=str, default='brightness', choices=['brightness', 'imagenet', 'compressibility'],
                     help='brightness = BASELINE.json configs[1] (the headline); imagenet = configs[3]')

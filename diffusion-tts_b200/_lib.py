@@ -22,7 +22,7 @@ class GemmDesc(C.Structure):
     _fields_ = [('a_ptr', c_vp * 3), ('a_channels', c_i32 * 3), ('n_seg', c_i32), ('seg', KSeg * 4),
                 ('batch', c_i32), ('H', c_i32), ('W', c_i32), ('w_ptr', c_vp), ('N', c_i32), ('Npad', c_i32),
                 ('Ktot', c_i32), ('bias', c_vp), ('residual', c_vp), ('ld_res', c_i32), ('out_scale', c_f32),
-                ('out', c_vp), ('ld_out', c_i32), ('out_fp32', c_i32), ('gn_stats', c_vp), ('reverse', c_i32), ('a_stride', c_i32 * 3), ('geglu', c_i32)]
+                ('out', c_vp), ('ld_out', c_i32), ('out_fp32', c_i32), ('gn_stats', c_vp), ('reverse', c_i32), ('a_stride', c_i32 * 3), ('geglu', c_i32), ('upsample2x', c_i32)]
 
 
 class GnStatsDesc(C.Structure):

@@ -131,6 +131,30 @@ int make_tmap(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims, 
 }
 
 // bf16 [rows, cols] matrix with row pitch `ld` elements; box = [box_rows][box_cols], 128B swizzle.
+// explicit byte strides (dims[0] is contiguous): strided views such as one phase of a 2x-upsampled NHWC tensor
+int make_tmap_strided(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) return fail("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i < rank - 1) gstr[i] = strides_bytes[i];
+  }
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[200];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled (strided) failed (%d) rank=%d", static_cast<int>(r), rank);
+    return fail(buf);
+  }
+  return 0;
+}
+
 int make_tmap_2d_ld(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_cols,
                     uint32_t box_rows) {
   EncodeTiledFn enc = get_encode();
@@ -701,8 +725,39 @@ void b200ns_debug_force_tile_width(int bn) { g_force_bn = bn; }
 static long gemm_per_kb(int c) { return c >= 192 ? 2 * c : (c == 128 ? 330 : 300); }
 
 static int add_gemm_part(b200ns_plan* p, const b200ns_gemm_desc* d, int BN_forced, int ld_stats);
+static int add_gemm_cols(b200ns_plan* p, const b200ns_gemm_desc* d);
+
+// phase (py, px) of a fused "nearest 2x upsample + 3x3 conv" while its launches are being added (else phase < 0)
+struct UpPhase {
+  int phase = -1, dy0 = 0, dx0 = 0;
+};
+static UpPhase g_up;
 
 int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d) {
+  if (!d->upsample2x) return add_gemm_cols(p, d);
+  // out [batch, 2H, 2W, ld_out] = conv3x3(nearest_up2(A)) as 4 phase launches of a 2x2-tap conv over the low-res A:
+  // w_ptr = [4][Npad][Ktot], Ktot = 4 taps x channels of every segment, the 3x3 weights that land on the same source
+  // pixel pre-summed (ops.pack_conv_up2); the desc's H, W are the LOW-res dims and its segments say taps = 9.
+  if (d->out_fp32 || d->residual != nullptr || d->geglu) return fail("gemm(upsample2x): bf16 output, no residual, no geglu");
+  if ((d->H * d->W) % 64) return fail("gemm(upsample2x): H*W must be a multiple of 64");
+  for (int s = 0; s < d->n_seg; ++s)
+    if (d->seg[s].taps != 9 || d->a_stride[d->seg[s].src] == 2) return fail("gemm(upsample2x): every segment must be a plain 3x3 conv");
+  int rc = 0;
+  for (int ph = 0; ph < 4 && rc == 0; ++ph) {
+    const int py = ph >> 1, px = ph & 1;
+    b200ns_gemm_desc dp = *d;
+    dp.w_ptr = static_cast<const char*>(d->w_ptr) + static_cast<size_t>(ph) * d->Npad * d->Ktot * 2;
+    dp.out = static_cast<char*>(d->out) + (static_cast<size_t>(py) * 2 * d->W + px) * d->ld_out * 2;
+    g_up.phase = ph;
+    g_up.dy0 = py - 1;
+    g_up.dx0 = px - 1;
+    rc = add_gemm_cols(p, &dp);
+  }
+  g_up.phase = -1;
+  return rc;
+}
+
+static int add_gemm_cols(b200ns_plan* p, const b200ns_gemm_desc* d) {
   // Tile width.  One launch uses one width c (a template parameter) and needs c | columns, so a weight matrix whose
   // padded width has no wide divisor (SD-1.5: 320 = 5 x 64) is covered by up to TWO launches over column slices
   // [0, n1*c1) and [n1*c1, Npad) of widths c1 != c2 (320 = 192 + 128, 640 = 2*192 + 256): pointers are shifted, the A operand is shared.
@@ -808,8 +863,9 @@ static int add_gemm_part(b200ns_plan* p, const b200ns_gemm_desc* d, int BN_force
     if (sg.taps != 1 && sg.taps != 9) return fail("gemm: taps must be 1 or 9");
     if (sg.src < 0 || sg.src > 2 || d->a_ptr[sg.src] == nullptr) return fail("gemm: bad segment source");
     if (sg.cstart % 64 || sg.cstart + sg.cblocks * 64 > d->a_channels[sg.src]) return fail("gemm: bad channel range");
-    a.seg[s] = KSeg{sg.src, sg.taps, sg.cstart, sg.cblocks};
-    nkb += sg.taps * sg.cblocks;
+    const int taps = g_up.phase >= 0 ? 4 : sg.taps;               // one phase of the fused upsample: 2x2 taps
+    a.seg[s] = KSeg{sg.src, taps, sg.cstart, sg.cblocks, g_up.dy0, g_up.dx0};
+    nkb += taps * sg.cblocks;
   }
   if (nkb * 64 != d->Ktot) return fail("gemm: Ktot does not match the K segments");
   a.nkb = nkb;
@@ -827,9 +883,26 @@ static int add_gemm_part(b200ns_plan* p, const b200ns_gemm_desc* d, int BN_force
   if (d->gn_stats != nullptr && (BN == 16 || a.M % 64)) return fail("gemm: gn_stats needs bf16 output, N tiles >= 64 and M % 64 == 0");
   if (!d->out_fp32 && (d->ld_out % 8)) return fail("gemm: ld_out must be a multiple of 8 for bf16 output");
   if (d->residual != nullptr && (d->ld_res % 8)) return fail("gemm: ld_res must be a multiple of 8");
+  a.out4d = 0;
+  a.stats_in_rows = a.stats_img_rows = a.stats_off = 0;
   if (BN != 16) {
-    int rc = make_tmap_2d_ld(&g.tmO, d->out, static_cast<uint64_t>(d->geglu ? d->N / 2 : d->N), static_cast<uint64_t>(a.M),
-                             static_cast<uint64_t>(d->ld_out), 64, 128);
+    int rc;
+    if (g_up.phase >= 0) {      // every other pixel of every other row of the [batch, 2H, 2W, ld_out] tensor (base = phase)
+      const uint64_t ld = static_cast<uint64_t>(d->ld_out);
+      const uint64_t dims[4] = {static_cast<uint64_t>(d->N), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                                static_cast<uint64_t>(d->batch)};
+      const uint64_t strides[3] = {2 * ld * 2, 2 * (2 * static_cast<uint64_t>(W)) * ld * 2,
+                                   (2 * static_cast<uint64_t>(H)) * (2 * static_cast<uint64_t>(W)) * ld * 2};
+      const uint32_t box[4] = {64, static_cast<uint32_t>(boxW), static_cast<uint32_t>(tileH), static_cast<uint32_t>(tileN)};
+      rc = make_tmap_strided(&g.tmO, d->out, 4, dims, strides, box);
+      a.out4d = 1;
+      a.stats_in_rows = (H * W) / 64;
+      a.stats_img_rows = 4 * a.stats_in_rows;
+      a.stats_off = g_up.phase * a.stats_in_rows;
+    } else {
+      rc = make_tmap_2d_ld(&g.tmO, d->out, static_cast<uint64_t>(d->geglu ? d->N / 2 : d->N), static_cast<uint64_t>(a.M),
+                           static_cast<uint64_t>(d->ld_out), 64, 128);
+    }
     if (rc) return rc;
     rc = make_tmap_2d_ld(&g.tmR, d->residual ? d->residual : d->out, static_cast<uint64_t>(d->N),
                          static_cast<uint64_t>(a.M), static_cast<uint64_t>(d->residual ? d->ld_res : d->ld_out), 64, 128);

@@ -79,6 +79,12 @@ DEVINL void tma_store_2d(const CUtensorMap* m, const void* smem, int c0, int c1)
                "r"(smem_u32(smem)), "r"(c0), "r"(c1)
                : "memory");
 }
+DEVINL void tma_store_4d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 DEVINL void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 DEVINL void bulk_wait_group_read() {     // all but the latest N groups have finished READING shared memory

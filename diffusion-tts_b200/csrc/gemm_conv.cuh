@@ -30,6 +30,7 @@ namespace b200 {
 
 struct KSeg {
   int src, taps, cstart, cblocks;
+  int dy0, dx0;                  // taps == 4 (one phase of conv3x3 o nearest-upsample-2x): tap t reads pixel (y + dy0 + t/2, x + dx0 + t%2)
 };
 
 struct GemmArgs {
@@ -53,6 +54,15 @@ struct GemmArgs {
   int ld_stats;                  // row pitch of gn_stats in channels (= the full N when this launch covers a column slice)
   int src_stride[3];             // 1, or 2: the source is sampled with stride 2 (3x3 stride-2 pad-1 conv: Downsample2D)
   int reverse;                   // walk the tiles last-to-first (start on what the producer of A wrote last: L2 hits)
+  // Fused "nearest 2x upsample, then 3x3 conv" (Conv2d(up=True) networks.py:72-80, Upsample2D upsampling.py): the output
+  // pixel (2y+py, 2x+px) only ever sees a 2x2 neighbourhood of the LOW-resolution input, with the 3x3 weights that fall on
+  // the same source pixel pre-summed -- 4 launches (one per phase (py, px)) of a 2x2-tap conv over the low-res tensor:
+  // 16 instead of 36 MACs per input channel and output pixel, and the upsampled tensor is never written.
+  int out4d;                     // 1: `out` is stored through a 4-D map [N, W, H, batch] whose pixel strides skip every other
+                                 //    row / column of the high-res tensor (base shifted by the phase)
+  int stats_in_rows;             // gn_stats rows (64 pixels each) per image in THIS launch (0: plain layout)
+  int stats_img_rows;            // gn_stats rows per image in the high-res tensor (4 x stats_in_rows)
+  int stats_off;                 // first gn_stats row of this phase inside an image
   int geglu;                     // 1: the weight rows come in groups of 128 = [64 hidden | 64 gate] and the epilogue stores
                                  //    hidden * gelu(gate) (exact erf GELU) as bf16 [M, N/2]: GEGLU (activations.py:117-123)
                                  //    fused into the projection, whose [M, N] output never touches HBM
@@ -104,8 +114,8 @@ DEVINL void gemm_producer(const CUtensorMap& tmA0, const CUtensorMap& tmA1, cons
       const CUtensorMap* tm = sg.src == 0 ? &tmA0 : (sg.src == 1 ? &tmA1 : &tmA2);
       const int sdn = a.src_stride[sg.src];          // stride 2: input row = 2*out_row + dy (TMA elementStrides = 2)
       for (int tap = 0; tap < sg.taps; ++tap) {
-        const int dy = sg.taps == 9 ? tap / 3 - 1 : 0;
-        const int dx = sg.taps == 9 ? tap % 3 - 1 : 0;
+        const int dy = sg.taps == 9 ? tap / 3 - 1 : (sg.taps == 4 ? sg.dy0 + (tap >> 1) : 0);
+        const int dx = sg.taps == 9 ? tap % 3 - 1 : (sg.taps == 4 ? sg.dx0 + (tap & 1) : 0);
         for (int cb = 0; cb < sg.cblocks; ++cb, ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -390,7 +400,20 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
         named_barrier_sync(1, 256);
         if (is_e) {
-          tma_store_2d(&tmO, smem_slot + (k % SLOTS) * Cfg::SLOT_BYTES, nt * BN + j * 64, mt * 128);
+          if (a.out4d) {                     // one phase of the fused upsample: strided pixels of the high-res tensor
+            int n0, y0 = 0, x0 = 0;
+            if (a.tiles_per_img > 0) {
+              n0 = mt / a.tiles_per_img;
+              const int r = mt % a.tiles_per_img;
+              y0 = (r / a.x_chunks) * a.tileH;
+              x0 = (r % a.x_chunks) * 128;
+            } else {
+              n0 = mt * a.tileN;
+            }
+            tma_store_4d(&tmO, smem_slot + (k % SLOTS) * Cfg::SLOT_BYTES, nt * BN + j * 64, x0, y0, n0);
+          } else {
+            tma_store_2d(&tmO, smem_slot + (k % SLOTS) * Cfg::SLOT_BYTES, nt * BN + j * 64, mt * 128);
+          }
           bulk_commit_group();
         }
         if (a.gn_stats != nullptr) {
@@ -422,12 +445,16 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
           }
           if (rg < 2) {                               // lane rg = 0 writes the first 64-row half, rg = 1 the second
-            const int hrow = mt * 2 + static_cast<int>(rg);
+            const int hrow_in = mt * 2 + static_cast<int>(rg);
+            // phase launches of the fused upsample: the statistics rows of one image are the 4 phases' rows back to back
+            const int hrow = a.stats_in_rows > 0
+                                 ? (hrow_in / a.stats_in_rows) * a.stats_img_rows + a.stats_off + hrow_in % a.stats_in_rows
+                                 : hrow_in;
             const int n = nt * BN + j * 64 + static_cast<int>(unit * 8 + cp * 2);
-            if (hrow * 64 < a.M && n + 1 < a.N) {
+            if (hrow_in * 64 < a.M && n + 1 < a.N) {
               const float4 o4 = rg == 0 ? make_float4(s0[0], q0[0], s1[0], q1[0]) : make_float4(s0[1], q0[1], s1[1], q1[1]);
               *reinterpret_cast<float4*>(a.gn_stats + static_cast<size_t>(hrow) * a.ld_stats + n) = o4;
-            } else if (hrow * 64 < a.M && n < a.N) {
+            } else if (hrow_in * 64 < a.M && n < a.N) {
               a.gn_stats[static_cast<size_t>(hrow) * a.ld_stats + n] = rg == 0 ? make_float2(s0[0], q0[0]) : make_float2(s0[1], q0[1]);
             }
           }

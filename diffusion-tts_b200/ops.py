@@ -239,6 +239,25 @@ def image_sums(img: torch.Tensor, want_u8: bool = False):
     return sums, u8
 
 
+def pack_conv_up2(w: torch.Tensor, splits: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] fp32 -> bf16 [4, Cout, 4*Cin]: the four 2x2 phase kernels of `conv3x3(nearest_upsample_2x(x))`.
+    Output pixel (2y+py, 2x+px) reads the low-res pixels (y+py-1+a, x+px-1+c), a, c in {0, 1}; the 3x3 taps that fall on the
+    same source pixel are summed in fp32.  K order per phase = per input-channel split: (tap a*2+c, channel), like _pack_conv."""
+    G = [[[0], [1, 2]], [[0, 1], [2]]]                        # [phase][tap] -> 3x3 kernel indices along one axis
+    w = w.detach().float().cpu()
+    out = []
+    for py in range(2):
+        for px in range(2):
+            parts, c0 = [], 0
+            for cs in (splits or [w.shape[1]]):
+                ws = w[:, c0:c0 + cs]
+                taps = [sum(ws[:, :, ky, kx] for ky in G[py][a] for kx in G[px][c]) for a in range(2) for c in range(2)]
+                parts.append(torch.stack(taps, dim=1).reshape(w.shape[0], -1))          # [Cout, 4, cs] -> [Cout, 4*cs]
+                c0 += cs
+            out.append(torch.cat(parts, dim=1))
+    return torch.stack(out).contiguous().to(torch.bfloat16)
+
+
 def interleave_geglu(t: torch.Tensor) -> torch.Tensor:
     """Rows [hidden (F) ; gate (F)] of a GEGLU projection (weight [2F, K] or bias [2F]) -> groups of
     [64 hidden | 64 gate] rows, the order the fused GEGLU epilogue of the GEMM expects.  F % 64 == 0."""
@@ -305,10 +324,12 @@ class Plan:
 
     def add_gemm(self, a: Sequence[torch.Tensor], segs: Sequence[Tuple[int, int, int, int]], w: torch.Tensor, N: int,
                  out: torch.Tensor, *, bias=None, residual=None, out_scale=1.0, gn_stats=None, reverse=False, a_stride=None,
-                 label='gemm', alg_k=None, geglu=False):
+                 label='gemm', alg_k=None, geglu=False, upsample2x=False):
         """a: 1-3 NHWC bf16 tensors [B,H,W,C]; segs: (src, taps, cstart, cblocks); w: bf16 [Npad,Ktot].
         gn_stats: optional fp32 [M/64, N, 2] receiving per-channel (sum, sumsq) of the stored output.
-        geglu: w / bias rows in groups of [64 hidden | 64 gate] (`interleave_geglu`); out is [.., N/2] = hidden * gelu(gate)."""
+        geglu: w / bias rows in groups of [64 hidden | 64 gate] (`interleave_geglu`); out is [.., N/2] = hidden * gelu(gate).
+        upsample2x: out [B,2H,2W,N] = conv3x3(nearest_up2(a)) from the LOW-res a; w = pack_conv_up2(...) [4, Npad, Ktot];
+        segs say taps = 9; gn_stats (optional) is fp32 [4*M/64, N, 2] over the high-res output."""
         d = L.GemmDesc()
         a_stride = list(a_stride) if a_stride is not None else [1] * len(a)
         B, H, W_, _ = a[0].shape
@@ -325,7 +346,14 @@ class Plan:
             d.seg[i] = L.KSeg(src, taps, cstart, cblocks)
         d.batch, d.H, d.W = B, H, W_
         _c(w, torch.bfloat16)
-        d.w_ptr, d.N, d.Npad, d.Ktot = L.ptr(w), N, w.shape[0], w.shape[1]
+        up = 4 if upsample2x else 1
+        if upsample2x:
+            if w.dim() != 3 or w.shape[0] != 4 or tuple(out.shape[:3]) != (B, 2 * H, 2 * W_):
+                raise RuntimeError('gemm(upsample2x): w must be [4, Npad, Ktot] (pack_conv_up2) and out [B, 2H, 2W, N]')
+            d.w_ptr, d.N, d.Npad, d.Ktot = L.ptr(w), N, w.shape[1], w.shape[2]
+        else:
+            d.w_ptr, d.N, d.Npad, d.Ktot = L.ptr(w), N, w.shape[0], w.shape[1]
+        d.upsample2x = int(bool(upsample2x))
         d.bias = L.ptr(bias)
         d.residual = L.ptr(residual)
         d.ld_res = residual.shape[-1] if residual is not None else 0
@@ -334,7 +362,7 @@ class Plan:
         d.out_fp32 = 1 if out.dtype == torch.float32 else 0
         if gn_stats is not None:
             _c(gn_stats, torch.float32)
-            if gn_stats.numel() != (B * H * W_ // 64) * N * 2:
+            if gn_stats.numel() != up * (B * H * W_ // 64) * N * 2:
                 raise RuntimeError('gn_stats must be fp32 [M/64, N, 2]')
         d.gn_stats = L.ptr(gn_stats)
         d.reverse = int(reverse)
@@ -349,7 +377,7 @@ class Plan:
             cols = L.lib().b200ns_plan_gemm_cols(self._h, j)
             self.labels.append(label if n_after - n_before == 1 else f'{label}[{cols}]')
             self.kinds.append('gemm')
-            self.flops.append(2.0 * B * H * W_ * cols * (alg_k if alg_k else w.shape[1]))
+            self.flops.append(2.0 * B * H * W_ * cols * (alg_k if alg_k else w.shape[-1]))
 
     def add_gn_stats(self, x: Sequence[torch.Tensor], groups: int, partial: torch.Tensor, splits: int, *, pre_add=None,
                      b_emb=1, label='gn_stats'):

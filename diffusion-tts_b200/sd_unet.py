@@ -24,7 +24,7 @@ from typing import Dict, List, Optional
 
 import torch
 
-from .ops import Plan, interleave_geglu
+from .ops import Plan, interleave_geglu, pack_conv_up2
 from .unet import ForwardPlan, _pack_conv
 
 CTX_ROWS = 128          # 77 context tokens padded to a multiple of the key tile
@@ -221,12 +221,16 @@ class SDPlan(ForwardPlan):
                     x = self._transformer(eng, f'up_blocks.{i}.attentions.{j}', x)
             if i != len(boc) - 1:
                 p = f'up_blocks.{i}.upsamplers.0.conv'
-                u = self._act('up', B, 2 * res, 2 * res, rev[i])
-                P.add_upsample2x(x, u, label=f'up_blocks.{i}.upsample')
                 res *= 2
                 y = self._persist(p, res, res, rev[i])
-                P.add_gemm([u], [(0, 9, 0, rev[i] // 64)], W_[f'{p}.w'], rev[i], y, bias=W_[f'{p}.b'],
-                           gn_stats=self._new_stats(y), reverse=self._rev(u, y), label=p)
+                if eng.fused_upsample:      # conv3x3(nearest_up2(x)) as four 2x2-tap phase launches over the low-res x
+                    P.add_gemm([x], [(0, 9, 0, rev[i] // 64)], W_[f'{p}.wup'], rev[i], y, bias=W_[f'{p}.b'],
+                               gn_stats=self._new_stats(y), reverse=self._rev(x, y), label=p, upsample2x=True)
+                else:
+                    u = self._act('up', B, res, res, rev[i])
+                    P.add_upsample2x(x, u, label=f'up_blocks.{i}.upsample')
+                    P.add_gemm([u], [(0, 9, 0, rev[i] // 64)], W_[f'{p}.w'], rev[i], y, bias=W_[f'{p}.b'],
+                               gn_stats=self._new_stats(y), reverse=self._rev(u, y), label=p)
                 self.block_out[p] = y
                 x = y
         a = self._act('a0', B, H, H, c0)
@@ -238,11 +242,13 @@ class SDPlan(ForwardPlan):
 class SDUNetEngine:
     """Packed weights + cached plans.  `set_context(ctx_pair)` once per prompt, then `forward(x, t)`."""
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device='cuda', use_graphs: bool = True, fused_geglu: bool = True):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device='cuda', use_graphs: bool = True, fused_geglu: bool = True,
+                 fused_upsample: bool = True):
         from . import _lib
         _lib.lib()
         self.device = torch.device(device)
         self.fused_geglu = fused_geglu
+        self.fused_upsample = fused_upsample
         if self.device.type != 'cuda':
             raise RuntimeError('SDUNetEngine requires a CUDA device (B200); there is no CPU fallback')
         self.use_graphs = use_graphs
@@ -305,7 +311,11 @@ class SDUNetEngine:
         for k in sd:
             if k.endswith(('downsamplers.0.conv.weight', 'upsamplers.0.conv.weight')):
                 p = k[:-len('.weight')]
-                w[f'{p}.w'], w[f'{p}.b'] = bf(_pack_conv(cpu(sd[k]))), f(sd[f'{p}.bias'])
+                w[f'{p}.b'] = f(sd[f'{p}.bias'])
+                if 'upsamplers' in k and self.fused_upsample:
+                    w[f'{p}.wup'] = pack_conv_up2(cpu(sd[k])).to(dev)
+                else:
+                    w[f'{p}.w'] = bf(_pack_conv(cpu(sd[k])))
 
         def pad_rows(m, hd, dp):          # [heads*hd, K] -> [heads*dp, K], zero rows between heads
             out = torch.zeros(heads * dp, m.shape[1])

@@ -25,7 +25,7 @@ from typing import Dict, List, Optional
 
 import torch
 
-from .ops import Plan
+from .ops import Plan, pack_conv_up2
 
 
 @dataclass
@@ -376,13 +376,23 @@ class ForwardPlan:
         cin, cout = blk.cin, blk.cout
         resample = 1 if blk.up else (2 if blk.down else 0)
         need_raw = resample != 0                      # skip path sees the resampled raw input
-        a0 = self._act('a0', B, Ho, Ho, cin)
         xr = self._act('xr', B, Ho, Ho, cin) if need_raw else None
-        self._gn(xs, cin, Hin, Hin, W_[f'{n}.norm0.weight'], W_[f'{n}.norm0.bias'], a0, silu=True, resample=resample,
-                 raw_out=xr, label=f'{n}.norm0')
         h = self._act('h', B, Ho, Ho, cout)
-        P.add_gemm([a0], [(0, 9, 0, cin // 64)], W_[f'{n}.conv0.w'], cout, h, bias=W_[f'{n}.conv0.b'],
-                   gn_stats=self._new_stats(h, 'h_stats'), reverse=self._rev(a0, h), label=f'{n}.conv0')
+        if blk.up and eng.fused_upsample and len(xs) == 1:
+            # Conv2d(up=True) with resample_filter [1,1] (networks.py:72-80) = conv3x3(nearest_up2(.)): normalise at the LOW
+            # resolution and let four 2x2-tap phase GEMMs write the high-res conv0 output (16 instead of 36 MACs per input
+            # channel and output pixel; the upsampled activation is never written).  The skip path still sees up2(x).
+            a0 = self._act('a0', B, Hin, Hin, cin)
+            self._gn(xs, cin, Hin, Hin, W_[f'{n}.norm0.weight'], W_[f'{n}.norm0.bias'], a0, silu=True, label=f'{n}.norm0')
+            P.add_upsample2x(xs[0], xr, label=f'{n}.skip_up2')
+            P.add_gemm([a0], [(0, 9, 0, cin // 64)], W_[f'{n}.conv0.wup'], cout, h, bias=W_[f'{n}.conv0.b'],
+                       gn_stats=self._new_stats(h, 'h_stats'), reverse=self._rev(a0, h), label=f'{n}.conv0', upsample2x=True)
+        else:
+            a0 = self._act('a0', B, Ho, Ho, cin)
+            self._gn(xs, cin, Hin, Hin, W_[f'{n}.norm0.weight'], W_[f'{n}.norm0.bias'], a0, silu=True, resample=resample,
+                     raw_out=xr, label=f'{n}.norm0')
+            P.add_gemm([a0], [(0, 9, 0, cin // 64)], W_[f'{n}.conv0.w'], cout, h, bias=W_[f'{n}.conv0.b'],
+                       gn_stats=self._new_stats(h, 'h_stats'), reverse=self._rev(a0, h), label=f'{n}.conv0')
         a1 = self._act('a1', B, Ho, Ho, cout)
         off = eng.affine_off[n]
         if cfg.adaptive_scale:
@@ -435,9 +445,11 @@ class UNetEngine:
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], device='cuda', use_graphs: bool = True,
                  fused_gn_stats: bool = True, alternate_walk: bool = True, lanes: Optional[int] = None,
-                 lane_min_res: int = 32):
+                 lane_min_res: int = 32, fused_upsample: Optional[bool] = None):
         from . import _lib
         self.use_graphs = use_graphs
+        # up-sampling blocks: conv0(up2(x)) as four 2x2-tap phase GEMMs over the low-res input (B200NS_FUSED_UP=0: off)
+        self.fused_upsample = (os.environ.get('B200NS_FUSED_UP', '1') != '0') if fused_upsample is None else fused_upsample
         self.fused_gn_stats = fused_gn_stats      # GroupNorm statistics from the producing GEMM's epilogue
         self.alternate_walk = alternate_walk      # consecutive kernels walk the batch in opposite directions (L2 reuse)
         # sub-batches on parallel graph branches at resolutions >= lane_min_res (see ForwardPlan)
@@ -484,7 +496,10 @@ class UNetEngine:
                 for nm in ('norm0', 'norm1') + (('norm2',) if b.attention else ()):
                     w[f'{n}.{nm}.weight'], w[f'{n}.{nm}.bias'] = f(sd[f'{n}.{nm}.weight']), f(sd[f'{n}.{nm}.bias'])
                 # conv0 reads the normalised concat materialised by gn_apply: plain (tap, channel) order
-                w[f'{n}.conv0.w'] = _pack_conv(sd[f'{n}.conv0.weight'].detach().float().cpu()).to(dev)
+                if b.up and self.fused_upsample:
+                    w[f'{n}.conv0.wup'] = pack_conv_up2(sd[f'{n}.conv0.weight']).to(dev)
+                else:
+                    w[f'{n}.conv0.w'] = _pack_conv(sd[f'{n}.conv0.weight'].detach().float().cpu()).to(dev)
                 w[f'{n}.conv0.b'] = f(sd[f'{n}.conv0.bias'])
                 w1 = _pack_conv(sd[f'{n}.conv1.weight'].detach().float().cpu())
                 if b.skip_conv:

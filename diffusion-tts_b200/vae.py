@@ -154,12 +154,16 @@ class VAEPlan(ForwardPlan):
                 x = self._resnet(eng, f'decoder.up_blocks.{i}.resnets.{j}', x)
             if i != len(ups) - 1:
                 p = f'decoder.up_blocks.{i}.upsamplers.0.conv'
-                u = self._act('up', B, 2 * res, 2 * res, c)
-                P.add_upsample2x(x, u, label=f'decoder.up_blocks.{i}.upsample')
                 res *= 2
                 y = self._out_buf(p, res, c)
-                P.add_gemm([u], [(0, 9, 0, c // 64)], W_[f'{p}.w'], c, y, bias=W_[f'{p}.b'], gn_stats=self._stats_for(y),
-                           reverse=self._rev(u, y), label=p)
+                if eng.fused_upsample:      # conv3x3(nearest_up2(x)) as four 2x2-tap phase launches over the low-res x
+                    P.add_gemm([x], [(0, 9, 0, c // 64)], W_[f'{p}.wup'], c, y, bias=W_[f'{p}.b'], gn_stats=self._stats_for(y),
+                               reverse=self._rev(x, y), label=p, upsample2x=True)
+                else:
+                    u = self._act('up', B, res, res, c)
+                    P.add_upsample2x(x, u, label=f'decoder.up_blocks.{i}.upsample')
+                    P.add_gemm([u], [(0, 9, 0, c // 64)], W_[f'{p}.w'], c, y, bias=W_[f'{p}.b'], gn_stats=self._stats_for(y),
+                               reverse=self._rev(u, y), label=p)
                 x = y
         c0 = ups[-1]
         a = self._act('a0', B, res, res, c0)
@@ -174,13 +178,14 @@ class VAEDecoderEngine:
     `decode_latents(x0)` applies the 1 / scaling_factor of the pipeline (pipeline_stable_diffusion.py:1112)."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], device='cuda', use_graphs: bool = True, scaling_factor: float = 0.18215,
-                 keep_taps: bool = False):
+                 keep_taps: bool = False, fused_upsample: bool = True):
         from . import _lib
         _lib.lib()
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise RuntimeError('VAEDecoderEngine requires a CUDA device (B200); there is no CPU fallback')
         self.use_graphs, self.keep_taps, self.scaling_factor = use_graphs, keep_taps, scaling_factor
+        self.fused_upsample = fused_upsample
         self.cfg = vae_config_from_state_dict(state_dict)
         for c in self.cfg['up_channels'] + [self.cfg['top']]:
             if c % 64:
@@ -221,7 +226,11 @@ class VAEDecoderEngine:
             else:
                 w[f'{p}.conv2.w'], w[f'{p}.conv2.b'] = w2.to(dev), f(sd[f'{p}.conv2.bias'])
         for p in sorted({k[:-len('.conv.weight')] for k in sd if k.startswith('decoder.') and k.endswith('upsamplers.0.conv.weight')}):
-            w[f'{p}.conv.w'], w[f'{p}.conv.b'] = bf(_pack_conv(cpu(sd[f'{p}.conv.weight']))), f(sd[f'{p}.conv.bias'])
+            w[f'{p}.conv.b'] = f(sd[f'{p}.conv.bias'])
+            if self.fused_upsample:
+                w[f'{p}.conv.wup'] = ops.pack_conv_up2(cpu(sd[f'{p}.conv.weight'])).to(dev)
+            else:
+                w[f'{p}.conv.w'] = bf(_pack_conv(cpu(sd[f'{p}.conv.weight'])))
         a = 'decoder.mid_block.attentions.0'
         w[f'{a}.group_norm.weight'], w[f'{a}.group_norm.bias'] = f(sd[f'{a}.group_norm.weight']), f(sd[f'{a}.group_norm.bias'])
         for nm, src in (('q', 'to_q'), ('k', 'to_k'), ('v', 'to_v'), ('out', 'to_out.0')):

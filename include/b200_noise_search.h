@@ -156,6 +156,12 @@ typedef struct {
    * come in groups of 128 = [64 hidden rows | 64 gate rows] of the same 64 output features; `out` is bf16 [M, N/2]
    * (ld_out >= N/2) = hidden * gelu(gate), exact erf GELU.  No residual / gn_stats; Npad % 128 == 0. */
   int32_t geglu;
+  /* 1: out [batch, 2H, 2W, ld_out] = conv3x3(nearest_upsample_2x(A)) (Conv2d(up=True), networks.py:72-80 with
+   * resample_filter [1,1]; diffusers Upsample2D) WITHOUT materialising the upsampled tensor: H, W are the LOW-res dims of
+   * the A tensors, every segment says taps = 9, w_ptr = bf16 [4][Npad][Ktot] with Ktot = 4 * 64 * sum(cblocks): per output
+   * phase (py, px) the 3x3 weights that read the same source pixel pre-summed into a 2x2 kernel (tap order a*2+c; source
+   * pixel (y + py - 1 + a, x + px - 1 + c)).  gn_stats (optional) covers the high-res output.  No residual / fp32 / geglu. */
+  int32_t upsample2x;
 } b200ns_gemm_desc;
 int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d);
 /* Tuning aid: force the N tile width (64/128/192/256; 0 = cost model) of subsequently added bf16 GEMMs whose padded

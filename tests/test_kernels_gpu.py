@@ -409,3 +409,38 @@ def test_candidates_and_gather(ops):
     got = ops.gather_rows(cand.reshape(N, b, C, H, H), idx).cpu()
     assert torch.equal(got, torch.stack([ref.reshape(N, b, C, H, H)[4, 0], ref.reshape(N, b, C, H, H)[1, 1]]))
     assert torch.equal(ops.quantize_u8(cand).cpu(), O.quantize_u8(ref))
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cout', [(2, 8, 8, 64, 128), (3, 16, 16, 128, 192), (1, 32, 64, 64, 320), (1, 4, 256, 64, 64)])
+def test_conv_fused_nearest_upsample(ops, B, H, W, Cin, Cout):
+    """out = conv3x3(nearest_upsample_2x(x)) from the LOW-res x as four 2x2-tap phase launches (pre-summed weights): against
+    torch on the same bf16-rounded phase weights, plus the high-res GroupNorm statistics side band."""
+    torch.manual_seed(3)
+    x = torch.randn(B, H, W, Cin, device='cuda').to(torch.bfloat16)
+    w = torch.randn(Cout, Cin, 3, 3, device='cuda') / math.sqrt(Cin * 9)
+    bias = torch.randn(Cout, device='cuda')
+    wp = ops.pack_conv_up2(w).cuda()
+    out = torch.zeros(B, 2 * H, 2 * W, Cout, device='cuda', dtype=torch.bfloat16)
+    st = torch.zeros(B * 4 * H * W // 64, Cout, 2, device='cuda')
+    plan = ops.Plan()
+    plan.add_gemm([x], [(0, 9, 0, Cin // 64)], wp, Cout, out, bias=bias, gn_stats=st, upsample2x=True)
+    plan.run()
+    torch.cuda.synchronize()
+    # exact-arithmetic reference of the same decomposition: phase kernels (bf16-rounded) applied to the padded low-res input
+    xf = F.pad(x.float().permute(0, 3, 1, 2), (1, 1, 1, 1))
+    ref = torch.zeros(B, Cout, 2 * H, 2 * W, device='cuda')
+    for ph in range(4):
+        py, px = ph >> 1, ph & 1
+        k = wp[ph].float().reshape(Cout, 4, Cin)
+        for a in range(2):
+            for c in range(2):
+                ref[:, :, py::2, px::2] += torch.einsum('oc,bchw->bohw', k[:, a * 2 + c], xf[:, :, py + a:py + a + H, px + c:px + c + W])
+    ref = (ref + bias.view(1, -1, 1, 1)).permute(0, 2, 3, 1)
+    assert _rel_err(out, ref) < 6e-3
+    # and against the un-fused definition (differs only by the bf16 rounding of the pre-summed weights)
+    full = F.conv2d(F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode='nearest'), w, bias, padding=1).permute(0, 2, 3, 1)
+    assert _rel_err(out, full) < 1e-2
+    per_img = out.float().reshape(B, -1, Cout)
+    s_img = st.reshape(B, -1, Cout, 2)
+    assert torch.allclose(s_img[..., 0].sum(1), per_img.sum(1), rtol=1e-3, atol=5e-2)
+    assert torch.allclose(s_img[..., 1].sum(1), (per_img ** 2).sum(1), rtol=1e-3, atol=5e-2)

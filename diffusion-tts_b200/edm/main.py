@@ -173,7 +173,8 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
                       norm_mode: str = 'kernel', scale_table: Optional[torch.Tensor] = None,
                       teacher_x: Optional[List[torch.Tensor]] = None, step_indices: Optional[List[int]] = None,
                       x_init: Optional[torch.Tensor] = None, on_step=None,
-                      commit: str = 'reuse', mirror_rng: bool = True, prefetch: bool = False) -> (torch.Tensor, SearchRecord):
+                      commit: str = 'reuse', mirror_rng: bool = True, prefetch: bool = False,
+                      dedupe_noise_free: bool = False) -> (torch.Tensor, SearchRecord):
     """ZERO_ORDER == EPS_GREEDY branch (edm/main.py:714-860).
 
     Extras over the reference (all optional): `shard` (candidate sharding over ranks), `record`,
@@ -181,6 +182,10 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
     calls), `teacher_x` (force the committed state per step; parity tests), `step_indices` / `x_init`
     (run a sub-sequence of steps from a given state; benchmarks), `on_step(i, x_next, idx, scores)`
     (called after every committed step, e.g. to read results back to the host).
+
+    `dedupe_noise_free` (off by default; never used for the headline number): on the steps whose noise scale is exactly 0
+    (t outside [S_min, S_max]) all N candidates are the same tensor -- evaluate one and replicate its score / state.
+    Bit-identical results; bench.py reports the throughput with it as a separate figure.
 
     `prefetch`: precomputed noise that lives in (pinned) host memory is staged one round ahead on a side stream, so the
     host->device copies run underneath the previous round's network evaluations.  Meant for callers whose `on_step` does
@@ -301,8 +306,17 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
             local = ops.make_candidates(pivot, Z, norms, sc, fresh_mask, ZF)      # [(hi-lo)*b, C, H, W]
             # ---- evaluate this rank's slice: 2 NFE + Tweedie x0 + score (:809-838)
             want_x = commit == 'reuse' and k == K - 1
-            scores, x_cands = _score_rows(params.scorer, stepper, x_cur, local, i, labels_rows, C, HW, want_x)
-            scores = scores.reshape(hi - lo, b)
+            if dedupe_noise_free and table.steps[i].s == 0.0:
+                # gamma = 0: x_hat = x_cur for every candidate (edm/main.py:83-85), so the N candidates are the same
+                # tensor; the kernels are batch-position invariant, hence N identical scores and identical x_next
+                # (tests: test_noise_free_steps_are_exact_ties).  Evaluate candidate 0 and replicate -- bit-identical.
+                s1, x1 = _score_rows(params.scorer, stepper, x_cur, local[:b], i,
+                                     labels_rows[:b] if labels_rows is not None else None, C, HW, want_x)
+                scores = s1.reshape(1, b).expand(hi - lo, b).contiguous()
+                x_cands = x1.unsqueeze(0).expand(hi - lo, *x1.shape).reshape((hi - lo) * b, *x1.shape[1:]).contiguous() if want_x else None
+            else:
+                scores, x_cands = _score_rows(params.scorer, stepper, x_cur, local, i, labels_rows, C, HW, want_x)
+                scores = scores.reshape(hi - lo, b)
             rec.scored_candidates += (hi - lo) * b
             # ---- first-max argmax (+ cross-rank reduction of the packed key) (:842)
             idx, key = ops.argmax_first(scores, idx_base=lo, want_key=True)

@@ -318,3 +318,25 @@ def test_mcts_tiny_matches_oracle(pkg):
         assert float((x.cpu() - x_o).abs().max()) < 0.1
         img, img_o = (x.cpu() * 127.5 + 128).clip(0, 255), (x_o * 127.5 + 128).clip(0, 255)
         assert float((img - img_o).abs().mean()) < 1.0
+
+
+def test_noise_free_dedupe_is_bit_identical(pkg):
+    """dedupe_noise_free evaluates the N identical candidates of a gamma = 0 step once: same scores, indices and states."""
+    den, em, sc = pkg
+    g = load_golden('search_eps_greedy_tiny.pt')
+    onet, spec, sd = oracle_net(g['cfg'], g['seed'])
+    latents, labels, pre = search_inputs(g)
+    net = den.B200Denoiser(sd, device='cuda')
+    table = den.StepTable(net, 'cuda', g['num_steps'], **g['sampler_kw'])
+    assert any(c.s == 0.0 for c in table.steps) and any(c.s != 0.0 for c in table.steps)
+    params = em.SamplingParams(N=g['N'], K=g['K'], eps=0.0, lambda_param=g['lambda_param'], scorer=sc.BrightnessScorer())
+    noise = {k: v.cuda() for k, v in pre.items()}
+    out = []
+    for dd in (False, True):
+        x, rec = em.eps_greedy_search(net, latents.cuda(), labels.cuda(), params, table, precomputed_noise=noise, record=True,
+                                      dedupe_noise_free=dd)
+        torch.cuda.synchronize()
+        out.append((x.cpu(), [t.cpu() for t in rec.indices], [t.cpu() for t in rec.scores], [t.cpu() for t in rec.x_steps]))
+    assert torch.equal(out[0][0], out[1][0])
+    for j in (1, 2, 3):
+        assert all(torch.equal(a, b) for a, b in zip(out[0][j], out[1][j]))

@@ -61,6 +61,31 @@ bool pdl_enabled() {
   }
   return v == 1;
 }
+// 2-CTA clusters for the GEMM (B200NS_CL2=1): see gemm_conv.cuh (multicast weight tiles)
+bool cl2_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200NS_CL2");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_cluster2(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -184,6 +209,7 @@ struct GemmOp {
   GemmArgs args;
   int BN;
   int grid;
+  int cl2;
 };
 struct GnStatsOp {
   GnStatsArgs args;
@@ -258,8 +284,24 @@ int num_sms() {
 }
 
 template <int BN>
+int launch_gemm_cl2(const GemmOp& g, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(gemm_conv_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  CK(launch_cluster2(gemm_conv_kernel<BN, true>, dim3(g.grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, g.tmA[0], g.tmA[1], g.tmA[2],
+                     g.tmB, g.tmO, g.tmR, g.args));
+  CK_LAUNCH("gemm_conv_kernel<cl2>");
+  return 0;
+}
+template <int BN>
 int launch_gemm_t(const GemmOp& g, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
+  if constexpr (BN == 192 || BN == 256) {
+    if (g.cl2) return launch_gemm_cl2<BN>(g, st);
+  }
   static bool attr_set = false;
   if (!attr_set) {
     CK(cudaFuncSetAttribute(gemm_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -925,14 +967,21 @@ static int add_gemm_part(b200ns_plan* p, const b200ns_gemm_desc* d, int BN_force
     if (rc) return rc;
     a.src_stride[i] = sdn;
   }
+  // clusters of two CTAs on two M-adjacent tiles of one column slice: each fetches half of the weight tile for both
+  g.cl2 = (cl2_enabled() && (BN == 192 || BN == 256) && a.m_tiles * a.n_tiles >= 2 * num_sms() && !d->out_fp32) ? 1 : 0;
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(d->Ktot), static_cast<uint64_t>(d->Npad)};
-    const uint32_t box[2] = {64, static_cast<uint32_t>(BN)};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(g.cl2 ? BN / 2 : BN)};
     int rc = make_tmap(&g.tmB, d->w_ptr, 2, dims, box);
     if (rc) return rc;
   }
   const int tiles = a.m_tiles * a.n_tiles;
   g.grid = tiles < num_sms() ? tiles : num_sms();
+  if (g.cl2) {
+    const int super_tiles = ((a.m_tiles + 1) / 2) * a.n_tiles;
+    const int max_pairs = num_sms() / 2;
+    g.grid = 2 * (super_tiles < max_pairs ? super_tiles : max_pairs);
+  }
   p->push(op);
   return 0;
 }

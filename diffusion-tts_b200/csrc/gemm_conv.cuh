@@ -86,18 +86,42 @@ struct GemmCfg {
   static constexpr int THREADS = 320;
 };
 
+// Tile schedule.  CL2 = false: tile (mt, nt) = blockIdx.x + it * gridDim.x, nt fastest.  CL2 = true (clusters of two CTAs):
+// the pair walks "super tiles" (two M-adjacent tiles of the SAME column slice), CTA rank r taking mt = 2*mtp + r, so that
+// both CTAs need the same weight tile at the same time and each fetches half of it for both (multicast).
+template <bool CL2>
+DEVINL bool gemm_tile_at(const GemmArgs& a, int it, int& mt, int& nt) {
+  if constexpr (CL2) {
+    const int pairs = gridDim.x >> 1, pid = blockIdx.x >> 1;
+    const int S = ((a.m_tiles + 1) >> 1) * a.n_tiles;
+    const int st = pid + it * pairs;
+    if (st >= S) return false;
+    const int sl = a.reverse ? S - 1 - st : st;
+    mt = 2 * (sl / a.n_tiles) + static_cast<int>(cluster_ctarank());
+    nt = sl % a.n_tiles;
+    return true;
+  } else {
+    const int num_tiles = a.m_tiles * a.n_tiles;
+    const int tile = blockIdx.x + it * gridDim.x;
+    if (tile >= num_tiles) return false;
+    const int tl = a.reverse ? num_tiles - 1 - tile : tile;
+    mt = tl / a.n_tiles;
+    nt = tl % a.n_tiles;
+    return true;
+  }
+}
+
 // ===================== TMA producer (one thread) =====================
-template <int BN>
+template <int BN, bool CL2 = false>
 DEVINL void gemm_producer(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmA2, const CUtensorMap& tmB,
                           const GemmArgs& a, uint8_t* smem_a, uint8_t* smem_b, uint64_t* full_bar, uint64_t* empty_bar) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
-  const int num_tiles = a.m_tiles * a.n_tiles;
+  const int rank = CL2 ? static_cast<int>(cluster_ctarank()) : 0;
   int stage = 0;
   uint32_t phase = 0;
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int tl = a.reverse ? num_tiles - 1 - tile : tile;
-    const int mt = tl / a.n_tiles, nt = tl % a.n_tiles;
+  int mt, nt;
+  for (int it = 0; gemm_tile_at<CL2>(a, it, mt, nt); ++it) {
     int n0, y0, x0 = 0;
     if (a.tiles_per_img > 0) {
       n0 = mt / a.tiles_per_img;
@@ -120,7 +144,12 @@ DEVINL void gemm_producer(const CUtensorMap& tmA0, const CUtensorMap& tmA1, cons
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           tma_load_4d(smem_a + stage * Cfg::A_BYTES, tm, &full_bar[stage], sg.cstart + cb * 64, x0 * sdn + dx, y0 * sdn + dy, n0);
-          tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * 64, nt * BN);
+          if constexpr (CL2) {            // tmB's box is BN/2 rows: my half of the weight tile, for both CTAs of the pair
+            tma_load_2d_mc(smem_b + stage * Cfg::B_BYTES + rank * (Cfg::B_BYTES / 2), &tmB, &full_bar[stage], kb * 64,
+                           nt * BN + rank * (BN / 2), 3);
+          } else {
+            tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * 64, nt * BN);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -132,18 +161,18 @@ DEVINL void gemm_producer(const CUtensorMap& tmA0, const CUtensorMap& tmA1, cons
 }
 
 // ===================== MMA issuer (one thread) =====================
-template <int BN>
+template <int BN, bool CL2 = false>
 DEVINL void gemm_mma(const GemmArgs& a, uint8_t* smem_a, uint8_t* smem_b, uint64_t* full_bar, uint64_t* empty_bar,
                      uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t tmem_base) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
-  const int num_tiles = a.m_tiles * a.n_tiles;
   int stage = 0;
   uint32_t phase = 0;
   int acc = 0;
   uint32_t acc_phase = 0;
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+  int mt_, nt_;
+  for (int it = 0; gemm_tile_at<CL2>(a, it, mt_, nt_); ++it) {
     mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
     tc_fence_after();
     const uint32_t d_tmem = tmem_base + acc * BN;
@@ -157,7 +186,10 @@ DEVINL void gemm_mma(const GemmArgs& a, uint8_t* smem_a, uint8_t* smem_b, uint64
         // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in the (addr>>4) field
         umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
       }
-      umma_commit(&empty_bar[stage]);
+      if constexpr (CL2)
+        umma_commit_mc(&empty_bar[stage], 3);      // the peer writes half of this stage too: release it in both CTAs
+      else
+        umma_commit(&empty_bar[stage]);
       if (++stage == STAGES) {
         stage = 0;
         phase ^= 1;
@@ -174,7 +206,7 @@ DEVINL void gemm_mma(const GemmArgs& a, uint8_t* smem_a, uint8_t* smem_b, uint64
 // ---------------------------------------------------------------------------------------------------------
 // Main kernel: BN in {64,128,192,256}, bf16 output through the TMA slot ring.
 // ---------------------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, bool CL2 = false>
 __global__ void __launch_bounds__(320, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
@@ -200,7 +232,6 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = a.m_tiles * a.n_tiles;
   const bool has_res = a.residual != nullptr;
 
   if (warp == 0 && lane == 0) {
@@ -212,7 +243,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (has_res) prefetch_tmap(&tmR);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL2 ? 2 : 1);      // CL2: released by both CTAs' MMA warps (multicast commit)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -227,14 +258,15 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL2) cluster_sync_all();        // the peer's barriers exist before anything is multicast into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                   // everything above overlapped the previous kernel's tail (PDL)
 
   if (warp == 0) {
-    if (lane == 0) gemm_producer<BN>(tmA0, tmA1, tmA2, tmB, a, smem_a, smem_b, full_bar, empty_bar);
+    if (lane == 0) gemm_producer<BN, CL2>(tmA0, tmA1, tmA2, tmB, a, smem_a, smem_b, full_bar, empty_bar);
   } else if (warp == 1) {
-    if (lane == 0) gemm_mma<BN>(a, smem_a, smem_b, full_bar, empty_bar, tfull_bar, tempty_bar, tmem_base);
+    if (lane == 0) gemm_mma<BN, CL2>(a, smem_a, smem_b, full_bar, empty_bar, tfull_bar, tempty_bar, tmem_base);
   } else {
     // ===================== epilogue (warps 2..9, 256 threads) =====================
     const int et = threadIdx.x - 64;        // 0..255
@@ -249,11 +281,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
     // sub-box kk of this CTA's tile sequence -> global coordinates; issues the residual TMA load
     auto issue_res = [&](uint32_t kk) {
-      const int tile = blockIdx.x + static_cast<int>(kk / NSUB) * gridDim.x;
-      if (tile >= num_tiles) return;
+      int mt, nt;
+      if (!gemm_tile_at<CL2>(a, static_cast<int>(kk / NSUB), mt, nt)) return;
       const int j = kk % NSUB;
-      const int tl = a.reverse ? num_tiles - 1 - tile : tile;
-    const int mt = tl / a.n_tiles, nt = tl % a.n_tiles;
       const uint32_t s = kk % SLOTS;
       mbar_arrive_expect_tx(&rfull_bar[s], Cfg::SLOT_BYTES);
       tma_load_2d(smem_slot + s * Cfg::SLOT_BYTES, &tmR, &rfull_bar[s], nt * BN + j * 64, mt * 128);
@@ -270,9 +300,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if constexpr (NSUB % 2 == 0) {
       if (a.geglu) {
         // ---- GEGLU epilogue: input sub-boxes (2jj, 2jj+1) = (hidden, gate) columns of the same 64 output features
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-          const int tl = a.reverse ? num_tiles - 1 - tile : tile;
-          const int mt = tl / a.n_tiles, nt = tl % a.n_tiles;
+        int mt, nt;
+        for (int it = 0; gemm_tile_at<CL2>(a, it, mt, nt); ++it) {
           if (et < BN) {
             const int n = nt * BN + et;
             smem_bias[acc * BN + et] = (a.bias != nullptr && n < a.N) ? __ldg(a.bias + n) : 0.f;
@@ -335,9 +364,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         num_tiles_done = true;
       }
     }
-    for (int tile = blockIdx.x; !num_tiles_done && tile < num_tiles; tile += gridDim.x) {
-      const int tl = a.reverse ? num_tiles - 1 - tile : tile;
-    const int mt = tl / a.n_tiles, nt = tl % a.n_tiles;
+    int mt, nt;
+    for (int it = 0; !num_tiles_done && gemm_tile_at<CL2>(a, it, mt, nt); ++it) {
       // bias of this tile's columns -> smem (double buffered by accumulator index)
       if (et < BN) {
         const int n = nt * BN + et;
@@ -470,6 +498,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL2) cluster_sync_all();        // nobody leaves while the peer may still multicast / arrive into this CTA
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);

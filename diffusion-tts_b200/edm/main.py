@@ -94,12 +94,8 @@ def _gather_winner(rows: torch.Tensor, idx: torch.Tensor, lo: int, hi: int, shar
     """rows [hi-lo, b, ...] fp64 = this rank's slice; idx [b] global winner indices -> [b, ...] on every rank."""
     if shard.world == 1:
         return ops.gather_rows(rows, (idx - lo).contiguous())
-    import torch.distributed as dist
-    owned = (idx >= lo) & (idx < hi)
-    out = ops.gather_rows(rows, (idx - lo).clamp(0, hi - lo - 1).contiguous())
-    out = out * owned.to(torch.float64).view(-1, *([1] * (out.dim() - 1)))
-    dist.all_reduce(out, op=dist.ReduceOp.SUM, group=shard.group)
-    return out
+    from ..sharding import exchange_winner
+    return exchange_winner(rows, idx, lo, hi, shard.group, gather=ops.gather_rows)
 
 
 def _scale_table(num_steps: int, K: int, N: int, lam: float) -> torch.Tensor:

@@ -16,3 +16,20 @@ def pack_key(scores: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
 
 def unpack_index(key: torch.Tensor) -> torch.Tensor:
     return 0xFFFFFFFF - (key & 0xFFFFFFFF)
+
+
+def exchange_winner(rows: torch.Tensor, idx: torch.Tensor, lo: int, hi: int, group=None, gather=None) -> torch.Tensor:
+    """rows [hi-lo, b, ...] = this rank's slice of per-candidate tensors (candidates, committed states); idx [b] = the global
+    winner per image.  The owner of each winner contributes the row, every other rank zeros, to an all_reduce(SUM)
+    (x + 0 is exact): afterwards every rank holds the winners, and only b rows crossed the interconnect.
+    `gather(rows, local_idx)` picks rows[local_idx[j], j] (the CUDA path passes ops.gather_rows)."""
+    import torch.distributed as dist
+    n_local = hi - lo
+    owned = (idx >= lo) & (idx < hi)
+    local = (idx - lo).clamp(0, n_local - 1).contiguous()
+    if gather is None:
+        gather = lambda r, li: r[li, torch.arange(r.shape[1], device=r.device)]
+    out = gather(rows, local)
+    out = out * owned.to(out.dtype).view(-1, *([1] * (out.dim() - 1)))
+    dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    return out

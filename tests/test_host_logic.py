@@ -123,12 +123,18 @@ def _gloo_worker(rank, world, port, q):
     key = keys.max(dim=0).values
     dist.all_reduce(key, op=dist.ReduceOp.MAX)
     idx = unpack_index(key)
-    q.put((rank, idx.tolist(), scores.argmax(dim=0).tolist()))
+    # winner exchange (edm/main.py:_gather_winner): per-candidate tensors live on their owner only
+    from diffusion_tts_b200.sharding import exchange_winner
+    cands = torch.randn(N, b, 4, 5, generator=g, dtype=torch.float64)
+    won = exchange_winner(cands[lo:hi].contiguous(), idx, lo, hi)
+    ref_won = cands[scores.argmax(dim=0), torch.arange(b)]
+    q.put((rank, idx.tolist(), scores.argmax(dim=0).tolist(), bool(torch.equal(won, ref_won))))
     dist.destroy_process_group()
 
 
 def test_sharded_argmax_gloo_world2():
-    """N>1 path of 8(e): per-rank packed keys + all_reduce(MAX) == torch.argmax over all candidates."""
+    """N>1 path of 8(e): per-rank packed keys + all_reduce(MAX) == torch.argmax over all candidates, and the winner
+    exchange (owner contributes the row, the others zeros, all_reduce(SUM)) hands every rank the winning rows."""
     import torch.multiprocessing as mp
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
@@ -139,9 +145,10 @@ def test_sharded_argmax_gloo_world2():
     res = [q.get(timeout=120) for _ in procs]
     for p in procs:
         p.join(timeout=60)
-    for rank, idx, ref in res:
+    for rank, idx, ref, won_ok in res:
         assert idx == ref, (rank, idx, ref)
         assert idx[1] == 2 and idx[2] == 0
+        assert won_ok                                # every rank ends up with the winners' rows, bit-exactly
 
 
 def test_philox4x32_known_answers():

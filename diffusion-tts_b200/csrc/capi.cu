@@ -53,14 +53,15 @@ cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 // (profiles/r01_pdl_ab.txt) the eps_greedy step is 32.5 ms with PDL against 32.2 ms without -- the GPU runs
 // power-capped (sw_power_cap, ~1.7 GHz), so the idle gaps between kernels are paid back as clocks and hiding them gains
 // nothing.
-bool pdl_enabled() {
+int pdl_mode() {          // 0 off (default), 1 every plan kernel, 2 only the latency-bound GroupNorm kernels
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("B200NS_PDL");
-    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    v = (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
   }
-  return v == 1;
+  return v;
 }
+bool pdl_enabled() { return pdl_mode() == 1; }
 // 2-CTA clusters for the GEMM (B200NS_CL2=1): see gemm_conv.cuh (multicast weight tiles)
 bool cl2_enabled() {
   static int v = -1;
@@ -84,6 +85,20 @@ cudaError_t launch_cluster2(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl_light(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_mode() != 0 ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 template <typename... KArgs, typename... Args>
@@ -409,16 +424,16 @@ int run_op(const Op& op, cudaStream_t st) {
       return 0;
     case OP_GN_APPLY:
       if (op.gna.threads > 256)
-        launch_pdl(gn_apply_kernel<true>, op.gna.grid, dim3(op.gna.threads), 0, st, op.gna.args);
+        launch_pdl_light(gn_apply_kernel<true>, op.gna.grid, dim3(op.gna.threads), 0, st, op.gna.args);
       else
-        launch_pdl(gn_apply_kernel<false>, op.gna.grid, dim3(op.gna.threads), 0, st, op.gna.args);
+        launch_pdl_light(gn_apply_kernel<false>, op.gna.grid, dim3(op.gna.threads), 0, st, op.gna.args);
       CK_LAUNCH("gn_apply_kernel");
       return 0;
     case OP_GN_FINALIZE:
       if (op.gnf.wide)
-        launch_pdl(gn_finalize_kernel<true>, dim3(op.gnf.n_pairs), dim3(256), 0, st, op.gnf.args, op.gnf.n_pairs);
+        launch_pdl_light(gn_finalize_kernel<true>, dim3(op.gnf.n_pairs), dim3(256), 0, st, op.gnf.args, op.gnf.n_pairs);
       else
-        launch_pdl(gn_finalize_kernel<false>, dim3(op.gnf.grid), dim3(256), 0, st, op.gnf.args, op.gnf.n_pairs);
+        launch_pdl_light(gn_finalize_kernel<false>, dim3(op.gnf.grid), dim3(256), 0, st, op.gnf.args, op.gnf.n_pairs);
       CK_LAUNCH("gn_finalize_kernel");
       return 0;
     case OP_ATTN:

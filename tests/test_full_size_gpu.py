@@ -125,3 +125,37 @@ def test_candidate_geometry_and_commit(ctx):
     xc, rc = _run(ctx, pre, steps, commit='recompute')
     assert all(torch.equal(a, b) for a, b in zip(rr.indices, rc.indices))
     assert all(torch.equal(a, b) for a, b in zip(rr.x_steps, rc.x_steps)) and torch.equal(xr, xc)
+
+
+def test_sd15_unet_and_vae_full_size_invariances():
+    """SD backend at BASELINE.json config-5 sizes (SD-1.5-shaped UNet2DConditionModel, 64x64 latents; SD-1.5 VAE decoder to
+    512x512): the same latent gives the same bits at every batch position and batch size (what makes candidate scores
+    independent of how the candidates are batched / sharded / chunked), repeated runs are deterministic, and the two CFG
+    halves with the same context agree."""
+    from diffusion_tts_b200 import build
+    build.build()
+    from diffusion_tts_b200.arch import random_state_dict, sd_unet_param_shapes, vae_decoder_param_shapes
+    from diffusion_tts_b200.sd_unet import SDUNetEngine
+    from diffusion_tts_b200.vae import VAEDecoderEngine
+    g = torch.Generator().manual_seed(21)
+    eng = SDUNetEngine(random_state_dict(sd_unet_param_shapes(), 1234), device='cuda')
+    ctx = torch.randn(1, 77, 768, generator=g)
+    eng.set_context(torch.cat([ctx, ctx]).cuda())                 # both halves see the same context
+    lat = torch.randn(3, 4, 64, 64, generator=g).cuda()
+    x6 = torch.cat([lat, lat])                                     # rows [uncond half; cond half]
+    out6 = eng.forward(x6, 481).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(out6[:3], out6[3:])                         # same input, same context, other half of the batch
+    assert torch.equal(eng.forward(x6, 481), out6)                 # deterministic
+    x2 = torch.cat([lat[1:2], lat[1:2]])
+    out2 = eng.forward(x2, 481)
+    assert torch.equal(out2[0], out6[1])                           # batch 2 vs batch 6, other position: same bits
+    del eng
+    torch.cuda.empty_cache()
+    veng = VAEDecoderEngine(random_state_dict(vae_decoder_param_shapes(), 4321), device='cuda')
+    z = torch.randn(3, 4, 64, 64, generator=g).cuda()
+    img3 = veng.decode(z).clone()
+    assert img3.shape == (3, 512, 512, 3) and bool(torch.isfinite(img3).all())
+    img1 = veng.decode(z[2:3])
+    assert torch.equal(img1[0], img3[2])                           # chunking the candidates does not change a decode
+    assert torch.equal(veng.decode(z), img3)

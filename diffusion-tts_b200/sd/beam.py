@@ -18,7 +18,8 @@ share the two prompt contexts whose cross-attention K/V were projected once), th
 quantise / score arithmetic in two fused kernels, the top-B on the device, no host sync in the loop.
 `decode` is injectable: identity (latent-space scoring, config 5) is fused; anything else falls back to
 `scorer(decode(x0))` on materialised tensors.  Candidates can be sharded over the ranks of a process group: every
-rank builds all candidate latents (cheap), runs the big UNet call on its slice only, and the scores are all-gathered.
+rank builds all candidate latents (cheap), runs the big UNet call on its slice only, and the scores are all-gathered;
+the beams' own UNet call is split over the ranks as well (eps all-gathered) when the rank count divides B.
 """
 from __future__ import annotations
 
@@ -87,7 +88,12 @@ def sd_beam_search(eng: SDUNetEngine, table: DDIMTable, latents: torch.Tensor, c
     world = shard.world if shard is not None else 1
     lo, hi = shard.bounds(R) if shard is not None else (0, R)
     beams = x.expand(B, -1, -1, -1).contiguous()                       # :1046: B copies of the initial latents
-    fp1 = eng.plan(2 * B, H)
+    # the beams' own UNet call is sharded too when the ranks divide B: rank r evaluates beams [r*B/G, (r+1)*B/G) and the
+    # eps halves are all-gathered (64 KB per beam); the engine is batch-invariant, so every rank ends with the same bits
+    shard_beams = world > 1 and B % world == 0
+    Bp = B // world if shard_beams else B
+    b_lo = shard.rank * Bp if shard_beams else 0
+    fp1 = eng.plan(2 * Bp, H)
     fp2 = eng.plan(2 * (hi - lo), H)
     rec = BeamRecord()
     step_ids = list(range(len(table.timesteps))) if steps is None else steps
@@ -95,9 +101,15 @@ def sd_beam_search(eng: SDUNetEngine, table: DDIMTable, latents: torch.Tensor, c
         t = table.timesteps[i]
         cf = table.coeffs(t)
         # ---- eps of the beams: one UNet call of batch 2B
-        fp1.x_in[:B].copy_(beams)
-        fp1.x_in[B:].copy_(beams)
+        mine = beams[b_lo:b_lo + Bp]
+        fp1.x_in[:Bp].copy_(mine)
+        fp1.x_in[Bp:].copy_(mine)
         eps1 = eng.run(fp1, t)
+        if shard_beams:
+            import torch.distributed as dist
+            allg = torch.empty((world,) + tuple(eps1.shape), device=dev, dtype=eps1.dtype)
+            dist.all_gather_into_tensor(allg, eps1.contiguous(), group=shard.group)
+            eps1 = torch.cat([allg[:, :Bp].reshape(B, *eps1.shape[1:]), allg[:, Bp:].reshape(B, *eps1.shape[1:])])
         # ---- all B*N candidates (DDIM step with per-candidate variance noise)
         if noises is not None:
             nz = noises[i].to(device=dev, dtype=torch.float32).reshape(R, C, H, W).contiguous()

@@ -234,3 +234,64 @@ def vae_decoder_param_shapes(latent_channels=4, out_channels=3, block_out_channe
     shp['decoder.conv_norm_out.weight'], shp['decoder.conv_norm_out.bias'] = (boc[0],), (boc[0],)
     shp['decoder.conv_out.weight'], shp['decoder.conv_out.bias'] = (out_channels, boc[0], 3, 3), (out_channels,)
     return shp
+
+
+def ddpmpp_param_shapes(img_resolution=32, in_channels=3, out_channels=3, label_dim=0, model_channels=128,
+                        channel_mult: Sequence[int] = (2, 2, 2), channel_mult_emb=4, num_blocks=4,
+                        attn_resolutions: Sequence[int] = (16,)) -> Dict[str, Tuple[int, ...]]:
+    """Parameter inventory of the DDPM++ preset of `SongUNet` (BASELINE.json configs[0]: EDM CIFAR-10 32x32; positional
+    embedding, 'standard' encoder / decoder, resample_filter [1,1]): names and shapes as the reference registers them
+    (edm/training/networks.py:229-319; preset edm/train.py:118-122).  Differences from ADM: additive embedding (`affine` has
+    cout outputs), 1x1 `skip` convs on every resampling block, decoder attention only in the last block of a level, the
+    `aux_norm` / `aux_conv` output head.  tests/test_host_logic.py checks it against the oracle's spec-derived inventory."""
+    E = model_channels * channel_mult_emb
+    shp: Dict[str, Tuple[int, ...]] = {
+        'map_layer0.weight': (E, model_channels), 'map_layer0.bias': (E,),
+        'map_layer1.weight': (E, E), 'map_layer1.bias': (E,),
+    }
+    if label_dim:
+        shp['map_label.weight'], shp['map_label.bias'] = (model_channels, label_dim), (model_channels,)
+
+    def unet_block(name, cin, cout, attention, resample=False):
+        shp[f'{name}.norm0.weight'] = shp[f'{name}.norm0.bias'] = (cin,)
+        shp[f'{name}.conv0.weight'], shp[f'{name}.conv0.bias'] = (cout, cin, 3, 3), (cout,)
+        shp[f'{name}.affine.weight'], shp[f'{name}.affine.bias'] = (cout, E), (cout,)
+        shp[f'{name}.norm1.weight'] = shp[f'{name}.norm1.bias'] = (cout,)
+        shp[f'{name}.conv1.weight'], shp[f'{name}.conv1.bias'] = (cout, cout, 3, 3), (cout,)
+        if cin != cout or resample:
+            shp[f'{name}.skip.weight'], shp[f'{name}.skip.bias'] = (cout, cin, 1, 1), (cout,)
+        if attention:
+            shp[f'{name}.norm2.weight'] = shp[f'{name}.norm2.bias'] = (cout,)
+            shp[f'{name}.qkv.weight'], shp[f'{name}.qkv.bias'] = (3 * cout, cout, 1, 1), (3 * cout,)
+            shp[f'{name}.proj.weight'], shp[f'{name}.proj.bias'] = (cout, cout, 1, 1), (cout,)
+
+    skips, c = [], in_channels
+    for level, mult in enumerate(channel_mult):
+        res = img_resolution >> level
+        if level == 0:
+            shp[f'enc.{res}x{res}_conv.weight'], shp[f'enc.{res}x{res}_conv.bias'] = (model_channels, c, 3, 3), (model_channels,)
+            c = model_channels
+        else:
+            unet_block(f'enc.{res}x{res}_down', c, c, False, resample=True)
+        skips.append(c)
+        for idx in range(num_blocks):
+            c_new = model_channels * mult
+            unet_block(f'enc.{res}x{res}_block{idx}', c, c_new, res in attn_resolutions)
+            c = c_new
+            skips.append(c)
+    for level, mult in reversed(list(enumerate(channel_mult))):
+        res = img_resolution >> level
+        if level == len(channel_mult) - 1:
+            unet_block(f'dec.{res}x{res}_in0', c, c, True)
+            unet_block(f'dec.{res}x{res}_in1', c, c, False)
+        else:
+            unet_block(f'dec.{res}x{res}_up', c, c, False, resample=True)
+        for idx in range(num_blocks + 1):
+            c_new = model_channels * mult
+            unet_block(f'dec.{res}x{res}_block{idx}', c + skips.pop(), c_new, idx == num_blocks and res in attn_resolutions)
+            c = c_new
+        if level == 0:
+            shp[f'dec.{res}x{res}_aux_norm.weight'] = shp[f'dec.{res}x{res}_aux_norm.bias'] = (c,)
+            shp[f'dec.{res}x{res}_aux_conv.weight'] = (out_channels, c, 3, 3)
+            shp[f'dec.{res}x{res}_aux_conv.bias'] = (out_channels,)
+    return shp

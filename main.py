@@ -7,6 +7,8 @@ Differences from the reference CLI, all forced by the offline B200 setting:
   * `--network` (new, optional): a local network pickle / `.pt` bundle.  The reference downloads
     the ImageNet-64 ADM pickle (main.py:157-158); without `--network` this front end builds a
     random-init ADM of the same architecture so that the path can run without network access.
+  * `--arch adm|ddpmpp` (new, optional): which random-init architecture stands in when `--network` is absent -- ddpmpp is the
+    CIFAR-10 32x32 SongUNet of BASELINE.json configs[0] (`--method naive`, unconditional).
   * `--classifier` (new, optional): a local `64x64_classifier.pt` for `--scorer imagenet` (random-init otherwise).
   * `--backend sd` runs `--method beam | eps_greedy | zero_order | naive | rejection` (BASELINE.json config 5 = beam): an SD-1.5-shaped UNet (random-init unless
     `--network` names a state-dict `.pt`), latent-space scoring of the Tweedie x0, pseudo prompt embeddings (the CLIP
@@ -37,6 +39,12 @@ def get_scorer(backend, scorer_name, device='cuda', classifier=None):
     if scorer_name == 'compressibility':
         return scorers.CompressibilityScorer(dtype=torch.float32, device=device)
     raise ValueError(f"Unknown or invalid scorer '{scorer_name}' for backend '{backend}'")
+
+
+def random_init_ddpmpp(seed=4321):
+    """CIFAR-10 32x32 DDPM++ (SongUNet) bundle, random init (BASELINE.json configs[0]; reference preset edm/train.py:118-122)."""
+    from diffusion_tts_b200.arch import ddpmpp_param_shapes, random_state_dict
+    return dict(state_dict=random_state_dict(ddpmpp_param_shapes(), seed), sigma_data=0.5)
 
 
 def random_init_adm(seed=1234):
@@ -100,6 +108,8 @@ def main():
     parser.add_argument('--device', type=str, default='cuda', help='Device')
     parser.add_argument('--network', type=str, default=None, help='Local network pickle / .pt bundle')
     parser.add_argument('--classifier', type=str, default=None, help='Local 64x64_classifier.pt for --scorer imagenet')
+    parser.add_argument('--arch', type=str, default='adm', choices=['adm', 'ddpmpp'],
+                        help='edm, without --network: random-init ImageNet-64 ADM (class-cond) or CIFAR-10 32x32 DDPM++ (uncond)')
     parser.add_argument('--steps', type=int, default=None, help='Override the number of sampler steps (sd: 50)')
     parser.add_argument('--vae', type=str, default=None,
                         help="sd: AutoencoderKL state-dict .pt (or 'random'): decode each candidate before scoring")
@@ -115,8 +125,10 @@ def main():
     scorer = get_scorer('edm', args.scorer, args.device, args.classifier)
     num_images = 1
     gridw = gridh = 1
-    latents = torch.randn([num_images, 3, 64, 64])
-    class_labels = torch.eye(1000)[torch.randint(1000, size=[num_images])]
+    ddpmpp = args.network is None and args.arch == 'ddpmpp'
+    res = 32 if ddpmpp else 64
+    latents = torch.randn([num_images, 3, res, res])
+    class_labels = None if ddpmpp else torch.eye(1000)[torch.randint(1000, size=[num_images])]
     device = torch.device(args.device)
     num_steps = 18
 
@@ -134,7 +146,7 @@ def main():
     sampling_params = {'scorer': scorer}
     if args.method in ['rejection', 'zero_order', 'eps_greedy', 'beam', 'mcts']:
         sampling_params.update(N=args.N, K=args.K, lambda_param=args.lambda_, eps=args.eps, B=args.B, S=args.S)
-    network = args.network if args.network is not None else random_init_adm()
+    network = args.network if args.network is not None else (random_init_ddpmpp() if ddpmpp else random_init_adm())
     outname = args.output or f"edm_{args.method}_{args.scorer}.png"
     generate_image_grid(network, outname, latents, class_labels, seed=args.seed, gridw=gridw, gridh=gridh,
                         device=device, num_steps=num_steps, S_churn=40, S_min=0.05, S_max=50, S_noise=1.003,

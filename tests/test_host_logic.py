@@ -164,3 +164,15 @@ def test_philox4x32_known_answers():
     v = rand1_values(0, 0, 4)
     assert v.dtype == np.float32 and abs(float(v[0]) - 0.39904648) < 1e-7 and ((v >= 0) & (v < 1)).all()
     assert np.array_equal(rand1_values(0, 8, 2), v[2:])            # offset advances by 4 per call
+
+
+def test_ddpmpp_param_shapes_match_the_oracle_spec():
+    """arch.ddpmpp_param_shapes (what the CLI random-initialises for BASELINE.json configs[0]) == the inventory the oracle
+    derives from the SongUNet constructor restatement (networks.py:229-319), CIFAR-10 preset and a tiny variant."""
+    from oracle import edm_oracle as O
+    from diffusion_tts_b200.arch import ddpmpp_param_shapes
+    for kw in (dict(img_resolution=32, model_channels=128, channel_mult=[2, 2, 2], num_blocks=4, attn_resolutions=[16]),
+               dict(img_resolution=16, model_channels=64, channel_mult=[2, 4], num_blocks=1, attn_resolutions=[8])):
+        spec = O.build_unet_spec('SongUNet', kw['img_resolution'], 3, 3, label_dim=0, model_channels=kw['model_channels'],
+                                 channel_mult=kw['channel_mult'], num_blocks=kw['num_blocks'], attn_resolutions=kw['attn_resolutions'])
+        assert {k: tuple(v) for k, v in O.unet_param_shapes(spec).items()} == ddpmpp_param_shapes(**kw)

@@ -78,6 +78,7 @@ SIGNATURES = {
     'b200ns_plan_create': (c_vp, []),
     'b200ns_plan_destroy': (None, [c_vp]),
     'b200ns_plan_size': (C.c_int, [c_vp]),
+    'b200ns_plan_set_pdl': (C.c_int, [c_vp, C.c_int]),
     'b200ns_plan_gemm_cols': (C.c_int, [c_vp, C.c_int]),
     'b200ns_debug_force_tile_width': (None, [C.c_int]),
     'b200ns_plan_set_lane': (C.c_int, [c_vp, C.c_int]),

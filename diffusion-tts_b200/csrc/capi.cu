@@ -53,7 +53,9 @@ cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 // (profiles/r01_pdl_ab.txt) the eps_greedy step is 32.5 ms with PDL against 32.2 ms without -- the GPU runs
 // power-capped (sw_power_cap, ~1.7 GHz), so the idle gaps between kernels are paid back as clocks and hiding them gains
 // nothing.
+int g_pdl_override = -1;   // >= 0 while the ops of a plan with its own PDL setting are being launched / captured
 int pdl_mode() {          // 0 off (default), 1 every plan kernel, 2 only the latency-bound GroupNorm kernels
+  if (g_pdl_override >= 0) return g_pdl_override;
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("B200NS_PDL");
@@ -532,6 +534,7 @@ struct b200ns_plan {
     op.lane = cur_lane;
     ops.push_back(op);
   }
+  int pdl = -1;                             // -1: the process-wide B200NS_PDL setting; 0/1/2: this plan's own (small batches: 1)
   cudaGraphExec_t graph_exec = nullptr;     // optional: the whole plan captured once as a CUDA graph
   size_t graph_ops = 0;
 };
@@ -686,7 +689,9 @@ int b200ns_plan_instantiate_graph(b200ns_plan* p) {
   cudaStream_t cs;
   CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
   for (size_t i = 0; i < p->ops.size(); ++i) {
+    g_pdl_override = p->pdl;
     int rc = run_op(p->ops[i], cs);
+    g_pdl_override = -1;
     if (rc) {
       cudaStreamDestroy(cs);
       return rc;
@@ -748,6 +753,11 @@ int b200ns_plan_set_lane(b200ns_plan* p, int lane) {
   p->cur_lane = lane;
   return 0;
 }
+int b200ns_plan_set_pdl(b200ns_plan* p, int mode) {
+  if (mode < -1 || mode > 2) return fail("plan_set_pdl: mode must be -1 (process default), 0, 1 or 2");
+  p->pdl = mode;
+  return 0;
+}
 int b200ns_plan_size(const b200ns_plan* p) { return static_cast<int>(p->ops.size()); }
 int b200ns_plan_gemm_cols(const b200ns_plan* p, int op) {
   if (op < 0 || op >= static_cast<int>(p->ops.size()) || p->ops[op].kind != OP_GEMM) return -1;
@@ -756,13 +766,16 @@ int b200ns_plan_gemm_cols(const b200ns_plan* p, int op) {
 
 int b200ns_plan_run_range(b200ns_plan* p, int first, int last, void* stream) {
   if (first < 0 || last > static_cast<int>(p->ops.size()) || first > last) return fail("plan_run_range: bad range");
+  g_pdl_override = p->pdl;
   for (int i = first; i < last; ++i) {
     int rc = run_op(p->ops[i], S(stream));
     if (rc) {
+      g_pdl_override = -1;
       g_err = "plan op " + std::to_string(i) + ": " + g_err;
       return rc;
     }
   }
+  g_pdl_override = -1;
   return 0;
 }
 int b200ns_plan_run(b200ns_plan* p, void* stream) {

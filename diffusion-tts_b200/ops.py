@@ -306,6 +306,10 @@ class Plan:
         """Ops added from now on go to graph branch `lane` (0 = main stream; 1..3 run in parallel when captured)."""
         L.check(L.lib().b200ns_plan_set_lane(self._h, lane), 'plan_set_lane')
 
+    def set_pdl(self, mode: int):
+        """Programmatic dependent launch for this plan (-1 process default, 0 off, 1 all kernels, 2 GroupNorm only)."""
+        L.check(L.lib().b200ns_plan_set_pdl(self._h, int(mode)), 'plan_set_pdl')
+
     def instantiate_graph(self):
         """Capture the whole plan as one CUDA graph (static buffers): run() then costs one launch."""
         L.check(L.lib().b200ns_plan_instantiate_graph(self._h), 'plan_instantiate_graph')

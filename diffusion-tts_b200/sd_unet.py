@@ -20,6 +20,7 @@ computed once per prompt (`set_context`) and shared by all candidates, beams and
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -70,6 +71,8 @@ class SDPlan(ForwardPlan):
         self.n_lanes, self._lane = 1, None
         self._eps = 1e-5
         self._build_sd(eng)
+        if os.environ.get('B200NS_PDL') is None and self.B_full <= 4:
+            self.plan.set_pdl(1)          # small batches are launch-latency bound: overlap each kernel's prologue with its predecessor
         if eng.use_graphs:
             torch.cuda.synchronize(dev)
             self.plan.instantiate_graph()

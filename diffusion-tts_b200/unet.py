@@ -168,6 +168,8 @@ class ForwardPlan:
         self.lane_min_res = getattr(eng, 'lane_min_res', 32)
         self._lane: Optional[int] = None                  # None: full batch on the main stream
         self._build(eng)
+        if os.environ.get('B200NS_PDL') is None and self.B_full <= 4:
+            self.plan.set_pdl(1)          # small batches are launch-latency bound: overlap each kernel's prologue with its predecessor
         if eng.use_graphs:
             torch.cuda.synchronize(dev)
             self.plan.instantiate_graph()

@@ -23,6 +23,7 @@ fills TMEM, so it runs unfused, per sample, on the GEMM kernel (0.07 of the deco
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -65,6 +66,8 @@ class VAEPlan(ForwardPlan):
         self._flip = 0
         self.keep_taps = eng.keep_taps
         self._build(eng)
+        if os.environ.get('B200NS_PDL') is None and self.B_full <= 4:
+            self.plan.set_pdl(1)          # small batches are launch-latency bound: overlap each kernel's prologue with its predecessor
         if eng.use_graphs:
             torch.cuda.synchronize(dev)
             self.plan.instantiate_graph()

@@ -101,6 +101,10 @@ int b200ns_jpeg_tables_bytes(void);
 typedef struct b200ns_plan b200ns_plan;
 b200ns_plan* b200ns_plan_create(void);
 void b200ns_plan_destroy(b200ns_plan* p);
+/* Programmatic dependent launch for this plan's kernels (call before b200ns_plan_instantiate_graph): -1 = the process-wide
+ * B200NS_PDL setting, 0 off, 1 every kernel, 2 GroupNorm kernels only.  Batch-1..4 plans are latency-bound (one 32x32 DDPM++
+ * NFE at batch 1: 1.83 -> 1.69 ms with mode 1); large batches are power-bound and lose ~1 % (profiles/r01_pdl_ab.txt). */
+int b200ns_plan_set_pdl(b200ns_plan* p, int mode);
 int b200ns_plan_size(const b200ns_plan* p);
 /* Valid output columns of GEMM launch `op` (-1 if `op` is not a GEMM).  One b200ns_plan_add_gemm call may append two
  * launches over column slices (see there), so callers that keep per-launch metadata ask how the columns were split. */

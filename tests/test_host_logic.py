@@ -176,3 +176,64 @@ def test_ddpmpp_param_shapes_match_the_oracle_spec():
         spec = O.build_unet_spec('SongUNet', kw['img_resolution'], 3, 3, label_dim=0, model_channels=kw['model_channels'],
                                  channel_mult=kw['channel_mult'], num_blocks=kw['num_blocks'], attn_resolutions=kw['attn_resolutions'])
         assert {k: tuple(v) for k, v in O.unet_param_shapes(spec).items()} == ddpmpp_param_shapes(**kw)
+
+
+def test_pack_conv_up2_is_the_phase_decomposition_of_upsample_then_conv():
+    """ops.pack_conv_up2: conv3x3(nearest_up2(x)) == four 2x2-tap convs over the low-res x, output phase (py, px) reading
+    pixels (y+py-1+a, x+px-1+c) with the 3x3 taps that hit the same source pixel summed (checked in fp64 against F.conv2d,
+    up to the bf16 rounding of the packed weights), single- and multi-source K layouts."""
+    import torch.nn.functional as F
+    from diffusion_tts_b200.ops import pack_conv_up2
+    g = torch.Generator().manual_seed(0)
+    Cin, Cout, H, W = 6, 4, 5, 7
+    x = torch.randn(2, Cin, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g, dtype=torch.float64)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2.0, mode='nearest'), w, padding=1)
+    for splits in (None, [2, 4]):
+        wp = pack_conv_up2(w.float(), splits)
+        assert wp.shape == (4, Cout, 4 * Cin) and wp.dtype == torch.bfloat16
+        xp = F.pad(x, (1, 1, 1, 1))
+        out = torch.zeros_like(ref)
+        for ph in range(4):
+            py, px = ph >> 1, ph & 1
+            c0 = 0
+            col = 0
+            for cs in (splits or [Cin]):
+                k = wp[ph][:, col:col + 4 * cs].double().reshape(Cout, 4, cs)
+                for a in range(2):
+                    for c in range(2):
+                        out[:, :, py::2, px::2] += torch.einsum('oc,bchw->bohw', k[:, a * 2 + c],
+                                                                xp[:, c0:c0 + cs, py + a:py + a + H, px + c:px + c + W])
+                c0 += cs
+                col += 4 * cs
+        assert float((out - ref).abs().max()) < 0.05 * float(ref.abs().max())        # bf16 weights
+        assert float((out - ref).norm() / ref.norm()) < 5e-3
+
+
+def test_interleave_geglu_layout():
+    """ops.interleave_geglu: rows [hidden F | gate F] -> groups of [64 hidden | 64 gate] of the same 64 output features."""
+    from diffusion_tts_b200.ops import interleave_geglu
+    F_ = 192
+    w = torch.arange(2 * F_ * 3, dtype=torch.float32).reshape(2 * F_, 3)
+    wi = interleave_geglu(w)
+    for grp in range(F_ // 64):
+        assert torch.equal(wi[grp * 128:grp * 128 + 64], w[grp * 64:(grp + 1) * 64])
+        assert torch.equal(wi[grp * 128 + 64:(grp + 1) * 128], w[F_ + grp * 64:F_ + (grp + 1) * 64])
+    b = torch.arange(2 * F_, dtype=torch.float32)
+    assert torch.equal(interleave_geglu(b)[64:128], b[F_:F_ + 64])
+
+
+def test_b200_ddim_table_matches_the_reference_scheduler_fixture():
+    """sd/beam.py:DDIMTable (the scalars handed to the DDIM kernels) against the vendored DDIMScheduler fixture: timesteps,
+    and pred_x0 / prev_sample recomputed from its fp32 scalars in the kernels' op order."""
+    import os
+    from diffusion_tts_b200.sd.beam import DDIMTable
+    fx = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'sd_ddim.pt'))
+    tab = DDIMTable(fx['num_inference_steps'])
+    assert tab.timesteps == fx['timesteps']
+    f32 = lambda v: torch.tensor(v, dtype=torch.float32)
+    for r in fx['rows']:
+        cf = tab.coeffs(r['t'])
+        x0 = (r['sample'] - f32(cf['sqrt_beta_t']) * r['eps']) / f32(cf['sqrt_alpha_t'])
+        prev = f32(cf['sqrt_alpha_prev']) * x0 + f32(cf['dir_coef']) * r['eps'] + f32(cf['std']) * r['noise']
+        assert torch.equal(x0, r['x0']) and torch.equal(prev, r['prev'])

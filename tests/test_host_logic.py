@@ -237,3 +237,60 @@ def test_b200_ddim_table_matches_the_reference_scheduler_fixture():
         x0 = (r['sample'] - f32(cf['sqrt_beta_t']) * r['eps']) / f32(cf['sqrt_alpha_t'])
         prev = f32(cf['sqrt_alpha_prev']) * x0 + f32(cf['dir_coef']) * r['eps'] + f32(cf['std']) * r['noise']
         assert torch.equal(x0, r['x0']) and torch.equal(prev, r['prev'])
+
+
+def test_mcts_selection_matches_the_oracle_on_random_trees():
+    """edm/main.py:_mcts_select (product) == oracle mcts_select (pinned to the reference) on random trees with ties and
+    unvisited children: same path, by node identity."""
+    import random
+    from oracle import edm_oracle as O
+    from diffusion_tts_b200.edm.main import _MCTSNode, _mcts_select
+    rnd = random.Random(7)
+    for trial in range(50):
+        def build(depth, cls):
+            n = cls(None, depth, visit=rnd.choice([0, 1, 2, 5]))
+            n.reward = rnd.choice([0.0, 0.5, 1.0, 2.5])
+            return n
+        root_p, root_o = build(0, _MCTSNode), None
+        root_p.visit = max(root_p.visit, 1)
+        root_o = O.MCTSNode(None, 0, visit=root_p.visit)
+        root_o.reward = root_p.reward
+        frontier = [(root_p, root_o)]
+        while frontier:
+            p, o = frontier.pop()
+            if p.depth >= 3 or (p.depth > 0 and rnd.random() < 0.3):
+                continue
+            for _ in range(rnd.choice([2, 3])):
+                cp = build(p.depth + 1, _MCTSNode)
+                if p.visit == 0:
+                    cp.visit = 0                      # a child cannot have been visited more than its parent
+                co = O.MCTSNode(None, cp.depth, visit=cp.visit)
+                co.reward = cp.reward
+                p.children.append(cp)
+                o.children.append(co)
+                frontier.append((cp, co))
+        pp, po = _mcts_select(root_p), O.mcts_select(root_o)
+        assert len(pp) == len(po)
+        a, b = root_p, root_o
+        for np_, no_ in zip(pp[1:], po[1:]):
+            assert a.children.index(np_) == b.children.index(no_)
+            a, b = np_, no_
+
+
+def test_engine_configs_are_inferred_from_state_dict_shapes():
+    """sd_config_from_state_dict / vae_config_from_state_dict read the architecture off parameter names and shapes."""
+    from diffusion_tts_b200.arch import sd_unet_param_shapes, vae_decoder_param_shapes
+    from diffusion_tts_b200.sd_unet import sd_config_from_state_dict
+    from diffusion_tts_b200.vae import vae_config_from_state_dict
+    meta = lambda shapes: {k: torch.empty(v, device='meta') for k, v in shapes.items()}
+    cfg = sd_config_from_state_dict(meta(sd_unet_param_shapes()))
+    assert cfg['block_out_channels'] == [320, 640, 1280, 1280] and cfg['layers_per_block'] == 2
+    assert cfg['cross_attn_down'] == [True, True, True, False] and cfg['cross_attention_dim'] == 768 and cfg['in_channels'] == 4
+    tiny = sd_config_from_state_dict(meta(sd_unet_param_shapes(block_out_channels=(64, 128), layers_per_block=1,
+                                                               cross_attn_down=(True, False), cross_attention_dim=64)))
+    assert tiny['block_out_channels'] == [64, 128] and tiny['cross_attn_down'] == [True, False]
+    v = vae_config_from_state_dict(meta(vae_decoder_param_shapes()))
+    assert v['up_channels'] == [512, 512, 256, 128] and v['resnets_per_block'] == 3 and v['top'] == 512 and v['latent_channels'] == 4
+    from diffusion_tts_b200.sd.pipeline import pseudo_prompt_embeddings
+    e1, e2 = pseudo_prompt_embeddings('a photo of a cat'), pseudo_prompt_embeddings('a photo of a cat')
+    assert e1.shape == (2, 77, 768) and torch.equal(e1, e2) and not torch.equal(e1[0], e1[1])

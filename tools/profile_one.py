@@ -27,7 +27,7 @@ fp.x_in.normal_()
 plan = fp.plan
 plan.run()
 torch.cuda.synchronize()
-idx = [plan.labels.index(l) for l in labels]
+idx = [next(i for i, x in enumerate(plan.labels) if x == l or x.startswith(l + '[')) for l in labels]      # 'name[cols]': slices / phases
 for i in idx:                                   # warm
     plan.run(i, i + 1)
 torch.cuda.synchronize()

@@ -13,8 +13,12 @@ pivot update and the commit step (2 more denoiser calls at batch 1).  Steps cycl
 
 `value`  : candidates/s with all inputs (noise directions, pivots) resident in HBM.
 `e2e`    : the same loop through the public API with HOST (pinned) noise buffers: per step the
-           pivot and the N direction tensors are copied host->device and the winning index,
-           its score and the committed state are read back.
+           pivot and this rank's slice of the N direction tensors are copied host->device and the
+           winning index, its score and the committed state are copied back into pinned host buffers
+           (asynchronously, in stream order; the timed region ends with a synchronize, so every byte
+           has arrived inside it).
+`extras` : the same steps with the exact shortcut for the noise-free timesteps (the N identical
+           candidates of such a step evaluated once) -- reported separately, never the headline.
 `--impl reference` times the reference algorithm's CPU path (oracle port, all host threads) on
 a bounded sample of the same workload.
 """

@@ -198,13 +198,15 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(noise, steps_idx, x_init, on_step=None, dedupe=False):
+    esc = None if args.escalate < 0 else bool(args.escalate)
+
+    def timed(noise, steps_idx, x_init, on_step=None, dedupe=False, escalate=esc):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         x, rec = eps_greedy_search(net, None, labels, params, table, precomputed_noise=noise, shard=shard,
                                    step_indices=steps_idx, x_init=x_init, on_step=on_step, prefetch=bool(args.prefetch),
-                                   dedupe_noise_free=dedupe)
+                                   dedupe_noise_free=dedupe, escalate=escalate)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -296,6 +298,7 @@ def run_b200(args):
                 'h2d_bytes_per_step_per_rank': h2d_rank, 'd2h_bytes_per_step_per_rank': d2h,
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': launches,
+        'escalation': {'mode': args.escalate, 'rows_refined_per_step': rec.escalated, 'truncated_rounds': rec.truncated},
         'extras': {'value_with_noise_free_dedupe': N * args.steps / (ms_dd / 1e3), 'ms_per_step': ms_dd / args.steps,
                    'noise_free_steps': noise_free,
                    'note': 'same candidates counted; on the timesteps with noise scale 0 the N identical candidates are '
@@ -326,6 +329,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', type=str, default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--escalate', type=int, default=-1, help='near-tie precision escalation: 1 on, 0 off, -1 = API default (on)')
     ap.add_argument('--prefetch', type=int, default=0, help='e2e: stage the next step\'s host noise on a side stream (no measurable gain)')
     ap.add_argument('--async-readback', type=int, default=1, help='e2e: per-step results into pinned buffers, asynchronously')
     ap.add_argument('--scorer', type=str, default='brightness', choices=['brightness', 'imagenet', 'compressibility'],

@@ -21,11 +21,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= newest:
         return OUT
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', OUT, os.path.join(CSRC, 'capi.cu')]
+    # build into a private temp file and rename atomically: concurrent builders (torchrun ranks) or a process that is
+    # dlopen-ing the library never see a half-written .so
+    tmp = f'{OUT}.{os.getpid()}.tmp'
+    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', tmp, os.path.join(CSRC, 'capi.cu')]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError('nvcc failed building libb200ns.so')
+    os.replace(tmp, OUT)
     if verbose:
         sys.stderr.write(res.stderr)
     return OUT

@@ -16,6 +16,7 @@
 #include "gemm_conv.cuh"
 #include "groupnorm.cuh"
 #include "jpeg.cuh"
+#include "precise.cuh"
 #include "sampler.cuh"
 #include "sdops.cuh"
 #include "vae.cuh"
@@ -219,7 +220,8 @@ int make_tmap_2d_ld(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t ro
 
 // ------------------------------------------------------------------ plan ops
 enum OpKind { OP_GEMM, OP_GN_STATS, OP_GN_APPLY, OP_GN_FINALIZE, OP_ATTN, OP_LINEAR, OP_IM2COL, OP_U8F32, OP_POOL_TOKENS, OP_POOL_ATTN,
-              OP_SOFTMAX_GATHER, OP_LAYERNORM, OP_GEGLU, OP_UPSAMPLE2X, OP_SOFTMAX_ROWS };
+              OP_SOFTMAX_GATHER, OP_LAYERNORM, OP_GEGLU, OP_UPSAMPLE2X, OP_SOFTMAX_ROWS,
+              OP_GN_STATS_PREC, OP_GN_APPLY_PREC, OP_ATTN_PREC, OP_IM2COL_PREC };
 
 struct GemmOp {
   CUtensorMap tmA[3], tmB, tmO, tmR;
@@ -227,6 +229,16 @@ struct GemmOp {
   int BN;
   int grid;
   int cl2;
+  int prec;                  // split-fp16 precise GEMM (precise.cuh)
+  GemmPrecArgs pargs;
+};
+struct GnPrecOp {
+  GnPrecArgs args;
+  int grid;
+};
+struct AttnPrecOp {
+  AttnPrecArgs args;
+  dim3 grid;
 };
 struct GnStatsOp {
   GnStatsArgs args;
@@ -284,6 +296,8 @@ struct Op {
     AttnOp attn;
     LinearOp lin;
     Im2colOp i2c;
+    GnPrecOp gnp;
+    AttnPrecOp attnp;
   };
   int lane;     // 0 = main stream; k > 0: parallel branch k of the captured graph (see b200ns_plan_set_lane)
   Op() { memset(this, 0, sizeof(*this)); }
@@ -340,7 +354,30 @@ int launch_gemm_small_n(const GemmOp& g, cudaStream_t st) {
   CK_LAUNCH("gemm_small_n_kernel");
   return 0;
 }
+template <int BN>
+int launch_gemm_prec_t(const GemmOp& g, cudaStream_t st) {
+  using Cfg = GemmPrecCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(gemm_prec_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  gemm_prec_kernel<BN><<<dim3(g.grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st>>>(g.tmA[0], g.tmA[1], g.tmA[2], g.tmB, g.args, g.pargs);
+  CK_LAUNCH("gemm_prec_kernel");
+  return 0;
+}
+int launch_gemm_prec(const GemmOp& g, cudaStream_t st) {
+  switch (g.BN) {
+    case 256: return launch_gemm_prec_t<256>(g, st);
+    case 192: return launch_gemm_prec_t<192>(g, st);
+    case 128: return launch_gemm_prec_t<128>(g, st);
+    case 64: return launch_gemm_prec_t<64>(g, st);
+    case 16: return launch_gemm_prec_t<16>(g, st);
+  }
+  return fail("bad BN (prec)");
+}
 int launch_gemm(const GemmOp& g, cudaStream_t st) {
+  if (g.prec) return launch_gemm_prec(g, st);
   switch (g.BN) {
     case 256: return launch_gemm_t<256>(g, st);
     case 192: return launch_gemm_t<192>(g, st);
@@ -454,6 +491,29 @@ int run_op(const Op& op, cudaStream_t st) {
       if (op.attn.vrow && op.attn.head_dim == 192) return launch_attn_v3<64, 192>(op.attn, st);
       if (op.attn.vrow) return op.attn.KT == 128 ? launch_attn_v3<128>(op.attn, st) : launch_attn_v3<64>(op.attn, st);
       return op.attn.KT == 128 ? launch_attn_t<128, false>(op.attn, st) : launch_attn_t<64, false>(op.attn, st);
+    case OP_GN_STATS_PREC:
+      gn_stats_prec_kernel<<<dim3(op.gnp.args.groups, op.gnp.args.batch), 256, 0, st>>>(op.gnp.args);
+      CK_LAUNCH("gn_stats_prec_kernel");
+      return 0;
+    case OP_GN_APPLY_PREC:
+      gn_apply_prec_kernel<<<op.gnp.grid, 256, 0, st>>>(op.gnp.args);
+      CK_LAUNCH("gn_apply_prec_kernel");
+      return 0;
+    case OP_ATTN_PREC: {
+      static bool attr_set = false;
+      if (!attr_set) {
+        CK(cudaFuncSetAttribute(attention_prec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_PREC_SMEM));
+        attr_set = true;
+      }
+      attention_prec_kernel<<<op.attnp.grid, 256, ATTN_PREC_SMEM, st>>>(op.attnp.args);
+      CK_LAUNCH("attention_prec_kernel");
+      return 0;
+    }
+    case OP_IM2COL_PREC:
+      im2col_c3_prec_kernel<<<op.i2c.grid, 256, 0, st>>>(op.i2c.d.x, reinterpret_cast<__half*>(op.i2c.d.out), op.i2c.d.batch,
+                                                        op.i2c.d.C, op.i2c.d.H, op.i2c.d.W);
+      CK_LAUNCH("im2col_c3_prec_kernel");
+      return 0;
     case OP_LINEAR:
       launch_pdl(linear_kernel, dim3(op.lin.grid), dim3(256), 0, st, op.lin.args);
       CK_LAUNCH("linear_kernel");
@@ -804,6 +864,12 @@ struct UpPhase {
 static UpPhase g_up;
 
 int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d) {
+  if (d->prec) {
+    if (d->upsample2x || d->geglu || d->gn_stats != nullptr) return fail("gemm(prec): no upsample2x / geglu / gn_stats");
+    if (!d->out_fp32 && (d->N % 32 || d->out_lo_off % 8)) return fail("gemm(prec): split output needs N % 32 == 0 and out_lo_off % 8 == 0");
+    if (d->residual != nullptr && (d->res_lo_off % 8 || d->ld_res % 8)) return fail("gemm(prec): residual planes must be 16-byte aligned");
+    return add_gemm_part(p, d, 0, d->N);
+  }
   if (!d->upsample2x) return add_gemm_cols(p, d);
   // out [batch, 2H, 2W, ld_out] = conv3x3(nearest_up2(A)) as 4 phase launches of a 2x2-tap conv over the low-res A:
   // w_ptr = [4][Npad][Ktot], Ktot = 4 taps x channels of every segment, the 3x3 weights that land on the same source
@@ -926,7 +992,7 @@ static int add_gemm_part(b200ns_plan* p, const b200ns_gemm_desc* d, int BN_force
   g.BN = BN;
   a.n_tiles = d->Npad / BN;
   a.n_seg = d->n_seg;
-  if (d->n_seg < 1 || d->n_seg > 4) return fail("gemm: n_seg out of range");
+  if (d->n_seg < 1 || d->n_seg > 8) return fail("gemm: n_seg out of range");
   int nkb = 0;
   for (int s = 0; s < d->n_seg; ++s) {
     const b200ns_kseg& sg = d->seg[s];
@@ -940,7 +1006,14 @@ static int add_gemm_part(b200ns_plan* p, const b200ns_gemm_desc* d, int BN_force
   if (nkb * 64 != d->Ktot) return fail("gemm: Ktot does not match the K segments");
   a.nkb = nkb;
   a.bias = d->bias;
-  a.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
+  a.fp16 = d->prec ? 1 : 0;
+  g.prec = d->prec ? 1 : 0;
+  g.pargs.acc_scale = d->prec ? d->acc_scale : 1.0f;
+  g.pargs.out_lo_off = d->out_lo_off;
+  g.pargs.res = d->prec ? reinterpret_cast<const __half*>(d->residual) : nullptr;
+  g.pargs.ld_res = d->ld_res;
+  g.pargs.res_lo_off = d->res_lo_off;
+  a.residual = d->prec ? nullptr : reinterpret_cast<const __nv_bfloat16*>(d->residual);
   a.ld_res = d->ld_res;
   a.out_scale = d->out_scale;
   a.out = d->out;
@@ -955,7 +1028,7 @@ static int add_gemm_part(b200ns_plan* p, const b200ns_gemm_desc* d, int BN_force
   if (d->residual != nullptr && (d->ld_res % 8)) return fail("gemm: ld_res must be a multiple of 8");
   a.out4d = 0;
   a.stats_in_rows = a.stats_img_rows = a.stats_off = 0;
-  if (BN != 16) {
+  if (BN != 16 && !d->prec) {
     int rc;
     if (g_up.phase >= 0) {      // every other pixel of every other row of the [batch, 2H, 2W, ld_out] tensor (base = phase)
       const uint64_t ld = static_cast<uint64_t>(d->ld_out);
@@ -996,7 +1069,7 @@ static int add_gemm_part(b200ns_plan* p, const b200ns_gemm_desc* d, int BN_force
     a.src_stride[i] = sdn;
   }
   // clusters of two CTAs on two M-adjacent tiles of one column slice: each fetches half of the weight tile for both
-  g.cl2 = (cl2_enabled() && (BN == 192 || BN == 256) && a.m_tiles * a.n_tiles >= 2 * num_sms() && !d->out_fp32) ? 1 : 0;
+  g.cl2 = (cl2_enabled() && !d->prec && (BN == 192 || BN == 256) && a.m_tiles * a.n_tiles >= 2 * num_sms() && !d->out_fp32) ? 1 : 0;
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(d->Ktot), static_cast<uint64_t>(d->Npad)};
     const uint32_t box[2] = {64, static_cast<uint32_t>(g.cl2 ? BN / 2 : BN)};
@@ -1377,6 +1450,95 @@ int b200ns_sd_candidates(const float* pivot, const float* dirs, const float* u, 
   if (N <= 0 || E <= 0) return fail("sd_candidates: N and E must be positive");
   sd_candidates_kernel<<<static_cast<unsigned>(N), 256, 0, S(stream)>>>(pivot, dirs, u, fresh, cand, E, lambda, sqrt_e);
   CK_LAUNCH("sd_candidates_kernel");
+  return 0;
+}
+
+static int fill_gn_prec(GnPrecArgs& a, const b200ns_gn_prec_desc* d) {
+  a.x0 = reinterpret_cast<const __half*>(d->x_ptr[0]);
+  a.x1 = reinterpret_cast<const __half*>(d->x_ptr[1]);
+  a.C0 = d->x_channels[0];
+  a.C1 = d->x_ptr[1] ? d->x_channels[1] : 0;
+  a.C = a.C0 + a.C1;
+  if (a.x0 == nullptr || d->mean_rstd == nullptr) return fail("gn_prec: null pointer");
+  if (a.C % 8 || a.C0 % 8) return fail("gn_prec: channels must be multiples of 8");
+  if (d->groups < 1 || a.C % d->groups) return fail("gn_prec: bad group count");
+  if (d->resample == 2 && (d->H % 2 || d->W % 2)) return fail("gn_prec: odd size cannot be downsampled");
+  a.H = d->H;
+  a.W = d->W;
+  a.groups = d->groups;
+  a.cpg = a.C / d->groups;
+  a.eps = d->eps;
+  a.gamma = d->gamma;
+  a.beta = d->beta;
+  a.pre_add = d->pre_add;
+  a.ld_pre_add = d->ld_pre_add;
+  a.film_scale = d->film_scale;
+  a.film_shift = d->film_shift;
+  a.ld_film = d->ld_film;
+  a.b_emb = d->b_emb > 0 ? d->b_emb : 1;
+  a.silu = d->silu;
+  a.resample = d->resample;
+  a.out = reinterpret_cast<__half*>(d->out);
+  a.raw_out = reinterpret_cast<__half*>(d->raw_out);
+  a.mean_rstd = reinterpret_cast<float2*>(d->mean_rstd);
+  a.batch = d->batch;
+  return 0;
+}
+
+int b200ns_plan_add_gn_stats_prec(b200ns_plan* p, const b200ns_gn_prec_desc* d) {
+  Op op;
+  op.kind = OP_GN_STATS_PREC;
+  int rc = fill_gn_prec(op.gnp.args, d);
+  if (rc) return rc;
+  if (d->batch > 65535) return fail("gn_stats_prec: batch > 65535");
+  p->push(op);
+  return 0;
+}
+
+int b200ns_plan_add_gn_apply_prec(b200ns_plan* p, const b200ns_gn_prec_desc* d) {
+  Op op;
+  op.kind = OP_GN_APPLY_PREC;
+  int rc = fill_gn_prec(op.gnp.args, d);
+  if (rc) return rc;
+  if (d->out == nullptr || d->gamma == nullptr || d->beta == nullptr) return fail("gn_apply_prec: null pointer");
+  const GnPrecArgs& a = op.gnp.args;
+  const int outH = a.resample == 1 ? a.H * 2 : (a.resample == 2 ? a.H / 2 : a.H);
+  const int outW = a.resample == 1 ? a.W * 2 : (a.resample == 2 ? a.W / 2 : a.W);
+  op.gnp.grid = grid_for(static_cast<int64_t>(a.batch) * outH * outW * (a.C / 8), 256, 148 * 8);
+  p->push(op);
+  return 0;
+}
+
+int b200ns_plan_add_attention_prec(b200ns_plan* p, const b200ns_attn_prec_desc* d) {
+  if (d->L % 64 || d->L <= 0) return fail("attention_prec: L must be a positive multiple of 64");
+  if (d->ld % 8 || d->lo_off % 8 || d->k_col0 % 8 || d->v_col0 % 8) return fail("attention_prec: columns must be 16-byte aligned");
+  if (static_cast<int64_t>(d->batch) * d->heads > 65535) return fail("attention_prec: batch * heads > 65535");
+  Op op;
+  op.kind = OP_ATTN_PREC;
+  AttnPrecArgs& a = op.attnp.args;
+  a.qkv = reinterpret_cast<const __half*>(d->qkv);
+  a.ld = d->ld;
+  a.lo_off = d->lo_off;
+  a.k_col0 = d->k_col0;
+  a.v_col0 = d->v_col0;
+  a.out = reinterpret_cast<__half*>(d->out);
+  a.ld_out = d->ld_out;
+  a.out_lo_off = d->out_lo_off;
+  a.heads = d->heads;
+  a.L = d->L;
+  a.scale = d->scale > 0.f ? d->scale : 0.125f;
+  op.attnp.grid = dim3(d->L / 64, d->batch * d->heads);
+  p->push(op);
+  return 0;
+}
+
+int b200ns_plan_add_im2col_prec(b200ns_plan* p, const b200ns_im2col_desc* d) {
+  if (d->C * 9 > 64) return fail("im2col_prec: C*9 must be <= 64");
+  Op op;
+  op.kind = OP_IM2COL_PREC;
+  op.i2c.d = *d;
+  op.i2c.grid = grid_for(static_cast<int64_t>(d->batch) * d->H * d->W * 64, 256, 148 * 8);
+  p->push(op);
   return 0;
 }
 

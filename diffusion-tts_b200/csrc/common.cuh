@@ -253,6 +253,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool b_mn_m
          (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// Same with IEEE half operands (A/B format fields [7,10) and [10,13) = 0): the split-fp16 precise path.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
 // ---------------------------------------------------------------- misc
 DEVINL float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 // x*sigmoid(x) = 0.5x*(1 + tanh(x/2)): one MUFU op instead of two; tanh.approx error ~2^-11, far below bf16's 2^-8

@@ -35,7 +35,7 @@ struct KSeg {
 
 struct GemmArgs {
   int n_seg;
-  KSeg seg[4];
+  KSeg seg[8];
   int nkb;                       // total K blocks of 64
   int M, N;                      // valid rows / cols
   int H, W;                      // spatial dims
@@ -66,6 +66,7 @@ struct GemmArgs {
   int geglu;                     // 1: the weight rows come in groups of 128 = [64 hidden | 64 gate] and the epilogue stores
                                  //    hidden * gelu(gate) (exact erf GELU) as bf16 [M, N/2]: GEGLU (activations.py:117-123)
                                  //    fused into the projection, whose [M, N] output never touches HBM
+  int fp16;                      // 1: operands are IEEE half (the split-fp16 "precise" path, precise.cuh) instead of bf16
 };
 
 template <int BN>
@@ -166,7 +167,7 @@ DEVINL void gemm_mma(const GemmArgs& a, uint8_t* smem_a, uint8_t* smem_b, uint64
                      uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t tmem_base) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
-  constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+  const uint32_t idesc = a.fp16 ? umma_idesc_f16(128, BN) : umma_idesc_bf16(128, BN);
   int stage = 0;
   uint32_t phase = 0;
   int acc = 0;

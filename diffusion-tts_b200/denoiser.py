@@ -60,6 +60,22 @@ class B200Denoiser:
         cfg = self.engine.cfg
         self.img_resolution, self.img_channels, self.label_dim = cfg.img_resolution, cfg.in_channels, cfg.label_dim
         self.sigma_data, self.sigma_min, self.sigma_max = sigma_data, sigma_min, sigma_max
+        self._state_dict = state_dict            # a reference only: the precise engine packs its weights lazily
+        self._precise = None
+
+    @property
+    def supports_precise(self) -> bool:
+        """The fp32-faithful re-scoring engine (precise.py) implements head_dim-64 attention (ADM) only."""
+        cfg = self.engine.cfg
+        return all((not b.attention) or b.cout // b.heads == 64 for b in cfg.enc + cfg.dec if b.kind == 'block')
+
+    @property
+    def precise_engine(self):
+        """Split-fp16 twin of `engine` for near-tie contenders (built on first use)."""
+        if self._precise is None:
+            from .precise import PreciseUNetEngine
+            self._precise = PreciseUNetEngine(self.engine, self._state_dict)
+        return self._precise
 
     def to(self, device):
         if torch.device(device) != self.device:
@@ -177,13 +193,20 @@ class HeunStepper:
                            else torch.zeros([1, net.label_dim], device=net.device))
 
     def _forward(self, fp, i: int, which: int):
-        eng = self.net.engine
         fp.emb_in.copy_(self.table.emb[i, which].unsqueeze(0).expand(fp.b_emb, -1))
         fp.plan.run()
         return fp.out
 
-    def _plan(self, R: int, b: int):
-        fp = self.net.engine.plan(R, b)
+    def _plan(self, R: int, b: int, precise: bool = False, row_images: Optional[torch.Tensor] = None):
+        eng = self.net.precise_engine if precise else self.net.engine
+        if row_images is not None:
+            # arbitrary rows (near-tie contenders of several images): one embedding row per batch row
+            fp = eng.plan(R, R)
+            if self.labels is not None:
+                fp.labels.copy_(self.labels.expand(R, -1) if self.labels.shape[0] == 1 else self.labels[row_images])
+            fp._labels_src = None
+            return fp
+        fp = eng.plan(R, b)
         if self.labels is not None and getattr(fp, '_labels_src', None) is not self.labels:
             fp.labels.copy_(self.labels.expand(fp.b_emb, -1) if self.labels.shape[0] == 1 else self.labels)
             fp._labels_src = self.labels
@@ -191,11 +214,16 @@ class HeunStepper:
 
     @torch.no_grad()
     def step(self, x_cur: torch.Tensor, eps: torch.Tensor, i: int, *, want_x_next=True, want_u8=False,
-             want_sums=False):
-        """x_cur [b,C,H,W] fp64 (shared), eps [R,C,H,W] fp64.  Returns (x_next, x0_u8, chan_sums)."""
+             want_sums=False, precise: bool = False, row_images: Optional[torch.Tensor] = None):
+        """x_cur [b,C,H,W] fp64 (shared), eps [R,C,H,W] fp64.  Returns (x_next, x0_u8, chan_sums).
+
+        `precise`: evaluate the network with the split-fp16 (fp32-faithful) engine instead of the bf16 one.
+        `row_images` (int64 [R]): row r belongs to image row_images[r] instead of r % b (contender subsets)."""
         c = self.table.steps[i]
         R, b = eps.shape[0], x_cur.shape[0]
-        fp = self._plan(R, b)
+        if row_images is not None:
+            x_cur = x_cur.index_select(0, row_images).contiguous()
+        fp = self._plan(R, b, precise, row_images)
         x_hat, _ = ops.heun_pre(x_cur, eps, c.s, c.c_in1, net_in=fp.x_in)
         F1 = self._forward(fp, i, 0)
         if c.last:

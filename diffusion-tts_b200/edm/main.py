@@ -61,6 +61,18 @@ class SearchRecord:
     final_image: Optional[torch.Tensor] = None
     final_scores: Optional[torch.Tensor] = None
     scored_candidates: int = 0
+    # near-tie escalation (always filled: host integers, no sync of their own)
+    escalated: List[int] = field(default_factory=list)            # per round: rows re-scored by the precise engine (this rank)
+    refined: List[Optional[torch.Tensor]] = field(default_factory=list)   # per round (record only): [N_local, b] refined scores, -inf = not a contender
+    truncated: int = 0                                            # rounds whose contender list exceeded max_contenders
+
+
+# Near-tie escalation (SURVEY.md 7 hard part 1b).  A candidate is a contender when its bf16 score is within DELTA of the
+# round's best; contenders are re-scored by the fp32-faithful engine (precise.py) and the argmax is taken over the refined
+# scores.  DELTA bounds the DIFFERENCE of two candidates' bf16 score errors (the error common to all candidates of a round
+# cancels in the comparison): measured on the ADM-64 N=64 reference fixture, see DESIGN.md 2.
+ESCALATION_DELTA = 4e-4
+MAX_CONTENDERS = 8
 
 
 @dataclass
@@ -163,6 +175,65 @@ class _NoiseStager:
         return dst
 
 
+def _key_score(key: torch.Tensor) -> torch.Tensor:
+    """fp32 score packed in the high half of an argmax key (csrc/sampler.cuh: orderable_f32 is an involution)."""
+    o = (key >> 32).to(torch.int32)
+    return torch.where(o < 0, o ^ 0x7FFFFFFF, o).view(torch.float32)
+
+
+def _escalate(scorer, stepper: HeunStepper, x_cur, local, scores, key, idx, i, lo, hi, b, labels_rows, C, HW, shard,
+              delta: float, max_rows: int, x_cands: Optional[torch.Tensor]):
+    """One round's near-tie escalation.  scores [nl, b] (this rank's bf16 scores), key [b] (the GLOBAL packed argmax key).
+    Returns (idx [b] global winners, rows refined here, refined score table or None, truncated?).  `x_cands` (the
+    candidates' x_next, [nl*b, ...]) gets the precise x_next of the refined rows written in place."""
+    nl = hi - lo
+    thr = (_key_score(key) - delta).unsqueeze(0)                           # [1, b]
+    mask = scores >= thr                                                   # contenders (the best itself included)
+    cnt = mask.sum(dim=0)
+    if shard.world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=shard.group)
+    multi = cnt > 1                                                        # images whose best has company within delta
+    host = torch.cat([(mask & multi.unsqueeze(0)).reshape(-1).to(torch.float32), scores.reshape(-1)]).cpu()   # THE host sync
+    m_host, s_host = host[:nl * b].bool(), host[nl * b:]
+    any_multi = bool(multi.any()) if shard.world > 1 else bool(m_host.any())
+    if not any_multi:
+        return idx, 0, None, False
+    rows = torch.nonzero(m_host).flatten()                                 # row = n_local * b + j
+    truncated = rows.numel() > max_rows
+    if truncated:                                                          # keep the best-scoring rows (ties: lowest row)
+        order = torch.sort(s_host[rows], descending=True, stable=True).indices[:max_rows]
+        rows = rows[order].sort().values
+    refined = torch.where(mask & ~multi.unsqueeze(0), scores, torch.full_like(scores, float('-inf')))
+    n_rows = int(rows.numel())
+    if n_rows:
+        rows_d = rows.to(scores.device)
+        imgs = rows_d % b
+        eps_rows = local.index_select(0, rows_d).contiguous()
+        lab = labels_rows.index_select(0, rows_d) if labels_rows is not None else None
+        if getattr(scorer, 'fused_sums', False):
+            x_p, _, sums = stepper.step(x_cur, eps_rows, i, want_x_next=x_cands is not None, want_sums=True, precise=True,
+                                        row_images=imgs if b > 1 else None)
+            s_p = scorer.score_from_sums(sums, C, HW)
+        else:
+            x_p, u8, _ = stepper.step(x_cur, eps_rows, i, want_x_next=x_cands is not None, want_u8=True, want_sums=False,
+                                      precise=True, row_images=imgs if b > 1 else None)
+            timesteps = torch.zeros(u8.shape[0], device=u8.device)
+            timesteps._b200_uniform_value = 0.0
+            s_p = torch.as_tensor(scorer(u8, lab, timesteps)).to(device=u8.device, dtype=torch.float32).reshape(-1)
+        refined.view(-1).index_copy_(0, rows_d, s_p.contiguous())
+        if x_cands is not None:
+            x_cands.index_copy_(0, rows_d, x_p)
+    idx2, key2 = ops.argmax_first(refined.contiguous(), idx_base=lo, want_key=True)
+    if shard.world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(key2, op=dist.ReduceOp.MAX, group=shard.group)
+        idx2 = 0xFFFFFFFF - (key2 & 0xFFFFFFFF)
+    else:
+        idx2 = idx2 + lo
+    return idx2, n_rows, refined, truncated
+
+
 @torch.no_grad()
 def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: SamplingParams, table: StepTable, *,
                       precomputed_noise: Optional[Dict] = None, shard: Optional[Shard] = None, record: bool = False,
@@ -170,7 +241,9 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
                       teacher_x: Optional[List[torch.Tensor]] = None, step_indices: Optional[List[int]] = None,
                       x_init: Optional[torch.Tensor] = None, on_step=None,
                       commit: str = 'reuse', mirror_rng: bool = True, prefetch: bool = False,
-                      dedupe_noise_free: bool = False) -> (torch.Tensor, SearchRecord):
+                      dedupe_noise_free: bool = False, escalate: Optional[bool] = None, delta: float = ESCALATION_DELTA,
+                      max_contenders: int = MAX_CONTENDERS,
+                      bernoulli_draws: Optional[torch.Tensor] = None) -> (torch.Tensor, SearchRecord):
     """ZERO_ORDER == EPS_GREEDY branch (edm/main.py:714-860).
 
     Extras over the reference (all optional): `shard` (candidate sharding over ranks), `record`,
@@ -188,6 +261,17 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
     not synchronise (asynchronous copies into pinned buffers, as bench.py's end-to-end leg does): measured on B200,
     33.27 -> 32.96 ms per step end to end; with a blocking `on_step` (`.cpu()`) it is counter-productive (42 ms), hence off
     by default.
+
+    `escalate` (default: on whenever the network has a precise twin, i.e. ADM): near-tie precision escalation.  The bf16
+    network puts ~1e-4 of noise on the scores while the reference runs it in fp32, so after the bf16 pass every candidate
+    whose score is within `delta` of the round's best is re-evaluated by the split-fp16 (fp32-faithful) engine and the
+    first-max argmax is taken over the refined scores (edm/main.py:842 on the reference's own precision).  Rounds with a
+    single contender -- and the noise-free steps, whose N candidates are one tensor -- cost nothing extra; otherwise one
+    host read of the [N, b] score table per round decides which rows to refine (at most `max_contenders` per rank, best
+    first).  The committed state of a refined winner is its precise x_next.
+
+    `bernoulli_draws` (tests): the uniform draws of edm/main.py:751 in call order, [num_steps*K*N] fp32, used INSTEAD of
+    `torch.rand(1, device)` -- a reference run on another device (CPU) drew them from another generator.
 
     `commit`: the reference re-runs `step` on the winning noise at batch b (edm/main.py:860).  All kernels
     here are batch-size and batch-position invariant (fixed reduction orders), so the winner's x_next from
@@ -218,6 +302,13 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
         dist.broadcast(scales, src=dist.get_global_rank(shard.group, 0) if shard.group is not None else 0, group=shard.group)
     labels_rows = class_labels.repeat(hi - lo, 1) if class_labels is not None else None
     use_mirror = mirror_rng and philox.mirror_ok(device)
+    if escalate is None:
+        escalate = net.supports_precise
+    elif escalate and not net.supports_precise:
+        raise NotImplementedError('escalate=True: the precise engine implements head_dim-64 attention (ADM) only')
+    if escalate:
+        for R in range(1, max_contenders + 1):        # all contender batch sizes up front: no plan is built mid-run
+            net.precise_engine.plan(R, 1 if b == 1 else R)
     pre = precomputed_noise
     if pre is not None and 'pivot' in pre:                                # :724-727 (value unused, RNG untouched)
         pass
@@ -245,7 +336,10 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
             bulk = (pre is not None and i in pre and k < pre[i].shape[1] and N <= pre[i].shape[2] and
                     (eps_p <= 0 or all(f'fresh_{i}_{k}_{n}' in pre for n in range(N))))
             dirs, fresh, perturb = [], [], []
-            if bulk and use_mirror:
+            if bulk and bernoulli_draws is not None:
+                r0 = (i * K + k) * N
+                perturb_host = bernoulli_draws[r0:r0 + N].to(torch.float32).cpu().numpy() < np.float32(1 - eps_p)
+            elif bulk and use_mirror:
                 # the N `torch.rand(1)` draws of :751 evaluated on the host from the generator's (seed, offset) --
                 # same values, same final RNG state, no kernels in the stream (philox.py)
                 perturb_host = philox.rand1_sequence(device, N) < np.float32(1 - eps_p)
@@ -322,6 +416,16 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
                 idx = 0xFFFFFFFF - (key & 0xFFFFFFFF)
             else:
                 idx = idx + lo
+            # ---- near-tie escalation: re-score the contenders with the fp32-faithful engine, argmax over the refined table
+            n_esc, refined = 0, None
+            if escalate and table.steps[i].s != 0.0:
+                idx, n_esc, refined, trunc = _escalate(params.scorer, stepper, x_cur, local, scores, key, idx, i, lo, hi, b,
+                                                       labels_rows, C, HW, shard, delta, max_contenders,
+                                                       x_cands if want_x else None)
+                rec.truncated += int(trunc)
+            rec.escalated.append(n_esc)
+            if record:
+                rec.refined.append(refined)
             # ---- new pivot = the winning candidate (:848-857); it lives on its owner's GPU only: the other ranks
             # contribute zeros to an all_reduce(SUM) (x + 0 is exact), 96 KiB per image over NVLink -- and only when
             # somebody reads it (another local-search round, a recomputed commit, a trace)

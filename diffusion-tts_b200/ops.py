@@ -4,11 +4,17 @@ from libb200ns.so on torch's current stream; nothing falls back to PyTorch math.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
 
 from . import _lib as L
+from . import torch_ops as T
+
+# The sampler / scorer entry points and the plan runner go through their torch.library registrations
+# (torch.ops.b200ns.*, torch_ops.py); B200NS_TORCH_OPS=0 calls the C ABI through ctypes directly.
+USE_TORCH_OPS = os.environ.get('B200NS_TORCH_OPS', '1') != '0'
 
 # number of libb200ns kernel launches issued through this module (bench.py reports it)
 LAUNCHES = [0]
@@ -40,8 +46,11 @@ def heun_pre(x_cur: torch.Tensor, eps: torch.Tensor, s: float, c_in: float, *, x
     E = eps[0].numel()
     x_hat = torch.empty_like(eps) if x_hat is None else _c(x_hat, torch.float64)
     net_in = torch.empty(eps.shape, dtype=torch.float32, device=eps.device) if net_in is None else _c(net_in, torch.float32)
-    L.check(L.lib().b200ns_heun_pre(L.ptr(x_cur), L.ptr(eps), L.ptr(x_hat), L.ptr(net_in), R, b, E, float(s),
-                                    float(c_in), L.cur_stream()), 'heun_pre')
+    if USE_TORCH_OPS:
+        T.OPS.heun_pre_(x_cur, eps, x_hat, net_in, float(s), float(c_in))
+    else:
+        L.check(L.lib().b200ns_heun_pre(L.ptr(x_cur), L.ptr(eps), L.ptr(x_hat), L.ptr(net_in), R, b, E, float(s),
+                                        float(c_in), L.cur_stream()), 'heun_pre')
     _count()
     return x_hat, net_in
 
@@ -55,8 +64,11 @@ def heun_mid(x_hat: torch.Tensor, F1: torch.Tensor, c_skip, c_out, t_hat, dt, c_
     net_in2 = (torch.empty(x_hat.shape, dtype=torch.float32, device=x_hat.device) if net_in2 is None
                else _c(net_in2, torch.float32))
     x_eul = torch.empty_like(x_hat) if want_x_eul else None
-    L.check(L.lib().b200ns_heun_mid(L.ptr(x_hat), L.ptr(F1), L.ptr(net_in2), L.ptr(x_eul), R, Cc, H * W, float(c_skip),
-                                    float(c_out), float(t_hat), float(dt), float(c_in_next), L.cur_stream()), 'heun_mid')
+    if USE_TORCH_OPS:
+        T.OPS.heun_mid_(x_hat, F1, net_in2, x_eul, float(c_skip), float(c_out), float(t_hat), float(dt), float(c_in_next))
+    else:
+        L.check(L.lib().b200ns_heun_mid(L.ptr(x_hat), L.ptr(F1), L.ptr(net_in2), L.ptr(x_eul), R, Cc, H * W, float(c_skip),
+                                        float(c_out), float(t_hat), float(dt), float(c_in_next), L.cur_stream()), 'heun_mid')
     _count()
     return (net_in2, x_eul) if want_x_eul else net_in2
 
@@ -73,9 +85,13 @@ def heun_post(x_hat, F1, F2, c_skip1, c_out1, t_hat, dt, c_skip2=0.0, c_out2=0.0
     x_next = torch.empty_like(x_hat) if want_x_next else None
     u8 = torch.empty(x_hat.shape, dtype=torch.uint8, device=dev) if want_u8 else None
     sums = torch.empty((R, 4), dtype=torch.int32, device=dev) if want_sums else None
-    L.check(L.lib().b200ns_heun_post(L.ptr(x_hat), L.ptr(F1), L.ptr(F2), L.ptr(x_next), L.ptr(u8), L.ptr(sums), R, Cc,
-                                     H * W, float(c_skip1), float(c_out1), float(t_hat), float(dt), float(c_skip2),
-                                     float(c_out2), float(t_next), L.cur_stream()), 'heun_post')
+    if USE_TORCH_OPS:
+        T.OPS.heun_post_(x_hat, F1, F2, x_next, u8, sums, float(c_skip1), float(c_out1), float(t_hat), float(dt),
+                         float(c_skip2), float(c_out2), float(t_next))
+    else:
+        L.check(L.lib().b200ns_heun_post(L.ptr(x_hat), L.ptr(F1), L.ptr(F2), L.ptr(x_next), L.ptr(u8), L.ptr(sums), R, Cc,
+                                         H * W, float(c_skip1), float(c_out1), float(t_hat), float(dt), float(c_skip2),
+                                         float(c_out2), float(t_next), L.cur_stream()), 'heun_post')
     _count()
     return x_next, u8, sums
 
@@ -84,7 +100,10 @@ def quantize_u8(x: torch.Tensor) -> torch.Tensor:
     _chk_cuda(x)
     _c(x, torch.float64)
     out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
-    L.check(L.lib().b200ns_quantize_u8(L.ptr(x), L.ptr(out), x.numel(), L.cur_stream()), 'quantize_u8')
+    if USE_TORCH_OPS:
+        T.OPS.quantize_u8_(x, out)
+    else:
+        L.check(L.lib().b200ns_quantize_u8(L.ptr(x), L.ptr(out), x.numel(), L.cur_stream()), 'quantize_u8')
     _count()
     return out
 
@@ -95,7 +114,10 @@ def channel_sums_u8(img: torch.Tensor) -> torch.Tensor:
     M, Cc = img.shape[0], img.shape[1]
     HW = img[0, 0].numel()
     sums = torch.empty((M, 4), dtype=torch.int32, device=img.device)
-    L.check(L.lib().b200ns_channel_sums_u8(L.ptr(img), L.ptr(sums), M, Cc, HW, L.cur_stream()), 'channel_sums_u8')
+    if USE_TORCH_OPS:
+        T.OPS.channel_sums_u8_(img, sums)
+    else:
+        L.check(L.lib().b200ns_channel_sums_u8(L.ptr(img), L.ptr(sums), M, Cc, HW, L.cur_stream()), 'channel_sums_u8')
     _count()
     return sums
 
@@ -104,7 +126,10 @@ def brightness_from_sums(sums: torch.Tensor, Cc: int, HW: int) -> torch.Tensor:
     _chk_cuda(sums)
     M = sums.shape[0]
     scores = torch.empty((M,), dtype=torch.float32, device=sums.device)
-    L.check(L.lib().b200ns_brightness_from_sums(L.ptr(sums), L.ptr(scores), M, Cc, HW, L.cur_stream()), 'brightness')
+    if USE_TORCH_OPS:
+        T.OPS.brightness_from_sums_(sums, scores, Cc, HW)
+    else:
+        L.check(L.lib().b200ns_brightness_from_sums(L.ptr(sums), L.ptr(scores), M, Cc, HW, L.cur_stream()), 'brightness')
     _count()
     return scores
 
@@ -116,7 +141,10 @@ def argmax_first(scores: torch.Tensor, idx_base: int = 0, want_key: bool = False
     N, b = scores.shape
     idx = torch.empty((b,), dtype=torch.int64, device=scores.device)
     key = torch.empty((b,), dtype=torch.int64, device=scores.device) if want_key else None
-    L.check(L.lib().b200ns_argmax_first(L.ptr(scores), N, b, idx_base, L.ptr(idx), L.ptr(key), L.cur_stream()), 'argmax')
+    if USE_TORCH_OPS:
+        T.OPS.argmax_first_(scores, idx_base, idx, key)
+    else:
+        L.check(L.lib().b200ns_argmax_first(L.ptr(scores), N, b, idx_base, L.ptr(idx), L.ptr(key), L.cur_stream()), 'argmax')
     _count()
     return (idx, key) if want_key else idx
 
@@ -128,7 +156,10 @@ def gather_rows(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     N, b = src.shape[0], src.shape[1]
     E = src[0, 0].numel()
     dst = torch.empty(src.shape[1:], dtype=torch.float64, device=src.device)
-    L.check(L.lib().b200ns_gather_rows(L.ptr(src), L.ptr(idx), L.ptr(dst), N, b, E, L.cur_stream()), 'gather_rows')
+    if USE_TORCH_OPS:
+        T.OPS.gather_rows_(src, idx, dst)
+    else:
+        L.check(L.lib().b200ns_gather_rows(L.ptr(src), L.ptr(idx), L.ptr(dst), N, b, E, L.cur_stream()), 'gather_rows')
     _count()
     return dst
 
@@ -138,7 +169,10 @@ def direction_norms(dirs: torch.Tensor) -> torch.Tensor:
     _c(dirs, torch.float64)
     R = dirs.shape[0]
     norms = torch.empty((R,), dtype=torch.float64, device=dirs.device)
-    L.check(L.lib().b200ns_direction_norms(L.ptr(dirs), L.ptr(norms), R, dirs[0].numel(), L.cur_stream()), 'norms')
+    if USE_TORCH_OPS:
+        T.OPS.direction_norms_(dirs, norms)
+    else:
+        L.check(L.lib().b200ns_direction_norms(L.ptr(dirs), L.ptr(norms), R, dirs[0].numel(), L.cur_stream()), 'norms')
     _count()
     return norms
 
@@ -150,8 +184,11 @@ def make_candidates(pivot, dirs, norms, scale, fresh_mask=None, fresh=None) -> t
     R, b = dirs.shape[0], pivot.shape[0]
     E = dirs[0].numel()
     cand = torch.empty_like(dirs)
-    L.check(L.lib().b200ns_make_candidates(L.ptr(pivot), L.ptr(dirs), L.ptr(norms), L.ptr(scale), L.ptr(fresh_mask),
-                                           L.ptr(fresh), L.ptr(cand), R, b, E, L.cur_stream()), 'make_candidates')
+    if USE_TORCH_OPS:
+        T.OPS.make_candidates_(pivot, dirs, norms, scale, fresh_mask, fresh, cand)
+    else:
+        L.check(L.lib().b200ns_make_candidates(L.ptr(pivot), L.ptr(dirs), L.ptr(norms), L.ptr(scale), L.ptr(fresh_mask),
+                                               L.ptr(fresh), L.ptr(cand), R, b, E, L.cur_stream()), 'make_candidates')
     _count()
     return cand
 
@@ -296,7 +333,10 @@ class Plan:
 
     def run(self, first: Optional[int] = None, last: Optional[int] = None):
         if first is None:
-            L.check(L.lib().b200ns_plan_run(self._h, L.cur_stream()), 'plan_run')
+            if USE_TORCH_OPS:
+                T.OPS.plan_run(int(self._h))
+            else:
+                L.check(L.lib().b200ns_plan_run(self._h, L.cur_stream()), 'plan_run')
             _count(len(self.labels))
         else:
             L.check(L.lib().b200ns_plan_run_range(self._h, first, last, L.cur_stream()), 'plan_run_range')
@@ -534,6 +574,101 @@ class Plan:
         self.labels.append(label)
         self.kinds.append('im2col')
         self.flops.append(0.0)
+
+    # ---- split-fp16 "precise" ops (csrc/precise.cuh): near-tie re-scoring of a search round's contenders
+    def add_gemm_prec(self, a: Sequence[torch.Tensor], segs: Sequence[Tuple[int, int, int, int]], w: torch.Tensor, N: int,
+                      out: torch.Tensor, *, acc_scale: float, bias=None, residual=None, out_scale=1.0, label='gemm_prec',
+                      flops: float = 0.0):
+        """a: 1-3 split-half NHWC tensors [B,H,W,2C]; segs: (src, taps, cstart, cblocks) over the 2C physical channels, laid
+        out by the caller as [hi|lo] x [Whi|Whi] + [hi] x [Wlo]; w: half [Npad, Ktot] (pre-scaled by 1/acc_scale);
+        out: split half [B,H,W,2N] or fp32 [..., N]; residual: split half [B,H,W,2N]."""
+        d = L.GemmDesc()
+        B, H, W_, _ = a[0].shape
+        for i, t in enumerate(a):
+            _c(t, torch.float16)
+            if t.shape[1] != H or t.shape[2] != W_:
+                raise RuntimeError('gemm_prec: sources must share the spatial dims')
+            d.a_ptr[i] = L.ptr(t)
+            d.a_channels[i] = t.shape[3]
+            d.a_stride[i] = 1
+        d.n_seg = len(segs)
+        for i, (src, taps, cstart, cblocks) in enumerate(segs):
+            d.seg[i] = L.KSeg(src, taps, cstart, cblocks)
+        d.batch, d.H, d.W = B, H, W_
+        _c(w, torch.float16)
+        d.w_ptr, d.N, d.Npad, d.Ktot = L.ptr(w), N, w.shape[0], w.shape[1]
+        d.bias = L.ptr(bias)
+        d.out_scale = float(out_scale)
+        d.out = L.ptr(out)
+        d.ld_out = out.shape[-1]
+        d.out_fp32 = 1 if out.dtype == torch.float32 else 0
+        if not d.out_fp32:
+            _c(out, torch.float16)
+            if out.shape[-1] != 2 * N:
+                raise RuntimeError('gemm_prec: split output must have 2N columns')
+            d.out_lo_off = N
+        if residual is not None:
+            _c(residual, torch.float16)
+            d.residual, d.ld_res, d.res_lo_off = L.ptr(residual), residual.shape[-1], residual.shape[-1] // 2
+        d.prec, d.acc_scale = 1, float(acc_scale)
+        self._k(*a, w, bias, residual, out)
+        L.check(L.lib().b200ns_plan_add_gemm(self._h, C.byref(d)), 'plan_add_gemm(prec)')
+        self.labels.append(label)
+        self.kinds.append('gemm_prec')
+        self.flops.append(flops)
+
+    def _gn_prec_desc(self, x, groups, eps, mean_rstd, gamma=None, beta=None, out=None, *, pre_add=None, film_scale=None,
+                      film_shift=None, b_emb=1, silu=False, resample=0, raw_out=None):
+        d = L.GnPrecDesc()
+        B, H, W_, _ = x[0].shape
+        for i, t in enumerate(x):
+            _c(t, torch.float16)
+            d.x_ptr[i] = L.ptr(t)
+            d.x_channels[i] = t.shape[3] // 2
+        d.batch, d.H, d.W, d.groups, d.eps = B, H, W_, groups, float(eps)
+        d.gamma = L.ptr(_c(gamma, torch.float32)) if gamma is not None else None
+        d.beta = L.ptr(_c(beta, torch.float32)) if beta is not None else None
+        d.pre_add = L.ptr(pre_add)
+        d.ld_pre_add = pre_add.stride(0) if pre_add is not None else 0
+        d.film_scale, d.film_shift = L.ptr(film_scale), L.ptr(film_shift)
+        d.ld_film = film_scale.stride(0) if film_scale is not None else 0
+        d.b_emb, d.silu, d.resample = b_emb, int(silu), resample
+        d.out = L.ptr(_c(out, torch.float16)) if out is not None else None
+        d.raw_out = L.ptr(raw_out)
+        d.mean_rstd = L.ptr(_c(mean_rstd, torch.float32))
+        self._k(*x, gamma, beta, pre_add, film_scale, film_shift, out, raw_out, mean_rstd)
+        return d
+
+    def add_gn_prec(self, x: Sequence[torch.Tensor], groups: int, eps: float, mean_rstd: torch.Tensor, gamma, beta, out, *,
+                    pre_add=None, film_scale=None, film_shift=None, b_emb=1, silu=True, resample=0, raw_out=None, label='gn_prec'):
+        """GroupNorm (+FiLM, +SiLU, +2x resample) over split-half NHWC tensors [B,H,W,2C_i]: one statistics launch (fp64)
+        and one apply launch (fp32, exact expf / division)."""
+        d = self._gn_prec_desc(x, groups, eps, mean_rstd, gamma, beta, out, pre_add=pre_add, film_scale=film_scale,
+                               film_shift=film_shift, b_emb=b_emb, silu=silu, resample=resample, raw_out=raw_out)
+        L.check(L.lib().b200ns_plan_add_gn_stats_prec(self._h, C.byref(d)), 'plan_add_gn_stats_prec')
+        self._misc('gn_stats_prec', f'{label}.stats')
+        L.check(L.lib().b200ns_plan_add_gn_apply_prec(self._h, C.byref(d)), 'plan_add_gn_apply_prec')
+        self._misc('gn_apply_prec', f'{label}.apply')
+
+    def add_attention_prec(self, qkv: torch.Tensor, out: torch.Tensor, batch: int, heads: int, Lseq: int, Cc: int,
+                           label='attention_prec'):
+        """qkv split half [batch*L, 2*3C] ([Q|K|V] head-major inside each plane); out split half [batch*L, 2C]."""
+        d = L.AttnPrecDesc()
+        d.qkv, d.ld, d.lo_off, d.k_col0, d.v_col0 = L.ptr(_c(qkv, torch.float16)), qkv.shape[-1], 3 * Cc, Cc, 2 * Cc
+        d.out, d.ld_out, d.out_lo_off = L.ptr(_c(out, torch.float16)), out.shape[-1], Cc
+        d.batch, d.heads, d.L, d.scale = batch, heads, Lseq, 0.0
+        self._k(qkv, out)
+        L.check(L.lib().b200ns_plan_add_attention_prec(self._h, C.byref(d)), 'plan_add_attention_prec')
+        self._misc('attention_prec', label)
+
+    def add_im2col_prec(self, x: torch.Tensor, out: torch.Tensor, label='im2col_prec'):
+        d = L.Im2colDesc()
+        B, Cc, H, W_ = x.shape
+        d.x, d.out = L.ptr(_c(x, torch.float32)), L.ptr(_c(out, torch.float16))
+        d.batch, d.C, d.H, d.W = B, Cc, H, W_
+        self._k(x, out)
+        L.check(L.lib().b200ns_plan_add_im2col_prec(self._h, C.byref(d)), 'plan_add_im2col_prec')
+        self._misc('im2col_prec', label)
 
     def _misc(self, kind, label):
         self.labels.append(label)

@@ -30,6 +30,7 @@ def exchange_winner(rows: torch.Tensor, idx: torch.Tensor, lo: int, hi: int, gro
     if gather is None:
         gather = lambda r, li: r[li, torch.arange(r.shape[1], device=r.device)]
     out = gather(rows, local)
-    out = out * owned.to(out.dtype).view(-1, *([1] * (out.dim() - 1)))
+    # masked select, not a multiplication: a diverged (Inf/NaN) losing candidate on a non-owner must not poison the sum
+    out = torch.where(owned.view(-1, *([1] * (out.dim() - 1))), out, torch.zeros_like(out))
     dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
     return out

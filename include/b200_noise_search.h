@@ -135,7 +135,7 @@ typedef struct {
   const void* a_ptr[3];      /* bf16 NHWC [batch,H,W,a_channels[i]]; unused = NULL */
   int32_t a_channels[3];
   int32_t n_seg;
-  b200ns_kseg seg[4];
+  b200ns_kseg seg[8];
   int32_t batch, H, W;
   const void* w_ptr;         /* bf16 [Npad, Ktot] */
   int32_t N, Npad, Ktot;
@@ -166,6 +166,14 @@ typedef struct {
    * phase (py, px) the 3x3 weights that read the same source pixel pre-summed into a 2x2 kernel (tap order a*2+c; source
    * pixel (y + py - 1 + a, x + px - 1 + c)).  gn_stats (optional) covers the high-res output.  No residual / fp32 / geglu. */
   int32_t upsample2x;
+  /* --- split-fp16 "precise" GEMM (near-tie re-scoring, see the block comment further down).  prec = 1: the A tensors and
+   * w_ptr hold IEEE half (activations [.., 2C] = hi plane | lo plane; the caller lays the K segments out as
+   * [hi|lo] x [Whi|Whi] + [hi] x [Wlo]); the accumulator is multiplied by acc_scale (weights are pre-scaled by a power of
+   * two); `out` is fp32 (out_fp32) or split half [M, ld_out] with the lo plane at column out_lo_off; `residual` is a
+   * split half tensor with its lo plane at column res_lo_off.  No gn_stats / geglu / upsample2x / strided sources. */
+  int32_t prec;
+  float acc_scale;
+  int32_t out_lo_off, res_lo_off;
 } b200ns_gemm_desc;
 int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d);
 /* Tuning aid: force the N tile width (64/128/192/256; 0 = cost model) of subsequently added bf16 GEMMs whose padded
@@ -278,6 +286,50 @@ typedef struct {
   int32_t batch, C, H, W;
 } b200ns_im2col_desc;
 int b200ns_plan_add_im2col(b200ns_plan* p, const b200ns_im2col_desc* d);
+
+/* ------------------------------------------------------------------ precise (fp32-faithful) re-scoring path
+ * The bf16 engine carries ~1e-4 of score noise; the reference evaluates the network in fp32 (networks.py:655-667) and the
+ * north star demands the SAME selected indices (edm/main.py:842).  The contenders within delta of a round's best score are
+ * therefore re-evaluated by these ops: activations in "split fp16" (v = hi + lo, two IEEE halves, NHWC [B,H,W,2C] with the
+ * lo plane at channel offset C), GEMMs on the same tcgen05 main loop over 3 K segments (b200ns_gemm_desc.prec),
+ * GroupNorm statistics in fp64 and SiLU / softmax with IEEE expf and division, attention in fp32 on the FMA pipe. */
+typedef struct {
+  const void* x_ptr[2];      /* split half NHWC [batch, H, W, 2*x_channels[i]]; second source optional (decoder concat) */
+  int32_t x_channels[2];     /* logical channels C_i */
+  int32_t batch, H, W, groups;
+  float eps;
+  const float* gamma;
+  const float* beta;
+  const float* pre_add;      /* fp32 [b_emb, ld_pre_add] or NULL (networks.py:175) */
+  int32_t ld_pre_add;
+  const float* film_scale;   /* fp32 [b_emb, ld_film] or NULL (networks.py:173) */
+  const float* film_shift;
+  int32_t ld_film, b_emb;
+  int32_t silu, resample;    /* as b200ns_gn_apply_desc */
+  void* out;                 /* split half [batch, H', W', 2C] */
+  void* raw_out;             /* split half or NULL */
+  float* mean_rstd;          /* fp32 [batch, groups, 2]: written by the stats op, read by the apply op */
+} b200ns_gn_prec_desc;
+/* per-(sample, group) mean / rstd in fp64 over hi + lo (+ pre_add) -> mean_rstd (networks.py:104-106) */
+int b200ns_plan_add_gn_stats_prec(b200ns_plan* p, const b200ns_gn_prec_desc* d);
+/* y = act(FiLM(norm(x))) with optional 2x resample, fp32 arithmetic, split half in / out */
+int b200ns_plan_add_gn_apply_prec(b200ns_plan* p, const b200ns_gn_prec_desc* d);
+
+/* Self-attention, head_dim 64, fp32 (networks.py:113-118): qkv split half [batch*L, ld] with the lo plane at column
+ * lo_off; inside a plane Q at column head*64, K at k_col0 + head*64, V at v_col0 + head*64; out split half
+ * [batch*L, ld_out] (head h at column h*64, lo plane at out_lo_off).  L % 64 == 0. */
+typedef struct {
+  const void* qkv;
+  int32_t ld, lo_off, k_col0, v_col0;
+  void* out;
+  int32_t ld_out, out_lo_off;
+  int32_t batch, heads, L;
+  float scale;               /* 0 = 1/sqrt(64) */
+} b200ns_attn_prec_desc;
+int b200ns_plan_add_attention_prec(b200ns_plan* p, const b200ns_attn_prec_desc* d);
+
+/* 3x3 im2col of the fp32 NCHW network input (Cin*9 <= 64) into split half [batch*H*W, 128] = [64 hi taps | 64 lo taps]. */
+int b200ns_plan_add_im2col_prec(b200ns_plan* p, const b200ns_im2col_desc* d);
 
 /* ------------------------------------------------------------------ classifier scorer glue
  * ImageNetScorer (edm/scorers.py:143-174) around EncoderUNetModel (edm/unet.py:701-912): the torso runs

@@ -101,7 +101,50 @@ def gen_unet(cfg, seed, name, batch, sigmas):
     save(name, dict(cfg=cfg, seed=seed, cases=outs))
 
 
-def gen_search(cfg, seed, name, method, N, K, num_steps, b=1, eps=0.0):
+class StepTrace:
+    """sys.setprofile hook around the reference's `step` closure (edm/main.py:82-96): records the fp64 state the
+    reference COMMITS per timestep -- x_cur going into, and x_next coming out of, the batch-b commit call
+    (edm/main.py:860) -- without touching the reference source.  The teacher states of the full-size parity test."""
+
+    def __init__(self, b):
+        self.b, self.x_cur, self.x_next, self._open = b, {}, {}, {}
+
+    def __call__(self, frame, event, arg):
+        code = frame.f_code
+        if code.co_name != 'step' or not code.co_filename.endswith('edm/main.py'):
+            return
+        if event == 'call':
+            loc = frame.f_locals
+            if loc['x_cur'].shape[0] == self.b:
+                i = int(loc['i'])
+                self.x_cur[i] = loc['x_cur'].detach().clone()
+                self._open[id(frame)] = i
+        elif event == 'return' and id(frame) in self._open:
+            self.x_next[self._open.pop(id(frame))] = arg[0].detach().clone()
+
+
+def ref_classifier_scorer(seed):
+    """The reference ImageNetScorer around a seeded full-size EncoderUNetModel (edm/scorers.py:56-174; __init__
+    bypassed: it downloads the pretrained checkpoint)."""
+    import scorers as ref_scorers
+    from unet import EncoderUNetModel
+    from oracle import classifier_oracle as CO
+    model = EncoderUNetModel(num_head_channels=64, use_scale_shift_norm=True, resblock_updown=True,
+                             pool='attention', **FULL_CLS)
+    model.load_state_dict(CO.seeded_classifier_state_dict(CO.classifier_param_shapes(**FULL_CLS), seed))
+    model.eval().requires_grad_(False)
+    sc = ref_scorers.ImageNetScorer.__new__(ref_scorers.ImageNetScorer)
+    torch.nn.Module.__init__(sc)
+    sc.dtype = torch.float32
+    sc.model = model
+    return sc
+
+
+def gen_search(cfg, seed, name, method, N, K, num_steps, b=1, eps=0.0, trace=False, scorer='brightness',
+               all_fresh=False):
+    """`trace`: also store the committed fp64 states (StepTrace).  `all_fresh`: supply fresh_{i}_{k}_{n} for every
+    candidate and record the reference's own `torch.rand(1)` Bernoulli draws (edm/main.py:751), so that 0 < eps < 1 is
+    reproducible on another device.  `scorer`: 'brightness' | 'imagenet' (seeded full-size classifier, seed + 10)."""
     import main as ref_main
     import scorers as ref_scorers
     net, spec, sd = ref_net(cfg, seed)
@@ -118,29 +161,58 @@ def gen_search(cfg, seed, name, method, N, K, num_steps, b=1, eps=0.0):
         for i in range(num_steps):
             pre[f'pivot_{i}'] = torch.randn(b, c, res, res, generator=g, dtype=torch.float64)
             pre[i] = torch.randn(b, K, N, c, res, res, generator=g, dtype=torch.float64)
-            if eps == 1.0:
+            if eps == 1.0 or all_fresh:
                 for k in range(K):
                     for n in range(N):
                         pre[f'fresh_{i}_{k}_{n}'] = torch.randn(b, c, res, res, generator=g, dtype=torch.float64)
     elif method == 'REJECTION_SAMPLING':
         for i in range(num_steps):
             pre[i] = torch.randn(b, N, c, res, res, generator=g, dtype=torch.float64)
-    rec = Rec(ref_scorers.BrightnessScorer())
+    rec = Rec(ref_scorers.BrightnessScorer() if scorer == 'brightness' else ref_classifier_scorer(seed + 10))
     params = dict(scorer=rec, N=N, K=K, eps=eps, lambda_param=0.15)
     kw = dict(S_churn=40, S_min=0.05, S_max=50, S_noise=1.003)
     out_png = os.path.join(tmp, 'o.png')
+    tr = StepTrace(b) if trace else None
+    draws = []
+    real_rand = torch.rand
+
+    def rec_rand(*a, **k):
+        r = real_rand(*a, **k)
+        if r.numel() == 1:
+            draws.append(float(r))
+        return r
+
+    import time
+    t0 = time.time()
     with contextlib.redirect_stdout(io.StringIO()):
-        ref_main.generate_image_grid(pkl, out_png, latents, labels, seed=seed, gridw=b, gridh=1,
-                                     device=torch.device('cpu'), num_steps=num_steps,
-                                     sampling_method=getattr(ref_main.SamplingMethod, method),
-                                     sampling_params=params, precomputed_noise=dict(pre), **kw)
+        torch.rand = rec_rand
+        if tr is not None:
+            sys.setprofile(tr)
+        try:
+            ref_main.generate_image_grid(pkl, out_png, latents, labels, seed=seed, gridw=b, gridh=1,
+                                         device=torch.device('cpu'), num_steps=num_steps,
+                                         sampling_method=getattr(ref_main.SamplingMethod, method),
+                                         sampling_params=params, precomputed_noise=dict(pre), **kw)
+        finally:
+            sys.setprofile(None)
+            torch.rand = real_rand
+    print(f'{name}: reference ran {time.time() - t0:.0f} s')
+    extra = {}
+    if tr is not None:
+        extra['x_cur_steps'] = torch.stack([tr.x_cur[i] for i in range(num_steps)])
+        extra['x_next_steps'] = torch.stack([tr.x_next[i] for i in range(num_steps)])
+    if all_fresh:
+        extra['bernoulli_draws'] = torch.tensor(draws, dtype=torch.float32)       # [num_steps*K*N] in call order
+        assert len(draws) == num_steps * K * N, len(draws)
     scales = {f'{i}_{k}_{n}': hash(f'{i}_{k}_{n}') % 1000 / 1000.0
               for i in range(num_steps) for k in range(K) for n in range(N)}
     # noise is regenerated by the test from (seed+2) in the same draw order; store only outputs
+    small = N * b * res * res <= 16384
     save(name, dict(cfg=cfg, seed=seed, method=method, N=N, K=K, num_steps=num_steps, b=b, eps=eps,
-                    lambda_param=0.15, sampler_kw=kw, scales=scales,
+                    lambda_param=0.15, sampler_kw=kw, scales=scales, scorer=scorer, all_fresh=all_fresh, **extra,
                     score_calls=[r for _, r in rec.calls[:-1]],
-                    scored_u8_first=rec.calls[0][0], scored_u8_last=rec.calls[-2][0] if len(rec.calls) > 1 else None,
+                    scored_u8_first=rec.calls[0][0] if small else None,
+                    scored_u8_last=rec.calls[-2][0] if (small and len(rec.calls) > 1) else None,
                     final_image=rec.calls[-1][0], final_scores=rec.calls[-1][1]))
 
 
@@ -230,14 +302,32 @@ def gen_scalar():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--full', action='store_true', help='also the full-size ADM-64 / DDPM++-32 forwards (slow)')
+    ap.add_argument('--search-full', nargs='*', default=None, metavar='JOB',
+                    help='ONLY the ADM-64 N=64 search fixtures (the north-star config; ~45 CPU-minutes each on 8 cores): '
+                         'any of eps0 (18 steps, brightness), eps04 (6 steps, eps=0.4, recorded Bernoulli draws), '
+                         'imagenet (4 steps, classifier scorer in the loop); no names = all three')
     args = ap.parse_args()
     assert os.environ.get('PYTHONHASHSEED') == '0', 'run with PYTHONHASHSEED=0'
     os.makedirs(GOLD, exist_ok=True)
+    if args.search_full is not None:
+        jobs = args.search_full or ['eps0', 'imagenet', 'eps04']
+        if 'eps0' in jobs:
+            gen_search(FULL_ADM, 1234, 'search_eps_greedy_adm64_N64.pt', 'EPS_GREEDY', N=64, K=1, num_steps=18, b=1,
+                       trace=True)
+        if 'imagenet' in jobs:
+            gen_search(FULL_ADM, 1234, 'search_imagenet_adm64_N64.pt', 'EPS_GREEDY', N=64, K=1, num_steps=4, b=1,
+                       trace=True, scorer='imagenet')
+        if 'eps04' in jobs:
+            gen_search(FULL_ADM, 1234, 'search_eps04_adm64_N64.pt', 'EPS_GREEDY', N=64, K=1, num_steps=6, b=1, eps=0.4,
+                       trace=True, all_fresh=True)
+        return
     gen_scalar()
     gen_unet(TINY_ADM, 11, 'unet_tiny_adm.pt', batch=2, sigmas=[80.0, 1.5, 0.01])
     gen_unet(TINY_SONG, 12, 'unet_tiny_song.pt', batch=2, sigmas=[40.0, 0.3])
     gen_search(TINY_ADM, 11, 'search_eps_greedy_tiny.pt', 'EPS_GREEDY', N=4, K=2, num_steps=6, b=2)
     gen_search(TINY_ADM, 11, 'search_eps1_tiny.pt', 'EPS_GREEDY', N=3, K=1, num_steps=4, b=1, eps=1.0)
+    gen_search(TINY_ADM, 11, 'search_eps04_tiny.pt', 'EPS_GREEDY', N=8, K=2, num_steps=6, b=2, eps=0.4, trace=True,
+               all_fresh=True)
     gen_search(TINY_ADM, 11, 'search_rejection_tiny.pt', 'REJECTION_SAMPLING', N=4, K=1, num_steps=5, b=2)
     gen_search(TINY_SONG, 12, 'search_naive_tiny_song.pt', 'NAIVE', N=1, K=1, num_steps=18, b=1)
     gen_mcts(TINY_ADM, 11, 'search_mcts_tiny.pt', N=2, S=20, num_steps=4, b=1)

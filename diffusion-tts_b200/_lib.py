@@ -23,7 +23,8 @@ class GemmDesc(C.Structure):
                 ('batch', c_i32), ('H', c_i32), ('W', c_i32), ('w_ptr', c_vp), ('N', c_i32), ('Npad', c_i32),
                 ('Ktot', c_i32), ('bias', c_vp), ('residual', c_vp), ('ld_res', c_i32), ('out_scale', c_f32),
                 ('out', c_vp), ('ld_out', c_i32), ('out_fp32', c_i32), ('gn_stats', c_vp), ('reverse', c_i32), ('a_stride', c_i32 * 3), ('geglu', c_i32), ('upsample2x', c_i32),
-                ('prec', c_i32), ('acc_scale', c_f32), ('out_lo_off', c_i32), ('res_lo_off', c_i32)]
+                ('prec', c_i32), ('acc_scale', c_f32), ('out_lo_off', c_i32), ('res_lo_off', c_i32),
+                ('prec_splits', c_i32), ('prec_bn', c_i32), ('prec_partial', c_vp)]
 
 
 class GnStatsDesc(C.Structure):
@@ -43,7 +44,8 @@ class GnPrecDesc(C.Structure):
     _fields_ = [('x_ptr', c_vp * 2), ('x_channels', c_i32 * 2), ('batch', c_i32), ('H', c_i32), ('W', c_i32),
                 ('groups', c_i32), ('eps', c_f32), ('gamma', c_vp), ('beta', c_vp), ('pre_add', c_vp),
                 ('ld_pre_add', c_i32), ('film_scale', c_vp), ('film_shift', c_vp), ('ld_film', c_i32), ('b_emb', c_i32),
-                ('silu', c_i32), ('resample', c_i32), ('out', c_vp), ('raw_out', c_vp), ('mean_rstd', c_vp)]
+                ('silu', c_i32), ('resample', c_i32), ('out', c_vp), ('raw_out', c_vp), ('mean_rstd', c_vp), ('partial', c_vp),
+                ('ticket', c_vp)]
 
 
 class AttnPrecDesc(C.Structure):
@@ -105,6 +107,7 @@ SIGNATURES = {
     'b200ns_plan_add_attention': (C.c_int, [c_vp, C.POINTER(AttnDesc)]),
     'b200ns_plan_add_linear': (C.c_int, [c_vp, C.POINTER(LinearDesc)]),
     'b200ns_plan_add_im2col': (C.c_int, [c_vp, C.POINTER(Im2colDesc)]),
+    'b200ns_debug_prec_nolo': (C.c_int, [C.c_int]),
     'b200ns_plan_add_im2col_prec': (C.c_int, [c_vp, C.POINTER(Im2colDesc)]),
     'b200ns_plan_add_gn_stats_prec': (C.c_int, [c_vp, C.POINTER(GnPrecDesc)]),
     'b200ns_plan_add_gn_apply_prec': (C.c_int, [c_vp, C.POINTER(GnPrecDesc)]),

@@ -364,6 +364,11 @@ int launch_gemm_prec_t(const GemmOp& g, cudaStream_t st) {
   }
   gemm_prec_kernel<BN><<<dim3(g.grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st>>>(g.tmA[0], g.tmA[1], g.tmA[2], g.tmB, g.args, g.pargs);
   CK_LAUNCH("gemm_prec_kernel");
+  if (g.pargs.splits > 1) {          // add the K slices in order, then bias / residual / scale / split store
+    const int64_t items = static_cast<int64_t>(g.args.M) * ((g.args.N + 7) / 8);
+    gemm_prec_finish_kernel<<<grid_for(items, 256, 148 * 8), 256, 0, st>>>(g.args, g.pargs);
+    CK_LAUNCH("gemm_prec_finish_kernel");
+  }
   return 0;
 }
 int launch_gemm_prec(const GemmOp& g, cudaStream_t st) {
@@ -492,7 +497,7 @@ int run_op(const Op& op, cudaStream_t st) {
       if (op.attn.vrow) return op.attn.KT == 128 ? launch_attn_v3<128>(op.attn, st) : launch_attn_v3<64>(op.attn, st);
       return op.attn.KT == 128 ? launch_attn_t<128, false>(op.attn, st) : launch_attn_t<64, false>(op.attn, st);
     case OP_GN_STATS_PREC:
-      gn_stats_prec_kernel<<<dim3(op.gnp.args.groups, op.gnp.args.batch), 256, 0, st>>>(op.gnp.args);
+      gn_stats_prec_kernel<<<dim3(op.gnp.args.splits, op.gnp.args.batch), (op.gnp.args.C / 8) * op.gnp.args.PY, 0, st>>>(op.gnp.args);
       CK_LAUNCH("gn_stats_prec_kernel");
       return 0;
     case OP_GN_APPLY_PREC:
@@ -846,6 +851,12 @@ int b200ns_plan_run(b200ns_plan* p, void* stream) {
   return b200ns_plan_run_range(p, 0, static_cast<int>(p->ops.size()), stream);
 }
 
+int b200ns_debug_prec_nolo(int on) {
+  const int v = on ? 1 : 0;
+  CK(cudaMemcpyToSymbol(g_prec_nolo, &v, sizeof(int)));
+  return 0;
+}
+
 static int g_force_bn = 0;
 void b200ns_debug_force_tile_width(int bn) { g_force_bn = bn; }
 
@@ -868,7 +879,9 @@ int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d) {
     if (d->upsample2x || d->geglu || d->gn_stats != nullptr) return fail("gemm(prec): no upsample2x / geglu / gn_stats");
     if (!d->out_fp32 && (d->N % 32 || d->out_lo_off % 8)) return fail("gemm(prec): split output needs N % 32 == 0 and out_lo_off % 8 == 0");
     if (d->residual != nullptr && (d->res_lo_off % 8 || d->ld_res % 8)) return fail("gemm(prec): residual planes must be 16-byte aligned");
-    return add_gemm_part(p, d, 0, d->N);
+    if (d->prec_splits > 1 && d->prec_partial == nullptr) return fail("gemm(prec): split-K needs prec_partial");
+    if (d->prec_bn != 0 && (d->Npad % d->prec_bn)) return fail("gemm(prec): prec_bn must divide Npad");
+    return add_gemm_part(p, d, d->prec_bn, d->N);
   }
   if (!d->upsample2x) return add_gemm_cols(p, d);
   // out [batch, 2H, 2W, ld_out] = conv3x3(nearest_up2(A)) as 4 phase launches of a 2x2-tap conv over the low-res A:
@@ -1013,6 +1026,16 @@ static int add_gemm_part(b200ns_plan* p, const b200ns_gemm_desc* d, int BN_force
   g.pargs.res = d->prec ? reinterpret_cast<const __half*>(d->residual) : nullptr;
   g.pargs.ld_res = d->ld_res;
   g.pargs.res_lo_off = d->res_lo_off;
+  {
+    int sp = (d->prec && d->prec_splits > 1) ? d->prec_splits : 1;
+    if (sp > nkb) sp = nkb;
+    const int per = (nkb + sp - 1) / sp;
+    sp = (nkb + per - 1) / per;                  // no empty slice
+    g.pargs.splits = sp;
+    g.pargs.kb_per_split = per;
+    g.pargs.partial = d->prec ? d->prec_partial : nullptr;
+    g.pargs.ld_partial = a.n_tiles * BN;
+  }
   a.residual = d->prec ? nullptr : reinterpret_cast<const __nv_bfloat16*>(d->residual);
   a.ld_res = d->ld_res;
   a.out_scale = d->out_scale;
@@ -1076,7 +1099,7 @@ static int add_gemm_part(b200ns_plan* p, const b200ns_gemm_desc* d, int BN_force
     int rc = make_tmap(&g.tmB, d->w_ptr, 2, dims, box);
     if (rc) return rc;
   }
-  const int tiles = a.m_tiles * a.n_tiles;
+  const int tiles = a.m_tiles * a.n_tiles * (g.prec ? g.pargs.splits : 1);
   g.grid = tiles < num_sms() ? tiles : num_sms();
   if (g.cl2) {
     const int super_tiles = ((a.m_tiles + 1) / 2) * a.n_tiles;
@@ -1482,6 +1505,15 @@ static int fill_gn_prec(GnPrecArgs& a, const b200ns_gn_prec_desc* d) {
   a.raw_out = reinterpret_cast<__half*>(d->raw_out);
   a.mean_rstd = reinterpret_cast<float2*>(d->mean_rstd);
   a.batch = d->batch;
+  a.partial = d->partial;
+  a.ticket = d->ticket;
+  // pixel splits: a function of the image size ONLY (batch-size / batch-position invariance of the reduction order)
+  const int HW = d->H * d->W;
+  a.splits = HW / 64 < 1 ? 1 : (HW / 64 > 16 ? 16 : HW / 64);
+  if (HW % a.splits) a.splits = 1;
+  const int VC = a.C / 8;
+  if (a.C > 2048) return fail("gn_prec: more than 2048 channels");
+  a.PY = 256 / VC < 1 ? 1 : 256 / VC;
   return 0;
 }
 
@@ -1491,6 +1523,7 @@ int b200ns_plan_add_gn_stats_prec(b200ns_plan* p, const b200ns_gn_prec_desc* d) 
   int rc = fill_gn_prec(op.gnp.args, d);
   if (rc) return rc;
   if (d->batch > 65535) return fail("gn_stats_prec: batch > 65535");
+  if (d->partial == nullptr || d->ticket == nullptr) return fail("gn_stats_prec: partial / ticket scratch missing");
   p->push(op);
   return 0;
 }

@@ -18,9 +18,13 @@
 
 namespace b200 {
 
+// experiment switch (b200ns_debug_prec_nolo): 1 = drop the lo plane, i.e. plain fp16 storage -- measures what a single-plane
+// fp16 engine would give against the reference (tools/measure_precise_error.py)
+__device__ int g_prec_nolo = 0;
+
 DEVINL void split_h(float v, __half& hi, __half& lo) {
   hi = __float2half_rn(v);
-  lo = __float2half_rn(v - __half2float(hi));
+  lo = g_prec_nolo ? __float2half_rn(0.f) : __float2half_rn(v - __half2float(hi));
 }
 DEVINL void unpack8h(const uint4& u, float (&f)[8]) {
   const __half2* h = reinterpret_cast<const __half2*>(&u);
@@ -51,16 +55,23 @@ DEVINL void store8_split(__half* p, int lo_off, const float (&f)[8]) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// GEMM / implicit-GEMM conv with split-fp16 output.  Same TMA producer and MMA issuer as gemm_conv_kernel
-// (GemmArgs.fp16 = 1 selects the half-precision instruction descriptor); the epilogue is deliberately simple
-// (contender batches are tiny): 4 warps, TMEM -> registers -> (acc * acc_scale + bias + residual) * out_scale
-// -> hi / lo halves (or fp32) -> 16-byte global stores.
+// GEMM / implicit-GEMM conv with split-fp16 output.  Same tcgen05 main loop as gemm_conv_kernel (GemmArgs.fp16 = 1
+// selects the half-precision instruction descriptor), plus SPLIT-K: contender batches are tiny (M = a few hundred rows at
+// the 8x8 / 16x16 levels against K up to 41 472), so the K range of every output tile is cut into `splits` slices that run
+// on different SMs; each slice stores its fp32 partial tile and gemm_prec_finish_kernel adds the slices IN ORDER and applies
+// (acc * acc_scale + bias + residual) * out_scale -> hi / lo halves (or fp32).  `splits` is a function of the layer alone
+// (never of the batch), so a sample's bits do not depend on how many contenders share its launch.  splits == 1: the
+// epilogue finishes the tile itself.
 // ---------------------------------------------------------------------------------------------------------
 struct GemmPrecArgs {
   float acc_scale;               // weights are stored pre-multiplied by a power of two (keeps Wlo out of the half subnormals)
   int out_lo_off;                // column offset of the lo plane in `out` (halves); unused for fp32 output
   const __half* res;             // split-fp16 residual [M, ld_res] or null
   int ld_res, res_lo_off;
+  int splits;                    // K slices per output tile
+  int kb_per_split;              // K blocks (of 64) per slice
+  float* partial;                // [splits][m_tiles*128][n_tiles*BN] fp32 (splits > 1)
+  int ld_partial;                // n_tiles*BN
 };
 
 template <int BN>
@@ -70,6 +81,127 @@ struct GemmPrecCfg {
   static constexpr int SMEM_BYTES = STAGES * Base::STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int THREADS = 192;
 };
+
+// work item `it` of this CTA -> (m tile, n tile, K slice); K slice fastest: the slices of one tile run side by side
+DEVINL bool gemm_prec_item(const GemmArgs& a, const GemmPrecArgs& pa, int it, int& mt, int& nt, int& ks) {
+  const int total = a.m_tiles * a.n_tiles * pa.splits;
+  const int w = blockIdx.x + it * gridDim.x;
+  if (w >= total) return false;
+  ks = w % pa.splits;
+  const int tl = w / pa.splits;
+  mt = tl / a.n_tiles;
+  nt = tl % a.n_tiles;
+  return true;
+}
+
+template <int BN>
+DEVINL void gemm_prec_producer(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmA2, const CUtensorMap& tmB,
+                               const GemmArgs& a, const GemmPrecArgs& pa, uint8_t* smem_a, uint8_t* smem_b, uint64_t* full_bar,
+                               uint64_t* empty_bar) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  int stage = 0;
+  uint32_t phase = 0;
+  int mt, nt, ks;
+  for (int it = 0; gemm_prec_item(a, pa, it, mt, nt, ks); ++it) {
+    const int kb0 = ks * pa.kb_per_split, kb1 = min(a.nkb, kb0 + pa.kb_per_split);
+    int n0, y0, x0 = 0;
+    if (a.tiles_per_img > 0) {
+      n0 = mt / a.tiles_per_img;
+      const int r = mt % a.tiles_per_img;
+      y0 = (r / a.x_chunks) * a.tileH;
+      x0 = (r % a.x_chunks) * 128;
+    } else {
+      n0 = mt * a.tileN;
+      y0 = 0;
+    }
+    int kb = 0;
+    for (int s = 0; s < a.n_seg; ++s) {
+      const KSeg sg = a.seg[s];
+      const CUtensorMap* tm = sg.src == 0 ? &tmA0 : (sg.src == 1 ? &tmA1 : &tmA2);
+      if (kb + sg.taps * sg.cblocks <= kb0 || kb >= kb1) {      // the whole segment lies outside this slice
+        kb += sg.taps * sg.cblocks;
+        continue;
+      }
+      for (int tap = 0; tap < sg.taps; ++tap) {
+        const int dy = sg.taps == 9 ? tap / 3 - 1 : 0;
+        const int dx = sg.taps == 9 ? tap % 3 - 1 : 0;
+        for (int cb = 0; cb < sg.cblocks; ++cb, ++kb) {
+          if (kb < kb0 || kb >= kb1) continue;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_4d(smem_a + stage * Cfg::A_BYTES, tm, &full_bar[stage], sg.cstart + cb * 64, x0 + dx, y0 + dy, n0);
+          tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * 64, nt * BN);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int BN>
+DEVINL void gemm_prec_mma(const GemmArgs& a, const GemmPrecArgs& pa, uint8_t* smem_a, uint8_t* smem_b, uint64_t* full_bar,
+                          uint64_t* empty_bar, uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t tmem_base) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  const uint32_t idesc = umma_idesc_f16(128, BN);
+  int stage = 0;
+  uint32_t phase = 0;
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  int mt, nt, ks;
+  for (int it = 0; gemm_prec_item(a, pa, it, mt, nt, ks); ++it) {
+    const int kb0 = ks * pa.kb_per_split, kb1 = min(a.nkb, kb0 + pa.kb_per_split);
+    mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + acc * BN;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * Cfg::A_BYTES));
+      const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * Cfg::B_BYTES));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > kb0) || (k != 0));
+      umma_commit(&empty_bar[stage]);
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    umma_commit(&tfull_bar[acc]);
+    if (++acc == 2) {
+      acc = 0;
+      acc_phase ^= 1;
+    }
+  }
+}
+
+// (acc * acc_scale + bias + residual) * out_scale for 8 consecutive columns of row m -> split halves or fp32
+DEVINL void gemm_prec_store8(const GemmArgs& a, const GemmPrecArgs& pa, int m, int n, float (&v)[8]) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    v[e] = __fmul_rn(v[e], pa.acc_scale);
+    if (a.bias != nullptr) v[e] += __ldg(a.bias + n + e);
+  }
+  if (pa.res != nullptr) {
+    float f[8];
+    load8_split(pa.res + static_cast<size_t>(m) * pa.ld_res + n, pa.res_lo_off, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] += f[e];
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] *= a.out_scale;
+  if (a.out_fp32) {
+    float* o = reinterpret_cast<float*>(a.out) + static_cast<size_t>(m) * a.ld_out + n;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = v[e];
+  } else {
+    store8_split(reinterpret_cast<__half*>(a.out) + static_cast<size_t>(m) * a.ld_out + n, pa.out_lo_off, v);
+  }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(192, 1)
@@ -116,17 +248,17 @@ gemm_prec_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) gemm_producer<BN>(tmA0, tmA1, tmA2, tmB, a, smem_a, smem_b, full_bar, empty_bar);
+    if (lane == 0) gemm_prec_producer<BN>(tmA0, tmA1, tmA2, tmB, a, pa, smem_a, smem_b, full_bar, empty_bar);
   } else if (warp == 1) {
-    if (lane == 0) gemm_mma<BN>(a, smem_a, smem_b, full_bar, empty_bar, tfull_bar, tempty_bar, tmem_base);
+    if (lane == 0) gemm_prec_mma<BN>(a, pa, smem_a, smem_b, full_bar, empty_bar, tfull_bar, tempty_bar, tmem_base);
   } else {
     // epilogue: warps 2..5, one per TMEM lane quarter (a warp may only touch lanes 32*(warp%4) ..)
     const int q = warp & 3;
     const int row = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    int mt, nt;
-    for (int it = 0; gemm_tile_at<false>(a, it, mt, nt); ++it) {
+    int mt, nt, ks;
+    for (int it = 0; gemm_prec_item(a, pa, it, mt, nt, ks); ++it) {
       const int m = mt * 128 + row;
       const bool m_ok = m < a.M;
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -136,7 +268,11 @@ gemm_prec_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         uint32_t r[16];
         tmem_ld16(t_row, r);
         tmem_ld_wait();
-        if (m_ok) {
+        if (pa.splits > 1) {
+          float* o = pa.partial + (static_cast<size_t>(ks) * a.m_tiles * 128 + m) * pa.ld_partial + nt * BN;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(r[j]);
+        } else if (m_ok) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int n = nt * BN + j;
@@ -163,36 +299,19 @@ gemm_prec_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           tmem_ld32(t_row + j * 32, r);
           tmem_ld_wait();
           const int n0 = nt * BN + j * 32;
-          if (m_ok && n0 < a.N) {                  // N is a multiple of 32 for split output (checked on the host)
-            float v[32];
+          if (pa.splits > 1) {                       // raw fp32 partial tile (rows past M are zero: TMA zero fill)
+            float4* o = reinterpret_cast<float4*>(pa.partial + (static_cast<size_t>(ks) * a.m_tiles * 128 + m) * pa.ld_partial + n0);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              v[i] = __fmul_rn(__uint_as_float(r[i]), pa.acc_scale);
-              if (a.bias != nullptr) v[i] += __ldg(a.bias + n0 + i);
-            }
-            if (pa.res != nullptr) {
-              const __half* rp = pa.res + static_cast<size_t>(m) * pa.ld_res + n0;
+            for (int i = 0; i < 8; ++i)
+              o[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                                 __uint_as_float(r[4 * i + 3]));
+          } else if (m_ok && n0 < a.N) {             // N is a multiple of 32 for split output (checked on the host)
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float f[8];
-                load8_split(rp + 8 * i, pa.res_lo_off, f);
+            for (int i = 0; i < 4; ++i) {
+              float v[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[8 * i + e] += f[e];
-              }
-            }
-            if (a.out_fp32) {
-              float* o = reinterpret_cast<float*>(a.out) + static_cast<size_t>(m) * a.ld_out + n0;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = v[i] * a.out_scale;
-            } else {
-              __half* o = reinterpret_cast<__half*>(a.out) + static_cast<size_t>(m) * a.ld_out + n0;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float f[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = v[8 * i + e] * a.out_scale;
-                store8_split(o + 8 * i, pa.out_lo_off, f);
-              }
+              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * i + e]);
+              gemm_prec_store8(a, pa, m, n0 + 8 * i, v);
             }
           }
         }
@@ -212,6 +331,43 @@ gemm_prec_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// splits > 1: out = finish(sum over slices in order).  One thread per (row, 8 columns); N % 8 == 0 or the fp32 N < 8 case.
+__global__ void __launch_bounds__(256) gemm_prec_finish_kernel(const GemmArgs a, const GemmPrecArgs pa) {
+  const int n8 = (a.N + 7) >> 3;
+  const long long total = static_cast<long long>(a.M) * n8;
+  const size_t slice = static_cast<size_t>(a.m_tiles) * 128 * pa.ld_partial;
+  for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * 256) {
+    const int m = static_cast<int>(idx / n8);
+    const int n = static_cast<int>(idx % n8) * 8;
+    const float* p = pa.partial + static_cast<size_t>(m) * pa.ld_partial + n;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < pa.splits; ++s) {
+      const float4 x0 = *reinterpret_cast<const float4*>(p + s * slice);
+      const float4 x1 = *reinterpret_cast<const float4*>(p + s * slice + 4);
+      v[0] += x0.x; v[1] += x0.y; v[2] += x0.z; v[3] += x0.w;
+      v[4] += x1.x; v[5] += x1.y; v[6] += x1.z; v[7] += x1.w;
+    }
+    if (n + 8 <= a.N) {
+      gemm_prec_store8(a, pa, m, n, v);
+    } else {                                         // ragged tail (the 3-channel fp32 output conv)
+      for (int e = 0; n + e < a.N; ++e) {
+        float y = __fmul_rn(v[e], pa.acc_scale);
+        if (a.bias != nullptr) y += __ldg(a.bias + n + e);
+        y *= a.out_scale;
+        if (a.out_fp32) {
+          reinterpret_cast<float*>(a.out)[static_cast<size_t>(m) * a.ld_out + n + e] = y;
+        } else {
+          __half hi, lo;
+          split_h(y, hi, lo);
+          __half* o = reinterpret_cast<__half*>(a.out) + static_cast<size_t>(m) * a.ld_out + n + e;
+          o[0] = hi;
+          o[pa.out_lo_off] = lo;
+        }
+      }
+    }
   }
 }
 
@@ -236,46 +392,81 @@ struct GnPrecArgs {
   __half* raw_out;           // split, the resampled un-normalised input, or null
   float2* mean_rstd;         // [batch, groups]
   int batch;
+  double* partial;           // [batch, splits, groups, 2] fp64 scratch of the statistics kernel
+  int splits, PY;            // pixel splits per sample (a function of H*W only); pixel rows per CTA pass
+  int* ticket;               // [batch] zero-initialised arrival counters (reset by the last CTA of a sample)
 };
 
-// grid (groups, batch), 256 threads: fp64 sums of (hi + lo [+ pre_add]) over the group, fixed order
+// grid (splits, batch), (C/8)*PY threads: fp64 sums of (hi + lo [+ pre_add]) per (sample, split, group) in a fixed order; the
+// LAST CTA of a sample to finish (ticket) adds the splits in order and writes (mean, rstd) -- which CTA is last does not
+// matter, the summation order is fixed, so the result is bit-identical at any batch position.
 __global__ void __launch_bounds__(256) gn_stats_prec_kernel(const GnPrecArgs a) {
-  __shared__ double s_s[8], s_q[8];
-  const int g = blockIdx.x, bi = blockIdx.y;
+  __shared__ double s_sum[2048];
+  __shared__ double s_sq[2048];
+  __shared__ int s_last;
+  const int VC = a.C >> 3;
+  const int vx = threadIdx.x % VC, py = threadIdx.x / VC;
+  const int split = blockIdx.x, bi = blockIdx.y;
   const int HW = a.H * a.W;
-  const int c0 = g * a.cpg;
-  double ds = 0.0, dq = 0.0;
-  for (int p = threadIdx.x; p < HW; p += 256) {
-    for (int j = 0; j < a.cpg; ++j) {
-      const int c = c0 + j;
-      float v;
-      if (c < a.C0) {
-        const __half* s = a.x0 + (static_cast<size_t>(bi) * HW + p) * (2 * a.C0) + c;
-        v = __half2float(s[0]) + __half2float(s[a.C0]);
-      } else {
-        const __half* s = a.x1 + (static_cast<size_t>(bi) * HW + p) * (2 * a.C1) + (c - a.C0);
-        v = __half2float(s[0]) + __half2float(s[a.C1]);
-      }
-      if (a.pre_add != nullptr) v += a.pre_add[static_cast<size_t>(bi % a.b_emb) * a.ld_pre_add + c];
-      ds += static_cast<double>(v);
-      dq += static_cast<double>(v) * static_cast<double>(v);
+  const int ppb = HW / a.splits;
+  const int c = vx * 8;
+  const __half* src;
+  int Cs;
+  if (c < a.C0) {
+    src = a.x0 + c;
+    Cs = a.C0;
+  } else {
+    src = a.x1 + (c - a.C0);
+    Cs = a.C1;
+  }
+  src += (static_cast<size_t>(bi) * HW + static_cast<size_t>(split) * ppb) * (2 * Cs);
+  float pa[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (a.pre_add != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pa[j] = a.pre_add[static_cast<size_t>(bi % a.b_emb) * a.ld_pre_add + c + j];
+  }
+  double s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ss[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int p = py; p < ppb; p += a.PY) {
+    float f[8];
+    load8_split(src + static_cast<size_t>(p) * (2 * Cs), Cs, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const double v = static_cast<double>(f[j] + pa[j]);
+      s[j] += v;
+      ss[j] += v * v;
     }
   }
+  // level 1: per-channel sums over py (fixed order) through shared memory, PY*C <= 2048 doubles
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    ds += __shfl_xor_sync(0xffffffffu, ds, o);
-    dq += __shfl_xor_sync(0xffffffffu, dq, o);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    s_s[threadIdx.x >> 5] = ds;
-    s_q[threadIdx.x >> 5] = dq;
+  for (int j = 0; j < 8; ++j) {
+    s_sum[py * a.C + c + j] = s[j];
+    s_sq[py * a.C + c + j] = ss[j];
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  // level 2: thread g adds its group's channels (and pixel rows) in a fixed order
+  for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
+    double ds = 0.0, dq = 0.0;
+    for (int cc = g * a.cpg; cc < (g + 1) * a.cpg; ++cc)
+      for (int y = 0; y < a.PY; ++y) {
+        ds += s_sum[y * a.C + cc];
+        dq += s_sq[y * a.C + cc];
+      }
+    double* o = a.partial + ((static_cast<size_t>(bi) * a.splits + split) * a.groups + g) * 2;
+    o[0] = ds;
+    o[1] = dq;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(a.ticket + bi, 1) == a.splits - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
     double ts = 0.0, tq = 0.0;
-    for (int w = 0; w < 8; ++w) {
-      ts += s_s[w];
-      tq += s_q[w];
+    for (int sp = 0; sp < a.splits; ++sp) {
+      const volatile double* o = a.partial + ((static_cast<size_t>(bi) * a.splits + sp) * a.groups + g) * 2;
+      ts += o[0];
+      tq += o[1];
     }
     const double n = static_cast<double>(HW) * a.cpg;
     const double mean = ts / n;
@@ -284,6 +475,7 @@ __global__ void __launch_bounds__(256) gn_stats_prec_kernel(const GnPrecArgs a) 
     a.mean_rstd[static_cast<size_t>(bi) * a.groups + g] =
         make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps))));
   }
+  if (threadIdx.x == 0) a.ticket[bi] = 0;
 }
 
 DEVINL float silu_exact(float x) { return x / (1.0f + expf(-x)); }

@@ -71,7 +71,7 @@ class SearchRecord:
 # round's best; contenders are re-scored by the fp32-faithful engine (precise.py) and the argmax is taken over the refined
 # scores.  DELTA bounds the DIFFERENCE of two candidates' bf16 score errors (the error common to all candidates of a round
 # cancels in the comparison): measured on the ADM-64 N=64 reference fixture, see DESIGN.md 2.
-ESCALATION_DELTA = 4e-4
+ESCALATION_KAPPA = 1.25
 MAX_CONTENDERS = 8
 
 
@@ -182,51 +182,72 @@ def _key_score(key: torch.Tensor) -> torch.Tensor:
 
 
 def _escalate(scorer, stepper: HeunStepper, x_cur, local, scores, key, idx, i, lo, hi, b, labels_rows, C, HW, shard,
-              delta: float, max_rows: int, x_cands: Optional[torch.Tensor]):
+              delta: Optional[float], kappa: float, max_rows: int):
     """One round's near-tie escalation.  scores [nl, b] (this rank's bf16 scores), key [b] (the GLOBAL packed argmax key).
-    Returns (idx [b] global winners, rows refined here, refined score table or None, truncated?).  `x_cands` (the
-    candidates' x_next, [nl*b, ...]) gets the precise x_next of the refined rows written in place."""
+    Returns (idx [b] global winners, rows refined here, refined score table or None, truncated?).
+
+    Contenders of image j: every candidate whose score is within delta_j of the round's best, delta_j = `delta` if given,
+    else kappa * std_n(scores[:, j]) (the bf16 score noise that matters -- the part that DIFFERS between candidates --
+    measures ~0.24 of the spread of the scores themselves at every noise level), but never more than the
+    `max_rows` best-scoring ones per image.  All of this is a function of the GLOBAL score table, so a sharded run refines
+    exactly the rows an unsharded run refines."""
     nl = hi - lo
-    thr = (_key_score(key) - delta).unsqueeze(0)                           # [1, b]
-    mask = scores >= thr                                                   # contenders (the best itself included)
-    cnt = mask.sum(dim=0)
+    N = nl * shard.world
+    best = _key_score(key)                                                  # [b] global best score
+    dist = None
     if shard.world > 1:
         import torch.distributed as dist
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=shard.group)
-    multi = cnt > 1                                                        # images whose best has company within delta
-    host = torch.cat([(mask & multi.unsqueeze(0)).reshape(-1).to(torch.float32), scores.reshape(-1)]).cpu()   # THE host sync
-    m_host, s_host = host[:nl * b].bool(), host[nl * b:]
-    any_multi = bool(multi.any()) if shard.world > 1 else bool(m_host.any())
-    if not any_multi:
+    if delta is None:
+        mom = torch.stack([scores.sum(0, dtype=torch.float64), (scores.double() ** 2).sum(0)])        # [2, b]
+        if dist is not None:
+            dist.all_reduce(mom, op=dist.ReduceOp.SUM, group=shard.group)
+        mean = mom[0] / N
+        d = (kappa * (mom[1] / N - mean * mean).clamp_min(0).sqrt()).to(torch.float32)
+    else:
+        d = torch.full_like(best, float(delta))
+    thr = best - d
+    # the max_rows-th best score per image, globally: the contender list never grows beyond max_rows per image
+    M = min(max_rows, N)
+    top = torch.topk(scores, min(M, nl), dim=0).values                      # [<=M, b] local
+    if dist is not None:
+        allt = [torch.empty_like(top) for _ in range(shard.world)]
+        dist.all_gather(allt, top.contiguous(), group=shard.group)
+        top = torch.topk(torch.cat(allt, dim=0), M, dim=0).values
+    floor = top[M - 1]
+    mask = scores >= torch.maximum(thr, floor).unsqueeze(0)                 # contenders (the best itself included)
+    cnt = mask.sum(dim=0)
+    wide = (scores >= thr.unsqueeze(0)).sum(dim=0)                          # without the cap
+    if dist is not None:
+        both = torch.stack([cnt, wide])
+        dist.all_reduce(both, op=dist.ReduceOp.SUM, group=shard.group)
+        cnt, wide = both[0], both[1]
+    multi = cnt > 1                                                         # images whose best has company
+    sel = mask & multi.unsqueeze(0)
+    host = torch.cat([sel.reshape(-1).to(torch.float32), (wide > cnt).to(torch.float32), multi.to(torch.float32)]).cpu()   # THE host sync
+    m_host = host[:nl * b].bool()
+    truncated = bool(host[nl * b:nl * b + b].any())
+    if not bool(host[nl * b + b:].any()):
         return idx, 0, None, False
-    rows = torch.nonzero(m_host).flatten()                                 # row = n_local * b + j
-    truncated = rows.numel() > max_rows
-    if truncated:                                                          # keep the best-scoring rows (ties: lowest row)
-        order = torch.sort(s_host[rows], descending=True, stable=True).indices[:max_rows]
-        rows = rows[order].sort().values
+    rows = torch.nonzero(m_host).flatten()                                  # row = n_local * b + j
     refined = torch.where(mask & ~multi.unsqueeze(0), scores, torch.full_like(scores, float('-inf')))
     n_rows = int(rows.numel())
     if n_rows:
         rows_d = rows.to(scores.device)
-        imgs = rows_d % b
         eps_rows = local.index_select(0, rows_d).contiguous()
         lab = labels_rows.index_select(0, rows_d) if labels_rows is not None else None
+        row_images = (rows_d % b) if b > 1 else None
         if getattr(scorer, 'fused_sums', False):
-            x_p, _, sums = stepper.step(x_cur, eps_rows, i, want_x_next=x_cands is not None, want_sums=True, precise=True,
-                                        row_images=imgs if b > 1 else None)
+            _, _, sums = stepper.step(x_cur, eps_rows, i, want_x_next=False, want_sums=True, precise=True, row_images=row_images)
             s_p = scorer.score_from_sums(sums, C, HW)
         else:
-            x_p, u8, _ = stepper.step(x_cur, eps_rows, i, want_x_next=x_cands is not None, want_u8=True, want_sums=False,
-                                      precise=True, row_images=imgs if b > 1 else None)
+            _, u8, _ = stepper.step(x_cur, eps_rows, i, want_x_next=False, want_u8=True, want_sums=False, precise=True,
+                                    row_images=row_images)
             timesteps = torch.zeros(u8.shape[0], device=u8.device)
             timesteps._b200_uniform_value = 0.0
             s_p = torch.as_tensor(scorer(u8, lab, timesteps)).to(device=u8.device, dtype=torch.float32).reshape(-1)
         refined.view(-1).index_copy_(0, rows_d, s_p.contiguous())
-        if x_cands is not None:
-            x_cands.index_copy_(0, rows_d, x_p)
     idx2, key2 = ops.argmax_first(refined.contiguous(), idx_base=lo, want_key=True)
-    if shard.world > 1:
-        import torch.distributed as dist
+    if dist is not None:
         dist.all_reduce(key2, op=dist.ReduceOp.MAX, group=shard.group)
         idx2 = 0xFFFFFFFF - (key2 & 0xFFFFFFFF)
     else:
@@ -241,8 +262,8 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
                       teacher_x: Optional[List[torch.Tensor]] = None, step_indices: Optional[List[int]] = None,
                       x_init: Optional[torch.Tensor] = None, on_step=None,
                       commit: str = 'reuse', mirror_rng: bool = True, prefetch: bool = False,
-                      dedupe_noise_free: bool = False, escalate: Optional[bool] = None, delta: float = ESCALATION_DELTA,
-                      max_contenders: int = MAX_CONTENDERS,
+                      dedupe_noise_free: bool = False, escalate: Optional[bool] = None, delta: Optional[float] = None,
+                      kappa: float = ESCALATION_KAPPA, max_contenders: int = MAX_CONTENDERS,
                       bernoulli_draws: Optional[torch.Tensor] = None) -> (torch.Tensor, SearchRecord):
     """ZERO_ORDER == EPS_GREEDY branch (edm/main.py:714-860).
 
@@ -264,11 +285,13 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
 
     `escalate` (default: on whenever the network has a precise twin, i.e. ADM): near-tie precision escalation.  The bf16
     network puts ~1e-4 of noise on the scores while the reference runs it in fp32, so after the bf16 pass every candidate
-    whose score is within `delta` of the round's best is re-evaluated by the split-fp16 (fp32-faithful) engine and the
-    first-max argmax is taken over the refined scores (edm/main.py:842 on the reference's own precision).  Rounds with a
-    single contender -- and the noise-free steps, whose N candidates are one tensor -- cost nothing extra; otherwise one
-    host read of the [N, b] score table per round decides which rows to refine (at most `max_contenders` per rank, best
-    first).  The committed state of a refined winner is its precise x_next.
+    whose score is within delta of the round's best -- `delta` if given, else `kappa` x the standard deviation of the
+    round's scores (the candidate-dependent part of the bf16 score noise is a fixed fraction of that spread) -- is
+    re-evaluated by the split-fp16 (fp32-faithful) engine and the first-max argmax is taken over the refined scores
+    (edm/main.py:842 on the reference's own precision).  Rounds with a single contender -- and the noise-free steps, whose
+    N candidates are one tensor -- cost nothing extra; otherwise one host read per round decides which rows to refine (at
+    most `max_contenders` per image, best first).  The committed state stays the bf16 engine's x_next of the winner, so
+    commit 'reuse' and 'recompute' remain bit-identical.
 
     `bernoulli_draws` (tests): the uniform draws of edm/main.py:751 in call order, [num_steps*K*N] fp32, used INSTEAD of
     `torch.rand(1, device)` -- a reference run on another device (CPU) drew them from another generator.
@@ -307,7 +330,7 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
     elif escalate and not net.supports_precise:
         raise NotImplementedError('escalate=True: the precise engine implements head_dim-64 attention (ADM) only')
     if escalate:
-        for R in range(1, max_contenders + 1):        # all contender batch sizes up front: no plan is built mid-run
+        for R in range(1, min(max_contenders, MAX_CONTENDERS) + 1):   # the usual contender batch sizes up front: no plan is built mid-run
             net.precise_engine.plan(R, 1 if b == 1 else R)
     pre = precomputed_noise
     if pre is not None and 'pivot' in pre:                                # :724-727 (value unused, RNG untouched)
@@ -420,8 +443,7 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
             n_esc, refined = 0, None
             if escalate and table.steps[i].s != 0.0:
                 idx, n_esc, refined, trunc = _escalate(params.scorer, stepper, x_cur, local, scores, key, idx, i, lo, hi, b,
-                                                       labels_rows, C, HW, shard, delta, max_contenders,
-                                                       x_cands if want_x else None)
+                                                       labels_rows, C, HW, shard, delta, kappa, max_contenders)
                 rec.truncated += int(trunc)
             rec.escalated.append(n_esc)
             if record:

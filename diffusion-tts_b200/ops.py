@@ -578,7 +578,7 @@ class Plan:
     # ---- split-fp16 "precise" ops (csrc/precise.cuh): near-tie re-scoring of a search round's contenders
     def add_gemm_prec(self, a: Sequence[torch.Tensor], segs: Sequence[Tuple[int, int, int, int]], w: torch.Tensor, N: int,
                       out: torch.Tensor, *, acc_scale: float, bias=None, residual=None, out_scale=1.0, label='gemm_prec',
-                      flops: float = 0.0):
+                      flops: float = 0.0, splits: int = 1, bn: int = 0, partial: Optional[torch.Tensor] = None):
         """a: 1-3 split-half NHWC tensors [B,H,W,2C]; segs: (src, taps, cstart, cblocks) over the 2C physical channels, laid
         out by the caller as [hi|lo] x [Whi|Whi] + [hi] x [Wlo]; w: half [Npad, Ktot] (pre-scaled by 1/acc_scale);
         out: split half [B,H,W,2N] or fp32 [..., N]; residual: split half [B,H,W,2N]."""
@@ -611,7 +611,14 @@ class Plan:
             _c(residual, torch.float16)
             d.residual, d.ld_res, d.res_lo_off = L.ptr(residual), residual.shape[-1], residual.shape[-1] // 2
         d.prec, d.acc_scale = 1, float(acc_scale)
-        self._k(*a, w, bias, residual, out)
+        d.prec_splits, d.prec_bn = int(splits), int(bn)
+        if splits > 1:
+            # fp32 partial tiles of the K slices: [splits, ceil(M/128)*128, Npad]
+            need = splits * ((B * H * W_ + 127) // 128) * 128 * w.shape[0]
+            if partial is None or partial.dtype != torch.float32 or partial.numel() < need:
+                raise RuntimeError('gemm_prec: split-K needs an fp32 `partial` workspace of splits*Mpad*Npad elements')
+            d.prec_partial = L.ptr(partial)
+        self._k(*a, w, bias, residual, out, partial)
         L.check(L.lib().b200ns_plan_add_gemm(self._h, C.byref(d)), 'plan_add_gemm(prec)')
         self.labels.append(label)
         self.kinds.append('gemm_prec')
@@ -621,6 +628,17 @@ class Plan:
                       film_shift=None, b_emb=1, silu=False, resample=0, raw_out=None):
         d = L.GnPrecDesc()
         B, H, W_, _ = x[0].shape
+        # statistics scratch, shared by every GroupNorm of the plan (ops run in stream order): fp64 partial sums per
+        # (sample, pixel split, group) and the per-sample arrival counters (zeroed once; the kernel resets them)
+        scr = getattr(self, '_gn_prec_scratch', None)
+        if scr is None or scr[0].shape[0] < B:
+            dev = x[0].device
+            scr = (torch.empty(B, 16, 64, 2, dtype=torch.float64, device=dev), torch.zeros(B, dtype=torch.int32, device=dev))
+            self._gn_prec_scratch = scr
+        if groups > 64:
+            raise RuntimeError('gn_prec: at most 64 groups')
+        d.partial, d.ticket = L.ptr(scr[0]), L.ptr(scr[1])
+        self._k(*scr)
         for i, t in enumerate(x):
             _c(t, torch.float16)
             d.x_ptr[i] = L.ptr(t)

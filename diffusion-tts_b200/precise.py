@@ -16,6 +16,7 @@ and batch-size invariant (order-fixed reductions), like the bf16 engine.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -46,6 +47,8 @@ def pack_split(blocks: Sequence[torch.Tensor], n_pad: Optional[int] = None):
         if C % 64:
             raise ValueError('split GEMM: channel blocks must be multiples of 64')
         hi, lo = split_half(b.to(torch.float32) * scale)
+        if os.environ.get('B200NS_PREC_NOLO') == '1':          # experiment: plain fp16 weights (see b200ns_debug_prec_nolo)
+            lo = torch.zeros_like(lo)
         parts.append(torch.cat([hi, hi], dim=2).reshape(N, taps * 2 * C))
         parts.append(lo.reshape(N, taps * C))
         segs.append(((taps, 2 * C // 64), (taps, C // 64)))
@@ -53,6 +56,18 @@ def pack_split(blocks: Sequence[torch.Tensor], n_pad: Optional[int] = None):
     if n_pad is not None and n_pad > N:
         w = torch.cat([w, torch.zeros(n_pad - N, w.shape[1], dtype=w.dtype)], dim=0)
     return w.contiguous(), 1.0 / scale, segs
+
+
+def split_k_policy(hw: int, n_pad: int, nkb: int, sms: int = 148) -> Tuple[int, int]:
+    """(N tile width, K slices) of a precise GEMM.  Contender batches are tiny, so a layer is cut until ONE sample's worth
+    of work items (M tiles x N tiles x K slices) fills the SMs; both numbers depend on the layer only -- never on the
+    batch -- so a sample's bits do not depend on how many contenders share its launch."""
+    if n_pad % 64:
+        return 0, 1                               # the 3-channel output conv (Npad = 16): cost model, no split
+    bn = 128 if n_pad % 128 == 0 else 64
+    tiles = max(1, hw // 128) * (n_pad // bn)
+    splits = max(1, min(-(-sms // tiles), nkb // 8, 32))
+    return bn, splits
 
 
 def _conv_block(w: torch.Tensor, c0: int = 0, c1: Optional[int] = None) -> torch.Tensor:
@@ -107,8 +122,17 @@ class PreciseForwardPlan:
             flat.append((i, sa[0], 0, sa[1]))
             flat.append((i, sb[0], 0, sb[1]))
         B, H, W_, _ = srcs[0].shape
+        bn, splits = split_k_policy(H * W_, w.shape[0], w.shape[1] // 64)
+        partial = None
+        if splits > 1:
+            need = splits * ((B * H * W_ + 127) // 128) * 128 * w.shape[0]
+            partial = self._scratch.get('splitk')
+            if partial is None or partial.numel() < need:
+                partial = torch.empty(need, device=self.x_in.device, dtype=torch.float32)
+                self._scratch['splitk'] = partial
         self.plan.add_gemm_prec(srcs, flat, w, N, out, acc_scale=acc_scale, bias=bias, residual=residual,
-                                out_scale=out_scale, label=label, flops=2.0 * B * H * W_ * N * w.shape[1])
+                                out_scale=out_scale, label=label, flops=2.0 * B * H * W_ * N * w.shape[1],
+                                splits=splits, bn=bn, partial=partial)
 
     def _build(self, eng: 'PreciseUNetEngine'):
         self._eng = eng
@@ -240,6 +264,9 @@ class PreciseUNetEngine:
         self.base, self.cfg, self.device, self.use_graphs = base, base.cfg, base.device, use_graphs
         sd = {k[len('model.'):] if k.startswith('model.') else k: v for k, v in state_dict.items()}
         self.w: Dict[str, tuple] = {}
+        if os.environ.get('B200NS_PREC_NOLO') == '1':
+            from . import _lib
+            _lib.check(_lib.lib().b200ns_debug_prec_nolo(1), 'debug_prec_nolo')
         self._pack(sd)
         self._plans: Dict[tuple, PreciseForwardPlan] = {}
 

@@ -174,6 +174,12 @@ typedef struct {
   int32_t prec;
   float acc_scale;
   int32_t out_lo_off, res_lo_off;
+  /* prec only -- split-K: the K range of every output tile is cut into prec_splits slices (a function of the layer, never of
+   * the batch: batch-size invariance) that run on different SMs and leave fp32 partial tiles in prec_partial
+   * (>= prec_splits * ceil(M/128)*128 * Npad floats); a finishing kernel adds them in order.  prec_bn: N tile width
+   * (256/192/128/64, 16 for Npad = 16; 0 = cost model). */
+  int32_t prec_splits, prec_bn;
+  float* prec_partial;
 } b200ns_gemm_desc;
 int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d);
 /* Tuning aid: force the N tile width (64/128/192/256; 0 = cost model) of subsequently added bf16 GEMMs whose padded
@@ -309,6 +315,8 @@ typedef struct {
   void* out;                 /* split half [batch, H', W', 2C] */
   void* raw_out;             /* split half or NULL */
   float* mean_rstd;          /* fp32 [batch, groups, 2]: written by the stats op, read by the apply op */
+  double* partial;           /* stats scratch: fp64 [batch, 16, groups, 2] */
+  int32_t* ticket;           /* stats scratch: int32 [batch], zero-initialised once (the kernel resets it) */
 } b200ns_gn_prec_desc;
 /* per-(sample, group) mean / rstd in fp64 over hi + lo (+ pre_add) -> mean_rstd (networks.py:104-106) */
 int b200ns_plan_add_gn_stats_prec(b200ns_plan* p, const b200ns_gn_prec_desc* d);
@@ -327,6 +335,9 @@ typedef struct {
   float scale;               /* 0 = 1/sqrt(64) */
 } b200ns_attn_prec_desc;
 int b200ns_plan_add_attention_prec(b200ns_plan* p, const b200ns_attn_prec_desc* d);
+
+/* Experiment switch: 1 = the precise kernels write a zero lo plane (plain fp16 storage), 0 = split fp16 (default). */
+int b200ns_debug_prec_nolo(int on);
 
 /* 3x3 im2col of the fp32 NCHW network input (Cin*9 <= 64) into split half [batch*H*W, 128] = [64 hi taps | 64 lo taps]. */
 int b200ns_plan_add_im2col_prec(b200ns_plan* p, const b200ns_im2col_desc* d);

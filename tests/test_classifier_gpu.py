@@ -60,7 +60,7 @@ def test_imagenet_scorer_in_search_loop(cls):
             return s
     params.scorer = Spy()
     x, rec = em.eps_greedy_search(net, latents.cuda(), labels.cuda(), params, table,
-                                  precomputed_noise={k: v.cuda() for k, v in pre.items()}, record=True)
+                                  precomputed_noise={k: v.cuda() for k, v in pre.items()}, record=True, escalate=False)
     assert len(seen) == g['num_steps']
     for im, lab, s in seen:                      # every scored batch agrees with the CPU oracle's classifier
         ref = CO.imagenet_score(csd, gc['cfg'], im, lab, torch.zeros(im.shape[0]))

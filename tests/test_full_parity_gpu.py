@@ -81,7 +81,7 @@ def _fresh_inputs(gold, pre):
     return latents, labels, pre
 
 
-def _run(pkg, gold, scorer, *, escalate, fresh_mask=None):
+def _run(pkg, gold, scorer, *, escalate, fresh_mask=None, **extra):
     den, em, sc = pkg
     net = _net(den, gold)
     if gold.get('all_fresh'):
@@ -91,7 +91,7 @@ def _run(pkg, gold, scorer, *, escalate, fresh_mask=None):
     table = den.StepTable(net, 'cuda', gold['num_steps'], **gold['sampler_kw'])
     params = em.SamplingParams(N=gold['N'], K=gold['K'], eps=gold['eps'], lambda_param=gold['lambda_param'], scorer=scorer)
     teacher = [t.cuda() for t in gold['x_next_steps']]
-    kw = {}
+    kw = dict(extra)
     if fresh_mask is not None:
         kw['bernoulli_draws'] = fresh_mask
     x, rec = em.eps_greedy_search(net, latents.cuda(), labels.cuda(), params, table,
@@ -120,6 +120,8 @@ def _report(tag, gold, rec, table):
     os.makedirs(OUT, exist_ok=True)
     with open(os.path.join(OUT, f'parity_full_{tag}.json'), 'w') as f:
         json.dump(dict(tag=tag, flips=flips, rounds=rows), f, indent=1)
+    torch.save(dict(scores=[s.cpu() for s in rec.scores], refined=[None if r is None else r.cpu() for r in rec.refined],
+                    ref=[s.float() for s in gold['score_calls']]), os.path.join(OUT, f'parity_full_{tag}_tables.pt'))
     print(f'[{tag}] flips vs the reference: {flips} of {len(rows)} rounds')
     for row in rows:
         print('  r%-2d s=%.3g idx %s ref %s gap %.2e spread %.2e | err max %.2e common %+.2e diff-std %.2e diff-max %.2e | esc %d' % (
@@ -160,7 +162,8 @@ def test_adm64_N64_indices_equal_the_reference(pkg):
         dirs[n] = pre[i][:, 0, n]
         scale = O.candidate_scale_fp32(gold['scales'][f'{i}_0_{n}'], lam)
         want = O.make_candidates(pre[f'pivot_{i}'], [dirs[n]], [scale], [None])
-        assert torch.equal(piv.cpu(), want), i
+        # (the direction norm is a CUDA reduction here and a CPU reduction in the reference: last-ulp differences)
+        assert (piv.cpu() - want).abs().max() < 1e-12, i
 
 
 @pytest.mark.skipif(not _have('search_eps04_adm64_N64.pt'), reason='fixture not generated')
@@ -187,4 +190,33 @@ def test_adm64_N64_classifier_scorer_indices_equal_the_reference(pkg):
     scorer = ImageNetScorer(state_dict=csd, device='cuda')
     rec, table = _run(pkg, gold, scorer, escalate=True)
     flips, rows = _report('imagenet', gold, rec, table)
-    assert flips == 0, [r for r in rows if r['idx'] != r['idx_ref']]
+    bad = []
+    for row, so in zip(rows, gold['score_calls']):
+        if row['noise_scale'] == 0.0:
+            # gamma = 0: the N candidates are ONE tensor.  The reference's CPU classifier is not batch-position invariant
+            # (its scores for the identical images differ in the last bits, so its argmax there is rounding noise and
+            # irrelevant: no noise is injected); here identical inputs give identical bits and the first index wins.
+            assert float(so.max() - so.min()) < 1e-6 * float(so.abs().max()) + 1e-9, row
+            assert row['idx'] == [0] * gold['b'], row
+        elif row['idx'] != row['idx_ref']:
+            bad.append(row)
+    assert not bad, bad
+
+
+@pytest.mark.skipif(not _have('search_eps_greedy_adm64_N64.pt') or os.environ.get('B200NS_ANALYSIS') != '1',
+                    reason='analysis run (B200NS_ANALYSIS=1): every candidate through the precise engine')
+def test_analysis_precise_scores_of_all_candidates(pkg):
+    """Not a gate: dumps the precise engine's score of ALL 64 candidates per round next to the reference's, i.e. the error
+    distribution of the fp32-faithful path itself (with B200NS_PREC_NOLO=1: of plain fp16 storage) -> gpurun_out/."""
+    den, em, sc = pkg
+    gold = load_golden('search_eps_greedy_adm64_N64.pt')
+    rec, table = _run(pkg, gold, sc.BrightnessScorer(device='cuda'), escalate=True, delta=1e9, max_contenders=gold['N'])
+    tag = 'all_nolo' if os.environ.get('B200NS_PREC_NOLO') == '1' else 'all_precise'
+    _report(tag, gold, rec, table)
+    for r, (p, so) in enumerate(zip(rec.refined, gold['score_calls'])):
+        if p is None:
+            continue
+        err = p.cpu().flatten() - so.flatten().float()
+        d = err - err.mean()
+        print('  %s r%-2d: precise-vs-reference err max %.2e common %+.2e diff-std %.2e diff-max %.2e  argmax %d ref %d' % (
+            tag, r, err.abs().max(), err.mean(), d.std(), d.abs().max(), int(p.flatten().argmax()), int(so.flatten().argmax())))

@@ -80,6 +80,6 @@ def test_sharded_search_equals_unsharded_bit_for_bit():
     for rank, out, err in res:
         assert err is None, err
         for esc, (ok, n_esc) in out.items():
-            assert ok, (rank, esc)
+            assert ok, (rank, esc, n_esc)
             if esc and rank == 0:
                 assert n_esc[1] > 0, 'the escalated run must actually have refined some contenders'

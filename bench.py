@@ -206,7 +206,7 @@ def run_b200(args):
         e0.record()
         x, rec = eps_greedy_search(net, None, labels, params, table, precomputed_noise=noise, shard=shard,
                                    step_indices=steps_idx, x_init=x_init, on_step=on_step, prefetch=bool(args.prefetch),
-                                   dedupe_noise_free=dedupe, escalate=escalate)
+                                   dedupe_noise_free=dedupe, escalate=escalate, **({'kappa': args.kappa} if args.kappa > 0 else {}))
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -329,6 +329,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', type=str, default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--kappa', type=float, default=0.0, help='escalation threshold in units of the score spread (0 = API default)')
     ap.add_argument('--escalate', type=int, default=-1, help='near-tie precision escalation: 1 on, 0 off, -1 = API default (on)')
     ap.add_argument('--prefetch', type=int, default=0, help='e2e: stage the next step\'s host noise on a side stream (no measurable gain)')
     ap.add_argument('--async-readback', type=int, default=1, help='e2e: per-step results into pinned buffers, asynchronously')

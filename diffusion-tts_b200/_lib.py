@@ -9,7 +9,15 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libb200ns.so')
+# 16-bit storage type of activations / weights: IEEE half by default (3.5x less candidate-dependent score noise than
+# bfloat16 at the same tensor-core rate, and the reference's own GPU dtype); B200NS_ACT=bf16 selects the bfloat16 build.
+ACT_BF16 = os.environ.get('B200NS_ACT', 'fp16').lower() in ('bf16', 'bfloat16')
+LIB_PATH = os.path.join(_HERE, 'libb200ns_bf16.so' if ACT_BF16 else 'libb200ns.so')
+try:
+    import torch as _torch
+    ACT_DTYPE = _torch.bfloat16 if ACT_BF16 else _torch.float16
+except ImportError:                      # symbol checks without torch
+    ACT_DTYPE = None
 
 c_i32, c_i64, c_f32, c_f64, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_void_p
 
@@ -77,6 +85,7 @@ class Im2colDesc(C.Structure):
 SIGNATURES = {
     'b200ns_last_error': (C.c_char_p, []),
     'b200ns_device_ok': (C.c_int, [C.c_int]),
+    'b200ns_act_is_fp16': (C.c_int, []),
     'b200ns_heun_pre': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f64, c_f32, c_vp]),
     'b200ns_heun_mid': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_f32, c_f32, c_f64, c_f64, c_f32, c_vp]),
     'b200ns_heun_post': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_f32, c_f32, c_f64, c_f64,
@@ -141,6 +150,8 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
+        if bool(handle.b200ns_act_is_fp16()) == ACT_BF16:
+            raise RuntimeError(f'{LIB_PATH} was built for the other 16-bit storage type (B200NS_ACT): rebuild')
         _lib = handle
     return _lib
 

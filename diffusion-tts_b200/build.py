@@ -5,7 +5,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-OUT = os.path.join(HERE, 'libb200ns.so')
+ACT_BF16 = os.environ.get('B200NS_ACT', 'fp16').lower() in ('bf16', 'bfloat16')
+OUT = os.path.join(HERE, 'libb200ns_bf16.so' if ACT_BF16 else 'libb200ns.so')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-shared',
               '-Xcompiler', '-fPIC']
 
@@ -24,7 +25,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     # build into a private temp file and rename atomically: concurrent builders (torchrun ranks) or a process that is
     # dlopen-ing the library never see a half-written .so
     tmp = f'{OUT}.{os.getpid()}.tmp'
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', tmp, os.path.join(CSRC, 'capi.cu')]
+    cmd = [nvcc] + NVCC_FLAGS + (['-DB200NS_ACT_BF16'] if ACT_BF16 else []) + (['-Xptxas', '-v'] if verbose else []) + ['-o', tmp, os.path.join(CSRC, 'capi.cu')]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

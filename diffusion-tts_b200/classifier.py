@@ -15,6 +15,8 @@ from typing import Dict, List, Optional
 import numpy as np
 import torch
 
+from ._lib import ACT_DTYPE
+
 from .ops import Plan
 from .scorers import Scorer
 from .unet import Block, ForwardPlan, NetConfig, _pack_conv
@@ -81,7 +83,7 @@ class ClassifierPlan(ForwardPlan):
         col = self._act('col', B, H, H, 64)
         P.add_im2col(self.x_in, col, label='input_conv.im2col')
         c0 = eng.blocks[0].cin
-        x = torch.empty(B, H, H, c0, device=dev, dtype=torch.bfloat16)
+        x = torch.empty(B, H, H, c0, device=dev, dtype=ACT_DTYPE)
         P.add_gemm([col], [(0, 1, 0, 1)], W_['input_conv.w'], c0, x, bias=W_['input_conv.b'], alg_k=27,
                    gn_stats=self._new_stats(x), label='input_conv')
         for blk in eng.blocks:
@@ -161,7 +163,7 @@ class ClassifierEngine:
                   'out.0.bias'):
             w[k] = f(sd[k])
         wi = sd['input_blocks.0.0.weight'].detach().float().cpu()
-        wp = torch.zeros(wi.shape[0], 64, dtype=torch.bfloat16)
+        wp = torch.zeros(wi.shape[0], 64, dtype=ACT_DTYPE)
         wp[:, :27] = _pack_conv(wi)
         w['input_conv.w'], w['input_conv.b'] = wp.to(dev), f(sd['input_blocks.0.0.bias'])
         res = image_size
@@ -184,7 +186,7 @@ class ClassifierEngine:
             w[f'{n}.conv0.b'] = f(sd[f'{rp}.in_layers.2.bias'])
             w1 = _pack_conv(sd[f'{rp}.out_layers.3.weight'].detach().float().cpu())
             if blk.skip_conv:
-                ws = sd[f'{rp}.skip_connection.weight'].detach().float().cpu()[:, :, 0, 0].to(torch.bfloat16)
+                ws = sd[f'{rp}.skip_connection.weight'].detach().float().cpu()[:, :, 0, 0].to(ACT_DTYPE)
                 w[f'{n}.conv1skip.w'] = torch.cat([w1, ws], dim=1).contiguous().to(dev)
                 w[f'{n}.conv1skip.b'] = f(sd[f'{rp}.out_layers.3.bias']) + f(sd[f'{rp}.skip_connection.bias'])
             else:
@@ -195,10 +197,10 @@ class ClassifierEngine:
                 # QKVAttentionLegacy channel order (head, {q,k,v}, d) (edm/unet.py:365) -> [Q | K | V], head-major
                 wq = sd[f'{ap}.qkv.weight'].detach().float().cpu()[:, :, 0].reshape(heads, 3, 64, C).permute(1, 0, 2, 3)
                 bq = sd[f'{ap}.qkv.bias'].detach().float().cpu().reshape(heads, 3, 64).permute(1, 0, 2)
-                w[f'{n}.qkv.w'] = wq.reshape(3 * C, C).contiguous().to(torch.bfloat16).to(dev)
+                w[f'{n}.qkv.w'] = wq.reshape(3 * C, C).contiguous().to(ACT_DTYPE).to(dev)
                 w[f'{n}.qkv.b'] = bq.reshape(3 * C).contiguous().to(dev)
                 w[f'{n}.proj.w'] = sd[f'{ap}.proj_out.weight'].detach().float().cpu()[:, :, 0].contiguous().to(
-                    torch.bfloat16).to(dev)
+                    ACT_DTYPE).to(dev)
                 w[f'{n}.proj.b'] = f(sd[f'{ap}.proj_out.bias'])
             self.affine_off[n] = off
             aff_w.append(sd[f'{rp}.emb_layers.1.weight'].detach().float().cpu())
@@ -211,7 +213,7 @@ class ClassifierEngine:
         w['pool.pos'] = f(sd['out.2.positional_embedding'])
         wqkv = sd['out.2.qkv_proj.weight'].detach().float().cpu()[:, :, 0]          # rows [q | k | v] (edm/unet.py:398)
         w['pool.qkv.weight'], w['pool.qkv.bias'] = wqkv.contiguous().to(dev), f(sd['out.2.qkv_proj.bias'])
-        w['pool.kv.w'] = wqkv[C:].contiguous().to(torch.bfloat16).to(dev)
+        w['pool.kv.w'] = wqkv[C:].contiguous().to(ACT_DTYPE).to(dev)
         w['pool.kv.b'] = f(sd['out.2.qkv_proj.bias'])[C:].contiguous()
         w['pool.c_proj.weight'] = sd['out.2.c_proj.weight'].detach().float()[:, :, 0].contiguous().to(dev)
         w['pool.c_proj.bias'] = f(sd['out.2.c_proj.bias'])

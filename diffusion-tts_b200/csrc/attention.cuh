@@ -16,7 +16,7 @@
 namespace b200 {
 
 struct AttnArgs {
-  __nv_bfloat16* out;
+  act_t* out;
   int ld_out;
   int heads, L;
   int k_col0;
@@ -81,9 +81,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tO = tmem_base + 128;
-  constexpr uint32_t idesc_s = umma_idesc_bf16(128, KT);
+  constexpr uint32_t idesc_s = umma_idesc_act(128, KT);
   // VROW: B = V [KT keys x 64 d] as loaded (d contiguous) = MN-major operand; else V^T (K-major)
-  constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, VROW);
+  constexpr uint32_t idesc_o = umma_idesc_act(128, 64, VROW);
 
   auto load_kv = [&](int kt, int st) {
     mbar_arrive_expect_tx(&bar_kv[st], Cfg::K_BYTES + Cfg::V_BYTES);
@@ -159,10 +159,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           lsum += p[j];
         }
         uint4 u;
-        u.x = pack_bf16(p[0], p[1]);
-        u.y = pack_bf16(p[2], p[3]);
-        u.z = pack_bf16(p[4], p[5]);
-        u.w = pack_bf16(p[6], p[7]);
+        u.x = pack_act(p[0], p[1]);
+        u.y = pack_act(p[2], p[3]);
+        u.z = pack_act(p[4], p[5]);
+        u.w = pack_act(p[6], p[7]);
         *reinterpret_cast<uint4*>(prow + (((ch0 + g) ^ r7) << 4)) = u;
       }
     }
@@ -210,10 +210,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       uint4 u;
-      u.x = pack_bf16(o[8 * j + 0] * inv, o[8 * j + 1] * inv);
-      u.y = pack_bf16(o[8 * j + 2] * inv, o[8 * j + 3] * inv);
-      u.z = pack_bf16(o[8 * j + 4] * inv, o[8 * j + 5] * inv);
-      u.w = pack_bf16(o[8 * j + 6] * inv, o[8 * j + 7] * inv);
+      u.x = pack_act(o[8 * j + 0] * inv, o[8 * j + 1] * inv);
+      u.y = pack_act(o[8 * j + 2] * inv, o[8 * j + 3] * inv);
+      u.z = pack_act(o[8 * j + 4] * inv, o[8 * j + 5] * inv);
+      u.w = pack_act(o[8 * j + 6] * inv, o[8 * j + 7] * inv);
       op[j] = u;
     }
   }
@@ -279,8 +279,8 @@ attention_kernel_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tO = tmem_base + 128;
-  constexpr uint32_t idesc_s = umma_idesc_bf16(128, KT);
-  constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, true);      // B = V, MN-major
+  constexpr uint32_t idesc_s = umma_idesc_act(128, KT);
+  constexpr uint32_t idesc_o = umma_idesc_act(128, 64, true);      // B = V, MN-major
 
   auto load_k = [&](int kt) {
     mbar_arrive_expect_tx(bar_k, Cfg::K_BYTES);
@@ -349,10 +349,10 @@ attention_kernel_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         lsum += p[j];
       }
       uint4 u;
-      u.x = pack_bf16(p[0], p[1]);
-      u.y = pack_bf16(p[2], p[3]);
-      u.z = pack_bf16(p[4], p[5]);
-      u.w = pack_bf16(p[6], p[7]);
+      u.x = pack_act(p[0], p[1]);
+      u.y = pack_act(p[2], p[3]);
+      u.z = pack_act(p[4], p[5]);
+      u.w = pack_act(p[6], p[7]);
       // key block g (8 keys = 16 B) of atom g/8, swizzled by the row
       *reinterpret_cast<uint4*>(prow + (g >> 3) * 16384 + (((g & 7) ^ r7) << 4)) = u;
     }
@@ -400,10 +400,10 @@ attention_kernel_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       uint4 u;
-      u.x = pack_bf16(o[8 * j + 0] * inv, o[8 * j + 1] * inv);
-      u.y = pack_bf16(o[8 * j + 2] * inv, o[8 * j + 3] * inv);
-      u.z = pack_bf16(o[8 * j + 4] * inv, o[8 * j + 5] * inv);
-      u.w = pack_bf16(o[8 * j + 6] * inv, o[8 * j + 7] * inv);
+      u.x = pack_act(o[8 * j + 0] * inv, o[8 * j + 1] * inv);
+      u.y = pack_act(o[8 * j + 2] * inv, o[8 * j + 3] * inv);
+      u.z = pack_act(o[8 * j + 4] * inv, o[8 * j + 5] * inv);
+      u.w = pack_act(o[8 * j + 6] * inv, o[8 * j + 7] * inv);
       op[j] = u;
     }
   }
@@ -498,8 +498,8 @@ attention_kernel_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 4) {
     // ===================== issuer: TMA + MMA (one thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, KT);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, D, true);       // B = V, MN-major, N = D
+      constexpr uint32_t idesc_s = umma_idesc_act(128, KT);
+      constexpr uint32_t idesc_o = umma_idesc_act(128, D, true);       // B = V, MN-major, N = D
       auto load_k = [&](int kt) {
         mbar_arrive_expect_tx(&bar_k[kt & 1], Cfg::K_BYTES);
 #pragma unroll
@@ -612,7 +612,7 @@ attention_kernel_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const float p0 = poly ? ex2_poly(x0) : ex2_approx(x0);
         const float p1 = poly ? ex2_poly(x1) : ex2_approx(x1);
         lsum += p0 + p1;
-        pk[j] = pack_bf16(p0, p1);
+        pk[j] = pack_act(p0, p1);
       }
       l_run = l_run * alpha + lsum;
       if (kt > 0) {
@@ -655,10 +655,10 @@ attention_kernel_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint4 u;
-          u.x = pack_bf16(__uint_as_float(r[8 * j + 0]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
-          u.y = pack_bf16(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
-          u.z = pack_bf16(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
-          u.w = pack_bf16(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
+          u.x = pack_act(__uint_as_float(r[8 * j + 0]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
+          u.y = pack_act(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
+          u.z = pack_act(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
+          u.w = pack_act(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
           op[h * 4 + j] = u;
         }
       }
@@ -719,8 +719,8 @@ attention_d256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tO = tmem_base + 256;
-  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64);
-  constexpr uint32_t idesc_o = umma_idesc_bf16(128, 256, true);
+  constexpr uint32_t idesc_s = umma_idesc_act(128, 64);
+  constexpr uint32_t idesc_o = umma_idesc_act(128, 256, true);
 
   // chunk g in [0, n): K chunk g ; g in [n, 2n): V chunk g-n
   auto load_chunk = [&](int g) {
@@ -790,10 +790,10 @@ attention_d256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         lsum += p[j];
       }
       uint4 u;
-      u.x = pack_bf16(p[0], p[1]);
-      u.y = pack_bf16(p[2], p[3]);
-      u.z = pack_bf16(p[4], p[5]);
-      u.w = pack_bf16(p[6], p[7]);
+      u.x = pack_act(p[0], p[1]);
+      u.y = pack_act(p[2], p[3]);
+      u.z = pack_act(p[4], p[5]);
+      u.w = pack_act(p[6], p[7]);
       *reinterpret_cast<uint4*>(prow + (((ch0 + g) ^ r7) << 4)) = u;
     }
   }
@@ -834,10 +834,10 @@ attention_d256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint4 u;
-        u.x = pack_bf16(__uint_as_float(r[8 * j + 0]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
-        u.y = pack_bf16(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
-        u.z = pack_bf16(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
-        u.w = pack_bf16(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
+        u.x = pack_act(__uint_as_float(r[8 * j + 0]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
+        u.y = pack_act(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
+        u.z = pack_act(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
+        u.w = pack_act(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
         op[j] = u;
       }
     }

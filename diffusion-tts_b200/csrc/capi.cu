@@ -524,7 +524,7 @@ int run_op(const Op& op, cudaStream_t st) {
       CK_LAUNCH("linear_kernel");
       return 0;
     case OP_IM2COL:
-      launch_pdl(im2col_c3_kernel, dim3(op.i2c.grid), dim3(256), 0, st, op.i2c.d.x, reinterpret_cast<__nv_bfloat16*>(op.i2c.d.out),
+      launch_pdl(im2col_c3_kernel, dim3(op.i2c.grid), dim3(256), 0, st, op.i2c.d.x, reinterpret_cast<act_t*>(op.i2c.d.out),
                  op.i2c.d.batch, op.i2c.d.C, op.i2c.d.H, op.i2c.d.W);
       CK_LAUNCH("im2col_c3_kernel");
       return 0;
@@ -534,15 +534,15 @@ int run_op(const Op& op, cudaStream_t st) {
       CK_LAUNCH("u8_to_unit_f32_kernel");
       return 0;
     case OP_POOL_TOKENS:
-      pool_tokens_kernel<<<op.misc.i0, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(op.misc.p0),
+      pool_tokens_kernel<<<op.misc.i0, 256, 0, st>>>(reinterpret_cast<const act_t*>(op.misc.p0),
                                                      reinterpret_cast<const float*>(op.misc.p1),
-                                                     reinterpret_cast<__nv_bfloat16*>(op.misc.p2),
+                                                     reinterpret_cast<act_t*>(op.misc.p2),
                                                      reinterpret_cast<float*>(op.misc.p3), op.misc.i1, op.misc.i2);
       CK_LAUNCH("pool_tokens_kernel");
       return 0;
     case OP_POOL_ATTN:
       pool_attention_kernel<<<dim3(op.misc.i2 / 64, op.misc.i0), 128, 0, st>>>(
-          reinterpret_cast<const float*>(op.misc.p0), reinterpret_cast<const __nv_bfloat16*>(op.misc.p1),
+          reinterpret_cast<const float*>(op.misc.p0), reinterpret_cast<const act_t*>(op.misc.p1),
           reinterpret_cast<float*>(op.misc.p2), op.misc.i1, op.misc.i2);
       CK_LAUNCH("pool_attention_kernel");
       return 0;
@@ -553,10 +553,10 @@ int run_op(const Op& op, cudaStream_t st) {
       CK_LAUNCH("softmax_gather_kernel");
       return 0;
     case OP_LAYERNORM: {
-      const __nv_bfloat16* lx = reinterpret_cast<const __nv_bfloat16*>(op.misc.p0);
+      const act_t* lx = reinterpret_cast<const act_t*>(op.misc.p0);
       const float* lg = reinterpret_cast<const float*>(op.misc.p1);
       const float* lb = reinterpret_cast<const float*>(op.misc.p3);
-      __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(op.misc.p2);
+      act_t* lo = reinterpret_cast<act_t*>(op.misc.p2);
       const int nchunk = op.misc.i0 / 8;
       const int64_t rows = op.misc.n;
       if (nchunk <= 40) {               // 4 rows per warp, 32 per CTA
@@ -571,19 +571,19 @@ int run_op(const Op& op, cudaStream_t st) {
     }
     case OP_GEGLU:
       launch_pdl(geglu_kernel, dim3(grid_for(op.misc.n * (op.misc.i0 / 8), 256, 148 * 32)), dim3(256), 0, st,
-                 reinterpret_cast<const __nv_bfloat16*>(op.misc.p0), reinterpret_cast<__nv_bfloat16*>(op.misc.p2), op.misc.n, op.misc.i0);
+                 reinterpret_cast<const act_t*>(op.misc.p0), reinterpret_cast<act_t*>(op.misc.p2), op.misc.n, op.misc.i0);
       CK_LAUNCH("geglu_kernel");
       return 0;
     case OP_SOFTMAX_ROWS:
       softmax_rows_kernel<<<static_cast<unsigned>(op.misc.n), 256, 0, st>>>(reinterpret_cast<const float*>(op.misc.p0),
-                                                                             reinterpret_cast<__nv_bfloat16*>(op.misc.p2),
+                                                                             reinterpret_cast<act_t*>(op.misc.p2),
                                                                              op.misc.i0, op.misc.f0);
       CK_LAUNCH("softmax_rows_kernel");
       return 0;
     case OP_UPSAMPLE2X:
       launch_pdl(upsample2x_kernel, dim3(grid_for(static_cast<int64_t>(op.misc.i0) * op.misc.i1 * op.misc.i2 * 4 * (op.misc.n / 8), 256, 148 * 32)),
-                 dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(op.misc.p0),
-                 reinterpret_cast<__nv_bfloat16*>(op.misc.p2), op.misc.i0, op.misc.i1, op.misc.i2, static_cast<int>(op.misc.n));
+                 dim3(256), 0, st, reinterpret_cast<const act_t*>(op.misc.p0),
+                 reinterpret_cast<act_t*>(op.misc.p2), op.misc.i0, op.misc.i1, op.misc.i2, static_cast<int>(op.misc.n));
       CK_LAUNCH("upsample2x_kernel");
       return 0;
   }
@@ -607,6 +607,14 @@ struct b200ns_plan {
 extern "C" {
 
 const char* b200ns_last_error(void) { return g_err.c_str(); }
+
+int b200ns_act_is_fp16(void) {
+#ifdef B200NS_ACT_BF16
+  return 0;
+#else
+  return 1;
+#endif
+}
 
 int b200ns_device_ok(int dev) {
   int major = 0;
@@ -881,7 +889,22 @@ int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d) {
     if (d->residual != nullptr && (d->res_lo_off % 8 || d->ld_res % 8)) return fail("gemm(prec): residual planes must be 16-byte aligned");
     if (d->prec_splits > 1 && d->prec_partial == nullptr) return fail("gemm(prec): split-K needs prec_partial");
     if (d->prec_bn != 0 && (d->Npad % d->prec_bn)) return fail("gemm(prec): prec_bn must divide Npad");
-    return add_gemm_part(p, d, d->prec_bn, d->N);
+    int bn = d->prec_bn;
+    if (bn == 0 && !d->out_fp32 && d->Npad % 64 == 0) {
+      // tile width by the same waves x cost-per-K-block model as the bf16 GEMMs, over M tiles x N tiles x K slices (the
+      // width may depend on the batch: it changes which SM computes an element, not the order of its K sum)
+      const int m_tiles = (d->batch * d->H * d->W + 127) / 128;
+      const int sp = d->prec_splits > 1 ? d->prec_splits : 1;
+      const int cands[4] = {256, 192, 128, 64};
+      long best = -1;
+      for (int c : cands) {
+        if (d->Npad % c) continue;
+        const long items = static_cast<long>(m_tiles) * (d->Npad / c) * sp;
+        const long cost = ((items + num_sms() - 1) / num_sms()) * gemm_per_kb(c);
+        if (best < 0 || cost < best) best = cost, bn = c;
+      }
+    }
+    return add_gemm_part(p, d, bn, d->N);
   }
   if (!d->upsample2x) return add_gemm_cols(p, d);
   // out [batch, 2H, 2W, ld_out] = conv3x3(nearest_up2(A)) as 4 phase launches of a 2x2-tap conv over the low-res A:
@@ -1036,7 +1059,7 @@ static int add_gemm_part(b200ns_plan* p, const b200ns_gemm_desc* d, int BN_force
     g.pargs.partial = d->prec ? d->prec_partial : nullptr;
     g.pargs.ld_partial = a.n_tiles * BN;
   }
-  a.residual = d->prec ? nullptr : reinterpret_cast<const __nv_bfloat16*>(d->residual);
+  a.residual = d->prec ? nullptr : reinterpret_cast<const act_t*>(d->residual);
   a.ld_res = d->ld_res;
   a.out_scale = d->out_scale;
   a.out = d->out;
@@ -1114,8 +1137,8 @@ int b200ns_plan_add_gn_stats(b200ns_plan* p, const b200ns_gn_stats_desc* d) {
   Op op;
   op.kind = OP_GN_STATS;
   GnStatsArgs& a = op.gns.args;
-  a.x0 = reinterpret_cast<const __nv_bfloat16*>(d->x_ptr[0]);
-  a.x1 = reinterpret_cast<const __nv_bfloat16*>(d->x_ptr[1]);
+  a.x0 = reinterpret_cast<const act_t*>(d->x_ptr[0]);
+  a.x1 = reinterpret_cast<const act_t*>(d->x_ptr[1]);
   a.C0 = d->x_channels[0];
   a.C1 = d->x_ptr[1] ? d->x_channels[1] : 0;
   a.C = a.C0 + a.C1;
@@ -1143,8 +1166,8 @@ int b200ns_plan_add_gn_apply(b200ns_plan* p, const b200ns_gn_apply_desc* d) {
   Op op;
   op.kind = OP_GN_APPLY;
   GnApplyArgs& a = op.gna.args;
-  a.x0 = reinterpret_cast<const __nv_bfloat16*>(d->x_ptr[0]);
-  a.x1 = reinterpret_cast<const __nv_bfloat16*>(d->x_ptr[1]);
+  a.x0 = reinterpret_cast<const act_t*>(d->x_ptr[0]);
+  a.x1 = reinterpret_cast<const act_t*>(d->x_ptr[1]);
   a.C0 = d->x_channels[0];
   a.C1 = d->x_ptr[1] ? d->x_channels[1] : 0;
   a.C = a.C0 + a.C1;
@@ -1168,8 +1191,8 @@ int b200ns_plan_add_gn_apply(b200ns_plan* p, const b200ns_gn_apply_desc* d) {
   a.b_emb = d->b_emb > 0 ? d->b_emb : 1;
   a.silu = d->silu;
   a.resample = d->resample;
-  a.out = reinterpret_cast<__nv_bfloat16*>(d->out);
-  a.raw_out = reinterpret_cast<__nv_bfloat16*>(d->raw_out);
+  a.out = reinterpret_cast<act_t*>(d->out);
+  a.raw_out = reinterpret_cast<act_t*>(d->raw_out);
   a.mean_rstd = reinterpret_cast<const float2*>(d->mean_rstd);
   a.reverse = d->reverse;
   if (d->mean_rstd == nullptr && d->partial == nullptr) return fail("gn_apply: need partial or mean_rstd");
@@ -1222,7 +1245,7 @@ int b200ns_plan_add_attention(b200ns_plan* p, const b200ns_attn_desc* d) {
   if (d->L % 64) return fail("attention: L must be a multiple of 64");
   o.head_dim = d->head_dim > 0 ? d->head_dim : 64;
   o.KT = (d->L % 128 == 0) ? 128 : 64;
-  o.args.out = reinterpret_cast<__nv_bfloat16*>(d->out);
+  o.args.out = reinterpret_cast<act_t*>(d->out);
   o.args.ld_out = d->ld_out;
   o.args.heads = d->heads;
   o.args.L = d->L;
@@ -1509,7 +1532,7 @@ static int fill_gn_prec(GnPrecArgs& a, const b200ns_gn_prec_desc* d) {
   a.ticket = d->ticket;
   // pixel splits: a function of the image size ONLY (batch-size / batch-position invariance of the reduction order)
   const int HW = d->H * d->W;
-  a.splits = HW / 64 < 1 ? 1 : (HW / 64 > 16 ? 16 : HW / 64);
+  a.splits = HW / 64 < 1 ? 1 : (HW / 64 > 64 ? 64 : HW / 64);
   if (HW % a.splits) a.splits = 1;
   const int VC = a.C / 8;
   if (a.C > 2048) return fail("gn_prec: more than 2048 channels");

@@ -17,15 +17,15 @@ __global__ void u8_to_unit_f32_kernel(const uint8_t* __restrict__ in, float* __r
 // x = cat([mean(x), x]) + positional_embedding                       (edm/unet.py:63-65)
 // act [B, T, C] bf16 (T spatial tokens), pos fp32 [C, T+1] -> tok [B, T, C] bf16 (spatial tokens),
 // tok0 [B, C] fp32 (the mean token).  grid (B), any block size.
-__global__ void pool_tokens_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ pos,
-                                   __nv_bfloat16* __restrict__ tok, float* __restrict__ tok0, int T, int C) {
+__global__ void pool_tokens_kernel(const act_t* __restrict__ act, const float* __restrict__ pos,
+                                   act_t* __restrict__ tok, float* __restrict__ tok0, int T, int C) {
   const int b = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float sum = 0.f;
     for (int t = 0; t < T; ++t) {
-      const float v = __bfloat162float(act[(static_cast<size_t>(b) * T + t) * C + c]);
+      const float v = act2f(act[(static_cast<size_t>(b) * T + t) * C + c]);
       sum += v;
-      tok[(static_cast<size_t>(b) * T + t) * C + c] = __float2bfloat16(v + pos[static_cast<size_t>(c) * (T + 1) + 1 + t]);
+      tok[(static_cast<size_t>(b) * T + t) * C + c] = f2act(v + pos[static_cast<size_t>(c) * (T + 1) + 1 + t]);
     }
     tok0[static_cast<size_t>(b) * C + c] = sum / static_cast<float>(T) + pos[static_cast<size_t>(c) * (T + 1)];
   }
@@ -35,7 +35,7 @@ __global__ void pool_tokens_kernel(const __nv_bfloat16* __restrict__ act, const 
 //   w = softmax_t( (q0 . k_t) / sqrt(64) ), a = sum_t w_t v_t  over T+1 tokens (token 0 = mean token).
 // qkv0 fp32 [B, 3C] = qkv_proj(mean token) as [q | k | v]; kv bf16 [B, T, 2C] = [k | v] of the spatial tokens.
 // grid (heads, B), 128 threads, T <= 127.
-__global__ void pool_attention_kernel(const float* __restrict__ qkv0, const __nv_bfloat16* __restrict__ kv,
+__global__ void pool_attention_kernel(const float* __restrict__ qkv0, const act_t* __restrict__ kv,
                                       float* __restrict__ out, int T, int C) {
   __shared__ float s_q[64];
   __shared__ float s_w[128];
@@ -50,8 +50,8 @@ __global__ void pool_attention_kernel(const float* __restrict__ qkv0, const __nv
     if (tid == 0) {
       for (int d = 0; d < 64; ++d) acc = fmaf(s_q[d], q0[C + h * 64 + d], acc);
     } else {
-      const __nv_bfloat16* kp = kv + (static_cast<size_t>(b) * T + (tid - 1)) * 2 * C + h * 64;
-      for (int d = 0; d < 64; ++d) acc = fmaf(s_q[d], __bfloat162float(kp[d]), acc);
+      const act_t* kp = kv + (static_cast<size_t>(b) * T + (tid - 1)) * 2 * C + h * 64;
+      for (int d = 0; d < 64; ++d) acc = fmaf(s_q[d], act2f(kp[d]), acc);
     }
     s = acc * 0.125f;
   }
@@ -75,7 +75,7 @@ __global__ void pool_attention_kernel(const float* __restrict__ qkv0, const __nv
   if (tid < 64) {
     float acc = s_w[0] * q0[2 * C + h * 64 + tid];
     for (int t = 0; t < T; ++t)
-      acc = fmaf(s_w[t + 1], __bfloat162float(kv[(static_cast<size_t>(b) * T + t) * 2 * C + C + h * 64 + tid]), acc);
+      acc = fmaf(s_w[t + 1], act2f(kv[(static_cast<size_t>(b) * T + t) * 2 * C + C + h * 64 + tid]), acc);
     out[static_cast<size_t>(b) * C + h * 64 + tid] = acc / s_red[1];
   }
 }

@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -129,10 +130,14 @@ DEVINL uint32_t lds32(uint32_t addr) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
-DEVINL float lds_bf16(uint32_t addr) {
+DEVINL float lds_act(uint32_t addr) {
   uint16_t h;
   asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(addr) : "memory");
+#ifdef B200NS_ACT_BF16
   return __uint_as_float(static_cast<uint32_t>(h) << 16);
+#else
+  return __half2float(__ushort_as_half(h));
+#endif
 }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM
@@ -303,13 +308,38 @@ DEVINL float gelu_erf(float x) {
   return x * half_one_plus_erf;
 }
 
-DEVINL uint32_t pack_bf16(float a, float b) {
+// ---- the 16-bit storage type of activations and weights ("act").  Default: IEEE half -- 11 significand bits against
+// bfloat16's 8, i.e. ~3.5x less candidate-dependent score noise in the search (measured on the ADM-64 N=64 reference
+// fixture), at the same tensor-core rate; it is also the reference's own GPU dtype (EDMPrecond use_fp16,
+// networks.py:658; the SD pipeline runs fp16).  -DB200NS_ACT_BF16 builds the bfloat16 variant (A/B, range-critical nets).
+#ifdef B200NS_ACT_BF16
+using act_t = __nv_bfloat16;
+DEVINL uint32_t pack_act(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-DEVINL float2 unpack_bf16(uint32_t u) {
+DEVINL float2 unpack_act(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
+DEVINL float act2f(act_t v) { return __bfloat162float(v); }
+DEVINL act_t f2act(float v) { return __float2bfloat16(v); }
+__host__ __device__ constexpr uint32_t umma_idesc_act(int M, int N, bool b_mn_major = false) { return umma_idesc_bf16(M, N, b_mn_major); }
+#else
+using act_t = __half;
+DEVINL uint32_t pack_act(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+DEVINL float2 unpack_act(uint32_t u) {
+  __half2 v = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(v);
+}
+DEVINL float act2f(act_t v) { return __half2float(v); }
+DEVINL act_t f2act(float v) { return __float2half_rn(v); }
+__host__ __device__ constexpr uint32_t umma_idesc_act(int M, int N, bool b_mn_major = false) {
+  return umma_idesc_f16(M, N) | (b_mn_major ? (1u << 16) : 0u);
+}
+#endif
 
 }  // namespace b200

@@ -44,7 +44,7 @@ struct GemmArgs {
   int x_chunks;                  // W/128 when a row is wider than a tile (VAE decoder, W = 256 / 512): tile = 128 pixels of ONE row
   int m_tiles, n_tiles;
   const float* bias;
-  const __nv_bfloat16* residual;
+  const act_t* residual;
   int ld_res;
   float out_scale;
   void* out;
@@ -167,7 +167,7 @@ DEVINL void gemm_mma(const GemmArgs& a, uint8_t* smem_a, uint8_t* smem_b, uint64
                      uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t tmem_base) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
-  const uint32_t idesc = a.fp16 ? umma_idesc_f16(128, BN) : umma_idesc_bf16(128, BN);
+  const uint32_t idesc = a.fp16 ? umma_idesc_f16(128, BN) : umma_idesc_act(128, BN);
   int stage = 0;
   uint32_t phase = 0;
   int acc = 0;
@@ -334,18 +334,18 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 // the unfused path rounds the projection to bf16 before GEGLU: keep that rounding so that both paths agree
-                const float hv = __bfloat162float(__float2bfloat16(__uint_as_float(rh[4 * i + c]) + hb[c]));
-                const float gv = __bfloat162float(__float2bfloat16(__uint_as_float(rg[4 * i + c]) + gb[c]));
+                const float hv = act2f(f2act(__uint_as_float(rh[4 * i + c]) + hb[c]));
+                const float gv = act2f(f2act(__uint_as_float(rg[4 * i + c]) + gb[c]));
                 v[4 * i + c] = hv * gelu_erf(gv);
               }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               uint4 u;
-              u.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
-              u.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
-              u.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
-              u.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+              u.x = pack_act(v[8 * i + 0], v[8 * i + 1]);
+              u.y = pack_act(v[8 * i + 2], v[8 * i + 3]);
+              u.z = pack_act(v[8 * i + 4], v[8 * i + 5]);
+              u.w = pack_act(v[8 * i + 6], v[8 * i + 7]);
               sts128(slot + row_off + (((half * 4 + i) ^ rsw) << 4), u);
             }
             fence_proxy_async_smem();
@@ -405,19 +405,19 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           for (int i = 0; i < 4; ++i) {
             const uint4 u = lds128(slot + row_off + (((half * 4 + i) ^ rsw) << 4));
             float2 f;
-            f = unpack_bf16(u.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
-            f = unpack_bf16(u.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
-            f = unpack_bf16(u.z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
-            f = unpack_bf16(u.w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
+            f = unpack_act(u.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
+            f = unpack_act(u.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
+            f = unpack_act(u.z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
+            f = unpack_act(u.w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
           }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 u;
-          u.x = pack_bf16(v[8 * i + 0] * a.out_scale, v[8 * i + 1] * a.out_scale);
-          u.y = pack_bf16(v[8 * i + 2] * a.out_scale, v[8 * i + 3] * a.out_scale);
-          u.z = pack_bf16(v[8 * i + 4] * a.out_scale, v[8 * i + 5] * a.out_scale);
-          u.w = pack_bf16(v[8 * i + 6] * a.out_scale, v[8 * i + 7] * a.out_scale);
+          u.x = pack_act(v[8 * i + 0] * a.out_scale, v[8 * i + 1] * a.out_scale);
+          u.y = pack_act(v[8 * i + 2] * a.out_scale, v[8 * i + 3] * a.out_scale);
+          u.z = pack_act(v[8 * i + 4] * a.out_scale, v[8 * i + 5] * a.out_scale);
+          u.w = pack_act(v[8 * i + 6] * a.out_scale, v[8 * i + 7] * a.out_scale);
           sts128(slot + row_off + (((half * 4 + i) ^ rsw) << 4), u);
         }
         fence_proxy_async_smem();           // generic-proxy writes -> visible to the TMA store
@@ -456,7 +456,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const uint32_t w = lds32(base + i * 1024u);
-            const float x0 = __uint_as_float(w << 16), x1 = __uint_as_float(w & 0xffff0000u);
+            const float2 xx = unpack_act(w);
+            const float x0 = xx.x, x1 = xx.y;
             const int hf = i >> 3;
             s0[hf] += x0;
             q0[hf] = fmaf(x0, x0, q0[hf]);
@@ -588,12 +589,12 @@ gemm_small_n_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           if (n < a.N) {
             float v = __uint_as_float(r[j]);
             if (a.bias != nullptr) v += __ldg(a.bias + n);
-            if (has_res) v += __bfloat162float(a.residual[static_cast<size_t>(m) * a.ld_res + n]);
+            if (has_res) v += act2f(a.residual[static_cast<size_t>(m) * a.ld_res + n]);
             v *= a.out_scale;
             if (a.out_fp32)
               reinterpret_cast<float*>(a.out)[static_cast<size_t>(m) * a.ld_out + n] = v;
             else
-              reinterpret_cast<__nv_bfloat16*>(a.out)[static_cast<size_t>(m) * a.ld_out + n] = __float2bfloat16(v);
+              reinterpret_cast<act_t*>(a.out)[static_cast<size_t>(m) * a.ld_out + n] = f2act(v);
           }
         }
       }

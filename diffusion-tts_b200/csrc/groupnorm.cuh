@@ -12,8 +12,8 @@
 namespace b200 {
 
 struct GnStatsArgs {
-  const __nv_bfloat16* x0;
-  const __nv_bfloat16* x1;
+  const act_t* x0;
+  const act_t* x1;
   int C0, C1, C;           // C = C0 + C1
   int HW, groups, cpg;
   const float* pre_add;    // [b_emb, ld_pre_add] or null
@@ -22,28 +22,28 @@ struct GnStatsArgs {
   int splits, PY;
 };
 
-DEVINL void load8(const __nv_bfloat16* p, float (&f)[8]) {
+DEVINL void load8(const act_t* p, float (&f)[8]) {
   const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
   float2 t;
-  t = unpack_bf16(u.x); f[0] = t.x; f[1] = t.y;
-  t = unpack_bf16(u.y); f[2] = t.x; f[3] = t.y;
-  t = unpack_bf16(u.z); f[4] = t.x; f[5] = t.y;
-  t = unpack_bf16(u.w); f[6] = t.x; f[7] = t.y;
+  t = unpack_act(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_act(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_act(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_act(u.w); f[6] = t.x; f[7] = t.y;
 }
-DEVINL uint4 load_raw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+DEVINL uint4 load_raw(const act_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 DEVINL void unpack8(const uint4& u, float (&f)[8]) {
   float2 t;
-  t = unpack_bf16(u.x); f[0] = t.x; f[1] = t.y;
-  t = unpack_bf16(u.y); f[2] = t.x; f[3] = t.y;
-  t = unpack_bf16(u.z); f[4] = t.x; f[5] = t.y;
-  t = unpack_bf16(u.w); f[6] = t.x; f[7] = t.y;
+  t = unpack_act(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_act(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_act(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_act(u.w); f[6] = t.x; f[7] = t.y;
 }
-DEVINL void store8(__nv_bfloat16* p, const float (&f)[8]) {
+DEVINL void store8(act_t* p, const float (&f)[8]) {
   uint4 u;
-  u.x = pack_bf16(f[0], f[1]);
-  u.y = pack_bf16(f[2], f[3]);
-  u.z = pack_bf16(f[4], f[5]);
-  u.w = pack_bf16(f[6], f[7]);
+  u.x = pack_act(f[0], f[1]);
+  u.y = pack_act(f[2], f[3]);
+  u.z = pack_act(f[4], f[5]);
+  u.w = pack_act(f[6], f[7]);
   *reinterpret_cast<uint4*>(p) = u;
 }
 
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256, 4) gn_stats_kernel(const GnStatsArgs a) {
   const int split = blockIdx.x, bi = blockIdx.y;
   const int ppb = a.HW / a.splits;
   const int c = vx * 8;
-  const __nv_bfloat16* src;
+  const act_t* src;
   int ld;
   if (c < a.C0) {
     src = a.x0 + c;
@@ -239,8 +239,8 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const GnFinalizeArgs a
 }
 
 struct GnApplyArgs {
-  const __nv_bfloat16* x0;
-  const __nv_bfloat16* x1;
+  const act_t* x0;
+  const act_t* x1;
   int C0, C1, C;
   int H, W, groups, cpg;   // INPUT spatial dims
   const double* partial;
@@ -254,8 +254,8 @@ struct GnApplyArgs {
   const float* film_shift;
   int ld_film, b_emb;
   int silu, resample;      // 0 none, 1 up x2, 2 down x2
-  __nv_bfloat16* out;
-  __nv_bfloat16* raw_out;
+  act_t* out;
+  act_t* raw_out;
   int PY, ITER;
   const float2* mean_rstd; // [batch, groups] from gn_finalize_kernel (then `partial` is unused)
   int reverse;             // walk samples / pixel chunks last-to-first (L2 hits on what the producer wrote last)
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(WIDE ? 512 : 256, WIDE ? 1 : 3) gn_apply_kerne
   __syncthreads();
 
   const int c = vx * 8;
-  const __nv_bfloat16* src;
+  const act_t* src;
   int ld;
   if (c < a.C0) {
     src = a.x0 + c;

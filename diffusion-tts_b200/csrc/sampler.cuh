@@ -275,7 +275,7 @@ __global__ void linear_kernel(const LinearArgs a) {
 }
 
 // 3x3 im2col of fp32 NCHW [B,C,H,W] (C<=7) -> bf16 [B*H*W, 64]; k = (kh*3+kw)*C + c.
-__global__ void im2col_c3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int C, int H,
+__global__ void im2col_c3_kernel(const float* __restrict__ x, act_t* __restrict__ out, int B, int C, int H,
                                  int W) {
   pdl_launch_dependents();
   pdl_wait();
@@ -300,10 +300,10 @@ __global__ void im2col_c3_kernel(const float* __restrict__ x, __nv_bfloat16* __r
       f[j] = v;
     }
     uint4 u;
-    u.x = pack_bf16(f[0], f[1]);
-    u.y = pack_bf16(f[2], f[3]);
-    u.z = pack_bf16(f[4], f[5]);
-    u.w = pack_bf16(f[6], f[7]);
+    u.x = pack_act(f[0], f[1]);
+    u.y = pack_act(f[2], f[3]);
+    u.z = pack_act(f[4], f[5]);
+    u.w = pack_act(f[6], f[7]);
     *reinterpret_cast<uint4*>(out + m * 64 + chunk * 8) = u;
   }
 }

@@ -17,8 +17,8 @@ namespace b200 {
 // LPR=8, 5 chunks per lane) keeps 4 rows x 640 B in flight per warp instead of one.  C multiple of 8, C/8 <= LPR*CPL;
 // bf16 in/out, fp32 statistics (two-pass over the registers, fixed shuffle order => batch-position invariant).
 template <int LPR, int CPL>
-__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
+__global__ void __launch_bounds__(256) layernorm_kernel(const act_t* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, act_t* __restrict__ out,
                                                         int64_t rows, int C, float eps) {
   pdl_launch_dependents();
   pdl_wait();
@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
   const int64_t warp = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t row = warp * RPW + lane / LPR;
   const bool live = row < rows;
-  const __nv_bfloat16* xr = x + (live ? row : 0) * C;
+  const act_t* xr = x + (live ? row : 0) * C;
   const int nchunk = C >> 3;
   float v[CPL][8];
   float s = 0.f;
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
 }
 
 // in [rows, 2F] = [hidden | gate] -> out [rows, F] = hidden * gelu(gate)   (F multiple of 8)
-__global__ void __launch_bounds__(256) geglu_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+__global__ void __launch_bounds__(256) geglu_kernel(const act_t* __restrict__ in, act_t* __restrict__ out,
                                                     int64_t rows, int F) {
   pdl_launch_dependents();
   pdl_wait();
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) geglu_kernel(const __nv_bfloat16* __restr
 }
 
 // bf16 NHWC [B,H,W,C] -> [B,2H,2W,C], nearest
-__global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+__global__ void __launch_bounds__(256) upsample2x_kernel(const act_t* __restrict__ in, act_t* __restrict__ out,
                                                          int B, int H, int W, int C) {
   pdl_launch_dependents();
   pdl_wait();

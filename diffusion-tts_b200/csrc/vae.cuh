@@ -14,7 +14,7 @@
 namespace b200 {
 
 // one CTA (256 threads) per row; L multiple of 8, L <= 256 * 32
-__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, __nv_bfloat16* __restrict__ P, int L,
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, act_t* __restrict__ P, int L,
                                                            float scale_log2e) {
   __shared__ float s_red[8];
   __shared__ float s_bcast;
@@ -56,12 +56,12 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
   }
   __syncthreads();
   const float inv = s_bcast;
-  __nv_bfloat16* p = P + row * L;
+  act_t* p = P + row * L;
   n = 0;
   for (int c = threadIdx.x * 4; c < L; c += 1024, ++n) {
     uint2 u;
-    u.x = pack_bf16(v[4 * n + 0] * inv, v[4 * n + 1] * inv);
-    u.y = pack_bf16(v[4 * n + 2] * inv, v[4 * n + 3] * inv);
+    u.x = pack_act(v[4 * n + 0] * inv, v[4 * n + 1] * inv);
+    u.y = pack_act(v[4 * n + 2] * inv, v[4 * n + 3] * inv);
     *reinterpret_cast<uint2*>(p + c) = u;
   }
 }

@@ -10,6 +10,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib as L
+from ._lib import ACT_DTYPE
 from . import torch_ops as T
 
 # The sampler / scorer entry points and the plan runner go through their torch.library registrations
@@ -292,7 +293,7 @@ def pack_conv_up2(w: torch.Tensor, splits: Optional[Sequence[int]] = None) -> to
                 parts.append(torch.stack(taps, dim=1).reshape(w.shape[0], -1))          # [Cout, 4, cs] -> [Cout, 4*cs]
                 c0 += cs
             out.append(torch.cat(parts, dim=1))
-    return torch.stack(out).contiguous().to(torch.bfloat16)
+    return torch.stack(out).contiguous().to(ACT_DTYPE)
 
 
 def interleave_geglu(t: torch.Tensor) -> torch.Tensor:
@@ -379,7 +380,7 @@ class Plan:
         B, H, W_, _ = a[0].shape
         H, W_ = H // a_stride[0], W_ // a_stride[0]           # output spatial dims (stride-2 sources are 2H x 2W)
         for i, t in enumerate(a):
-            _c(t, torch.bfloat16)
+            _c(t, ACT_DTYPE)
             if t.shape[1] != H * a_stride[i] or t.shape[2] != W_ * a_stride[i]:
                 raise RuntimeError('gemm: source spatial dims do not match the output dims times the source stride')
             d.a_ptr[i] = L.ptr(t)
@@ -389,7 +390,7 @@ class Plan:
         for i, (src, taps, cstart, cblocks) in enumerate(segs):
             d.seg[i] = L.KSeg(src, taps, cstart, cblocks)
         d.batch, d.H, d.W = B, H, W_
-        _c(w, torch.bfloat16)
+        _c(w, ACT_DTYPE)
         up = 4 if upsample2x else 1
         if upsample2x:
             if w.dim() != 3 or w.shape[0] != 4 or tuple(out.shape[:3]) != (B, 2 * H, 2 * W_):
@@ -428,7 +429,7 @@ class Plan:
         d = L.GnStatsDesc()
         B, H, W_, _ = x[0].shape
         for i, t in enumerate(x):
-            _c(t, torch.bfloat16)
+            _c(t, ACT_DTYPE)
             d.x_ptr[i] = L.ptr(t)
             d.x_channels[i] = t.shape[3]
         d.batch, d.HW, d.groups = B, H * W_, groups
@@ -469,7 +470,7 @@ class Plan:
         d = L.GnApplyDesc()
         B, H, W_, _ = x[0].shape
         for i, t in enumerate(x):
-            _c(t, torch.bfloat16)
+            _c(t, ACT_DTYPE)
             d.x_ptr[i] = L.ptr(t)
             d.x_channels[i] = t.shape[3]
         d.batch, d.H, d.W, d.groups = B, H, W_, groups
@@ -481,7 +482,7 @@ class Plan:
         d.ld_film = film_scale.stride(0) if film_scale is not None else 0
         d.b_emb = b_emb
         d.silu, d.resample = int(silu), resample
-        d.out, d.raw_out = L.ptr(_c(out, torch.bfloat16)), L.ptr(raw_out)
+        d.out, d.raw_out = L.ptr(_c(out, ACT_DTYPE)), L.ptr(raw_out)
         d.mean_rstd = L.ptr(mean_rstd)
         d.reverse = int(reverse)
         self._k(*x, partial, gamma, beta, pre_add, film_scale, film_shift, out, raw_out, mean_rstd)
@@ -496,17 +497,17 @@ class Plan:
         """qk: [batch*L, ld] with Q at col head*64, K at k_col0 + head*64; V either transposed in `vt`
         ([batch*heads*64, L]) or (vt=None) row-major in `qk` at v_col0 + head*64."""
         d = L.AttnDesc()
-        d.qk, d.ld_qk, d.k_col0 = L.ptr(_c(qk, torch.bfloat16)), qk.shape[-1], k_col0
+        d.qk, d.ld_qk, d.k_col0 = L.ptr(_c(qk, ACT_DTYPE)), qk.shape[-1], k_col0
         d.vt = L.ptr(vt)
         d.v_col0 = v_col0
         d.head_dim = head_dim
         d.reverse = int(reverse)
         d.scale = float(scale)
         if kv is not None:         # cross-attention: K/V of the (few) contexts, [kv_batch * kv_rows, ld_kv]
-            d.kv, d.ld_kv = L.ptr(_c(kv, torch.bfloat16)), kv.shape[-1]
+            d.kv, d.ld_kv = L.ptr(_c(kv, ACT_DTYPE)), kv.shape[-1]
             d.kv_batch, d.kv_rows, d.kv_len, d.kv_div = kv.numel() // (kv.shape[-1] * kv_rows), kv_rows, kv_len, kv_div
             self._keep.append(kv)
-        d.out, d.ld_out = L.ptr(_c(out, torch.bfloat16)), out.shape[-1]
+        d.out, d.ld_out = L.ptr(_c(out, ACT_DTYPE)), out.shape[-1]
         d.batch, d.heads, d.L = batch, heads, Lseq
         self._k(qk, vt, out)
         L.check(L.lib().b200ns_plan_add_attention(self._h, C.byref(d)), 'plan_add_attention')
@@ -534,8 +535,8 @@ class Plan:
         """nn.LayerNorm over the last dim of a bf16 tensor [..., C]."""
         Cc = x.shape[-1]
         self._k(x, gamma, beta, out)
-        L.check(L.lib().b200ns_plan_add_layernorm(self._h, L.ptr(_c(x, torch.bfloat16)), L.ptr(_c(gamma, torch.float32)),
-                                                  L.ptr(_c(beta, torch.float32)), L.ptr(_c(out, torch.bfloat16)),
+        L.check(L.lib().b200ns_plan_add_layernorm(self._h, L.ptr(_c(x, ACT_DTYPE)), L.ptr(_c(gamma, torch.float32)),
+                                                  L.ptr(_c(beta, torch.float32)), L.ptr(_c(out, ACT_DTYPE)),
                                                   x.numel() // Cc, Cc, float(eps)), 'plan_add_layernorm')
         self._misc('layernorm', label)
 
@@ -545,7 +546,7 @@ class Plan:
         if x.shape[-1] != 2 * F_:
             raise RuntimeError('geglu: input must be twice as wide as the output')
         self._k(x, out)
-        L.check(L.lib().b200ns_plan_add_geglu(self._h, L.ptr(_c(x, torch.bfloat16)), L.ptr(_c(out, torch.bfloat16)),
+        L.check(L.lib().b200ns_plan_add_geglu(self._h, L.ptr(_c(x, ACT_DTYPE)), L.ptr(_c(out, ACT_DTYPE)),
                                               out.numel() // F_, F_), 'plan_add_geglu')
         self._misc('geglu', label)
 
@@ -553,21 +554,21 @@ class Plan:
         """S fp32 [rows, L] -> P bf16 [rows, L] = softmax(scale * S) over the last axis."""
         self._k(S, P)
         rows, L_ = S.shape[-2] * (S.numel() // (S.shape[-1] * S.shape[-2])), S.shape[-1]
-        L.check(L.lib().b200ns_plan_add_softmax_rows(self._h, L.ptr(_c(S, torch.float32)), L.ptr(_c(P, torch.bfloat16)), rows, L_,
+        L.check(L.lib().b200ns_plan_add_softmax_rows(self._h, L.ptr(_c(S, torch.float32)), L.ptr(_c(P, ACT_DTYPE)), rows, L_,
                                                      float(scale)), 'plan_add_softmax_rows')
         self._misc('softmax_rows', label)
 
     def add_upsample2x(self, x: torch.Tensor, out: torch.Tensor, label='upsample2x'):
         B, H, W_, Cc = x.shape
         self._k(x, out)
-        L.check(L.lib().b200ns_plan_add_upsample2x(self._h, L.ptr(_c(x, torch.bfloat16)), L.ptr(_c(out, torch.bfloat16)),
+        L.check(L.lib().b200ns_plan_add_upsample2x(self._h, L.ptr(_c(x, ACT_DTYPE)), L.ptr(_c(out, ACT_DTYPE)),
                                                    B, H, W_, Cc), 'plan_add_upsample2x')
         self._misc('upsample2x', label)
 
     def add_im2col(self, x: torch.Tensor, out: torch.Tensor, label='im2col'):
         d = L.Im2colDesc()
         B, Cc, H, W_ = x.shape
-        d.x, d.out = L.ptr(_c(x, torch.float32)), L.ptr(_c(out, torch.bfloat16))
+        d.x, d.out = L.ptr(_c(x, torch.float32)), L.ptr(_c(out, ACT_DTYPE))
         d.batch, d.C, d.H, d.W = B, Cc, H, W_
         self._k(x, out)
         L.check(L.lib().b200ns_plan_add_im2col(self._h, C.byref(d)), 'plan_add_im2col')
@@ -633,7 +634,7 @@ class Plan:
         scr = getattr(self, '_gn_prec_scratch', None)
         if scr is None or scr[0].shape[0] < B:
             dev = x[0].device
-            scr = (torch.empty(B, 16, 64, 2, dtype=torch.float64, device=dev), torch.zeros(B, dtype=torch.int32, device=dev))
+            scr = (torch.empty(B, 64, 64, 2, dtype=torch.float64, device=dev), torch.zeros(B, dtype=torch.int32, device=dev))
             self._gn_prec_scratch = scr
         if groups > 64:
             raise RuntimeError('gn_prec: at most 64 groups')
@@ -701,14 +702,14 @@ class Plan:
 
     def add_pool_tokens(self, act, pos, tok, tok0, batch, T, Cc, label='pool_tokens'):
         self._k(act, pos, tok, tok0)
-        L.check(L.lib().b200ns_plan_add_pool_tokens(self._h, L.ptr(_c(act, torch.bfloat16)), L.ptr(_c(pos, torch.float32)),
-                                                    L.ptr(_c(tok, torch.bfloat16)), L.ptr(_c(tok0, torch.float32)), batch, T,
+        L.check(L.lib().b200ns_plan_add_pool_tokens(self._h, L.ptr(_c(act, ACT_DTYPE)), L.ptr(_c(pos, torch.float32)),
+                                                    L.ptr(_c(tok, ACT_DTYPE)), L.ptr(_c(tok0, torch.float32)), batch, T,
                                                     Cc), 'plan_add_pool_tokens')
         self._misc('misc', label)
 
     def add_pool_attention(self, qkv0, kv, out, batch, T, Cc, label='pool_attention'):
         self._k(qkv0, kv, out)
-        L.check(L.lib().b200ns_plan_add_pool_attention(self._h, L.ptr(_c(qkv0, torch.float32)), L.ptr(_c(kv, torch.bfloat16)),
+        L.check(L.lib().b200ns_plan_add_pool_attention(self._h, L.ptr(_c(qkv0, torch.float32)), L.ptr(_c(kv, ACT_DTYPE)),
                                                        L.ptr(_c(out, torch.float32)), batch, T, Cc), 'plan_add_pool_attention')
         self._misc('misc', label)
 

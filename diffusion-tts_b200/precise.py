@@ -132,7 +132,7 @@ class PreciseForwardPlan:
                 self._scratch['splitk'] = partial
         self.plan.add_gemm_prec(srcs, flat, w, N, out, acc_scale=acc_scale, bias=bias, residual=residual,
                                 out_scale=out_scale, label=label, flops=2.0 * B * H * W_ * N * w.shape[1],
-                                splits=splits, bn=bn, partial=partial)
+                                splits=splits, bn=0, partial=partial)      # tile width: the C side's cost model
 
     def _build(self, eng: 'PreciseUNetEngine'):
         self._eng = eng

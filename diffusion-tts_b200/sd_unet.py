@@ -25,6 +25,8 @@ from typing import Dict, List, Optional
 
 import torch
 
+from ._lib import ACT_DTYPE
+
 from .ops import Plan, interleave_geglu, pack_conv_up2
 from .unet import ForwardPlan, _pack_conv
 
@@ -274,16 +276,16 @@ class SDUNetEngine:
         heads = cfg['heads']
         f = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
         cpu = lambda t: t.detach().float().cpu()
-        bf = lambda t: t.contiguous().to(torch.bfloat16).to(dev)
+        bf = lambda t: t.contiguous().to(ACT_DTYPE).to(dev)
         for k in ('time_embedding.linear_1.weight', 'time_embedding.linear_1.bias', 'time_embedding.linear_2.weight',
                   'time_embedding.linear_2.bias', 'conv_norm_out.weight', 'conv_norm_out.bias'):
             w[k] = f(sd[k])
         cin = cfg['in_channels']
-        wp = torch.zeros(sd['conv_in.weight'].shape[0], 64, dtype=torch.bfloat16)
+        wp = torch.zeros(sd['conv_in.weight'].shape[0], 64, dtype=ACT_DTYPE)
         wp[:, :9 * cin] = _pack_conv(cpu(sd['conv_in.weight']))
         w['conv_in.w'], w['conv_in.b'] = wp.to(dev), f(sd['conv_in.bias'])
         wo = cpu(sd['conv_out.weight'])
-        wp = torch.zeros(16, 9 * wo.shape[1], dtype=torch.bfloat16)
+        wp = torch.zeros(16, 9 * wo.shape[1], dtype=ACT_DTYPE)
         wp[:wo.shape[0]] = _pack_conv(wo)
         w['conv_out.w'], w['conv_out.b'] = wp.to(dev), f(sd['conv_out.bias'])
 
@@ -302,7 +304,7 @@ class SDUNetEngine:
             off += cout
             w2 = _pack_conv(cpu(sd[f'{p}.conv2.weight']))
             if f'{p}.conv_shortcut.weight' in sd:            # [conv2 taps x cout | shortcut over the raw (concat) input]
-                ws = cpu(sd[f'{p}.conv_shortcut.weight'])[:, :, 0, 0].to(torch.bfloat16)
+                ws = cpu(sd[f'{p}.conv_shortcut.weight'])[:, :, 0, 0].to(ACT_DTYPE)
                 w[f'{p}.conv2sc.w'] = torch.cat([w2, ws], dim=1).contiguous().to(dev)
                 w[f'{p}.conv2sc.b'] = f(sd[f'{p}.conv2.bias']) + f(sd[f'{p}.conv_shortcut.bias'])
             else:
@@ -364,13 +366,13 @@ class SDUNetEngine:
         if Dc != self.cfg['cross_attention_dim'] or Dc % 64:
             raise ValueError('context width does not match the UNet (and must be a multiple of 64)')
         self.ctx_len = T
-        ctx = torch.zeros(2, 1, CTX_ROWS, Dc, device=self.device, dtype=torch.bfloat16)     # zero padded tokens
-        ctx[:, 0, :T] = ctx_pair.to(device=self.device, dtype=torch.bfloat16)
+        ctx = torch.zeros(2, 1, CTX_ROWS, Dc, device=self.device, dtype=ACT_DTYPE)     # zero padded tokens
+        ctx[:, 0, :T] = ctx_pair.to(device=self.device, dtype=ACT_DTYPE)
         plan = Plan()
         for name, wkv in self._kvw.items():
             kv = self.ctx_kv.get(name)
             if kv is None:
-                kv = torch.empty(2, 1, CTX_ROWS, wkv.shape[0], device=self.device, dtype=torch.bfloat16)
+                kv = torch.empty(2, 1, CTX_ROWS, wkv.shape[0], device=self.device, dtype=ACT_DTYPE)
                 self.ctx_kv[name] = kv
             plan.add_gemm([ctx], [(0, 1, 0, Dc // 64)], wkv, wkv.shape[0], kv, label=f'{name}.kv')
         plan.run()

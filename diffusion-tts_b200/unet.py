@@ -25,6 +25,8 @@ from typing import Dict, List, Optional
 
 import torch
 
+from ._lib import ACT_DTYPE
+
 from .ops import Plan, pack_conv_up2
 
 
@@ -129,7 +131,7 @@ def _pack_conv(w: torch.Tensor, splits: Optional[List[int]] = None) -> torch.Ten
         ws = w[:, c0:c0 + c]
         parts.append(ws.permute(0, 2, 3, 1).reshape(w.shape[0], -1))
         c0 += c
-    return torch.cat(parts, dim=1).contiguous().to(torch.bfloat16)
+    return torch.cat(parts, dim=1).contiguous().to(ACT_DTYPE)
 
 
 def _groups(c: int) -> int:
@@ -175,7 +177,7 @@ class ForwardPlan:
             self.plan.instantiate_graph()
 
     # -- helpers
-    def _buf(self, key: str, numel: int, dtype=torch.bfloat16) -> torch.Tensor:
+    def _buf(self, key: str, numel: int, dtype=ACT_DTYPE) -> torch.Tensor:
         key = f'{key}@{self._lane}'                       # scratch is private to a lane (lanes run concurrently)
         t = self._scratch.get(key)
         if t is None or t.numel() < numel:
@@ -186,7 +188,7 @@ class ForwardPlan:
     def _act(self, key: str, B, H, W, C) -> torch.Tensor:
         return self._buf(key, B * H * W * C)[:B * H * W * C].view(B, H, W, C)
 
-    def _persist(self, key: str, *shape, dtype=torch.bfloat16) -> torch.Tensor:
+    def _persist(self, key: str, *shape, dtype=ACT_DTYPE) -> torch.Tensor:
         """Full-batch tensor that outlives the op (block outputs / skips), allocated once per name."""
         t = self._full.get(key)
         if t is None:
@@ -487,7 +489,7 @@ class UNetEngine:
         for b in cfg.enc + cfg.dec:
             n = b.name
             if b.kind == 'conv':
-                wp = torch.zeros(b.cout, 64, dtype=torch.bfloat16)
+                wp = torch.zeros(b.cout, 64, dtype=ACT_DTYPE)
                 wp[:, :9 * b.cin] = _pack_conv(sd[f'{n}.weight'].detach().float().cpu())
                 w[f'{n}.w'], w[f'{n}.b'] = wp.to(dev), f(sd[f'{n}.bias'])
             elif b.kind == 'aux_norm':
@@ -505,7 +507,7 @@ class UNetEngine:
                 w[f'{n}.conv0.b'] = f(sd[f'{n}.conv0.bias'])
                 w1 = _pack_conv(sd[f'{n}.conv1.weight'].detach().float().cpu())
                 if b.skip_conv:
-                    ws = sd[f'{n}.skip.weight'].detach().float().cpu()[:, :, 0, 0].to(torch.bfloat16)
+                    ws = sd[f'{n}.skip.weight'].detach().float().cpu()[:, :, 0, 0].to(ACT_DTYPE)
                     w[f'{n}.conv1skip.w'] = torch.cat([w1, ws], dim=1).contiguous().to(dev)
                     w[f'{n}.conv1skip.b'] = f(sd[f'{n}.conv1.bias']) + f(sd[f'{n}.skip.bias'])
                 else:
@@ -515,10 +517,10 @@ class UNetEngine:
                     # reference channel order (head, d, {q,k,v}) (networks.py:182) -> [Q | K | V], head-major
                     wq = sd[f'{n}.qkv.weight'].detach().float().cpu()[:, :, 0, 0].reshape(C, 3, C).permute(1, 0, 2)
                     bq = sd[f'{n}.qkv.bias'].detach().float().cpu().reshape(C, 3).permute(1, 0)
-                    w[f'{n}.qkv.w'] = wq.reshape(3 * C, C).contiguous().to(torch.bfloat16).to(dev)
+                    w[f'{n}.qkv.w'] = wq.reshape(3 * C, C).contiguous().to(ACT_DTYPE).to(dev)
                     w[f'{n}.qkv.b'] = bq.reshape(3 * C).contiguous().to(dev)
                     w[f'{n}.proj.w'] = sd[f'{n}.proj.weight'].detach().float().cpu()[:, :, 0, 0].contiguous().to(
-                        torch.bfloat16).to(dev)
+                        ACT_DTYPE).to(dev)
                     w[f'{n}.proj.b'] = f(sd[f'{n}.proj.bias'])
                 self.affine_off[n] = off
                 aff_w.append(sd[f'{n}.affine.weight'].detach().float().cpu())
@@ -533,7 +535,7 @@ class UNetEngine:
 
     def _pack_out_conv(self, sd, key, name):
         wt = sd[f'{key}.weight'].detach().float().cpu()
-        wp = torch.zeros(16, 9 * wt.shape[1], dtype=torch.bfloat16)
+        wp = torch.zeros(16, 9 * wt.shape[1], dtype=ACT_DTYPE)
         wp[:wt.shape[0]] = _pack_conv(wt)
         self.w[f'{name}.w'] = wp.to(self.device)
         self.w[f'{name}.b'] = sd[f'{key}.bias'].detach().to(device=self.device, dtype=torch.float32).contiguous()

@@ -28,6 +28,8 @@ from typing import Dict, List, Optional
 
 import torch
 
+from ._lib import ACT_DTYPE
+
 from . import ops
 from .ops import Plan
 from .unet import ForwardPlan, _pack_conv
@@ -202,17 +204,17 @@ class VAEDecoderEngine:
         dev, w = self.device, self.w
         f = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
         cpu = lambda t: t.detach().float().cpu()
-        bf = lambda t: t.contiguous().to(torch.bfloat16).to(dev)
+        bf = lambda t: t.contiguous().to(ACT_DTYPE).to(dev)
         w['post_quant.w'] = f(sd['post_quant_conv.weight'][:, :, 0, 0])
         w['post_quant.b'] = f(sd['post_quant_conv.bias'])
         for k in ('decoder.conv_norm_out.weight', 'decoder.conv_norm_out.bias'):
             w[k] = f(sd[k])
         cin = self.cfg['latent_channels']
-        wp = torch.zeros(self.cfg['top'], 64, dtype=torch.bfloat16)
+        wp = torch.zeros(self.cfg['top'], 64, dtype=ACT_DTYPE)
         wp[:, :9 * cin] = _pack_conv(cpu(sd['decoder.conv_in.weight']))
         w['decoder.conv_in.w'], w['decoder.conv_in.b'] = wp.to(dev), f(sd['decoder.conv_in.bias'])
         wo = cpu(sd['decoder.conv_out.weight'])
-        wp = torch.zeros(16, 9 * wo.shape[1], dtype=torch.bfloat16)
+        wp = torch.zeros(16, 9 * wo.shape[1], dtype=ACT_DTYPE)
         wp[:wo.shape[0]] = _pack_conv(wo)
         w['decoder.conv_out.w'], w['decoder.conv_out.b'] = wp.to(dev), f(sd['decoder.conv_out.bias'])
         for p in sorted({k[:-len('.conv1.weight')] for k in sd if k.startswith('decoder.') and k.endswith('.conv1.weight')}):
@@ -223,7 +225,7 @@ class VAEDecoderEngine:
             w[f'{p}.conv1.w'], w[f'{p}.conv1.b'] = bf(_pack_conv(w1)), f(sd[f'{p}.conv1.bias'])
             w2 = _pack_conv(cpu(sd[f'{p}.conv2.weight']))
             if f'{p}.conv_shortcut.weight' in sd:
-                ws = cpu(sd[f'{p}.conv_shortcut.weight'])[:, :, 0, 0].to(torch.bfloat16)
+                ws = cpu(sd[f'{p}.conv_shortcut.weight'])[:, :, 0, 0].to(ACT_DTYPE)
                 w[f'{p}.conv2sc.w'] = torch.cat([w2, ws], dim=1).contiguous().to(dev)
                 w[f'{p}.conv2sc.b'] = f(sd[f'{p}.conv2.bias']) + f(sd[f'{p}.conv_shortcut.bias'])
             else:

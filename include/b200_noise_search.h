@@ -22,6 +22,9 @@ extern "C" {
 #endif
 
 const char* b200ns_last_error(void);
+/* 1 if the library stores activations / weights as IEEE half (the default build), 0 for the bfloat16 build
+ * (-DB200NS_ACT_BF16).  "bf16" in the comments below means this 16-bit storage type. */
+int b200ns_act_is_fp16(void);
 /* 1 if device `dev` is compute capability 10.x (B200), else 0. */
 int b200ns_device_ok(int dev);
 
@@ -315,7 +318,7 @@ typedef struct {
   void* out;                 /* split half [batch, H', W', 2C] */
   void* raw_out;             /* split half or NULL */
   float* mean_rstd;          /* fp32 [batch, groups, 2]: written by the stats op, read by the apply op */
-  double* partial;           /* stats scratch: fp64 [batch, 16, groups, 2] */
+  double* partial;           /* stats scratch: fp64 [batch, 64, groups, 2] */
   int32_t* ticket;           /* stats scratch: int32 [batch], zero-initialised once (the kernel resets it) */
 } b200ns_gn_prec_desc;
 /* per-(sample, group) mean / rstd in fp64 over hi + lo (+ pre_add) -> mean_rstd (networks.py:104-106) */

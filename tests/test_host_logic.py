@@ -10,6 +10,8 @@ import sys
 import pytest
 import torch
 
+from diffusion_tts_b200._lib import ACT_DTYPE as ACT  # noqa: E402  (the engine's 16-bit storage type)
+
 from oracle import edm_oracle as O
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -191,7 +193,7 @@ def test_pack_conv_up2_is_the_phase_decomposition_of_upsample_then_conv():
     ref = F.conv2d(F.interpolate(x, scale_factor=2.0, mode='nearest'), w, padding=1)
     for splits in (None, [2, 4]):
         wp = pack_conv_up2(w.float(), splits)
-        assert wp.shape == (4, Cout, 4 * Cin) and wp.dtype == torch.bfloat16
+        assert wp.shape == (4, Cout, 4 * Cin) and wp.dtype == ACT
         xp = F.pad(x, (1, 1, 1, 1))
         out = torch.zeros_like(ref)
         for ph in range(4):

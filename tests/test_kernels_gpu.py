@@ -4,6 +4,8 @@ import math
 
 import pytest
 import torch
+
+from diffusion_tts_b200._lib import ACT_DTYPE as ACT  # noqa: E402  (the engine's 16-bit storage type)
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
@@ -23,12 +25,12 @@ def _rel_err(a, b):
 
 
 def _nhwc(x):       # NCHW fp32 -> NHWC bf16
-    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    return x.permute(0, 2, 3, 1).contiguous().to(ACT)
 
 
 def _pack_w(w):     # [Cout,Cin,k,k] -> bf16 [Cout, k*k*Cin] (tap-major, channel-minor)
     co, ci, kh, kw = w.shape
-    return w.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).contiguous().to(torch.bfloat16)
+    return w.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).contiguous().to(ACT)
 
 
 @pytest.mark.parametrize('B,H,Cin,Cout,k', [
@@ -42,7 +44,7 @@ def test_conv_gemm(ops, B, H, Cin, Cout, k):
     w = torch.randn(Cout, Cin, k, k, device=dev) / math.sqrt(Cin * k * k)
     bias = torch.randn(Cout, device=dev)
     xa, wp = _nhwc(x), _pack_w(w)
-    out = torch.empty(B, H, H, Cout, device=dev, dtype=torch.bfloat16)
+    out = torch.empty(B, H, H, Cout, device=dev, dtype=ACT)
     plan = ops.Plan()
     plan.add_gemm([xa], [(0, k * k, 0, Cin // 64)], wp, Cout, out, bias=bias)
     plan.run()
@@ -67,16 +69,16 @@ def test_conv_fused_skip_dual_source_residual(ops):
     bias = torch.randn(Co, device=dev)
     ha, x0a, x1a = _nhwc(h), _nhwc(x0), _nhwc(x1)
     # segment-major K packing: [conv1 taps x Co | skip C0 | skip C1]
-    wp = torch.cat([_pack_w(w1), ws[:, :C0, 0, 0].to(torch.bfloat16), ws[:, C0:, 0, 0].to(torch.bfloat16)], dim=1).contiguous()
-    out = torch.empty(B, H, H, Co, device=dev, dtype=torch.bfloat16)
+    wp = torch.cat([_pack_w(w1), ws[:, :C0, 0, 0].to(ACT), ws[:, C0:, 0, 0].to(ACT)], dim=1).contiguous()
+    out = torch.empty(B, H, H, Co, device=dev, dtype=ACT)
     # sources: 0 = h ; the skip operands come from a 2nd launch-level source, so run as two plans:
     # (a) h + x0 as sources [conv1 | skip(x0)], (b) check dual-source concat conv separately.
     plan = ops.Plan()
-    wpa = torch.cat([_pack_w(w1), ws[:, :C0, 0, 0].to(torch.bfloat16)], dim=1).contiguous()
+    wpa = torch.cat([_pack_w(w1), ws[:, :C0, 0, 0].to(ACT)], dim=1).contiguous()
     plan.add_gemm([ha, x0a], [(0, 9, 0, Co // 64), (1, 1, 0, C0 // 64)], wpa, Co, out, bias=bias, out_scale=0.5)
     plan.run()
-    ref = (F.conv2d(ha.float().permute(0, 3, 1, 2), w1.to(torch.bfloat16).float(), None, padding=1) +
-           F.conv2d(x0a.float().permute(0, 3, 1, 2), ws[:, :C0].to(torch.bfloat16).float()) +
+    ref = (F.conv2d(ha.float().permute(0, 3, 1, 2), w1.to(ACT).float(), None, padding=1) +
+           F.conv2d(x0a.float().permute(0, 3, 1, 2), ws[:, :C0].to(ACT).float()) +
            bias.view(1, -1, 1, 1)) * 0.5
     assert _rel_err(out, ref.permute(0, 2, 3, 1)) < 6e-3
     # dual-source 3x3 conv over cat([x0, x1]) with a residual
@@ -88,7 +90,7 @@ def test_conv_fused_skip_dual_source_residual(ops):
     plan2.add_gemm([x0a, x1a], [(0, 9, 0, C0 // 64), (1, 9, 0, C1 // 64)], wpc, Co, out2, bias=bias, residual=res)
     plan2.run()
     xcat = torch.cat([x0a, x1a], dim=3).float().permute(0, 3, 1, 2)
-    ref2 = F.conv2d(xcat, wc.to(torch.bfloat16).float(), bias, padding=1).permute(0, 2, 3, 1) + res.float()
+    ref2 = F.conv2d(xcat, wc.to(ACT).float(), bias, padding=1).permute(0, 2, 3, 1) + res.float()
     assert _rel_err(out2, ref2) < 6e-3
 
 
@@ -100,13 +102,13 @@ def test_conv_small_n_fp32_out(ops):
     x = torch.randn(B, Cin, H, H, device=dev)
     w = torch.randn(3, Cin, 3, 3, device=dev) / math.sqrt(Cin * 9)
     bias = torch.randn(3, device=dev)
-    wp = torch.zeros(16, 9 * Cin, device=dev, dtype=torch.bfloat16)
+    wp = torch.zeros(16, 9 * Cin, device=dev, dtype=ACT)
     wp[:3] = _pack_w(w)
     out = torch.empty(B, H, H, 3, device=dev, dtype=torch.float32)
     plan = ops.Plan()
     plan.add_gemm([_nhwc(x)], [(0, 9, 0, Cin // 64)], wp, 3, out, bias=bias)
     plan.run()
-    ref = F.conv2d(_nhwc(x).float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), bias, padding=1).permute(0, 2, 3, 1)
+    ref = F.conv2d(_nhwc(x).float().permute(0, 3, 1, 2), w.to(ACT).float(), bias, padding=1).permute(0, 2, 3, 1)
     assert _rel_err(out, ref) < 2e-3
 
 
@@ -117,15 +119,15 @@ def test_first_conv_im2col(ops):
     x = torch.randn(B, 3, H, H, device=dev)
     w = torch.randn(Co, 3, 3, 3, device=dev) / math.sqrt(27)
     bias = torch.randn(Co, device=dev)
-    col = torch.empty(B, H, H, 64, device=dev, dtype=torch.bfloat16)
-    wp = torch.zeros(Co, 64, device=dev, dtype=torch.bfloat16)
+    col = torch.empty(B, H, H, 64, device=dev, dtype=ACT)
+    wp = torch.zeros(Co, 64, device=dev, dtype=ACT)
     wp[:, :27] = _pack_w(w)
-    out = torch.empty(B, H, H, Co, device=dev, dtype=torch.bfloat16)
+    out = torch.empty(B, H, H, Co, device=dev, dtype=ACT)
     plan = ops.Plan()
     plan.add_im2col(x, col)
     plan.add_gemm([col], [(0, 1, 0, 1)], wp, Co, out, bias=bias)
     plan.run()
-    ref = F.conv2d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), bias, padding=1).permute(0, 2, 3, 1)
+    ref = F.conv2d(x.to(ACT).float(), w.to(ACT).float(), bias, padding=1).permute(0, 2, 3, 1)
     assert _rel_err(out, ref) < 6e-3
 
 
@@ -149,7 +151,7 @@ def test_groupnorm(ops, C0, C1, H, resample, film, silu):
     splits = 4
     partial = torch.empty(B, splits, groups, 2, device=dev, dtype=torch.float64)
     Ho = H * 2 if resample == 1 else (H // 2 if resample == 2 else H)
-    out = torch.empty(B, Ho, Ho, C, device=dev, dtype=torch.bfloat16)
+    out = torch.empty(B, Ho, Ho, C, device=dev, dtype=ACT)
     raw = torch.empty_like(out)
     plan = ops.Plan()
     plan.add_gn_stats(xs, groups, partial, splits)
@@ -179,9 +181,9 @@ def test_attention(ops, B, heads, L):
     q = torch.randn(B, L, C, device=dev)
     k = torch.randn(B, L, C, device=dev)
     v = torch.randn(B, L, C, device=dev)
-    qk = torch.cat([q, k], dim=2).to(torch.bfloat16).contiguous()                  # [B, L, 2C]
-    vt = v.to(torch.bfloat16).reshape(B, L, heads, 64).permute(0, 2, 3, 1).contiguous()   # [B, heads, 64, L]
-    out = torch.zeros(B, L, C, device=dev, dtype=torch.bfloat16)
+    qk = torch.cat([q, k], dim=2).to(ACT).contiguous()                  # [B, L, 2C]
+    vt = v.to(ACT).reshape(B, L, heads, 64).permute(0, 2, 3, 1).contiguous()   # [B, heads, 64, L]
+    out = torch.zeros(B, L, C, device=dev, dtype=ACT)
     plan = ops.Plan()
     plan.add_attention(qk.reshape(B * L, 2 * C), C, vt.reshape(B * heads * 64, L), out.reshape(B * L, C), B, heads, L)
     plan.run()
@@ -199,8 +201,8 @@ def test_attention_row_major_v(ops, B, heads, L):
     torch.manual_seed(15)
     dev = 'cuda'
     C = heads * 64
-    qkv = torch.randn(B, L, 3 * C, device=dev).to(torch.bfloat16).contiguous()
-    out = torch.zeros(B, L, C, device=dev, dtype=torch.bfloat16)
+    qkv = torch.randn(B, L, 3 * C, device=dev).to(ACT).contiguous()
+    out = torch.zeros(B, L, C, device=dev, dtype=ACT)
     plan = ops.Plan()
     plan.add_attention(qkv.reshape(B * L, 3 * C), C, None, out.reshape(B * L, C), B, heads, L, v_col0=2 * C)
     plan.run()
@@ -216,8 +218,8 @@ def test_attention_head_dim_256(ops, B, L):
     torch.manual_seed(16)
     dev = 'cuda'
     C = 256
-    qkv = torch.randn(B, L, 3 * C, device=dev).to(torch.bfloat16).contiguous()
-    out = torch.zeros(B, L, C, device=dev, dtype=torch.bfloat16)
+    qkv = torch.randn(B, L, 3 * C, device=dev).to(ACT).contiguous()
+    out = torch.zeros(B, L, C, device=dev, dtype=ACT)
     plan = ops.Plan()
     plan.add_attention(qkv.reshape(B * L, 3 * C), C, None, out.reshape(B * L, C), B, 1, L, v_col0=2 * C, head_dim=256)
     plan.run()
@@ -241,7 +243,7 @@ def test_gemm_epilogue_gn_stats_and_finalize(ops, B, H, C0, C1, Cout, k, pre):
         w = torch.randn(Cout, Cin, k, k, device=dev) / math.sqrt(Cin * k * k)
         bias = torch.randn(Cout, device=dev)
         res = _nhwc(torch.randn(B, Cout, H, H, device=dev))
-        out = torch.empty(B, H, H, Cout, device=dev, dtype=torch.bfloat16)
+        out = torch.empty(B, H, H, Cout, device=dev, dtype=ACT)
         st = torch.full((B * H * H // 64, Cout, 2), float('nan'), device=dev)
         plan = ops.Plan()
         plan.add_gemm([x], [(0, k * k, 0, Cin // 64)], _pack_w(w), Cout, out, bias=bias, residual=res, out_scale=0.7,
@@ -261,7 +263,7 @@ def test_gemm_epilogue_gn_stats_and_finalize(ops, B, H, C0, C1, Cout, k, pre):
     pa = torch.randn(1, C, device=dev) if pre else None
     gamma, beta = torch.randn(C, device=dev), torch.randn(C, device=dev)
     mr = torch.empty(B, groups, 2, device=dev)
-    y = torch.empty(B, H, H, C, device=dev, dtype=torch.bfloat16)
+    y = torch.empty(B, H, H, C, device=dev, dtype=ACT)
     plan = ops.Plan()
     plan.add_gn_finalize(stats, [Cout] * len(outs), B, H * H, groups, 1e-5, mr, pre_add=pa)
     plan.add_gn_apply(outs, groups, None, 1, 1e-5, gamma, beta, y, pre_add=pa, silu=True, mean_rstd=mr)
@@ -416,11 +418,11 @@ def test_conv_fused_nearest_upsample(ops, B, H, W, Cin, Cout):
     """out = conv3x3(nearest_upsample_2x(x)) from the LOW-res x as four 2x2-tap phase launches (pre-summed weights): against
     torch on the same bf16-rounded phase weights, plus the high-res GroupNorm statistics side band."""
     torch.manual_seed(3)
-    x = torch.randn(B, H, W, Cin, device='cuda').to(torch.bfloat16)
+    x = torch.randn(B, H, W, Cin, device='cuda').to(ACT)
     w = torch.randn(Cout, Cin, 3, 3, device='cuda') / math.sqrt(Cin * 9)
     bias = torch.randn(Cout, device='cuda')
     wp = ops.pack_conv_up2(w).cuda()
-    out = torch.zeros(B, 2 * H, 2 * W, Cout, device='cuda', dtype=torch.bfloat16)
+    out = torch.zeros(B, 2 * H, 2 * W, Cout, device='cuda', dtype=ACT)
     st = torch.zeros(B * 4 * H * W // 64, Cout, 2, device='cuda')
     plan = ops.Plan()
     plan.add_gemm([x], [(0, 9, 0, Cin // 64)], wp, Cout, out, bias=bias, gn_stats=st, upsample2x=True)

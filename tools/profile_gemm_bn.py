@@ -3,16 +3,18 @@ Usage: python tools/profile_gemm_bn.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+
+from diffusion_tts_b200._lib import ACT_DTYPE as ACT  # noqa: E402  (the engine's 16-bit storage type)
 from diffusion_tts_b200 import build
 build.build()
 from diffusion_tts_b200 import ops, _lib as L
 
 def run(B, H, Cin, N, taps, bn, res=False, stats=False):
     L.lib().b200ns_debug_force_tile_width(bn)
-    x = torch.randn(B, H, H, Cin, device='cuda').to(torch.bfloat16)
-    w = (torch.randn(N, taps * Cin, device='cuda') / (taps * Cin) ** 0.5).to(torch.bfloat16)
-    out = torch.empty(B, H, H, N, device='cuda', dtype=torch.bfloat16)
-    r = torch.randn(B, H, H, N, device='cuda').to(torch.bfloat16) if res else None
+    x = torch.randn(B, H, H, Cin, device='cuda').to(ACT)
+    w = (torch.randn(N, taps * Cin, device='cuda') / (taps * Cin) ** 0.5).to(ACT)
+    out = torch.empty(B, H, H, N, device='cuda', dtype=ACT)
+    r = torch.randn(B, H, H, N, device='cuda').to(ACT) if res else None
     st = torch.empty(B * H * H // 64, N, 2, device='cuda') if stats else None
     plan = ops.Plan()
     plan.add_gemm([x], [(0, taps, 0, Cin // 64)], w, N, out, residual=r, gn_stats=st)

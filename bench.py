@@ -8,17 +8,27 @@ S_noise=1.003) -- BASELINE.json configs[1].
 One "step" = one denoising timestep of the eps_greedy search with K_local=1: build N=64
 candidates per GPU around the pivot, 2 batched denoiser calls (1 on the last of 18 steps),
 Tweedie x0, brightness score, first-max argmax (+ all-reduce of the packed key when N>1 GPUs),
-pivot update and the commit step (2 more denoiser calls at batch 1).  Steps cycle through the
-18 timesteps, so any multiple of 18 steps averages 426.5 GFLOP per scored candidate.
+NEAR-TIE ESCALATION (the contenders within kappa x spread of the best score are re-scored by the
+fp32-faithful split-fp16 engine, so that the selected index equals the fp32 reference's:
+tests/test_full_parity_gpu.py), pivot update, commit.  commit = 'reuse': the winner's own x_next is
+the committed state (bit-identical to the reference's recomputation at batch 1, which is therefore
+NOT executed and NOT counted: `config.commit`).  Steps cycle through the 18 timesteps, so any
+multiple of 18 steps averages 426.5 GFLOP per scored candidate (35/18 network evaluations).
 
-`value`  : candidates/s with all inputs (noise directions, pivots) resident in HBM.
+`value`  : candidates/s with all inputs (noise directions, pivots) resident in HBM, escalation ON.
 `e2e`    : the same loop through the public API with HOST (pinned) noise buffers: per step the
            pivot and this rank's slice of the N direction tensors are copied host->device and the
            winning index, its score and the committed state are copied back into pinned host buffers
            (asynchronously, in stream order; the timed region ends with a synchronize, so every byte
            has arrived inside it).
-`extras` : the same steps with the exact shortcut for the noise-free timesteps (the N identical
-           candidates of such a step evaluated once) -- reported separately, never the headline.
+`extras` : reported separately, never the headline --
+           no_escalation        the plain 16-bit tensor-core path (what round 1 measured)
+           noise_free_dedupe    + the exact shortcut for the noise-free timesteps
+           eps04                eps = 0.4 (CLI default): fresh-noise candidates mixed in (Bernoulli on the host mirror)
+           commit_recompute     the reference's literal commit (2 more network calls at batch 1 per step)
+           strong_config3       BASELINE.json configs[2]: zero_order N=256 TOTAL, sharded over the run's GPUs
+           sampler_gbs          the fused sampler / scorer kernels at 4096 synthetic candidate rows vs the HBM peak
+           eager_b200           the reference algorithm in plain PyTorch eager ON THIS GPU (fp32, and bf16 autocast)
 `--impl reference` times the reference algorithm's CPU path (oracle port, all host threads) on
 a bounded sample of the same workload.
 """
@@ -44,12 +54,12 @@ METRIC = 'scored_candidates_per_sec'
 UNIT = 'candidates/s'
 
 
-def workload_name(n_total, scorer='brightness'):
+def workload_name(n_total, scorer='brightness', eps=0.0, method='eps_greedy'):
     sc = 'brightness scorer' if scorer == 'brightness' else ('ImageNet classifier-probability scorer (EncoderUNetModel 64x64, '
                                                              'random-init, in the loop)' if scorer == 'imagenet' else
                                                              'compressibility scorer (exact JPEG q80 byte count)')
-    return (f'EDM ImageNet-64 ADM (DhariwalUNet 295.9M, class-cond, random-init), eps_greedy N={n_total} '
-            f'(={N_PER_GPU}/GPU) K=1 lambda=0.15 eps=0, {sc}, 18-step Heun cycle, b=1 image')
+    return (f'EDM ImageNet-64 ADM (DhariwalUNet 295.9M, class-cond, random-init), {method} N={n_total} '
+            f'(={N_PER_GPU}/GPU) K=1 lambda=0.15 eps={eps:g}, {sc}, 18-step Heun cycle, b=1 image')
 
 
 class ClockSampler:
@@ -90,37 +100,45 @@ def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get('bf16_tflops_sustained', 1415.6), d.get('hbm_gbs', 6452.2), 'measured (MEASURED_PEAKS.json, sustained bf16)'
-    return 1400.0, 6650.0, 'fallback (B200_PROFILING.md)'
+        return (d.get('bf16_tflops_sustained', 1415.6), d.get('bf16_tflops', 1691.7), d.get('hbm_gbs', 6452.2),
+                'measured (MEASURED_PEAKS.json; frac is against the sustained 16-bit figure, the step runs for seconds)')
+    return 1400.0, 1650.0, 6650.0, 'fallback (B200_PROFILING.md)'
 
 
 # ------------------------------------------------------------------------------------ reference arm / cpu baseline
-def oracle_cpu_rate(n_cand: int, steps, warmup: int):
-    """Reference algorithm on the host cores (oracle port of edm/main.py:714-860 + the fp32
-    ADM-64 forward): `n_cand` candidates through each listed timestep, K=1."""
+def oracle_rate(n_cand: int, steps, warmup: int, device='cpu', autocast=None):
+    """Reference algorithm (oracle port of edm/main.py:714-860 + the fp32 ADM-64 forward) on `device`:
+    `n_cand` candidates through each listed timestep, K=1, incl. the reference's commit recomputation."""
+    import contextlib
     from oracle import edm_oracle as O
     torch.manual_seed(0)
+    dev = torch.device(device)
     spec = O.build_unet_spec('DhariwalUNet', 64, 3, 3, label_dim=1000)
-    sd = O.seeded_state_dict(O.unet_param_shapes(spec), 1234)
+    sd = {k: v.to(dev) for k, v in O.seeded_state_dict(O.unet_param_shapes(spec), 1234).items()}
     net = O.OracleNet(spec, sd)
-    t_steps = O.karras_schedule(NUM_STEPS)
+    t_steps = O.karras_schedule(NUM_STEPS).to(dev)
     g = torch.Generator().manual_seed(1)
-    labels = torch.eye(1000)[torch.randint(1000, (1,), generator=g)]
-    x = torch.randn(1, 3, 64, 64, generator=g, dtype=torch.float64) * t_steps[0]
+    labels = torch.eye(1000)[torch.randint(1000, (1,), generator=g)].to(dev)
+    x = (torch.randn(1, 3, 64, 64, generator=g, dtype=torch.float64) * t_steps[0].cpu()).to(dev)
     lam = 0.15 * (3 * 64 * 64) ** 0.5
     times = []
+    sync = (lambda: torch.cuda.synchronize(dev)) if dev.type == 'cuda' else (lambda: None)
     for it, i in enumerate(steps):
-        pivot = torch.randn(1, 3, 64, 64, generator=g, dtype=torch.float64)
-        dirs = [torch.randn(1, 3, 64, 64, generator=g, dtype=torch.float64) for _ in range(n_cand)]
+        pivot = torch.randn(1, 3, 64, 64, generator=g, dtype=torch.float64).to(dev)
+        dirs = [torch.randn(1, 3, 64, 64, generator=g, dtype=torch.float64).to(dev) for _ in range(n_cand)]
+        sync()
         t0 = time.perf_counter()
-        scales = [O.candidate_scale_fp32(((i * 31 + n * 17) % 1000) / 1000.0, lam) for n in range(n_cand)]
-        cands = O.make_candidates(pivot, dirs, scales, [None] * n_cand)
-        _, x0 = O.heun_step(net, x.repeat(n_cand, 1, 1, 1), t_steps[i], t_steps[i + 1], i, cands,
-                            labels.repeat(n_cand, 1), num_steps=NUM_STEPS, **SAMPLER)
-        scores = O.brightness_score(O.quantize_u8(x0)).reshape(n_cand, 1)
-        best = O.argmax_first(scores, dim=0)
-        pivot = cands[best[0]:best[0] + 1]
-        x_new, _ = O.heun_step(net, x, t_steps[i], t_steps[i + 1], i, pivot, labels, num_steps=NUM_STEPS, **SAMPLER)
+        ctx = torch.autocast('cuda', dtype=autocast) if autocast is not None else contextlib.nullcontext()
+        with ctx, torch.no_grad():
+            scales = [O.candidate_scale_fp32(((i * 31 + n * 17) % 1000) / 1000.0, lam).to(dev) for n in range(n_cand)]
+            cands = O.make_candidates(pivot, dirs, scales, [None] * n_cand)
+            _, x0 = O.heun_step(net, x.repeat(n_cand, 1, 1, 1), t_steps[i], t_steps[i + 1], i, cands,
+                                labels.repeat(n_cand, 1), num_steps=NUM_STEPS, **SAMPLER)
+            scores = O.brightness_score(O.quantize_u8(x0)).reshape(n_cand, 1)
+            best = O.argmax_first(scores, dim=0)
+            pivot = cands[best[0]:best[0] + 1]
+            x_new, _ = O.heun_step(net, x, t_steps[i], t_steps[i + 1], i, pivot, labels, num_steps=NUM_STEPS, **SAMPLER)
+        sync()
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
@@ -131,20 +149,65 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    n_cand = 2
+    # torchrun exports OMP_NUM_THREADS=1: the reference arm uses every host core regardless of how it was launched
+    torch.set_num_threads(os.cpu_count() or 1)
+    n_cand = 8
     steps = [(8 + j) % NUM_STEPS for j in range(args.warmup + args.steps)]
-    rate, per_step = oracle_cpu_rate(n_cand, steps, args.warmup)
+    rate, per_step = oracle_rate(n_cand, steps, args.warmup)
     cores = torch.get_num_threads()
-    sample = (f'{n_cand} candidates per step (of the {N_PER_GPU} of the workload) through {args.steps} eps_greedy '
-              f'timesteps incl. the commit step, fp32 ADM-64 on CPU')
+    sample = (f'{n_cand} candidates per step (of the {N_PER_GPU} of the workload; cost per candidate is linear) through '
+              f'{args.steps} eps_greedy timesteps incl. the reference\'s commit recomputation, fp32 ADM-64 on CPU')
     line = {'metric': METRIC, 'value': rate, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': per_step * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
-            'config': {'workload': workload_name(N_PER_GPU * args.gpus), 'sampled': sample},
+            'config': {'workload': workload_name(N_PER_GPU * args.gpus), 'sampled': sample, 'commit': 'recompute (reference)',
+                       'note': 'the reference has no multi-GPU path: the same single-process CPU figure at every --gpus'},
             'cpu_baseline': {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ sampler kernels vs HBM
+def sampler_gbs(dev, peak_gbs, rows=4096, reps=5):
+    """north_star (2): achieved HBM GB/s of the fused sampler / scorer kernels on `rows` synthetic candidate rows
+    (E = 12288; >= 400 MB per tensor, far beyond the 126 MB L2).  Algorithmic bytes per row (fp64 state, fp32 net I/O):
+    norms R 8E; candidates R 8E + W 8E; pre R 8E + W 8E + W 4E; mid R 8E + R 4E + W 4E; post R 8E + R 4E + R 4E (+ sums)."""
+    from diffusion_tts_b200 import ops
+    E = 3 * 64 * 64
+    g = torch.Generator(device=dev).manual_seed(3)
+    x_cur = torch.randn(1, 3, 64, 64, dtype=torch.float64, device=dev, generator=g)
+    dirs = torch.randn(rows, 3, 64, 64, dtype=torch.float64, device=dev, generator=g)
+    F1 = torch.randn(rows, 64, 64, 3, dtype=torch.float32, device=dev, generator=g)
+    F2 = torch.randn(rows, 64, 64, 3, dtype=torch.float32, device=dev, generator=g)
+    scale = torch.rand(rows, dtype=torch.float32, device=dev, generator=g)
+    out = {}
+
+    def timeit(name, nbytes, fn):
+        fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / reps
+        out[name] = {'gbs': nbytes / ms / 1e6, 'ms': ms, 'frac_of_hbm_peak': nbytes / ms / 1e6 / peak_gbs}
+
+    norms = ops.direction_norms(dirs)
+    cand = ops.make_candidates(x_cur, dirs, norms, scale)
+    x_hat, net_in = ops.heun_pre(x_cur, cand, 1.5, 0.7)
+    timeit('direction_norms', rows * 8 * E, lambda: ops.direction_norms(dirs))
+    timeit('make_candidates', rows * 16 * E, lambda: ops.make_candidates(x_cur, dirs, norms, scale))
+    timeit('heun_pre', rows * 20 * E, lambda: ops.heun_pre(x_cur, cand, 1.5, 0.7, x_hat=x_hat, net_in=net_in))
+    timeit('heun_mid', rows * 16 * E, lambda: ops.heun_mid(x_hat, F1, 0.3, 0.8, 2.0, -0.5, 0.6, net_in2=net_in))
+    timeit('heun_post_score', rows * 16 * E,
+           lambda: ops.heun_post(x_hat, F1, F2, 0.3, 0.8, 2.0, -0.5, 0.35, 0.75, 1.5, want_x_next=False, want_sums=True))
+    tot_b = rows * (8 + 16 + 20 + 16 + 16) * E
+    tot_ms = sum(v['ms'] for v in out.values())
+    return {'rows': rows, 'bytes_per_row': 76 * E, 'aggregate_gbs': tot_b / tot_ms / 1e6, 'hbm_peak_gbs': peak_gbs,
+            'aggregate_frac': tot_b / tot_ms / 1e6 / peak_gbs, 'kernels': out}
 
 
 # ------------------------------------------------------------------------------------ B200 arm
@@ -159,11 +222,15 @@ def run_b200(args):
         dist.init_process_group('nccl', device_id=dev)
     sys.path.insert(0, ROOT)
     import __graft_entry__ as ge
+    if world > 1:                          # one builder per node: the others wait, then only load the finished .so
+        if local_rank == 0:
+            ge.build(oracle=False)
+        dist.barrier()
     ge.build(oracle=False)
-    from diffusion_tts_b200 import ops
+    from diffusion_tts_b200 import _lib, ops
     from diffusion_tts_b200.arch import adm_param_shapes, random_state_dict
     from diffusion_tts_b200.denoiser import B200Denoiser, StepTable
-    from diffusion_tts_b200.edm.main import SamplingParams, Shard, eps_greedy_search
+    from diffusion_tts_b200.edm.main import ESCALATION_KAPPA, SamplingParams, Shard, eps_greedy_search
     from diffusion_tts_b200.scorers import BrightnessScorer
 
     N = N_PER_GPU * world
@@ -192,21 +259,21 @@ def run_b200(args):
         host[i] = torch.randn(1, 1, N, 3, 64, 64, generator=g, dtype=torch.float64).pin_memory()
     on_dev = {k: v.to(dev) for k, v in host.items()}
     x0 = (latents.to(torch.float64) * table.t_steps[0].cpu()).to(dev)
+    esc = True if args.escalate < 0 else bool(args.escalate)
+    kappa = args.kappa if args.kappa > 0 else ESCALATION_KAPPA
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    esc = None if args.escalate < 0 else bool(args.escalate)
-
-    def timed(noise, steps_idx, x_init, on_step=None, dedupe=False, escalate=esc):
+    def timed(noise, steps_idx, x_init, on_step=None, dedupe=False, escalate=esc, p=params, commit='reuse', sh=shard):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        x, rec = eps_greedy_search(net, None, labels, params, table, precomputed_noise=noise, shard=shard,
+        x, rec = eps_greedy_search(net, None, labels, p, table, precomputed_noise=noise, shard=sh,
                                    step_indices=steps_idx, x_init=x_init, on_step=on_step, prefetch=bool(args.prefetch),
-                                   dedupe_noise_free=dedupe, escalate=escalate, **({'kappa': args.kappa} if args.kappa > 0 else {}))
+                                   dedupe_noise_free=dedupe, escalate=escalate, kappa=kappa, commit=commit)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -214,7 +281,13 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item(), x, rec
 
-    # ---- device-resident run
+    def rate(noise, n_total, **kw):
+        """warm-up + timed run of the standard step sequence -> (candidates/s, ms per step, record)"""
+        _, xw, _ = timed(noise, order[:args.warmup], x0, **kw)
+        ms_, _, rec_ = timed(noise, order[args.warmup:], xw, **kw)
+        return n_total * args.steps / (ms_ / 1e3), ms_ / args.steps, rec_
+
+    # ---- device-resident run: THE headline (escalation on)
     _, x, _ = timed(on_dev, order[:args.warmup], x0)
     clocks = ClockSampler(local_rank)
     clocks.start()                      # every rank samples its own GPU; rank 0's goes into `clocks`, all into `per_rank`
@@ -224,11 +297,52 @@ def run_b200(args):
     clk = clocks.stop()
     value = N * args.steps / (ms / 1e3)
 
-    # ---- reported separately, NOT the headline: the same steps with the exact shortcut for the noise-free timesteps (all N
-    # candidates of such a step are one tensor: evaluate it once); results are bit-identical
-    timed(on_dev, order[:args.warmup], x0, dedupe=True)
-    ms_dd, x_dd, _ = timed(on_dev, order[args.warmup:], x, dedupe=True)
-    noise_free = sum(1 for j in order[args.warmup:] if table.steps[j].s == 0.0)
+    extras = {}
+    # ---- the plain tensor-core path without escalation (round 1's configuration), and with the noise-free shortcut
+    v_ne, ms_ne, _ = rate(on_dev, N, escalate=False)
+    extras['no_escalation'] = {'value': v_ne, 'ms_per_step': ms_ne,
+                               'note': 'argmax over the 16-bit scores only: indices may differ from the fp32 reference on near ties'}
+    v_dd, ms_dd, _ = rate(on_dev, N, dedupe=True)
+    extras['noise_free_dedupe'] = {'value': v_dd, 'ms_per_step': ms_dd,
+                                   'noise_free_steps': sum(1 for j in order[args.warmup:] if table.steps[j].s == 0.0),
+                                   'note': 'same candidates counted; on the timesteps with noise scale 0 the N identical candidates '
+                                           'are evaluated once (bit-identical results); not the headline'}
+    # ---- the reference's literal commit step (2 more network evaluations at batch 1 per step)
+    v_rc, ms_rc, _ = rate(on_dev, N, commit='recompute')
+    extras['commit_recompute'] = {'value': v_rc, 'ms_per_step': ms_rc}
+    # ---- eps = 0.4 (the CLI default): every candidate is a fresh N(0,I) draw with probability 0.4
+    if not args.quick:
+        p04 = SamplingParams(N=N, K=1, eps=0.4, lambda_param=0.15, scorer=scorer)
+        noise04 = dict(on_dev)
+        gd = torch.Generator(device=dev).manual_seed(5)
+        fresh = {i: torch.randn(N, 1, 3, 64, 64, generator=gd, dtype=torch.float64, device=dev) for i in sorted(set(order))}
+        for i, t in fresh.items():
+            for n in range(N):
+                noise04[f'fresh_{i}_0_{n}'] = t[n]
+        torch.manual_seed(11)
+        v04, ms04, rec04 = rate(noise04, N, p=p04)
+        extras['eps04'] = {'value': v04, 'ms_per_step': ms04, 'rows_refined_per_step': rec04.escalated,
+                           'workload': workload_name(N, args.scorer, eps=0.4)}
+        del noise04, fresh
+    # ---- BASELINE.json configs[2]: zero_order N = 256 in total, strong-scaled over the run's GPUs
+    if not args.quick and 256 % world == 0:
+        p3 = SamplingParams(N=256, K=1, eps=0.0, lambda_param=0.15, scorer=scorer)
+        g3 = torch.Generator().manual_seed(2)
+        lo3, hi3 = shard.bounds(256)
+        noise3 = {}
+        for i in sorted(set(order)):
+            noise3[f'pivot_{i}'] = torch.randn(1, 3, 64, 64, generator=g3, dtype=torch.float64).to(dev)
+            full = torch.randn(1, 1, 256, 3, 64, 64, generator=g3, dtype=torch.float64)
+            # every rank keeps the full tensor shape the API expects but only ITS slice is ever read
+            noise3[i] = full.to(dev) if world == 1 else torch.zeros(1, 1, 256, 3, 64, 64, dtype=torch.float64, device=dev)
+            if world > 1:
+                noise3[i][:, :, lo3:hi3] = full[:, :, lo3:hi3].to(dev)
+        v3, ms3, rec3 = rate(noise3, 256, p=p3)
+        extras['strong_config3'] = {'value': v3, 'ms_per_step': ms3, 'N_total': 256, 'N_per_gpu': 256 // world,
+                                    'scaling': 'strong', 'rows_refined_per_step': rec3.escalated,
+                                    'workload': workload_name(256, args.scorer, method='zero_order').replace(
+                                        f'(={N_PER_GPU}/GPU)', f'(={256 // world}/GPU)')}
+        del noise3
 
     # ---- end-to-end run: host (pinned) noise in, per-step results out
     results = []
@@ -263,12 +377,14 @@ def run_b200(args):
     gemm_ms = sum(t for t, k in zip(per_op, fp.plan.kinds) if k == 'gemm')
     gemm_flops = sum(f for f, k in zip(fp.plan.flops, fp.plan.kinds) if k == 'gemm')
     n_gemm = sum(1 for k in fp.plan.kinds if k == 'gemm')
-    peak_tf, peak_gbs, peak_src = peaks()
+    peak_tf, peak_burst, peak_gbs, peak_src = peaks()
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12
     by_kind = {}
     for t, k in zip(per_op, fp.plan.kinds):
         by_kind[k] = by_kind.get(k, 0.0) + t
     nfe_ms = sum(per_op)
+    # network evaluations actually executed per step in the timed region (commit = reuse: none for the commit)
+    step_flops = N_PER_GPU * 35 / 18 * FLOP_PER_NFE
 
     per_rank = None
     if world > 1:                       # which GPU is the slow one?  (weak scaling waits for the slowest rank every step)
@@ -281,40 +397,64 @@ def run_b200(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    if not args.quick:
+        extras['sampler_gbs'] = sampler_gbs(dev, peak_gbs)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        rate, per_step = oracle_cpu_rate(2, [8, 9, 10], 1)
-        cpu = {'value': rate, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-               'sample': '2 candidates x 2 timed eps_greedy timesteps (i=9,10; 1 warm-up) incl. commit, fp32 ADM-64 '
-                         'oracle port on the host cores'}
+        torch.set_num_threads(os.cpu_count() or 1)
+        r_cpu, _ = oracle_rate(2, [8, 9, 10], 1)
+        cpu = {'value': r_cpu, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+               'sample': '2 candidates x 2 timed eps_greedy timesteps (i=9,10; 1 warm-up) incl. the reference\'s commit '
+                         'recomputation, fp32 ADM-64 oracle port on the host cores'}
+        # the same-box bar: the reference algorithm in plain PyTorch eager on THIS GPU
+        eager = {}
+        for tag, ac in (('fp32', None), ('bf16_autocast', torch.bfloat16)):
+            try:
+                r_e, ms_e = oracle_rate(16, [8, 9, 10, 11], 1, device=dev, autocast=ac)
+                eager[tag] = {'value': r_e, 'unit': UNIT, 'ms_per_step': ms_e * 1e3}
+            except Exception as e:          # the oracle is test infrastructure: never let it take the bench line down
+                eager[tag] = {'error': f'{type(e).__name__}: {e}'[:200]}
+            torch.cuda.empty_cache()
+        eager['sample'] = ('oracle port of the reference (plain PyTorch ops: cuDNN / cuBLAS / ATen) on this GPU, 16 candidates x 3 '
+                           'timed timesteps incl. the reference\'s commit recomputation; TF32 off (torch default)')
+        extras['eager_b200'] = eager
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'bf16', 'data': 'synthetic',
+        'dtype': 'bf16' if _lib.ACT_BF16 else 'fp16', 'data': 'synthetic',
         'config': {'workload': workload_name(N, args.scorer), 'N_per_gpu': N_PER_GPU, 'K': 1, 'num_steps': NUM_STEPS,
-                   'l2': 'not flushed: per-step working set (0.6 GB bf16 weights + >2 GB activations) exceeds the 126 MB L2',
-                   'sampler_state': 'fp64', 'unet': 'bf16 storage, fp32 accumulate/GroupNorm/softmax'},
+                   'commit': "reuse (the winner's own x_next; bit-identical to the reference's batch-1 recomputation, "
+                             "tests/test_search_gpu.py::test_commit_reuse_is_bit_identical; the recomputation is not executed)",
+                   'escalate': esc, 'kappa': kappa,
+                   'l2': 'not flushed: per-step working set (0.6 GB 16-bit weights + >2 GB activations) exceeds the 126 MB L2',
+                   'sampler_state': 'fp64',
+                   'unet': ('bf16' if _lib.ACT_BF16 else 'IEEE fp16') + ' storage, fp32 accumulate/GroupNorm/softmax; '
+                           'near-tie contenders re-scored in split fp16 (fp32-faithful)'},
         'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h * world,
                 'h2d_bytes_per_step_per_rank': h2d_rank, 'd2h_bytes_per_step_per_rank': d2h,
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': launches,
-        'escalation': {'mode': args.escalate, 'rows_refined_per_step': rec.escalated, 'truncated_rounds': rec.truncated},
-        'extras': {'value_with_noise_free_dedupe': N * args.steps / (ms_dd / 1e3), 'ms_per_step': ms_dd / args.steps,
-                   'noise_free_steps': noise_free,
-                   'note': 'same candidates counted; on the timesteps with noise scale 0 the N identical candidates are '
-                           'evaluated once (bit-identical results, eps_greedy_search(dedupe_noise_free=True)); not the headline'},
+        'escalation': {'rows_refined_per_step': rec.escalated, 'rounds_with_escalation': sum(1 for r in rec.escalated if r),
+                       'truncated_rounds': rec.truncated,
+                       'note': 'rows = contenders of this rank re-evaluated by the precise engine (2 more network evaluations each)'},
+        'extras': extras,
         'clocks': clk,
         'per_rank': per_rank,
         'roofline': {'bound': 'tensor', 'kernel': 'gemm_conv_kernel (tcgen05 implicit-GEMM conv3x3/1x1)',
                      'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
+                     'frac_of_burst_peak': achieved / peak_burst, 'peak_burst': peak_burst,
                      'peak_source': peak_src, 'traffic': 591.9e6,
-                     'traffic_note': 'bytes; ncu dram read+write of the largest of the GEMM launches (dec.64x64_up.conv1, '
-                                     '540 us of the NFE) vs 604e6 algorithmic (A + residual + out + weights): '
-                                     'profiles/r01_ncu_full_v3_summary.txt',
+                     'traffic_source': 'NOT re-measured by this run: ncu dram read+write of the largest GEMM launch '
+                                       '(dec.64x64_up.conv1) from the round-1 capture profiles/r01_ncu_full_v3_summary.txt, '
+                                       'vs 604e6 algorithmic bytes (A + residual + out + weights)',
                      'launches_per_nfe': n_gemm,
                      'flops_per_nfe_batch': gemm_flops, 'gemm_ms_per_nfe': gemm_ms, 'nfe_ms': nfe_ms,
                      'ms_by_kernel_kind': by_kind,
-                     'whole_step_tflops': (N_PER_GPU * 35 / 18 + 35 / 18) * FLOP_PER_NFE / (ms / args.steps / 1e3) / 1e12},
+                     'whole_step_tflops': step_flops / (ms / args.steps / 1e3) / 1e12,
+                     'whole_step_tflops_no_escalation': step_flops / (ms_ne / 1e3) / 1e12,
+                     'whole_step_note': 'reference FLOP count (219.33 GFLOP per sample-NFE) of the 35/18 x 64 candidate evaluations '
+                                        'per step; the commit recomputation is not executed (commit = reuse) and not counted; '
+                                        'the precise re-evaluations of the contenders are work on top, not counted either'},
         'cpu_baseline': cpu,
     }
     print(json.dumps(line))
@@ -329,8 +469,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', type=str, default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--quick', action='store_true', help='skip the eps04 / strong_config3 / sampler_gbs extras')
     ap.add_argument('--kappa', type=float, default=0.0, help='escalation threshold in units of the score spread (0 = API default)')
-    ap.add_argument('--escalate', type=int, default=-1, help='near-tie precision escalation: 1 on, 0 off, -1 = API default (on)')
+    ap.add_argument('--escalate', type=int, default=-1, help='near-tie precision escalation of the headline run: 1 on, 0 off, -1 = on')
     ap.add_argument('--prefetch', type=int, default=0, help='e2e: stage the next step\'s host noise on a side stream (no measurable gain)')
     ap.add_argument('--async-readback', type=int, default=1, help='e2e: per-step results into pinned buffers, asynchronously')
     ap.add_argument('--scorer', type=str, default='brightness', choices=['brightness', 'imagenet', 'compressibility'],

@@ -641,6 +641,11 @@ int b200ns_heun_mid(const double* x_hat, const float* F1, float* net_in2, double
   k.dt = dt;
   k.c_in_next = c_in_next;
   const int64_t total = R * C * HW;
+  if (C == 3 && HW % 2 == 0) {          // RGB: two pixels x three channels per thread, vector loads / stores
+    heun_mid_c3_kernel<<<grid_for(R * HW / 2, 256), 256, 0, S(stream)>>>(x_hat, F1, net_in2, x_eul, R * HW / 2, HW, k);
+    CK_LAUNCH("heun_mid_c3_kernel");
+    return 0;
+  }
   heun_mid_kernel<<<grid_for(total, 256), 256, 0, S(stream)>>>(x_hat, F1, net_in2, x_eul, total, C, HW, k);
   CK_LAUNCH("heun_mid_kernel");
   return 0;
@@ -663,6 +668,13 @@ int b200ns_heun_post(const double* x_hat, const float* F1, const float* F2, doub
   const int max_chunks = (HW + 255) / 256;
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
+  if (C == 3 && HW % 2 == 0) {
+    const int max_c3 = (HW / 2 + 255) / 256;
+    heun_post_c3_kernel<<<dim3(chunks > max_c3 ? max_c3 : chunks, static_cast<unsigned>(R)), 256, 0, S(stream)>>>(
+        x_hat, F1, F2, x_next, x0_u8, chan_sums, HW, k);
+    CK_LAUNCH("heun_post_c3_kernel");
+    return 0;
+  }
   heun_post_kernel<<<dim3(chunks, static_cast<unsigned>(R)), 256, 0, S(stream)>>>(x_hat, F1, F2, x_next, x0_u8, chan_sums,
                                                                                  C, HW, k);
   CK_LAUNCH("heun_post_kernel");

@@ -111,6 +111,103 @@ __global__ void heun_post_kernel(const double* __restrict__ x_hat, const float* 
   }
 }
 
+// ---- C == 3 fast paths (RGB images, every EDM config): one thread owns TWO adjacent pixels of all three channels, so the
+// NHWC network output is read as 24 contiguous bytes per thread (three float2; a warp reads 768 contiguous bytes -- the
+// scalar kernels above fetch every 32-byte sector of F three times, once per channel pass) and the planar fp64 state moves
+// as double2.  Arithmetic per element is identical to the scalar kernels (same rounded operations in the same order).
+DEVINL void heun_elem(double xh, float f1, float f2, bool second, const HeunCoef& k, double& xn, double& den) {
+  const double D1 = denoise(xh, f1, k.c_skip1, k.c_out1);
+  const double d_cur = __ddiv_rn(__dsub_rn(xh, D1), k.t_hat);
+  xn = __dadd_rn(xh, __dmul_rn(k.dt, d_cur));
+  den = D1;
+  if (second) {
+    den = denoise(xn, f2, k.c_skip2, k.c_out2);
+    const double d_prime = __ddiv_rn(__dsub_rn(xn, den), k.t_next);
+    const double avg = __dadd_rn(__dmul_rn(0.5, d_cur), __dmul_rn(0.5, d_prime));
+    xn = __dadd_rn(xh, __dmul_rn(k.dt, avg));
+  }
+}
+
+// total2 = R * HW / 2 pixel pairs
+__global__ void heun_mid_c3_kernel(const double* __restrict__ x_hat, const float* __restrict__ F1, float* __restrict__ net_in2,
+                                   double* __restrict__ x_eul, int64_t total2, int HW, HeunCoef k) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int half = HW >> 1;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total2; t += stride) {
+    const int64_t r = t / half;
+    const int p = static_cast<int>(t - r * half) * 2;
+    const float2* fp = reinterpret_cast<const float2*>(F1 + (r * HW + p) * 3);
+    const float2 a = __ldg(fp), b = __ldg(fp + 1), c = __ldg(fp + 2);          // (p,0) (p,1) | (p,2) (p+1,0) | (p+1,1) (p+1,2)
+    const float f[2][3] = {{a.x, a.y, b.x}, {b.y, c.x, c.y}};
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const int64_t i = (r * 3 + ch) * HW + p;
+      const double2 xh = *reinterpret_cast<const double2*>(x_hat + i);
+      double2 xe;
+      double den;
+      heun_elem(xh.x, f[0][ch], 0.f, false, k, xe.x, den);
+      heun_elem(xh.y, f[1][ch], 0.f, false, k, xe.y, den);
+      if (x_eul != nullptr) *reinterpret_cast<double2*>(x_eul + i) = xe;
+      *reinterpret_cast<float2*>(net_in2 + i) =
+          make_float2(__fmul_rn(k.c_in_next, static_cast<float>(xe.x)), __fmul_rn(k.c_in_next, static_cast<float>(xe.y)));
+    }
+  }
+}
+
+// grid (chunks, R); each CTA handles a contiguous range of pixel pairs of one candidate row
+__global__ void heun_post_c3_kernel(const double* __restrict__ x_hat, const float* __restrict__ F1, const float* __restrict__ F2,
+                                    double* __restrict__ x_next, uint8_t* __restrict__ x0_u8, uint32_t* __restrict__ chan_sums,
+                                    int HW, HeunCoef k) {
+  __shared__ uint32_t s_sum[3];
+  if (threadIdx.x < 3) s_sum[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t r = blockIdx.y;
+  const int half = HW >> 1;
+  const int per = (half + gridDim.x - 1) / gridDim.x;
+  const int q_begin = blockIdx.x * per, q_end = min(half, q_begin + per);
+  const bool second = F2 != nullptr;
+  uint32_t local[3] = {0, 0, 0};
+  for (int q = q_begin + threadIdx.x; q < q_end; q += blockDim.x) {
+    const int p = 2 * q;
+    const float2* fp = reinterpret_cast<const float2*>(F1 + (r * HW + p) * 3);
+    const float2 a = __ldg(fp), b = __ldg(fp + 1), c = __ldg(fp + 2);
+    const float f1[2][3] = {{a.x, a.y, b.x}, {b.y, c.x, c.y}};
+    float f2[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+    if (second) {
+      const float2* gp = reinterpret_cast<const float2*>(F2 + (r * HW + p) * 3);
+      const float2 a2 = __ldg(gp), b2 = __ldg(gp + 1), c2 = __ldg(gp + 2);
+      f2[0][0] = a2.x; f2[0][1] = a2.y; f2[0][2] = b2.x;
+      f2[1][0] = b2.y; f2[1][1] = c2.x; f2[1][2] = c2.y;
+    }
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const int64_t i = (r * 3 + ch) * HW + p;
+      const double2 xh = *reinterpret_cast<const double2*>(x_hat + i);
+      double2 xn;
+      double d0, d1;
+      heun_elem(xh.x, f1[0][ch], f2[0][ch], second, k, xn.x, d0);
+      heun_elem(xh.y, f1[1][ch], f2[1][ch], second, k, xn.y, d1);
+      if (x_next != nullptr) *reinterpret_cast<double2*>(x_next + i) = xn;
+      double q0 = fmin(fmax(__dadd_rn(__dmul_rn(d0, 127.5), 128.0), 0.0), 255.0);      // (x*127.5+128).clip(0,255).to(uint8)
+      double q1 = fmin(fmax(__dadd_rn(__dmul_rn(d1, 127.5), 128.0), 0.0), 255.0);
+      const uint32_t u0 = static_cast<uint32_t>(q0), u1 = static_cast<uint32_t>(q1);   // truncation; NaN -> 0
+      if (x0_u8 != nullptr) *reinterpret_cast<uchar2*>(x0_u8 + i) = make_uchar2(static_cast<uint8_t>(u0), static_cast<uint8_t>(u1));
+      local[ch] += u0 + u1;
+    }
+  }
+  if (chan_sums != nullptr) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      uint32_t v = local[ch];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&s_sum[ch], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) atomicAdd(&chan_sums[r * 4 + threadIdx.x], s_sum[threadIdx.x]);
+  }
+}
+
 __global__ void quantize_u8_kernel(const double* __restrict__ x, uint8_t* __restrict__ out, int64_t n) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {

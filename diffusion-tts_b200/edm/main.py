@@ -67,11 +67,14 @@ class SearchRecord:
     truncated: int = 0                                            # rounds whose contender list exceeded max_contenders
 
 
-# Near-tie escalation (SURVEY.md 7 hard part 1b).  A candidate is a contender when its bf16 score is within DELTA of the
-# round's best; contenders are re-scored by the fp32-faithful engine (precise.py) and the argmax is taken over the refined
-# scores.  DELTA bounds the DIFFERENCE of two candidates' bf16 score errors (the error common to all candidates of a round
-# cancels in the comparison): measured on the ADM-64 N=64 reference fixture, see DESIGN.md 2.
-ESCALATION_KAPPA = 1.25
+# Near-tie escalation (SURVEY.md 7 hard part 1b).  A candidate is a contender when its 16-bit score is within
+# delta = KAPPA x std_n(scores) of the round's best; contenders are re-scored by the fp32-faithful engine (precise.py) and
+# the argmax is taken over the refined scores.  What matters is the part of the 16-bit score error that DIFFERS between
+# candidates (the part common to all candidates of a round, 2e-5, cancels in the comparison): measured against the real
+# reference on the ADM-64 N=64 fixtures it has a standard deviation of 0.054-0.082 of the spread of the scores themselves at
+# every noise level (fp16 storage; 0.17-0.26 with bf16), i.e. the difference of two candidates' errors has sigma ~0.1 spread:
+# KAPPA = 0.35 is ~3.5 sigma (tests/test_full_parity_gpu.py dumps the tables).
+ESCALATION_KAPPA = 0.35
 MAX_CONTENDERS = 8
 
 
@@ -188,7 +191,7 @@ def _escalate(scorer, stepper: HeunStepper, x_cur, local, scores, key, idx, i, l
 
     Contenders of image j: every candidate whose score is within delta_j of the round's best, delta_j = `delta` if given,
     else kappa * std_n(scores[:, j]) (the bf16 score noise that matters -- the part that DIFFERS between candidates --
-    measures ~0.24 of the spread of the scores themselves at every noise level), but never more than the
+    measures ~0.07 of the spread of the scores themselves at every noise level), but never more than the
     `max_rows` best-scoring ones per image.  All of this is a function of the GLOBAL score table, so a sharded run refines
     exactly the rows an unsharded run refines."""
     nl = hi - lo

@@ -364,7 +364,7 @@ int launch_gemm_prec_t(const GemmOp& g, cudaStream_t st) {
   }
   gemm_prec_kernel<BN><<<dim3(g.grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st>>>(g.tmA[0], g.tmA[1], g.tmA[2], g.tmB, g.args, g.pargs);
   CK_LAUNCH("gemm_prec_kernel");
-  if (g.pargs.splits > 1) {          // add the K slices in order, then bias / residual / scale / split store
+  if (g.pargs.splits > 1 && (g.pargs.ticket == nullptr || BN == 16)) {   // (else: finished inside the kernel by the last slice)
     const int64_t items = static_cast<int64_t>(g.args.M) * ((g.args.N + 7) / 8);
     gemm_prec_finish_kernel<<<grid_for(items, 256, 148 * 8), 256, 0, st>>>(g.args, g.pargs);
     CK_LAUNCH("gemm_prec_finish_kernel");
@@ -900,6 +900,8 @@ int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d) {
     if (!d->out_fp32 && (d->N % 32 || d->out_lo_off % 8)) return fail("gemm(prec): split output needs N % 32 == 0 and out_lo_off % 8 == 0");
     if (d->residual != nullptr && (d->res_lo_off % 8 || d->ld_res % 8)) return fail("gemm(prec): residual planes must be 16-byte aligned");
     if (d->prec_splits > 1 && d->prec_partial == nullptr) return fail("gemm(prec): split-K needs prec_partial");
+    if (d->prec_ticket != nullptr && d->prec_ticket_len < ((d->batch * d->H * d->W + 127) / 128) * (d->Npad / 64))
+      return fail("gemm(prec): prec_ticket too small (need ceil(M/128) * Npad/64 counters)");
     if (d->prec_bn != 0 && (d->Npad % d->prec_bn)) return fail("gemm(prec): prec_bn must divide Npad");
     int bn = d->prec_bn;
     if (bn == 0 && !d->out_fp32 && d->Npad % 64 == 0) {
@@ -1070,6 +1072,7 @@ static int add_gemm_part(b200ns_plan* p, const b200ns_gemm_desc* d, int BN_force
     g.pargs.kb_per_split = per;
     g.pargs.partial = d->prec ? d->prec_partial : nullptr;
     g.pargs.ld_partial = a.n_tiles * BN;
+    g.pargs.ticket = (d->prec && sp > 1) ? d->prec_ticket : nullptr;
   }
   a.residual = d->prec ? nullptr : reinterpret_cast<const act_t*>(d->residual);
   a.ld_res = d->ld_res;

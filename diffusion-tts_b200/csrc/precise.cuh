@@ -72,6 +72,8 @@ struct GemmPrecArgs {
   int kb_per_split;              // K blocks (of 64) per slice
   float* partial;                // [splits][m_tiles*128][n_tiles*BN] fp32 (splits > 1)
   int ld_partial;                // n_tiles*BN
+  int* ticket;                   // [m_tiles*n_tiles] zero-initialised arrival counters (in-kernel finish), or null: the
+                                 // separate gemm_prec_finish_kernel adds the slices
 };
 
 template <int BN>
@@ -220,6 +222,7 @@ gemm_prec_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  __shared__ int s_last;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -322,6 +325,48 @@ gemm_prec_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
+      }
+      if constexpr (BN != 16) {
+        if (pa.splits > 1 && pa.ticket != nullptr) {
+          // in-kernel finish: the LAST K slice of this output tile to arrive adds all slices in slice order (which CTA is
+          // last does not matter: the summation order is fixed) and applies bias / residual / scale / split store -- no
+          // separate finishing launch
+          __threadfence();
+          named_barrier_sync(2, 128);
+          if (threadIdx.x == 64) {
+            const int t = atomicAdd(pa.ticket + mt * a.n_tiles + nt, 1);
+            s_last = (t == pa.splits - 1) ? 1 : 0;
+            if (s_last) pa.ticket[mt * a.n_tiles + nt] = 0;
+          }
+          named_barrier_sync(2, 128);
+          if (s_last) {
+            __threadfence();
+            const size_t slice = static_cast<size_t>(a.m_tiles) * 128 * pa.ld_partial;
+            if (m_ok) {
+#pragma unroll 1
+              for (int n0 = nt * BN; n0 < nt * BN + BN && n0 < a.N; n0 += 8) {
+                const float* p = pa.partial + static_cast<size_t>(m) * pa.ld_partial + n0;
+                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                for (int s0 = 0; s0 < pa.splits; s0 += 4) {          // 8 independent 16-byte L2 loads in flight
+                  float4 x0[4], x1[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const bool ok = s0 + u < pa.splits;
+                    x0[u] = ok ? __ldcg(reinterpret_cast<const float4*>(p + (s0 + u) * slice)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    x1[u] = ok ? __ldcg(reinterpret_cast<const float4*>(p + (s0 + u) * slice + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  }
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    v[0] += x0[u].x; v[1] += x0[u].y; v[2] += x0[u].z; v[3] += x0[u].w;
+                    v[4] += x1[u].x; v[5] += x1[u].y; v[6] += x1[u].z; v[7] += x1[u].w;
+                  }
+                }
+                gemm_prec_store8(a, pa, m, n0, v);
+              }
+            }
+          }
+          named_barrier_sync(2, 128);            // s_last is rewritten for the next item only after everybody read it
+        }
       }
     }
   }
@@ -486,10 +531,17 @@ __global__ void __launch_bounds__(256) gn_stats_prec_kernel(const GnPrecArgs a) 
   __threadfence();
   for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
     double ts = 0.0, tq = 0.0;
-    for (int sp = 0; sp < a.splits; ++sp) {
-      const volatile double* o = a.partial + ((static_cast<size_t>(bi) * a.splits + sp) * a.groups + g) * 2;
-      ts += o[0];
-      tq += o[1];
+    const double2* o = reinterpret_cast<const double2*>(a.partial) + static_cast<size_t>(bi) * a.splits * a.groups + g;
+    for (int sp0 = 0; sp0 < a.splits; sp0 += 8) {          // 8 independent L2 loads in flight, added in split order
+      double2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        v[u] = sp0 + u < a.splits ? __ldcg(o + static_cast<size_t>(sp0 + u) * a.groups) : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        ts += v[u].x;
+        tq += v[u].y;
+      }
     }
     const double n = static_cast<double>(HW) * a.cpg;
     const double mean = ts / n;

@@ -579,7 +579,8 @@ class Plan:
     # ---- split-fp16 "precise" ops (csrc/precise.cuh): near-tie re-scoring of a search round's contenders
     def add_gemm_prec(self, a: Sequence[torch.Tensor], segs: Sequence[Tuple[int, int, int, int]], w: torch.Tensor, N: int,
                       out: torch.Tensor, *, acc_scale: float, bias=None, residual=None, out_scale=1.0, label='gemm_prec',
-                      flops: float = 0.0, splits: int = 1, bn: int = 0, partial: Optional[torch.Tensor] = None):
+                      flops: float = 0.0, splits: int = 1, bn: int = 0, partial: Optional[torch.Tensor] = None,
+                      ticket: Optional[torch.Tensor] = None):
         """a: 1-3 split-half NHWC tensors [B,H,W,2C]; segs: (src, taps, cstart, cblocks) over the 2C physical channels, laid
         out by the caller as [hi|lo] x [Whi|Whi] + [hi] x [Wlo]; w: half [Npad, Ktot] (pre-scaled by 1/acc_scale);
         out: split half [B,H,W,2N] or fp32 [..., N]; residual: split half [B,H,W,2N]."""
@@ -619,7 +620,9 @@ class Plan:
             if partial is None or partial.dtype != torch.float32 or partial.numel() < need:
                 raise RuntimeError('gemm_prec: split-K needs an fp32 `partial` workspace of splits*Mpad*Npad elements')
             d.prec_partial = L.ptr(partial)
-        self._k(*a, w, bias, residual, out, partial)
+            if ticket is not None:               # in-kernel finish (the last K slice of a tile adds all of them)
+                d.prec_ticket, d.prec_ticket_len = L.ptr(_c(ticket, torch.int32)), ticket.numel()
+        self._k(*a, w, bias, residual, out, partial, ticket)
         L.check(L.lib().b200ns_plan_add_gemm(self._h, C.byref(d)), 'plan_add_gemm(prec)')
         self.labels.append(label)
         self.kinds.append('gemm_prec')

@@ -70,6 +70,10 @@ def split_k_policy(hw: int, n_pad: int, nkb: int, sms: int = 148) -> Tuple[int, 
     return bn, splits
 
 
+def cfg_hw(fp) -> int:
+    return fp.x_in.shape[2] * fp.x_in.shape[3]
+
+
 def _conv_block(w: torch.Tensor, c0: int = 0, c1: Optional[int] = None) -> torch.Tensor:
     """[Cout, Cin, k, k] fp32 -> [Cout, k*k, Cin[c0:c1]] (tap-major, channel-minor: the A operand's K order)."""
     w = w.detach().float().cpu()
@@ -130,9 +134,14 @@ class PreciseForwardPlan:
             if partial is None or partial.numel() < need:
                 partial = torch.empty(need, device=self.x_in.device, dtype=torch.float32)
                 self._scratch['splitk'] = partial
+        ticket = self._scratch.get('ticket')
+        if ticket is None:
+            # arrival counters of the in-kernel split-K finish: one per (M tile, 64-column slice), zeroed once
+            ticket = torch.zeros(((self.B * cfg_hw(self) + 127) // 128) * 64, device=self.x_in.device, dtype=torch.int32)
+            self._scratch['ticket'] = ticket
         self.plan.add_gemm_prec(srcs, flat, w, N, out, acc_scale=acc_scale, bias=bias, residual=residual,
                                 out_scale=out_scale, label=label, flops=2.0 * B * H * W_ * N * w.shape[1],
-                                splits=splits, bn=0, partial=partial)      # tile width: the C side's cost model
+                                splits=splits, bn=0, partial=partial, ticket=ticket)      # tile width: the C side's cost model
 
     def _build(self, eng: 'PreciseUNetEngine'):
         self._eng = eng

@@ -114,7 +114,15 @@ def sd_beam_search(eng: SDUNetEngine, table: DDIMTable, latents: torch.Tensor, c
         if noises is not None:
             nz = noises[i].to(device=dev, dtype=torch.float32).reshape(R, C, H, W).contiguous()
         else:
-            nz = torch.stack([torch.randn(N, C, H, W, device=dev) for _ in range(B)]).reshape(R, C, H, W)
+            # the reference's draws, call for call (oracle/sd_oracle.py:draw_beam_noise, pinned against the real pipeline):
+            # per beam N separate randn_like([1,C,H,W]) (:1080), then one DISCARDED draw per scored candidate -- the
+            # scoring-only second scheduler.step runs with eta = 1 and no variance_noise (:1109 -> scheduling_ddim.py:457)
+            per = []
+            for _b in range(B):
+                per.append(torch.cat([torch.randn(1, C, H, W, device=dev) for _ in range(N)]))
+                for _ in range(N):
+                    torch.randn(1, C, H, W, device=dev)
+            nz = torch.stack(per).reshape(R, C, H, W)
         cand = ops.ddim_cfg_step(eps1, beams, nz, N, guidance_scale, cf['sqrt_beta_t'], cf['sqrt_alpha_t'],
                                  cf['sqrt_alpha_prev'], cf['dir_coef'], cf['std'])
         # ---- second UNet call at the same t on this rank's slice, both CFG halves

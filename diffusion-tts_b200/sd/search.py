@@ -98,6 +98,12 @@ def sd_eps_greedy_search(eng: SDUNetEngine, table: DDIMTable, latents: torch.Ten
                         dirs.append(torch.randn_like(x))
                     if not fresh[n]:
                         u[n] = float(noise['u'][i][k][n]) if noise is not None else torch.rand(1).item()
+                if noise is None:
+                    # one DISCARDED device draw per scored candidate: the reference's scoring-only second scheduler.step runs
+                    # with eta = 1 and no variance_noise (:1412 -> scheduling_ddim.py:457-461); without it every later pivot /
+                    # direction of a free-running run would differ from the reference at the same seed
+                    for _ in range(N):
+                        torch.randn_like(x)
                 D = (noise['dirs'][i][k].to(device=dev, dtype=torch.float32).contiguous() if noise is not None
                      else torch.cat(dirs))
                 cands = ops.sd_candidates(pivot, D, torch.from_numpy(u).to(dev), lam, sqrt_e,

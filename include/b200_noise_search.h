@@ -183,6 +183,10 @@ typedef struct {
    * (256/192/128/64, 16 for Npad = 16; 0 = cost model). */
   int32_t prec_splits, prec_bn;
   float* prec_partial;
+  /* optional: int32 [prec_ticket_len >= ceil(M/128) * Npad/64] arrival counters, zero-initialised ONCE (the kernel resets
+   * them): the last K slice of an output tile to arrive adds all slices itself -- no finishing launch. */
+  int32_t* prec_ticket;
+  int32_t prec_ticket_len;
 } b200ns_gemm_desc;
 int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d);
 /* Tuning aid: force the N tile width (64/128/192/256; 0 = cost model) of subsequently added bf16 GEMMs whose padded

@@ -334,3 +334,55 @@ def image_brightness(image: torch.Tensor) -> torch.Tensor:
     u8 = (image * 127.5 + 128).clip(0, 255).to(torch.uint8)
     w = torch.tensor([0.2126, 0.7152, 0.0722]).view(1, 3, 1, 1)
     return ((u8.float() / 255.0) * w).sum(dim=1).mean(dim=(1, 2)).clamp(0, 1)
+
+
+# ---------------------------------------------------------------------------------------------- reference RNG call order
+# The search branches draw from torch's GLOBAL generators, in this order (pinned against the real pipeline by
+# oracle/make_golden_sd_search.py -> tests/golden/sd_search_tiny.pt, tests/test_sd_oracle.py):
+#   * every candidate noise is its own `torch.randn_like(latents)` call of shape [1,4,H,W] (:1080, :1375, :1377);
+#   * the scoring-only second `scheduler.step(noise_pred_tminusone, t, latents_cand, **extra_step_kwargs)` (:1109, :1412)
+#     runs with eta = 1 and NO variance_noise, so scheduling_ddim.py:457-461 draws -- and discards the effect of -- one
+#     more `randn_tensor(model_output.shape, generator=None)` per scored candidate;
+#   * eps_greedy / zero_order: `torch.rand(1).item()` decides fresh-vs-perturb (:1373) and, on the perturb branch, scales the
+#     direction (:1379) -- on the CPU generator whatever the device, i.e. on a CPU run they interleave with the randn draws.
+# A device run (CUDA) keeps the rand(1) draws on the CPU generator and the randn draws on the device generator.
+def draw_beam_noise(shape, n_steps: int, B: int, N: int, device=None):
+    """The variance noises of the beam branch in the reference's call order: per step, per beam: N candidate draws, then
+    the N discarded draws of the scoring-only steps.  Returns noises[i] = [B, N, 4, H, W]."""
+    out = []
+    for _ in range(n_steps):
+        per = []
+        for _b in range(B):
+            cands = [torch.randn(shape, device=device) for _ in range(N)]                  # :1080
+            for _ in range(N):
+                torch.randn(shape, device=device)                                          # :1109 -> scheduling_ddim.py:457
+            per.append(torch.cat(cands))
+        out.append(torch.stack(per))
+    return out
+
+
+def draw_eps_greedy_noise(shape, n_steps: int, N: int, K: int, eps: float, method: str, device=None) -> dict:
+    """pivot / r / dirs / u of the eps_greedy, zero_order and naive branches in the reference's call order (:1366-1379)
+    plus the discarded per-candidate draw of the scoring-only step (:1412)."""
+    noise = dict(pivot=[], dirs=[], r=[], u=[])
+    for _ in range(n_steps):
+        noise['pivot'].append(torch.randn(shape, device=device))                            # :1366
+        dk, rk, uk = [], [], []
+        if method in ('eps_greedy', 'zero_order'):
+            for _k in range(K):
+                dirs, rs, us = [], [], []
+                for _n in range(N):
+                    r = torch.rand(1).item()                                                # :1373 (CPU generator)
+                    rs.append(r)
+                    dirs.append(torch.randn(shape, device=device))                          # :1375 / :1377
+                    fresh = (r < eps) if method == 'eps_greedy' else 0.0
+                    us.append(0.0 if fresh else torch.rand(1).item())                       # :1379
+                for _n in range(N):
+                    torch.randn(shape, device=device)                                       # :1412 -> scheduling_ddim.py:457
+                dk.append(torch.cat(dirs))
+                rk.append(rs)
+                uk.append(us)
+        noise['dirs'].append(dk)
+        noise['r'].append(rk)
+        noise['u'].append(uk)
+    return noise

@@ -364,7 +364,7 @@ int launch_gemm_prec_t(const GemmOp& g, cudaStream_t st) {
   }
   gemm_prec_kernel<BN><<<dim3(g.grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st>>>(g.tmA[0], g.tmA[1], g.tmA[2], g.tmB, g.args, g.pargs);
   CK_LAUNCH("gemm_prec_kernel");
-  if (g.pargs.splits > 1 && (g.pargs.ticket == nullptr || BN == 16)) {   // (else: finished inside the kernel by the last slice)
+  if (g.pargs.splits > 1) {          // add the K slices in order, then bias / residual / scale / split store
     const int64_t items = static_cast<int64_t>(g.args.M) * ((g.args.N + 7) / 8);
     gemm_prec_finish_kernel<<<grid_for(items, 256, 148 * 8), 256, 0, st>>>(g.args, g.pargs);
     CK_LAUNCH("gemm_prec_finish_kernel");
@@ -805,8 +805,15 @@ int b200ns_plan_instantiate_graph(b200ns_plan* p) {
         open[l] = false;
       }
   };
+  // B200NS_LANES_SEQ=1 (experiment): the sub-batches of a laned plan run one after the other on the main stream instead
+  // of on parallel branches -- every kernel then works on 1/lanes of the batch, so a producer's output (<= 50 MB at
+  // 64x64 with 2 lanes) is still in the 126 MB L2 when its consumer starts
+  static const bool lanes_seq = [] {
+    const char* e = getenv("B200NS_LANES_SEQ");
+    return e != nullptr && e[0] == '1';
+  }();
   for (size_t i = 0; i < p->ops.size() && rc == 0; ++i) {
-    const int lane = p->ops[i].lane;
+    const int lane = lanes_seq ? 0 : p->ops[i].lane;
     if (lane <= 0 || lane >= MAX_LANES) {
       join_all();
       if (rc == 0) rc = run_op(p->ops[i], cs);
@@ -1131,7 +1138,13 @@ static int add_gemm_part(b200ns_plan* p, const b200ns_gemm_desc* d, int BN_force
   }
   // clusters of two CTAs on two M-adjacent tiles of one column slice: each fetches half of the weight tile for both
   g.cl2 = (cl2_enabled() && !d->prec && (BN == 192 || BN == 256) && a.m_tiles * a.n_tiles >= 2 * num_sms() && !d->out_fp32) ? 1 : 0;
-  {
+  if (d->prec) {        // K-block-major weights [nkb][Npad][64] (precise.cuh: gemm_prec_producer)
+    const uint64_t dims[2] = {64, static_cast<uint64_t>(nkb) * static_cast<uint64_t>(d->Npad)};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(BN)};
+    int rc = make_tmap(&g.tmB, d->w_ptr, 2, dims, box);
+    if (rc) return rc;
+    g.pargs.n_pad = d->Npad;
+  } else {
     const uint64_t dims[2] = {static_cast<uint64_t>(d->Ktot), static_cast<uint64_t>(d->Npad)};
     const uint32_t box[2] = {64, static_cast<uint32_t>(g.cl2 ? BN / 2 : BN)};
     int rc = make_tmap(&g.tmB, d->w_ptr, 2, dims, box);
@@ -1547,7 +1560,7 @@ static int fill_gn_prec(GnPrecArgs& a, const b200ns_gn_prec_desc* d) {
   a.ticket = d->ticket;
   // pixel splits: a function of the image size ONLY (batch-size / batch-position invariance of the reduction order)
   const int HW = d->H * d->W;
-  a.splits = HW / 64 < 1 ? 1 : (HW / 64 > 64 ? 64 : HW / 64);
+  a.splits = HW / 16 < 1 ? 1 : (HW / 16 > 64 ? 64 : HW / 16);      // 16..64 pixels per CTA: short per-thread load chains
   if (HW % a.splits) a.splits = 1;
   const int VC = a.C / 8;
   if (a.C > 2048) return fail("gn_prec: more than 2048 channels");

@@ -72,8 +72,9 @@ struct GemmPrecArgs {
   int kb_per_split;              // K blocks (of 64) per slice
   float* partial;                // [splits][m_tiles*128][n_tiles*BN] fp32 (splits > 1)
   int ld_partial;                // n_tiles*BN
-  int* ticket;                   // [m_tiles*n_tiles] zero-initialised arrival counters (in-kernel finish), or null: the
-                                 // separate gemm_prec_finish_kernel adds the slices
+  int n_pad;                     // padded output columns (row pitch of the K-block-major weight matrix)
+  int* ticket;                   // reserved (an in-kernel finish by the last-arriving slice was measured 2.7x SLOWER than the
+                                 // separate finishing launch: one row per thread is a serial chain of L2 round trips)
 };
 
 template <int BN>
@@ -133,7 +134,10 @@ DEVINL void gemm_prec_producer(const CUtensorMap& tmA0, const CUtensorMap& tmA1,
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           tma_load_4d(smem_a + stage * Cfg::A_BYTES, tm, &full_bar[stage], sg.cstart + cb * 64, x0 + dx, y0 + dy, n0);
-          tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * 64, nt * BN);
+          // weights are stored K-block-major ([nkb][Npad][64]): the BN x 64 tile of K block kb is ONE contiguous
+          // BN*128-byte run of HBM (row-major [Npad][Ktot] would be BN scattered 128-byte reads per tile, which is
+          // what small-M launches -- they stream every weight exactly once -- are bound by)
+          tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], 0, kb * pa.n_pad + nt * BN);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -222,7 +226,6 @@ gemm_prec_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  __shared__ int s_last;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -325,48 +328,6 @@ gemm_prec_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
-      }
-      if constexpr (BN != 16) {
-        if (pa.splits > 1 && pa.ticket != nullptr) {
-          // in-kernel finish: the LAST K slice of this output tile to arrive adds all slices in slice order (which CTA is
-          // last does not matter: the summation order is fixed) and applies bias / residual / scale / split store -- no
-          // separate finishing launch
-          __threadfence();
-          named_barrier_sync(2, 128);
-          if (threadIdx.x == 64) {
-            const int t = atomicAdd(pa.ticket + mt * a.n_tiles + nt, 1);
-            s_last = (t == pa.splits - 1) ? 1 : 0;
-            if (s_last) pa.ticket[mt * a.n_tiles + nt] = 0;
-          }
-          named_barrier_sync(2, 128);
-          if (s_last) {
-            __threadfence();
-            const size_t slice = static_cast<size_t>(a.m_tiles) * 128 * pa.ld_partial;
-            if (m_ok) {
-#pragma unroll 1
-              for (int n0 = nt * BN; n0 < nt * BN + BN && n0 < a.N; n0 += 8) {
-                const float* p = pa.partial + static_cast<size_t>(m) * pa.ld_partial + n0;
-                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                for (int s0 = 0; s0 < pa.splits; s0 += 4) {          // 8 independent 16-byte L2 loads in flight
-                  float4 x0[4], x1[4];
-#pragma unroll
-                  for (int u = 0; u < 4; ++u) {
-                    const bool ok = s0 + u < pa.splits;
-                    x0[u] = ok ? __ldcg(reinterpret_cast<const float4*>(p + (s0 + u) * slice)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    x1[u] = ok ? __ldcg(reinterpret_cast<const float4*>(p + (s0 + u) * slice + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                  }
-#pragma unroll
-                  for (int u = 0; u < 4; ++u) {
-                    v[0] += x0[u].x; v[1] += x0[u].y; v[2] += x0[u].z; v[3] += x0[u].w;
-                    v[4] += x1[u].x; v[5] += x1[u].y; v[6] += x1[u].z; v[7] += x1[u].w;
-                  }
-                }
-                gemm_prec_store8(a, pa, m, n0, v);
-              }
-            }
-          }
-          named_barrier_sync(2, 128);            // s_last is rewritten for the next item only after everybody read it
-        }
       }
     }
   }

@@ -598,7 +598,9 @@ class Plan:
             d.seg[i] = L.KSeg(src, taps, cstart, cblocks)
         d.batch, d.H, d.W = B, H, W_
         _c(w, torch.float16)
-        d.w_ptr, d.N, d.Npad, d.Ktot = L.ptr(w), N, w.shape[0], w.shape[1]
+        if w.dim() != 3 or w.shape[2] != 64:
+            raise RuntimeError('gemm_prec: w must be K-block-major [Ktot/64, Npad, 64] (precise.pack_split)')
+        d.w_ptr, d.N, d.Npad, d.Ktot = L.ptr(w), N, w.shape[1], w.shape[0] * 64
         d.bias = L.ptr(bias)
         d.out_scale = float(out_scale)
         d.out = L.ptr(out)
@@ -616,7 +618,7 @@ class Plan:
         d.prec_splits, d.prec_bn = int(splits), int(bn)
         if splits > 1:
             # fp32 partial tiles of the K slices: [splits, ceil(M/128)*128, Npad]
-            need = splits * ((B * H * W_ + 127) // 128) * 128 * w.shape[0]
+            need = splits * ((B * H * W_ + 127) // 128) * 128 * w.shape[1]
             if partial is None or partial.dtype != torch.float32 or partial.numel() < need:
                 raise RuntimeError('gemm_prec: split-K needs an fp32 `partial` workspace of splits*Mpad*Npad elements')
             d.prec_partial = L.ptr(partial)

@@ -33,7 +33,7 @@ def split_half(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 def pack_split(blocks: Sequence[torch.Tensor], n_pad: Optional[int] = None):
     """blocks: fp32 [N, taps, C_i] weight blocks that share one accumulator (K-concatenated).
-    Returns (half [Npad, Ktot], acc_scale, segs) with, per block, K = [taps x (hi_c | hi_c)] ++ [taps x lo_c] -- the B
+    Returns (half [Ktot/64, Npad, 64] (K-block-major), acc_scale, segs) with, per block, K = [taps x (hi_c | hi_c)] ++ [taps x lo_c] -- the B
     operand of `[hi|lo] x [Whi|Whi] + [hi] x [Wlo]` -- weights pre-multiplied by a power of two so that |W| <= 1024
     (Wlo stays a normal half for all but the smallest weights); segs = per block ((taps, 2C/64), (taps, C/64))."""
     N = blocks[0].shape[0]
@@ -55,7 +55,9 @@ def pack_split(blocks: Sequence[torch.Tensor], n_pad: Optional[int] = None):
     w = torch.cat(parts, dim=1)
     if n_pad is not None and n_pad > N:
         w = torch.cat([w, torch.zeros(n_pad - N, w.shape[1], dtype=w.dtype)], dim=0)
-    return w.contiguous(), 1.0 / scale, segs
+    # K-block-major [Ktot/64, Npad, 64]: the weight tile of one K block is one contiguous run of HBM
+    w = w.reshape(w.shape[0], w.shape[1] // 64, 64).permute(1, 0, 2).contiguous()
+    return w, 1.0 / scale, segs
 
 
 def split_k_policy(hw: int, n_pad: int, nkb: int, sms: int = 148) -> Tuple[int, int]:
@@ -68,10 +70,6 @@ def split_k_policy(hw: int, n_pad: int, nkb: int, sms: int = 148) -> Tuple[int, 
     tiles = max(1, hw // 128) * (n_pad // bn)
     splits = max(1, min(-(-sms // tiles), nkb // 8, 32))
     return bn, splits
-
-
-def cfg_hw(fp) -> int:
-    return fp.x_in.shape[2] * fp.x_in.shape[3]
 
 
 def _conv_block(w: torch.Tensor, c0: int = 0, c1: Optional[int] = None) -> torch.Tensor:
@@ -126,22 +124,17 @@ class PreciseForwardPlan:
             flat.append((i, sa[0], 0, sa[1]))
             flat.append((i, sb[0], 0, sb[1]))
         B, H, W_, _ = srcs[0].shape
-        bn, splits = split_k_policy(H * W_, w.shape[0], w.shape[1] // 64)
+        bn, splits = split_k_policy(H * W_, w.shape[1], w.shape[0])
         partial = None
         if splits > 1:
-            need = splits * ((B * H * W_ + 127) // 128) * 128 * w.shape[0]
+            need = splits * ((B * H * W_ + 127) // 128) * 128 * w.shape[1]
             partial = self._scratch.get('splitk')
             if partial is None or partial.numel() < need:
                 partial = torch.empty(need, device=self.x_in.device, dtype=torch.float32)
                 self._scratch['splitk'] = partial
-        ticket = self._scratch.get('ticket')
-        if ticket is None:
-            # arrival counters of the in-kernel split-K finish: one per (M tile, 64-column slice), zeroed once
-            ticket = torch.zeros(((self.B * cfg_hw(self) + 127) // 128) * 64, device=self.x_in.device, dtype=torch.int32)
-            self._scratch['ticket'] = ticket
         self.plan.add_gemm_prec(srcs, flat, w, N, out, acc_scale=acc_scale, bias=bias, residual=residual,
-                                out_scale=out_scale, label=label, flops=2.0 * B * H * W_ * N * w.shape[1],
-                                splits=splits, bn=0, partial=partial, ticket=ticket)      # tile width: the C side's cost model
+                                out_scale=out_scale, label=label, flops=2.0 * B * H * W_ * N * w.shape[0] * 64,
+                                splits=splits, bn=0, partial=partial)      # tile width: the C side's cost model
 
     def _build(self, eng: 'PreciseUNetEngine'):
         self._eng = eng

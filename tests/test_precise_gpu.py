@@ -63,10 +63,10 @@ def test_gemm_prec_conv_matches_fp64(pkg, B, H, cin, cout, taps):
     P = ops.Plan()
     P.add_gemm_prec([xs], flat, wp.cuda(), cout, out, acc_scale=acc_scale, bias=bias.cuda(), residual=rs, out_scale=0.75)
     # the same GEMM with the layer's split-K policy (K slices on different SMs, partial tiles added in order)
-    bn, splits = precise.split_k_policy(H * H, wp.shape[0], wp.shape[1] // 64)
+    bn, splits = precise.split_k_policy(H * H, wp.shape[1], wp.shape[0])
     splits = max(splits, 3)
     out_sk = torch.empty_like(out)
-    ws_ = torch.empty(splits * ((B * H * H + 127) // 128) * 128 * wp.shape[0], dtype=torch.float32, device='cuda')
+    ws_ = torch.empty(splits * ((B * H * H + 127) // 128) * 128 * wp.shape[1], dtype=torch.float32, device='cuda')
     P.add_gemm_prec([xs], flat, wp.cuda(), cout, out_sk, acc_scale=acc_scale, bias=bias.cuda(), residual=rs, out_scale=0.75,
                     splits=splits, bn=bn, partial=ws_)
     P.run()

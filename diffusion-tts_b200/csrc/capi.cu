@@ -66,13 +66,13 @@ int pdl_mode() {          // 0 off (default), 1 every plan kernel, 2 only the la
 }
 bool pdl_enabled() { return pdl_mode() == 1; }
 // 2-CTA clusters for the GEMM (B200NS_CL2=1): see gemm_conv.cuh (multicast weight tiles)
-bool cl2_enabled() {
+int cl2_enabled() {         // 0 off, 1 = multicast weight tiles (B200NS_CL2=1), 2 = CTA-pair MMA, cta_group::2 (B200NS_CL2=2)
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("B200NS_CL2");
-    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    v = (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
   }
-  return v == 1;
+  return v;
 }
 template <typename... KArgs, typename... Args>
 cudaError_t launch_cluster2(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
@@ -315,6 +315,19 @@ int num_sms() {
 }
 
 template <int BN>
+int launch_gemm_cg2(const GemmOp& g, cudaStream_t st) {          // CTA pair, tcgen05 cta_group::2 (M = 256)
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(gemm_conv_kernel<BN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  CK(launch_cluster2(gemm_conv_kernel<BN, true, true>, dim3(g.grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, g.tmA[0], g.tmA[1],
+                     g.tmA[2], g.tmB, g.tmO, g.tmR, g.args));
+  CK_LAUNCH("gemm_conv_kernel<cg2>");
+  return 0;
+}
+template <int BN>
 int launch_gemm_cl2(const GemmOp& g, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
@@ -331,6 +344,7 @@ template <int BN>
 int launch_gemm_t(const GemmOp& g, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   if constexpr (BN == 192 || BN == 256) {
+    if (g.cl2 == 2) return launch_gemm_cg2<BN>(g, st);
     if (g.cl2) return launch_gemm_cl2<BN>(g, st);
   }
   static bool attr_set = false;
@@ -1137,7 +1151,8 @@ static int add_gemm_part(b200ns_plan* p, const b200ns_gemm_desc* d, int BN_force
     a.src_stride[i] = sdn;
   }
   // clusters of two CTAs on two M-adjacent tiles of one column slice: each fetches half of the weight tile for both
-  g.cl2 = (cl2_enabled() && !d->prec && (BN == 192 || BN == 256) && a.m_tiles * a.n_tiles >= 2 * num_sms() && !d->out_fp32) ? 1 : 0;
+  g.cl2 = (cl2_enabled() && !d->prec && (BN == 192 || BN == 256) && a.m_tiles * a.n_tiles >= 2 * num_sms() && !d->out_fp32)
+              ? cl2_enabled() : 0;
   if (d->prec) {        // K-block-major weights [nkb][Npad][64] (precise.cuh: gemm_prec_producer)
     const uint64_t dims[2] = {64, static_cast<uint64_t>(nkb) * static_cast<uint64_t>(d->Npad)};
     const uint32_t box[2] = {64, static_cast<uint32_t>(BN)};

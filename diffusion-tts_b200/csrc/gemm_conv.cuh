@@ -113,7 +113,7 @@ DEVINL bool gemm_tile_at(const GemmArgs& a, int it, int& mt, int& nt) {
 }
 
 // ===================== TMA producer (one thread) =====================
-template <int BN, bool CL2 = false>
+template <int BN, bool CL2 = false, bool CG2 = false>
 DEVINL void gemm_producer(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmA2, const CUtensorMap& tmB,
                           const GemmArgs& a, uint8_t* smem_a, uint8_t* smem_b, uint64_t* full_bar, uint64_t* empty_bar) {
   using Cfg = GemmCfg<BN>;
@@ -143,6 +143,19 @@ DEVINL void gemm_producer(const CUtensorMap& tmA0, const CUtensorMap& tmA1, cons
         const int dx = sg.taps == 9 ? tap % 3 - 1 : (sg.taps == 4 ? sg.dx0 + (tap & 1) : 0);
         for (int cb = 0; cb < sg.cblocks; ++cb, ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if constexpr (CG2) {
+            // CTA pair: my 128 rows of A and MY HALF of the weight tile go into my own shared memory; the bytes are
+            // counted on the LEADER's full barrier, which therefore completes when both CTAs' operands have landed
+            const uint32_t full0 = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            mbar_arrive_expect_tx_cluster(full0, Cfg::A_BYTES + Cfg::B_BYTES / 2);
+            tma_load_4d_cg2(smem_a + stage * Cfg::A_BYTES, tm, full0, sg.cstart + cb * 64, x0 * sdn + dx, y0 * sdn + dy, n0);
+            tma_load_2d_cg2(smem_b + stage * Cfg::B_BYTES, &tmB, full0, kb * 64, nt * BN + rank * (BN / 2));
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           tma_load_4d(smem_a + stage * Cfg::A_BYTES, tm, &full_bar[stage], sg.cstart + cb * 64, x0 * sdn + dx, y0 * sdn + dy, n0);
           if constexpr (CL2) {            // tmB's box is BN/2 rows: my half of the weight tile, for both CTAs of the pair
@@ -162,12 +175,12 @@ DEVINL void gemm_producer(const CUtensorMap& tmA0, const CUtensorMap& tmA1, cons
 }
 
 // ===================== MMA issuer (one thread) =====================
-template <int BN, bool CL2 = false>
+template <int BN, bool CL2 = false, bool CG2 = false>
 DEVINL void gemm_mma(const GemmArgs& a, uint8_t* smem_a, uint8_t* smem_b, uint64_t* full_bar, uint64_t* empty_bar,
                      uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t tmem_base) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
-  const uint32_t idesc = a.fp16 ? umma_idesc_f16(128, BN) : umma_idesc_act(128, BN);
+  const uint32_t idesc = CG2 ? umma_idesc_act(256, BN) : (a.fp16 ? umma_idesc_f16(128, BN) : umma_idesc_act(128, BN));
   int stage = 0;
   uint32_t phase = 0;
   int acc = 0;
@@ -185,9 +198,14 @@ DEVINL void gemm_mma(const GemmArgs& a, uint8_t* smem_a, uint8_t* smem_b, uint64
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in the (addr>>4) field
-        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+        if constexpr (CG2)
+          umma_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);     // M = 256: my rows + the peer's, B = both halves
+        else
+          umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
       }
-      if constexpr (CL2)
+      if constexpr (CG2)
+        umma_commit_cg2_mc(&empty_bar[stage], 3);  // both CTAs' stages are free once the pair's MMAs have read them
+      else if constexpr (CL2)
         umma_commit_mc(&empty_bar[stage], 3);      // the peer writes half of this stage too: release it in both CTAs
       else
         umma_commit(&empty_bar[stage]);
@@ -196,7 +214,10 @@ DEVINL void gemm_mma(const GemmArgs& a, uint8_t* smem_a, uint8_t* smem_b, uint64
         phase ^= 1;
       }
     }
-    umma_commit(&tfull_bar[acc]);
+    if constexpr (CG2)
+      umma_commit_cg2_mc(&tfull_bar[acc], 3);      // each CTA's epilogue reads its own 128 accumulator rows
+    else
+      umma_commit(&tfull_bar[acc]);
     if (++acc == 2) {
       acc = 0;
       acc_phase ^= 1;
@@ -207,7 +228,9 @@ DEVINL void gemm_mma(const GemmArgs& a, uint8_t* smem_a, uint8_t* smem_b, uint64
 // ---------------------------------------------------------------------------------------------------------
 // Main kernel: BN in {64,128,192,256}, bf16 output through the TMA slot ring.
 // ---------------------------------------------------------------------------------------------------------
-template <int BN, bool CL2 = false>
+// CG2 (with CL2 scheduling): tcgen05 cta_group::2 -- the pair's leader issues M = 256 MMAs over both CTAs' A rows and the
+// two halves of the weight tile, one half in each CTA's shared memory (half the B staging and operand traffic per SM).
+template <int BN, bool CL2 = false, bool CG2 = false>
 __global__ void __launch_bounds__(320, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
@@ -243,19 +266,24 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     prefetch_tmap(&tmO);
     if (has_res) prefetch_tmap(&tmR);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CL2 ? 2 : 1);      // CL2: released by both CTAs' MMA warps (multicast commit)
+      mbar_init(&full_bar[s], CG2 ? 2 : 1);       // CG2: both CTAs' producers arrive (with their byte counts) on the leader's
+      mbar_init(&empty_bar[s], (CL2 && !CG2) ? 2 : 1);      // CL2: released by both CTAs' MMA warps (multicast commit)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);
+      mbar_init(&tempty_bar[i], CG2 ? 16 : 8);    // CG2: the leader's MMA waits for both CTAs' epilogue warps
     }
     for (int s = 0; s < SLOTS; ++s) mbar_init(&rfull_bar[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CG2) {
+      tmem_alloc_cg2(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -265,9 +293,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   pdl_wait();                   // everything above overlapped the previous kernel's tail (PDL)
 
   if (warp == 0) {
-    if (lane == 0) gemm_producer<BN, CL2>(tmA0, tmA1, tmA2, tmB, a, smem_a, smem_b, full_bar, empty_bar);
+    if (lane == 0) gemm_producer<BN, CL2, CG2>(tmA0, tmA1, tmA2, tmB, a, smem_a, smem_b, full_bar, empty_bar);
   } else if (warp == 1) {
-    if (lane == 0) gemm_mma<BN, CL2>(a, smem_a, smem_b, full_bar, empty_bar, tfull_bar, tempty_bar, tmem_base);
+    if (lane == 0 && (!CG2 || cluster_ctarank() == 0))      // CG2: only the pair's leader issues MMAs
+      gemm_mma<BN, CL2, CG2>(a, smem_a, smem_b, full_bar, empty_bar, tfull_bar, tempty_bar, tmem_base);
   } else {
     // ===================== epilogue (warps 2..9, 256 threads) =====================
     const int et = threadIdx.x - 64;        // 0..255
@@ -280,6 +309,17 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
     const uint32_t rsw = static_cast<uint32_t>(row & 7);
 
+    // accumulator buffer `ac` fully read: tell the MMA issuer (CG2: the pair's leader, possibly in the other CTA)
+    auto arrive_tempty = [&](int ac) {
+      if constexpr (CG2) {
+        if (cluster_ctarank() == 0)
+          mbar_arrive(&tempty_bar[ac]);
+        else
+          mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[ac]), 0));
+      } else {
+        mbar_arrive(&tempty_bar[ac]);
+      }
+    };
     // sub-box kk of this CTA's tile sequence -> global coordinates; issues the residual TMA load
     auto issue_res = [&](uint32_t kk) {
       int mt, nt;
@@ -321,7 +361,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             if (jj == NSUB / 2 - 1) {
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+              if (lane == 0) arrive_tempty(acc);
             }
             const uint32_t bh = bias0 + static_cast<uint32_t>(acc * BN + (2 * jj) * 64 + half * 32) * 4u;
             const uint32_t bg = bh + 64u * 4u;
@@ -396,7 +436,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         if (j == NSUB - 1) {                // accumulator fully read: hand it back to the MMA warp early
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (lane == 0) arrive_tempty(acc);
         } else {                            // next sub-box's accumulator columns stream in behind this one's maths
           tmem_ld32(t_row + (j + 1) * 64 + half * 32, r);
         }
@@ -503,7 +543,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if constexpr (CL2) cluster_sync_all();        // nobody leaves while the peer may still multicast / arrive into this CTA
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (CG2)
+      tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS);
+    else
+      tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 

@@ -66,11 +66,15 @@ int pdl_mode() {          // 0 off (default), 1 every plan kernel, 2 only the la
 }
 bool pdl_enabled() { return pdl_mode() == 1; }
 // 2-CTA clusters for the GEMM (B200NS_CL2=1): see gemm_conv.cuh (multicast weight tiles)
-int cl2_enabled() {         // 0 off, 1 = multicast weight tiles (B200NS_CL2=1), 2 = CTA-pair MMA, cta_group::2 (B200NS_CL2=2)
+// Launch mode of the large (>= 2 waves) BN = 192 / 256 GEMMs: 2 (default) = CTA pairs with tcgen05 cta_group::2 (M = 256 MMAs; each
+// SM stages and reads half of the weight tile), 1 = 2-CTA clusters that multicast the weight tile, 0 = single CTAs.  All three
+// give bit-identical outputs (tools/check_cg2.py); measured per ADM-64 forward at batch 64: 12.55 / 12.47 / 12.33 ms of GEMM time
+// for modes 0 / 1 / 2 (profiles/r02_gemm_launch_modes.txt) -- the step is power-capped, so halving the B operand traffic buys 2 %.
+int cl2_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("B200NS_CL2");
-    v = (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
+    v = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
   }
   return v;
 }

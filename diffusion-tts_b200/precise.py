@@ -66,9 +66,10 @@ def split_k_policy(hw: int, n_pad: int, nkb: int, sms: int = 148) -> Tuple[int, 
     batch -- so a sample's bits do not depend on how many contenders share its launch."""
     if n_pad % 64:
         return 0, 1                               # the 3-channel output conv (Npad = 16): cost model, no split
-    bn = 128 if n_pad % 128 == 0 else 64
+    bn = 192 if n_pad % 192 == 0 else (128 if n_pad % 128 == 0 else 64)
     tiles = max(1, hw // 128) * (n_pad // bn)
-    splits = max(1, min(-(-sms // tiles), nkb // 8, 32))
+    # every SM pulls its own stream of weights from HBM (~40 GB/s per SM): one sample must already occupy all of them
+    splits = max(1, min(-(-sms // tiles), nkb // 4, 64))
     return bn, splits
 
 
@@ -134,7 +135,7 @@ class PreciseForwardPlan:
                 self._scratch['splitk'] = partial
         self.plan.add_gemm_prec(srcs, flat, w, N, out, acc_scale=acc_scale, bias=bias, residual=residual,
                                 out_scale=out_scale, label=label, flops=2.0 * B * H * W_ * N * w.shape[0] * 64,
-                                splits=splits, bn=0, partial=partial)      # tile width: the C side's cost model
+                                splits=splits, bn=bn, partial=partial)
 
     def _build(self, eng: 'PreciseUNetEngine'):
         self._eng = eng

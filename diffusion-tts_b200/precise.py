@@ -66,11 +66,12 @@ def split_k_policy(hw: int, n_pad: int, nkb: int, sms: int = 148) -> Tuple[int, 
     batch -- so a sample's bits do not depend on how many contenders share its launch."""
     if n_pad % 64:
         return 0, 1                               # the 3-channel output conv (Npad = 16): cost model, no split
-    bn = 192 if n_pad % 192 == 0 else (128 if n_pad % 128 == 0 else 64)
+    # (measured: forcing 192-wide tiles with up to 64 slices -- every SM busy at batch 1 -- was 10-20 % SLOWER than this
+    # policy with the C side's cost model choosing the width: more partial-tile traffic and finishing work)
+    bn = 128 if n_pad % 128 == 0 else 64
     tiles = max(1, hw // 128) * (n_pad // bn)
-    # every SM pulls its own stream of weights from HBM (~40 GB/s per SM): one sample must already occupy all of them
-    splits = max(1, min(-(-sms // tiles), nkb // 4, 64))
-    return bn, splits
+    splits = max(1, min(-(-sms // tiles), nkb // 8, 32))
+    return 0, splits
 
 
 def _conv_block(w: torch.Tensor, c0: int = 0, c1: Optional[int] = None) -> torch.Tensor:

@@ -13,7 +13,8 @@ The reference drives the SD backend as
   * `out.images` is the decoded image when a VAE is given, else a visualisation of the first three latent channels;
     `out.latents` is the search result itself.
 `method` = beam (sd/beam.py), eps_greedy / zero_order / naive (sd/search.py; 'rejection' is the naive loop, repeated by
-main.py like the reference's main.py:131); mcts raises NotImplementedError (8 f4).
+main.py like the reference's main.py:131), mcts (sd/search.py:sd_mcts_as_shipped -- the reference branch as shipped never
+back-propagates a reward, so its observable behaviour is a DDIM step with the step's first noise draw).
 """
 from __future__ import annotations
 
@@ -25,7 +26,7 @@ import torch
 
 from ..sd_unet import SDUNetEngine
 from .beam import DDIMTable, sd_beam_search
-from .search import sd_eps_greedy_search
+from .search import sd_eps_greedy_search, sd_mcts_as_shipped
 
 
 def pseudo_prompt_embeddings(prompt: str, negative_prompt: str = '', tokens: int = 77, dim: int = 768) -> torch.Tensor:
@@ -59,9 +60,7 @@ class B200LatentBeamPipeline:
                  method: str = 'beam', params: Optional[dict] = None, guidance_scale: float = 7.5,
                  negative_prompt: str = '', latents: Optional[torch.Tensor] = None, height: int = 512, width: int = 512,
                  generator: Optional[torch.Generator] = None):
-        if method == 'mcts':
-            raise NotImplementedError("SD method 'mcts' is not on the B200 hot path (SURVEY.md 8 f4)")
-        if method not in ('beam', 'eps_greedy', 'zero_order', 'naive', 'rejection'):
+        if method not in ('beam', 'eps_greedy', 'zero_order', 'naive', 'rejection', 'mcts'):
             raise ValueError(f"Unknown method: {method}")
         params = params or {}
         if height != width or height % 64:
@@ -84,6 +83,10 @@ class B200LatentBeamPipeline:
             B, N = int(params['B']), int(params['N'])                      # pipeline_stable_diffusion.py:1046,1080
             best, rec = sd_beam_search(self.unet, table, latents, ctx, B, N, **kw)
             score = float(rec.final_score)
+        elif method == 'mcts':   # as shipped: no reward ever reaches the tree (see sd_mcts_as_shipped); same RNG consumption
+            kw.pop('shard')
+            best, rec = sd_mcts_as_shipped(self.unet, table, latents, ctx, int(params['N']), int(params['S']), **kw)
+            score = float(rec.max_score)
         else:   # eps_greedy / zero_order, and the plain eta=1 DDIM loop every other method name falls through to (:1330-1437)
             m = method if method in ('eps_greedy', 'zero_order') else 'naive'
             best, rec = sd_eps_greedy_search(self.unet, table, latents, ctx, int(params.get('N', 1)), int(params.get('K', 1)),

@@ -142,3 +142,51 @@ def sd_eps_greedy_search(eng: SDUNetEngine, table: DDIMTable, latents: torch.Ten
             last_best_score = torch.as_tensor(scorer(decode(x))).to(device=dev, dtype=torch.float32).reshape(-1)
     rec.max_score = last_best_score.reshape(())
     return x, rec
+
+
+@torch.no_grad()
+def sd_mcts_as_shipped(eng: SDUNetEngine, table: DDIMTable, latents: torch.Tensor, ctx_pair: Optional[torch.Tensor], N: int,
+                       S: int, *, guidance_scale: float = 7.5, decode: Optional[Callable] = None,
+                       scorer: Optional[Callable] = None, record: bool = False):
+    """`method="mcts"` of the SD backend, AS SHIPPED (pipeline_stable_diffusion.py:1172-1333).  The reference's tree never
+    receives a reward: no rollout is scored, `visits` / `total_reward` are never updated, so the selection walk stays at the
+    root, the first min(N, S) iterations each add one child (a DDIM step with a fresh `randn_like`), every iteration runs a
+    discarded rollout, and `max(children, key = -inf)` returns the FIRST child.  The observable behaviour -- pinned against the
+    real pipeline by tests/test_sd_oracle.py::test_mcts_as_shipped_matches_the_real_pipeline -- is a DDIM step with the step's
+    first noise draw, plus the RNG consumption of the discarded work, reproduced here draw for draw (one child draw per
+    expansion, one per rollout step: scheduler.step with eta = 1 and no variance_noise, scheduling_ddim.py:457).  The UNet
+    evaluations whose results the reference throws away are not executed: S * (T - i + 2) network calls per step become 1."""
+    if (decode is None) != (scorer is None):
+        raise ValueError('decode and scorer go together: give both (generic path) or neither (fused latent brightness)')
+    dev = eng.device
+    if ctx_pair is not None:
+        eng.set_context(ctx_pair)
+    x = latents.to(device=dev, dtype=torch.float32).contiguous()
+    C, H, W = x.shape[1:]
+    fp1 = eng.plan(2, H)
+    rec = SDSearchRecord()
+    T = len(table.timesteps)
+    for i, t in enumerate(table.timesteps):
+        first = None
+        for s in range(S):
+            if s < N:                                                    # expansion: one child per iteration (:1216-1251)
+                noise = torch.randn_like(x)
+                first = noise if first is None else first
+            for _ in range(i, T):                                        # the discarded rollout's draws (:1276-1300)
+                torch.randn_like(x)
+        if first is not None:                                            # "best" child = the first one (:1305-1308)
+            cf = table.coeffs(t)
+            fp1.x_in[:1].copy_(x)
+            fp1.x_in[1:].copy_(x)
+            eps1 = eng.run(fp1, t)
+            x = ops.ddim_cfg_step(eps1, x, first, 1, guidance_scale, cf['sqrt_beta_t'], cf['sqrt_alpha_t'], cf['sqrt_alpha_prev'],
+                                  cf['dir_coef'], cf['std'])
+        if record:
+            rec.x.append(x)
+    if scorer is None:                                                   # max_score is None -> the final result is scored (:1466)
+        zero = torch.zeros(2, H, W, C, device=dev, dtype=torch.float32)
+        score = ops.ddim_x0_score(zero, x, 0.0, 0.0, 1.0)[0]
+    else:
+        score = torch.as_tensor(scorer(decode(x))).to(device=dev, dtype=torch.float32).reshape(-1)
+    rec.max_score = score.reshape(())
+    return x, rec

@@ -58,7 +58,10 @@ class Rec:
         import importlib.util
         img = images[0]                                                         # uint8 [1,3,h,w] (pipeline...:1115)
         w = torch.tensor([0.2126, 0.7152, 0.0722]).view(1, 3, 1, 1)
-        s = ((img.float() / 255.0) * w).sum(dim=1).mean(dim=(1, 2)).clamp(0, 1)       # sd/scorers.py:43-64, RGB branch
+        if img.shape[1] == 3:
+            s = ((img.float() / 255.0) * w).sum(dim=1).mean(dim=(1, 2)).clamp(0, 1)   # sd/scorers.py:43-64, RGB branch
+        else:                           # output_type='latent': the final 4-channel latents are "the image" (:1463, :66-67)
+            s = (img.float() / 255.0).mean(dim=(1, 2, 3))
         self.scores.append(float(s))
         return s
 
@@ -79,7 +82,8 @@ def main():
     pipe = build_pipe()
     cases = [run(pipe, 'beam', {'B': 2, 'N': 3, 'K': 1, 'lambda': 0.15, 'eps': 0.4, 'S': 8}, 5),
              run(pipe, 'eps_greedy', {'B': 2, 'N': 4, 'K': 2, 'lambda': 0.15, 'eps': 0.4, 'S': 8}, 6),
-             run(pipe, 'zero_order', {'B': 2, 'N': 3, 'K': 1, 'lambda': 0.15, 'eps': 0.4, 'S': 8}, 7)]
+             run(pipe, 'zero_order', {'B': 2, 'N': 3, 'K': 1, 'lambda': 0.15, 'eps': 0.4, 'S': 8}, 7),
+             run(pipe, 'mcts', {'B': 2, 'N': 2, 'K': 1, 'lambda': 0.15, 'eps': 0.4, 'S': 3}, 8)]
     path = os.path.join(GOLD, 'sd_search_tiny.pt')
     torch.save(dict(steps=STEPS, H=H, unet_seed=UNET_SEED, vae_seed=VAE_SEED, input_seed=INPUT_SEED, guidance=7.5,
                     scaling_factor=float(pipe.vae.config.scaling_factor), cases=cases), path)

@@ -386,3 +386,35 @@ def draw_eps_greedy_noise(shape, n_steps: int, N: int, K: int, eps: float, metho
         noise['r'].append(rk)
         noise['u'].append(uk)
     return noise
+
+
+def mcts_as_shipped(unet: Callable, tab: DDIMTable, latents: torch.Tensor, ctx_pair: torch.Tensor, N: int, S: int,
+                    guidance: float = 7.5, score_fn: Callable = latent_brightness, device=None):
+    """The `mcts` branch AS SHIPPED (pipeline_stable_diffusion.py:1172-1333).  Nothing in it ever scores a rollout or
+    increments `visits` / `total_reward`, hence: the selection walk never leaves the root (:1211: a child with visits == 0
+    stops it), the first N of the S iterations expand one child each with a fresh `randn_like` (:1243), every iteration runs
+    a rollout to the last timestep whose result is discarded, and `max(children, key = -inf for all)` (:1306) returns the
+    FIRST child.  The observable behaviour is therefore: x <- DDIM step with the step's first noise draw -- plus the RNG
+    consumption of the discarded work (one child draw per expansion, one `randn_tensor` per rollout step: the rollout calls
+    scheduler.step with eta = 1 and no variance_noise, :1288 -> scheduling_ddim.py:457).  This restatement skips the UNet
+    evaluations whose outputs are unused and reproduces the draws; oracle/make_golden_sd_search.py pins it (final latents,
+    max_score) against the real pipeline.  Returns (latents, max_score)."""
+    def guided(x, t):
+        xin = torch.cat([x, x])
+        ctx = torch.cat([ctx_pair[0:1].expand(x.shape[0], -1, -1), ctx_pair[1:2].expand(x.shape[0], -1, -1)])
+        eu, et = unet(xin, t, ctx).chunk(2)
+        return eu + guidance * (et - eu)
+
+    x = latents.clone()
+    T = len(tab.timesteps)
+    for i, t in enumerate(tab.timesteps):
+        first = None
+        for s in range(S):
+            if s < N:                                                              # expansion (:1216-1251)
+                noise = torch.randn(x.shape, device=device)
+                first = noise if first is None else first
+            for _ in range(i, T):                                                  # rollout (:1276-1300): discarded draws
+                torch.randn(x.shape, device=device)
+        if first is not None:                                                      # :1305-1308
+            x, _ = ddim_step(tab, guided(x, t), t, x, variance_noise=first)
+    return x, float(score_fn(x))                                                   # :1466-1471

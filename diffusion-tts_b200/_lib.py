@@ -33,7 +33,7 @@ class GemmDesc(C.Structure):
                 ('out', c_vp), ('ld_out', c_i32), ('out_fp32', c_i32), ('gn_stats', c_vp), ('reverse', c_i32), ('a_stride', c_i32 * 3), ('geglu', c_i32), ('upsample2x', c_i32),
                 ('prec', c_i32), ('acc_scale', c_f32), ('out_lo_off', c_i32), ('res_lo_off', c_i32),
                 ('prec_splits', c_i32), ('prec_bn', c_i32), ('prec_partial', c_vp), ('prec_ticket', c_vp),
-                ('prec_ticket_len', c_i32)]
+                ('prec_ticket_len', c_i32), ('act', c_i32)]
 
 
 class GnStatsDesc(C.Structure):
@@ -55,6 +55,12 @@ class GnPrecDesc(C.Structure):
                 ('ld_pre_add', c_i32), ('film_scale', c_vp), ('film_shift', c_vp), ('ld_film', c_i32), ('b_emb', c_i32),
                 ('silu', c_i32), ('resample', c_i32), ('out', c_vp), ('raw_out', c_vp), ('mean_rstd', c_vp), ('partial', c_vp),
                 ('ticket', c_vp)]
+
+
+class ClipPreprocessDesc(C.Structure):
+    _fields_ = [('img', c_vp), ('tmp', c_vp), ('patches', c_vp), ('h_bounds', c_vp), ('h_coeffs', c_vp), ('v_bounds', c_vp),
+                ('v_coeffs', c_vp), ('lut', c_vp), ('batch', c_i32), ('H', c_i32), ('W', c_i32), ('S', c_i32), ('P', c_i32),
+                ('Lp', c_i32), ('Kp', c_i32), ('hks', c_i32), ('vks', c_i32)]
 
 
 class AttnPrecDesc(C.Structure):
@@ -127,6 +133,9 @@ SIGNATURES = {
     'b200ns_plan_add_pool_attention': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32]),
     'b200ns_plan_add_softmax_gather': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32]),
     'b200ns_plan_add_layernorm': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_f32]),
+    'b200ns_plan_add_clip_preprocess': (C.c_int, [c_vp, c_vp]),
+    'b200ns_plan_add_clip_pool_ln': (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i32, c_i32, c_f32]),
+    'b200ns_plan_add_clip_cosine': (C.c_int, [c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_i32]),
     'b200ns_plan_add_geglu': (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i32]),
     'b200ns_plan_add_upsample2x': (C.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32]),
     'b200ns_ddim_cfg_step': (C.c_int, [c_vp] * 6 + [c_i64, c_i32, c_i32, c_i32] + [c_f32] * 6 + [c_vp]),

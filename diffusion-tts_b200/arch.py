@@ -295,3 +295,38 @@ def ddpmpp_param_shapes(img_resolution=32, in_channels=3, out_channels=3, label_
             shp[f'dec.{res}x{res}_aux_conv.weight'] = (out_channels, c, 3, 3)
             shp[f'dec.{res}x{res}_aux_conv.bias'] = (out_channels,)
     return shp
+
+
+def clip_param_shapes(hidden=1024, layers=24, intermediate=4096, image_size=224, patch=14, proj=768, t_hidden=768, t_layers=12,
+                      t_intermediate=3072, vocab=49408, max_pos=77, vision_only=False) -> Dict[str, Tuple[int, ...]]:
+    """Parameter inventory of transformers' `CLIPModel` (the reference's CLIPScorer loads openai/clip-vit-large-patch14,
+    sd/scorers.py:150-163; the defaults are that checkpoint's sizes).  `vision_only`: the half the per-candidate path uses.
+    tests/test_clip_oracle.py pins the names against the oracle's table, which oracle/make_golden_clip.py checks against
+    transformers itself."""
+    shp: Dict[str, Tuple[int, ...]] = {}
+
+    def tower(prefix, h, inter, n):
+        for i in range(n):
+            p = f'{prefix}.encoder.layers.{i}'
+            for nm in ('q_proj', 'k_proj', 'v_proj', 'out_proj'):
+                shp[f'{p}.self_attn.{nm}.weight'], shp[f'{p}.self_attn.{nm}.bias'] = (h, h), (h,)
+            for nm in ('layer_norm1', 'layer_norm2'):
+                shp[f'{p}.{nm}.weight'] = shp[f'{p}.{nm}.bias'] = (h,)
+            shp[f'{p}.mlp.fc1.weight'], shp[f'{p}.mlp.fc1.bias'] = (inter, h), (inter,)
+            shp[f'{p}.mlp.fc2.weight'], shp[f'{p}.mlp.fc2.bias'] = (h, inter), (h,)
+
+    shp['vision_model.embeddings.class_embedding'] = (hidden,)
+    shp['vision_model.embeddings.patch_embedding.weight'] = (hidden, 3, patch, patch)
+    shp['vision_model.embeddings.position_embedding.weight'] = ((image_size // patch) ** 2 + 1, hidden)
+    shp['vision_model.pre_layrnorm.weight'] = shp['vision_model.pre_layrnorm.bias'] = (hidden,)      # sic: transformers' spelling
+    tower('vision_model', hidden, intermediate, layers)
+    shp['vision_model.post_layernorm.weight'] = shp['vision_model.post_layernorm.bias'] = (hidden,)
+    shp['visual_projection.weight'] = (proj, hidden)
+    if not vision_only:
+        shp['logit_scale'] = ()
+        shp['text_model.embeddings.token_embedding.weight'] = (vocab, t_hidden)
+        shp['text_model.embeddings.position_embedding.weight'] = (max_pos, t_hidden)
+        tower('text_model', t_hidden, t_intermediate, t_layers)
+        shp['text_model.final_layer_norm.weight'] = shp['text_model.final_layer_norm.bias'] = (t_hidden,)
+        shp['text_projection.weight'] = (proj, t_hidden)
+    return shp

@@ -13,6 +13,7 @@
 #include "../../include/b200_noise_search.h"
 #include "attention.cuh"
 #include "classifier.cuh"
+#include "clip.cuh"
 #include "gemm_conv.cuh"
 #include "groupnorm.cuh"
 #include "jpeg.cuh"
@@ -225,7 +226,8 @@ int make_tmap_2d_ld(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t ro
 // ------------------------------------------------------------------ plan ops
 enum OpKind { OP_GEMM, OP_GN_STATS, OP_GN_APPLY, OP_GN_FINALIZE, OP_ATTN, OP_LINEAR, OP_IM2COL, OP_U8F32, OP_POOL_TOKENS, OP_POOL_ATTN,
               OP_SOFTMAX_GATHER, OP_LAYERNORM, OP_GEGLU, OP_UPSAMPLE2X, OP_SOFTMAX_ROWS,
-              OP_GN_STATS_PREC, OP_GN_APPLY_PREC, OP_ATTN_PREC, OP_IM2COL_PREC };
+              OP_GN_STATS_PREC, OP_GN_APPLY_PREC, OP_ATTN_PREC, OP_IM2COL_PREC,
+              OP_CLIP_PREPROCESS, OP_CLIP_POOL_LN, OP_CLIP_COSINE };
 
 struct GemmOp {
   CUtensorMap tmA[3], tmB, tmO, tmR;
@@ -302,6 +304,7 @@ struct Op {
     Im2colOp i2c;
     GnPrecOp gnp;
     AttnPrecOp attnp;
+    ClipPreArgs clip;
   };
   int lane;     // 0 = main stream; k > 0: parallel branch k of the captured graph (see b200ns_plan_set_lane)
   Op() { memset(this, 0, sizeof(*this)); }
@@ -597,6 +600,27 @@ int run_op(const Op& op, cudaStream_t st) {
                                                                              reinterpret_cast<act_t*>(op.misc.p2),
                                                                              op.misc.i0, op.misc.f0);
       CK_LAUNCH("softmax_rows_kernel");
+      return 0;
+    case OP_CLIP_PREPROCESS: {
+      const ClipPreArgs& c = op.clip;
+      clip_resize_h_kernel<<<grid_for(static_cast<int64_t>(c.batch) * 3 * c.H * c.S, 256, 148 * 16), 256, 0, st>>>(c);
+      CK_LAUNCH("clip_resize_h_kernel");
+      clip_patches_kernel<<<grid_for(static_cast<int64_t>(c.batch) * c.G * c.G * c.Kp, 256, 148 * 16), 256, 0, st>>>(c);
+      CK_LAUNCH("clip_patches_kernel");
+      return 0;
+    }
+    case OP_CLIP_POOL_LN:
+      clip_pool_ln_kernel<<<op.misc.i0, 256, 0, st>>>(reinterpret_cast<const act_t*>(op.misc.p0), op.misc.n,
+                                                      reinterpret_cast<const float*>(op.misc.p1),
+                                                      reinterpret_cast<const float*>(op.misc.p3),
+                                                      reinterpret_cast<float*>(op.misc.p2), op.misc.i1, op.misc.f0);
+      CK_LAUNCH("clip_pool_ln_kernel");
+      return 0;
+    case OP_CLIP_COSINE:
+      clip_cosine_kernel<<<(op.misc.i0 + 3) / 4, 128, 0, st>>>(reinterpret_cast<const float*>(op.misc.p0),
+                                                               reinterpret_cast<const float*>(op.misc.p1), op.misc.i2,
+                                                               reinterpret_cast<float*>(op.misc.p2), op.misc.i0, op.misc.i1);
+      CK_LAUNCH("clip_cosine_kernel");
       return 0;
     case OP_UPSAMPLE2X:
       launch_pdl(upsample2x_kernel, dim3(grid_for(static_cast<int64_t>(op.misc.i0) * op.misc.i1 * op.misc.i2 * 4 * (op.misc.n / 8), 256, 148 * 32)),
@@ -1109,6 +1133,8 @@ static int add_gemm_part(b200ns_plan* p, const b200ns_gemm_desc* d, int BN_force
   a.ld_stats = ld_stats;
   a.reverse = d->reverse;
   a.geglu = d->geglu;
+  a.act = d->act;
+  if (d->act != 0 && (d->act != 1 || d->geglu || d->upsample2x || d->prec)) return fail("gemm: act must be 0 or 1 (quick_gelu), without geglu / upsample2x / prec");
   if (d->gn_stats != nullptr && (BN == 16 || a.M % 64)) return fail("gemm: gn_stats needs bf16 output, N tiles >= 64 and M % 64 == 0");
   if (!d->out_fp32 && (d->ld_out % 8)) return fail("gemm: ld_out must be a multiple of 8 for bf16 output");
   if (d->residual != nullptr && (d->ld_res % 8)) return fail("gemm: ld_res must be a multiple of 8");
@@ -1641,6 +1667,68 @@ int b200ns_plan_add_im2col_prec(b200ns_plan* p, const b200ns_im2col_desc* d) {
   op.kind = OP_IM2COL_PREC;
   op.i2c.d = *d;
   op.i2c.grid = grid_for(static_cast<int64_t>(d->batch) * d->H * d->W * 64, 256, 148 * 8);
+  p->push(op);
+  return 0;
+}
+
+int b200ns_plan_add_clip_preprocess(b200ns_plan* p, const b200ns_clip_preprocess_desc* d) {
+  if (d->batch <= 0 || d->S <= 0 || d->P <= 0 || d->S % d->P) return fail("clip_preprocess: crop size must be a multiple of the patch size");
+  const int G = d->S / d->P;
+  if (d->Kp < 3 * d->P * d->P || d->Kp % 8 || d->Lp < G * G + 1) return fail("clip_preprocess: Kp >= 3*P*P (multiple of 8) and Lp >= G*G + 1 required");
+  if (d->hks <= 0 || d->vks <= 0 || d->H <= 0 || d->W <= 0) return fail("clip_preprocess: bad sizes");
+  Op op;
+  op.kind = OP_CLIP_PREPROCESS;
+  ClipPreArgs& c = op.clip;
+  c.img = d->img;
+  c.tmp = d->tmp;
+  c.patches = reinterpret_cast<act_t*>(d->patches);
+  c.hb = d->h_bounds;
+  c.hk = d->h_coeffs;
+  c.vb = d->v_bounds;
+  c.vk = d->v_coeffs;
+  c.lut = d->lut;
+  c.batch = d->batch;
+  c.H = d->H;
+  c.W = d->W;
+  c.S = d->S;
+  c.P = d->P;
+  c.G = G;
+  c.Lp = d->Lp;
+  c.Kp = d->Kp;
+  c.hks = d->hks;
+  c.vks = d->vks;
+  p->push(op);
+  return 0;
+}
+
+int b200ns_plan_add_clip_pool_ln(b200ns_plan* p, const void* x, int64_t row_stride, const float* gamma, const float* beta,
+                                 float* out, int32_t batch, int32_t C, float eps) {
+  if (batch <= 0 || C <= 0) return fail("clip_pool_ln: bad sizes");
+  Op op;
+  op.kind = OP_CLIP_POOL_LN;
+  op.misc.p0 = x;
+  op.misc.p1 = gamma;
+  op.misc.p3 = const_cast<float*>(beta);
+  op.misc.p2 = out;
+  op.misc.n = row_stride;
+  op.misc.i0 = batch;
+  op.misc.i1 = C;
+  op.misc.f0 = eps;
+  p->push(op);
+  return 0;
+}
+
+int b200ns_plan_add_clip_cosine(b200ns_plan* p, const float* image_embeds, const float* text_embeds, int32_t text_rows,
+                                float* score, int32_t batch, int32_t D) {
+  if (batch <= 0 || D <= 0 || (text_rows != 1 && text_rows != batch)) return fail("clip_cosine: text_rows must be 1 or batch");
+  Op op;
+  op.kind = OP_CLIP_COSINE;
+  op.misc.p0 = image_embeds;
+  op.misc.p1 = text_embeds;
+  op.misc.p2 = score;
+  op.misc.i0 = batch;
+  op.misc.i1 = D;
+  op.misc.i2 = text_rows;
   p->push(op);
   return 0;
 }

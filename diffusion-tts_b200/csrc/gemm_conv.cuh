@@ -67,6 +67,7 @@ struct GemmArgs {
                                  //    hidden * gelu(gate) (exact erf GELU) as bf16 [M, N/2]: GEGLU (activations.py:117-123)
                                  //    fused into the projection, whose [M, N] output never touches HBM
   int fp16;                      // 1: operands are IEEE half (the split-fp16 "precise" path, precise.cuh) instead of bf16
+  int act;                       // 1: quick_gelu(acc + bias) = x * sigmoid(1.702 x) before the residual / out_scale (CLIP MLP)
 };
 
 template <int BN>
@@ -440,6 +441,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         } else {                            // next sub-box's accumulator columns stream in behind this one's maths
           tmem_ld32(t_row + (j + 1) * 64 + half * 32, r);
         }
+        if (a.act == 1) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __fdividef(v[i], 1.f + __expf(-1.702f * v[i]));
+        }
         if (has_res) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -632,6 +637,7 @@ gemm_small_n_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           if (n < a.N) {
             float v = __uint_as_float(r[j]);
             if (a.bias != nullptr) v += __ldg(a.bias + n);
+            if (a.act == 1) v = __fdividef(v, 1.f + __expf(-1.702f * v));
             if (has_res) v += act2f(a.residual[static_cast<size_t>(m) * a.ld_res + n]);
             v *= a.out_scale;
             if (a.out_fp32)

@@ -369,7 +369,7 @@ class Plan:
 
     def add_gemm(self, a: Sequence[torch.Tensor], segs: Sequence[Tuple[int, int, int, int]], w: torch.Tensor, N: int,
                  out: torch.Tensor, *, bias=None, residual=None, out_scale=1.0, gn_stats=None, reverse=False, a_stride=None,
-                 label='gemm', alg_k=None, geglu=False, upsample2x=False):
+                 label='gemm', alg_k=None, geglu=False, upsample2x=False, act=0):
         """a: 1-3 NHWC bf16 tensors [B,H,W,C]; segs: (src, taps, cstart, cblocks); w: bf16 [Npad,Ktot].
         gn_stats: optional fp32 [M/64, N, 2] receiving per-channel (sum, sumsq) of the stored output.
         geglu: w / bias rows in groups of [64 hidden | 64 gate] (`interleave_geglu`); out is [.., N/2] = hidden * gelu(gate).
@@ -412,6 +412,7 @@ class Plan:
         d.gn_stats = L.ptr(gn_stats)
         d.reverse = int(reverse)
         d.geglu = int(bool(geglu))
+        d.act = int(act)                                       # 1: quick_gelu(acc + bias) in the epilogue (CLIP MLP)
         if geglu and out.shape[-1] * 2 != N:
             raise RuntimeError('gemm(geglu): out must have N/2 columns')
         self._k(*a, w, bias, residual, out, gn_stats)
@@ -493,7 +494,8 @@ class Plan:
 
     def add_attention(self, qk: torch.Tensor, k_col0: int, vt: Optional[torch.Tensor], out: torch.Tensor, batch: int,
                       heads: int, Lseq: int, label='attention', v_col0: int = 0, head_dim: int = 64, reverse=False,
-                      scale: float = 0.0, kv: Optional[torch.Tensor] = None, kv_rows: int = 0, kv_len: int = 0, kv_div: int = 1):
+                      scale: float = 0.0, kv: Optional[torch.Tensor] = None, kv_rows: int = 0, kv_len: int = 0, kv_div: int = 1,
+                      kv_ld: int = 0):
         """qk: [batch*L, ld] with Q at col head*64, K at k_col0 + head*64; V either transposed in `vt`
         ([batch*heads*64, L]) or (vt=None) row-major in `qk` at v_col0 + head*64."""
         d = L.AttnDesc()
@@ -504,7 +506,12 @@ class Plan:
         d.reverse = int(reverse)
         d.scale = float(scale)
         if kv is not None:         # cross-attention: K/V of the (few) contexts, [kv_batch * kv_rows, ld_kv]
-            d.kv, d.ld_kv = L.ptr(_c(kv, ACT_DTYPE)), kv.shape[-1]
+            if kv_ld:              # a column window [K | V] of a wider row-major matrix (e.g. of a fused QKV projection)
+                if kv.dtype != ACT_DTYPE or kv.stride(-1) != 1 or kv.stride(0) != kv_ld:
+                    raise RuntimeError('attention: kv window must be a column slice of a contiguous activation matrix')
+                d.kv, d.ld_kv = L.ptr(kv), kv_ld
+            else:
+                d.kv, d.ld_kv = L.ptr(_c(kv, ACT_DTYPE)), kv.shape[-1]
             d.kv_batch, d.kv_rows, d.kv_len, d.kv_div = kv.numel() // (kv.shape[-1] * kv_rows), kv_rows, kv_len, kv_div
             self._keep.append(kv)
         d.out, d.ld_out = L.ptr(_c(out, ACT_DTYPE)), out.shape[-1]
@@ -698,6 +705,42 @@ class Plan:
         self.labels.append(label)
         self.kinds.append(kind)
         self.flops.append(0.0)
+
+    def add_clip_preprocess(self, img: torch.Tensor, tmp: torch.Tensor, patches: torch.Tensor, hb, hk, vb, vk, lut, S: int, P: int,
+                            Lp: int, label='clip_preprocess'):
+        """uint8 [B,3,H,W] -> the patch-embedding GEMM's A matrix (activation type) [B*Lp, Kp]: Pillow's bicubic resize + centre
+        crop + rescale/normalise of CLIPImageProcessor, bit-exact (csrc/clip.cuh).  hb/vb int32 [S,2], hk/vk int32 [S,ks]."""
+        d = L.ClipPreprocessDesc()
+        B, _, H, W_ = img.shape
+        d.img, d.tmp, d.patches = L.ptr(_c(img, torch.uint8)), L.ptr(_c(tmp, torch.uint8)), L.ptr(_c(patches, ACT_DTYPE))
+        if tmp.numel() < B * 3 * H * S or patches.shape[0] != B * Lp or img.shape[1] != 3:
+            raise RuntimeError('clip_preprocess: tmp must hold [B,3,H,S] bytes and patches must be [B*Lp, Kp]')
+        for t in (hb, hk, vb, vk):
+            _c(t, torch.int32)
+        if tuple(hb.shape) != (S, 2) or tuple(vb.shape) != (S, 2) or hk.shape[0] != S or vk.shape[0] != S:
+            raise RuntimeError('clip_preprocess: bounds must be [S,2] and coefficients [S,ks]')
+        d.h_bounds, d.h_coeffs, d.v_bounds, d.v_coeffs = L.ptr(hb), L.ptr(hk), L.ptr(vb), L.ptr(vk)
+        d.lut = L.ptr(_c(lut, torch.float32))
+        d.batch, d.H, d.W, d.S, d.P, d.Lp, d.Kp, d.hks, d.vks = B, H, W_, S, P, Lp, patches.shape[1], hk.shape[1], vk.shape[1]
+        self._k(img, tmp, patches, hb, hk, vb, vk, lut)
+        L.check(L.lib().b200ns_plan_add_clip_preprocess(self._h, C.byref(d)), 'plan_add_clip_preprocess')
+        self._misc('clip_preprocess', label)
+
+    def add_clip_pool_ln(self, x: torch.Tensor, row_stride: int, gamma, beta, out: torch.Tensor, batch: int, eps: float = 1e-5,
+                         label='clip_pool_ln'):
+        self._k(x, gamma, beta, out)
+        L.check(L.lib().b200ns_plan_add_clip_pool_ln(self._h, L.ptr(_c(x, ACT_DTYPE)), row_stride, L.ptr(_c(gamma, torch.float32)),
+                                                     L.ptr(_c(beta, torch.float32)), L.ptr(_c(out, torch.float32)), batch,
+                                                     out.shape[-1], float(eps)), 'plan_add_clip_pool_ln')
+        self._misc('clip_pool_ln', label)
+
+    def add_clip_cosine(self, image_embeds: torch.Tensor, text_embeds: torch.Tensor, score: torch.Tensor, label='clip_cosine'):
+        self._k(image_embeds, text_embeds, score)
+        B, D = image_embeds.shape
+        L.check(L.lib().b200ns_plan_add_clip_cosine(self._h, L.ptr(_c(image_embeds, torch.float32)),
+                                                    L.ptr(_c(text_embeds, torch.float32)), text_embeds.shape[0],
+                                                    L.ptr(_c(score, torch.float32)), B, D), 'plan_add_clip_cosine')
+        self._misc('clip_cosine', label)
 
     def add_u8_to_f32(self, src: torch.Tensor, dst: torch.Tensor, label='u8_to_f32'):
         self._k(src, dst)

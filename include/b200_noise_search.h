@@ -188,6 +188,9 @@ typedef struct {
    * them): the last K slice of an output tile to arrive adds all slices itself -- no finishing launch. */
   int32_t* prec_ticket;
   int32_t prec_ticket_len;
+  /* epilogue activation applied to (acc + bias) before the residual / out_scale: 0 none, 1 quick_gelu x * sigmoid(1.702 x)
+   * (CLIP's MLP, transformers activations.py QuickGELUActivation; 16-bit engine only) */
+  int32_t act;
 } b200ns_gemm_desc;
 int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d);
 /* Tuning aid: force the N tile width (64/128/192/256; 0 = cost model) of subsequently added bf16 GEMMs whose padded
@@ -349,6 +352,36 @@ int b200ns_debug_prec_nolo(int on);
 
 /* 3x3 im2col of the fp32 NCHW network input (Cin*9 <= 64) into split half [batch*H*W, 128] = [64 hi taps | 64 lo taps]. */
 int b200ns_plan_add_im2col_prec(b200ns_plan* p, const b200ns_im2col_desc* d);
+
+/* ------------------------------------------------------------------ CLIP scorer glue
+ * CLIPScorer (reference sd/scorers.py:149-213): `self.processor(images=...)` -> `self.clip.get_image_features` -> cosine
+ * similarity with the prompt embedding.  The ViT tower runs on the plan ops above (GEMM with act = 1 for quick_gelu,
+ * LayerNorm, attention with kv_len masking of the padded tokens); these are the remaining pieces. */
+/* CLIPImageProcessor (PIL path) in integer arithmetic, bit-exact: Pillow's two-pass 8-bit bicubic resize (coefficients
+ * scaled by 2^22, computed by the host: bounds int32 [S,2] = (first input index, taps), coeffs int32 [S, ks], already
+ * restricted to the S centre-cropped output columns / rows), rescale + normalise through lut fp32 [3,256], written as the
+ * patch matrix of the patch-embedding GEMM: patches (activation type) [batch*Lp, Kp], row b*Lp + 1 + py*(S/P) + px,
+ * column c*P*P + i*P + j, columns >= 3*P*P zero.  Row b*Lp (class token) and rows > (S/P)^2 are NOT written (keep them 0).
+ * tmp: uint8 [batch,3,H,S] workspace. */
+typedef struct {
+  const uint8_t* img;        /* [batch,3,H,W] */
+  uint8_t* tmp;
+  void* patches;
+  const int32_t* h_bounds;
+  const int32_t* h_coeffs;
+  const int32_t* v_bounds;
+  const int32_t* v_coeffs;
+  const float* lut;
+  int32_t batch, H, W, S, P, Lp, Kp, hks, vks;
+} b200ns_clip_preprocess_desc;
+int b200ns_plan_add_clip_preprocess(b200ns_plan* p, const b200ns_clip_preprocess_desc* d);
+/* pooled = post_layernorm(last_hidden_state[:, 0]) (modeling_clip.py CLIPVisionTransformer): x activation rows
+ * b*row_stride (elements), C channels -> out fp32 [batch, C], LayerNorm in fp32. */
+int b200ns_plan_add_clip_pool_ln(b200ns_plan* p, const void* x, int64_t row_stride, const float* gamma, const float* beta,
+                                 float* out, int32_t batch, int32_t C, float eps);
+/* score[b] = sum_d (image_embeds[b,d]/|image_embeds[b]|) * (text_embeds[b or 0,d]/|text_embeds[..]|)   sd/scorers.py:178-213 */
+int b200ns_plan_add_clip_cosine(b200ns_plan* p, const float* image_embeds, const float* text_embeds, int32_t text_rows,
+                                float* score, int32_t batch, int32_t D);
 
 /* ------------------------------------------------------------------ classifier scorer glue
  * ImageNetScorer (edm/scorers.py:143-174) around EncoderUNetModel (edm/unet.py:701-912): the torso runs

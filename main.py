@@ -14,8 +14,11 @@ Differences from the reference CLI, all forced by the offline B200 setting:
     `--network` names a state-dict `.pt`), latent-space scoring of the Tweedie x0, pseudo prompt embeddings (the CLIP
     text encoder and the VAE are unreachable offline; SURVEY.md 8 f1).  `--steps` (new) overrides the 50 DDIM steps;
     `--vae PATH|random` (new) decodes every candidate's x0 to a 512x512 image on the B200 VAE engine before scoring.
-  * `--scorer clip` (a second network family) and `--backend sd --method mcts` are not part of the B200 hot path and raise
-    NotImplementedError; `--backend edm --method mcts` runs (batched expansions / rollouts).
+  * `--scorer clip` (sd): the ViT tower + Pillow-exact preprocessing run on the B200 engine (diffusion_tts_b200/clip.py);
+    `--clip PATH|random` (new) is a transformers CLIPModel state dict (random-init ViT-L/14 otherwise -- the reference downloads
+    openai/clip-vit-large-patch14), `--clip-text PATH` (new) a precomputed prompt embedding [1, 768]; without it (no tokenizer
+    vocabulary offline) a deterministic pseudo embedding of the prompt string stands in.  Needs decoded images: implies `--vae`.
+  * `--method mcts`: edm runs batched expansions / rollouts; sd runs the reference branch as shipped.
 """
 import argparse
 
@@ -41,6 +44,27 @@ def get_scorer(backend, scorer_name, device='cuda', classifier=None):
     raise ValueError(f"Unknown or invalid scorer '{scorer_name}' for backend '{backend}'")
 
 
+def get_clip_scorer(args):
+    """CLIPScorer (reference main.py:66-67, sd/scorers.py:149-213) on the B200 engine."""
+    import hashlib
+    from diffusion_tts_b200.arch import clip_param_shapes, random_state_dict
+    from diffusion_tts_b200.clip import CLIPScorer
+    if args.clip not in (None, 'random'):
+        sd = torch.load(args.clip, map_location='cpu')
+    else:
+        print('[clip scorer] no --clip checkpoint given: using a random-init CLIP ViT-L/14 vision tower (303.5M parameters)')
+        sd = random_state_dict(clip_param_shapes(vision_only=True), 33)
+    scorer = CLIPScorer(sd, dtype=torch.float32, device=args.device)
+    if args.clip_text is not None:
+        emb = torch.load(args.clip_text, map_location='cpu')
+    else:
+        print('[clip scorer] no --clip-text embedding given: using a pseudo embedding of the prompt string')
+        seed = int.from_bytes(hashlib.sha256(args.prompt.encode()).digest()[:8], 'little') % (2 ** 63)
+        emb = torch.randn(1, scorer.engine.cfg['proj'], generator=torch.Generator().manual_seed(seed))
+    scorer.set_text_embeds(args.prompt, emb)
+    return scorer
+
+
 def random_init_ddpmpp(seed=4321):
     """CIFAR-10 32x32 DDPM++ (SongUNet) bundle, random init (BASELINE.json configs[0]; reference preset edm/train.py:118-122)."""
     from diffusion_tts_b200.arch import ddpmpp_param_shapes, random_state_dict
@@ -59,8 +83,10 @@ def main_sd(args):
     from diffusion_tts_b200.arch import random_state_dict, sd_unet_param_shapes
     from diffusion_tts_b200.sd.pipeline import B200LatentBeamPipeline
     if args.scorer == 'clip':
-        raise NotImplementedError('the CLIP scorer is not on the B200 hot path (SURVEY.md 8 f4)')
-    scorer = get_scorer('sd', args.scorer, args.device)
+        scorer = get_clip_scorer(args)
+        args.vae = args.vae or 'random'            # CLIP scores decoded RGB images
+    else:
+        scorer = get_scorer('sd', args.scorer, args.device)
     if args.network is not None:
         sd = torch.load(args.network, map_location='cpu')
     else:
@@ -113,6 +139,9 @@ def main():
     parser.add_argument('--steps', type=int, default=None, help='Override the number of sampler steps (sd: 50)')
     parser.add_argument('--vae', type=str, default=None,
                         help="sd: AutoencoderKL state-dict .pt (or 'random'): decode each candidate before scoring")
+    parser.add_argument('--clip', type=str, default=None, help="sd, --scorer clip: CLIPModel state-dict .pt (or 'random')")
+    parser.add_argument('--clip-text', dest='clip_text', type=str, default=None,
+                        help='sd, --scorer clip: precomputed prompt embedding .pt [1, proj]')
     args = parser.parse_args()
 
     if args.backend == 'sd' and args.scorer == 'imagenet':

@@ -152,11 +152,16 @@ def clip_preprocess(images: torch.Tensor, size: int = 224) -> torch.Tensor:
         a = pil_bicubic_resize_u8(a, nh, nw)
         top, left = (nh - size) // 2, (nw - size) // 2
         a = a[top:top + size, left:left + size]
-        x = torch.from_numpy(a.copy()).permute(2, 0, 1).to(torch.float32) * (1.0 / 255.0)
-        mean = torch.tensor(CLIP_MEAN).view(3, 1, 1)
-        std = torch.tensor(CLIP_STD).view(3, 1, 1)
-        out.append((x - mean) / std)
+        out.append(torch.from_numpy(normalise_lut()[np.arange(3)[:, None, None], a.transpose(2, 0, 1)]))
     return torch.stack(out)
+
+
+def normalise_lut() -> np.ndarray:
+    """fp32 [3, 256]: the processor's rescale + normalise of every possible uint8 value, in ITS arithmetic
+    (image_transforms.py rescale: float32(float64(v) * (1/255)); normalize: (x - mean) / std in float32)."""
+    v = (np.arange(256, dtype=np.float64) * 0.00392156862745098).astype(np.float32)
+    mean, std = np.array(CLIP_MEAN, dtype=np.float32), np.array(CLIP_STD, dtype=np.float32)
+    return ((v[None, :] - mean[:, None]) / std[:, None]).astype(np.float32)
 
 
 # ---------------------------------------------------------------------------------------------- towers

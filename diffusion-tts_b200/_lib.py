@@ -94,6 +94,7 @@ SIGNATURES = {
     'b200ns_device_ok': (C.c_int, [C.c_int]),
     'b200ns_act_is_fp16': (C.c_int, []),
     'b200ns_heun_pre': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f64, c_f32, c_vp]),
+    'b200ns_heun_pre_f32noise': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f64, c_f32, c_vp]),
     'b200ns_heun_mid': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_f32, c_f32, c_f64, c_f64, c_f32, c_vp]),
     'b200ns_heun_post': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_f32, c_f32, c_f64, c_f64,
                                    c_f32, c_f32, c_f64, c_vp]),

@@ -669,8 +669,17 @@ int b200ns_heun_pre(const double* x_cur, const double* eps, double* x_hat, float
                     int64_t E, double s, float c_in, void* stream) {
   if (E % 2) return fail("heun_pre: E must be even");
   const int64_t total = R * E;
-  heun_pre_kernel<<<grid_for(total / 2, 256), 256, 0, S(stream)>>>(x_cur, eps, x_hat, net_in, total, b * E, s, c_in);
+  heun_pre_kernel<double><<<grid_for(total / 2, 256), 256, 0, S(stream)>>>(x_cur, eps, x_hat, net_in, total, b * E, s, c_in);
   CK_LAUNCH("heun_pre_kernel");
+  return 0;
+}
+
+int b200ns_heun_pre_f32noise(const double* x_cur, const float* eps, double* x_hat, float* net_in, int64_t R, int64_t b,
+                             int64_t E, double s, float c_in, void* stream) {
+  if (E % 2) return fail("heun_pre: E must be even");
+  const int64_t total = R * E;
+  heun_pre_kernel<float><<<grid_for(total / 2, 256), 256, 0, S(stream)>>>(x_cur, eps, x_hat, net_in, total, b * E, s, c_in);
+  CK_LAUNCH("heun_pre_kernel<float>");
   return 0;
 }
 

@@ -13,16 +13,27 @@
 namespace b200 {
 
 // x_hat = x_cur + s*eps ; net_in = c_in * fp32(x_hat)        (edm/main.py:85; networks.py:655,665)
-__global__ void heun_pre_kernel(const double* __restrict__ x_cur, const double* __restrict__ eps,
+// NoiseT = double: eps is fp64 like x_cur (randn_like(x_cur), :750-800) and s*eps is an fp64 product.
+// NoiseT = float : eps is an fp32 tensor (the MCTS depth noises, :445, or an fp32 precomputed_noise): torch multiplies the
+//                  0-dim fp64 scale into it IN fp32 (the scalar is rounded to fp32 first) and only the sum is fp64.
+template <typename NoiseT>
+__global__ void heun_pre_kernel(const double* __restrict__ x_cur, const NoiseT* __restrict__ eps,
                                 double* __restrict__ x_hat, float* __restrict__ net_in, int64_t total,
                                 int64_t bE, double s, float c_in) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 2;
+  const float s32 = static_cast<float>(s);
   for (int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 2; i < total; i += stride) {
-    const double2 e = *reinterpret_cast<const double2*>(eps + i);
     const double2 x = *reinterpret_cast<const double2*>(x_cur + (i % bE));
     double2 h;
-    h.x = __dadd_rn(x.x, __dmul_rn(s, e.x));
-    h.y = __dadd_rn(x.y, __dmul_rn(s, e.y));
+    if constexpr (sizeof(NoiseT) == 4) {
+      const float2 e = *reinterpret_cast<const float2*>(eps + i);
+      h.x = __dadd_rn(x.x, static_cast<double>(__fmul_rn(s32, e.x)));
+      h.y = __dadd_rn(x.y, static_cast<double>(__fmul_rn(s32, e.y)));
+    } else {
+      const double2 e = *reinterpret_cast<const double2*>(eps + i);
+      h.x = __dadd_rn(x.x, __dmul_rn(s, e.x));
+      h.y = __dadd_rn(x.y, __dmul_rn(s, e.y));
+    }
     *reinterpret_cast<double2*>(x_hat + i) = h;
     float2 o;
     o.x = __fmul_rn(c_in, static_cast<float>(h.x));

@@ -579,7 +579,7 @@ def mcts_search(net: B200Denoiser, latents, class_labels, params: SamplingParams
             if throwaway:
                 for _ in range(b):
                     torch.randn(1, *shape, device=device)                     # eager default of the dict .get at :578
-            eps = depth_noise[i][s].to(torch.float64).contiguous()            # [b, C, H, W]
+            eps = depth_noise[i][s].contiguous()     # [b, C, H, W], fp32 like the reference's: the noise term is an fp32 product
             xc, _, _ = steppers[s].step(node.x.contiguous(), eps, i, want_x_next=True)
             node.children = [_MCTSNode(xc[n:n + 1], i + 1) for n in range(b)]
 
@@ -697,10 +697,12 @@ def generate_image_grid(
     sampling_method: SamplingMethod = SamplingMethod.NAIVE,
     sampling_params: Optional[Dict[str, Any]] = None,
     precomputed_noise: Optional[Dict[int, torch.Tensor]] = None,
-    shard: Optional[Shard] = None, record: bool = False,
+    shard: Optional[Shard] = None, record: bool = False, search_options: Optional[dict] = None,
 ):
     """Same contract as the reference's generate_image_grid (edm/main.py:47-886).  Returns None
-    like the reference unless `record=True`, in which case the SearchRecord is returned."""
+    like the reference unless `record=True`, in which case the SearchRecord is returned.
+    `search_options` (not in the reference): keyword options of `eps_greedy_search` for the zero_order / eps_greedy methods,
+    e.g. {'escalate': False} or {'kappa': 0.5, 'max_contenders': 4}."""
     device = torch.device(device)
     if device.type != 'cuda':
         raise RuntimeError('the B200 path needs a CUDA device; there is no CPU fallback')
@@ -729,7 +731,8 @@ def generate_image_grid(
         print(f"Zero-Order parameters: lambda={method_params.lambda_param}, N={method_params.N}, "
               f"K={method_params.K}, eps={method_params.eps}")
         x_next, rec = eps_greedy_search(net, latents, class_labels, method_params, table,
-                                        precomputed_noise=precomputed_noise, shard=shard, record=record)
+                                        precomputed_noise=precomputed_noise, shard=shard, record=record,
+                                        **(search_options or {}))
     else:
         x_next, rec = naive_search(net, latents, class_labels, table, record=record)
 

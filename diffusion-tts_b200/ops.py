@@ -39,19 +39,21 @@ def _c(t: torch.Tensor, dtype) -> torch.Tensor:
 
 # ------------------------------------------------------------------ sampler / scorer
 def heun_pre(x_cur: torch.Tensor, eps: torch.Tensor, s: float, c_in: float, *, x_hat=None, net_in=None):
-    """x_hat = x_cur + s*eps; net_in = c_in*fp32(x_hat).  x_cur [b,C,H,W] fp64, eps [R,C,H,W] fp64.
-    `x_hat` / `net_in` may be preallocated (e.g. the U-Net engine's static input buffer)."""
+    """x_hat = x_cur + s*eps; net_in = c_in*fp32(x_hat).  x_cur [b,C,H,W] fp64, eps [R,C,H,W] fp64 -- or fp32, in which
+    case the noise term is the fp32 product fp32(s)*eps like torch's own type promotion (edm/main.py:85 with the fp32 MCTS
+    depth noises of :445).  `x_hat` / `net_in` may be preallocated (e.g. the U-Net engine's static input buffer)."""
     _chk_cuda(x_cur, eps)
-    _c(x_cur, torch.float64), _c(eps, torch.float64)
+    _c(x_cur, torch.float64), _c(eps, torch.float32 if eps.dtype == torch.float32 else torch.float64)
     R, b = eps.shape[0], x_cur.shape[0]
     E = eps[0].numel()
-    x_hat = torch.empty_like(eps) if x_hat is None else _c(x_hat, torch.float64)
+    x_hat = torch.empty(eps.shape, dtype=torch.float64, device=eps.device) if x_hat is None else _c(x_hat, torch.float64)
     net_in = torch.empty(eps.shape, dtype=torch.float32, device=eps.device) if net_in is None else _c(net_in, torch.float32)
     if USE_TORCH_OPS:
         T.OPS.heun_pre_(x_cur, eps, x_hat, net_in, float(s), float(c_in))
     else:
-        L.check(L.lib().b200ns_heun_pre(L.ptr(x_cur), L.ptr(eps), L.ptr(x_hat), L.ptr(net_in), R, b, E, float(s),
-                                        float(c_in), L.cur_stream()), 'heun_pre')
+        fn = L.lib().b200ns_heun_pre_f32noise if eps.dtype == torch.float32 else L.lib().b200ns_heun_pre
+        L.check(fn(L.ptr(x_cur), L.ptr(eps), L.ptr(x_hat), L.ptr(net_in), R, b, E, float(s), float(c_in), L.cur_stream()),
+                'heun_pre')
     _count()
     return x_hat, net_in
 

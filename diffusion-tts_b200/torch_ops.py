@@ -45,8 +45,8 @@ def _p(t):
 
 def _heun_pre_(x_cur, eps, x_hat, net_in, s, c_in):
     R, b = eps.shape[0], x_cur.shape[0]
-    L.check(L.lib().b200ns_heun_pre(_p(x_cur), _p(eps), _p(x_hat), _p(net_in), R, b, eps[0].numel(), float(s), float(c_in),
-                                    L.cur_stream()), 'heun_pre')
+    fn = L.lib().b200ns_heun_pre_f32noise if eps.dtype == torch.float32 else L.lib().b200ns_heun_pre
+    L.check(fn(_p(x_cur), _p(eps), _p(x_hat), _p(net_in), R, b, eps[0].numel(), float(s), float(c_in), L.cur_stream()), 'heun_pre')
 
 
 def _heun_mid_(x_hat, F1, net_in2, x_eul, c_skip, c_out, t_hat, dt, c_in_next):

@@ -34,6 +34,11 @@ int b200ns_device_ok(int dev);
  * eps/x_hat are [R,E] fp64, net_in is fp32 [R,E] (NCHW).  s = sqrt(t_hat^2-t_cur^2)*S_noise. */
 int b200ns_heun_pre(const double* x_cur, const double* eps, double* x_hat, float* net_in,
                     int64_t R, int64_t b, int64_t E, double s, float c_in, void* stream);
+/* The same with an fp32 noise tensor (the MCTS depth noises edm/main.py:445, or an fp32 precomputed_noise): torch evaluates
+ * `sqrt(...) * S_noise * eps_i` with a 0-dim fp64 scale and an fp32 tensor as an fp32 product (scale rounded to fp32), and only
+ * the sum with x_cur in fp64:  x_hat = x_cur + double(fp32(s) * eps). */
+int b200ns_heun_pre_f32noise(const double* x_cur, const float* eps, double* x_hat, float* net_in,
+                             int64_t R, int64_t b, int64_t E, double s, float c_in, void* stream);
 
 /* Euler half step: D1 = c_skip*fp32(x_hat) + c_out*F1 ; d = (x_hat - D1)/t_hat ;
  * x_eul = x_hat + dt*d ; net_in2 = c_in_next*fp32(x_eul).            edm/main.py:87-91,

@@ -351,6 +351,27 @@ def test_sampler_kernels_bit_exact(ops):
         assert torch.equal(idx.cpu(), O.argmax_first(score_ref.reshape(N, b)))
 
 
+def test_heun_pre_with_fp32_noise_follows_torch_promotion(ops):
+    """The MCTS depth noises are fp32 (edm/main.py:445): torch evaluates `sqrt(...) * S_noise * eps_i` (0-dim fp64 x fp32
+    tensor) as an fp32 product and adds it to the fp64 state.  Bit-exact against that expression."""
+    g = torch.Generator().manual_seed(9)
+    b, R, C, H = 2, 6, 3, 8
+    x_cur = torch.randn(b, C, H, H, generator=g, dtype=torch.float64) * 40
+    eps32 = torch.randn(R, C, H, H, generator=g)
+    t_hat, t_cur = torch.tensor(61.7, dtype=torch.float64), torch.tensor(57.3, dtype=torch.float64)
+    scale = (t_hat ** 2 - t_cur ** 2).sqrt() * 1.003
+    term = scale * eps32
+    assert term.dtype == torch.float32
+    want = x_cur.repeat(R // b, 1, 1, 1) + term
+    assert want.dtype == torch.float64
+    c_in = torch.tensor(0.0161, dtype=torch.float32)
+    x_hat, net_in = ops.heun_pre(x_cur.cuda(), eps32.cuda(), float(scale), float(c_in))
+    assert torch.equal(x_hat.cpu(), want)
+    assert torch.equal(net_in.cpu(), c_in * want.to(torch.float32))
+    x_hat64, _ = ops.heun_pre(x_cur.cuda(), eps32.double().cuda(), float(scale), float(c_in))
+    assert not torch.equal(x_hat64.cpu(), want)                    # the fp64 product differs in the last bits
+
+
 def test_scorer_argmax_ties_and_keys(ops):
     dev = 'cuda'
     g = torch.Generator().manual_seed(9)

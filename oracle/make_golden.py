@@ -305,7 +305,8 @@ def main():
     ap.add_argument('--search-full', nargs='*', default=None, metavar='JOB',
                     help='ONLY the ADM-64 N=64 search fixtures (the north-star config; ~45 CPU-minutes each on 8 cores): '
                          'any of eps0 (18 steps, brightness), eps04 (6 steps, eps=0.4, recorded Bernoulli draws), '
-                         'imagenet (4 steps, classifier scorer in the loop); no names = all three')
+                         'imagenet (4 steps, classifier scorer in the loop); no names = all three.  eps0_k2: a second seed with '
+                         'K=2 rounds per step (~90 CPU-minutes), only when named')
     args = ap.parse_args()
     assert os.environ.get('PYTHONHASHSEED') == '0', 'run with PYTHONHASHSEED=0'
     os.makedirs(GOLD, exist_ok=True)
@@ -317,6 +318,9 @@ def main():
         if 'imagenet' in jobs:
             gen_search(FULL_ADM, 1234, 'search_imagenet_adm64_N64.pt', 'EPS_GREEDY', N=64, K=1, num_steps=4, b=1,
                        trace=True, scorer='imagenet')
+        if 'eps0_k2' in jobs:   # a second weight / noise seed, two local-search rounds per step (the pivot moves inside a step)
+            gen_search(FULL_ADM, 4242, 'search_eps_greedy_adm64_N64_K2.pt', 'EPS_GREEDY', N=64, K=2, num_steps=18, b=1,
+                       trace=True)
         if 'eps04' in jobs:
             gen_search(FULL_ADM, 1234, 'search_eps04_adm64_N64.pt', 'EPS_GREEDY', N=64, K=1, num_steps=6, b=1, eps=0.4,
                        trace=True, all_fresh=True)

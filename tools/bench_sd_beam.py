@@ -18,7 +18,9 @@ ap.add_argument('--steps', type=int, default=10)
 ap.add_argument('--warmup', type=int, default=3)
 ap.add_argument('--per-gpu', type=int, default=32)
 ap.add_argument('--vae', action='store_true', help='decode every candidate x0 to a 512x512 image before scoring (SURVEY 8 f1)')
+ap.add_argument('--clip', action='store_true', help='--vae plus the CLIP ViT-L/14 scorer (random-init) on every decoded image (SURVEY 8 f4)')
 args = ap.parse_args()
+args.vae = args.vae or args.clip
 rank, world, lrank = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
 torch.cuda.set_device(lrank)
 dev = torch.device('cuda', lrank)
@@ -46,7 +48,13 @@ shard = Shard(rank, world, None) if world > 1 else None
 vae_kw = {}
 if args.vae:
     veng = VAEDecoderEngine(random_state_dict(vae_decoder_param_shapes(), 4321), device=dev)
-    vae_kw = dict(decode=lambda x0: x0, scorer=DecodedImageScorer(veng, None, chunk=8))
+    score_fn = None
+    if args.clip:
+        from diffusion_tts_b200.arch import clip_param_shapes
+        from diffusion_tts_b200.clip import CLIPScorer
+        score_fn = CLIPScorer(random_state_dict(clip_param_shapes(vision_only=True), 33), device=dev)
+        score_fn.set_text_embeds('a photo', torch.randn(1, 768, generator=g))
+    vae_kw = dict(decode=lambda x0: x0, scorer=DecodedImageScorer(veng, score_fn, 'a photo', chunk=8))
 total = args.warmup + args.steps
 noises = {i: torch.randn(B, N, 4, 64, 64, generator=g).to(dev) for i in range(total)}      # same on every rank
 
@@ -87,16 +95,16 @@ gemm_flops = sum(f for f, k in zip(fp.plan.flops, fp.plan.kinds) if k == 'gemm')
 by_kind = {}
 for t, k in zip(per_op, fp.plan.kinds):
     by_kind[k] = by_kind.get(k, 0.0) + t
-peak_tf, _, peak_src = peaks()
+peak_tf, _, _, peak_src = peaks()
 if rank == 0:
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12
     fwd_per_step = 2 * B + 2 * B * N // world                  # UNet forwards (samples) per rank and step
     print(json.dumps({
         'metric': 'scored_candidates_per_sec', 'value': value, 'unit': 'candidates/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'bf16', 'data': 'synthetic',
+        'dtype': 'bf16' if __import__('diffusion_tts_b200._lib', fromlist=['ACT_BF16']).ACT_BF16 else 'fp16', 'data': 'synthetic',
         'config': {'workload': f'SD-1.5-shaped UNet2DConditionModel (859.5M, random-init) 4x64x64 latents, beam B={B} N={N} '
-                               f'(={args.per_gpu} candidates/GPU), DDIM eta=1 CFG 7.5, ' + ('SD-1.5 VAE decode (49.5M, random-init) of every Tweedie x0 to 512x512 + RGB brightness' if args.vae else 'latent brightness on Tweedie x0'),
+                               f'(={args.per_gpu} candidates/GPU), DDIM eta=1 CFG 7.5, ' + ('SD-1.5 VAE decode (49.5M, random-init) of every Tweedie x0 to 512x512 + ' + ('CLIP ViT-L/14 scorer (random-init vision tower, Pillow-exact preprocessing)' if args.clip else 'RGB brightness') if args.vae else 'latent brightness on Tweedie x0'),
                    'B': B, 'N': N, 'candidates_per_gpu': args.per_gpu, 'unet_forwards_per_rank_step': fwd_per_step,
                    'l2': 'not flushed: 1.7 GB bf16 weights + ~9 GB activations per call exceed the 126 MB L2'},
         'gpu_launches': launches, 'clocks': clk,

@@ -383,11 +383,12 @@ int launch_gemm_prec_t(const GemmOp& g, cudaStream_t st) {
     CK(cudaFuncSetAttribute(gemm_prec_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  gemm_prec_kernel<BN><<<dim3(g.grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st>>>(g.tmA[0], g.tmA[1], g.tmA[2], g.tmB, g.args, g.pargs);
+  launch_pdl(gemm_prec_kernel<BN>, dim3(g.grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, g.tmA[0], g.tmA[1], g.tmA[2], g.tmB, g.args,
+             g.pargs);
   CK_LAUNCH("gemm_prec_kernel");
   if (g.pargs.splits > 1) {          // add the K slices in order, then bias / residual / scale / split store
     const int64_t items = static_cast<int64_t>(g.args.M) * ((g.args.N + 7) / 8);
-    gemm_prec_finish_kernel<<<grid_for(items, 256, 148 * 8), 256, 0, st>>>(g.args, g.pargs);
+    launch_pdl(gemm_prec_finish_kernel, dim3(grid_for(items, 256, 148 * 8)), dim3(256), 0, st, g.args, g.pargs);
     CK_LAUNCH("gemm_prec_finish_kernel");
   }
   return 0;
@@ -518,11 +519,12 @@ int run_op(const Op& op, cudaStream_t st) {
       if (op.attn.vrow) return op.attn.KT == 128 ? launch_attn_v3<128>(op.attn, st) : launch_attn_v3<64>(op.attn, st);
       return op.attn.KT == 128 ? launch_attn_t<128, false>(op.attn, st) : launch_attn_t<64, false>(op.attn, st);
     case OP_GN_STATS_PREC:
-      gn_stats_prec_kernel<<<dim3(op.gnp.args.splits, op.gnp.args.batch), (op.gnp.args.C / 8) * op.gnp.args.PY, 0, st>>>(op.gnp.args);
+      launch_pdl(gn_stats_prec_kernel, dim3(op.gnp.args.splits, op.gnp.args.batch), dim3((op.gnp.args.C / 8) * op.gnp.args.PY), 0, st,
+                 op.gnp.args);
       CK_LAUNCH("gn_stats_prec_kernel");
       return 0;
     case OP_GN_APPLY_PREC:
-      gn_apply_prec_kernel<<<op.gnp.grid, 256, 0, st>>>(op.gnp.args);
+      launch_pdl(gn_apply_prec_kernel, dim3(op.gnp.grid), dim3(256), 0, st, op.gnp.args);
       CK_LAUNCH("gn_apply_prec_kernel");
       return 0;
     case OP_ATTN_PREC: {
@@ -531,7 +533,7 @@ int run_op(const Op& op, cudaStream_t st) {
         CK(cudaFuncSetAttribute(attention_prec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_PREC_SMEM));
         attr_set = true;
       }
-      attention_prec_kernel<<<op.attnp.grid, 256, ATTN_PREC_SMEM, st>>>(op.attnp.args);
+      launch_pdl(attention_prec_kernel, op.attnp.grid, dim3(256), ATTN_PREC_SMEM, st, op.attnp.args);
       CK_LAUNCH("attention_prec_kernel");
       return 0;
     }

@@ -229,6 +229,7 @@ gemm_prec_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -254,6 +255,7 @@ gemm_prec_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                   // barriers, tensor maps and TMEM are set up while the predecessor drains
 
   if (warp == 0) {
     if (lane == 0) gemm_prec_producer<BN>(tmA0, tmA1, tmA2, tmB, a, pa, smem_a, smem_b, full_bar, empty_bar);
@@ -344,6 +346,8 @@ gemm_prec_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
 // splits > 1: out = finish(sum over slices in order).  One thread per (row, 8 columns); N % 8 == 0 or the fp32 N < 8 case.
 __global__ void __launch_bounds__(256) gemm_prec_finish_kernel(const GemmArgs a, const GemmPrecArgs pa) {
+  pdl_launch_dependents();      // programmatic dependent launch (small-row plans are latency-bound): the successor's prologue
+  pdl_wait();                   // overlaps this kernel; nothing is read before the predecessor has completed
   const int n8 = (a.N + 7) >> 3;
   const long long total = static_cast<long long>(a.M) * n8;
   const size_t slice = static_cast<size_t>(a.m_tiles) * 128 * pa.ld_partial;
@@ -412,6 +416,8 @@ __global__ void __launch_bounds__(256) gn_stats_prec_kernel(const GnPrecArgs a) 
   __shared__ double s_sum[2048];
   __shared__ double s_sq[2048];
   __shared__ int s_last;
+  pdl_launch_dependents();      // programmatic dependent launch (small-row plans are latency-bound): the successor's prologue
+  pdl_wait();                   // overlaps this kernel; nothing is read before the predecessor has completed
   const int VC = a.C >> 3;
   const int vx = threadIdx.x % VC, py = threadIdx.x / VC;
   const int split = blockIdx.x, bi = blockIdx.y;
@@ -520,6 +526,8 @@ DEVINL float silu_exact(float x) { return x / (1.0f + expf(-x)); }
 
 // one thread per (output pixel, 8-channel vector)
 __global__ void __launch_bounds__(256) gn_apply_prec_kernel(const GnPrecArgs a) {
+  pdl_launch_dependents();      // programmatic dependent launch (small-row plans are latency-bound): the successor's prologue
+  pdl_wait();                   // overlaps this kernel; nothing is read before the predecessor has completed
   const int VC = a.C >> 3;
   const int outW = a.resample == 1 ? a.W * 2 : (a.resample == 2 ? a.W / 2 : a.W);
   const int outH = a.resample == 1 ? a.H * 2 : (a.resample == 2 ? a.H / 2 : a.H);
@@ -622,6 +630,8 @@ __global__ void __launch_bounds__(256) attention_prec_kernel(const AttnPrecArgs 
   float* Ks = Qs + 64 * ATTN_PREC_PITCH;           // [d][key] pitch 68
   float* Ps = Ks + 64 * ATTN_PREC_PITCH;           // [key][q] pitch 68
   float* Vs = Ps + 64 * ATTN_PREC_PITCH;           // [key][d] pitch 64
+  pdl_launch_dependents();      // programmatic dependent launch (small-row plans are latency-bound): the successor's prologue
+  pdl_wait();                   // overlaps this kernel; nothing is read before the predecessor has completed
   const int tid = threadIdx.x;
   const int ty = tid >> 4, tx = tid & 15;
   const int bh = blockIdx.y;
@@ -732,6 +742,8 @@ __global__ void __launch_bounds__(256) attention_prec_kernel(const AttnPrecArgs 
 
 // 3x3 im2col of the fp32 NCHW network input (Cin*9 <= 64) into split [batch*H*W, 128]: hi taps | lo taps
 __global__ void im2col_c3_prec_kernel(const float* __restrict__ x, __half* __restrict__ out, int batch, int C, int H, int W) {
+  pdl_launch_dependents();      // programmatic dependent launch (small-row plans are latency-bound): the successor's prologue
+  pdl_wait();                   // overlaps this kernel; nothing is read before the predecessor has completed
   const long long total = static_cast<long long>(batch) * H * W * 64;
   for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * 256) {
     const int k = static_cast<int>(idx & 63);

@@ -96,9 +96,15 @@ class PreciseForwardPlan:
         self.block_out: Dict[str, torch.Tensor] = {}
         self._eps = cfg.eps
         self._build(eng)
+        if os.environ.get('B200NS_PDL') is None and os.environ.get('B200NS_PREC_PDL', '1') != '0':
+            # contender batches are a handful of rows: ~470 short, latency-bound launches per forward -> overlap every kernel's
+            # prologue with its predecessor's tail (programmatic dependent launch; all precise kernels call pdl_wait())
+            self.plan.set_pdl(1)
         if eng.use_graphs:
             torch.cuda.synchronize(dev)
             self.plan.instantiate_graph()
+            self.plan.run()               # the first launch uploads the ~470-node graph (milliseconds): pay it here, at build
+            torch.cuda.synchronize(dev)   # time, not inside the first search round that happens to have this many contenders
 
     def _act(self, key: str, B, H, W, C) -> torch.Tensor:
         """Split-half activation [B,H,W,2C] in a named scratch buffer."""

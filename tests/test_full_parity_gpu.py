@@ -166,6 +166,21 @@ def test_adm64_N64_indices_equal_the_reference(pkg):
         assert (piv.cpu() - want).abs().max() < 1e-12, i
 
 
+@pytest.mark.skipif(not _have('search_eps_greedy_adm64_N64_K2.pt'), reason='fixture not generated')
+def test_adm64_N64_K2_second_seed_indices_equal_the_reference(pkg):
+    """A second weight / noise seed (4242) with K = 2 local-search rounds per step: 36 rounds, the second round of every step
+    perturbs around the candidate the first round selected (edm/main.py:848-857), so a wrong pick in round 1 would also move
+    round 2's whole candidate set.  All indices must equal the reference's."""
+    den, em, sc = pkg
+    gold = load_golden('search_eps_greedy_adm64_N64_K2.pt')
+    assert gold['K'] == 2 and len(gold['score_calls']) == 2 * gold['num_steps']
+    rec, table = _run(pkg, gold, sc.BrightnessScorer(device='cuda'), escalate=True)
+    flips, rows = _report('escalated_K2', gold, rec, table)
+    assert flips == 0, [r for r in rows if r['idx'] != r['idx_ref']]
+    rec0, _ = _run(pkg, gold, sc.BrightnessScorer(device='cuda'), escalate=False)
+    _report('fp16_K2', gold, rec0, table)                                  # reported, not asserted: the plain 16-bit argmax
+
+
 @pytest.mark.skipif(not _have('search_eps04_adm64_N64.pt'), reason='fixture not generated')
 def test_adm64_N64_eps04_indices_equal_the_reference(pkg):
     """0 < eps < 1 (CLI default 0.4, edm/main.py:751,791-795): the reference's own Bernoulli draws (recorded by the

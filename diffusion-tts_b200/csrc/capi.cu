@@ -1108,7 +1108,9 @@ static int add_gemm_part(b200ns_plan* p, const b200ns_gemm_desc* d, int BN_force
     const b200ns_kseg& sg = d->seg[s];
     if (sg.taps != 1 && sg.taps != 9) return fail("gemm: taps must be 1 or 9");
     if (sg.src < 0 || sg.src > 2 || d->a_ptr[sg.src] == nullptr) return fail("gemm: bad segment source");
-    if (sg.cstart % 64 || sg.cstart + sg.cblocks * 64 > d->a_channels[sg.src]) return fail("gemm: bad channel range");
+    // precise GEMM: segments address the hi plane, the lo plane of the same channels lies a_channels/2 further right
+    if (sg.cstart % 64 || sg.cstart + sg.cblocks * 64 > (d->prec ? d->a_channels[sg.src] / 2 : d->a_channels[sg.src]))
+      return fail("gemm: bad channel range");
     const int taps = g_up.phase >= 0 ? 4 : sg.taps;               // one phase of the fused upsample: 2x2 taps
     a.seg[s] = KSeg{sg.src, taps, sg.cstart, sg.cblocks, g_up.dy0, g_up.dx0};
     nkb += taps * sg.cblocks;
@@ -1194,8 +1196,12 @@ static int add_gemm_part(b200ns_plan* p, const b200ns_gemm_desc* d, int BN_force
   // clusters of two CTAs on two M-adjacent tiles of one column slice: each fetches half of the weight tile for both
   g.cl2 = (cl2_enabled() && !d->prec && (BN == 192 || BN == 256) && a.m_tiles * a.n_tiles >= 2 * num_sms() && !d->out_fp32)
               ? cl2_enabled() : 0;
-  if (d->prec) {        // K-block-major weights [nkb][Npad][64] (precise.cuh: gemm_prec_producer)
-    const uint64_t dims[2] = {64, static_cast<uint64_t>(nkb) * static_cast<uint64_t>(d->Npad)};
+  if (d->prec) {        // K-block-major weights [nkb][hi, lo][Npad][64] (precise.cuh: gemm_prec_producer)
+    for (int i = 0; i < 3; ++i) {
+      if (d->a_ptr[i] != nullptr && d->a_channels[i] % 128) return fail("gemm(prec): split sources need 2 x (multiple of 64) channels");
+      g.pargs.lo_off[i] = d->a_channels[i] / 2;
+    }
+    const uint64_t dims[2] = {64, 2 * static_cast<uint64_t>(nkb) * static_cast<uint64_t>(d->Npad)};
     const uint32_t box[2] = {64, static_cast<uint32_t>(BN)};
     int rc = make_tmap(&g.tmB, d->w_ptr, 2, dims, box);
     if (rc) return rc;

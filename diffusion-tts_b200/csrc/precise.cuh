@@ -4,9 +4,10 @@
 //
 // Number format "split fp16": a value v is stored as two IEEE half numbers  hi = half(v), lo = half(v - hi)
 // (v ~ hi + lo to ~2^-22 relative; absolute floor 2^-25).  An activation tensor [rows, C] becomes [rows, 2C] halves:
-// columns [0, C) = hi plane, [C, 2C) = lo plane, so a GEMM over (hi + lo) x (Whi + Wlo) is the SAME implicit-GEMM main
-// loop (TMA boxes of 64 channels, tcgen05.mma kind::f16, fp32 accumulation in TMEM) over three K segments:
-//     [hi | lo] x [Whi | Whi]   +   [hi] x [Wlo]          (the lo x Wlo term, 2^-22, is dropped)
+// columns [0, C) = hi plane, [C, 2C) = lo plane, so a GEMM over (hi + lo) x (Whi + Wlo) is the same implicit-GEMM main
+// loop (TMA boxes of 64 channels, tcgen05.mma kind::f16, fp32 accumulation in TMEM) with three MMAs per K slice:
+//     hi x Whi  +  lo x Whi  +  hi x Wlo                  (the lo x Wlo term, 2^-22, is dropped)
+// on ONE staged copy of the four operand tiles (hi, lo, Whi, Wlo) per logical K block,
 // i.e. 3x the bf16 MMA work instead of the ~30x an FFMA path would cost.  Everything elementwise (GroupNorm, SiLU,
 // FiLM, softmax) is evaluated in fp32 / fp64 with IEEE division and expf (no .approx), attention runs on the FMA pipe in
 // fp32 (12 GFLOP of the 219 GFLOP per forward).  All reductions are order-fixed: identical inputs give identical bits at
@@ -73,6 +74,7 @@ struct GemmPrecArgs {
   float* partial;                // [splits][m_tiles*128][n_tiles*BN] fp32 (splits > 1)
   int ld_partial;                // n_tiles*BN
   int n_pad;                     // padded output columns (row pitch of the K-block-major weight matrix)
+  int lo_off[3];                 // per activation source: channel offset of its lo plane (= its logical channel count)
   int* ticket;                   // reserved (an in-kernel finish by the last-arriving slice was measured 2.7x SLOWER than the
                                  // separate finishing launch: one row per thread is a serial chain of L2 round trips)
 };
@@ -80,10 +82,16 @@ struct GemmPrecArgs {
 template <int BN>
 struct GemmPrecCfg {
   using Base = GemmCfg<BN>;
-  // no epilogue slot ring here, so the operand ring can be deeper: small-M launches stream every weight once from HBM and
-  // are bound by the bytes one SM keeps in flight (ncu: 1.0 TB/s with 4 x 40 KB per SM on 100 SMs)
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 192 ? 5 : (BN >= 128 ? 6 : (BN >= 64 ? 8 : 6)));
-  static constexpr int SMEM_BYTES = STAGES * Base::STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  // One pipeline stage = one LOGICAL K block of 64 channels: the hi and the lo plane of the activation tile and the hi and
+  // the lo plane of the weight tile, consumed by three MMAs per K slice (hi x Whi, lo x Whi, hi x Wlo).  Round 2's first
+  // version ran the same three products as three K segments of the 16-bit main loop, i.e. fetched the hi activation tile
+  // and the Whi tile TWICE (120 KB of operands per logical K block at BN = 192 against 80 KB here); small-row launches are
+  // bound by exactly that L2 -> shared-memory stream.  No epilogue slot ring here, so the whole shared memory is the ring.
+  static constexpr int A2_BYTES = 2 * Base::A_BYTES;
+  static constexpr int B2_BYTES = 2 * Base::B_BYTES;
+  static constexpr int STAGE_BYTES = A2_BYTES + B2_BYTES;
+  static constexpr int STAGES = (BN >= 192) ? 2 : (BN >= 128 ? 3 : (BN >= 64 ? 4 : 5));
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int THREADS = 192;
 };
 
@@ -104,7 +112,8 @@ DEVINL void gemm_prec_producer(const CUtensorMap& tmA0, const CUtensorMap& tmA1,
                                const GemmArgs& a, const GemmPrecArgs& pa, uint8_t* smem_a, uint8_t* smem_b, uint64_t* full_bar,
                                uint64_t* empty_bar) {
   using Cfg = GemmCfg<BN>;
-  constexpr int STAGES = GemmPrecCfg<BN>::STAGES;
+  using PCfg = GemmPrecCfg<BN>;
+  constexpr int STAGES = PCfg::STAGES;
   int stage = 0;
   uint32_t phase = 0;
   int mt, nt, ks;
@@ -134,12 +143,17 @@ DEVINL void gemm_prec_producer(const CUtensorMap& tmA0, const CUtensorMap& tmA1,
         for (int cb = 0; cb < sg.cblocks; ++cb, ++kb) {
           if (kb < kb0 || kb >= kb1) continue;
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_4d(smem_a + stage * Cfg::A_BYTES, tm, &full_bar[stage], sg.cstart + cb * 64, x0 + dx, y0 + dy, n0);
-          // weights are stored K-block-major ([nkb][Npad][64]): the BN x 64 tile of K block kb is ONE contiguous
-          // BN*128-byte run of HBM (row-major [Npad][Ktot] would be BN scattered 128-byte reads per tile, which is
-          // what small-M launches -- they stream every weight exactly once -- are bound by)
-          tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], 0, kb * pa.n_pad + nt * BN);
+          mbar_arrive_expect_tx(&full_bar[stage], PCfg::STAGE_BYTES);
+          uint8_t* sa = smem_a + stage * PCfg::A2_BYTES;
+          uint8_t* sb = smem_b + stage * PCfg::B2_BYTES;
+          const int c_hi = sg.cstart + cb * 64;
+          tma_load_4d(sa, tm, &full_bar[stage], c_hi, x0 + dx, y0 + dy, n0);
+          tma_load_4d(sa + Cfg::A_BYTES, tm, &full_bar[stage], c_hi + pa.lo_off[sg.src], x0 + dx, y0 + dy, n0);
+          // weights are stored K-block-major ([nkb][hi, lo][Npad][64]): the BN x 64 tile of one plane of K block kb is ONE
+          // contiguous BN*128-byte run of HBM (row-major [Npad][Ktot] would be BN scattered 128-byte reads per tile,
+          // which is what small-M launches -- they stream every weight exactly once -- are bound by)
+          tma_load_2d(sb, &tmB, &full_bar[stage], 0, (2 * kb) * pa.n_pad + nt * BN);
+          tma_load_2d(sb + Cfg::B_BYTES, &tmB, &full_bar[stage], 0, (2 * kb + 1) * pa.n_pad + nt * BN);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -154,7 +168,8 @@ template <int BN>
 DEVINL void gemm_prec_mma(const GemmArgs& a, const GemmPrecArgs& pa, uint8_t* smem_a, uint8_t* smem_b, uint64_t* full_bar,
                           uint64_t* empty_bar, uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t tmem_base) {
   using Cfg = GemmCfg<BN>;
-  constexpr int STAGES = GemmPrecCfg<BN>::STAGES;
+  using PCfg = GemmPrecCfg<BN>;
+  constexpr int STAGES = PCfg::STAGES;
   const uint32_t idesc = umma_idesc_f16(128, BN);
   int stage = 0;
   uint32_t phase = 0;
@@ -169,10 +184,16 @@ DEVINL void gemm_prec_mma(const GemmArgs& a, const GemmPrecArgs& pa, uint8_t* sm
     for (int kb = kb0; kb < kb1; ++kb) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
-      const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * Cfg::A_BYTES));
-      const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * Cfg::B_BYTES));
+      const uint64_t da_hi = umma_desc_sw128(smem_u32(smem_a + stage * PCfg::A2_BYTES));
+      const uint64_t da_lo = umma_desc_sw128(smem_u32(smem_a + stage * PCfg::A2_BYTES + Cfg::A_BYTES));
+      const uint64_t db_hi = umma_desc_sw128(smem_u32(smem_b + stage * PCfg::B2_BYTES));
+      const uint64_t db_lo = umma_desc_sw128(smem_u32(smem_b + stage * PCfg::B2_BYTES + Cfg::B_BYTES));
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > kb0) || (k != 0));
+      for (int k = 0; k < 4; ++k) {       // (hi + lo) x (Whi + Wlo) without the 2^-22 lo x Wlo term, fp32 accumulation in TMEM
+        umma_bf16(d_tmem, da_hi + 2 * k, db_hi + 2 * k, idesc, (kb > kb0) || (k != 0));
+        umma_bf16(d_tmem, da_lo + 2 * k, db_hi + 2 * k, idesc, 1);
+        umma_bf16(d_tmem, da_hi + 2 * k, db_lo + 2 * k, idesc, 1);
+      }
       umma_commit(&empty_bar[stage]);
       if (++stage == STAGES) {
         stage = 0;
@@ -217,12 +238,13 @@ gemm_prec_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const GemmArgs a,
                  const GemmPrecArgs pa) {
   using Cfg = GemmCfg<BN>;
-  constexpr int STAGES = GemmPrecCfg<BN>::STAGES;
+  using PCfg = GemmPrecCfg<BN>;
+  constexpr int STAGES = PCfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* smem_b = smem + STAGES * PCfg::A2_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * PCfg::STAGE_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;

@@ -590,9 +590,10 @@ class Plan:
                       out: torch.Tensor, *, acc_scale: float, bias=None, residual=None, out_scale=1.0, label='gemm_prec',
                       flops: float = 0.0, splits: int = 1, bn: int = 0, partial: Optional[torch.Tensor] = None,
                       ticket: Optional[torch.Tensor] = None):
-        """a: 1-3 split-half NHWC tensors [B,H,W,2C]; segs: (src, taps, cstart, cblocks) over the 2C physical channels, laid
-        out by the caller as [hi|lo] x [Whi|Whi] + [hi] x [Wlo]; w: half [Npad, Ktot] (pre-scaled by 1/acc_scale);
-        out: split half [B,H,W,2N] or fp32 [..., N]; residual: split half [B,H,W,2N]."""
+        """a: 1-3 split-half NHWC tensors [B,H,W,2C] (hi plane | lo plane); segs: (src, taps, cstart, cblocks) over the C
+        LOGICAL channels (= the hi plane); w: half, K-block-major [2*K/64, Npad, 64] = per K block the Whi tile, then the Wlo
+        tile (precise.pack_split; pre-scaled by 1/acc_scale); out: split half [B,H,W,2N] or fp32 [..., N]; residual: split
+        half [B,H,W,2N].  Per K block the kernel issues hi x Whi + lo x Whi + hi x Wlo."""
         d = L.GemmDesc()
         B, H, W_, _ = a[0].shape
         for i, t in enumerate(a):
@@ -607,9 +608,9 @@ class Plan:
             d.seg[i] = L.KSeg(src, taps, cstart, cblocks)
         d.batch, d.H, d.W = B, H, W_
         _c(w, torch.float16)
-        if w.dim() != 3 or w.shape[2] != 64:
-            raise RuntimeError('gemm_prec: w must be K-block-major [Ktot/64, Npad, 64] (precise.pack_split)')
-        d.w_ptr, d.N, d.Npad, d.Ktot = L.ptr(w), N, w.shape[1], w.shape[0] * 64
+        if w.dim() != 3 or w.shape[2] != 64 or w.shape[0] % 2:
+            raise RuntimeError('gemm_prec: w must be K-block-major [2*K/64, Npad, 64] (precise.pack_split)')
+        d.w_ptr, d.N, d.Npad, d.Ktot = L.ptr(w), N, w.shape[1], (w.shape[0] // 2) * 64
         d.bias = L.ptr(bias)
         d.out_scale = float(out_scale)
         d.out = L.ptr(out)

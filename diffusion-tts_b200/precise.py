@@ -33,9 +33,10 @@ def split_half(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 def pack_split(blocks: Sequence[torch.Tensor], n_pad: Optional[int] = None):
     """blocks: fp32 [N, taps, C_i] weight blocks that share one accumulator (K-concatenated).
-    Returns (half [Ktot/64, Npad, 64] (K-block-major), acc_scale, segs) with, per block, K = [taps x (hi_c | hi_c)] ++ [taps x lo_c] -- the B
-    operand of `[hi|lo] x [Whi|Whi] + [hi] x [Wlo]` -- weights pre-multiplied by a power of two so that |W| <= 1024
-    (Wlo stays a normal half for all but the smallest weights); segs = per block ((taps, 2C/64), (taps, C/64))."""
+    Returns (half [2*K/64, Npad, 64], acc_scale, segs): K-block-major, per logical K block of 64 channels the Whi tile followed
+    by the Wlo tile -- the B operands of `hi x Whi + lo x Whi + hi x Wlo` -- weights pre-multiplied by a power of two so that
+    |W| <= 1024 (Wlo stays a normal half for all but the smallest weights); segs = per block (taps, C/64) over the LOGICAL
+    channels (the hi plane of the activation; its lo plane lies C further right)."""
     N = blocks[0].shape[0]
     amax = max(float(b.abs().max()) for b in blocks)
     k = int(math.floor(10 - math.log2(amax))) if amax > 0 else 0
@@ -49,15 +50,20 @@ def pack_split(blocks: Sequence[torch.Tensor], n_pad: Optional[int] = None):
         hi, lo = split_half(b.to(torch.float32) * scale)
         if os.environ.get('B200NS_PREC_NOLO') == '1':          # experiment: plain fp16 weights (see b200ns_debug_prec_nolo)
             lo = torch.zeros_like(lo)
-        parts.append(torch.cat([hi, hi], dim=2).reshape(N, taps * 2 * C))
-        parts.append(lo.reshape(N, taps * C))
-        segs.append(((taps, 2 * C // 64), (taps, C // 64)))
-    w = torch.cat(parts, dim=1)
+        parts.append(torch.stack([hi.reshape(N, taps * C), lo.reshape(N, taps * C)]))          # [2, N, K_i]
+        segs.append((taps, C // 64))
+    w = torch.cat(parts, dim=2)                                                                 # [2, N, K]
     if n_pad is not None and n_pad > N:
-        w = torch.cat([w, torch.zeros(n_pad - N, w.shape[1], dtype=w.dtype)], dim=0)
-    # K-block-major [Ktot/64, Npad, 64]: the weight tile of one K block is one contiguous run of HBM
-    w = w.reshape(w.shape[0], w.shape[1] // 64, 64).permute(1, 0, 2).contiguous()
-    return w, 1.0 / scale, segs
+        w = torch.cat([w, torch.zeros(2, n_pad - N, w.shape[2], dtype=w.dtype)], dim=1)
+    # K-block-major [K/64][hi, lo][Npad][64]: every operand tile of a K block is one contiguous run of HBM
+    w = w.reshape(2, w.shape[1], w.shape[2] // 64, 64).permute(2, 0, 1, 3).contiguous()
+    return w.reshape(-1, w.shape[2], 64), 1.0 / scale, segs
+
+
+def flat_segs(segs) -> List[Tuple[int, int, int, int]]:
+    """pack_split's per-block (taps, cblocks) -> the (src, taps, cstart, cblocks) list of `Plan.add_gemm_prec`, block i
+    reading activation source i from its first channel."""
+    return [(i, taps, 0, cblocks) for i, (taps, cblocks) in enumerate(segs)]
 
 
 def split_k_policy(hw: int, n_pad: int, nkb: int, sms: int = 148) -> Tuple[int, int]:
@@ -70,7 +76,10 @@ def split_k_policy(hw: int, n_pad: int, nkb: int, sms: int = 148) -> Tuple[int, 
     # policy with the C side's cost model choosing the width: more partial-tile traffic and finishing work)
     bn = 128 if n_pad % 128 == 0 else 64
     tiles = max(1, hw // 128) * (n_pad // bn)
-    splits = max(1, min(-(-sms // tiles), nkb // 8, 32))
+    splits = max(1, min(-(-sms // tiles), (3 * nkb) // 8, 32))     # nkb = logical K blocks (3 MMAs each)
+    pref = int(os.environ.get('B200NS_PREC_BN_PREF', '0'))         # experiment: force a tile width where it divides
+    if pref and n_pad % pref == 0:
+        return pref, splits
     return 0, splits
 
 
@@ -127,12 +136,10 @@ class PreciseForwardPlan:
 
     def _gemm(self, srcs, key, N, out, *, bias, residual=None, out_scale=1.0, label=''):
         w, acc_scale, segs = self._eng.w[key]
-        flat = []
-        for i, (sa, sb) in enumerate(segs):
-            flat.append((i, sa[0], 0, sa[1]))
-            flat.append((i, sb[0], 0, sb[1]))
+        flat = flat_segs(segs)
         B, H, W_, _ = srcs[0].shape
-        bn, splits = split_k_policy(H * W_, w.shape[1], w.shape[0])
+        nkb = w.shape[0] // 2                                       # logical K blocks: [nkb][Whi, Wlo][Npad][64]
+        bn, splits = split_k_policy(H * W_, w.shape[1], nkb)
         partial = None
         if splits > 1:
             need = splits * ((B * H * W_ + 127) // 128) * 128 * w.shape[1]
@@ -141,7 +148,7 @@ class PreciseForwardPlan:
                 partial = torch.empty(need, device=self.x_in.device, dtype=torch.float32)
                 self._scratch['splitk'] = partial
         self.plan.add_gemm_prec(srcs, flat, w, N, out, acc_scale=acc_scale, bias=bias, residual=residual,
-                                out_scale=out_scale, label=label, flops=2.0 * B * H * W_ * N * w.shape[0] * 64,
+                                out_scale=out_scale, label=label, flops=2.0 * B * H * W_ * N * 3 * nkb * 64,
                                 splits=splits, bn=bn, partial=partial)
 
     def _build(self, eng: 'PreciseUNetEngine'):

@@ -175,9 +175,11 @@ typedef struct {
    * pixel (y + py - 1 + a, x + px - 1 + c)).  gn_stats (optional) covers the high-res output.  No residual / fp32 / geglu. */
   int32_t upsample2x;
   /* --- split-fp16 "precise" GEMM (near-tie re-scoring, see the block comment further down).  prec = 1: the A tensors and
-   * w_ptr hold IEEE half (activations [.., 2C] = hi plane | lo plane; the caller lays the K segments out as
-   * [hi|lo] x [Whi|Whi] + [hi] x [Wlo]; w_ptr is K-BLOCK-MAJOR [Ktot/64][Npad][64], so that the tile of one K block is one
-   * contiguous run of HBM -- small-M launches stream every weight once); the accumulator is multiplied by acc_scale (weights are pre-scaled by a power of
+   * w_ptr hold IEEE half.  Activations are [.., 2C] = hi plane | lo plane (a_channels = 2C); the K segments and Ktot
+   * describe the LOGICAL K (channel ranges of the hi plane; the lo plane of the same channels lies C further right).  w_ptr is
+   * K-BLOCK-MAJOR [Ktot/64][2 = Whi, Wlo][Npad][64], so that each operand tile of a K block is one contiguous run of HBM
+   * (small-M launches stream every weight once).  Per K block the kernel stages the four tiles hi, lo, Whi, Wlo once and
+   * issues hi x Whi + lo x Whi + hi x Wlo.  The accumulator is multiplied by acc_scale (weights are pre-scaled by a power of
    * two); `out` is fp32 (out_fp32) or split half [M, ld_out] with the lo plane at column out_lo_off; `residual` is a
    * split half tensor with its lo plane at column res_lo_off.  No gn_stats / geglu / upsample2x / strided sources. */
   int32_t prec;

@@ -58,12 +58,12 @@ def test_gemm_prec_conv_matches_fp64(pkg, B, H, cin, cout, taps):
     r64 = _join(rs.cpu()).permute(0, 3, 1, 2)
     want = (torch.nn.functional.conv2d(x64, w.double(), bias.double(), padding=k // 2) + r64) * 0.75
     wp, acc_scale, segs = precise.pack_split([precise._conv_block(w)])
-    flat = [(0, segs[0][0][0], 0, segs[0][0][1]), (0, segs[0][1][0], 0, segs[0][1][1])]
+    flat = precise.flat_segs(segs)
     out = torch.empty(B, H, H, 2 * cout, dtype=torch.float16, device='cuda')
     P = ops.Plan()
     P.add_gemm_prec([xs], flat, wp.cuda(), cout, out, acc_scale=acc_scale, bias=bias.cuda(), residual=rs, out_scale=0.75)
     # the same GEMM with the layer's split-K policy (K slices on different SMs, partial tiles added in order)
-    bn, splits = precise.split_k_policy(H * H, wp.shape[1], wp.shape[0])
+    bn, splits = precise.split_k_policy(H * H, wp.shape[1], wp.shape[0] // 2)
     splits = max(splits, 3)
     out_sk = torch.empty_like(out)
     ws_ = torch.empty(splits * ((B * H * H + 127) // 128) * 128 * wp.shape[1], dtype=torch.float32, device='cuda')
@@ -95,9 +95,7 @@ def test_gemm_prec_two_sources_and_fp32_out(pkg):
     want = torch.nn.functional.conv2d(j(s1), w1.double(), bias.double(), padding=1) + \
         torch.nn.functional.conv2d(torch.cat([j(sa), j(sb)], 1), ws.double())
     wp, acc_scale, segs = precise.pack_split([precise._conv_block(w1), precise._conv_block(ws, 0, ca), precise._conv_block(ws, ca, ca + cb)])
-    flat = []
-    for i, (a, b) in enumerate(segs):
-        flat += [(i, a[0], 0, a[1]), (i, b[0], 0, b[1])]
+    flat = precise.flat_segs(segs)
     out = torch.empty(B, H, H, 2 * cout, dtype=torch.float16, device='cuda')
     P = ops.Plan()
     P.add_gemm_prec([s1, sa, sb], flat, wp.cuda(), cout, out, acc_scale=acc_scale, bias=bias.cuda())
@@ -106,8 +104,7 @@ def test_gemm_prec_two_sources_and_fp32_out(pkg):
     b3 = torch.randn(3, generator=g)
     wp3, sc3, segs3 = precise.pack_split([precise._conv_block(w3)], n_pad=16)
     out3 = torch.empty(B, H, H, 3, dtype=torch.float32, device='cuda')
-    P.add_gemm_prec([s1], [(0, segs3[0][0][0], 0, segs3[0][0][1]), (0, segs3[0][1][0], 0, segs3[0][1][1])], wp3.cuda(), 3, out3,
-                    acc_scale=sc3, bias=b3.cuda())
+    P.add_gemm_prec([s1], precise.flat_segs(segs3), wp3.cuda(), 3, out3, acc_scale=sc3, bias=b3.cuda())
     P.run()
     torch.cuda.synchronize()
     assert _rel(j(out), want) < 1.5e-5

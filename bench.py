@@ -15,6 +15,9 @@ the committed state (bit-identical to the reference's recomputation at batch 1, 
 NOT executed and NOT counted: `config.commit`).  Steps cycle through the 18 timesteps, so any
 multiple of 18 steps averages 426.5 GFLOP per scored candidate (35/18 network evaluations).
 
+Before the W warm-up steps one untimed pass over the 18 timesteps builds every plan / graph / NCCL channel
+(initialisation); PYTHONHASHSEED is pinned to 0 (re-exec) because the reference derives the candidate scales
+from Python's salted hash() -- otherwise every process walks a different trajectory (3..7 escalated rounds).
 `value`  : candidates/s with all inputs (noise directions, pivots) resident in HBM, escalation ON.
 `e2e`    : the same loop through the public API with HOST (pinned) noise buffers: per step the
            pivot and this rank's slice of the N direction tensors are copied host->device and the

@@ -33,7 +33,8 @@ class GemmDesc(C.Structure):
                 ('out', c_vp), ('ld_out', c_i32), ('out_fp32', c_i32), ('gn_stats', c_vp), ('reverse', c_i32), ('a_stride', c_i32 * 3), ('geglu', c_i32), ('upsample2x', c_i32),
                 ('prec', c_i32), ('acc_scale', c_f32), ('out_lo_off', c_i32), ('res_lo_off', c_i32),
                 ('prec_splits', c_i32), ('prec_bn', c_i32), ('prec_partial', c_vp), ('prec_ticket', c_vp),
-                ('prec_ticket_len', c_i32), ('act', c_i32)]
+                ('prec_ticket_len', c_i32), ('act', c_i32),
+                ('xf_mean_rstd', c_vp), ('xf_gamma', c_vp), ('xf_beta', c_vp), ('xf_groups', c_i32)]
 
 
 class GnStatsDesc(C.Structure):

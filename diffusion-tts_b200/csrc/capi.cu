@@ -236,6 +236,7 @@ struct GemmOp {
   int grid;
   int cl2;
   int prec;                  // split-fp16 precise GEMM (precise.cuh)
+  int xf;                    // GroupNorm of the A operand in the operand path (gemm_conv.cuh: gemm_transform)
   GemmPrecArgs pargs;
 };
 struct GnPrecOp {
@@ -348,8 +349,22 @@ int launch_gemm_cl2(const GemmOp& g, cudaStream_t st) {
   return 0;
 }
 template <int BN>
+int launch_gemm_xf(const GemmOp& g, cudaStream_t st) {         // + 4 transform warps (GroupNorm of A in the operand path)
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(gemm_conv_kernel<BN, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  launch_pdl(gemm_conv_kernel<BN, false, false, true>, dim3(g.grid), dim3(Cfg::THREADS + 128), Cfg::SMEM_BYTES, st, g.tmA[0], g.tmA[1],
+             g.tmA[2], g.tmB, g.tmO, g.tmR, g.args);
+  CK_LAUNCH("gemm_conv_kernel<xf>");
+  return 0;
+}
+template <int BN>
 int launch_gemm_t(const GemmOp& g, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
+  if (g.xf) return launch_gemm_xf<BN>(g, st);
   if constexpr (BN == 192 || BN == 256) {
     if (g.cl2 == 2) return launch_gemm_cg2<BN>(g, st);
     if (g.cl2) return launch_gemm_cl2<BN>(g, st);
@@ -1015,6 +1030,14 @@ static int add_gemm_cols(b200ns_plan* p, const b200ns_gemm_desc* d) {
     return add_gemm_part(p, d, d->Npad % 256 == 0 ? 256 : 128, d->N);
   }
   if (g_force_bn > 0 && d->Npad % g_force_bn == 0) return add_gemm_part(p, d, g_force_bn, d->N);
+  if (d->xf_mean_rstd != nullptr) {      // experiment: tile width of the GEMMs with GroupNorm in the operand path
+    static int xf_bn = -1;
+    if (xf_bn < 0) {
+      const char* e = getenv("B200NS_XF_BN");
+      xf_bn = e != nullptr ? atoi(e) : 0;
+    }
+    if (xf_bn > 0 && d->Npad % xf_bn == 0) return add_gemm_part(p, d, xf_bn, d->N);
+  }
   const int m_tiles = (d->batch * d->H * d->W + 127) / 128;
   const int cands[4] = {256, 192, 128, 64};
   long best = -1;
@@ -1147,6 +1170,27 @@ static int add_gemm_part(b200ns_plan* p, const b200ns_gemm_desc* d, int BN_force
   a.reverse = d->reverse;
   a.geglu = d->geglu;
   a.act = d->act;
+  g.xf = 0;
+  a.xf_mean_rstd = nullptr;
+  if (d->xf_mean_rstd != nullptr) {
+    const int HW = H * W;
+    if (d->prec || d->upsample2x || d->out_fp32 || BN == 16) return fail("gemm(a_norm): 16-bit output GEMMs only");
+    if (d->n_seg != 1 || d->seg[0].taps != 1 || d->seg[0].cstart != 0 || d->seg[0].cblocks * 64 != d->a_channels[d->seg[0].src] ||
+        d->a_stride[d->seg[0].src] == 2)
+      return fail("gemm(a_norm): a single 1x1 segment over all channels of one source");
+    if (d->xf_gamma == nullptr || d->xf_beta == nullptr || d->xf_groups < 1 || d->a_channels[d->seg[0].src] % d->xf_groups)
+      return fail("gemm(a_norm): gamma / beta / groups");
+    if (HW < 64 || (HW < 128 && 128 % HW) || (HW >= 128 && HW % 128)) return fail("gemm(a_norm): H*W must be 64 or a multiple of 128");
+    // the coefficient tables [2 tiles][2 samples][C] x (k_a, k_b) live in the shared memory of one operand stage
+    if (32 * d->a_channels[d->seg[0].src] > 16384 + BN * 128) return fail("gemm(a_norm): too many channels for this tile width");
+    g.xf = 1;
+    a.xf_mean_rstd = reinterpret_cast<const float2*>(d->xf_mean_rstd);
+    a.xf_gamma = d->xf_gamma;
+    a.xf_beta = d->xf_beta;
+    a.xf_groups = d->xf_groups;
+    a.xf_cpg = d->a_channels[d->seg[0].src] / d->xf_groups;
+    a.xf_batch = d->batch;
+  }
   if (d->act != 0 && (d->act != 1 || d->geglu || d->upsample2x || d->prec)) return fail("gemm: act must be 0 or 1 (quick_gelu), without geglu / upsample2x / prec");
   if (d->gn_stats != nullptr && (BN == 16 || a.M % 64)) return fail("gemm: gn_stats needs bf16 output, N tiles >= 64 and M % 64 == 0");
   if (!d->out_fp32 && (d->ld_out % 8)) return fail("gemm: ld_out must be a multiple of 8 for bf16 output");
@@ -1194,7 +1238,7 @@ static int add_gemm_part(b200ns_plan* p, const b200ns_gemm_desc* d, int BN_force
     a.src_stride[i] = sdn;
   }
   // clusters of two CTAs on two M-adjacent tiles of one column slice: each fetches half of the weight tile for both
-  g.cl2 = (cl2_enabled() && !d->prec && (BN == 192 || BN == 256) && a.m_tiles * a.n_tiles >= 2 * num_sms() && !d->out_fp32)
+  g.cl2 = (cl2_enabled() && !d->prec && !g.xf && (BN == 192 || BN == 256) && a.m_tiles * a.n_tiles >= 2 * num_sms() && !d->out_fp32)
               ? cl2_enabled() : 0;
   if (d->prec) {        // K-block-major weights [nkb][hi, lo][Npad][64] (precise.cuh: gemm_prec_producer)
     for (int i = 0; i < 3; ++i) {

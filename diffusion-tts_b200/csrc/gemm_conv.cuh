@@ -68,6 +68,15 @@ struct GemmArgs {
                                  //    fused into the projection, whose [M, N] output never touches HBM
   int fp16;                      // 1: operands are IEEE half (the split-fp16 "precise" path, precise.cuh) instead of bf16
   int act;                       // 1: quick_gelu(acc + bias) = x * sigmoid(1.702 x) before the residual / out_scale (CLIP MLP)
+  // XF kernels only: GroupNorm (affine, no activation) of the A operand, applied to the TMA-landed shared-memory stage in
+  // place by four transform warps before the MMA warp consumes it -- the `norm -> 1x1 conv` pairs (attention norm2 -> qkv,
+  // networks.py:182-183; SD / VAE `norm -> proj_in`) without the normalised tensor ever being written:
+  //   a'[m, c] = a[m, c] * (rstd[s, g] * gamma[c]) + (beta[c] - mean[s, g] * rstd[s, g] * gamma[c]),  s = sample of row m
+  const float2* xf_mean_rstd;    // [batch, xf_groups] (gn_finalize_kernel)
+  const float* xf_gamma;
+  const float* xf_beta;
+  int xf_groups, xf_cpg;
+  int xf_batch;
 };
 
 template <int BN>
@@ -114,11 +123,11 @@ DEVINL bool gemm_tile_at(const GemmArgs& a, int it, int& mt, int& nt) {
 }
 
 // ===================== TMA producer (one thread) =====================
-template <int BN, bool CL2 = false, bool CG2 = false>
+template <int BN, bool CL2 = false, bool CG2 = false, bool XF = false>
 DEVINL void gemm_producer(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmA2, const CUtensorMap& tmB,
                           const GemmArgs& a, uint8_t* smem_a, uint8_t* smem_b, uint64_t* full_bar, uint64_t* empty_bar) {
   using Cfg = GemmCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
+  constexpr int STAGES = Cfg::STAGES - (XF ? 1 : 0);      // XF: the last stage's shared memory holds the coefficient tables
   const int rank = CL2 ? static_cast<int>(cluster_ctarank()) : 0;
   int stage = 0;
   uint32_t phase = 0;
@@ -176,11 +185,11 @@ DEVINL void gemm_producer(const CUtensorMap& tmA0, const CUtensorMap& tmA1, cons
 }
 
 // ===================== MMA issuer (one thread) =====================
-template <int BN, bool CL2 = false, bool CG2 = false>
+template <int BN, bool CL2 = false, bool CG2 = false, bool XF = false>
 DEVINL void gemm_mma(const GemmArgs& a, uint8_t* smem_a, uint8_t* smem_b, uint64_t* full_bar, uint64_t* empty_bar,
                      uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t tmem_base) {
   using Cfg = GemmCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
+  constexpr int STAGES = Cfg::STAGES - (XF ? 1 : 0);
   const uint32_t idesc = CG2 ? umma_idesc_act(256, BN) : (a.fp16 ? umma_idesc_f16(128, BN) : umma_idesc_act(128, BN));
   int stage = 0;
   uint32_t phase = 0;
@@ -231,20 +240,92 @@ DEVINL void gemm_mma(const GemmArgs& a, uint8_t* smem_a, uint8_t* smem_b, uint64
 // ---------------------------------------------------------------------------------------------------------
 // CG2 (with CL2 scheduling): tcgen05 cta_group::2 -- the pair's leader issues M = 256 MMAs over both CTAs' A rows and the
 // two halves of the weight tile, one half in each CTA's shared memory (half the B staging and operand traffic per SM).
-template <int BN, bool CL2 = false, bool CG2 = false>
-__global__ void __launch_bounds__(320, 1)
+// XF: four more warps (threads 320..447) normalise every A stage in place (GemmArgs.xf_*); the MMA warp then waits for
+// THEIR barrier instead of the TMA's.  Single-source 1x1 GEMMs only, no clusters.
+template <int BN>
+DEVINL void gemm_transform(const GemmArgs& a, uint8_t* smem_a, float2* tab, uint64_t* full_bar, uint64_t* xf_bar) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES - 1;
+  const int tt = threadIdx.x - 320;              // 0..127
+  const int j = tt & 7;                          // 16-byte chunk (8 channels) of the 64-channel K block
+  const int rbase = tt >> 3;                     // rows rbase + 16 i, i = 0..7
+  const int HW = a.H * a.W;
+  const int C = a.nkb * 64;                      // one 1x1 segment over all channels
+  int stage = 0;
+  uint32_t phase = 0;
+  int mt, nt;
+  for (int it = 0; gemm_tile_at<false>(a, it, mt, nt); ++it) {
+    // samples of this tile: one (HW >= 128), or two of 64 rows each (HW = 64)
+    const int s0 = a.tiles_per_img > 0 ? mt / a.tiles_per_img : mt * a.tileN;
+    const int n_s = a.tiles_per_img > 0 ? 1 : 2;
+    const int rows_per_sample = a.tiles_per_img > 0 ? 128 : HW;
+    // (k_a, k_b) of every channel for the tile's samples -> table `it & 1` (double buffered: a thread that is already in
+    // tile it + 1 writes the other table; the barrier below keeps everybody within one tile of each other)
+    float2* t0 = tab + static_cast<size_t>(it & 1) * 2 * C;
+    for (int c = tt; c < C; c += 128) {
+      const float gam = __ldg(a.xf_gamma + c), bet = __ldg(a.xf_beta + c);
+      const int g = c / a.xf_cpg;
+      for (int u = 0; u < n_s; ++u) {
+        int sidx = s0 + u;
+        if (sidx >= a.xf_batch) sidx = a.xf_batch - 1;             // rows past M (zero-filled by the TMA, never stored)
+        const float2 mr = __ldg(a.xf_mean_rstd + static_cast<size_t>(sidx) * a.xf_groups + g);
+        const float rs = mr.y * gam;                               // same expressions as gn_apply_kernel: bit-identical
+        // layout [K block][e = channel pair 0..3][j = 16-byte chunk 0..7][2]: the eight threads of a quarter warp (same e,
+        // j = 0..7) read 128 contiguous bytes -- channel-major order was a 4-way bank conflict on every table read
+        const int cc = c & 63;
+        t0[u * C + (c & ~63) + ((cc & 7) >> 1) * 16 + (cc >> 3) * 2 + (cc & 1)] = make_float2(rs, bet - mr.x * rs);
+      }
+    }
+    named_barrier_sync(2, 128);
+    for (int kb = 0; kb < a.nkb; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      const uint32_t base = smem_u32(smem_a + stage * Cfg::A_BYTES);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {              // rows 0..63 (sample 0) / 64..127 (sample 0 or 1)
+        const int u = (h * 64 >= rows_per_sample) ? 1 : 0;
+        const float4* tp = reinterpret_cast<const float4*>(t0 + u * C + kb * 64) + j;
+        float4 k[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) k[e] = tp[e * 8];              // (ka, kb) of channels j*8 + 2e, j*8 + 2e + 1
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = rbase + 16 * (4 * h + i);
+          const uint32_t addr = base + static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(j ^ (r & 7)) << 4);
+          uint4 v = lds128(addr);
+          float2 f;
+          f = unpack_act(v.x); v.x = pack_act(f.x * k[0].x + k[0].y, f.y * k[0].z + k[0].w);
+          f = unpack_act(v.y); v.y = pack_act(f.x * k[1].x + k[1].y, f.y * k[1].z + k[1].w);
+          f = unpack_act(v.z); v.z = pack_act(f.x * k[2].x + k[2].y, f.y * k[2].z + k[2].w);
+          f = unpack_act(v.w); v.w = pack_act(f.x * k[3].x + k[3].y, f.y * k[3].z + k[3].w);
+          sts128(addr, v);
+        }
+      }
+      fence_proxy_async_smem();                  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if ((tt & 31) == 0) mbar_arrive(&xf_bar[stage]);   // one arrival per warp (128 arrivals on one barrier serialise)
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  }
+}
+
+template <int BN, bool CL2 = false, bool CG2 = false, bool XF = false>
+__global__ void __launch_bounds__(XF ? 448 : 320, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const GemmArgs a) {
   using Cfg = GemmCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
+  constexpr int STAGES = Cfg::STAGES - (XF ? 1 : 0);   // XF: one stage less, its shared memory = the coefficient tables
   constexpr int NSUB = Cfg::NSUB;
   constexpr int SLOTS = Cfg::SLOTS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-  uint8_t* smem_slot = smem + STAGES * Cfg::STAGE_BYTES;                  // 1024-aligned (all sizes are multiples of 1 KB)
+  float2* xf_tab = reinterpret_cast<float2*>(smem + STAGES * Cfg::STAGE_BYTES);       // [2 tiles][2 samples][C] (k_a, k_b), XF only
+  uint8_t* smem_slot = smem + Cfg::STAGES * Cfg::STAGE_BYTES;             // 1024-aligned (all sizes are multiples of 1 KB)
   float* smem_bias = reinterpret_cast<float*>(smem_slot + SLOTS * Cfg::SLOT_BYTES);   // [2][BN]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_slot + Cfg::EPI_BYTES);
   uint64_t* full_bar = bars;
@@ -252,7 +333,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
   uint64_t* rfull_bar = bars + 2 * STAGES + 4;                            // [SLOTS] residual sub-box landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + SLOTS);
+  uint64_t* xf_bar = bars + 2 * STAGES + 4 + SLOTS;                       // [STAGES] A stage normalised in place (XF)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4 + SLOTS);
+  static_assert(!(XF && CL2), "the transform warps are not cluster-aware");
+  static_assert((3 * STAGES + 4 + SLOTS) * 8 + 4 <= 256, "barrier block");
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
@@ -275,6 +359,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       mbar_init(&tempty_bar[i], CG2 ? 16 : 8);    // CG2: the leader's MMA waits for both CTAs' epilogue warps
     }
     for (int s = 0; s < SLOTS; ++s) mbar_init(&rfull_bar[s], 1);
+    if constexpr (XF)
+      for (int s = 0; s < STAGES; ++s) mbar_init(&xf_bar[s], 4);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -294,10 +380,12 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   pdl_wait();                   // everything above overlapped the previous kernel's tail (PDL)
 
   if (warp == 0) {
-    if (lane == 0) gemm_producer<BN, CL2, CG2>(tmA0, tmA1, tmA2, tmB, a, smem_a, smem_b, full_bar, empty_bar);
+    if (lane == 0) gemm_producer<BN, CL2, CG2, XF>(tmA0, tmA1, tmA2, tmB, a, smem_a, smem_b, full_bar, empty_bar);
   } else if (warp == 1) {
     if (lane == 0 && (!CG2 || cluster_ctarank() == 0))      // CG2: only the pair's leader issues MMAs
-      gemm_mma<BN, CL2, CG2>(a, smem_a, smem_b, full_bar, empty_bar, tfull_bar, tempty_bar, tmem_base);
+      gemm_mma<BN, CL2, CG2, XF>(a, smem_a, smem_b, XF ? xf_bar : full_bar, empty_bar, tfull_bar, tempty_bar, tmem_base);
+  } else if (XF && warp >= 10) {
+    gemm_transform<BN>(a, smem_a, xf_tab, full_bar, xf_bar);
   } else {
     // ===================== epilogue (warps 2..9, 256 threads) =====================
     const int et = threadIdx.x - 64;        // 0..255

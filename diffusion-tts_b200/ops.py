@@ -371,7 +371,7 @@ class Plan:
 
     def add_gemm(self, a: Sequence[torch.Tensor], segs: Sequence[Tuple[int, int, int, int]], w: torch.Tensor, N: int,
                  out: torch.Tensor, *, bias=None, residual=None, out_scale=1.0, gn_stats=None, reverse=False, a_stride=None,
-                 label='gemm', alg_k=None, geglu=False, upsample2x=False, act=0):
+                 label='gemm', alg_k=None, geglu=False, upsample2x=False, act=0, a_norm=None):
         """a: 1-3 NHWC bf16 tensors [B,H,W,C]; segs: (src, taps, cstart, cblocks); w: bf16 [Npad,Ktot].
         gn_stats: optional fp32 [M/64, N, 2] receiving per-channel (sum, sumsq) of the stored output.
         geglu: w / bias rows in groups of [64 hidden | 64 gate] (`interleave_geglu`); out is [.., N/2] = hidden * gelu(gate).
@@ -415,6 +415,11 @@ class Plan:
         d.reverse = int(reverse)
         d.geglu = int(bool(geglu))
         d.act = int(act)                                       # 1: quick_gelu(acc + bias) in the epilogue (CLIP MLP)
+        if a_norm is not None:     # (mean_rstd fp32 [B, groups, 2], gamma, beta, groups): GroupNorm of A in the operand path
+            mr, gam, bet, groups = a_norm
+            d.xf_mean_rstd, d.xf_gamma, d.xf_beta = L.ptr(_c(mr, torch.float32)), L.ptr(_c(gam, torch.float32)), L.ptr(_c(bet, torch.float32))
+            d.xf_groups = int(groups)
+            self._k(mr, gam, bet)
         if geglu and out.shape[-1] * 2 != N:
             raise RuntimeError('gemm(geglu): out must have N/2 columns')
         self._k(*a, w, bias, residual, out, gn_stats)

@@ -147,6 +147,12 @@ class ForwardPlan:
     per-sample result is batch-invariant, so the split changes no bits.  Builder state (x, skips) always holds the
     FULL-batch tensors; ops see the current lane's slice (`_view`)."""
 
+    # GroupNorm of the A operand inside the qkv GEMM (norm2 -> qkv, `Plan.add_gemm(a_norm=...)`): built, bit-identical,
+    # and measured SLOWER than the separate pass at every level (DESIGN.md 4b), so it is off unless B200NS_FUSED_NORM_A=1.
+    # (class attribute: subclasses with their own __init__ -- classifier, SD, VAE plans -- inherit it)
+    fused_norm_a = os.environ.get('B200NS_FUSED_NORM_A', '0') == '1'
+
+
     def __init__(self, eng: 'UNetEngine', B: int, b_emb: int):
         cfg, dev = eng.cfg, eng.device
         self.B, self.B_full, self.b_emb = B, B, b_emb
@@ -427,11 +433,24 @@ class ForwardPlan:
         hd = cout // heads
         if hd not in (64, 256) or (hd == 256 and (heads != 1 or L > 256)):
             raise NotImplementedError(f'{n}: attention head_dim {hd} x {heads} heads at L={L} is not implemented')
-        a2 = self._act('a1', B, Ho, Ho, cout)
-        self._gn([out], cout, Ho, Ho, W_[f'{n}.norm2.weight'], W_[f'{n}.norm2.bias'], a2, silu=False, label=f'{n}.norm2')
         qkv = self._act('qkv', B, Ho, Ho, 3 * cout)          # [Q | K | V], each head-major, row-major per pixel
-        P.add_gemm([a2], [(0, 1, 0, cout // 64)], W_[f'{n}.qkv.w'], 3 * cout, qkv, bias=W_[f'{n}.qkv.b'],
-                   reverse=self._rev(a2, qkv), label=f'{n}.qkv')
+        st2 = self._stats.get(self._tk(out))
+        L2 = Ho * Ho
+        if self.fused_norm_a and st2 is not None and (L2 == 64 or L2 % 128 == 0):
+            # qkv(norm2(x)) (networks.py:182-183) with the GroupNorm applied INSIDE the GEMM's operand path: four transform
+            # warps normalise each TMA-landed A stage in shared memory before the MMA warp consumes it, so the normalised
+            # tensor is never written or re-read (bit-identical to the separate gn_apply pass)
+            g = self._num_groups(cout)
+            mr = self._buf('mean_rstd', self.B * 64 * 2, torch.float32)[:self.B * g * 2]
+            P.add_gn_finalize([st2], [cout], self.B, L2, g, self._eps, mr, b_emb=self.b_emb, label=f'{n}.norm2.finalize')
+            P.add_gemm([out], [(0, 1, 0, cout // 64)], W_[f'{n}.qkv.w'], 3 * cout, qkv, bias=W_[f'{n}.qkv.b'],
+                       reverse=self._rev(out, qkv), label=f'{n}.norm2+qkv',
+                       a_norm=(mr, W_[f'{n}.norm2.weight'], W_[f'{n}.norm2.bias'], g))
+        else:
+            a2 = self._act('a1', B, Ho, Ho, cout)
+            self._gn([out], cout, Ho, Ho, W_[f'{n}.norm2.weight'], W_[f'{n}.norm2.bias'], a2, silu=False, label=f'{n}.norm2')
+            P.add_gemm([a2], [(0, 1, 0, cout // 64)], W_[f'{n}.qkv.w'], 3 * cout, qkv, bias=W_[f'{n}.qkv.b'],
+                       reverse=self._rev(a2, qkv), label=f'{n}.qkv')
         att = self._act('a0', B, Ho, Ho, cout)
         # V is consumed in place as an MN-major UMMA operand: no transposed copy
         P.add_attention(qkv.view(B * L, 3 * cout), cout, None, att.view(B * L, cout), B, heads, L,

@@ -198,6 +198,15 @@ typedef struct {
   /* epilogue activation applied to (acc + bias) before the residual / out_scale: 0 none, 1 quick_gelu x * sigmoid(1.702 x)
    * (CLIP's MLP, transformers activations.py QuickGELUActivation; 16-bit engine only) */
   int32_t act;
+  /* optional: GroupNorm (affine, no activation) of the A operand inside the GEMM's operand path -- the `norm -> 1x1 conv`
+   * pairs of the attention blocks (edm/training/networks.py:182-183 `qkv(norm2(x))`; diffusers `proj_in(norm(x))`) without the
+   * normalised tensor being written: xf_mean_rstd fp32 [batch, xf_groups, 2] (b200ns_plan_add_gn_finalize), xf_gamma / xf_beta
+   * fp32 [channels].  Needs ONE 1x1 segment over all channels of one unstrided source, 16-bit output, H*W = 64 or a multiple
+   * of 128.  Bit-identical to b200ns_plan_add_gn_apply (silu = 0) followed by the plain GEMM. */
+  const float* xf_mean_rstd;
+  const float* xf_gamma;
+  const float* xf_beta;
+  int32_t xf_groups;
 } b200ns_gemm_desc;
 int b200ns_plan_add_gemm(b200ns_plan* p, const b200ns_gemm_desc* d);
 /* Tuning aid: force the N tile width (64/128/192/256; 0 = cost model) of subsequently added bf16 GEMMs whose padded

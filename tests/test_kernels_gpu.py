@@ -55,6 +55,39 @@ def test_conv_gemm(ops, B, H, Cin, Cout, k):
     assert err < 6e-3, f'rel err {err}'
 
 
+@pytest.mark.parametrize('B,H,C,N', [(3, 16, 128, 384), (5, 8, 192, 576), (2, 32, 64, 128), (64, 8, 768, 2304), (2, 32, 384, 1152),
+                                     (1, 8, 64, 64), (4, 16, 320, 320)])
+def test_gemm_with_groupnorm_in_the_operand_path_is_bit_identical(ops, B, H, C, N):
+    """`qkv(norm2(x))` (networks.py:182-183): GroupNorm applied to the TMA-landed A stage in shared memory by the GEMM's
+    transform warps == gn_apply (silu = 0) followed by the plain GEMM, bit for bit -- incl. two samples per 128-row tile
+    (H*W = 64), a partial last tile (odd batch), column-sliced launches (N = 320 = 192 + 128) and >= 2 waves of tiles."""
+    torch.manual_seed(B * 100 + H)
+    dev = 'cuda'
+    groups = 32
+    x = (torch.randn(B, H, H, C, device=dev) * 3 + 0.5).to(ACT)
+    w = (torch.randn(N, C, device=dev) / math.sqrt(C)).to(ACT)
+    bias = torch.randn(N, device=dev)
+    gamma, beta = torch.randn(C, device=dev) * 0.3 + 1, torch.randn(C, device=dev) * 0.2
+    xs = x.float().view(B, H * H, groups, C // groups)
+    mean = xs.mean(dim=(1, 3))
+    rstd = (xs.var(dim=(1, 3), unbiased=False) + 1e-5).rsqrt()
+    mr = torch.stack([mean, rstd], dim=-1).contiguous()                       # [B, groups, 2]
+    a2 = torch.empty_like(x)
+    out_ref, out = torch.empty(B, H, H, N, device=dev, dtype=ACT), torch.empty(B, H, H, N, device=dev, dtype=ACT)
+    plan = ops.Plan()
+    plan.add_gn_apply([x], groups, None, 1, 1e-5, gamma, beta, a2, silu=False, mean_rstd=mr)
+    plan.add_gemm([a2], [(0, 1, 0, C // 64)], w, N, out_ref, bias=bias)
+    plan.add_gemm([x], [(0, 1, 0, C // 64)], w, N, out, bias=bias, a_norm=(mr, gamma, beta, groups))
+    out_rev = torch.empty_like(out)
+    plan.add_gemm([x], [(0, 1, 0, C // 64)], w, N, out_rev, bias=bias, a_norm=(mr, gamma, beta, groups), reverse=True)
+    plan.run()
+    torch.cuda.synchronize()
+    want = F.linear(((xs - mean[:, None, :, None]) * rstd[:, None, :, None]).view(B, H, H, C) * gamma + beta, w.float(), bias)
+    assert _rel_err(out_ref, want) < 6e-3
+    assert torch.equal(out, out_ref), float((out.float() - out_ref.float()).abs().max())
+    assert torch.equal(out_rev, out_ref)
+
+
 def test_conv_fused_skip_dual_source_residual(ops):
     """conv1(h) + skip1x1(cat[x0,x1]) in one accumulator, + bias, * skip_scale; and the
     no-skip-conv flavour with a residual."""

@@ -27,6 +27,7 @@ import numpy as np
 import torch
 
 from .. import ops, philox
+from .._lib import ACT_BF16
 from ..denoiser import B200Denoiser, HeunStepper, StepTable, load_network
 from ..scorers import BrightnessScorer, Scorer
 
@@ -74,8 +75,10 @@ class SearchRecord:
 # reference on the ADM-64 N=64 fixtures it has a standard deviation of 0.054-0.082 of the spread of the scores themselves at
 # every noise level (fp16 storage; 0.17-0.26 with bf16), i.e. the difference of two candidates' errors has sigma ~0.1 spread:
 # KAPPA = 0.35 is ~3.5 sigma (tests/test_full_parity_gpu.py dumps the tables).
-ESCALATION_KAPPA = 0.35
-MAX_CONTENDERS = 8
+# The bfloat16-storage build (B200NS_ACT=bf16) carries 3-4x the noise (its worst observed gain of a candidate on the true best
+# is 0.5 of the spread: a flip at kappa = 0.35 on the K = 2 fixture), so its defaults are wider.
+ESCALATION_KAPPA = 1.25 if ACT_BF16 else 0.35
+MAX_CONTENDERS = 16 if ACT_BF16 else 8
 
 
 @dataclass

@@ -122,6 +122,7 @@ SIGNATURES = {
     'b200ns_plan_add_gn_stats': (C.c_int, [c_vp, C.POINTER(GnStatsDesc)]),
     'b200ns_plan_add_gn_apply': (C.c_int, [c_vp, C.POINTER(GnApplyDesc)]),
     'b200ns_plan_add_gn_finalize': (C.c_int, [c_vp, C.POINTER(GnFinalizeDesc)]),
+    'b200ns_plan_add_gn_norm': (C.c_int, [c_vp, C.POINTER(GnFinalizeDesc), C.POINTER(GnApplyDesc)]),
     'b200ns_plan_add_attention': (C.c_int, [c_vp, C.POINTER(AttnDesc)]),
     'b200ns_plan_add_linear': (C.c_int, [c_vp, C.POINTER(LinearDesc)]),
     'b200ns_plan_add_im2col': (C.c_int, [c_vp, C.POINTER(Im2colDesc)]),

@@ -224,7 +224,7 @@ int make_tmap_2d_ld(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t ro
 }
 
 // ------------------------------------------------------------------ plan ops
-enum OpKind { OP_GEMM, OP_GN_STATS, OP_GN_APPLY, OP_GN_FINALIZE, OP_ATTN, OP_LINEAR, OP_IM2COL, OP_U8F32, OP_POOL_TOKENS, OP_POOL_ATTN,
+enum OpKind { OP_GEMM, OP_GN_STATS, OP_GN_APPLY, OP_GN_FINALIZE, OP_GN_NORM, OP_ATTN, OP_LINEAR, OP_IM2COL, OP_U8F32, OP_POOL_TOKENS, OP_POOL_ATTN,
               OP_SOFTMAX_GATHER, OP_LAYERNORM, OP_GEGLU, OP_UPSAMPLE2X, OP_SOFTMAX_ROWS,
               OP_GN_STATS_PREC, OP_GN_APPLY_PREC, OP_ATTN_PREC, OP_IM2COL_PREC,
               OP_CLIP_PREPROCESS, OP_CLIP_POOL_LN, OP_CLIP_COSINE };
@@ -263,6 +263,12 @@ struct GnFinalizeOp {
   int n_pairs;
   int wide;
 };
+struct GnNormOp {          // finalize + apply in one cluster launch (low-resolution levels)
+  GnApplyArgs apply;
+  GnFinalizeArgs fin;
+  dim3 grid;
+  int threads;
+};
 struct AttnOp {
   CUtensorMap tmQ, tmK, tmV;
   AttnArgs args;
@@ -300,6 +306,7 @@ struct Op {
     GnStatsOp gns;
     GnApplyOp gna;
     GnFinalizeOp gnf;
+    GnNormOp gnn;
     AttnOp attn;
     LinearOp lin;
     Im2colOp i2c;
@@ -517,6 +524,24 @@ int run_op(const Op& op, cudaStream_t st) {
         launch_pdl_light(gn_finalize_kernel<false>, dim3(op.gnf.grid), dim3(256), 0, st, op.gnf.args, op.gnf.n_pairs);
       CK_LAUNCH("gn_finalize_kernel");
       return 0;
+    case OP_GN_NORM: {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = op.gnn.grid;
+      cfg.blockDim = dim3(op.gnn.threads);
+      cfg.stream = st;
+      cudaLaunchAttribute attr[2];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = GN_CLUSTER;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = pdl_mode() != 0 ? 2 : 1;
+      cudaLaunchKernelEx(&cfg, gn_norm_cluster_kernel, op.gnn.apply, op.gnn.fin);
+      CK_LAUNCH("gn_norm_cluster_kernel");
+      return 0;
+    }
     case OP_ATTN:
       if (op.attn.head_dim == 256) {
         static bool attr_set = false;
@@ -1368,6 +1393,33 @@ int b200ns_plan_add_gn_finalize(b200ns_plan* p, const b200ns_gn_finalize_desc* d
   op.gnf.n_pairs = d->groups * d->batch;
   op.gnf.grid = dim3((op.gnf.n_pairs + 7) / 8);
   op.gnf.wide = static_cast<long long>(a.HW / 64) * a.cpg > 4096 ? 1 : 0;      // a function of the shape only
+  p->push(op);
+  return 0;
+}
+
+// gn_finalize + gn_apply as ONE cluster launch (gn_norm_cluster_kernel): the two descriptors are exactly those of the two
+// separate ops (apply.mean_rstd == finalize.mean_rstd), the result is bit-identical to running them back to back.
+int b200ns_plan_add_gn_norm(b200ns_plan* p, const b200ns_gn_finalize_desc* f, const b200ns_gn_apply_desc* d) {
+  b200ns_plan tmp;
+  int rc = b200ns_plan_add_gn_finalize(&tmp, f);
+  if (rc) return rc;
+  rc = b200ns_plan_add_gn_apply(&tmp, d);
+  if (rc) return rc;
+  const Op& of = tmp.ops[0];
+  const Op& oa = tmp.ops[1];
+  if (of.gnf.wide || oa.gna.threads > 256) return fail("gn_norm: shape needs the wide kernels; use the separate ops");
+  if (d->mean_rstd == nullptr || d->mean_rstd != f->mean_rstd) return fail("gn_norm: apply.mean_rstd must be finalize.mean_rstd");
+  if (f->batch != d->batch || f->groups != d->groups || f->HW != d->H * d->W || of.gnf.args.C != oa.gna.args.C)
+    return fail("gn_norm: the two descriptors disagree");
+  Op op;
+  op.kind = OP_GN_NORM;
+  op.gnn.apply = oa.gna.args;
+  op.gnn.fin = of.gnf.args;
+  GnApplyArgs& a = op.gnn.apply;
+  const int dom = d->resample == 2 ? (d->H / 2) * (d->W / 2) : d->H * d->W;
+  a.ITER = (dom + GN_CLUSTER * a.PY - 1) / (GN_CLUSTER * a.PY);       // the sample's pixels over the cluster's CTAs
+  op.gnn.threads = oa.gna.threads;
+  op.gnn.grid = dim3(GN_CLUSTER, d->batch);
   p->push(op);
   return 0;
 }

@@ -74,6 +74,10 @@ DEVINL uint32_t cluster_ctarank() {
 DEVINL void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// split form without .aligned (callers whose last warp is partial): prior global writes of every thread of the cluster
+// are visible to every thread of the cluster after the wait
+DEVINL void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
+DEVINL void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
 // the box lands at the same CTA-relative offset in every CTA of `mask`, and completes bytes on the mbarrier at the same
 // offset in each of them
 DEVINL void tma_load_2d_mc(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t mask) {

@@ -162,22 +162,13 @@ struct GnFinalizeArgs {
 //               and the eight partial sums are combined in warp order: for the VAE decoder's 512x512 activations
 //               (4096 statistics rows per sample) a single warp per pair left the GPU idle (271 us per launch).
 // Which variant runs depends only on the tensor shape, so results stay batch-size and batch-position invariant.
-template <bool WIDE>
-__global__ void __launch_bounds__(256) gn_finalize_kernel(const GnFinalizeArgs a, int n_pairs) {
-  __shared__ double s_part[16];
-  pdl_launch_dependents();
-  pdl_wait();
-  const int lane = threadIdx.x & 31;
-  const int wid = threadIdx.x >> 5;
-  const int pair = WIDE ? blockIdx.x : blockIdx.x * 8 + wid;
-  if (pair >= n_pairs) return;
-  const int bi = pair / a.groups, g = pair - bi * a.groups;
+// (sum, sum of squares) of one (sample, group) over elements [begin, total) of its (statistics row, channel) list, by ONE
+// warp: lane-strided fp64 accumulation with 4 loads in flight, then a butterfly -- every lane ends with the same, order-fixed
+// pair.  Shared by gn_finalize_kernel and gn_norm_cluster_kernel, so both produce the same bits.
+DEVINL void gn_group_sums(const GnFinalizeArgs& a, int bi, int g, int begin, int total, int lane, double& ds, double& dq) {
   const int R = a.HW >> 6;
-  const int total_all = R * a.cpg;
-  const int chunk = WIDE ? (total_all + 7) / 8 : total_all;
-  const int begin = WIDE ? wid * chunk : 0;
-  const int total = WIDE ? min(total_all, begin + chunk) : total_all;
-  double ds = 0.0, dq = 0.0;
+  ds = 0.0;
+  dq = 0.0;
   auto fetch = [&](int i, float2& v, double& pa) {
     const int r = i / a.cpg;
     const int cc = g * a.cpg + (i - r * a.cpg);
@@ -214,6 +205,32 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const GnFinalizeArgs a
     ds += __shfl_xor_sync(0xffffffffu, ds, o);
     dq += __shfl_xor_sync(0xffffffffu, dq, o);
   }
+}
+DEVINL float2 gn_mean_rstd(const GnFinalizeArgs& a, double ds, double dq) {
+  const double n = static_cast<double>(a.HW) * a.cpg;
+  const double mean = ds / n;
+  double var = dq / n - mean * mean;
+  var = var < 0.0 ? 0.0 : var;
+  return make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps))));
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const GnFinalizeArgs a, int n_pairs) {
+  __shared__ double s_part[16];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int pair = WIDE ? blockIdx.x : blockIdx.x * 8 + wid;
+  if (pair >= n_pairs) return;
+  const int bi = pair / a.groups, g = pair - bi * a.groups;
+  const int R = a.HW >> 6;
+  const int total_all = R * a.cpg;
+  const int chunk = WIDE ? (total_all + 7) / 8 : total_all;
+  const int begin = WIDE ? wid * chunk : 0;
+  const int total = WIDE ? min(total_all, begin + chunk) : total_all;
+  double ds, dq;
+  gn_group_sums(a, bi, g, begin, total, lane, ds, dq);
   if (WIDE) {
     if (lane == 0) {
       s_part[2 * wid] = ds;
@@ -228,14 +245,7 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const GnFinalizeArgs a
       dq += s_part[2 * w + 1];
     }
   }
-  if (lane == 0) {
-    const double n = static_cast<double>(a.HW) * a.cpg;
-    const double mean = ds / n;
-    double var = dq / n - mean * mean;
-    var = var < 0.0 ? 0.0 : var;
-    a.mean_rstd[static_cast<size_t>(bi) * a.groups + g] =
-        make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps))));
-  }
+  if (lane == 0) a.mean_rstd[static_cast<size_t>(bi) * a.groups + g] = gn_mean_rstd(a, ds, dq);
 }
 
 struct GnApplyArgs {
@@ -263,40 +273,11 @@ struct GnApplyArgs {
 
 // grid (pixel chunks, batch); block = (C/8) * PY threads
 // WIDE: more than 2048 channels (SD-1.5 decoder concat 2560): up to 512 threads per block
-template <bool WIDE>
-__global__ void __launch_bounds__(WIDE ? 512 : 256, WIDE ? 1 : 3) gn_apply_kernel(const GnApplyArgs a) {
-  __shared__ float s_mean[64];
-  __shared__ float s_rstd[64];
-  pdl_launch_dependents();
-  pdl_wait();
+// y = act(FiLM(norm(x))) for the pixel chunk `bx` of sample `bi`; s_mean / s_rstd hold the sample's group statistics
+DEVINL void gn_apply_body(const GnApplyArgs& a, int bi, int bx, const float* s_mean, const float* s_rstd) {
   const int VC = a.C >> 3;
   const int vx = threadIdx.x % VC, py = threadIdx.x / VC;
-  const int bi = a.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
-  const int bx = a.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
   const int HW = a.H * a.W;
-  if (a.mean_rstd != nullptr) {
-    if (threadIdx.x < a.groups) {
-      const float2 mr = a.mean_rstd[static_cast<size_t>(bi) * a.groups + threadIdx.x];
-      s_mean[threadIdx.x] = mr.x;
-      s_rstd[threadIdx.x] = mr.y;
-    }
-  } else if (threadIdx.x < a.groups) {
-    const int g = threadIdx.x;
-    double ds = 0.0, dq = 0.0;
-    for (int sp = 0; sp < a.splits; ++sp) {
-      const double* o = a.partial + ((static_cast<size_t>(bi) * a.splits + sp) * a.groups + g) * 2;
-      ds += o[0];
-      dq += o[1];
-    }
-    const double n = static_cast<double>(HW) * a.cpg;
-    const double mean = ds / n;
-    double var = dq / n - mean * mean;
-    var = var < 0.0 ? 0.0 : var;
-    s_mean[g] = static_cast<float>(mean);
-    s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
-  }
-  __syncthreads();
-
   const int c = vx * 8;
   const act_t* src;
   int ld;
@@ -400,6 +381,76 @@ __global__ void __launch_bounds__(WIDE ? 512 : 256, WIDE ? 1 : 3) gn_apply_kerne
       }
     }
   }
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(WIDE ? 512 : 256, WIDE ? 1 : 3) gn_apply_kernel(const GnApplyArgs a) {
+  __shared__ float s_mean[64];
+  __shared__ float s_rstd[64];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int bi = a.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
+  const int bx = a.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const int HW = a.H * a.W;
+  if (a.mean_rstd != nullptr) {
+    if (threadIdx.x < a.groups) {
+      const float2 mr = a.mean_rstd[static_cast<size_t>(bi) * a.groups + threadIdx.x];
+      s_mean[threadIdx.x] = mr.x;
+      s_rstd[threadIdx.x] = mr.y;
+    }
+  } else if (threadIdx.x < a.groups) {
+    const int g = threadIdx.x;
+    double ds = 0.0, dq = 0.0;
+    for (int sp = 0; sp < a.splits; ++sp) {
+      const double* o = a.partial + ((static_cast<size_t>(bi) * a.splits + sp) * a.groups + g) * 2;
+      ds += o[0];
+      dq += o[1];
+    }
+    const double n = static_cast<double>(HW) * a.cpg;
+    const double mean = ds / n;
+    double var = dq / n - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    s_mean[g] = static_cast<float>(mean);
+    s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
+  }
+  __syncthreads();
+  gn_apply_body(a, bi, bx, s_mean, s_rstd);
+}
+
+// gn_finalize + gn_apply in ONE launch for the low-resolution levels (H*W <= 256), where both are latency-bound (6-8 us of
+// finalize and 13-18 us of apply for 6-19 MB tensors): one thread-block cluster of GN_CLUSTER CTAs per sample.  CTA r of the
+// cluster reduces the statistics of groups [r*gpc, (r+1)*gpc) -- one warp per group, the very code of gn_finalize_kernel, so
+// the bits are the same -- and writes (mean, rstd) to global memory; after a cluster barrier (release / acquire) every CTA
+// reads the sample's groups back from L2 and normalises its own eighth of the pixels.
+constexpr int GN_CLUSTER = 8;
+__global__ void __launch_bounds__(256, 3) gn_norm_cluster_kernel(const GnApplyArgs a, const GnFinalizeArgs f) {
+  __shared__ float s_mean[64];
+  __shared__ float s_rstd[64];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int bi = a.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
+  const int rank = blockIdx.x;                          // gridDim.x == GN_CLUSTER == the cluster's x extent
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nfull = blockDim.x >> 5;
+  const int gpc = (f.groups + GN_CLUSTER - 1) / GN_CLUSTER;
+  if (wid < nfull) {                                    // only complete warps reduce (the butterfly needs 32 lanes)
+    const int g_end = min(f.groups, (rank + 1) * gpc);
+    const int total = (f.HW >> 6) * f.cpg;
+    for (int g = rank * gpc + wid; g < g_end; g += nfull) {
+      double ds, dq;
+      gn_group_sums(f, bi, g, 0, total, lane, ds, dq);
+      if (lane == 0) f.mean_rstd[static_cast<size_t>(bi) * f.groups + g] = gn_mean_rstd(f, ds, dq);
+    }
+  }
+  __threadfence();
+  cluster_arrive_release();
+  cluster_wait_acquire();
+  if (threadIdx.x < a.groups) {
+    const float2 mr = __ldcg(f.mean_rstd + static_cast<size_t>(bi) * f.groups + threadIdx.x);
+    s_mean[threadIdx.x] = mr.x;
+    s_rstd[threadIdx.x] = mr.y;
+  }
+  __syncthreads();
+  gn_apply_body(a, bi, a.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x, s_mean, s_rstd);
 }
 
 }  // namespace b200

@@ -16,6 +16,10 @@ from . import torch_ops as T
 # The sampler / scorer entry points and the plan runner go through their torch.library registrations
 # (torch.ops.b200ns.*, torch_ops.py); B200NS_TORCH_OPS=0 calls the C ABI through ctypes directly.
 USE_TORCH_OPS = os.environ.get('B200NS_TORCH_OPS', '1') != '0'
+# 1 = gn_finalize + gn_apply as one thread-block-cluster launch at H*W <= 256 (bit-identical).  Measured on B200 at batch 64
+# (profiles/r02_gn_cluster_ab.txt): 4.7 us saved per 8x8 norm, nothing at 16x16, NFE graph 16.12-16.34 ms against
+# 16.05-16.19 ms with the two launches -- off by default.
+GN_CLUSTER = os.environ.get('B200NS_GN_CLUSTER', '0') == '1'
 
 # number of libb200ns kernel launches issued through this module (bench.py reports it)
 LAUNCHES = [0]
@@ -453,7 +457,7 @@ class Plan:
         self.flops.append(0.0)
 
     def add_gn_finalize(self, stats: Sequence[torch.Tensor], channels: Sequence[int], batch: int, HW: int, groups: int,
-                        eps: float, mean_rstd: torch.Tensor, *, pre_add=None, b_emb=1, label='gn_finalize'):
+                        eps: float, mean_rstd: torch.Tensor, *, pre_add=None, b_emb=1, label='gn_finalize', _desc_only=False):
         """stats: per-source fp32 [batch*HW/64, C_i, 2] written by the producing GEMMs -> mean_rstd fp32 [batch, groups, 2]."""
         d = L.GnFinalizeDesc()
         for i, (t, c) in enumerate(zip(stats, channels)):
@@ -466,6 +470,8 @@ class Plan:
         d.b_emb, d.eps = b_emb, float(eps)
         d.mean_rstd = L.ptr(_c(mean_rstd, torch.float32))
         self._k(*stats, pre_add, mean_rstd)
+        if _desc_only:
+            return d
         L.check(L.lib().b200ns_plan_add_gn_finalize(self._h, C.byref(d)), 'plan_add_gn_finalize')
         self.labels.append(label)
         self.kinds.append('gn_finalize')
@@ -474,7 +480,7 @@ class Plan:
     def add_gn_apply(self, x: Sequence[torch.Tensor], groups: int, partial: Optional[torch.Tensor], splits: int, eps: float,
                      gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor, *, pre_add=None, film_scale=None,
                      film_shift=None, b_emb=1, silu=True, resample=0, raw_out=None, mean_rstd=None, reverse=False,
-                     label='gn_apply'):
+                     label='gn_apply', _desc_only=False):
         d = L.GnApplyDesc()
         B, H, W_, _ = x[0].shape
         for i, t in enumerate(x):
@@ -494,10 +500,35 @@ class Plan:
         d.mean_rstd = L.ptr(mean_rstd)
         d.reverse = int(reverse)
         self._k(*x, partial, gamma, beta, pre_add, film_scale, film_shift, out, raw_out, mean_rstd)
+        if _desc_only:
+            return d
         L.check(L.lib().b200ns_plan_add_gn_apply(self._h, C.byref(d)), 'plan_add_gn_apply')
         self.labels.append(label)
         self.kinds.append('gn_apply')
         self.flops.append(0.0)
+
+    def add_gn_norm(self, stats: Sequence[torch.Tensor], x: Sequence[torch.Tensor], groups: int, eps: float,
+                    mean_rstd: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor, *, pre_add=None,
+                    film_scale=None, film_shift=None, b_emb=1, silu=True, resample=0, raw_out=None, reverse=False,
+                    label='gn'):
+        """GroupNorm from the producers' epilogue statistics: gn_finalize + gn_apply.  At the low-resolution levels
+        (H*W <= 256; both kernels are latency-bound there) the two run as ONE cluster launch (gn_norm_cluster_kernel,
+        bit-identical) when B200NS_GN_CLUSTER=1; measured no faster, so two launches by default."""
+        B, H, W_, _ = x[0].shape
+        chans = [t.shape[3] for t in x]
+        fin = dict(pre_add=pre_add, b_emb=b_emb)
+        app = dict(pre_add=pre_add, film_scale=film_scale, film_shift=film_shift, b_emb=b_emb, silu=silu, resample=resample,
+                   raw_out=raw_out, mean_rstd=mean_rstd, reverse=reverse)
+        if GN_CLUSTER and H * W_ <= 256 and (H * W_) % 64 == 0 and sum(chans) <= 2048:
+            f = self.add_gn_finalize(stats, chans, B, H * W_, groups, eps, mean_rstd, _desc_only=True, **fin)
+            a = self.add_gn_apply(x, groups, None, 1, eps, gamma, beta, out, _desc_only=True, **app)
+            L.check(L.lib().b200ns_plan_add_gn_norm(self._h, C.byref(f), C.byref(a)), 'plan_add_gn_norm')
+            self.labels.append(f'{label}.norm')
+            self.kinds.append('gn_norm')
+            self.flops.append(0.0)
+            return
+        self.add_gn_finalize(stats, chans, B, H * W_, groups, eps, mean_rstd, label=f'{label}.finalize', **fin)
+        self.add_gn_apply(x, groups, None, 1, eps, gamma, beta, out, label=f'{label}.apply', **app)
 
     def add_attention(self, qk: torch.Tensor, k_col0: int, vt: Optional[torch.Tensor], out: torch.Tensor, batch: int,
                       heads: int, Lseq: int, label='attention', v_col0: int = 0, head_dim: int = 64, reverse=False,

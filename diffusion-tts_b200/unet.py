@@ -267,12 +267,10 @@ class ForwardPlan:
         if all(st is not None for st in stats):
             # statistics come from the producing GEMMs' epilogues: no pass over the activations
             mr = self._buf('mean_rstd', self.B * 64 * 2, torch.float32)[:self.B * g * 2]
-            self.plan.add_gn_finalize(stats, [t.shape[3] for t in xs], self.B, H * W, g, eps, mr, pre_add=pre_add,
-                                      b_emb=self.b_emb, label=f'{label}.finalize')
-            self.plan.add_gn_apply(xs, g, None, 1, eps, gamma, beta, out, pre_add=pre_add,
-                                   film_scale=film[0] if film else None, film_shift=film[1] if film else None,
-                                   b_emb=self.b_emb, silu=silu, resample=resample, raw_out=raw_out, mean_rstd=mr,
-                                   reverse=self._rev(xs[0], out, raw_out), label=f'{label}.apply')
+            self.plan.add_gn_norm(stats, xs, g, eps, mr, gamma, beta, out, pre_add=pre_add,
+                                  film_scale=film[0] if film else None, film_shift=film[1] if film else None,
+                                  b_emb=self.b_emb, silu=silu, resample=resample, raw_out=raw_out,
+                                  reverse=self._rev(xs[0], out, raw_out), label=label)
             return
         splits = self._splits(H * W)
         partial = self._buf('partial', self.B * 512 * 32 * 2, torch.float64)[:self.B * splits * g * 2].view(

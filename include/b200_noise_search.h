@@ -270,6 +270,13 @@ typedef struct {
 } b200ns_gn_apply_desc;
 int b200ns_plan_add_gn_apply(b200ns_plan* p, const b200ns_gn_apply_desc* d);
 
+/* b200ns_plan_add_gn_finalize + b200ns_plan_add_gn_apply as ONE launch for the low-resolution levels (H*W <= 256, where the
+ * two kernels are latency-bound): a thread-block cluster of 8 CTAs per sample reduces the statistics (same code, same
+ * order, same bits as the finalize kernel), exchanges (mean, rstd) through `mean_rstd` across a cluster barrier and
+ * normalises the sample (GroupNorm.forward + the silu / addcmul glue of UNetBlock.forward, networks.py:104-106, 168-175).
+ * `a->mean_rstd` must equal `f->mean_rstd`.  Bit-identical to the two separate ops. */
+int b200ns_plan_add_gn_norm(b200ns_plan* p, const b200ns_gn_finalize_desc* f, const b200ns_gn_apply_desc* a);
+
 /* Self-attention, head_dim 64 or 256 (networks.py:113-118, 182-185): for each (batch, head)
  * O = softmax(Q K^T / sqrt(64)) V with fp32 softmax; Q,K come from qk [batch*L, ld_qk]
  * (Q at column head*64, K at column k_col0 + head*64), V^T from vt [batch*heads, 64, L];

@@ -311,6 +311,65 @@ def test_gemm_epilogue_gn_stats_and_finalize(ops, B, H, C0, C1, Cout, k, pre):
     assert _rel_err(y, ref) < 5e-3
 
 
+@pytest.mark.parametrize('B,H,C0,C1,resample,film,silu,pre,reverse', [
+    (3, 8, 768, 0, 0, True, True, False, False), (2, 8, 768, 768, 0, False, True, False, True),
+    (5, 16, 576, 0, 0, False, False, False, False), (3, 16, 576, 576, 0, True, True, False, True),
+    (2, 16, 576, 384, 1, False, True, False, False), (3, 16, 384, 0, 2, True, True, False, False),
+    (2, 8, 64, 0, 0, False, True, True, False), (4, 16, 192, 64, 0, True, True, True, False),
+    (64, 8, 768, 0, 0, True, True, False, True),
+])
+def test_groupnorm_cluster_launch_is_bit_identical(ops, B, H, C0, C1, resample, film, silu, pre, reverse):
+    """gn_norm_cluster_kernel (finalize + apply in one 8-CTA-cluster launch per sample, H*W <= 256) against the two
+    separate kernels on the same epilogue statistics: every output bit and (mean, rstd) must agree (concat sources,
+    FiLM, pre_add, both resample modes, partial last warps: C = 576 -> 216 threads, reversed walk)."""
+    torch.manual_seed(12)
+    dev = 'cuda'
+    chans = [c for c in (C0, C1) if c]
+    C = sum(chans)
+    groups = min(32, C // 4)
+    xs = [(torch.randn(B, H, H, c, device=dev) * 1.5 + 0.3).to(ACT) for c in chans]
+    stats = []
+    for x in xs:
+        x64 = x.float().reshape(-1, 64, x.shape[3])
+        stats.append(torch.stack([x64.sum(1), (x64 * x64).sum(1)], dim=2).contiguous())
+    gamma, beta = torch.randn(C, device=dev), torch.randn(C, device=dev)
+    pa = torch.randn(1, C, device=dev) if pre else None
+    fs = torch.randn(1, 2 * C, device=dev) * 0.3 if film else None
+    Ho = H * 2 if resample == 1 else (H // 2 if resample == 2 else H)
+    res = {}
+    for fused in (False, True):
+        mr = torch.full((B, groups, 2), float('nan'), device=dev)
+        out = torch.full((B, Ho, Ho, C), float('nan'), device=dev, dtype=ACT)
+        raw = torch.full((B, Ho, Ho, C), float('nan'), device=dev, dtype=ACT)
+        kw = dict(pre_add=pa, film_scale=fs[:, :C] if film else None, film_shift=fs[:, C:] if film else None, b_emb=1,
+                  silu=silu, resample=resample, raw_out=raw, reverse=reverse)
+        plan = ops.Plan()
+        old = ops.GN_CLUSTER
+        ops.GN_CLUSTER = fused
+        try:
+            plan.add_gn_norm(stats, xs, groups, 1e-5, mr, gamma, beta, out, **kw)
+        finally:
+            ops.GN_CLUSTER = old
+        assert plan.kinds == (['gn_norm'] if fused else ['gn_finalize', 'gn_apply'])
+        plan.run()
+        torch.cuda.synchronize()
+        res[fused] = (mr, out, raw)
+    for a, b in zip(res[False], res[True]):
+        assert not torch.isnan(a.float()).any()
+        assert torch.equal(a, b)
+    xc = torch.cat(xs, dim=3).float().permute(0, 3, 1, 2)
+    if pre:
+        xc = xc + pa.view(1, C, 1, 1)
+    y = F.group_norm(xc, groups, gamma, beta, 1e-5)
+    if film:
+        y = torch.addcmul(fs[:, C:, None, None], y, fs[:, :C, None, None] + 1)
+    if silu:
+        y = F.silu(y)
+    if resample:
+        y = O._resample(y, resample == 1, resample == 2)
+    assert _rel_err(res[True][1], y.permute(0, 2, 3, 1)) < 5e-3
+
+
 def test_linear(ops):
     torch.manual_seed(7)
     dev = 'cuda'

@@ -26,6 +26,7 @@ from Python's salted hash() -- otherwise every process walks a different traject
            has arrived inside it).
 `extras` : reported separately, never the headline --
            no_escalation        the plain 16-bit tensor-core path (what round 1 measured)
+           speculation          the precise pass of an escalated round overlapped with the next round (off by default: < 1 %)
            noise_free_dedupe    + the exact shortcut for the noise-free timesteps
            eps04                eps = 0.4 (CLI default): fresh-noise candidates mixed in (Bernoulli on the host mirror)
            commit_recompute     the reference's literal commit (2 more network calls at batch 1 per step)
@@ -234,7 +235,7 @@ def run_b200(args):
     from diffusion_tts_b200 import _lib, ops
     from diffusion_tts_b200.arch import adm_param_shapes, random_state_dict
     from diffusion_tts_b200.denoiser import B200Denoiser, StepTable
-    from diffusion_tts_b200.edm.main import ESCALATION_KAPPA, SamplingParams, Shard, eps_greedy_search
+    from diffusion_tts_b200.edm.main import ESCALATION_KAPPA, SPECULATE_DEFAULT, SamplingParams, Shard, eps_greedy_search
     from diffusion_tts_b200.scorers import BrightnessScorer
 
     N = N_PER_GPU * world
@@ -271,13 +272,15 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(noise, steps_idx, x_init, on_step=None, dedupe=False, escalate=esc, p=params, commit='reuse', sh=shard):
+    def timed(noise, steps_idx, x_init, on_step=None, dedupe=False, escalate=esc, p=params, commit='reuse', sh=shard,
+              speculate=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         x, rec = eps_greedy_search(net, None, labels, p, table, precomputed_noise=noise, shard=sh,
                                    step_indices=steps_idx, x_init=x_init, on_step=on_step, prefetch=bool(args.prefetch),
-                                   dedupe_noise_free=dedupe, escalate=escalate, kappa=kappa, commit=commit)
+                                   dedupe_noise_free=dedupe, escalate=escalate, kappa=kappa, commit=commit,
+                                   speculate=speculate)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -312,6 +315,13 @@ def run_b200(args):
     v_ne, ms_ne, _ = rate(on_dev, N, escalate=False)
     extras['no_escalation'] = {'value': v_ne, 'ms_per_step': ms_ne,
                                'note': 'argmax over the 16-bit scores only: indices may differ from the fp32 reference on near ties'}
+    if esc and not args.quick:
+        v_ns, ms_ns, rec_ns = rate(on_dev, N, speculate=not SPECULATE_DEFAULT)
+        extras['speculation' if not SPECULATE_DEFAULT else 'no_speculation'] = {
+            'value': v_ns, 'ms_per_step': ms_ns, 'rows_refined_per_step': rec_ns.escalated, 'mispredicted_rounds': rec_ns.mispredicted,
+            'speculated_rounds': sum(1 for e in rec_ns.escalation_log if e[2]),
+            'note': 'the other setting of `speculate` (overlap the precise pass of an escalated round with the next round, verify '
+                    'afterwards, roll back on a wrong guess; bit-identical results).  Off by default: the gain is < 1 %'}
     v_dd, ms_dd, _ = rate(on_dev, N, dedupe=True)
     extras['noise_free_dedupe'] = {'value': v_dd, 'ms_per_step': ms_dd,
                                    'noise_free_steps': sum(1 for j in order[args.warmup:] if table.steps[j].s == 0.0),
@@ -446,7 +456,9 @@ def run_b200(args):
                 'h2d_bytes_per_step_per_rank': h2d_rank, 'd2h_bytes_per_step_per_rank': d2h,
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': launches,
-        'escalation': {'rows_refined_per_step': rec.escalated, 'rounds_with_escalation': sum(1 for r in rec.escalated if r),
+        'escalation': {'speculative_overlap': SPECULATE_DEFAULT, 'mispredicted_rounds': rec.mispredicted, 'missed_steps': rec.missed_steps,
+                       'log_step_lead_speculated': rec.escalation_log,
+                       'rows_refined_per_step': rec.escalated, 'rounds_with_escalation': sum(1 for r in rec.escalated if r),
                        'truncated_rounds': rec.truncated,
                        'note': 'rows = contenders of this rank re-evaluated by the precise engine (2 more network evaluations each)'},
         'extras': extras,

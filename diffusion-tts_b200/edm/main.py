@@ -19,6 +19,8 @@ Deviations from the reference, each deliberate (SURVEY.md hard part 11):
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass, field
 from enum import Enum, auto
 from typing import Any, Dict, List, Optional
@@ -66,6 +68,9 @@ class SearchRecord:
     escalated: List[int] = field(default_factory=list)            # per round: rows re-scored by the precise engine (this rank)
     refined: List[Optional[torch.Tensor]] = field(default_factory=list)   # per round (record only): [N_local, b] refined scores, -inf = not a contender
     truncated: int = 0                                            # rounds whose contender list exceeded max_contenders
+    mispredicted: int = 0                                         # speculated rounds whose refined winner differed (rolled back)
+    escalation_log: List[tuple] = field(default_factory=list)     # per escalated round: (timestep, winner's lead / std per image, speculated?)
+    missed_steps: List[int] = field(default_factory=list)         # timesteps of the rolled-back rounds
 
 
 # Near-tie escalation (SURVEY.md 7 hard part 1b).  A candidate is a contender when its 16-bit score is within
@@ -181,6 +186,38 @@ class _NoiseStager:
         return dst
 
 
+# Speculation past escalated rounds (eps_greedy_search `speculate`): B200NS_SPECULATE=1 turns the default on,
+# B200NS_SPEC_PRIO is the CUDA priority of the stream the precise pass runs on (default -1 = above the main stream),
+# B200NS_SPEC_GAP the minimum lead of the 16-bit winner (in standard deviations of the round's scores) to speculate on.
+# OFF by default -- built, bit-identical (tests/test_search_gpu.py::test_speculation_*), and measured on B200 (DESIGN.md 4e,
+# profiles/r02_speculation_ab.txt): the 16-bit GEMMs are persistent and hold every SM, so the ~940 dependent launches of a
+# precise pass only advance at the main stream's kernel boundaries and the pass takes about as long as the round it hides
+# behind: 37.0 vs 37.1 ms per step with three of six escalated rounds speculated (all held), 36.9 vs 37.2 with two; and
+# without the lead gate two of six guesses were wrong (leads of 0.008 and 0.03-0.04 std) and cost a round each: 37.7 vs 37.0.
+SPECULATE_DEFAULT = os.environ.get('B200NS_SPECULATE', '0') == '1'
+SPEC_GAP = float(os.environ.get('B200NS_SPEC_GAP', '0.08'))       # minimum lead of the 16-bit winner, in units of the round's score std
+_SPEC_STREAMS: Dict[Any, Any] = {}
+
+
+def _speculation_on(speculate: Optional[bool], escalate: bool, scorer, device) -> bool:
+    if not escalate or torch.device(device).type != 'cuda':
+        return False
+    want = SPECULATE_DEFAULT if speculate is None else bool(speculate)
+    if want and not getattr(scorer, 'fused_sums', False):
+        # scorer networks (classifier, CLIP) own static plan buffers: two streams may not score through them at once
+        if speculate:
+            raise NotImplementedError('speculate=True needs a scorer that works from the fused channel sums (brightness)')
+        return False
+    return want
+
+
+def _speculation_stream(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _SPEC_STREAMS:
+        _SPEC_STREAMS[key] = torch.cuda.Stream(device=device, priority=int(os.environ.get('B200NS_SPEC_PRIO', '-1')))
+    return _SPEC_STREAMS[key]
+
+
 def _key_score(key: torch.Tensor) -> torch.Tensor:
     """fp32 score packed in the high half of an argmax key (csrc/sampler.cuh: orderable_f32 is an involution)."""
     o = (key >> 32).to(torch.int32)
@@ -188,7 +225,8 @@ def _key_score(key: torch.Tensor) -> torch.Tensor:
 
 
 def _escalate(scorer, stepper: HeunStepper, x_cur, local, scores, key, idx, i, lo, hi, b, labels_rows, C, HW, shard,
-              delta: Optional[float], kappa: float, max_rows: int):
+              delta: Optional[float], kappa: float, max_rows: int, side=None, spec_gap: float = 0.0,
+              log: Optional[list] = None):
     """One round's near-tie escalation.  scores [nl, b] (this rank's bf16 scores), key [b] (the GLOBAL packed argmax key).
     Returns (idx [b] global winners, rows refined here, refined score table or None, truncated?).
 
@@ -196,21 +234,29 @@ def _escalate(scorer, stepper: HeunStepper, x_cur, local, scores, key, idx, i, l
     else kappa * std_n(scores[:, j]) (the bf16 score noise that matters -- the part that DIFFERS between candidates --
     measures ~0.07 of the spread of the scores themselves at every noise level), but never more than the
     `max_rows` best-scoring ones per image.  All of this is a function of the GLOBAL score table, so a sharded run refines
-    exactly the rows an unsharded run refines."""
+    exactly the rows an unsharded run refines.
+
+    `side` (a CUDA stream): SPECULATIVE mode, five values are returned.  If the 16-bit winner leads the runner-up by at least
+    `spec_gap` x the standard deviation of the round's scores (a narrower lead is too likely to be overturned -- the
+    difference of two candidates' 16-bit errors has sigma ~ 0.1 std -- and a wrong guess costs a whole round), the precise
+    pass and the argmax over the refined table are enqueued on `side`, the fifth value is a `_Pending` and `idx` comes back
+    unchanged (the 16-bit winner, provisional): the caller carries on with it while the precise pass runs underneath the
+    next round, and `_Pending.resolve()` later tells whether the refined argmax agreed.  Otherwise the pass runs
+    synchronously as without `side` and the fifth value is None."""
     nl = hi - lo
     N = nl * shard.world
     best = _key_score(key)                                                  # [b] global best score
     dist = None
     if shard.world > 1:
         import torch.distributed as dist
-    if delta is None:
+    std = None
+    if delta is None or side is not None:
         mom = torch.stack([scores.sum(0, dtype=torch.float64), (scores.double() ** 2).sum(0)])        # [2, b]
         if dist is not None:
             dist.all_reduce(mom, op=dist.ReduceOp.SUM, group=shard.group)
         mean = mom[0] / N
-        d = (kappa * (mom[1] / N - mean * mean).clamp_min(0).sqrt()).to(torch.float32)
-    else:
-        d = torch.full_like(best, float(delta))
+        std = (mom[1] / N - mean * mean).clamp_min(0).sqrt().to(torch.float32)
+    d = kappa * std if delta is None else torch.full_like(best, float(delta))
     thr = best - d
     # the max_rows-th best score per image, globally: the contender list never grows beyond max_rows per image
     M = min(max_rows, N)
@@ -229,36 +275,73 @@ def _escalate(scorer, stepper: HeunStepper, x_cur, local, scores, key, idx, i, l
         cnt, wide = both[0], both[1]
     multi = cnt > 1                                                         # images whose best has company
     sel = mask & multi.unsqueeze(0)
-    host = torch.cat([sel.reshape(-1).to(torch.float32), (wide > cnt).to(torch.float32), multi.to(torch.float32)]).cpu()   # THE host sync
+    # speculation gate: every image whose best has company must be led by >= spec_gap x std (top = the global top-M scores)
+    clear = ((top[0] - top[1] >= spec_gap * std) | ~multi) if (side is not None and M > 1) else torch.zeros_like(multi)
+    host = torch.cat([sel.reshape(-1).to(torch.float32), (wide > cnt).to(torch.float32), multi.to(torch.float32),
+                      clear.to(torch.float32), ((top[0] - top[1]) / std.clamp_min(1e-30)) if (std is not None and M > 1)
+                      else torch.zeros_like(best)]).cpu()                                              # THE host sync
     m_host = host[:nl * b].bool()
     truncated = bool(host[nl * b:nl * b + b].any())
-    if not bool(host[nl * b + b:].any()):
-        return idx, 0, None, False
+    if not bool(host[nl * b + b:nl * b + 2 * b].any()):
+        return (idx, 0, None, False) if side is None else (idx, 0, None, False, None)
+    speculative = side is not None and bool(host[nl * b + 2 * b:nl * b + 3 * b].all())
+    if log is not None:       # (timestep, lead of the 16-bit winner over the runner-up in score standard deviations, speculated?)
+        log.append((i, [round(float(v), 4) for v in host[nl * b + 3 * b:]], speculative))
     rows = torch.nonzero(m_host).flatten()                                  # row = n_local * b + j
     refined = torch.where(mask & ~multi.unsqueeze(0), scores, torch.full_like(scores, float('-inf')))
     n_rows = int(rows.numel())
-    if n_rows:
-        rows_d = rows.to(scores.device)
-        eps_rows = local.index_select(0, rows_d).contiguous()
-        lab = labels_rows.index_select(0, rows_d) if labels_rows is not None else None
-        row_images = (rows_d % b) if b > 1 else None
-        if getattr(scorer, 'fused_sums', False):
-            _, _, sums = stepper.step(x_cur, eps_rows, i, want_x_next=False, want_sums=True, precise=True, row_images=row_images)
-            s_p = scorer.score_from_sums(sums, C, HW)
-        else:
-            _, u8, _ = stepper.step(x_cur, eps_rows, i, want_x_next=False, want_u8=True, want_sums=False, precise=True,
-                                    row_images=row_images)
-            timesteps = torch.zeros(u8.shape[0], device=u8.device)
-            timesteps._b200_uniform_value = 0.0
-            s_p = torch.as_tensor(scorer(u8, lab, timesteps)).to(device=u8.device, dtype=torch.float32).reshape(-1)
-        refined.view(-1).index_copy_(0, rows_d, s_p.contiguous())
-    idx2, key2 = ops.argmax_first(refined.contiguous(), idx_base=lo, want_key=True)
-    if dist is not None:
-        dist.all_reduce(key2, op=dist.ReduceOp.MAX, group=shard.group)
-        idx2 = 0xFFFFFFFF - (key2 & 0xFFFFFFFF)
-    else:
-        idx2 = idx2 + lo
-    return idx2, n_rows, refined, truncated
+
+    def precise_pass():
+        if n_rows:
+            rows_d = rows.to(scores.device)
+            eps_rows = local.index_select(0, rows_d).contiguous()
+            lab = labels_rows.index_select(0, rows_d) if labels_rows is not None else None
+            row_images = (rows_d % b) if b > 1 else None
+            if getattr(scorer, 'fused_sums', False):
+                _, _, sums = stepper.step(x_cur, eps_rows, i, want_x_next=False, want_sums=True, precise=True, row_images=row_images)
+                s_p = scorer.score_from_sums(sums, C, HW)
+            else:
+                _, u8, _ = stepper.step(x_cur, eps_rows, i, want_x_next=False, want_u8=True, want_sums=False, precise=True,
+                                        row_images=row_images)
+                timesteps = torch.zeros(u8.shape[0], device=u8.device)
+                timesteps._b200_uniform_value = 0.0
+                s_p = torch.as_tensor(scorer(u8, lab, timesteps)).to(device=u8.device, dtype=torch.float32).reshape(-1)
+            refined.view(-1).index_copy_(0, rows_d, s_p.contiguous())
+        return ops.argmax_first(refined.contiguous(), idx_base=lo, want_key=True)
+
+    def reduce_key(idx2, key2):
+        if dist is not None:
+            dist.all_reduce(key2, op=dist.ReduceOp.MAX, group=shard.group)
+            return 0xFFFFFFFF - (key2 & 0xFFFFFFFF)
+        return idx2 + lo
+
+    if not speculative:
+        out = (reduce_key(*precise_pass()), n_rows, refined, truncated)
+        return out if side is None else out + (None,)
+    main = torch.cuda.current_stream(scores.device)
+    ready = torch.cuda.Event()
+    ready.record(main)                     # everything the precise pass reads (x_cur, local, refined) has been enqueued
+    with torch.cuda.stream(side):
+        side.wait_event(ready)
+        idx2, key2 = precise_pass()
+        done = torch.cuda.Event()
+        done.record(side)
+    return idx, n_rows, refined, truncated, _Pending(done, idx2, key2, idx, reduce_key, keep=(x_cur, local, refined, scores))
+
+
+class _Pending:
+    """A precise re-scoring pass in flight on the speculation stream (see eps_greedy_search `speculate`)."""
+
+    def __init__(self, done, idx2, key2, idx_prov, reduce_key, keep):
+        self.done, self.idx2, self.key2, self.idx_prov, self.reduce_key, self.keep = done, idx2, key2, idx_prov, reduce_key, keep
+        self.ctx = None                    # the round's finish context, filled in by the search loop
+
+    def resolve(self) -> Optional[torch.Tensor]:
+        """Wait for the precise pass; None if the refined argmax equals the provisional (16-bit) winner, else the
+        refined winner indices [b] (global).  One host synchronisation."""
+        torch.cuda.current_stream(self.idx2.device).wait_event(self.done)
+        idx_true = self.reduce_key(self.idx2, self.key2)
+        return None if torch.equal(idx_true, self.idx_prov) else idx_true
 
 
 @torch.no_grad()
@@ -270,7 +353,8 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
                       commit: str = 'reuse', mirror_rng: bool = True, prefetch: bool = False,
                       dedupe_noise_free: bool = False, escalate: Optional[bool] = None, delta: Optional[float] = None,
                       kappa: float = ESCALATION_KAPPA, max_contenders: int = MAX_CONTENDERS,
-                      bernoulli_draws: Optional[torch.Tensor] = None) -> (torch.Tensor, SearchRecord):
+                      bernoulli_draws: Optional[torch.Tensor] = None, speculate: Optional[bool] = None,
+                      spec_gap: Optional[float] = None, _spec_sabotage: bool = False) -> (torch.Tensor, SearchRecord):
     """ZERO_ORDER == EPS_GREEDY branch (edm/main.py:714-860).
 
     Extras over the reference (all optional): `shard` (candidate sharding over ranks), `record`,
@@ -298,6 +382,18 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
     N candidates are one tensor -- cost nothing extra; otherwise one host read per round decides which rows to refine (at
     most `max_contenders` per image, best first).  The committed state stays the bf16 engine's x_next of the winner, so
     commit 'reuse' and 'recompute' remain bit-identical.
+
+    `speculate` (default: B200NS_SPECULATE, off -- measured to gain < 1 %, see SPECULATE_DEFAULT): with escalation on and a scorer that works from the fused channel sums
+    (brightness), an escalated round does not wait for its precise pass.  The pass runs on a second, high-priority stream
+    while the main stream starts the next round from the provisional 16-bit winner; after that round's scoring the refined
+    argmax is compared with the provisional one (the one host read an escalated round costs anyway).  Agreement -- every
+    round of the reference fixtures with IEEE-half storage -- means the ~14 ms latency-bound precise pass was hidden behind
+    throughput-bound work; disagreement rolls back: the escalated round's pivot / commit / trace are redone with the
+    refined winner, the RNG state is restored and the next round is re-run.  Either way the results are bit-identical to
+    the synchronous path (tests/test_search_gpu.py::test_speculation_*).  `on_step` of a step that rests on an unverified
+    winner is delivered once it is verified (one round later).  `spec_gap` (default B200NS_SPEC_GAP = 0.08): an escalated
+    round is only speculated past when its 16-bit winner leads the runner-up by that many standard deviations of the round's
+    scores; narrower leads are overturned too often (a wrong guess costs a round) and wait for their precise pass.
 
     `bernoulli_draws` (tests): the uniform draws of edm/main.py:751 in call order, [num_steps*K*N] fp32, used INSTEAD of
     `torch.rand(1, device)` -- a reference run on another device (CPU) drew them from another generator.
@@ -345,115 +441,26 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
         torch.randn_like(x_next)                                          # keeps the RNG stream aligned with :727
     seq = list(step_indices) if step_indices is not None else list(range(num_steps))
     stager = _NoiseStager(pre, device, lo, hi, enabled=prefetch)
-    for pos, i in enumerate(seq):
-        x_cur = x_next
-        if pre is not None and f'pivot_{i}' in pre:                       # :734-737
-            pivot = stager.take(f'pivot_{i}')
-            if pivot is not None:
-                pivot = pivot.clone()             # the staging buffer is recycled two rounds later; pivots may be recorded
-            else:
-                pivot = pre[f'pivot_{i}'].to(device=device, dtype=torch.float64, non_blocking=True)
-            pivot = pivot.contiguous()
-        else:
-            pivot = torch.randn_like(x_cur)
-        for k in range(K):
-            # next round's host noise starts crossing PCIe now, on the side stream
-            stager.prefetch(*((i, k + 1) if k + 1 < K else (seq[pos + 1] if pos + 1 < len(seq) else None, 0)))
-            # ---- candidate construction (:749-800).  RNG calls mirror the reference one for one; the
-            # Bernoulli stays on the device (no host sync) unless precomputed noise covers only one of
-            # the two branches AND 0 < eps < 1, where the reference's RNG consumption is data dependent.
-            bulk = (pre is not None and i in pre and k < pre[i].shape[1] and N <= pre[i].shape[2] and
-                    (eps_p <= 0 or all(f'fresh_{i}_{k}_{n}' in pre for n in range(N))))
-            dirs, fresh, perturb = [], [], []
-            if bulk and bernoulli_draws is not None:
-                r0 = (i * K + k) * N
-                perturb_host = bernoulli_draws[r0:r0 + N].to(torch.float32).cpu().numpy() < np.float32(1 - eps_p)
-            elif bulk and use_mirror:
-                # the N `torch.rand(1)` draws of :751 evaluated on the host from the generator's (seed, offset) --
-                # same values, same final RNG state, no kernels in the stream (philox.py)
-                perturb_host = philox.rand1_sequence(device, N) < np.float32(1 - eps_p)
-            else:
-                perturb_host = None
-                for n in range(N):
-                    p_t = torch.rand(1, device=device) < (1 - eps_p)                  # :751
-                    perturb.append(p_t)
-                    if bulk:
-                        continue
-                    has_dir = pre is not None and i in pre and k < pre[i].shape[1] and n < pre[i].shape[2]
-                    fkey = f'fresh_{i}_{k}_{n}'
-                    has_fresh = pre is not None and fkey in pre
-                    z_dir = pre[i][:, k, n].reshape(pivot.shape) if has_dir else None          # :755-759
-                    z_fresh = pre[fkey] if has_fresh else None                                 # :791-792
-                    if not has_dir and not has_fresh:
-                        z_dir = z_fresh = torch.randn_like(pivot)             # :767 / :795: one draw either way
-                    elif not (has_dir and has_fresh):
-                        branch = True if eps_p <= 0 else (False if eps_p >= 1 else bool(p_t))
-                        if branch and not has_dir:
-                            z_dir = torch.randn_like(pivot)
-                        if not branch and not has_fresh:
-                            z_fresh = torch.randn_like(x_cur)
-                        z_dir = z_dir if z_dir is not None else z_fresh
-                        z_fresh = z_fresh if z_fresh is not None else z_dir
-                    dirs.append(z_dir)
-                    fresh.append(z_fresh)
-            # ---- only this rank's candidates [lo, hi) are materialised (1/G of the transfers and of the fp64 passes)
-            nl = hi - lo
-            if bulk:      # every direction comes from one precomputed tensor: a single (async) transfer of the slice
-                Z = stager.take((i, k))
-                if Z is None:
-                    Z = pre[i][:, k, lo:hi].to(device=device, dtype=torch.float64, non_blocking=True)
-                Z = Z.transpose(0, 1).reshape(nl * b, *pivot.shape[1:]).contiguous()
-                ZF = Z if eps_p <= 0 else torch.stack([pre[f'fresh_{i}_{k}_{n}'].to(device=device, dtype=torch.float64)
-                                                       for n in range(lo, hi)]).reshape(nl * b, *pivot.shape[1:]).contiguous()
-            else:
-                as64 = lambda ts: torch.stack([t.to(device=device, dtype=torch.float64) for t in ts]).reshape(
-                    nl * b, *pivot.shape[1:]).contiguous()
-                Z = as64(dirs[lo:hi])
-                ZF = Z if all(f is d for f, d in zip(fresh[lo:hi], dirs[lo:hi])) else as64(fresh[lo:hi])
-            if perturb_host is not None:
-                if perturb_host[lo:hi].all():
-                    fresh_mask = torch.zeros(nl * b, dtype=torch.uint8, device=device)
-                else:
-                    fresh_mask = torch.from_numpy((~perturb_host[lo:hi]).astype(np.uint8)).to(device).repeat_interleave(b).contiguous()
-            else:
-                fresh_mask = (~torch.cat(perturb[lo:hi])).to(torch.uint8).repeat_interleave(b).contiguous()
-            if norm_mode == 'torch':                                      # strict: the reference's own call (:764)
-                norms = torch.cat([torch.norm(z, p=2, dim=tuple(range(1, z.dim()))) for z in Z.reshape(nl, b, *pivot.shape[1:])]).to(torch.float64)
-            else:
-                norms = ops.direction_norms(Z)
-            sc = scales[i, k, lo:hi].repeat_interleave(b).contiguous()
-            local = ops.make_candidates(pivot, Z, norms, sc, fresh_mask, ZF)      # [(hi-lo)*b, C, H, W]
-            # ---- evaluate this rank's slice: 2 NFE + Tweedie x0 + score (:809-838)
-            want_x = commit == 'reuse' and k == K - 1
-            if dedupe_noise_free and table.steps[i].s == 0.0:
-                # gamma = 0: x_hat = x_cur for every candidate (edm/main.py:83-85), so the N candidates are the same
-                # tensor; the kernels are batch-position invariant, hence N identical scores and identical x_next
-                # (tests: test_noise_free_steps_are_exact_ties).  Evaluate candidate 0 and replicate -- bit-identical.
-                s1, x1 = _score_rows(params.scorer, stepper, x_cur, local[:b], i,
-                                     labels_rows[:b] if labels_rows is not None else None, C, HW, want_x)
-                scores = s1.reshape(1, b).expand(hi - lo, b).contiguous()
-                x_cands = x1.unsqueeze(0).expand(hi - lo, *x1.shape).reshape((hi - lo) * b, *x1.shape[1:]).contiguous() if want_x else None
-            else:
-                scores, x_cands = _score_rows(params.scorer, stepper, x_cur, local, i, labels_rows, C, HW, want_x)
-                scores = scores.reshape(hi - lo, b)
-            rec.scored_candidates += (hi - lo) * b
-            # ---- first-max argmax (+ cross-rank reduction of the packed key) (:842)
-            idx, key = ops.argmax_first(scores, idx_base=lo, want_key=True)
-            if shard.world > 1:
-                import torch.distributed as dist
-                dist.all_reduce(key, op=dist.ReduceOp.MAX, group=shard.group)
-                idx = 0xFFFFFFFF - (key & 0xFFFFFFFF)
-            else:
-                idx = idx + lo
-            # ---- near-tie escalation: re-score the contenders with the fp32-faithful engine, argmax over the refined table
-            n_esc, refined = 0, None
-            if escalate and table.steps[i].s != 0.0:
-                idx, n_esc, refined, trunc = _escalate(params.scorer, stepper, x_cur, local, scores, key, idx, i, lo, hi, b,
-                                                       labels_rows, C, HW, shard, delta, kappa, max_contenders)
-                rec.truncated += int(trunc)
-            rec.escalated.append(n_esc)
+    # ---- speculation past an escalated round (`speculate`): the precise re-scoring of round r runs on a second stream
+    # underneath the 16-bit evaluations of round r+1, which start from the provisional (16-bit) winner; the refined argmax
+    # is checked right after round r+1's scoring and, if it disagrees, round r's outcome is corrected and round r+1 re-run
+    # from the restored RNG state -- results are identical to the synchronous path either way.
+    spec = _speculation_on(speculate, escalate, params.scorer, device)
+    side = _speculation_stream(device) if spec else None
+    rounds = [(pos, i, k) for pos, i in enumerate(seq) for k in (range(K) if K > 0 else (None,))]
+    pending: Optional[_Pending] = None
+    held: List[tuple] = []               # on_step calls of rounds that still rest on an unverified winner
+    x_cur = pivot = None
+
+    def finish(ctx, idx, hold: bool):
+        """Everything of a round that depends on its winner `idx`: the new pivot, the commit at the end of a step, the
+        trace.  Returns (pivot, x_next); called again with the refined winner when a speculation failed."""
+        i, k, x_cur, local, x_cands, scores, pivot = (ctx[n] for n in ('i', 'k', 'x_cur', 'local', 'x_cands', 'scores', 'pivot'))
+        x_next = ctx['x_next']
+        if k is not None:
+            rec.escalated.append(ctx['n_esc'])
             if record:
-                rec.refined.append(refined)
+                rec.refined.append(ctx['refined'])
             # ---- new pivot = the winning candidate (:848-857); it lives on its owner's GPU only: the other ranks
             # contribute zeros to an all_reduce(SUM) (x + 0 is exact), 96 KiB per image over NVLink -- and only when
             # somebody reads it (another local-search round, a recomputed commit, a trace)
@@ -462,6 +469,8 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
             if record:
                 rec.scores.append(scores)
                 rec.indices.append(idx)
+            if k < K - 1:
+                return pivot, x_next
         # ---- commit (:860)
         if commit == 'reuse' and K > 0:
             x_next = _gather_winner(x_cands.reshape(hi - lo, b, *x_cands.shape[1:]), idx, lo, hi, shard)
@@ -471,9 +480,173 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
             rec.pivots.append(pivot)
             rec.x_steps.append(x_next)
         if on_step is not None:
-            on_step(i, x_next, idx, scores)
+            (held.append if hold else (lambda a: on_step(*a)))((i, x_next, idx, scores))
         if teacher_x is not None:
             x_next = teacher_x[i].to(device=device, dtype=torch.float64).contiguous()
+        return pivot, x_next
+
+    def rec_mark():
+        return tuple(len(l) for l in (rec.scores, rec.indices, rec.escalated, rec.refined, rec.pivots, rec.x_steps))
+
+    def rec_rewind(mark):
+        for l, n in zip((rec.scores, rec.indices, rec.escalated, rec.refined, rec.pivots, rec.x_steps), mark):
+            del l[n:]
+
+    def settle(p: _Pending) -> bool:
+        """Verify the speculation `p`; on a miss redo its round's `finish` with the refined winner.  True = it held."""
+        nonlocal pivot, x_next
+        idx_true = p.resolve()
+        if idx_true is None:
+            for call in held:
+                on_step(*call)
+            held.clear()
+            return True
+        rec.mispredicted += 1
+        rec.missed_steps.append(p.ctx['i'])
+        held.clear()
+        rec_rewind(p.ctx['mark'])
+        pivot, x_next = finish(p.ctx, idx_true, False)
+        return False
+
+    r = 0
+    while r < len(rounds):
+        pos, i, k = rounds[r]
+        rng_mark = torch.cuda.get_rng_state(device) if pending is not None else None
+        if k is None or k == 0:
+            x_cur = x_next
+            if pre is not None and f'pivot_{i}' in pre:                       # :734-737
+                pivot = stager.take(f'pivot_{i}')
+                if pivot is not None:
+                    pivot = pivot.clone()             # the staging buffer is recycled two rounds later; pivots may be recorded
+                else:
+                    pivot = pre[f'pivot_{i}'].to(device=device, dtype=torch.float64, non_blocking=True)
+                pivot = pivot.contiguous()
+            else:
+                pivot = torch.randn_like(x_cur)
+        if k is None:                         # K == 0: no search rounds, the pivot is committed as drawn
+            pivot, x_next = finish(dict(i=i, k=None, x_cur=x_cur, local=None, x_cands=None, scores=None, pivot=pivot,
+                                        x_next=x_next), None, False)
+            r += 1
+            continue
+        # next round's host noise starts crossing PCIe now, on the side stream
+        stager.prefetch(*((i, k + 1) if k + 1 < K else (seq[pos + 1] if pos + 1 < len(seq) else None, 0)))
+        # ---- candidate construction (:749-800).  RNG calls mirror the reference one for one; the
+        # Bernoulli stays on the device (no host sync) unless precomputed noise covers only one of
+        # the two branches AND 0 < eps < 1, where the reference's RNG consumption is data dependent.
+        bulk = (pre is not None and i in pre and k < pre[i].shape[1] and N <= pre[i].shape[2] and
+                (eps_p <= 0 or all(f'fresh_{i}_{k}_{n}' in pre for n in range(N))))
+        dirs, fresh, perturb = [], [], []
+        if bulk and bernoulli_draws is not None:
+            r0 = (i * K + k) * N
+            perturb_host = bernoulli_draws[r0:r0 + N].to(torch.float32).cpu().numpy() < np.float32(1 - eps_p)
+        elif bulk and use_mirror:
+            # the N `torch.rand(1)` draws of :751 evaluated on the host from the generator's (seed, offset) --
+            # same values, same final RNG state, no kernels in the stream (philox.py)
+            perturb_host = philox.rand1_sequence(device, N) < np.float32(1 - eps_p)
+        else:
+            perturb_host = None
+            for n in range(N):
+                p_t = torch.rand(1, device=device) < (1 - eps_p)                  # :751
+                perturb.append(p_t)
+                if bulk:
+                    continue
+                has_dir = pre is not None and i in pre and k < pre[i].shape[1] and n < pre[i].shape[2]
+                fkey = f'fresh_{i}_{k}_{n}'
+                has_fresh = pre is not None and fkey in pre
+                z_dir = pre[i][:, k, n].reshape(pivot.shape) if has_dir else None          # :755-759
+                z_fresh = pre[fkey] if has_fresh else None                                 # :791-792
+                if not has_dir and not has_fresh:
+                    z_dir = z_fresh = torch.randn_like(pivot)             # :767 / :795: one draw either way
+                elif not (has_dir and has_fresh):
+                    branch = True if eps_p <= 0 else (False if eps_p >= 1 else bool(p_t))
+                    if branch and not has_dir:
+                        z_dir = torch.randn_like(pivot)
+                    if not branch and not has_fresh:
+                        z_fresh = torch.randn_like(x_cur)
+                    z_dir = z_dir if z_dir is not None else z_fresh
+                    z_fresh = z_fresh if z_fresh is not None else z_dir
+                dirs.append(z_dir)
+                fresh.append(z_fresh)
+        # ---- only this rank's candidates [lo, hi) are materialised (1/G of the transfers and of the fp64 passes)
+        nl = hi - lo
+        if bulk:      # every direction comes from one precomputed tensor: a single (async) transfer of the slice
+            Z = stager.take((i, k))
+            if Z is None:
+                Z = pre[i][:, k, lo:hi].to(device=device, dtype=torch.float64, non_blocking=True)
+            Z = Z.transpose(0, 1).reshape(nl * b, *pivot.shape[1:]).contiguous()
+            ZF = Z if eps_p <= 0 else torch.stack([pre[f'fresh_{i}_{k}_{n}'].to(device=device, dtype=torch.float64)
+                                                   for n in range(lo, hi)]).reshape(nl * b, *pivot.shape[1:]).contiguous()
+        else:
+            as64 = lambda ts: torch.stack([t.to(device=device, dtype=torch.float64) for t in ts]).reshape(
+                nl * b, *pivot.shape[1:]).contiguous()
+            Z = as64(dirs[lo:hi])
+            ZF = Z if all(f is d for f, d in zip(fresh[lo:hi], dirs[lo:hi])) else as64(fresh[lo:hi])
+        if perturb_host is not None:
+            if perturb_host[lo:hi].all():
+                fresh_mask = torch.zeros(nl * b, dtype=torch.uint8, device=device)
+            else:
+                fresh_mask = torch.from_numpy((~perturb_host[lo:hi]).astype(np.uint8)).to(device).repeat_interleave(b).contiguous()
+        else:
+            fresh_mask = (~torch.cat(perturb[lo:hi])).to(torch.uint8).repeat_interleave(b).contiguous()
+        if norm_mode == 'torch':                                      # strict: the reference's own call (:764)
+            norms = torch.cat([torch.norm(z, p=2, dim=tuple(range(1, z.dim()))) for z in Z.reshape(nl, b, *pivot.shape[1:])]).to(torch.float64)
+        else:
+            norms = ops.direction_norms(Z)
+        sc = scales[i, k, lo:hi].repeat_interleave(b).contiguous()
+        local = ops.make_candidates(pivot, Z, norms, sc, fresh_mask, ZF)      # [(hi-lo)*b, C, H, W]
+        # ---- evaluate this rank's slice: 2 NFE + Tweedie x0 + score (:809-838)
+        want_x = commit == 'reuse' and k == K - 1
+        if dedupe_noise_free and table.steps[i].s == 0.0:
+            # gamma = 0: x_hat = x_cur for every candidate (edm/main.py:83-85), so the N candidates are the same
+            # tensor; the kernels are batch-position invariant, hence N identical scores and identical x_next
+            # (tests: test_noise_free_steps_are_exact_ties).  Evaluate candidate 0 and replicate -- bit-identical.
+            s1, x1 = _score_rows(params.scorer, stepper, x_cur, local[:b], i,
+                                 labels_rows[:b] if labels_rows is not None else None, C, HW, want_x)
+            scores = s1.reshape(1, b).expand(hi - lo, b).contiguous()
+            x_cands = x1.unsqueeze(0).expand(hi - lo, *x1.shape).reshape((hi - lo) * b, *x1.shape[1:]).contiguous() if want_x else None
+        else:
+            scores, x_cands = _score_rows(params.scorer, stepper, x_cur, local, i, labels_rows, C, HW, want_x)
+            scores = scores.reshape(hi - lo, b)
+        rec.scored_candidates += (hi - lo) * b
+        # ---- first-max argmax (+ cross-rank reduction of the packed key) (:842)
+        idx, key = ops.argmax_first(scores, idx_base=lo, want_key=True)
+        if shard.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(key, op=dist.ReduceOp.MAX, group=shard.group)
+            idx = 0xFFFFFFFF - (key & 0xFFFFFFFF)
+        else:
+            idx = idx + lo
+        # ---- the previous round's speculation is settled here: its precise pass ran underneath this round's evaluations
+        if pending is not None:
+            p, pending = pending, None
+            if not settle(p):
+                # the refined winner differs: pivot / x_next have been corrected, this round ran on the wrong state -> redo
+                rec.scored_candidates -= (hi - lo) * b
+                torch.cuda.set_rng_state(rng_mark, device)
+                continue
+        # ---- near-tie escalation: re-score the contenders with the fp32-faithful engine, argmax over the refined table
+        n_esc, refined = 0, None
+        if escalate and table.steps[i].s != 0.0:
+            if spec:
+                idx, n_esc, refined, trunc, pending = _escalate(params.scorer, stepper, x_cur, local, scores, key, idx, i, lo, hi,
+                                                                b, labels_rows, C, HW, shard, delta, kappa, max_contenders,
+                                                                side=side, spec_gap=SPEC_GAP if spec_gap is None else spec_gap,
+                                                                log=rec.escalation_log)
+                if pending is not None and _spec_sabotage:
+                    idx = (idx + 1) % N          # tests: a wrong provisional winner forces the rollback path
+                    pending.idx_prov = idx
+            else:
+                idx, n_esc, refined, trunc = _escalate(params.scorer, stepper, x_cur, local, scores, key, idx, i, lo, hi, b,
+                                                       labels_rows, C, HW, shard, delta, kappa, max_contenders)
+            rec.truncated += int(trunc)
+        ctx = dict(i=i, k=k, x_cur=x_cur, local=local, x_cands=x_cands, scores=scores, pivot=pivot, x_next=x_next,
+                   n_esc=n_esc, refined=refined, mark=rec_mark())
+        if pending is not None:
+            pending.ctx = ctx
+        pivot, x_next = finish(ctx, idx, pending is not None)
+        r += 1
+    if pending is not None:
+        settle(pending)
     return x_next, rec
 
 

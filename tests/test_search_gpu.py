@@ -340,3 +340,68 @@ def test_noise_free_dedupe_is_bit_identical(pkg):
     assert torch.equal(out[0][0], out[1][0])
     for j in (1, 2, 3):
         assert all(torch.equal(a, b) for a, b in zip(out[0][j], out[1][j]))
+
+
+def _speculation_runs(pkg, *, eps, precomputed, K_override=None, b_images=None):
+    """The same free-running search three ways: synchronous escalation, speculation, speculation with a sabotaged
+    (always wrong) provisional winner -- delta is huge, so every noisy round escalates with max_contenders rows."""
+    den, em, sc = pkg
+    g = load_golden('search_eps_greedy_tiny.pt')
+    onet, spec, sd = oracle_net(g['cfg'], g['seed'])
+    latents, labels, pre = search_inputs(g)
+    net = den.B200Denoiser(sd, device='cuda')
+    assert net.supports_precise
+    table = den.StepTable(net, 'cuda', g['num_steps'], **g['sampler_kw'])
+    K = K_override or g['K']
+    params = em.SamplingParams(N=g['N'], K=K, eps=eps, lambda_param=g['lambda_param'], scorer=sc.BrightnessScorer())
+    noise = {k: v.cuda() for k, v in pre.items()} if precomputed else None
+    out = {}
+    for mode, kw in (('sync', dict(speculate=False)), ('spec', dict(speculate=True, spec_gap=0.0)),
+                     ('miss', dict(speculate=True, spec_gap=0.0, _spec_sabotage=True)), ('gate', dict(speculate=True, spec_gap=1e9))):
+        torch.manual_seed(11)
+        calls = []
+        x, rec = em.eps_greedy_search(net, latents.cuda(), labels.cuda(), params, table, precomputed_noise=noise,
+                                      record=True, escalate=True, delta=1e9, max_contenders=3,
+                                      on_step=lambda i, xn, idx, s: calls.append((i, xn.clone(), idx.clone())), **kw)
+        torch.cuda.synchronize()
+        out[mode] = dict(x=x.cpu(), idx=[t.cpu() for t in rec.indices], scores=[t.cpu() for t in rec.scores],
+                         refined=[None if t is None else t.cpu() for t in rec.refined], esc=list(rec.escalated),
+                         xs=[t.cpu() for t in rec.x_steps], piv=[t.cpu() for t in rec.pivots],
+                         rng=torch.rand(4, device='cuda').cpu(), calls=[(i, a.cpu(), c.cpu()) for i, a, c in calls],
+                         n=rec.scored_candidates, miss=rec.mispredicted)
+    return g, K, out
+
+
+def _assert_same_run(a, b):
+    assert torch.equal(a['x'], b['x'])
+    assert a['esc'] == b['esc'] and a['n'] == b['n']
+    for key in ('idx', 'scores', 'xs', 'piv'):
+        assert len(a[key]) == len(b[key]) and all(torch.equal(u, v) for u, v in zip(a[key], b[key])), key
+    assert len(a['refined']) == len(b['refined'])
+    for u, v in zip(a['refined'], b['refined']):
+        assert (u is None) == (v is None) and (u is None or torch.equal(u, v))
+    assert torch.equal(a['rng'], b['rng'])
+    assert len(a['calls']) == len(b['calls'])
+    for (i, xa, ia), (j, xb, ib) in zip(a['calls'], b['calls']):
+        assert i == j and torch.equal(xa, xb) and torch.equal(ia, ib)
+
+
+@pytest.mark.parametrize('eps,precomputed,K', [(0.0, True, None), (0.4, False, 2), (0.4, True, 1)])
+def test_speculation_past_escalated_rounds_is_bit_identical(pkg, eps, precomputed, K):
+    """`speculate`: the precise pass of an escalated round runs on a second stream while the next round starts from the
+    provisional 16-bit winner.  Whether the speculation holds ('spec': never rolled back unless the 16-bit winner really
+    loses) or every escalated round is rolled back ('miss': sabotaged provisional winner -> corrected pivot / commit /
+    trace, restored RNG state, next round re-run), indices, scores, refined tables, committed states, pivots, the on_step
+    sequence, the candidate count and the RNG state afterwards equal the synchronous run's -- with device RNG draws in the
+    loop (no precomputed noise, eps = 0.4) and K = 2 local-search rounds too."""
+    g, K, out = _speculation_runs(pkg, eps=eps, precomputed=precomputed, K_override=K)
+    assert sum(out['sync']['esc']) > 0, 'the run must escalate'
+    assert out['sync']['miss'] == 0
+    _assert_same_run(out['sync'], out['spec'])
+    _assert_same_run(out['sync'], out['miss'])
+    _assert_same_run(out['sync'], out['gate'])         # a lead nobody reaches: every escalated round waits (synchronous)
+    assert out['gate']['miss'] == 0
+    n_escalated_rounds = sum(1 for e in out['sync']['esc'] if e > 0)
+    # (a sabotaged winner coincides with the refined one now and then: N = 4)
+    assert 1 <= out['miss']['miss'] <= n_escalated_rounds and out['spec']['miss'] <= n_escalated_rounds
+    assert len(out['sync']['calls']) == g['num_steps']

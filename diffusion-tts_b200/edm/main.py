@@ -585,7 +585,11 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
             if perturb_host[lo:hi].all():
                 fresh_mask = torch.zeros(nl * b, dtype=torch.uint8, device=device)
             else:
-                fresh_mask = torch.from_numpy((~perturb_host[lo:hi]).astype(np.uint8)).to(device).repeat_interleave(b).contiguous()
+                # pinned + non_blocking: a copy from pageable memory is a synchronous cudaMemcpy that drains the stream every
+                # round (measured: eps = 0.4 at 39-46 ms per step depending on the box's host; the pinned block is recycled
+                # by torch's caching host allocator only after the copy has completed)
+                fresh_mask = torch.from_numpy((~perturb_host[lo:hi]).astype(np.uint8)).pin_memory().to(
+                    device, non_blocking=True).repeat_interleave(b).contiguous()
         else:
             fresh_mask = (~torch.cat(perturb[lo:hi])).to(torch.uint8).repeat_interleave(b).contiguous()
         if norm_mode == 'torch':                                      # strict: the reference's own call (:764)

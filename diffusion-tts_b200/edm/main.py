@@ -508,12 +508,20 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
         pivot, x_next = finish(p.ctx, idx_true, False)
         return False
 
-    r = 0
-    while r < len(rounds):
+    # ---- a round's noise inputs (pivot draw of a new step, directions, fresh noises, Bernoulli mask, direction norms) do not
+    # depend on any winner: they are prepared -- RNG draws in the reference's order, uploads, norms -- one round AHEAD, right
+    # after the previous round's evaluation has been enqueued and before its escalation decision synchronises with the host,
+    # so that the host-side work (64 dictionary lookups and a stack per round with eps > 0, the Philox mirror, ...) runs
+    # underneath the GPU's work instead of in the bubble behind the synchronisation (0.5-0.7 ms of host time per round).
+    # A re-run round (speculation miss) reuses its prepared inputs: no RNG state to restore.
+    tmpl = x_next                        # shape / dtype of one image batch: fp64 [b, C, H, W]
+    prepared: Dict[int, dict] = {}
+
+    def prepare(r: int) -> dict:
         pos, i, k = rounds[r]
-        rng_mark = torch.cuda.get_rng_state(device) if pending is not None else None
+        out = {}
+        x_cur = tmpl                     # only shapes / dtypes are taken from these two below
         if k is None or k == 0:
-            x_cur = x_next
             if pre is not None and f'pivot_{i}' in pre:                       # :734-737
                 pivot = stager.take(f'pivot_{i}')
                 if pivot is not None:
@@ -523,11 +531,10 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
                 pivot = pivot.contiguous()
             else:
                 pivot = torch.randn_like(x_cur)
-        if k is None:                         # K == 0: no search rounds, the pivot is committed as drawn
-            pivot, x_next = finish(dict(i=i, k=None, x_cur=x_cur, local=None, x_cands=None, scores=None, pivot=pivot,
-                                        x_next=x_next), None, False)
-            r += 1
-            continue
+            out['pivot0'] = pivot
+        if k is None:
+            return out
+        pivot = tmpl
         # next round's host noise starts crossing PCIe now, on the side stream
         stager.prefetch(*((i, k + 1) if k + 1 < K else (seq[pos + 1] if pos + 1 < len(seq) else None, 0)))
         # ---- candidate construction (:749-800).  RNG calls mirror the reference one for one; the
@@ -585,9 +592,8 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
             if perturb_host[lo:hi].all():
                 fresh_mask = torch.zeros(nl * b, dtype=torch.uint8, device=device)
             else:
-                # pinned + non_blocking: a copy from pageable memory is a synchronous cudaMemcpy that drains the stream every
-                # round (measured: eps = 0.4 at 39-46 ms per step depending on the box's host; the pinned block is recycled
-                # by torch's caching host allocator only after the copy has completed)
+                # pinned + non_blocking: a copy from pageable memory is a synchronous cudaMemcpy (the pinned block is recycled by
+                # torch's caching host allocator only after the copy has completed)
                 fresh_mask = torch.from_numpy((~perturb_host[lo:hi]).astype(np.uint8)).pin_memory().to(
                     device, non_blocking=True).repeat_interleave(b).contiguous()
         else:
@@ -597,7 +603,26 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
         else:
             norms = ops.direction_norms(Z)
         sc = scales[i, k, lo:hi].repeat_interleave(b).contiguous()
-        local = ops.make_candidates(pivot, Z, norms, sc, fresh_mask, ZF)      # [(hi-lo)*b, C, H, W]
+        out.update(Z=Z, ZF=ZF, fresh_mask=fresh_mask, norms=norms, sc=sc)
+        return out
+
+    r = 0
+    while r < len(rounds):
+        pos, i, k = rounds[r]
+        if r not in prepared:
+            prepared[r] = prepare(r)
+        inp = prepared[r]
+        if k is None or k == 0:
+            x_cur = x_next
+            pivot = inp['pivot0']
+        if k is None:                         # K == 0: no search rounds, the pivot is committed as drawn
+            pivot, x_next = finish(dict(i=i, k=None, x_cur=x_cur, local=None, x_cands=None, scores=None, pivot=pivot,
+                                        x_next=x_next), None, False)
+            prepared.pop(r, None)
+            r += 1
+            continue
+        nl = hi - lo
+        local = ops.make_candidates(pivot, inp['Z'], inp['norms'], inp['sc'], inp['fresh_mask'], inp['ZF'])      # [(hi-lo)*b, C, H, W]
         # ---- evaluate this rank's slice: 2 NFE + Tweedie x0 + score (:809-838)
         want_x = commit == 'reuse' and k == K - 1
         if dedupe_noise_free and table.steps[i].s == 0.0:
@@ -626,8 +651,9 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
             if not settle(p):
                 # the refined winner differs: pivot / x_next have been corrected, this round ran on the wrong state -> redo
                 rec.scored_candidates -= (hi - lo) * b
-                torch.cuda.set_rng_state(rng_mark, device)
                 continue
+        if r + 1 < len(rounds) and (r + 1) not in prepared:
+            prepared[r + 1] = prepare(r + 1)          # the next round's noise inputs, ahead of the host synchronisation below
         # ---- near-tie escalation: re-score the contenders with the fp32-faithful engine, argmax over the refined table
         n_esc, refined = 0, None
         if escalate and table.steps[i].s != 0.0:
@@ -648,6 +674,7 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
         if pending is not None:
             pending.ctx = ctx
         pivot, x_next = finish(ctx, idx, pending is not None)
+        prepared.pop(r, None)
         r += 1
     if pending is not None:
         settle(pending)

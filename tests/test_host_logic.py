@@ -296,3 +296,117 @@ def test_engine_configs_are_inferred_from_state_dict_shapes():
     from diffusion_tts_b200.sd.pipeline import pseudo_prompt_embeddings
     e1, e2 = pseudo_prompt_embeddings('a photo of a cat'), pseudo_prompt_embeddings('a photo of a cat')
     assert e1.shape == (2, 77, 768) and torch.equal(e1, e2) and not torch.equal(e1[0], e1[1])
+
+
+class _StubStep:
+    def __init__(self, s):
+        self.s = s
+
+
+class _StubTable:
+    def __init__(self, num_steps, noisy):
+        self.num_steps = num_steps
+        self.t_steps = torch.linspace(80.0, 0.0, num_steps + 1, dtype=torch.float64)
+        self.steps = [_StubStep(1.0 if i in noisy else 0.0) for i in range(num_steps)]
+
+
+class _StubNet:
+    device = torch.device('cpu')
+    label_dim = 0
+    supports_precise = False
+
+
+@pytest.mark.parametrize('eps,K,precomputed', [(0.0, 1, True), (0.4, 2, False), (1.0, 1, False), (0.4, 1, True), (0.0, 0, False)])
+def test_search_loop_control_flow_with_stub_kernels(monkeypatch, eps, K, precomputed):
+    """The eps_greedy / zero_order driver (edm/main.py:714-860) on CPU with the CUDA entry points replaced by torch
+    one-liners (test harness only): the loop's own logic -- flat rounds, noise inputs prepared one round ahead, first-max
+    argmax, pivot hand-over between local-search rounds, commit, trace, on_step order -- against a direct transcription of
+    the reference's loop on the same stub denoiser, incl. the RNG call order (the generator state afterwards is equal)."""
+    import numpy as np
+    import diffusion_tts_b200.edm.main as em
+    from diffusion_tts_b200 import ops
+
+    def stub_step(x_cur, eps_rows, i):                 # any deterministic map (x_cur, noise, step) -> (x_next, score)
+        x = x_cur.repeat(eps_rows.shape[0] // x_cur.shape[0], 1, 1, 1) * 0.9 + 0.1 * (i + 1) * eps_rows
+        return x, torch.tanh(x).mean(dim=(1, 2, 3)).to(torch.float32)
+
+    monkeypatch.setattr(ops, 'direction_norms', lambda Z: Z.flatten(1).norm(dim=1))
+    monkeypatch.setattr(ops, 'make_candidates', lambda pivot, Z, norms, sc, mask, ZF: torch.where(
+        mask.bool().view(-1, 1, 1, 1), ZF, pivot.repeat(Z.shape[0] // pivot.shape[0], 1, 1, 1) +
+        sc.view(-1, 1, 1, 1).to(torch.float32) * Z / norms.view(-1, 1, 1, 1)))
+    monkeypatch.setattr(ops, 'argmax_first', lambda s, idx_base=0, want_key=False: (
+        (s.argmax(dim=0), torch.zeros(s.shape[1], dtype=torch.int64)) if want_key else s.argmax(dim=0)))
+    monkeypatch.setattr(ops, 'gather_rows', lambda rows, idx: rows[idx, torch.arange(rows.shape[1])].contiguous())
+    monkeypatch.setattr(em, '_score_rows', lambda scorer, stepper, x_cur, e, i, lab, C, HW, want_x=False:
+                        (lambda xs: (xs[1], xs[0] if want_x else None))(stub_step(x_cur, e, i)))
+
+    class Stepper:
+        def __init__(self, *a):
+            pass
+
+        def step(self, x_cur, e, i, want_x_next=True, **kw):
+            return stub_step(x_cur, e, i)[0], None, None
+    monkeypatch.setattr(em, 'HeunStepper', Stepper)
+
+    N, steps, b = 5, 4, 2
+    g = torch.Generator().manual_seed(3)
+    latents = torch.randn(b, 3, 8, 8, generator=g)
+    pre = None
+    if precomputed:
+        pre = {}
+        for i in range(steps):
+            pre[f'pivot_{i}'] = torch.randn(b, 3, 8, 8, generator=g, dtype=torch.float64)
+            pre[i] = torch.randn(b, max(K, 1), N, 3, 8, 8, generator=g, dtype=torch.float64)
+            if eps > 0:
+                for k in range(K):
+                    for n in range(N):
+                        pre[f'fresh_{i}_{k}_{n}'] = torch.randn(b, 3, 8, 8, generator=g, dtype=torch.float64)
+    table = _StubTable(steps, noisy={0, 1, 2})
+    lam = 0.15 * np.sqrt(3 * 64 * 64)
+    scales = torch.rand(steps, max(K, 1), N, generator=g).to(torch.float32)
+    params = em.SamplingParams(N=N, K=K, eps=eps, lambda_param=0.15, scorer=object())
+    calls = []
+    torch.manual_seed(21)
+    x, rec = em.eps_greedy_search(_StubNet(), latents, None, params, table, precomputed_noise=pre, record=True,
+                                  scale_table=scales, commit='recompute' if K == 0 else 'reuse',
+                                  on_step=lambda i, xn, idx, s: calls.append((i, xn.clone())))
+    rng_after = torch.rand(3)
+
+    # ---- the reference's loop, transcribed (edm/main.py:724-860), on the same stub
+    torch.manual_seed(21)
+    xr = latents.to(torch.float64) * table.t_steps[0]
+    torch.randn_like(xr)                                                    # :727
+    idx_ref, x_ref = [], []
+    for i in range(steps):
+        x_cur = xr
+        pivot = pre[f'pivot_{i}'] if pre is not None else torch.randn_like(x_cur)
+        for k in range(K):
+            cands = []
+            for n in range(N):
+                perturb = bool(torch.rand(1) < (1 - eps))                   # :751
+                if pre is not None:
+                    z = pre[i][:, k, n]
+                    zf = pre.get(f'fresh_{i}_{k}_{n}', z)
+                else:
+                    z = zf = torch.randn_like(pivot)                        # :767 / :795
+                if perturb:
+                    nrm = z.flatten(1).norm(dim=1).view(-1, 1, 1, 1)
+                    cands.append(pivot + scales[i, k, n] * z / nrm)
+                else:
+                    cands.append(zf)
+            allc = torch.cat(cands, dim=0)
+            xc, sc = stub_step(x_cur, allc, i)
+            best = sc.reshape(N, b).argmax(dim=0)
+            pivot = torch.stack([allc.reshape(N, b, *allc.shape[1:])[best[j], j] for j in range(b)])
+            idx_ref.append(best)
+        xr = stub_step(x_cur, pivot, i)[0]                                  # :860
+        x_ref.append(xr)
+    assert len(rec.indices) == len(idx_ref) == steps * K
+    for a, r_ in zip(rec.indices, idx_ref):
+        assert torch.equal(a, r_)
+    for a, r_ in zip(rec.x_steps, x_ref):
+        assert torch.allclose(a, r_, rtol=0, atol=1e-12)
+    assert torch.allclose(x, xr, rtol=0, atol=1e-12)
+    assert [c[0] for c in calls] == list(range(steps)) and all(torch.equal(c[1], xs) for c, xs in zip(calls, rec.x_steps))
+    assert torch.equal(rng_after, torch.rand(3)), 'the RNG stream must be where the reference loop leaves it'
+    assert rec.scored_candidates == steps * K * N * b

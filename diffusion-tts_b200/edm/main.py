@@ -389,7 +389,8 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
     argmax is compared with the provisional one (the one host read an escalated round costs anyway).  Agreement -- every
     round of the reference fixtures with IEEE-half storage -- means the ~14 ms latency-bound precise pass was hidden behind
     throughput-bound work; disagreement rolls back: the escalated round's pivot / commit / trace are redone with the
-    refined winner, the RNG state is restored and the next round is re-run.  Either way the results are bit-identical to
+    refined winner and the next round is re-run on the noise inputs already prepared for it (they do not depend on any winner,
+    so no RNG state has to be restored).  Either way the results are bit-identical to
     the synchronous path (tests/test_search_gpu.py::test_speculation_*).  `on_step` of a step that rests on an unverified
     winner is delivered once it is verified (one round later).  `spec_gap` (default B200NS_SPEC_GAP = 0.08): an escalated
     round is only speculated past when its 16-bit winner leads the runner-up by that many standard deviations of the round's
@@ -444,7 +445,7 @@ def eps_greedy_search(net: B200Denoiser, latents, class_labels, params: Sampling
     # ---- speculation past an escalated round (`speculate`): the precise re-scoring of round r runs on a second stream
     # underneath the 16-bit evaluations of round r+1, which start from the provisional (16-bit) winner; the refined argmax
     # is checked right after round r+1's scoring and, if it disagrees, round r's outcome is corrected and round r+1 re-run
-    # from the restored RNG state -- results are identical to the synchronous path either way.
+    # on its (winner-independent, already prepared) noise inputs -- results are identical to the synchronous path either way.
     spec = _speculation_on(speculate, escalate, params.scorer, device)
     side = _speculation_stream(device) if spec else None
     rounds = [(pos, i, k) for pos, i in enumerate(seq) for k in (range(K) if K > 0 else (None,))]

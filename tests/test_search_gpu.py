@@ -391,7 +391,7 @@ def test_speculation_past_escalated_rounds_is_bit_identical(pkg, eps, precompute
     """`speculate`: the precise pass of an escalated round runs on a second stream while the next round starts from the
     provisional 16-bit winner.  Whether the speculation holds ('spec': never rolled back unless the 16-bit winner really
     loses) or every escalated round is rolled back ('miss': sabotaged provisional winner -> corrected pivot / commit /
-    trace, restored RNG state, next round re-run), indices, scores, refined tables, committed states, pivots, the on_step
+    trace, next round re-run on its prepared noise inputs), indices, scores, refined tables, committed states, pivots, the on_step
     sequence, the candidate count and the RNG state afterwards equal the synchronous run's -- with device RNG draws in the
     loop (no precomputed noise, eps = 0.4) and K = 2 local-search rounds too."""
     g, K, out = _speculation_runs(pkg, eps=eps, precomputed=precomputed, K_override=K)

@@ -316,6 +316,43 @@ class _StubNet:
     supports_precise = False
 
 
+def _stub_step(x_cur, eps_rows, i):                     # any deterministic map (x_cur, noise, step) -> (x_next, score)
+    x = x_cur.repeat(eps_rows.shape[0] // x_cur.shape[0], 1, 1, 1) * 0.9 + 0.1 * (i + 1) * eps_rows
+    return x, torch.tanh(x).mean(dim=(1, 2, 3)).to(torch.float32)
+
+
+def _install_stub_kernels(setattr_):
+    """Replace the CUDA entry points the search loop calls by torch one-liners (test harness only; `setattr_(obj, name,
+    value)` is monkeypatch.setattr or plain setattr in a spawned worker)."""
+    import diffusion_tts_b200.edm.main as em
+    from diffusion_tts_b200 import ops
+    from diffusion_tts_b200.sharding import pack_key
+
+    def argmax_first(s, idx_base=0, want_key=False):
+        n, b = s.shape
+        key = pack_key(s, (idx_base + torch.arange(n)).unsqueeze(1).expand(-1, b)).max(dim=0).values
+        idx = (0xFFFFFFFF - (key & 0xFFFFFFFF)) - idx_base            # local index, like the kernel
+        return (idx, key) if want_key else idx
+
+    class Stepper:
+        def __init__(self, *a):
+            pass
+
+        def step(self, x_cur, e, i, want_x_next=True, **kw):
+            return _stub_step(x_cur, e, i)[0], None, None
+
+    setattr_(ops, 'direction_norms', lambda Z: Z.flatten(1).norm(dim=1))
+    setattr_(ops, 'make_candidates', lambda pivot, Z, norms, sc, mask, ZF: torch.where(
+        mask.bool().view(-1, 1, 1, 1), ZF, pivot.repeat(Z.shape[0] // pivot.shape[0], 1, 1, 1) +
+        sc.view(-1, 1, 1, 1).to(torch.float32) * Z / norms.view(-1, 1, 1, 1)))
+    setattr_(ops, 'argmax_first', argmax_first)
+    setattr_(ops, 'gather_rows', lambda rows, idx: rows[idx, torch.arange(rows.shape[1])].contiguous())
+    setattr_(em, '_score_rows', lambda scorer, stepper, x_cur, e, i, lab, C, HW, want_x=False:
+             (lambda xs: (xs[1], xs[0] if want_x else None))(_stub_step(x_cur, e, i)))
+    setattr_(em, 'HeunStepper', Stepper)
+    return _stub_step
+
+
 @pytest.mark.parametrize('eps,K,precomputed', [(0.0, 1, True), (0.4, 2, False), (1.0, 1, False), (0.4, 1, True), (0.0, 0, False)])
 def test_search_loop_control_flow_with_stub_kernels(monkeypatch, eps, K, precomputed):
     """The eps_greedy / zero_order driver (edm/main.py:714-860) on CPU with the CUDA entry points replaced by torch
@@ -326,27 +363,7 @@ def test_search_loop_control_flow_with_stub_kernels(monkeypatch, eps, K, precomp
     import diffusion_tts_b200.edm.main as em
     from diffusion_tts_b200 import ops
 
-    def stub_step(x_cur, eps_rows, i):                 # any deterministic map (x_cur, noise, step) -> (x_next, score)
-        x = x_cur.repeat(eps_rows.shape[0] // x_cur.shape[0], 1, 1, 1) * 0.9 + 0.1 * (i + 1) * eps_rows
-        return x, torch.tanh(x).mean(dim=(1, 2, 3)).to(torch.float32)
-
-    monkeypatch.setattr(ops, 'direction_norms', lambda Z: Z.flatten(1).norm(dim=1))
-    monkeypatch.setattr(ops, 'make_candidates', lambda pivot, Z, norms, sc, mask, ZF: torch.where(
-        mask.bool().view(-1, 1, 1, 1), ZF, pivot.repeat(Z.shape[0] // pivot.shape[0], 1, 1, 1) +
-        sc.view(-1, 1, 1, 1).to(torch.float32) * Z / norms.view(-1, 1, 1, 1)))
-    monkeypatch.setattr(ops, 'argmax_first', lambda s, idx_base=0, want_key=False: (
-        (s.argmax(dim=0), torch.zeros(s.shape[1], dtype=torch.int64)) if want_key else s.argmax(dim=0)))
-    monkeypatch.setattr(ops, 'gather_rows', lambda rows, idx: rows[idx, torch.arange(rows.shape[1])].contiguous())
-    monkeypatch.setattr(em, '_score_rows', lambda scorer, stepper, x_cur, e, i, lab, C, HW, want_x=False:
-                        (lambda xs: (xs[1], xs[0] if want_x else None))(stub_step(x_cur, e, i)))
-
-    class Stepper:
-        def __init__(self, *a):
-            pass
-
-        def step(self, x_cur, e, i, want_x_next=True, **kw):
-            return stub_step(x_cur, e, i)[0], None, None
-    monkeypatch.setattr(em, 'HeunStepper', Stepper)
+    stub_step = _install_stub_kernels(monkeypatch.setattr)
 
     N, steps, b = 5, 4, 2
     g = torch.Generator().manual_seed(3)
@@ -410,3 +427,54 @@ def test_search_loop_control_flow_with_stub_kernels(monkeypatch, eps, K, precomp
     assert [c[0] for c in calls] == list(range(steps)) and all(torch.equal(c[1], xs) for c, xs in zip(calls, rec.x_steps))
     assert torch.equal(rng_after, torch.rand(3)), 'the RNG stream must be where the reference loop leaves it'
     assert rec.scored_candidates == steps * K * N * b
+
+
+def _gloo_search_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import diffusion_tts_b200.edm.main as em
+    dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
+    _install_stub_kernels(setattr)
+    N, K, steps, b = 8, 2, 4, 2
+    g = torch.Generator().manual_seed(9)
+    latents = torch.randn(b, 3, 8, 8, generator=g)
+    pre = {}
+    for i in range(steps):
+        pre[f'pivot_{i}'] = torch.randn(b, 3, 8, 8, generator=g, dtype=torch.float64)
+        pre[i] = torch.randn(b, K, N, 3, 8, 8, generator=g, dtype=torch.float64)
+        pre[i][:, :, 5] = pre[i][:, :, 2]                     # identical candidates on DIFFERENT shards: index 2 must win ties
+    scales = torch.rand(steps, K, N, generator=g).to(torch.float32)
+    scales[:, :, 5] = scales[:, :, 2]
+    table = _StubTable(steps, noisy={0, 1, 2})
+    params = em.SamplingParams(N=N, K=K, eps=0.0, lambda_param=0.15, scorer=object())
+    out = {}
+    for name, sh in (('sharded', em.Shard(rank, world, None)), ('single', em.Shard())):
+        torch.manual_seed(4)
+        x, rec = em.eps_greedy_search(_StubNet(), latents, None, params, table, precomputed_noise=pre, record=True,
+                                      scale_table=scales.clone(), shard=sh)
+        out[name] = (x, [t.clone() for t in rec.indices], [t.clone() for t in rec.x_steps], [t.clone() for t in rec.pivots],
+                     rec.scored_candidates)
+    same = (torch.equal(out['sharded'][0], out['single'][0]) and
+            all(torch.equal(a, c) for j in (1, 2, 3) for a, c in zip(out['sharded'][j], out['single'][j])))
+    q.put((rank, same, out['sharded'][4], out['single'][4], [t.tolist() for t in out['single'][1]]))
+    dist.destroy_process_group()
+
+
+def test_sharded_search_loop_gloo_world2_equals_unsharded():
+    """8(e) on CPU: the whole eps_greedy / zero_order driver with the candidates sharded over 2 gloo ranks (stub kernels) --
+    rank 0's scale table broadcast, per-rank candidate slices, packed-key all_reduce(MAX) with the first-index tie rule
+    across shards, winner exchange for the pivot of the next local-search round and for the commit -- gives every rank the
+    indices, pivots and committed states of the unsharded run, bit for bit, while scoring half of the candidates."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 137) % 1000
+    procs = [ctx.Process(target=_gloo_search_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, same, n_sh, n_one, idx in res:
+        assert same, rank
+        assert n_sh * 2 == n_one == 4 * 2 * 8 * 2
+        assert all(5 not in row for row in idx)                # the duplicate on the other shard never beats index 2

@@ -316,9 +316,28 @@ class _StubNet:
     supports_precise = False
 
 
+def _true_score(x):
+    return torch.tanh(x).mean(dim=(1, 2, 3)).to(torch.float32)
+
+
+_STUB_NOISE = {0: 0.0}    # amplitude of the stand-in for the 16-bit engine's candidate-dependent score noise
+
+
 def _stub_step(x_cur, eps_rows, i):                     # any deterministic map (x_cur, noise, step) -> (x_next, score)
-    x = x_cur.repeat(eps_rows.shape[0] // x_cur.shape[0], 1, 1, 1) * 0.9 + 0.1 * (i + 1) * eps_rows
-    return x, torch.tanh(x).mean(dim=(1, 2, 3)).to(torch.float32)
+    rep = eps_rows.shape[0] // x_cur.shape[0]
+    x = (x_cur.repeat(rep, 1, 1, 1) if rep > 1 else x_cur) * 0.9 + 0.1 * (i + 1) * eps_rows
+    s = _true_score(x)
+    if _STUB_NOISE[0]:
+        s = s + _STUB_NOISE[0] * torch.sin(1e4 * x.sum(dim=(1, 2, 3))).to(torch.float32)
+    return x, s
+
+
+class _StubScorer:
+    fused_sums = True
+
+    @staticmethod
+    def score_from_sums(sums, C, HW):
+        return sums
 
 
 def _install_stub_kernels(setattr_):
@@ -338,8 +357,12 @@ def _install_stub_kernels(setattr_):
         def __init__(self, *a):
             pass
 
-        def step(self, x_cur, e, i, want_x_next=True, **kw):
-            return _stub_step(x_cur, e, i)[0], None, None
+        def step(self, x_cur, e, i, want_x_next=True, precise=False, want_sums=False, row_images=None, **kw):
+            if row_images is not None:
+                x_cur = x_cur.index_select(0, row_images)
+            x, s16 = _stub_step(x_cur, e, i)
+            # the "precise engine": the same map without the 16-bit score noise (_StubScorer.score_from_sums is the identity)
+            return (x if want_x_next else None), None, (_true_score(x) if precise else s16) if want_sums else None
 
     setattr_(ops, 'direction_norms', lambda Z: Z.flatten(1).norm(dim=1))
     setattr_(ops, 'make_candidates', lambda pivot, Z, norms, sc, mask, ZF: torch.where(
@@ -455,7 +478,20 @@ def _gloo_search_worker(rank, world, port, q):
                      rec.scored_candidates)
     same = (torch.equal(out['sharded'][0], out['single'][0]) and
             all(torch.equal(a, c) for j in (1, 2, 3) for a, c in zip(out['sharded'][j], out['single'][j])))
-    q.put((rank, same, out['sharded'][4], out['single'][4], [t.tolist() for t in out['single'][1]]))
+    # ---- the same with near-tie escalation: the contender set is a function of the GLOBAL score table (moments and top-M
+    # gathered across the ranks), every rank refines its own contenders, the packed-key reduction runs over refined scores
+    _STUB_NOISE[0] = 4e-3
+    params_e = em.SamplingParams(N=N, K=K, eps=0.0, lambda_param=0.15, scorer=_StubScorer())
+    esc = {}
+    for name, sh in (('sharded', em.Shard(rank, world, None)), ('single', em.Shard())):
+        x, rec = em.eps_greedy_search(_StubPreciseNet(), latents, None, params_e, table, precomputed_noise=pre, record=True,
+                                      scale_table=scales.clone(), shard=sh, escalate=True, kappa=0.5, max_contenders=4)
+        esc[name] = (x, [t.clone() for t in rec.indices], [t.clone() for t in rec.x_steps], sum(rec.escalated))
+    same_e = (torch.equal(esc['sharded'][0], esc['single'][0]) and
+              all(torch.equal(a, c) for j in (1, 2) for a, c in zip(esc['sharded'][j], esc['single'][j])))
+    differs = any(not torch.equal(a, c) for a, c in zip(esc['single'][1], out['single'][1]))
+    q.put((rank, same, out['sharded'][4], out['single'][4], [t.tolist() for t in out['single'][1]],
+           same_e, esc['sharded'][3], esc['single'][3], differs))
     dist.destroy_process_group()
 
 
@@ -463,7 +499,8 @@ def test_sharded_search_loop_gloo_world2_equals_unsharded():
     """8(e) on CPU: the whole eps_greedy / zero_order driver with the candidates sharded over 2 gloo ranks (stub kernels) --
     rank 0's scale table broadcast, per-rank candidate slices, packed-key all_reduce(MAX) with the first-index tie rule
     across shards, winner exchange for the pivot of the next local-search round and for the commit -- gives every rank the
-    indices, pivots and committed states of the unsharded run, bit for bit, while scoring half of the candidates."""
+    indices, pivots and committed states of the unsharded run, bit for bit, while scoring half of the candidates; the same with
+    near-tie escalation on (global contender statistics, each rank refining its own contenders)."""
     import torch.multiprocessing as mp
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
@@ -474,7 +511,79 @@ def test_sharded_search_loop_gloo_world2_equals_unsharded():
     res = [q.get(timeout=180) for _ in procs]
     for p in procs:
         p.join(timeout=60)
-    for rank, same, n_sh, n_one, idx in res:
+    for rank, same, n_sh, n_one, idx, same_e, rows_sh, rows_one, differs in res:
         assert same, rank
         assert n_sh * 2 == n_one == 4 * 2 * 8 * 2
         assert all(5 not in row for row in idx)                # the duplicate on the other shard never beats index 2
+        assert same_e, rank                                    # escalation on: sharded == unsharded as well
+        assert rows_one > 0 and differs                        # ... and it really re-scored contenders and changed winners
+    assert sum(r[6] for r in res) == res[0][7]                 # the ranks' refined rows add up to the unsharded run's
+
+
+class _StubPreciseNet(_StubNet):
+    supports_precise = True
+
+    class precise_engine:
+        @staticmethod
+        def plan(R, b):
+            return None
+
+
+def _escalated_reference(scores, true_scores, kappa, delta, M):
+    """_escalate's contract, written directly: contenders = scores within delta (or kappa x population std) of the best,
+    at most the M best; refined table = true scores on the contenders of images whose best has company, the 16-bit best
+    alone otherwise, -inf elsewhere; first-index argmax."""
+    N, b = scores.shape
+    idx = []
+    for j in range(b):
+        s = scores[:, j]
+        d = delta if delta is not None else kappa * float(s.double().var(unbiased=False).sqrt().to(torch.float32))
+        thr = max(float(s.max()) - d, float(torch.topk(s, min(M, N)).values[-1]))
+        cont = s >= thr
+        ref = torch.full_like(s, float('-inf'))
+        ref[cont] = true_scores[cont, j] if int(cont.sum()) > 1 else s[cont]
+        idx.append(int(ref.argmax()))
+    return idx
+
+
+@pytest.mark.parametrize('kappa,delta,M', [(0.35, None, 8), (None, 5e-3, 3), (2.0, None, 2)])
+def test_escalation_host_logic_with_stub_engines(monkeypatch, kappa, delta, M):
+    """Near-tie escalation (edm/main.py:_escalate) on CPU with stub engines: a '16-bit' score = true score + a
+    candidate-dependent perturbation, a 'precise' engine returning the true score.  Every round's selected index equals a
+    direct statement of the contract (contender threshold from kappa x std or delta, the max_contenders cap, refined
+    scores only where the best has company, first-index argmax), the perturbation really flips some plain argmaxes, and
+    the rows counted as refined are the contenders."""
+    import diffusion_tts_b200.edm.main as em
+    _install_stub_kernels(monkeypatch.setattr)
+    monkeypatch.setitem(_STUB_NOISE, 0, 4e-3)
+    N, steps, b = 12, 6, 2
+    g = torch.Generator().manual_seed(17)
+    latents = torch.randn(b, 3, 8, 8, generator=g)
+    pre = {}
+    for i in range(steps):
+        pre[f'pivot_{i}'] = torch.randn(b, 3, 8, 8, generator=g, dtype=torch.float64)
+        pre[i] = torch.randn(b, 1, N, 3, 8, 8, generator=g, dtype=torch.float64)
+    table = _StubTable(steps, noisy=set(range(steps)))
+    scales = (torch.rand(steps, 1, N, generator=g) * 3).to(torch.float32)
+    params = em.SamplingParams(N=N, K=1, eps=0.0, lambda_param=0.15, scorer=_StubScorer())
+    kw = dict(kappa=kappa) if kappa is not None else dict(delta=delta)
+    x, rec = em.eps_greedy_search(_StubPreciseNet(), latents, None, params, table, precomputed_noise=pre, record=True,
+                                  scale_table=scales, escalate=True, max_contenders=M, **kw)
+    assert len(rec.indices) == steps
+    flips = refined_rows = 0
+    x_cur = latents.to(torch.float64) * table.t_steps[0]
+    for i in range(steps):
+        s16 = rec.scores[i]                                           # [N, b] as scored by the stub 16-bit engine
+        cand = pre[f'pivot_{i}'].repeat(N, 1, 1, 1) + scales[i, 0].repeat_interleave(b).view(-1, 1, 1, 1) * \
+            pre[i][:, 0].transpose(0, 1).reshape(N * b, 3, 8, 8) / pre[i][:, 0].transpose(0, 1).reshape(N * b, -1).norm(dim=1).view(-1, 1, 1, 1)
+        xs, s_chk = _stub_step(x_cur, cand, i)
+        assert torch.equal(s_chk.reshape(N, b), s16)
+        want = _escalated_reference(s16, _true_score(xs).reshape(N, b), kappa, delta, M)
+        assert rec.indices[i].tolist() == want, (i, rec.indices[i].tolist(), want)
+        flips += sum(int(a != c) for a, c in zip(want, s16.argmax(dim=0).tolist()))
+        if rec.refined[i] is not None:
+            refined_rows += int((rec.refined[i] > float('-inf')).sum()) - int(((rec.refined[i] > float('-inf')).sum(0) == 1).sum())
+        x_cur = rec.x_steps[i]
+    assert sum(rec.escalated) == refined_rows and refined_rows > 0
+    assert flips > 0, 'the stub perturbation is sized to flip near ties (3-5 of 12 image-rounds)'
+    assert rec.mispredicted == 0
